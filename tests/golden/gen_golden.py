@@ -1,0 +1,156 @@
+"""Generate the golden fixtures from the UNMODIFIED reference (run in the build container).
+
+    python tests/golden/gen_golden.py
+
+Needs ``/root/reference`` (or ``$CMARL_REFERENCE_DIR``); the GPU box never runs this, it only
+reads the committed ``*.npz``.  The reference has no tests or golden vectors of its own
+(SURVEY.md section 4), so every fixture is produced by executing the reference's real code:
+
+g1_params.npz      ``Actor``/``Critic`` of MME:160-200 built after ``torch.manual_seed`` in the
+                   order of MME:329-339 (MAPPO and IPPO shapes).
+g3_sample.npz      ``Actor.act`` (MME:172-176) under a known generator state + the exponential
+                   noise that state produces (pins "Categorical.sample == argmax(p/q)").
+g4_buffer.npz      ``RolloutBuffer.add/get_batch`` (MME:103-157) on ragged synthetic episodes,
+                   with and without ``normalize_reward``.
+g8_mappo*.npz      one whole iteration of ``mappo_multienvs.py`` executed with ``runpy`` on the
+                   numpy stand-in env (rollout with real worker processes, collate, TD(lambda)
+                   loop MME:484-512, 3 PPO epochs MME:521-603): the batch, returns, advantages,
+                   per-epoch statistics and the updated parameters.  ``_flags`` = all
+                   normalize_* flags on + gradient clipping.
+g8_ippo.npz        the same for ``ippo_multienvs.py``.
+"""
+from __future__ import annotations
+
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent.parent
+sys.path.insert(0, str(REPO))
+
+from oracle import ref_loader  # noqa: E402
+
+
+def flat(module):
+    return torch.cat([p.detach().reshape(-1) for p in module.parameters()]).numpy()
+
+
+def g1(ref, ref_ippo):
+    out = {}
+    for seed in (1, 7):
+        torch.manual_seed(seed)
+        a = ref.Actor(21, 32, 1, 5)
+        c = ref.Critic(54, 64, 1)
+        out[f"mappo_actor_s{seed}"] = flat(a)
+        out[f"mappo_critic_s{seed}"] = flat(c)
+        torch.manual_seed(seed)
+        a = ref_ippo.Actor(21, 32, 1, 5)
+        c = ref_ippo.Critic(21, 32, 1)
+        out[f"ippo_actor_s{seed}"] = flat(a)
+        out[f"ippo_critic_s{seed}"] = flat(c)
+    torch.manual_seed(3)
+    a = ref.Actor(21, 64, 2, 5)
+    c = ref.Critic(54, 128, 2)
+    out["mappo_actor_wide"] = flat(a)
+    out["mappo_critic_wide"] = flat(c)
+    np.savez_compressed(HERE / "g1_params.npz", **out)
+
+
+def g3(ref):
+    torch.manual_seed(11)
+    actor = ref.Actor(21, 32, 1, 5)
+    x = torch.randn(2048, 3, 21)
+    avail = torch.ones(2048, 3, 5, dtype=torch.bool)
+    avail[::7, 1, 3] = False
+    with torch.no_grad():
+        logits = actor.logits(x, avail)
+        torch.manual_seed(99)
+        actions, logp = actor.act(x, avail)
+        torch.manual_seed(99)
+        q = torch.empty(2048 * 3, 5).exponential_(1)
+    np.savez_compressed(HERE / "g3_sample.npz", params=flat(actor), x=x.numpy(), avail=avail.numpy(),
+                        logits=logits.numpy(), q=q.numpy().reshape(2048, 3, 5),
+                        actions=actions.numpy(), logp=logp.numpy())
+
+
+def g4(ref):
+    rng = np.random.default_rng(5)
+    lengths = [25, 7, 25, 1, 13]
+    out = {"lengths": np.array(lengths)}
+    for tag, norm in (("plain", False), ("normr", True)):
+        rb = ref.RolloutBuffer(len(lengths), 3, 21, 54, 5, normalize_reward=norm)
+        eps_np = []
+        for L in lengths:
+            ep = {
+                "obs": [rng.standard_normal((3, 21)) for _ in range(L)],
+                "actions": [torch.from_numpy(rng.integers(0, 5, 3)) for _ in range(L)],
+                "log_prob": [torch.from_numpy(-rng.random(3).astype(np.float32)) for _ in range(L)],
+                "reward": [float(-rng.random() * 4) for _ in range(L)],
+                "states": [rng.standard_normal(54).astype(np.float32) for _ in range(L)],
+                "done": [False] * L,
+                "avail_actions": [rng.integers(0, 2, (3, 5)) for _ in range(L)],
+            }
+            eps_np.append({k: np.stack([np.asarray(v) for v in vals]) for k, vals in ep.items()})
+            rb.add(ep)
+        batch = rb.get_batch()
+        names = ("obs", "actions", "log_probs", "reward", "states", "avail", "done", "mask")
+        for n, t in zip(names, batch):
+            out[f"{tag}_{n}"] = t.numpy()
+        for i, ep in enumerate(eps_np):
+            for k, v in ep.items():
+                out[f"{tag}_ep{i}_{k}"] = v
+    np.savez_compressed(HERE / "g4_buffer.npz", **out)
+
+
+def g8(script, tag, extra, B=6, seed=1):
+    argv = ["--env_type", "pz", "--env_name", "simple_spread_v3", "--batch_size", str(B),
+            "--total_timesteps", str(B * 25), "--eval_steps", "1000000000", "--seed", str(seed)] + extra
+    with tempfile.TemporaryDirectory() as tmp:
+        g = ref_loader.run_script(argv, script=script, cwd=tmp)
+    args = g["args"]
+    out = {
+        "seed": np.array(seed), "B": np.array(B),
+        "gamma": np.array(args.gamma), "td_lambda": np.array(args.td_lambda),
+        "ppo_clip": np.array(args.ppo_clip), "entropy_coef": np.array(args.entropy_coef),
+        "clip_gradients": np.array(args.clip_gradients), "epochs": np.array(args.epochs),
+        "lr_actor": np.array(args.learning_rate_actor), "lr_critic": np.array(args.learning_rate_critic),
+        "normalize_reward": np.array(args.normalize_reward),
+        "normalize_advantage": np.array(args.normalize_advantage),
+        "normalize_return": np.array(args.normalize_return),
+        "actor_hidden_dim": np.array(args.actor_hidden_dim), "critic_hidden_dim": np.array(args.critic_hidden_dim),
+        "obs": g["b_obs"].numpy(), "actions": g["b_actions"].numpy(), "log_probs": g["b_log_probs"].numpy(),
+        "reward": g["b_reward"].numpy(), "states": g["b_states"].numpy(),
+        "avail": g["b_avail_actions"].numpy(), "done": g["b_done"].numpy(), "mask": g["b_mask"].numpy(),
+        "return_lambda": g["return_lambda"].numpy(), "advantages": g["advantages"].numpy(),
+        "actor_final": flat(g["actor"]), "critic_final": flat(g["critic"]),
+        "actor_losses": np.array(g["actor_losses"]), "critic_losses": np.array(g["critic_losses"]),
+        "entropies": np.array(g["entropies_bonuses"]), "kls": np.array(g["kl_divergences"]),
+        "clipfracs": np.array([float(x) for x in g["clipped_ratios"]]),
+        "actor_grad_norms": np.array([float(x) for x in g["actor_gradients"]]),
+        "critic_grad_norms": np.array([float(x) for x in g["critic_gradients"]]),
+        "step": np.array(g["step"]), "training_step": np.array(g["training_step"]),
+    }
+    np.savez_compressed(HERE / f"g8_{tag}.npz", **out)
+    print(tag, "step", g["step"], "actor_losses", g["actor_losses"])
+
+
+def main():
+    if ref_loader.reference_dir() is None:
+        raise SystemExit("reference sources not found")
+    ref = ref_loader.load_module("mappo_multienvs.py")
+    ref_ippo = ref_loader.load_module("ippo_multienvs.py")
+    g1(ref, ref_ippo)
+    g3(ref)
+    g4(ref)
+    g8("mappo_multienvs.py", "mappo", [])
+    g8("mappo_multienvs.py", "mappo_flags",
+       ["--normalize_reward", "--normalize_advantage", "--normalize_return", "--clip_gradients", "0.5"], seed=2)
+    g8("ippo_multienvs.py", "ippo", [], seed=3)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,140 @@
+"""Pin the oracle (oracle/mappo.py) against fixtures produced by the unmodified reference.
+
+CPU only.  Fixtures: tests/golden/*.npz (see tests/golden/gen_golden.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mappo as om
+
+
+def T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def test_g1_param_init_bit_exact(golden):
+    g = golden("g1_params")
+    for seed in (1, 7):
+        a, c = om.build_networks(seed)
+        assert np.array_equal(a.flat_params().numpy(), g[f"mappo_actor_s{seed}"])
+        assert np.array_equal(c.flat_params().numpy(), g[f"mappo_critic_s{seed}"])
+        a, c = om.build_networks(seed, state_dim=21, critic_hidden=32)
+        assert np.array_equal(a.flat_params().numpy(), g[f"ippo_actor_s{seed}"])
+        assert np.array_equal(c.flat_params().numpy(), g[f"ippo_critic_s{seed}"])
+    a, c = om.build_networks(3, actor_hidden=64, actor_layers=2, critic_hidden=128, critic_layers=2)
+    assert np.array_equal(a.flat_params().numpy(), g["mappo_actor_wide"])
+    assert np.array_equal(c.flat_params().numpy(), g["mappo_critic_wide"])
+    assert a.flat_params().numel() == 64 * 21 + 64 + 2 * (64 * 64 + 64) + 5 * 64 + 5
+
+
+def test_g3_categorical_sample_is_exponential_race(golden):
+    g = golden("g3_sample")
+    actor = om.MLP(21, 32, 1, 5)
+    actor.load_flat(T(g["params"]))
+    with torch.no_grad():
+        logits = om.actor_logits(actor, T(g["x"]), T(g["avail"]))
+        assert np.array_equal(logits.numpy(), g["logits"])
+        actions, logp = om.race_sample(logits, T(g["q"]))
+    assert np.array_equal(actions.numpy(), g["actions"])          # bit-exact indices
+    assert np.array_equal(logp.numpy(), g["logp"])
+    # masked actions are never drawn
+    assert not ((~g["avail"]) & (np.eye(5, dtype=bool)[g["actions"]])).any()
+
+
+def _episodes(g, tag, n):
+    eps = []
+    for i in range(n):
+        eps.append({k: list(g[f"{tag}_ep{i}_{k}"]) for k in
+                    ("obs", "actions", "log_prob", "reward", "states", "done", "avail_actions")})
+    return eps
+
+
+@pytest.mark.parametrize("tag,norm", [("plain", False), ("normr", True)])
+def test_g4_buffer_collate_bit_exact(golden, tag, norm):
+    g = golden("g4_buffer")
+    batch = om.collate(_episodes(g, tag, len(g["lengths"])), 3, 21, 54, 5, normalize_reward=norm)
+    names = ("obs", "actions", "log_probs", "reward", "states", "avail", "done", "mask")
+    for n, t in zip(names, batch):
+        ref = g[f"{tag}_{n}"]
+        assert t.numpy().dtype == ref.dtype, n
+        assert np.array_equal(t.numpy(), ref), n
+
+
+def _batch(g):
+    return (T(g["obs"]), T(g["actions"]), T(g["log_probs"]), T(g["reward"]), T(g["states"]),
+            T(g["avail"]), T(g["done"]), T(g["mask"]))
+
+
+@pytest.mark.parametrize("name,ippo", [("g8_mappo", False), ("g8_mappo_flags", False), ("g8_ippo", True)])
+def test_g8_whole_iteration(golden, name, ippo):
+    """TD(lambda) + normalisation + 3 PPO epochs + Adam reproduce the reference run bit for bit."""
+    g = golden(name)
+    seed = int(g["seed"])
+    if ippo:
+        actor, critic = om.build_networks(seed, state_dim=21, critic_hidden=int(g["critic_hidden_dim"]))
+    else:
+        actor, critic = om.build_networks(seed)
+    batch = _batch(g)
+    obs, actions, logp, reward, states, avail, done, mask = batch
+    critic_in = obs if ippo else states
+    gamma, lam = float(g["gamma"]), float(g["td_lambda"])
+    ret, adv = om.td_lambda_loop(critic, critic_in, reward, mask, gamma, lam, 3)
+    # the batched form (used at large sizes) stays within the stated tolerance of the loop form
+    ret_b, adv_b = om.td_lambda_batched(critic, critic_in, reward, mask, gamma, lam, 3)
+    assert (ret_b - ret).abs().max() < 1e-5 and (adv_b - adv).abs().max() < 1e-5
+    if bool(g["normalize_advantage"]):
+        adv = om.normalize_masked(adv, mask)
+    if bool(g["normalize_return"]):
+        ret = om.normalize_masked(ret, mask)
+    assert np.array_equal(ret.numpy(), g["return_lambda"])
+    assert np.array_equal(adv.numpy(), g["advantages"])
+    if not ippo:
+        # MAPPO: the scalar advantage is broadcast to the agents (MME:484-485, 496, 502)
+        assert (adv[..., 0:1] == adv).all()
+
+    aopt, copt = om.make_optimizers(actor, critic, float(g["lr_actor"]), float(g["lr_critic"]))
+    stats = om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=int(g["epochs"]),
+                          clip=float(g["ppo_clip"]), ent_coef=float(g["entropy_coef"]),
+                          clip_gradients=float(g["clip_gradients"]), critic_on_obs=ippo)
+    np.testing.assert_array_equal(np.array(stats["actor_loss"]), g["actor_losses"])
+    np.testing.assert_array_equal(np.array(stats["critic_loss"]), g["critic_losses"])
+    np.testing.assert_array_equal(np.array(stats["entropy"]), g["entropies"])
+    np.testing.assert_array_equal(np.array(stats["kl"]), g["kls"])
+    np.testing.assert_array_equal(np.array(stats["clipfrac"]), g["clipfracs"])
+    np.testing.assert_array_equal(np.array(stats["actor_grad_norm"]), g["actor_grad_norms"])
+    np.testing.assert_array_equal(np.array(stats["critic_grad_norm"]), g["critic_grad_norms"])
+    assert np.array_equal(actor.flat_params().numpy(), g["actor_final"])
+    assert np.array_equal(critic.flat_params().numpy(), g["critic_final"])
+
+
+def test_flat_epoch_matches_loop_epoch(golden):
+    g = golden("g8_mappo")
+    actor, critic = om.build_networks(int(g["seed"]))
+    obs, actions, logp, reward, states, avail, done, mask = _batch(g)
+    adv, ret = T(g["advantages"]), T(g["return_lambda"])
+    outs = []
+    for fn in (om.ppo_epoch_loop, om.ppo_epoch_flat):
+        actor.zero_grad(); critic.zero_grad()
+        o = fn(actor, critic, obs, actions, logp, states, avail, mask, adv, ret, 0.2, 0.001)
+        o.actor_loss.backward(); o.critic_loss.backward()
+        outs.append((o, actor.flat_grads().clone(), critic.flat_grads().clone()))
+    (a, ga, gc), (b, gb, gd) = outs
+    assert abs(a.actor_loss.item() - b.actor_loss.item()) < 1e-5 * abs(a.actor_loss.item())
+    assert abs(a.critic_loss.item() - b.critic_loss.item()) < 1e-5 * abs(a.critic_loss.item())
+    assert (ga - gb).abs().max() <= 1e-5 * ga.abs().max()
+    assert (gc - gd).abs().max() <= 1e-5 * gc.abs().max()
+
+
+def test_scan_matches_loop_bit_exact_given_values(golden):
+    """td_lambda_scan is the bit-exact target of the CUDA scan: same fp32 op order as MME:496-504."""
+    g = golden("g8_mappo")
+    actor, critic = om.build_networks(int(g["seed"]))
+    obs, actions, logp, reward, states, avail, done, mask = _batch(g)
+    B, Tn = reward.shape
+    # batch-of-1 critic values, exactly what the loop sees
+    with torch.no_grad():
+        v = torch.stack([torch.stack([critic(states[b, t]) for t in range(Tn)]) for b in range(B)])
+    ret, adv = om.td_lambda_scan(v.expand(B, Tn, 3), reward, mask, float(g["gamma"]), float(g["td_lambda"]))
+    assert np.array_equal(ret.numpy(), g["return_lambda"])
+    assert np.array_equal(adv.numpy(), g["advantages"])
