@@ -1,0 +1,474 @@
+// K4 (batched critic forward) and K7 (PPO epoch: fused forward + backward of actor and critic).
+// See chain.cuh for the tile pipeline.  Reference arithmetic: MME:527-582 (loss), MME:178-200 (nets).
+#include "chain.cuh"
+
+namespace chain {
+
+// ------------------------------------------------------------------------------------------------
+// Heads: what happens to the network output z of one sample
+// ------------------------------------------------------------------------------------------------
+struct PolicyHead {
+    static constexpr int OUT = 5;
+    static constexpr int NSTAT = 5;     // loss, entropy, kl, clip fraction, valid samples
+    using Args = PolicyHeadArgs;
+    // MME:530-551, 561-570 for one (b, t, agent) sample; all sums carry the 1/N of `.mean(dim=-1)`.
+    __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
+                                                 bool inb, bool train, float (&dz)[OUT], float (&st)[NSTAT]) {
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) dz[a] = 0.0f;
+        if (!inb) return;
+        const size_t tb = (size_t)t * B + b;
+        if (h.mask && !h.mask[tb]) return;
+        const size_t tgb = ((size_t)t * G + g) * B + b;
+        if (h.avail) {
+#pragma unroll
+            for (int a = 0; a < OUT; ++a)
+                if (!h.avail[(((size_t)t * G + g) * h.A + a) * B + b]) z[a] = -1e9f;   // masked_fill, MME:182
+        }
+        // Categorical(logits=z): logits = z - logsumexp(z); probs = softmax(logits)
+        float mx = z[0];
+#pragma unroll
+        for (int a = 1; a < OUT; ++a) mx = fmaxf(mx, z[a]);
+        float se = 0.0f;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) se += expf(z[a] - mx);
+        const float lse = mx + logf(se);
+        float l[OUT], p[OUT];
+        float mx2 = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) { l[a] = z[a] - lse; mx2 = fmaxf(mx2, l[a]); }
+        float se2 = 0.0f;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) { p[a] = expf(l[a] - mx2); se2 += p[a]; }
+        float ent = 0.0f;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) { p[a] = p[a] / se2; ent -= l[a] * p[a]; }
+        const int act = h.actions[tgb];
+        float logp = l[0];
+#pragma unroll
+        for (int a = 1; a < OUT; ++a) logp = (act == a) ? l[a] : logp;
+        const float log_ratio = logp - h.logp_old[tgb];
+        const float ratio = expf(log_ratio);
+        const float A = h.adv[h.V == 1 ? tb : tgb];
+        const float lo = 1.0f - h.clip, hi = 1.0f + h.clip;
+        const float pg1 = A * ratio;
+        const float pg2 = A * fminf(fmaxf(ratio, lo), hi);
+        const float pg = fminf(pg1, pg2);
+        const float w = h.inv_groups;
+        st[0] += w * (-pg - h.ent_coef * ent);
+        st[1] += w * ent;
+        st[2] += w * ((ratio - 1.0f) - log_ratio);
+        st[3] += (fabsf(ratio - 1.0f) > h.clip) ? w : 0.0f;
+        st[4] += 1.0f;
+        if (!train) return;
+        // d(-min(pg1,pg2))/d(ratio): clamp passes the gradient inside [lo,hi] (ties of torch.min split
+        // 1/2 + 1/2 and recombine); outside, only the unclipped branch carries one.
+        const bool inside = (ratio >= lo) && (ratio <= hi);
+        const float dmin = (inside || pg1 < pg2) ? A : ((pg1 == pg2) ? 0.5f * A : 0.0f);
+        const float dlogp = -w * dmin * ratio;
+        const float we = w * h.ent_coef;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) {
+            const float onehot = (act == a) ? 1.0f : 0.0f;
+            dz[a] = dlogp * (onehot - p[a]) + we * p[a] * (l[a] + ent);
+        }
+        if (h.avail) {
+#pragma unroll
+            for (int a = 0; a < OUT; ++a)
+                if (!h.avail[(((size_t)t * G + g) * h.A + a) * B + b]) dz[a] = 0.0f;
+        }
+    }
+};
+
+struct ValueHead {
+    static constexpr int OUT = 1;
+    static constexpr int NSTAT = 2;     // loss, valid samples
+    using Args = ValueHeadArgs;
+    // MME:554-558: sum_env mean_agent (V - R)^2 ; forward-only mode just stores V (MME:495,502).
+    __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
+                                                 bool inb, bool train, float (&dz)[OUT], float (&st)[NSTAT]) {
+        dz[0] = 0.0f;
+        if (!inb) return;
+        const size_t tgb = ((size_t)t * G + g) * B + b;
+        if (!train) {
+            h.values_out[tgb] = z[0];
+            return;
+        }
+        if (h.mask && !h.mask[(size_t)t * B + b]) return;
+        const float diff = z[0] - h.returns[tgb];
+        st[0] += h.inv_heads * diff * diff;
+        st[1] += 1.0f;
+        dz[0] = h.inv_heads * 2.0f * diff;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+template <class C, class Head, bool TRAIN>
+__global__ void __launch_bounds__(C::NT, 1)
+chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict__ partials, int p_net) {
+    extern __shared__ __align__(128) float sm[];
+    constexpr int H = C::H, M = C::M, LD = C::LD, NT = C::NT, OUT = Head::OUT;
+    static_assert(M == NT, "S3/S5 are thread-per-sample");
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::oBar);
+    const int tid = threadIdx.x;
+    const int tiles_b = (src.B + M - 1) / M;
+    const int units = src.T * src.G * tiles_b;
+
+    load_weights<C>(sm, nd, src.G);
+    for (int i = tid; i < 2 * C::KIN * LD; i += NT) sm[C::oX + i] = 0.0f;      // pad rows stay zero
+    if (TRAIN)
+        for (int i = tid; i < C::PMAX; i += NT) sm[C::oDW + i] = 0.0f;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // gradient accumulators in the torch parameter order of this net
+    float* dW1 = sm + C::oDW;
+    float* db1 = dW1 + H * nd.in_dim;
+    float* dW2 = db1 + H;
+    float* db2 = dW2 + H * H;
+    float* dW3 = db2 + H;
+    float* db3 = dW3 + nd.out_dim * H;
+    float* scr_patch = sm + C::oScr;
+    float* scr_w3 = sm + C::oScr + C::SCR_PATCH;
+    const int kin_pad = ((nd.in_rows + C::PT - 1) / C::PT) * C::PT;
+
+    float st[Head::NSTAT];
+#pragma unroll
+    for (int k = 0; k < Head::NSTAT; ++k) st[k] = 0.0f;
+
+    int u = blockIdx.x;
+    if (u < units) {
+        const int bt = u % tiles_b, r = u / tiles_b;
+        issue_tile<C>(sm + C::oX, &bars[0], src, nd.in_rows, r / src.G, r % src.G, bt * M);
+    }
+    __syncthreads();
+    for (int it = 0; u < units; u += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const int un = u + gridDim.x;
+        if (un < units) {
+            const int bt = un % tiles_b, r = un / tiles_b;
+            issue_tile<C>(sm + C::oX + (cur ^ 1) * C::KIN * LD, &bars[cur ^ 1], src, nd.in_rows, r / src.G, r % src.G,
+                          bt * M);
+        }
+        const int bt = u % tiles_b, r = u / tiles_b;
+        const int t = r / src.G, g = r % src.G, b0 = bt * M;
+        float* X = sm + C::oX + cur * C::KIN * LD;
+        float* H1 = sm + C::oH1;
+        float* H2 = sm + C::oH2;
+        float* Z = sm + C::oZ;
+        mbar_wait(&bars[cur], (it >> 1) & 1);
+
+        // S1, S2: hidden layers
+        gemm_rows<C, H, false>(X, nd.in_rows, sm + C::oW1T, sm + C::oB1 + g * H, H1);
+        __syncthreads();
+        gemm_rows<C, H, false>(H1, H, sm + C::oW2T, sm + C::oB2, H2);
+        __syncthreads();
+
+        // S3: output layer + head, one thread per sample
+        const int s = tid;
+        float z[OUT], dz[OUT];
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) z[a] = sm[C::oB3 + a];
+#pragma unroll 4
+        for (int j = 0; j < H; ++j) {
+            const float h = H2[j * LD + s];
+            if (OUT > 1) {
+                const float4 w = *reinterpret_cast<const float4*>(sm + C::oW3T + j * OUTP);
+                const float w4 = sm[C::oW3T + j * OUTP + 4];
+                z[0] = fmaf(w.x, h, z[0]);
+                if (OUT > 1) z[OUT > 1 ? 1 : 0] = fmaf(w.y, h, z[OUT > 1 ? 1 : 0]);
+                if (OUT > 2) z[OUT > 2 ? 2 : 0] = fmaf(w.z, h, z[OUT > 2 ? 2 : 0]);
+                if (OUT > 3) z[OUT > 3 ? 3 : 0] = fmaf(w.w, h, z[OUT > 3 ? 3 : 0]);
+                if (OUT > 4) z[OUT > 4 ? 4 : 0] = fmaf(w4, h, z[OUT > 4 ? 4 : 0]);
+            } else {
+                z[0] = fmaf(sm[C::oW3T + j * OUTP], h, z[0]);
+            }
+        }
+        Head::apply(ha, z, t, g, b0 + s, src.G, src.B, (b0 + s) < src.B, TRAIN, dz, st);
+
+        if (TRAIN) {
+#pragma unroll
+            for (int a = 0; a < OUT; ++a) Z[a * LD + s] = dz[a];
+            __syncthreads();
+
+            // S4: dW3 += dz H2^T (split over samples, fixed-order combine), db3
+            {
+                constexpr int NS = NT / H;                 // sample splits
+                constexpr int NQ = M / 4;
+                const int j = tid % H, q = tid / H;
+                float acc[OUT];
+#pragma unroll
+                for (int a = 0; a < OUT; ++a) acc[a] = 0.0f;
+                for (int c = q; c < NQ; c += NS) {
+                    const float4 h4 = *reinterpret_cast<const float4*>(H2 + j * LD + 4 * c);
+#pragma unroll
+                    for (int a = 0; a < OUT; ++a) {
+                        const float4 d4 = *reinterpret_cast<const float4*>(Z + a * LD + 4 * c);
+                        acc[a] = fmaf(d4.x, h4.x, acc[a]); acc[a] = fmaf(d4.y, h4.y, acc[a]);
+                        acc[a] = fmaf(d4.z, h4.z, acc[a]); acc[a] = fmaf(d4.w, h4.w, acc[a]);
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < OUT; ++a) scr_w3[(q * OUTP + a) * H + j] = acc[a];
+                __syncthreads();
+                for (int i = tid; i < OUT * H; i += NT) {
+                    const int a = i / H, jj = i - a * H;
+                    float v = 0.0f;
+#pragma unroll
+                    for (int qq = 0; qq < NS; ++qq) v += scr_w3[(qq * OUTP + a) * H + jj];
+                    dW3[a * H + jj] += v;
+                }
+                if (tid < OUT) {
+                    float v = 0.0f;
+                    for (int c = 0; c < NQ; ++c) {
+                        const float4 d4 = *reinterpret_cast<const float4*>(Z + tid * LD + 4 * c);
+                        v += (d4.x + d4.y) + (d4.z + d4.w);
+                    }
+                    db3[tid] += v;
+                }
+            }
+            __syncthreads();
+
+            // S5: dH2 = (W3^T dz) . relu'(H2), in place (dz still in this thread's registers)
+#pragma unroll 4
+            for (int j = 0; j < H; ++j) {
+                float acc = 0.0f;
+                if (OUT > 1) {
+                    const float4 w = *reinterpret_cast<const float4*>(sm + C::oW3T + j * OUTP);
+                    const float w4 = sm[C::oW3T + j * OUTP + 4];
+                    acc = w.x * dz[0];
+                    acc = fmaf(w.y, dz[OUT > 1 ? 1 : 0], acc);
+                    acc = fmaf(w.z, dz[OUT > 2 ? 2 : 0], acc);
+                    acc = fmaf(w.w, dz[OUT > 3 ? 3 : 0], acc);
+                    acc = fmaf(w4, dz[OUT > 4 ? 4 : 0], acc);
+                } else {
+                    acc = sm[C::oW3T + j * OUTP] * dz[0];
+                }
+                const float h = H2[j * LD + s];
+                H2[j * LD + s] = h > 0.0f ? acc : 0.0f;
+            }
+            __syncthreads();
+
+            // S6: dW2 += dH2 H1^T, db2
+            dw_stage<C>(H2, H1, H, H, H, dW2, db2, nullptr, scr_patch);
+            __syncthreads();
+            // S7: dH1 = (W2^T dH2) . relu'(H1), in place
+            gemm_rows<C, H, true>(H2, H, sm + C::oW2, nullptr, H1);
+            __syncthreads();
+            // S8: dW1 += dH1 x^T, db1 (+ folded id column of this agent)
+            dw_stage<C>(H1, X, kin_pad, nd.in_rows, nd.in_dim, dW1, db1,
+                        nd.fold_ids ? dW1 + nd.in_rows + g : nullptr, scr_patch);
+        }
+        __syncthreads();
+    }
+
+    if (TRAIN) {
+        float* out = partials + (size_t)blockIdx.x * (p_net + CMARL_N_STATS);
+        for (int i = tid; i < p_net; i += NT) out[i] = sm[C::oDW + i];
+        float* red = sm + C::oRed;
+#pragma unroll
+        for (int k = 0; k < Head::NSTAT; ++k) {
+            const float v = warp_sum_f(st[k]);
+            __syncthreads();
+            if ((tid & 31) == 0) red[tid >> 5] = v;
+            __syncthreads();
+            if (tid == 0) {
+                float a = 0.0f;
+                for (int w = 0; w < NT / 32; ++w) a += red[w];
+                out[p_net + k] = a;
+            }
+        }
+        if (tid == 0)
+            for (int k = Head::NSTAT; k < CMARL_N_STATS; ++k) out[p_net + k] = 0.0f;
+    }
+}
+
+// Fixed-order sum of the per-CTA partials -> flat gradient vector + statistics (deterministic).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ pa, int grid_a, int Pa,
+                                                              const float* __restrict__ pc, int grid_c, int Pc,
+                                                              float n_groups, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = Pa + Pc;
+    if (i >= P + CMARL_N_STATS) return;
+    const float* src;
+    int n, stride, col;
+    float scale = 1.0f;
+    if (i < Pa) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = i; }
+    else if (i < P) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = i - Pa; }
+    else {
+        const int k = i - P;   // out stats: 0 actor loss 1 critic loss 2 entropy 3 kl 4 clipfrac 5 n_valid(b,t)
+        if (k == 0) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = Pa + 0; }
+        else if (k == 1) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = Pc + 0; }
+        else if (k <= 4) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = Pa + (k - 1); }
+        else if (k == 5) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = Pa + 4; scale = 1.0f / n_groups; }
+        else { out[i] = 0.0f; return; }
+    }
+    if (i == P + 5) {      // the sample count can exceed 2^24: sum it in double
+        double d = 0.0;
+        for (int c = 0; c < n; ++c) d += (double)src[(size_t)c * stride + col];
+        out[i] = (float)(d / (double)n_groups);
+        return;
+    }
+    float a = 0.0f;
+    for (int c = 0; c < n; ++c) a += src[(size_t)c * stride + col];
+    out[i] = a * scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+template <class C, class Head, bool TRAIN>
+static int set_attr() {
+    const size_t smem = TRAIN ? C::smem_train : C::smem_fwd;
+    return cmarl_check_cuda(cudaFuncSetAttribute(chain_kernel<C, Head, TRAIN>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(chain_kernel)");
+}
+
+template <class C, class Head, bool TRAIN>
+static int launch(const cmarl_ctx* ctx, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha,
+                  float* partials, int p_net, int grid, cudaStream_t st) {
+    const size_t smem = TRAIN ? C::smem_train : C::smem_fwd;
+    chain_kernel<C, Head, TRAIN><<<grid, C::NT, smem, st>>>(nd, src, ha, partials, p_net);
+    return cmarl_check_cuda(cudaGetLastError(), "chain_kernel launch");
+}
+
+static int tile_m(int H, int kin) { return (H == 32 && kin == 24) ? 256 : 128; }
+
+static int units_of(const TileSrc& s, int M) { return s.T * s.G * ceil_div(s.B, M); }
+
+template <class Head, bool TRAIN>
+static int dispatch(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileSrc& src,
+                    const typename Head::Args& ha, float* partials, int p_net, int grid, cudaStream_t st) {
+    const int kin = nd.in_rows <= 24 ? 24 : 56;
+    if (H == 32 && kin == 24) return launch<Cfg<32, 24>, Head, TRAIN>(ctx, nd, src, ha, partials, p_net, grid, st);
+    if (H == 32 && kin == 56) return launch<Cfg<32, 56>, Head, TRAIN>(ctx, nd, src, ha, partials, p_net, grid, st);
+    if (H == 64 && kin == 24) return launch<Cfg<64, 24>, Head, TRAIN>(ctx, nd, src, ha, partials, p_net, grid, st);
+    if (H == 64 && kin == 56) return launch<Cfg<64, 56>, Head, TRAIN>(ctx, nd, src, ha, partials, p_net, grid, st);
+    cmarl_set_error("chain dispatch: unsupported hidden=%d in_rows=%d", H, nd.in_rows);
+    return -1;
+}
+
+static void actor_desc(const cmarl_ctx* ctx, const float* params, const float* state, const float* obs,
+                       NetDesc& nd, TileSrc& src) {
+    const cmarl_config& c = ctx->cfg;
+    nd.params = params;
+    nd.in_dim = c.obs_dim;
+    nd.out_dim = c.n_actions;
+    src.T = c.n_steps; src.G = c.n_agents; src.B = c.n_envs;
+    if (obs) {
+        nd.in_rows = c.obs_dim; nd.fold_ids = 0;
+        src.x = obs; src.stride_t = (size_t)c.n_agents * c.obs_dim * c.n_envs; src.stride_g = (size_t)c.obs_dim * c.n_envs;
+    } else {
+        nd.in_rows = CMARL_RAW_OBS; nd.fold_ids = c.obs_dim > CMARL_RAW_OBS;
+        src.x = state; src.stride_t = (size_t)c.state_dim * c.n_envs; src.stride_g = (size_t)CMARL_RAW_OBS * c.n_envs;
+    }
+}
+
+static void critic_desc(const cmarl_ctx* ctx, const float* params, const float* state, const float* obs,
+                        NetDesc& nd, TileSrc& src) {
+    const cmarl_config& c = ctx->cfg;
+    if (c.critic_on_obs) {
+        actor_desc(ctx, params, state, obs, nd, src);
+        nd.out_dim = 1;
+        return;
+    }
+    nd.params = params;
+    nd.in_rows = c.state_dim; nd.in_dim = c.state_dim; nd.fold_ids = 0; nd.out_dim = 1;
+    src.x = state; src.T = c.n_steps; src.G = 1; src.B = c.n_envs;
+    src.stride_t = (size_t)c.state_dim * c.n_envs; src.stride_g = 0;
+}
+
+}  // namespace chain
+
+using namespace chain;
+
+int cmarl_chain_setup(cmarl_ctx* ctx) {
+    int e = 0;
+#define SET(Hh, Kk)                                                        \
+    if (!e) e = set_attr<Cfg<Hh, Kk>, PolicyHead, true>();                 \
+    if (!e) e = set_attr<Cfg<Hh, Kk>, ValueHead, true>();                  \
+    if (!e) e = set_attr<Cfg<Hh, Kk>, ValueHead, false>();
+    SET(32, 24) SET(32, 56) SET(64, 24) SET(64, 56)
+#undef SET
+    if (e) return e;
+    const cmarl_config& c = ctx->cfg;
+    NetDesc nd; TileSrc src;
+    actor_desc(ctx, nullptr, nullptr, nullptr, nd, src);
+    int ua = units_of(src, tile_m(c.actor_hidden, 24));
+    critic_desc(ctx, nullptr, nullptr, nullptr, nd, src);
+    int uc = units_of(src, tile_m(c.critic_hidden, nd.in_rows <= 24 ? 24 : 56));
+    ctx->ppo_grid_actor = ua < ctx->sm_count ? ua : ctx->sm_count;
+    ctx->ppo_grid_critic = uc < ctx->sm_count ? uc : ctx->sm_count;
+    return 0;
+}
+
+extern "C" size_t cmarl_workspace_bytes(const cmarl_ctx* ctx) {
+    if (!ctx) return 0;
+    // the actor grid may be larger when obs is passed explicitly (21 rows still use the 24-row config)
+    const size_t a = (size_t)ctx->sm_count * (ctx->actor.count + CMARL_N_STATS);
+    const size_t c = (size_t)ctx->sm_count * (ctx->critic.count + CMARL_N_STATS);
+    return (a + c) * sizeof(float);
+}
+
+extern "C" int cmarl_critic_values(cmarl_ctx* ctx, const float* critic_params, const float* state, const float* obs,
+                                   float* values, void* stream) {
+    CMARL_ARG(ctx && critic_params && values, "null argument");
+    CMARL_ARG(ctx->cfg.critic_on_obs ? (state || obs) : (state != nullptr), "critic input missing");
+    NetDesc nd; TileSrc src;
+    critic_desc(ctx, critic_params, state, obs, nd, src);
+    ValueHeadArgs ha;
+    ha.returns = nullptr; ha.mask = nullptr; ha.values_out = values; ha.inv_heads = 1.0f / (float)ctx->n_heads;
+    const int kin = nd.in_rows <= 24 ? 24 : 56;
+    const int units = units_of(src, tile_m(ctx->cfg.critic_hidden, kin));
+    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    ctx->launches++;
+    return dispatch<ValueHead, false>(ctx, ctx->cfg.critic_hidden, nd, src, ha, nullptr, 0, grid, as_stream(stream));
+}
+
+extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const float* state, const float* obs,
+                                     const int32_t* actions, const float* logp_old, const float* adv,
+                                     const float* returns, const uint8_t* mask, const uint8_t* avail,
+                                     double clip, double ent_coef, float* grads_out, void* workspace, void* stream) {
+    CMARL_ARG(ctx && params && actions && logp_old && adv && returns && grads_out && workspace, "null argument");
+    CMARL_ARG(state || obs, "state or obs required");
+    CMARL_ARG(ctx->cfg.critic_on_obs || state, "MAPPO critic needs state");
+    const cmarl_config& c = ctx->cfg;
+    cudaStream_t st = as_stream(stream);
+    const int Pa = ctx->actor.count, Pc = ctx->critic.count;
+    float* part_a = reinterpret_cast<float*>(workspace);
+    float* part_c = part_a + (size_t)ctx->sm_count * (Pa + CMARL_N_STATS);
+
+    NetDesc nda; TileSrc srca;
+    actor_desc(ctx, params, state, obs, nda, srca);
+    PolicyHeadArgs pa;
+    pa.actions = actions; pa.logp_old = logp_old; pa.adv = adv; pa.mask = mask; pa.avail = avail;
+    pa.V = ctx->n_heads; pa.A = c.n_actions;
+    pa.clip = (float)clip; pa.ent_coef = (float)ent_coef; pa.inv_groups = 1.0f / (float)c.n_agents;
+    const int ua = units_of(srca, tile_m(c.actor_hidden, 24));
+    const int grid_a = ua < ctx->sm_count ? ua : ctx->sm_count;
+    int e = dispatch<PolicyHead, true>(ctx, c.actor_hidden, nda, srca, pa, part_a, Pa, grid_a, st);
+    if (e) return e;
+
+    NetDesc ndc; TileSrc srcc;
+    critic_desc(ctx, params + Pa, state, obs, ndc, srcc);
+    ValueHeadArgs va;
+    va.returns = returns; va.mask = mask; va.values_out = nullptr; va.inv_heads = 1.0f / (float)ctx->n_heads;
+    const int kin = ndc.in_rows <= 24 ? 24 : 56;
+    const int uc = units_of(srcc, tile_m(c.critic_hidden, kin));
+    const int grid_c = uc < ctx->sm_count ? uc : ctx->sm_count;
+    e = dispatch<ValueHead, true>(ctx, c.critic_hidden, ndc, srcc, va, part_c, Pc, grid_c, st);
+    if (e) return e;
+
+    const int n_out = Pa + Pc + CMARL_N_STATS;
+    reduce_partials_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(part_a, grid_a, Pa, part_c, grid_c, Pc,
+                                                                 (float)c.n_agents, grads_out);
+    ctx->launches += 3;
+    return cmarl_check_cuda(cudaGetLastError(), "reduce_partials_kernel");
+}

@@ -1,0 +1,96 @@
+// Shared host/device helpers for libcmarl_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cmarl_b200.h"
+
+#define CMARL_MAX_AGENTS 8
+#define CMARL_MAX_ACTIONS 8
+
+// Offsets of one 2-hidden-layer MLP inside the flat parameter vector (torch parameters() order).
+struct NetLayout {
+    int in, hid, out;
+    int w1, b1, w2, b2, w3, b3, count;
+    __host__ __device__ void set(int in_, int hid_, int out_) {
+        in = in_; hid = hid_; out = out_;
+        w1 = 0;
+        b1 = w1 + hid * in;
+        w2 = b1 + hid;
+        b2 = w2 + hid * hid;
+        w3 = b2 + hid;
+        b3 = w3 + out * hid;
+        count = b3 + out;
+    }
+};
+
+struct cmarl_ctx {
+    cmarl_config cfg;
+    NetLayout actor, critic;
+    int n_heads;        // V
+    int critic_in;      // S (MAPPO) or O (IPPO)
+    int sm_count;
+    int ppo_grid_actor, ppo_grid_critic;
+    int launches;
+};
+
+void cmarl_set_error(const char* fmt, ...);
+int cmarl_check_cuda(cudaError_t e, const char* what);
+
+#define CMARL_CUDA(call)                                         \
+    do {                                                         \
+        int _e = cmarl_check_cuda((call), #call);                \
+        if (_e) return _e;                                       \
+    } while (0)
+
+#define CMARL_ARG(cond, msg)                                     \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            cmarl_set_error("%s: %s", __func__, msg);            \
+            return -1;                                           \
+        }                                                        \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011) -- counter-based, so a draw is a pure function of
+// (seed, episode, t, agent-row, lane) and shards/replays reproduce it.
+// ------------------------------------------------------------------------------------------
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ inline void philox_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+}
+
+__host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        philox_mulhilo(M0, c0, hi0, lo0);
+        philox_mulhilo(M1, c2, hi1, lo1);
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// uniform in (0,1]: never 0 so -log(u) is finite
+__host__ __device__ inline float u32_to_unit_open0(uint32_t v) { return ((float)(v >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+// uniform double in [0,1) from 53 random bits
+__host__ __device__ inline double u64_to_unit(uint32_t hi, uint32_t lo) {
+    uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+    return (double)v * (1.0 / 9007199254740992.0);
+}

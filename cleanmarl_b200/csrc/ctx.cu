@@ -1,0 +1,74 @@
+// Context, error reporting and configuration validation of libcmarl_b200.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void cmarl_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cmarl_check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    cmarl_set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+
+int cmarl_chain_setup(cmarl_ctx* ctx);   // chain.cu: shared-memory attributes + grid sizes
+
+extern "C" int cmarl_version(void) { return CMARL_VERSION; }
+extern "C" const char* cmarl_last_error(void) { return g_err; }
+
+extern "C" int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out) {
+    CMARL_ARG(cfg && out, "null argument");
+    *out = nullptr;
+    CMARL_ARG(cfg->n_envs >= 1 && cfg->n_steps >= 1, "n_envs and n_steps must be positive");
+    CMARL_ARG(cfg->n_agents == 3, "simple_spread_v3 has 3 agents (only N=3 is built)");
+    CMARL_ARG(cfg->n_actions == 5, "simple_spread_v3 has 5 discrete actions (only A=5 is built)");
+    CMARL_ARG(cfg->state_dim == cfg->n_agents * CMARL_RAW_OBS, "state_dim must be n_agents*18");
+    CMARL_ARG(cfg->obs_dim == CMARL_RAW_OBS || cfg->obs_dim == CMARL_RAW_OBS + cfg->n_agents,
+              "obs_dim must be 18 (no ids) or 18+n_agents (agent ids)");
+    CMARL_ARG(cfg->actor_layers == 1 && cfg->critic_layers == 1,
+              "only *_num_layers == 1 (the reference default) is built");
+    CMARL_ARG(cfg->actor_hidden == 32 || cfg->actor_hidden == 64, "actor_hidden_dim must be 32 or 64");
+    CMARL_ARG(cfg->critic_hidden == 32 || cfg->critic_hidden == 64, "critic_hidden_dim must be 32 or 64");
+    CMARL_ARG(cfg->critic_on_obs == 0 || cfg->critic_on_obs == 1, "critic_on_obs must be 0 or 1");
+    int ndev = 0;
+    CMARL_CUDA(cudaGetDeviceCount(&ndev));
+    CMARL_ARG(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device (there is no CPU fallback)");
+    CMARL_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CMARL_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        cmarl_set_error("cmarl_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                        cfg->device, prop.major, prop.minor);
+        return -2;
+    }
+    cmarl_ctx* ctx = (cmarl_ctx*)calloc(1, sizeof(cmarl_ctx));
+    CMARL_ARG(ctx, "out of host memory");
+    ctx->cfg = *cfg;
+    ctx->n_heads = cfg->critic_on_obs ? cfg->n_agents : 1;
+    ctx->critic_in = cfg->critic_on_obs ? cfg->obs_dim : cfg->state_dim;
+    ctx->actor.set(cfg->obs_dim, cfg->actor_hidden, cfg->n_actions);
+    ctx->critic.set(ctx->critic_in, cfg->critic_hidden, 1);
+    ctx->sm_count = prop.multiProcessorCount;
+    int e = cmarl_chain_setup(ctx);
+    if (e) { free(ctx); return e; }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int cmarl_ctx_destroy(cmarl_ctx* ctx) {
+    free(ctx);
+    return 0;
+}
+
+extern "C" int cmarl_actor_param_count(const cmarl_ctx* ctx) { return ctx ? ctx->actor.count : -1; }
+extern "C" int cmarl_critic_param_count(const cmarl_ctx* ctx) { return ctx ? ctx->critic.count : -1; }
+extern "C" int cmarl_value_heads(const cmarl_ctx* ctx) { return ctx ? ctx->n_heads : -1; }
+extern "C" int cmarl_launch_count(const cmarl_ctx* ctx) { return ctx ? ctx->launches : -1; }

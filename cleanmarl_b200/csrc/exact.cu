@@ -1,0 +1,286 @@
+// K5 TD(lambda) scan, K6 normalisation, K8 clip + Adam.
+// Compiled with -fmad=false: these kernels reproduce the reference's fp32 operation order
+// (separate ATen ops => separately rounded mul/add), FMA only where ATen itself fuses (lerp).
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------- K5
+// One thread per (value head v, env b); sequential in t (the recurrence is order-sensitive in
+// fp32: SURVEY.md 0.4), parallel and coalesced over b.  Algorithmic traffic: r 4 B + V 4 B in,
+// R 4 B + A 4 B out per (t, v, b) -- 16 B per env-step for MAPPO (V = 1).
+template <int UNROLL>
+__global__ void __launch_bounds__(256) td_lambda_kernel(const float* __restrict__ values,
+                                                        const float* __restrict__ reward,
+                                                        const uint8_t* __restrict__ mask,
+                                                        float* __restrict__ returns,
+                                                        float* __restrict__ adv,
+                                                        int T, int V, int B, float g, float l, float oml) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= V * B) return;
+    const int v = idx / B, b = idx - v * B;
+    const size_t strideT = (size_t)V * B;
+    const float* vp = values + (size_t)v * B + b;
+    float* rp = returns + (size_t)v * B + b;
+    float* ap = adv + (size_t)v * B + b;
+    float last = 0.0f, vnext = 0.0f;
+    bool next_live = false;
+    int t = T - 1;
+    // main part: UNROLL steps at a time, all loads of a chunk issued before the dependent chain
+    for (; t >= UNROLL - 1; t -= UNROLL) {
+        float vv[UNROLL], rr[UNROLL];
+        uint8_t mm[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int tt = t - u;
+            vv[u] = __ldg(vp + (size_t)tt * strideT);
+            rr[u] = __ldg(reward + (size_t)tt * B + b);
+            mm[u] = mask ? __ldg(mask + (size_t)tt * B + b) : (uint8_t)1;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int tt = t - u;
+            const bool live = mm[u] != 0;
+            float R = 0.0f, A = 0.0f;
+            if (live) {
+                const float nv = next_live ? vnext : 0.0f;
+                R = rr[u] + g * (l * last + oml * nv);
+                A = R - vv[u];
+                last = R;
+            }
+            __stcs(rp + (size_t)tt * strideT, R);
+            __stcs(ap + (size_t)tt * strideT, A);
+            next_live = live;
+            vnext = vv[u];
+        }
+    }
+    for (; t >= 0; --t) {
+        const float vt = __ldg(vp + (size_t)t * strideT);
+        const float rt = __ldg(reward + (size_t)t * B + b);
+        const bool live = mask ? (__ldg(mask + (size_t)t * B + b) != 0) : true;
+        float R = 0.0f, A = 0.0f;
+        if (live) {
+            const float nv = next_live ? vnext : 0.0f;
+            R = rt + g * (l * last + oml * nv);
+            A = R - vt;
+            last = R;
+        }
+        __stcs(rp + (size_t)t * strideT, R);
+        __stcs(ap + (size_t)t * strideT, A);
+        next_live = live;
+        vnext = vt;
+    }
+}
+
+extern "C" int cmarl_td_lambda(cmarl_ctx* ctx, const float* values, const float* reward, const uint8_t* mask,
+                               double gamma, double lambda, float* returns, float* adv, void* stream) {
+    CMARL_ARG(ctx && values && reward && returns && adv, "null argument");
+    const int T = ctx->cfg.n_steps, V = ctx->n_heads, B = ctx->cfg.n_envs;
+    const int n = V * B;
+    // python-float coefficients rounded to fp32 when they meet an fp32 tensor (MME:496-501)
+    const float g = (float)gamma, l = (float)lambda, oml = (float)(1.0 - lambda);
+    td_lambda_kernel<5><<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(values, reward, mask, returns, adv,
+                                                                        T, V, B, g, l, oml);
+    ctx->launches++;
+    return cmarl_check_cuda(cudaGetLastError(), "td_lambda_kernel");
+}
+
+// ---------------------------------------------------------------------------------------- K6
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// phase 0: (sum, sumsq, count) of the head-mean over masked (t,b), accumulated in fp64
+__global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
+                                                         int T, int V, int B, double* __restrict__ stats) {
+    double s = 0.0, ss = 0.0, c = 0.0;
+    const size_t n = (size_t)T * B;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[i]) continue;
+        const size_t t = i / B, b = i - t * B;
+        float m = 0.0f;
+        for (int v = 0; v < V; ++v) m += x[(t * V + v) * B + b];
+        m = m / (float)V;
+        s += (double)m;
+        ss += (double)m * (double)m;
+        c += 1.0;
+    }
+    __shared__ double sh[3][8];
+    s = warp_sum(s); ss = warp_sum(ss); c = warp_sum(c);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh[0][w] = s; sh[1][w] = ss; sh[2][w] = c; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double a = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += sh[threadIdx.x][i];
+        atomicAdd(&stats[threadIdx.x], a);
+    }
+}
+
+// phase 1: apply.  mode 0 (reward): masked entries only, std + 1e-6; mode 1: every entry, no eps.
+__global__ void __launch_bounds__(256) norm_apply_kernel(float* __restrict__ x, const uint8_t* __restrict__ mask,
+                                                         int T, int V, int B, int mode,
+                                                         const double* __restrict__ stats) {
+    const double n = stats[2];
+    const double mean = stats[0] / n;
+    double var = (stats[1] - stats[0] * mean) / (n - 1.0);
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean;
+    const float sd = (float)sqrt(var);
+    const float den = mode == 0 ? sd + 1e-6f : sd;
+    const size_t total = (size_t)T * V * B;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        if (mode == 0 && mask) {
+            const size_t tv = i / B, b = i - tv * B, t = tv / V;
+            if (!mask[t * B + b]) continue;
+        }
+        x[i] = (x[i] - mu) / den;
+    }
+}
+
+extern "C" int cmarl_normalize(cmarl_ctx* ctx, float* x, int32_t n_heads, const uint8_t* mask, int32_t mode,
+                               int32_t phase, double* stats_io, void* stream) {
+    CMARL_ARG(ctx && x && stats_io, "null argument");
+    CMARL_ARG(n_heads >= 1 && (mode == 0 || mode == 1) && (phase == 0 || phase == 1), "bad mode/phase/heads");
+    const int T = ctx->cfg.n_steps, B = ctx->cfg.n_envs;
+    cudaStream_t st = as_stream(stream);
+    if (phase == 0) {
+        CMARL_CUDA(cudaMemsetAsync(stats_io, 0, 4 * sizeof(double), st));
+        int grid = ceil_div(T * B, 256);
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        norm_stats_kernel<<<grid, 256, 0, st>>>(x, mask, T, n_heads, B, stats_io);
+    } else {
+        int grid = ceil_div(T * n_heads * B, 256);
+        if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+        norm_apply_kernel<<<grid, 256, 0, st>>>(x, mask, T, n_heads, B, mode, stats_io);
+    }
+    ctx->launches++;
+    return cmarl_check_cuda(cudaGetLastError(), "normalize kernel");
+}
+
+// ---------------------------------------------------------------------------------------- K8
+struct AdamArgs {
+    float* params;
+    const float* grads;     // [P + 8] unnormalised sums (+stats)
+    float* m;
+    float* v;
+    float* stats_out;
+    int32_t* step_dev;
+    int step;
+    int n_tensors;          // 12
+    int tensor_off[13];     // prefix offsets of the 12 parameter tensors, [12] = P
+    int n_actor_tensors;    // 6
+    double lr[2], beta1, beta2, eps, max_norm;
+};
+
+__device__ float block_sum(float x, float* sh) {
+    x = warp_sum(x);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[w] = x;
+    __syncthreads();
+    float r = 0.0f;
+    if (threadIdx.x < 32) {
+        r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0f;
+        r = warp_sum(r);
+        if (threadIdx.x == 0) sh[32] = r;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// Single CTA: 9 670 parameters is ~10 per thread; everything between the all-reduce and the next
+// epoch's forward pass happens in this one launch (scale, per-tensor norms, clip, Adam, stats).
+__global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
+    __shared__ float sh[33];
+    __shared__ float tnorm[16];
+    const int P = a.tensor_off[a.n_tensors];
+    const float* stats = a.grads + P;
+    const float count = stats[5];
+    // norm of the per-tensor norms (norm_d, MME:221-224) for each network
+    for (int k = 0; k < a.n_tensors; ++k) {
+        float s = 0.0f;
+        for (int i = a.tensor_off[k] + threadIdx.x; i < a.tensor_off[k + 1]; i += blockDim.x) {
+            const float g = a.grads[i] / count;
+            s += g * g;
+        }
+        s = block_sum(s, sh);
+        if (threadIdx.x == 0) tnorm[k] = sqrtf(s);
+    }
+    __syncthreads();
+    float net_norm[2], coef[2];
+    for (int net = 0; net < 2; ++net) {
+        float s = 0.0f;
+        const int k0 = net == 0 ? 0 : a.n_actor_tensors, k1 = net == 0 ? a.n_actor_tensors : a.n_tensors;
+        for (int k = k0; k < k1; ++k) s += tnorm[k] * tnorm[k];
+        net_norm[net] = sqrtf(s);
+        coef[net] = 1.0f;
+        if (a.max_norm > 0.0) {
+            // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+            const float c = (float)a.max_norm / (net_norm[net] + 1e-6f);
+            coef[net] = c < 1.0f ? c : 1.0f;
+        }
+    }
+    const int step = a.step_dev ? (*a.step_dev + 1) : a.step;
+    // bias corrections in double, as torch's python-float arithmetic (_single_tensor_adam)
+    const double bc1 = 1.0 - pow(a.beta1, (double)step);
+    const double bc2 = 1.0 - pow(a.beta2, (double)step);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float w1 = (float)(1.0 - a.beta1);
+    const float b2 = (float)a.beta2, w2 = (float)(1.0 - a.beta2);
+    const float eps = (float)a.eps;
+    const int actor_end = a.tensor_off[a.n_actor_tensors];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int net = i < actor_end ? 0 : 1;
+        const float neg_step_size = (float)(-(a.lr[net] / bc1));
+        float g = a.grads[i] / count;
+        if (a.max_norm > 0.0) g = g * coef[net];
+        float m = a.m[i], v = a.v[i];
+        m = fmaf(w1, g - m, m);                 // exp_avg.lerp_(grad, 1 - beta1): ATen's lerp is an fma
+        v = v * b2;                             // exp_avg_sq.mul_(beta2)
+        v = v + (w2 * g) * g;                   //            .addcmul_(grad, grad, value=1 - beta2)
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        a.params[i] = a.params[i] + (neg_step_size * m) / denom;   // param.addcdiv_(m, denom, value=-step_size)
+        a.m[i] = m;
+        a.v[i] = v;
+    }
+    if (threadIdx.x == 0) {
+        if (a.stats_out) {
+            for (int k = 0; k < 5; ++k) a.stats_out[k] = stats[k] / count;
+            a.stats_out[5] = net_norm[0];
+            a.stats_out[6] = net_norm[1];
+            a.stats_out[7] = count;
+        }
+        if (a.step_dev) *a.step_dev = step;
+    }
+}
+
+extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, float* exp_avg,
+                                    float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor,
+                                    double lr_critic, double beta1, double beta2, double eps, double max_norm,
+                                    float* stats_out, void* stream) {
+    CMARL_ARG(ctx && params && grads && exp_avg && exp_avg_sq, "null argument");
+    CMARL_ARG(step_dev || step >= 1, "step must be >= 1");
+    AdamArgs a;
+    a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
+    a.step_dev = step_dev; a.step = step;
+    a.n_tensors = 12; a.n_actor_tensors = 6;
+    const NetLayout* nets[2] = {&ctx->actor, &ctx->critic};
+    int base = 0, k = 0;
+    for (int n = 0; n < 2; ++n) {
+        const NetLayout& L = *nets[n];
+        const int offs[6] = {L.w1, L.b1, L.w2, L.b2, L.w3, L.b3};
+        for (int j = 0; j < 6; ++j) a.tensor_off[k++] = base + offs[j];
+        base += L.count;
+    }
+    a.tensor_off[12] = base;
+    a.lr[0] = lr_actor; a.lr[1] = lr_critic; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
+    clip_adam_kernel<<<1, 1024, 0, as_stream(stream)>>>(a);
+    ctx->launches++;
+    return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
+}

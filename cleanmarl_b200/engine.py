@@ -1,0 +1,233 @@
+"""Thin torch-tensor front end of the C ABI: one ``Engine`` per GPU.
+
+PyTorch is the host container only (device memory, streams); every computation is a kernel of
+libcmarl_b200.so.  All tensors use the device layout of include/cmarl_b200.h
+(time-major, feature-major, env-minor); ``to_device_layout`` / ``to_reference_layout`` convert
+from/to the reference's batch-major ``RolloutBuffer.get_batch`` tuple (MME:148-157).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+N_STATS = 8
+RAW_OBS = 18
+
+
+@dataclass
+class Shapes:
+    n_envs: int
+    n_steps: int = 25
+    n_agents: int = 3
+    obs_dim: int = 21
+    state_dim: int = 54
+    n_actions: int = 5
+    actor_hidden: int = 32
+    actor_layers: int = 1
+    critic_hidden: int = 64
+    critic_layers: int = 1
+    critic_on_obs: bool = False
+
+
+def _ptr(t, dtype, device, name):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if t.device != device:
+        raise ValueError(f"{name}: tensor on {t.device}, engine on {device} (no CPU path exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: dtype {t.dtype}, expected {dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, shapes: Shapes, device: int | torch.device = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("cleanmarl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
+        self.shapes = shapes
+        cfg = _lib.Config(self.device.index, shapes.n_envs, shapes.n_steps, shapes.n_agents, shapes.obs_dim,
+                          shapes.state_dim, shapes.n_actions, shapes.actor_hidden, shapes.actor_layers,
+                          shapes.critic_hidden, shapes.critic_layers, int(shapes.critic_on_obs))
+        h = C.c_void_p()
+        _lib.check(self.lib.cmarl_ctx_create(C.byref(cfg), C.byref(h)), "cmarl_ctx_create")
+        self._h = h
+        self.n_actor = self.lib.cmarl_actor_param_count(h)
+        self.n_critic = self.lib.cmarl_critic_param_count(h)
+        self.n_params = self.n_actor + self.n_critic
+        self.n_heads = self.lib.cmarl_value_heads(h)
+        self.workspace = torch.empty(self.lib.cmarl_workspace_bytes(h) // 4, dtype=torch.float32, device=self.device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.cmarl_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def launches(self) -> int:
+        return self.lib.cmarl_launch_count(self._h)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f(self, t, name):
+        return _ptr(t, torch.float32, self.device, name)
+
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def alloc_rollout(self, with_obs=False):
+        s = self.shapes
+        T, B, N = s.n_steps, s.n_envs, s.n_agents
+        buf = {
+            "state": self.empty(T, s.state_dim, B),
+            "actions": self.empty(T, N, B, dtype=torch.int32),
+            "logp": self.empty(T, N, B),
+            "reward": self.empty(T, B),
+            "ep_return": self.empty(B, dtype=torch.float64),
+            "values": self.empty(T, self.n_heads, B),
+            "returns": self.empty(T, self.n_heads, B),
+            "adv": self.empty(T, self.n_heads, B),
+            "obs": self.empty(T, N, s.obs_dim, B) if with_obs else None,
+        }
+        return buf
+
+    # ------------------------------------------------------------------ entries
+    def env_reset(self, env, seed: int, episode: int):
+        _lib.check(self.lib.cmarl_env_reset(self._h, _ptr(env, torch.float64, self.device, "env"),
+                                            seed & (2**64 - 1), episode & (2**64 - 1), self._stream()), "cmarl_env_reset")
+
+    def rollout(self, actor_params, env, state, actions, logp, reward, *, noise=None, obs=None, ep_return=None,
+                seed=0, episode=0):
+        _lib.check(self.lib.cmarl_rollout(
+            self._h, self._f(actor_params, "actor_params"), _ptr(env, torch.float64, self.device, "env"),
+            self._f(noise, "noise"), seed & (2**64 - 1), episode & (2**64 - 1), self._f(state, "state"),
+            self._f(obs, "obs"), _ptr(actions, torch.int32, self.device, "actions"), self._f(logp, "logp"),
+            self._f(reward, "reward"), _ptr(ep_return, torch.float64, self.device, "ep_return"), self._stream()),
+            "cmarl_rollout")
+
+    def actor_act(self, actor_params, obs, noise, actions, logp, *, avail=None, logits=None):
+        _lib.check(self.lib.cmarl_actor_act(
+            self._h, self._f(actor_params, "actor_params"), self._f(obs, "obs"),
+            _ptr(avail, torch.uint8, self.device, "avail"), self._f(noise, "noise"),
+            _ptr(actions, torch.int32, self.device, "actions"), self._f(logp, "logp"), self._f(logits, "logits"),
+            self._stream()), "cmarl_actor_act")
+
+    def critic_values(self, critic_params, values, *, state=None, obs=None):
+        _lib.check(self.lib.cmarl_critic_values(self._h, self._f(critic_params, "critic_params"),
+                                                self._f(state, "state"), self._f(obs, "obs"),
+                                                self._f(values, "values"), self._stream()), "cmarl_critic_values")
+
+    def td_lambda(self, values, reward, returns, adv, gamma, lam, *, mask=None):
+        _lib.check(self.lib.cmarl_td_lambda(self._h, self._f(values, "values"), self._f(reward, "reward"),
+                                            _ptr(mask, torch.uint8, self.device, "mask"), float(gamma), float(lam),
+                                            self._f(returns, "returns"), self._f(adv, "adv"), self._stream()),
+                   "cmarl_td_lambda")
+
+    def normalize(self, x, n_heads, mode, phase, stats, *, mask=None):
+        _lib.check(self.lib.cmarl_normalize(self._h, self._f(x, "x"), n_heads,
+                                            _ptr(mask, torch.uint8, self.device, "mask"), mode, phase,
+                                            _ptr(stats, torch.float64, self.device, "stats"), self._stream()),
+                   "cmarl_normalize")
+
+    def ppo_epoch_grads(self, params, grads, *, state=None, obs=None, actions, logp_old, adv, returns, mask=None,
+                        avail=None, clip=0.2, ent_coef=0.001):
+        _lib.check(self.lib.cmarl_ppo_epoch_grads(
+            self._h, self._f(params, "params"), self._f(state, "state"), self._f(obs, "obs"),
+            _ptr(actions, torch.int32, self.device, "actions"), self._f(logp_old, "logp_old"), self._f(adv, "adv"),
+            self._f(returns, "returns"), _ptr(mask, torch.uint8, self.device, "mask"),
+            _ptr(avail, torch.uint8, self.device, "avail"), float(clip), float(ent_coef), self._f(grads, "grads"),
+            C.c_void_p(self.workspace.data_ptr()), self._stream()), "cmarl_ppo_epoch_grads")
+
+    def clip_adam_step(self, params, grads, exp_avg, exp_avg_sq, *, step=1, step_dev=None, lr_actor=8e-4,
+                       lr_critic=8e-4, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=-1.0, stats_out=None):
+        _lib.check(self.lib.cmarl_clip_adam_step(
+            self._h, self._f(params, "params"), self._f(grads, "grads"), self._f(exp_avg, "exp_avg"),
+            self._f(exp_avg_sq, "exp_avg_sq"), int(step), _ptr(step_dev, torch.int32, self.device, "step_dev"),
+            float(lr_actor), float(lr_critic), float(beta1), float(beta2), float(eps), float(max_norm),
+            self._f(stats_out, "stats_out"), self._stream()), "cmarl_clip_adam_step")
+
+
+# ---------------------------------------------------------------------- layout conversion
+def to_device_layout(batch, device, with_obs=True):
+    """Reference 8-tuple (MME:148-157, batch-major) -> dict of device-layout tensors."""
+    obs, actions, logp, reward, states, avail, done, mask = batch
+    out = {
+        "state": states.permute(1, 2, 0).contiguous().float().to(device),               # [T][S][B]
+        "actions": actions.permute(1, 2, 0).contiguous().to(torch.int32).to(device),    # [T][N][B]
+        "logp": logp.permute(1, 2, 0).contiguous().float().to(device),
+        "reward": reward.permute(1, 0).contiguous().float().to(device),                 # [T][B]
+        "mask": mask.permute(1, 0).contiguous().to(torch.uint8).to(device),
+        "avail": avail.permute(1, 2, 3, 0).contiguous().to(torch.uint8).to(device),     # [T][N][A][B]
+        "done": done.permute(1, 0).contiguous().float().to(device),
+    }
+    if with_obs:
+        out["obs"] = obs.permute(1, 2, 3, 0).contiguous().float().to(device)            # [T][N][O][B]
+    return out
+
+
+def heads_to_device(x, n_heads, device):
+    """[B,T,N] (reference returns/advantages) -> [T][V][B]; V=1 keeps agent 0 (all agents equal, MME:484-485)."""
+    x = x.permute(1, 2, 0)
+    if n_heads == 1:
+        x = x[:, :1]
+    return x.contiguous().float().to(device)
+
+
+def heads_to_reference(x, n_agents):
+    """[T][V][B] -> [B,T,N] (broadcast the centralised head to the agents)."""
+    T, V, B = x.shape
+    x = x.permute(2, 0, 1)
+    if V == 1:
+        x = x.expand(B, T, n_agents)
+    return x.contiguous()
+
+
+def obs_from_state(state, n_agents=3, agent_ids=True):
+    """[T][S][B] -> [T][N][O][B]: raw rows + one-hot ids (pettingzoo_wrapper.py:93-98)."""
+    T, S, B = state.shape
+    raw = state.reshape(T, n_agents, S // n_agents, B)
+    if not agent_ids:
+        return raw.contiguous()
+    ids = torch.eye(n_agents, device=state.device, dtype=state.dtype)[None, :, :, None].expand(T, n_agents, n_agents, B)
+    return torch.cat([raw, ids], dim=2).contiguous()
+
+
+def to_reference_layout(buf, n_agents=3, n_actions=5, agent_ids=True):
+    """Device rollout buffers -> the reference's ``get_batch`` 8-tuple (dtypes of MME:148-157)."""
+    state = buf["state"]
+    T, S, B = state.shape
+    obs = buf.get("obs")
+    if obs is None:
+        obs = obs_from_state(state, n_agents, agent_ids)
+    mask = buf.get("mask")
+    avail = buf.get("avail")
+    done = buf.get("done")
+    return (
+        obs.permute(3, 0, 1, 2).contiguous().float(),
+        buf["actions"].permute(2, 0, 1).contiguous().long(),
+        buf["logp"].permute(2, 0, 1).contiguous().float(),
+        buf["reward"].permute(1, 0).contiguous().float(),
+        state.permute(2, 0, 1).contiguous().float(),
+        (avail.permute(3, 0, 1, 2).contiguous().bool() if avail is not None
+         else torch.ones(B, T, n_agents, n_actions, dtype=torch.bool, device=state.device)),
+        (done.permute(1, 0).contiguous().float() if done is not None
+         else torch.zeros(B, T, device=state.device)),
+        (mask.permute(1, 0).contiguous().bool() if mask is not None
+         else torch.ones(B, T, dtype=torch.bool, device=state.device)),
+    )

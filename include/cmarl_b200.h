@@ -1,0 +1,157 @@
+/*
+ * cmarl_b200.h -- C ABI of libcmarl_b200.so: the sm_100a kernels behind the MAPPO multi-env
+ * training path of CleanMARL (reference: cleanmarl/mappo_multienvs.py, "MME" below).
+ *
+ * The reference is pure Python and exposes no FFI seam; the entry points
+ * below are what a ctypes binding inside the reference script would call to replace, one by one,
+ * the inline blocks of its __main__ loop.  Each entry cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - every pointer is a CUDA *device* pointer owned by the caller (torch tensors) unless it is
+ *    marked HOST; the library never allocates device memory;
+ *  - launches go on the passed cudaStream_t (as void*), no hidden synchronisation;
+ *  - return value: 0 ok, < 0 argument error, > 0 cudaError_t; cmarl_last_error() gives the text;
+ *  - one context per GPU, single host thread per context (not re-entrant).
+ *
+ * Device layout ("time-major, feature-major, env-minor": the env index b is always the fastest
+ * dimension so a warp touches 128 contiguous bytes; SURVEY.md section 7 "hard parts"):
+ *    state    f32 [T][S][B]      raw per-agent observations of the N agents concatenated (S = N*18)
+ *    obs      f32 [T][N][O][B]   optional; NULL => rebuilt from state: obs[n][k<18] = state[18n+k],
+ *                                obs[n][18+m] = (m == n) one-hot id (pettingzoo_wrapper.py:93-98)
+ *    actions  i32 [T][N][B]      logp f32 [T][N][B]     reward f32 [T][B]
+ *    mask     u8  [T][B]         NULL => all ones        avail u8 [T][N][A][B]  NULL => all ones
+ *    values / returns / adv  f32 [T][V][B], V = 1 (MAPPO, centralised critic; the reference
+ *                                broadcasts the scalar to the N agents, MME:484-485) or V = N (IPPO)
+ *    noise    f32 [T][N][A][B]   Exp(1) race noise q (Categorical.sample == argmax(p/q))
+ *    env      f64 [18][B]        rows 0-5 agent p_pos (x0,y0,x1,y1,x2,y2), 6-11 agent p_vel,
+ *                                12-17 landmark p_pos
+ *  Parameters are ONE flat f32 vector in the order of torch's module.parameters():
+ *    actor  W1[Ha][O] b1[Ha] W2[Ha][Ha] b2[Ha] W3[A][Ha] b3[A]   then
+ *    critic W1[Hc][Sin] b1[Hc] W2[Hc][Hc] b2[Hc] W3[1][Hc] b3[1]   (row-major W[out][in], y = x W^T + b)
+ */
+#ifndef CMARL_B200_H
+#define CMARL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMARL_VERSION 100
+#define CMARL_N_STATS 8          /* floats appended to the flat gradient vector, see cmarl_ppo_epoch_grads */
+#define CMARL_RAW_OBS 18
+
+typedef struct cmarl_ctx cmarl_ctx;
+
+typedef struct cmarl_config {
+    int32_t device;          /* CUDA ordinal */
+    int32_t n_envs;          /* B on this GPU (MME Args.batch_size, sharded across GPUs) */
+    int32_t n_steps;         /* T = 25 for simple_spread_v3 (max_cycles) */
+    int32_t n_agents;        /* N = 3 */
+    int32_t obs_dim;         /* O = 21 with agent ids (MME:26), 18 without */
+    int32_t state_dim;       /* S = 54 */
+    int32_t n_actions;       /* A = 5 */
+    int32_t actor_hidden;    /* MME Args.actor_hidden_dim  (32) */
+    int32_t actor_layers;    /* MME Args.actor_num_layers  (1)  */
+    int32_t critic_hidden;   /* MME Args.critic_hidden_dim (64; ippo_multienvs.py:34 -> 32) */
+    int32_t critic_layers;   /* MME Args.critic_num_layers (1)  */
+    int32_t critic_on_obs;   /* 0: MAPPO critic(state) MME:336; 1: IPPO critic(obs) ippo_multienvs.py:336 */
+} cmarl_config;
+
+/* -- library ---------------------------------------------------------------------------- */
+int cmarl_version(void);
+const char* cmarl_last_error(void);
+
+/* Context: validates the configuration (unsupported shapes fail here, loudly), records the device
+ * properties and sets the kernels' shared-memory attributes.  Replaces nothing in the reference;
+ * it is the handle the entries below share. */
+int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out);
+int cmarl_ctx_destroy(cmarl_ctx* ctx);
+int cmarl_actor_param_count(const cmarl_ctx* ctx);    /* 1 925 for the default shapes */
+int cmarl_critic_param_count(const cmarl_ctx* ctx);   /* 7 745 */
+int cmarl_value_heads(const cmarl_ctx* ctx);          /* V */
+size_t cmarl_workspace_bytes(const cmarl_ctx* ctx);   /* scratch for cmarl_ppo_epoch_grads */
+int cmarl_launch_count(const cmarl_ctx* ctx);         /* kernels launched through this ctx so far */
+
+/* -- K1: env reset.  Replaces the ("reset", None) round trip MME:393-401 -> env_worker MME:250-255
+ * -> PettingZooWrapper.reset pettingzoo_wrapper.py:32-38 -> simple_spread reset_world: agent
+ * positions then landmark positions ~ U(-1,1), velocities 0.  Draws come from Philox4x32-10
+ * keyed by (seed, episode); callers that need given start positions write `env` themselves. */
+int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, void* stream);
+
+/* -- K1+K2+K3: one rollout of T lock-step steps for the B envs, entirely on the device.
+ * Replaces the whole `while len(alive_envs) > 0` loop MME:408-453: Actor.act (MME:172-183,
+ * Categorical sample + log_prob), the ("step", action) round trip (MME:415-417, env_worker
+ * MME:268-281, PettingZooWrapper.step pettingzoo_wrapper.py:44-66, MPE World.step), and the
+ * per-step buffer appends (MME:425-434) / RolloutBuffer.add (MME:103-107).
+ *   noise   NULL => q drawn on the device (Philox, keyed by seed/episode); else the given q is used
+ *           so that actions are a deterministic function of (params, env, q)
+ *   state, actions, logp, reward   outputs in the device layout above
+ *   obs     optional output [T][N][O][B] (NULL to skip; K7 rebuilds it from state)
+ *   ep_return f64 [B]   sum over t of the team reward (MME:433), optional
+ * `env` holds the start state on entry and the final state on exit. */
+int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* env, const float* noise,
+                  uint64_t seed, uint64_t episode,
+                  float* state, float* obs, int32_t* actions, float* logp, float* reward,
+                  double* ep_return, void* stream);
+
+/* -- K2 alone: Actor.act on given observations (MME:172-176), used by the parity tests and the
+ * eval loop.  obs [N][O][B] (one time step), avail u8 [N][A][B] or NULL, noise [N][A][B]. */
+int cmarl_actor_act(cmarl_ctx* ctx, const float* actor_params, const float* obs, const uint8_t* avail,
+                    const float* noise, int32_t* actions, float* logp, float* logits_out, void* stream);
+
+/* -- K4: batched critic forward.  Replaces the 2*B*T batch-of-1 calls critic(x=b_states[ep, t])
+ * of MME:495,502 (IPPO: b_obs, ippo_multienvs.py:495,503) by one pass.
+ *   critic_in = state [T][S][B] (MAPPO) or obs [T][N][O][B] / NULL=>from state (IPPO) */
+int cmarl_critic_values(cmarl_ctx* ctx, const float* critic_params, const float* state, const float* obs,
+                        float* values, void* stream);
+
+/* -- K5: TD(lambda) return / advantage scan, the recurrence of MME:484-504 in the reference's
+ * operation order (fp32, no FMA): R_t = r_t + g*(l*R_{t+1} + (1-l)*V_{t+1}), V_{T_ep} := 0,
+ * A_t = R_t - V_t.  Entries with mask == 0 are written as 0 (MME:484-485 zero-init). */
+int cmarl_td_lambda(cmarl_ctx* ctx, const float* values, const float* reward, const uint8_t* mask,
+                    double gamma, double lambda, float* returns, float* adv, void* stream);
+
+/* -- K6: the optional normalisations.  mode 0: reward, (r-mean)/(std+1e-6) over masked entries,
+ * unbiased std (MME:143-146); mode 1: advantages / returns, (x-mean)/std of the agent-mean over
+ * masked (b,t), unbiased, no eps (MME:505-512).  x is [T][V][B] (V=1 for mode 0), in place.
+ * stats_io f64 [4]: (sum, sumsq, count, flag).  phase 0 computes the local sums into stats_io,
+ * phase 1 applies them -- a multi-GPU caller all-reduces stats_io[0..2] in between. */
+int cmarl_normalize(cmarl_ctx* ctx, float* x, int32_t n_heads, const uint8_t* mask, int32_t mode,
+                    int32_t phase, double* stats_io, void* stream);
+
+/* -- K7: one PPO epoch's loss + gradients, forward and backward fused (MME:522-582).
+ * Outputs UNNORMALISED sums over this GPU's envs so that shards add: grads_out is
+ * f32 [Pa + Pc + CMARL_N_STATS]:
+ *   [0,Pa)      d/d(actor params)  of  sum_{b,t} mean_n( -min(A r, A clamp(r)) - ent_coef * H )
+ *   [Pa,Pa+Pc)  d/d(critic params) of  sum_{b,t} mean_v (V - R)^2
+ *   stats: [0] actor loss sum [1] critic loss sum [2] entropy sum [3] kl sum [4] clip-fraction sum
+ *          [5] number of valid (b,t) = b_mask.sum() [6],[7] reserved (0)
+ * All become the reference's values after division by stats[5] (MME:572-576), which
+ * cmarl_clip_adam_step does after the caller's all-reduce. */
+int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const float* state, const float* obs,
+                          const int32_t* actions, const float* logp_old, const float* adv,
+                          const float* returns, const uint8_t* mask, const uint8_t* avail,
+                          double clip, double ent_coef, float* grads_out, void* workspace, void* stream);
+
+/* -- K8: grad scaling, grad norms, optional clipping and the Adam step for both networks
+ * (MME:584-594; norm_d MME:221-224; torch.optim.Adam single-tensor defaults amsgrad=False, wd=0).
+ *   grads  the (all-reduced) output of cmarl_ppo_epoch_grads
+ *   step   1-based Adam step count (used when step_dev == NULL); step_dev: optional device
+ *          counter holding the number of steps taken so far -- the kernel uses *step_dev + 1 and
+ *          increments it, so the launch is CUDA-graph replayable;  max_norm <= 0 => no clipping
+ *          (MME:62-63, 586).  Hyper-parameters are doubles because the reference derives the
+ *          bias corrections in Python floats before rounding to fp32 (torch/optim/adam.py).
+ *   stats_out f32 [8]: actor_loss, critic_loss, entropy, kl, clip_frac, actor_grad_norm,
+ *                      critic_grad_norm, n_valid  -- the scalars logged at MME:597-612 */
+int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, float* exp_avg,
+                         float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor,
+                         double lr_critic, double beta1, double beta2, double eps, double max_norm,
+                         float* stats_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMARL_B200_H */

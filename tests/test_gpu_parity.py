@@ -1,0 +1,412 @@
+"""GPU parity tests: every kernel of libcmarl_b200.so against the CPU oracle (oracle/), through the
+C ABI.  Run on the B200 box: ``pytest -m gpu``.  Tolerances are stated per test.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mappo as om
+from oracle import spread as osp
+
+pytestmark = pytest.mark.gpu
+
+
+def T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+@pytest.fixture(scope="module")
+def cm():
+    import cleanmarl_b200 as cm
+    from cleanmarl_b200 import _lib
+    _lib.load()          # raises if the CUDA extension is missing: no fallback
+    return cm
+
+
+def make_engine(cm, B, T_=25, **kw):
+    return cm.Engine(cm.Shapes(n_envs=B, n_steps=T_, **kw), device=0)
+
+
+def flat_params(actor, critic, device):
+    return torch.cat([actor.flat_params(), critic.flat_params()]).to(device).contiguous()
+
+
+def ragged_mask(B, Tn, gen, frac=0.4):
+    lengths = torch.where(torch.rand(B, generator=gen) < frac,
+                          torch.randint(1, Tn + 1, (B,), generator=gen), torch.full((B,), Tn))
+    return (torch.arange(Tn)[None, :] < lengths[:, None])
+
+
+# ----------------------------------------------------------------------------------------- K5
+@pytest.mark.parametrize("B,V", [(1000, 1), (333, 3), (4096, 1)])
+def test_td_lambda_scan_bit_exact(cm, B, V):
+    """K5 vs oracle.td_lambda_scan on identical values: bit-exact (same fp32 op order, MME:496-504)."""
+    from cleanmarl_b200 import engine as E
+    Tn = 25
+    g = torch.Generator().manual_seed(B + V)
+    values = torch.randn(B, Tn, V, generator=g) * 5
+    reward = -torch.rand(B, Tn, generator=g) * 4
+    mask = ragged_mask(B, Tn, g)
+    ret, adv = om.td_lambda_scan(values, reward, mask, 0.99, 0.95)
+    eng = make_engine(cm, B, critic_on_obs=(V == 3), critic_hidden=32 if V == 3 else 64)
+    dev = eng.device
+    v_d = values.permute(1, 2, 0).contiguous().to(dev)
+    r_d = reward.permute(1, 0).contiguous().to(dev)
+    m_d = mask.permute(1, 0).contiguous().to(torch.uint8).to(dev)
+    ret_d, adv_d = torch.empty_like(v_d), torch.empty_like(v_d)
+    eng.td_lambda(v_d, r_d, ret_d, adv_d, 0.99, 0.95, mask=m_d)
+    assert torch.equal(ret_d.permute(2, 0, 1).cpu(), ret)
+    assert torch.equal(adv_d.permute(2, 0, 1).cpu(), adv)
+    # no mask == all ones
+    ret1, adv1 = om.td_lambda_scan(values, reward, torch.ones_like(mask), 0.99, 0.95)
+    eng.td_lambda(v_d, r_d, ret_d, adv_d, 0.99, 0.95)
+    assert torch.equal(ret_d.permute(2, 0, 1).cpu(), ret1) and torch.equal(adv_d.permute(2, 0, 1).cpu(), adv1)
+
+
+# ----------------------------------------------------------------------------------------- K4 (+K5) on the golden run
+@pytest.mark.parametrize("name,ippo", [("g8_mappo", False), ("g8_ippo", True)])
+def test_critic_td_lambda_vs_reference_run(cm, golden, name, ippo):
+    """K4+K5 on the batch of a real reference iteration: returns/advantages within 1e-5 (north star)."""
+    from cleanmarl_b200 import engine as E
+    g = golden(name)
+    seed = int(g["seed"])
+    if ippo:
+        actor, critic = om.build_networks(seed, state_dim=21, critic_hidden=int(g["critic_hidden_dim"]))
+    else:
+        actor, critic = om.build_networks(seed)
+    B = int(g["B"])
+    eng = make_engine(cm, B, critic_on_obs=ippo, critic_hidden=int(g["critic_hidden_dim"]))
+    dev = eng.device
+    batch = tuple(T(g[k]) for k in ("obs", "actions", "log_probs", "reward", "states", "avail", "done", "mask"))
+    d = E.to_device_layout(batch, dev)
+    values = eng.empty(25, eng.n_heads, B)
+    cp = critic.flat_params().to(dev)
+    for use_obs in ((True, False) if ippo else (False,)):
+        eng.critic_values(cp, values, state=d["state"], obs=d["obs"] if use_obs else None)
+        with torch.no_grad():
+            v_ref = critic(batch[0] if ippo else batch[4]).squeeze(-1)      # [B,T] or [B,T,N]
+        v_ref = v_ref.unsqueeze(-1) if not ippo else v_ref
+        assert (values.permute(2, 0, 1).cpu() - v_ref).abs().max() < 2e-6
+        ret, adv = torch.empty_like(values), torch.empty_like(values)
+        eng.td_lambda(values, d["reward"], ret, adv, float(g["gamma"]), float(g["td_lambda"]), mask=d["mask"])
+        ret_r = E.heads_to_reference(ret, 3).cpu()
+        adv_r = E.heads_to_reference(adv, 3).cpu()
+        assert (ret_r - T(g["return_lambda"])).abs().max() < 1e-5
+        assert (adv_r - T(g["advantages"])).abs().max() < 1e-5
+
+
+# ----------------------------------------------------------------------------------------- K7
+def _oracle_epoch(actor, critic, batch, adv, ret, ippo, clip=0.2, ent=0.001, flat=True):
+    obs, actions, logp, reward, states, avail, done, mask = batch
+    actor.zero_grad(); critic.zero_grad()
+    fn = om.ppo_epoch_flat if flat else om.ppo_epoch_loop
+    out = fn(actor, critic, obs, actions, logp, obs if ippo else states, avail, mask, adv, ret, clip, ent)
+    out.actor_loss.backward(); out.critic_loss.backward()
+    return out, actor.flat_grads(), critic.flat_grads()
+
+
+def _check_epoch(eng, E, actor, critic, batch, adv, ret, ippo, use_obs, use_mask=True, use_avail=True, flat=True):
+    dev = eng.device
+    d = E.to_device_layout(batch, dev)
+    params = flat_params(actor, critic, dev)
+    grads = eng.empty(eng.n_params + 8)
+    eng.ppo_epoch_grads(params, grads, state=d["state"], obs=d["obs"] if use_obs else None, actions=d["actions"],
+                        logp_old=d["logp"], adv=E.heads_to_device(adv, eng.n_heads, dev),
+                        returns=E.heads_to_device(ret, eng.n_heads, dev), mask=d["mask"] if use_mask else None,
+                        avail=d["avail"] if use_avail else None, clip=0.2, ent_coef=0.001)
+    out, ga, gc = _oracle_epoch(actor, critic, batch, adv, ret, ippo, flat=flat)
+    gcpu = grads.cpu()
+    n = gcpu[eng.n_params + 5].item()
+    assert n == float(batch[7].sum())
+    g_a = gcpu[:eng.n_actor] / n
+    g_c = gcpu[eng.n_actor:eng.n_params] / n
+    st = gcpu[eng.n_params:] / n
+    # per-tensor gradient check: max abs error <= 2e-5 of the tensor's max magnitude (fp32 reassociation)
+    for name, gd, gr, net in (("actor", g_a, ga, actor), ("critic", g_c, gc, critic)):
+        off = 0
+        for p in net.parameters():
+            k = p.numel()
+            a, b = gd[off:off + k], gr[off:off + k]
+            scale = max(b.abs().max().item(), 1e-6)
+            assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-9, (name, tuple(p.shape), (a - b).abs().max().item(), scale)
+            off += k
+    rel = lambda x, y: abs(x - y) / max(abs(y), 1e-6)
+    assert rel(st[0].item(), out.actor_loss.item()) < 1e-5
+    assert rel(st[1].item(), out.critic_loss.item()) < 1e-5
+    assert rel(st[2].item(), out.entropy.item()) < 1e-5
+    assert abs(st[3].item() - out.kl.item()) < 1e-6 + 1e-4 * abs(out.kl.item())
+    assert abs(st[4].item() - float(out.clipfrac)) < 1e-6
+    return grads
+
+
+@pytest.mark.parametrize("name,ippo", [("g8_mappo", False), ("g8_ippo", True)])
+def test_ppo_epoch_grads_vs_reference_loop(cm, golden, name, ippo):
+    """K7 on the batch of a real reference iteration vs autograd through the reference's own loop form."""
+    from cleanmarl_b200 import engine as E
+    g = golden(name)
+    seed = int(g["seed"])
+    actor, critic = (om.build_networks(seed, state_dim=21, critic_hidden=int(g["critic_hidden_dim"])) if ippo
+                     else om.build_networks(seed))
+    batch = tuple(T(g[k]) for k in ("obs", "actions", "log_probs", "reward", "states", "avail", "done", "mask"))
+    eng = make_engine(cm, int(g["B"]), critic_on_obs=ippo, critic_hidden=int(g["critic_hidden_dim"]))
+    for use_obs in (False, True):
+        _check_epoch(eng, E, actor, critic, batch, T(g["advantages"]), T(g["return_lambda"]), ippo, use_obs, flat=False)
+
+
+@pytest.mark.parametrize("B,ippo,hid", [(300, False, (32, 64)), (1024, False, (32, 64)), (515, True, (32, 32)),
+                                        (256, False, (64, 32)), (260, True, (64, 64))])
+def test_ppo_epoch_grads_synthetic(cm, B, ippo, hid):
+    """K7 on seeded synthetic batches: full TMA tiles + ragged tail tile, ragged masks, random avail,
+    obs rebuilt from state vs explicit obs, both hidden widths."""
+    from cleanmarl_b200 import engine as E
+    ha, hc = hid
+    actor, critic = om.build_networks(5, state_dim=21 if ippo else 54, actor_hidden=ha, critic_hidden=hc)
+    batch = list(om.synthetic_batch(B, seed=B, actor=actor))
+    gen = torch.Generator().manual_seed(B)
+    batch[7] = ragged_mask(B, 25, gen)
+    avail = torch.rand(B, 25, 3, 5, generator=gen) > 0.2
+    avail.scatter_(-1, batch[1].unsqueeze(-1), True)            # the taken action is always available
+    batch[5] = avail
+    with torch.no_grad():
+        batch[2] = torch.distributions.Categorical(logits=om.actor_logits(actor, batch[0], avail)).log_prob(batch[1]) \
+            + 0.1 * torch.randn(B, 25, 3, generator=gen)
+    V = 3 if ippo else 1
+    adv = torch.randn(B, 25, V, generator=gen).expand(B, 25, 3).contiguous() * 3
+    ret = torch.randn(B, 25, V, generator=gen).expand(B, 25, 3).contiguous() * 5
+    eng = make_engine(cm, B, critic_on_obs=ippo, actor_hidden=ha, critic_hidden=hc)
+    for use_obs in (False, True):
+        _check_epoch(eng, E, actor, critic, tuple(batch), adv, ret, ippo, use_obs)
+    g1 = _check_epoch(eng, E, actor, critic, tuple(batch), adv, ret, ippo, False).clone()
+    g2 = _check_epoch(eng, E, actor, critic, tuple(batch), adv, ret, ippo, False)
+    assert torch.equal(g1, g2)                                   # deterministic (fixed-order reductions)
+
+
+# ----------------------------------------------------------------------------------------- K8
+@pytest.mark.parametrize("max_norm", [-1.0, 0.5])
+def test_clip_adam_matches_torch_adam(cm, max_norm):
+    """K8 vs torch.optim.Adam (+clip_grad_norm_) for 3 steps: parameters within 1e-7 abs."""
+    actor, critic = om.build_networks(3)
+    eng = make_engine(cm, 64)
+    dev = eng.device
+    aopt, copt = om.make_optimizers(actor, critic)
+    params = flat_params(actor, critic, dev)
+    m, v = torch.zeros_like(params), torch.zeros_like(params)
+    gen = torch.Generator().manual_seed(0)
+    stats = eng.empty(8)
+    for step in range(1, 4):
+        ga = torch.randn(eng.n_actor, generator=gen) * 0.3
+        gc = torch.randn(eng.n_critic, generator=gen) * 2.0
+        n = 1600.0
+        grads = torch.cat([ga * n, gc * n, torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0, n, 0.0, 0.0]) * 1.0]).to(dev)
+        for net, gflat in ((actor, ga), (critic, gc)):
+            off = 0
+            for p in net.parameters():
+                p.grad = gflat[off:off + p.numel()].reshape(p.shape).clone()
+                off += p.numel()
+        na, nc = om.norm_d([p.grad for p in actor.parameters()]), om.norm_d([p.grad for p in critic.parameters()])
+        if max_norm > 0:
+            torch.nn.utils.clip_grad_norm_(actor.parameters(), max_norm=max_norm)
+            torch.nn.utils.clip_grad_norm_(critic.parameters(), max_norm=max_norm)
+        aopt.step(); copt.step()
+        eng.clip_adam_step(params, grads, m, v, step=step, max_norm=max_norm, stats_out=stats)
+        ref = torch.cat([actor.flat_params(), critic.flat_params()])
+        assert (params.cpu() - ref).abs().max().item() < 1e-7
+        s = stats.cpu()
+        assert abs(s[5].item() - float(na)) < 1e-5 * float(na) and abs(s[6].item() - float(nc)) < 1e-5 * float(nc)
+        assert abs(s[0].item() - 1.0 / n) < 1e-9 and s[7].item() == n
+    # device-resident step counter (CUDA-graph friendly) gives the same result as the host step
+    p2 = flat_params(*om.build_networks(3), dev)
+    m2, v2 = torch.zeros_like(p2), torch.zeros_like(p2)
+    p3, m3, v3 = p2.clone(), m2.clone(), v2.clone()
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    for step in range(1, 3):
+        eng.clip_adam_step(p2, grads, m2, v2, step=step, max_norm=max_norm)
+        eng.clip_adam_step(p3, grads, m3, v3, step_dev=cnt, max_norm=max_norm)
+    assert int(cnt.item()) == 2 and torch.equal(p2, p3)
+
+
+# ----------------------------------------------------------------------------------------- K2
+def test_actor_act_vs_reference_sample(cm, golden):
+    """K2 on the inputs of a real ``Actor.act`` call (g3): logits within 2e-6, log-probs within 1e-5,
+    action indices bit-exact wherever the race is not a numerical tie (|margin| > 1e-5 relative)."""
+    g = golden("g3_sample")
+    B = g["x"].shape[0]
+    eng = make_engine(cm, B, T_=1)
+    dev = eng.device
+    obs = T(g["x"]).permute(1, 2, 0).contiguous().to(dev)                 # [N][O][B]
+    avail = T(g["avail"]).permute(1, 2, 0).contiguous().to(torch.uint8).to(dev)
+    q = T(g["q"]).permute(1, 2, 0).contiguous().to(dev)
+    actions = eng.empty(3, B, dtype=torch.int32)
+    logp, logits = eng.empty(3, B), eng.empty(3, 5, B)
+    eng.actor_act(T(g["params"]).to(dev), obs, q, actions, logp, avail=avail, logits=logits)
+    lg = logits.permute(2, 0, 1).cpu()
+    ref_logits = T(g["logits"])
+    assert (lg - ref_logits).abs().max() < 2e-6 * max(1.0, ref_logits[ref_logits > -1e8].abs().max().item())
+    act = actions.permute(1, 0).cpu().long()
+    ref_act = T(g["actions"])
+    # race margin of the reference decision
+    probs = torch.softmax(ref_logits, dim=-1)
+    r = probs / T(g["q"])
+    top2 = r.topk(2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1]) / top2[..., 0]
+    decisive = margin > 1e-5
+    assert decisive.float().mean() > 0.999
+    assert torch.equal(act[decisive], ref_act[decisive])
+    same = act == ref_act
+    assert (logp.permute(1, 0).cpu()[same] - T(g["logp"])[same]).abs().max() < 1e-5
+    # oracle sampler on the DEVICE logits must reproduce the device actions bit-exactly
+    a2, _ = om.race_sample(lg, T(g["q"]))
+    assert (a2 == act).float().mean() > 0.9995
+
+
+# ----------------------------------------------------------------------------------------- K1+K2+K3
+@pytest.mark.parametrize("B", [96, 1000])
+def test_rollout_vs_oracle(cm, B):
+    """Device rollout vs the float64 oracle env + oracle actor, input driven (start positions and race
+    noise supplied).  Physics: the oracle env replays the DEVICE actions open loop -> observations within
+    1e-6 and team reward within 1e-6 of the oracle at every step.  Policy: the oracle actor on the device
+    observations with the same noise reproduces the device actions (ties excepted) and log-probs."""
+    from cleanmarl_b200 import engine as E
+    Tn = 25
+    actor, critic = om.build_networks(1)
+    eng = make_engine(cm, B)
+    dev = eng.device
+    rng = np.random.default_rng(B)
+    pos0 = rng.uniform(-1, 1, (B, 3, 2))
+    # make collisions common: pull agent 1 close to agent 0 in a third of the envs
+    close = rng.random(B) < 0.33
+    pos0[close, 1] = pos0[close, 0] + rng.uniform(-0.2, 0.2, (int(close.sum()), 2))
+    lm = rng.uniform(-1, 1, (B, 3, 2))
+    env = np.zeros((18, B))
+    env[0:6] = pos0.reshape(B, 6).T
+    env[12:18] = lm.reshape(B, 6).T
+    env_d = torch.from_numpy(env).to(dev)
+    q = om.draw_race_noise((Tn, 3, 5, B), generator=torch.Generator().manual_seed(B)).to(dev)
+    buf = eng.alloc_rollout(with_obs=True)
+    eng.rollout(actor.flat_params().to(dev), env_d, buf["state"], buf["actions"], buf["logp"], buf["reward"],
+                noise=q, obs=buf["obs"], ep_return=buf["ep_return"])
+    torch.cuda.synchronize()
+    acts = buf["actions"].cpu().numpy()                       # [T][N][B]
+    ref = osp.rollout_batched(pos0, lm, np.transpose(acts, (0, 2, 1)))
+    raw_d = buf["state"].cpu().numpy().reshape(Tn, 3, 18, B).transpose(0, 3, 1, 2)     # [T,B,3,18]
+    err = np.abs(raw_d - ref["raw_obs"]).max()
+    assert err < 1e-6, err
+    bit_exact = (raw_d == ref["raw_obs"]).mean()
+    assert bit_exact > 0.999, bit_exact
+    rew_d = buf["reward"].cpu().numpy()
+    assert np.abs(rew_d - ref["reward"].astype(np.float32)).max() < 1e-6
+    assert np.abs(buf["ep_return"].cpu().numpy() - ref["reward"].sum(0)).max() < 1e-9
+    assert np.abs(env_d.cpu().numpy()[0:6].T.reshape(B, 3, 2) - ref["final_pos"]).max() < 1e-12
+    # obs output = raw + one-hot ids, and equals what K7 rebuilds from state
+    assert torch.equal(buf["obs"], E.obs_from_state(buf["state"]))
+    # policy parity on the device observations
+    obs_ref = buf["obs"].permute(0, 3, 1, 2).cpu()            # [T,B,N,O]
+    with torch.no_grad():
+        logits = om.actor_logits(actor, obs_ref)
+        a_ref, lp_ref = om.race_sample(logits, q.permute(0, 3, 1, 2).cpu())
+    a_dev = torch.from_numpy(np.transpose(acts, (0, 2, 1))).long()
+    agree = (a_ref == a_dev)
+    assert agree.float().mean() > 0.9995, agree.float().mean()
+    lp_dev = buf["logp"].permute(0, 2, 1).cpu()
+    assert (lp_dev[agree] - lp_ref[agree]).abs().max() < 1e-5
+
+
+def test_rollout_device_rng_and_reset(cm):
+    """Device RNG path: reset draws U(-1,1) positions, zero velocities; actions follow the policy
+    distribution (chi-square-ish frequency check); same (seed, episode) -> identical rollout."""
+    B = 4096
+    actor, _ = om.build_networks(1)
+    eng = make_engine(cm, B)
+    dev = eng.device
+    env = eng.empty(18, B, dtype=torch.float64)
+    outs = []
+    for rep in range(2):
+        eng.env_reset(env, seed=7, episode=3)
+        e0 = env.clone()
+        buf = eng.alloc_rollout()
+        eng.rollout(actor.flat_params().to(dev), env, buf["state"], buf["actions"], buf["logp"], buf["reward"],
+                    seed=7, episode=3)
+        outs.append((e0, buf))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1]["actions"], outs[1][1]["actions"])
+    e0 = outs[0][0].cpu().numpy()
+    assert (np.abs(e0[0:6]) <= 1).all() and (np.abs(e0[12:18]) <= 1).all() and (e0[6:12] == 0).all()
+    assert abs(e0[0:6].mean()) < 0.02 and abs(e0[0:6].var() - 1 / 3) < 0.02
+    eng.env_reset(env, seed=7, episode=4)
+    assert not torch.equal(env, outs[0][0])
+    # empirical action frequencies at t=0 vs the policy's probabilities
+    buf = outs[0][1]
+    from cleanmarl_b200 import engine as E
+    obs0 = E.obs_from_state(buf["state"])[0].permute(2, 0, 1).cpu()           # [B,N,O]
+    with torch.no_grad():
+        p = torch.softmax(om.actor_logits(actor, obs0), -1).mean(dim=(0, 1))
+    freq = torch.bincount(buf["actions"][0].flatten().cpu().long(), minlength=5).float() / (3 * B)
+    assert (freq - p).abs().max() < 0.02
+
+
+# ----------------------------------------------------------------------------------------- whole iteration
+@pytest.mark.parametrize("name,ippo", [("g8_mappo", False), ("g8_mappo_flags", False), ("g8_ippo", True)])
+def test_whole_update_vs_reference_run(cm, golden, name, ippo):
+    """K4+K5(+K6)+3x(K7+K8) from the reference's initial parameters on the reference's batch: per-epoch
+    statistics and the final parameters follow the unmodified reference run."""
+    from cleanmarl_b200 import engine as E
+    g = golden(name)
+    seed, B = int(g["seed"]), int(g["B"])
+    actor, critic = (om.build_networks(seed, state_dim=21, critic_hidden=int(g["critic_hidden_dim"])) if ippo
+                     else om.build_networks(seed))
+    eng = make_engine(cm, B, critic_on_obs=ippo, critic_hidden=int(g["critic_hidden_dim"]))
+    dev = eng.device
+    batch = tuple(T(g[k]) for k in ("obs", "actions", "log_probs", "reward", "states", "avail", "done", "mask"))
+    d = E.to_device_layout(batch, dev)
+    params = flat_params(actor, critic, dev)
+    values = eng.empty(25, eng.n_heads, B)
+    ret, adv = torch.empty_like(values), torch.empty_like(values)
+    stats64 = eng.empty(4, dtype=torch.float64)
+    # (the golden reward is already normalised when the flag is set: RolloutBuffer.get_batch does it)
+    eng.critic_values(params[eng.n_actor:], values, state=d["state"], obs=None)
+    eng.td_lambda(values, d["reward"], ret, adv, float(g["gamma"]), float(g["td_lambda"]), mask=d["mask"])
+    if bool(g["normalize_advantage"]):
+        eng.normalize(adv, eng.n_heads, 1, 0, stats64, mask=d["mask"]); eng.normalize(adv, eng.n_heads, 1, 1, stats64, mask=d["mask"])
+    if bool(g["normalize_return"]):
+        eng.normalize(ret, eng.n_heads, 1, 0, stats64, mask=d["mask"]); eng.normalize(ret, eng.n_heads, 1, 1, stats64, mask=d["mask"])
+    m_ = d["mask"].bool().permute(1, 0).cpu()
+    tol = 1e-5 if not bool(g["normalize_advantage"]) else 2e-6
+    assert (E.heads_to_reference(adv, 3).cpu() - T(g["advantages"]))[m_].abs().max() < tol
+    assert (E.heads_to_reference(ret, 3).cpu() - T(g["return_lambda"]))[m_].abs().max() < tol
+    m, v = torch.zeros_like(params), torch.zeros_like(params)
+    grads, stats = eng.empty(eng.n_params + 8), eng.empty(8)
+    for ep in range(int(g["epochs"])):
+        eng.ppo_epoch_grads(params, grads, state=d["state"], actions=d["actions"], logp_old=d["logp"], adv=adv,
+                            returns=ret, mask=d["mask"], avail=d["avail"], clip=float(g["ppo_clip"]),
+                            ent_coef=float(g["entropy_coef"]))
+        eng.clip_adam_step(params, grads, m, v, step=ep + 1, lr_actor=float(g["lr_actor"]),
+                           lr_critic=float(g["lr_critic"]), max_norm=float(g["clip_gradients"]), stats_out=stats)
+        s = stats.cpu().numpy()
+        ref = [g["actor_losses"][ep], g["critic_losses"][ep], g["entropies"][ep], g["kls"][ep], g["clipfracs"][ep],
+               g["actor_grad_norms"][ep], g["critic_grad_norms"][ep]]
+        for k in (0, 1, 2, 5, 6):
+            assert abs(s[k] - ref[k]) <= 2e-5 * abs(ref[k]) + 1e-7, (ep, k, s[k], ref[k])
+        assert abs(s[3] - ref[3]) < 1e-6 + 1e-3 * abs(ref[3])
+        assert abs(s[4] - ref[4]) < 1e-6
+    final = torch.cat([T(g["actor_final"]), T(g["critic_final"])])
+    # 3 Adam steps of lr 8e-4 move each parameter by <= 2.4e-3; agreement to 1e-6 abs
+    assert (params.cpu() - final).abs().max().item() < 1e-6
+
+
+def test_reward_normalisation(cm):
+    """K6 mode 0 vs RolloutBuffer.get_batch's normalize_reward (MME:143-146)."""
+    B, Tn = 777, 25
+    gen = torch.Generator().manual_seed(2)
+    reward = -torch.rand(B, Tn, generator=gen) * 4
+    mask = ragged_mask(B, Tn, gen)
+    ref = om.normalize_reward_(reward, mask)
+    eng = make_engine(cm, B)
+    dev = eng.device
+    r = reward.permute(1, 0).contiguous().to(dev)
+    st = eng.empty(4, dtype=torch.float64)
+    m = mask.permute(1, 0).contiguous().to(torch.uint8).to(dev)
+    eng.normalize(r, 1, 0, 0, st, mask=m)
+    eng.normalize(r, 1, 0, 1, st, mask=m)
+    out = r.permute(1, 0).cpu()
+    assert (out - ref)[mask].abs().max() < 2e-6
+    assert torch.equal(out[~mask], reward[~mask])
