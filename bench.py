@@ -1,0 +1,394 @@
+"""bench.py -- throughput of the MAPPO multi-env training path (rollout + TD(lambda)/GAE + PPO epochs).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path, host cores
+
+Metric (BASELINE.json): agent-env-steps/s of one full training iteration; a "step" is one iteration =
+B*T*N agent-env-steps.  Workload at N=1: BASELINE.json configs[1] (mappo_multienvs.py, simple_spread_v3,
+3 agents, num_envs=4096); N>1 keeps 4096 envs per GPU (weak scaling, envs sharded, one gradient
+all-reduce per PPO epoch).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+T_STEPS, N_AGENTS, N_ACT = 25, 3, 5
+METRIC = "agent_env_steps_per_sec"
+UNIT = "agent-env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=4096)
+    ap.add_argument("--algo", default="mappo", choices=["mappo", "ippo"])
+    ap.add_argument("--ref-envs", type=int, default=32, help="envs in the reference arm's bounded sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gae-envs", type=int, default=1 << 20, help="envs for the stand-alone GAE roofline probe")
+    return ap.parse_args()
+
+
+def peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.is_file():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"{a.algo}_multienvs.py simple_spread_v3, 3 agents, T=25, num_envs={a.envs_per_gpu * world} "
+                    f"({a.envs_per_gpu}/GPU), 3 PPO epochs, actor 21-32-32-5, critic "
+                    f"{'21-32-32-1 per agent' if a.algo == 'ippo' else '54-64-64-1'}",
+        "global_batch": a.envs_per_gpu * world,
+        "envs_per_gpu": a.envs_per_gpu,
+        "agent_env_steps_per_step": a.envs_per_gpu * world * T_STEPS * N_AGENTS,
+        "parallelism": f"dp{world} (envs sharded, 1 all-reduce of 9678 floats per epoch)" if world > 1 else "single GPU",
+        "l2": "flushed between timed iterations (256 MiB write, outside the per-step event pairs)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_port_iteration(B, seed=1):
+    """One full iteration of the oracle port (reference arithmetic, torch CPU) on B envs; returns seconds."""
+    import numpy as np
+    import torch
+    from oracle import mappo as om
+    from oracle import spread as osp
+    actor, critic = om.build_networks(seed)
+    aopt, copt = om.make_optimizers(actor, critic)
+    rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    pos = rng.uniform(-1, 1, (B, 3, 2)); vel = np.zeros_like(pos); lm = rng.uniform(-1, 1, (B, 3, 2))
+    eps = {k: [] for k in ("obs", "actions", "log_prob", "reward", "states")}
+    ids = np.broadcast_to(np.eye(3), (B, 3, 3))
+    for t in range(T_STEPS):
+        raw = osp.observe_batched(pos, vel, lm)
+        obs = np.concatenate([raw, ids], axis=-1)
+        with torch.no_grad():
+            logits = om.actor_logits(actor, torch.from_numpy(obs).float())
+            a, lp = om.race_sample(logits, om.draw_race_noise(logits.shape))
+        pos, vel, rew = osp.step_batched(pos, vel, lm, a.numpy())
+        eps["obs"].append(obs); eps["actions"].append(a); eps["log_prob"].append(lp)
+        eps["reward"].append(rew[:, 0]); eps["states"].append(raw.reshape(B, 54))
+    obs = torch.from_numpy(np.stack(eps["obs"], 1)).float()
+    states = torch.from_numpy(np.stack(eps["states"], 1)).float()
+    actions = torch.stack(eps["actions"], 1)
+    logp = torch.stack(eps["log_prob"], 1)
+    reward = torch.from_numpy(np.stack(eps["reward"], 1)).float()
+    mask = torch.ones(B, T_STEPS, dtype=torch.bool)
+    avail = torch.ones(B, T_STEPS, 3, 5, dtype=torch.bool)
+    batch = (obs, actions, logp, reward, states, avail, torch.zeros(B, T_STEPS), mask)
+    ret, adv = om.td_lambda_loop(critic, states, reward, mask, 0.99, 0.95, 3)      # the reference's loop form
+    om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(sample_envs=64, reps=2):
+    import torch
+    cpu_port_iteration(8)
+    ts = [cpu_port_iteration(sample_envs) for _ in range(reps)]
+    t = min(ts)
+    return {"value": sample_envs * T_STEPS * N_AGENTS / t, "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"oracle port (reference arithmetic on torch CPU; vectorised numpy env instead of one process "
+                      f"per env), one full iteration on {sample_envs} of the envs, best of {reps}: {t:.2f} s"}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import ref_loader
+    B = a.ref_envs
+    K, W = a.steps, a.warmup
+    # keep the CPU arm inside a few minutes: one reference iteration at B=32 takes ~1.5-3 s on 8 cores
+    K = min(K, 5)
+    W = min(W, 1)
+    cfg = workload_config(a, world)
+    per_step = B * T_STEPS * N_AGENTS
+    script = f"{a.algo}_multienvs.py"
+    if ref_loader.reference_dir() is not None:
+        import tempfile
+        import torch.utils.tensorboard as tb
+
+        stamps = []
+
+        class StampWriter:
+            """Stands in for the TensorBoard writer (a dependency, not reference code): the reference logs
+            train/num_updates exactly once per iteration (MME:612), which gives per-iteration wall clock
+            without touching the script."""
+
+            def __init__(self, *a_, **k_):
+                pass
+
+            def add_scalar(self, tag, *a_, **k_):
+                if tag == "train/num_updates":
+                    stamps.append(time.perf_counter())
+
+            def add_text(self, *a_, **k_):
+                pass
+
+            def close(self):
+                pass
+
+        tb.SummaryWriter = StampWriter
+        iters = max(W, 1) + K
+        argv = ["--env_type", "pz", "--env_name", "simple_spread_v3", "--batch_size", str(B),
+                "--total_timesteps", str(B * T_STEPS * iters), "--eval_steps", "1000000000"]
+        with tempfile.TemporaryDirectory() as tmp:
+            ref_loader.run_script(argv, script=script, cwd=tmp)
+        assert len(stamps) == iters, (len(stamps), iters)
+        dt = (stamps[-1] - stamps[-1 - K]) / K
+        kind = "reference"
+        sample = (f"unmodified {script} from {ref_loader.reference_dir()} (runpy, tyro CLI, one worker process per env) "
+                  f"on oracle/env_stub (numpy simple_spread; PettingZoo not installed), --batch_size {B}, "
+                  f"{K} iterations after {max(W, 1)} warm-up: {dt:.2f} s per iteration")
+    else:
+        ts = [cpu_port_iteration(B) for _ in range(W + K)][W:]
+        dt = sum(ts) / len(ts)
+        kind = "port"
+        sample = f"oracle port, full iteration on {B} envs (reference sources not present on this box)"
+    val = per_step / dt
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": K,
+           "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": sample,
+                            "torch_threads": torch.get_num_threads()},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_b200(a):
+    import torch
+    from cleanmarl_b200.mappo import MAPPO, Args, init_distributed
+    import cleanmarl_b200 as cm
+
+    rank, world, local = init_distributed()
+    if world != a.gpus and rank == 0:
+        print(f"warning: --gpus {a.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = a.envs_per_gpu
+    args = Args(batch_size=B * world, seed=1)
+    tr = MAPPO(args, device_index=local, rank=rank, world_size=world, ippo=(a.algo == "ippo"))
+    eng = tr.engine
+    hbm_peak, sm_max, peak_src = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps, each bracketed by an event pair on the launching stream; L2 flushed in between."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        w0 = time.perf_counter()
+        for s, e in evs:
+            flush.zero_()
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = [s.elapsed_time(e) for s, e in evs]
+        t = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t) / 1e3, wall, ms
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(max(a.warmup, 3)):
+        tr.iteration()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launches
+    secs, wall, ms = timed(tr.iteration, a.steps)
+    launches = eng.launches - l0
+    per_step = B * world * T_STEPS * N_AGENTS
+    value = per_step * a.steps / secs
+
+    # ---- end to end through the public API with HOST inputs (start states + race noise), D2H of results ----
+    env_h = torch.empty(18, B, dtype=torch.float64).uniform_(-1, 1).pin_memory()
+    env_h[6:12] = 0
+    noise_h = torch.empty(T_STEPS, N_AGENTS, N_ACT, B).exponential_(1).pin_memory()
+    env_d = torch.empty_like(env_h, device=dev)
+    noise_d = torch.empty_like(noise_h, device=dev)
+    stats_h = torch.empty(args.epochs, 8).pin_memory()
+    ret_h = torch.empty(B, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        env_d.copy_(env_h, non_blocking=True)
+        noise_d.copy_(noise_h, non_blocking=True)
+        tr.iteration(env_init=env_d, noise=noise_d)
+        stats_h.copy_(tr.epoch_stats, non_blocking=True)
+        ret_h.copy_(tr.buf["ep_return"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()               # the caller reads the results every step
+
+    for _ in range(3):
+        e2e_step()
+    e_secs, e_wall, _ = timed(e2e_step, a.steps)
+    # host-visible time: the results are read on the host every step, so wall clock is the honest number
+    if world > 1:
+        tw = torch.tensor([e_wall], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(tw, op=torch.distributed.ReduceOp.MAX)
+        e_wall = float(tw)
+    clk = clocks.stop() if rank == 0 else None
+    h2d = env_h.numel() * 8 + noise_h.numel() * 4
+    d2h = stats_h.numel() * 4 + ret_h.numel() * 8
+
+    # ---- per-kernel device times over a few iterations (library-internal event pairs) ----
+    eng.timing(True)
+    nb = 5
+    for _ in range(nb):
+        flush.zero_()
+        tr.iteration()
+    kt = eng.read_timing()
+    eng.timing(False)
+    kernels = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / nb, "ms_per_step": v[0] / nb}
+               for k, v in kt.items()}
+    step_kernel_ms = sum(v["ms_per_step"] for v in kernels.values())
+    for v in kernels.values():
+        v["share"] = v["ms_per_step"] / step_kernel_ms
+    # algorithmic bytes / flops per launch (DESIGN.md "kernels"): per env-step figures x B*T
+    bt = B * T_STEPS
+    ippo = a.algo == "ippo"
+    alg = {
+        "ppo_actor_chain": (bt * (216 + 12 + 12 + (12 if ippo else 4)), bt * 3 * 9792),
+        "ppo_critic_chain": (bt * (216 + (12 if ippo else 4)), bt * (27072 if ippo else 38784)),
+        "critic_values": (bt * (216 + (12 if ippo else 4)), bt * (3 * 3456 if ippo else 15232)),
+        "rollout": (bt * (216 + 12 + 12 + 4), bt * 3 * 3712),
+        "td_lambda_scan": (bt * 16 * (3 if ippo else 1), bt * 6),
+    }
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12            # TFLOP/s FFMA at max clock
+    for k, (by, fl) in alg.items():
+        if k in kernels:
+            t = kernels[k]["ms_per_launch"] * 1e-3
+            kernels[k].update({"alg_bytes": by, "alg_flops": fl, "gbs": by / t / 1e9, "tflops": fl / t / 1e12,
+                               "hbm_frac": by / t / 1e9 / hbm_peak, "fp32_frac": fl / t / 1e12 / fp32_peak})
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom].get("gbs"), "peak": hbm_peak, "unit": "GB/s",
+                "frac": kernels[dom].get("hbm_frac"), "traffic": None, "peak_source": peak_src,
+                "note": "the dominant kernel is an fp32 FFMA-bound fused MLP fwd+bwd (~160 FLOP/B); its "
+                        "compute-side fraction is fp32_frac in `kernels`; the HBM-bound GAE kernel is `gae_roofline`",
+                "fp32_tflops": kernels[dom].get("tflops"), "fp32_peak_tflops": fp32_peak,
+                "fp32_frac": kernels[dom].get("fp32_frac")}
+
+    # ---- stand-alone GAE scan at a size that leaves L2 (the metric BASELINE.json names) ----
+    gae = None
+    if rank == 0 and a.gae_envs > 0:
+        Bg = a.gae_envs
+        e2 = cm.Engine(cm.Shapes(n_envs=Bg), local)
+        v = torch.randn(T_STEPS, 1, Bg, device=dev); r = torch.randn(T_STEPS, Bg, device=dev)
+        R = torch.empty_like(v); A = torch.empty_like(v)
+        for _ in range(3):
+            e2.td_lambda(v, r, R, A, 0.99, 0.95)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for s, e in evs:
+            flush.zero_()
+            s.record(); e2.td_lambda(v, r, R, A, 0.99, 0.95); e.record()
+        torch.cuda.synchronize()
+        tg = statistics.median(s.elapsed_time(e) for s, e in evs) * 1e-3
+        by = 16 * Bg * T_STEPS
+        gae = {"kernel": "td_lambda_scan", "bound": "hbm", "envs": Bg, "alg_bytes": by, "ms": tg * 1e3,
+               "achieved": by / tg / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": by / tg / 1e9 / hbm_peak,
+               "note": "16 B per env-step (r, V in; R, A out), inputs larger than L2 (419 MB), L2 flushed"}
+        e2.close()
+        del v, r, R, A
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        cfg = workload_config(a, world)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+               "ms_per_step": secs / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": cfg,
+               "e2e": {"value": per_step * a.steps / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "ms_per_step": e_wall / a.steps * 1e3,
+                       "device_ms_per_step": e_secs / a.steps * 1e3,
+                       "inputs": "start states f64 [18][B] + Exp(1) race noise f32 [T][N][A][B] from pinned host "
+                                 "memory every step; D2H: per-epoch stats + per-env episode return"},
+               "gpu_launches": launches, "clocks": clk, "roofline": roofline, "gae_roofline": gae,
+               "kernels": kernels, "cpu_baseline": cpu, "wall_ms_per_step": wall / a.steps * 1e3}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -33,7 +33,12 @@ _SIGNATURES = {
     "cmarl_value_heads": (C.c_int, [_P]),
     "cmarl_workspace_bytes": (C.c_size_t, [_P]),
     "cmarl_launch_count": (C.c_int, [_P]),
+    "cmarl_timing_enable": (C.c_int, [_P, C.c_int]),
+    "cmarl_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "cmarl_kernel_name": (C.c_char_p, [C.c_int]),
     "cmarl_env_reset": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
+    "cmarl_env_observe": (C.c_int, [_P, _P, _P, _P]),
+    "cmarl_env_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "cmarl_rollout": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P, _P]),
     "cmarl_actor_act": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cmarl_critic_values": (C.c_int, [_P, _P, _P, _P, _P, _P]),

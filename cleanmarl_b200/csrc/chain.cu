@@ -428,7 +428,7 @@ extern "C" int cmarl_critic_values(cmarl_ctx* ctx, const float* critic_params, c
     const int kin = nd.in_rows <= 24 ? 24 : 56;
     const int units = units_of(src, tile_m(ctx->cfg.critic_hidden, kin));
     const int grid = units < ctx->sm_count ? units : ctx->sm_count;
-    ctx->launches++;
+    KernelTimer kt(ctx, K_CRITIC, as_stream(stream));
     return dispatch<ValueHead, false>(ctx, ctx->cfg.critic_hidden, nd, src, ha, nullptr, 0, grid, as_stream(stream));
 }
 
@@ -453,7 +453,11 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     pa.clip = (float)clip; pa.ent_coef = (float)ent_coef; pa.inv_groups = 1.0f / (float)c.n_agents;
     const int ua = units_of(srca, tile_m(c.actor_hidden, 24));
     const int grid_a = ua < ctx->sm_count ? ua : ctx->sm_count;
-    int e = dispatch<PolicyHead, true>(ctx, c.actor_hidden, nda, srca, pa, part_a, Pa, grid_a, st);
+    int e;
+    {
+        KernelTimer kt(ctx, K_PPO_ACTOR, st);
+        e = dispatch<PolicyHead, true>(ctx, c.actor_hidden, nda, srca, pa, part_a, Pa, grid_a, st);
+    }
     if (e) return e;
 
     NetDesc ndc; TileSrc srcc;
@@ -463,12 +467,17 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     const int kin = ndc.in_rows <= 24 ? 24 : 56;
     const int uc = units_of(srcc, tile_m(c.critic_hidden, kin));
     const int grid_c = uc < ctx->sm_count ? uc : ctx->sm_count;
-    e = dispatch<ValueHead, true>(ctx, c.critic_hidden, ndc, srcc, va, part_c, Pc, grid_c, st);
+    {
+        KernelTimer kt(ctx, K_PPO_CRITIC, st);
+        e = dispatch<ValueHead, true>(ctx, c.critic_hidden, ndc, srcc, va, part_c, Pc, grid_c, st);
+    }
     if (e) return e;
 
     const int n_out = Pa + Pc + CMARL_N_STATS;
-    reduce_partials_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(part_a, grid_a, Pa, part_c, grid_c, Pc,
-                                                                 (float)c.n_agents, grads_out);
-    ctx->launches += 3;
+    {
+        KernelTimer kt(ctx, K_PPO_REDUCE, st);
+        reduce_partials_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(part_a, grid_a, Pa, part_c, grid_c, Pc,
+                                                                     (float)c.n_agents, grads_out);
+    }
     return cmarl_check_cuda(cudaGetLastError(), "reduce_partials_kernel");
 }

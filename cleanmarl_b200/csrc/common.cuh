@@ -27,6 +27,18 @@ struct NetLayout {
     }
 };
 
+enum KernelId { K_RESET = 0, K_ENVSTEP, K_ROLLOUT, K_ACT, K_CRITIC, K_TD, K_NORM, K_PPO_ACTOR, K_PPO_CRITIC,
+                K_PPO_REDUCE, K_ADAM };
+static_assert(K_ADAM + 1 == CMARL_NK, "kernel id table");
+constexpr int CMARL_TIMING_POOL = 256;
+
+struct cmarl_timing {
+    cudaEvent_t ev[CMARL_NK][CMARL_TIMING_POOL][2];
+    int n[CMARL_NK];
+    double sum_ms[CMARL_NK];
+    long long count[CMARL_NK];
+};
+
 struct cmarl_ctx {
     cmarl_config cfg;
     NetLayout actor, critic;
@@ -35,6 +47,18 @@ struct cmarl_ctx {
     int sm_count;
     int ppo_grid_actor, ppo_grid_critic;
     int launches;
+    int timing_on;
+    cmarl_timing* timing;
+};
+
+void cmarl_time_begin(cmarl_ctx* ctx, int id, cudaStream_t st);
+void cmarl_time_end(cmarl_ctx* ctx, int id, cudaStream_t st);
+
+// RAII bracket used at every launch site
+struct KernelTimer {
+    cmarl_ctx* ctx; int id; cudaStream_t st;
+    KernelTimer(cmarl_ctx* c, int i, cudaStream_t s) : ctx(c), id(i), st(s) { ctx->launches++; if (ctx->timing_on) cmarl_time_begin(ctx, id, st); }
+    ~KernelTimer() { if (ctx->timing_on) cmarl_time_end(ctx, id, st); }
 };
 
 void cmarl_set_error(const char* fmt, ...);

@@ -63,7 +63,76 @@ extern "C" int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out) {
     return 0;
 }
 
+static void timing_drain(cmarl_ctx* ctx) {
+    cmarl_timing* t = ctx->timing;
+    if (!t) return;
+    cudaDeviceSynchronize();
+    for (int k = 0; k < CMARL_NK; ++k) {
+        for (int i = 0; i < t->n[k]; ++i) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, t->ev[k][i][0], t->ev[k][i][1]) == cudaSuccess) {
+                t->sum_ms[k] += ms;
+                t->count[k] += 1;
+            }
+        }
+        t->n[k] = 0;
+    }
+}
+
+void cmarl_time_begin(cmarl_ctx* ctx, int id, cudaStream_t st) {
+    cmarl_timing* t = ctx->timing;
+    if (t->n[id] == CMARL_TIMING_POOL) timing_drain(ctx);
+    cudaEvent_t* e = t->ev[id][t->n[id]];
+    if (!e[0]) { cudaEventCreate(&e[0]); cudaEventCreate(&e[1]); }
+    cudaEventRecord(e[0], st);
+}
+
+void cmarl_time_end(cmarl_ctx* ctx, int id, cudaStream_t st) {
+    cmarl_timing* t = ctx->timing;
+    cudaEventRecord(t->ev[id][t->n[id]][1], st);
+    t->n[id]++;
+}
+
+extern "C" int cmarl_timing_enable(cmarl_ctx* ctx, int on) {
+    CMARL_ARG(ctx, "null ctx");
+    if (on && !ctx->timing) {
+        ctx->timing = (cmarl_timing*)calloc(1, sizeof(cmarl_timing));
+        CMARL_ARG(ctx->timing, "out of host memory");
+    }
+    if (!on && ctx->timing_on) timing_drain(ctx);
+    ctx->timing_on = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int cmarl_timing_read(cmarl_ctx* ctx, double* sum_ms, int64_t* launches) {
+    CMARL_ARG(ctx && sum_ms && launches, "null argument");
+    for (int k = 0; k < CMARL_NK; ++k) { sum_ms[k] = 0.0; launches[k] = 0; }
+    if (!ctx->timing) return 0;
+    timing_drain(ctx);
+    for (int k = 0; k < CMARL_NK; ++k) {
+        sum_ms[k] = ctx->timing->sum_ms[k];
+        launches[k] = ctx->timing->count[k];
+        ctx->timing->sum_ms[k] = 0.0;
+        ctx->timing->count[k] = 0;
+    }
+    return 0;
+}
+
+extern "C" const char* cmarl_kernel_name(int id) {
+    static const char* names[CMARL_NK] = {"env_reset", "env_step", "rollout", "actor_act", "critic_values",
+                                          "td_lambda_scan", "normalize", "ppo_actor_chain", "ppo_critic_chain",
+                                          "ppo_reduce_partials", "clip_adam"};
+    return (id >= 0 && id < CMARL_NK) ? names[id] : "?";
+}
+
 extern "C" int cmarl_ctx_destroy(cmarl_ctx* ctx) {
+    if (ctx && ctx->timing) {
+        for (int k = 0; k < CMARL_NK; ++k)
+            for (int i = 0; i < CMARL_TIMING_POOL; ++i)
+                for (int j = 0; j < 2; ++j)
+                    if (ctx->timing->ev[k][i][j]) cudaEventDestroy(ctx->timing->ev[k][i][j]);
+        free(ctx->timing);
+    }
     free(ctx);
     return 0;
 }

@@ -77,9 +77,11 @@ extern "C" int cmarl_td_lambda(cmarl_ctx* ctx, const float* values, const float*
     const int n = V * B;
     // python-float coefficients rounded to fp32 when they meet an fp32 tensor (MME:496-501)
     const float g = (float)gamma, l = (float)lambda, oml = (float)(1.0 - lambda);
-    td_lambda_kernel<5><<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(values, reward, mask, returns, adv,
-                                                                        T, V, B, g, l, oml);
-    ctx->launches++;
+    {
+        KernelTimer kt(ctx, K_TD, as_stream(stream));
+        td_lambda_kernel<5><<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(values, reward, mask, returns, adv,
+                                                                            T, V, B, g, l, oml);
+    }
     return cmarl_check_cuda(cudaGetLastError(), "td_lambda_kernel");
 }
 
@@ -149,6 +151,7 @@ extern "C" int cmarl_normalize(cmarl_ctx* ctx, float* x, int32_t n_heads, const 
     CMARL_ARG(n_heads >= 1 && (mode == 0 || mode == 1) && (phase == 0 || phase == 1), "bad mode/phase/heads");
     const int T = ctx->cfg.n_steps, B = ctx->cfg.n_envs;
     cudaStream_t st = as_stream(stream);
+    KernelTimer kt(ctx, K_NORM, st);
     if (phase == 0) {
         CMARL_CUDA(cudaMemsetAsync(stats_io, 0, 4 * sizeof(double), st));
         int grid = ceil_div(T * B, 256);
@@ -159,7 +162,6 @@ extern "C" int cmarl_normalize(cmarl_ctx* ctx, float* x, int32_t n_heads, const 
         if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
         norm_apply_kernel<<<grid, 256, 0, st>>>(x, mask, T, n_heads, B, mode, stats_io);
     }
-    ctx->launches++;
     return cmarl_check_cuda(cudaGetLastError(), "normalize kernel");
 }
 
@@ -280,7 +282,9 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     }
     a.tensor_off[12] = base;
     a.lr[0] = lr_actor; a.lr[1] = lr_critic; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
-    clip_adam_kernel<<<1, 1024, 0, as_stream(stream)>>>(a);
-    ctx->launches++;
+    {
+        KernelTimer kt(ctx, K_ADAM, as_stream(stream));
+        clip_adam_kernel<<<1, 1024, 0, as_stream(stream)>>>(a);
+    }
     return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
 }

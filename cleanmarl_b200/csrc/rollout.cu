@@ -307,6 +307,45 @@ __global__ void __launch_bounds__(256) env_reset_kernel(double* __restrict__ env
     }
 }
 
+// ---- K1 alone: observe / single step, one thread per env -------------------------------------
+__global__ void __launch_bounds__(128) env_step_kernel(double* __restrict__ env, const int32_t* __restrict__ actions,
+                                                       float* __restrict__ state_out, float* __restrict__ reward_out,
+                                                       int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double p[6], v[6], lm[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        p[i] = env[(size_t)i * B + b]; v[i] = env[(size_t)(6 + i) * B + b]; lm[i] = env[(size_t)(12 + i) * B + b];
+    }
+    if (actions) {
+        double np_[6], nv[6];
+#pragma unroll
+        for (int n = 0; n < NAG; ++n) {
+            double fx, fy;
+            spread::agent_force(n, p, actions[(size_t)n * B + b], fx, fy);
+            double px = p[2 * n], py = p[2 * n + 1], vx = v[2 * n], vy = v[2 * n + 1];
+            spread::integrate(px, py, vx, vy, fx, fy);
+            np_[2 * n] = px; np_[2 * n + 1] = py; nv[2 * n] = vx; nv[2 * n + 1] = vy;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            p[i] = np_[i]; v[i] = nv[i];
+            env[(size_t)i * B + b] = p[i]; env[(size_t)(6 + i) * B + b] = v[i];
+        }
+        if (reward_out) reward_out[b] = (float)spread::reward_agent0(p, lm);
+    }
+    if (state_out) {
+#pragma unroll
+        for (int n = 0; n < NAG; ++n) {
+            float x[CMARL_RAW_OBS];
+            spread::observe(n, p, v, lm, x);
+#pragma unroll
+            for (int k = 0; k < CMARL_RAW_OBS; ++k) state_out[(size_t)(n * CMARL_RAW_OBS + k) * B + b] = x[k];
+        }
+    }
+}
+
 template <int H>
 size_t actor_smem_bytes() { return (size_t)ActorSmem<H>::oEnd * sizeof(float); }
 
@@ -315,9 +354,33 @@ size_t actor_smem_bytes() { return (size_t)ActorSmem<H>::oEnd * sizeof(float); }
 extern "C" int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, void* stream) {
     CMARL_ARG(ctx && env, "null argument");
     const int B = ctx->cfg.n_envs;
-    env_reset_kernel<<<ceil_div(B, 256), 256, 0, as_stream(stream)>>>(env, B, seed, episode);
-    ctx->launches++;
+    {
+        KernelTimer kt(ctx, K_RESET, as_stream(stream));
+        env_reset_kernel<<<ceil_div(B, 256), 256, 0, as_stream(stream)>>>(env, B, seed, episode);
+    }
     return cmarl_check_cuda(cudaGetLastError(), "env_reset_kernel");
+}
+
+extern "C" int cmarl_env_observe(cmarl_ctx* ctx, const double* env, float* state_out, void* stream) {
+    CMARL_ARG(ctx && env && state_out, "null argument");
+    const int B = ctx->cfg.n_envs;
+    {
+        KernelTimer kt(ctx, K_ENVSTEP, as_stream(stream));
+        env_step_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(const_cast<double*>(env), nullptr, state_out,
+                                                                        nullptr, B);
+    }
+    return cmarl_check_cuda(cudaGetLastError(), "env_step_kernel(observe)");
+}
+
+extern "C" int cmarl_env_step(cmarl_ctx* ctx, double* env, const int32_t* actions, float* state_out,
+                              float* reward_out, void* stream) {
+    CMARL_ARG(ctx && env && actions, "null argument");
+    const int B = ctx->cfg.n_envs;
+    {
+        KernelTimer kt(ctx, K_ENVSTEP, as_stream(stream));
+        env_step_kernel<<<ceil_div(B, 128), 128, 0, as_stream(stream)>>>(env, actions, state_out, reward_out, B);
+    }
+    return cmarl_check_cuda(cudaGetLastError(), "env_step_kernel");
 }
 
 extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* env, const float* noise,
@@ -331,13 +394,14 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
     const int grid = ceil_div(a.B, EPB);
     cudaStream_t st = as_stream(stream);
     if (ctx->cfg.actor_hidden == 32) {
+        KernelTimer kt(ctx, K_ROLLOUT, st);
         rollout_kernel<32><<<grid, RT, actor_smem_bytes<32>(), st>>>(a);
     } else {
         CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)actor_smem_bytes<64>()));
+        KernelTimer kt(ctx, K_ROLLOUT, st);
         rollout_kernel<64><<<grid, RT, actor_smem_bytes<64>(), st>>>(a);
     }
-    ctx->launches++;
     return cmarl_check_cuda(cudaGetLastError(), "rollout_kernel");
 }
 
@@ -350,12 +414,13 @@ extern "C" int cmarl_actor_act(cmarl_ctx* ctx, const float* actor_params, const 
     const int grid = ceil_div(a.B, EPB);
     cudaStream_t st = as_stream(stream);
     if (ctx->cfg.actor_hidden == 32) {
+        KernelTimer kt(ctx, K_ACT, st);
         actor_act_kernel<32><<<grid, RT, actor_smem_bytes<32>(), st>>>(a);
     } else {
         CMARL_CUDA(cudaFuncSetAttribute(actor_act_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)actor_smem_bytes<64>()));
+        KernelTimer kt(ctx, K_ACT, st);
         actor_act_kernel<64><<<grid, RT, actor_smem_bytes<64>(), st>>>(a);
     }
-    ctx->launches++;
     return cmarl_check_cuda(cudaGetLastError(), "actor_act_kernel");
 }

@@ -82,6 +82,17 @@ class Engine:
     def launches(self) -> int:
         return self.lib.cmarl_launch_count(self._h)
 
+    def timing(self, on: bool):
+        _lib.check(self.lib.cmarl_timing_enable(self._h, int(on)), "cmarl_timing_enable")
+
+    def read_timing(self) -> dict:
+        """{kernel name: (total ms, launches)} since the last read (synchronises the device)."""
+        nk = 11
+        ms = (C.c_double * nk)()
+        cnt = (C.c_int64 * nk)()
+        _lib.check(self.lib.cmarl_timing_read(self._h, ms, cnt), "cmarl_timing_read")
+        return {self.lib.cmarl_kernel_name(k).decode(): (ms[k], cnt[k]) for k in range(nk) if cnt[k]}
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -111,6 +122,16 @@ class Engine:
     def env_reset(self, env, seed: int, episode: int):
         _lib.check(self.lib.cmarl_env_reset(self._h, _ptr(env, torch.float64, self.device, "env"),
                                             seed & (2**64 - 1), episode & (2**64 - 1), self._stream()), "cmarl_env_reset")
+
+    def env_observe(self, env, state_out):
+        _lib.check(self.lib.cmarl_env_observe(self._h, _ptr(env, torch.float64, self.device, "env"),
+                                              self._f(state_out, "state_out"), self._stream()), "cmarl_env_observe")
+
+    def env_step(self, env, actions, state_out=None, reward_out=None):
+        _lib.check(self.lib.cmarl_env_step(self._h, _ptr(env, torch.float64, self.device, "env"),
+                                           _ptr(actions, torch.int32, self.device, "actions"),
+                                           self._f(state_out, "state_out"), self._f(reward_out, "reward_out"),
+                                           self._stream()), "cmarl_env_step")
 
     def rollout(self, actor_params, env, state, actions, logp, reward, *, noise=None, obs=None, ep_return=None,
                 seed=0, episode=0):

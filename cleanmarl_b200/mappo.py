@@ -1,0 +1,336 @@
+"""Host-side mirror of the reference's in-file objects for the MAPPO / IPPO multi-env path.
+
+Reference: ``cleanmarl/mappo_multienvs.py`` (MME) and ``cleanmarl/ippo_multienvs.py``.
+  Args            <- MME:18-79 (same fields, same defaults except ``device``)
+  SpreadVecEnv    <- env duck-type ``cleanmarl/env/common_interface.py:5-23`` with a leading env axis,
+                     backed by the device simple_spread_v3 kernel instead of one process per env
+                     (MME:246-285, 299-319)
+  ActorCritic     <- ``Actor`` / ``Critic`` (MME:160-200) as one flat device parameter vector with the
+                     reference's initialisation (MME:291-294, 329-339)
+  MAPPO           <- the body of the ``while step < total_timesteps`` loop (MME:379-612)
+
+Only orchestration lives here; every number is produced by a kernel of libcmarl_b200.so.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from .engine import Engine, Shapes, obs_from_state, to_reference_layout
+
+
+@dataclass
+class Args:
+    env_type: str = "pz"
+    """ Pettingzoo only (the reference also lists smaclite / lbf; not built here) """
+    env_name: str = "simple_spread_v3"
+    """ Name of the environment"""
+    env_family: str = "mpe"
+    """ Env family when using pz"""
+    agent_ids: bool = True
+    """ Include id (one-hot vector) at the agent of the observations"""
+    batch_size: int = 3
+    """ Number of episodes to collect in each rollout (= number of parallel device envs)"""
+    actor_hidden_dim: int = 32
+    """ Hidden dimension of actor network"""
+    actor_num_layers: int = 1
+    """ Number of hidden layers of actor network"""
+    critic_hidden_dim: int = 64
+    """ Hidden dimension of critic network"""
+    critic_num_layers: int = 1
+    """ Number of hidden layers of critic network"""
+    optimizer: str = "Adam"
+    """ The optimizer"""
+    learning_rate_actor: float = 0.0008
+    """ Learning rate for the actor"""
+    learning_rate_critic: float = 0.0008
+    """ Learning rate for the critic"""
+    total_timesteps: int = 1000000
+    """ Total steps in the environment during training"""
+    gamma: float = 0.99
+    """ Discount factor"""
+    td_lambda: float = 0.95
+    """ TD(lambda) discount factor"""
+    normalize_reward: bool = False
+    """ Normalize the rewards if True"""
+    normalize_advantage: bool = False
+    """ Normalize the advantage if True"""
+    normalize_return: bool = False
+    """ Normalize the returns if True"""
+    epochs: int = 3
+    """ Number of training epochs"""
+    ppo_clip: float = 0.2
+    """ PPO clipping factor """
+    entropy_coef: float = 0.001
+    """ Entropy coefficient """
+    clip_gradients: float = -1
+    """ 0< for no clipping and 0> if clipping at clip_gradients"""
+    log_every: int = 10
+    """ Logging steps """
+    eval_steps: int = 50
+    """ Evaluate the policy each eval_steps training steps"""
+    num_eval_ep: int = 10
+    """ Number of evaluation episodes"""
+    use_wnb: bool = False
+    """ Logging to Weights & Biases if True"""
+    wnb_project: str = ""
+    """ Weights & Biases project name"""
+    wnb_entity: str = ""
+    """ Weights & Biases entity name"""
+    device: str = "cuda"
+    """ Device: cuda only (the reference defaults to cpu; this implementation has no CPU path)"""
+    seed: int = 1
+    """ Random seed"""
+
+
+def validate_args(args: Args):
+    """Fail loudly at start-up on anything the device path does not implement (no fallbacks)."""
+    if args.env_type != "pz" or args.env_family != "mpe" or args.env_name != "simple_spread_v3":
+        raise SystemExit(f"cleanmarl_b200 only implements --env_type pz --env_family mpe --env_name simple_spread_v3 "
+                         f"(got {args.env_type}/{args.env_family}/{args.env_name})")
+    if not str(args.device).startswith("cuda"):
+        raise SystemExit(f"--device {args.device}: cleanmarl_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    if args.optimizer != "Adam":
+        raise SystemExit("only --optimizer Adam is implemented")
+    if args.actor_num_layers != 1 or args.critic_num_layers != 1:
+        raise SystemExit("only *_num_layers 1 (the reference default) is implemented")
+    if args.batch_size < 1 or args.epochs < 1:
+        raise SystemExit("batch_size and epochs must be positive")
+
+
+# ---------------------------------------------------------------------------------------------
+class ActorCritic:
+    """Flat parameter vector [actor | critic] with the reference's init.
+
+    ``torch.manual_seed(seed)`` followed by the ``nn.Linear`` constructors in the order of
+    MME:329-339 (actor layers, then critic layers) reproduces the reference's parameters bit for
+    bit; layout = ``module.parameters()`` order (W1, b1, W2, b2, W3, b3 per network).
+    """
+
+    def __init__(self, engine: Engine, seed: int | None):
+        s = engine.shapes
+        if seed is not None:
+            torch.manual_seed(seed)
+        critic_in = s.obs_dim if s.critic_on_obs else s.state_dim
+        dims_a = [s.obs_dim] + [s.actor_hidden] * (s.actor_layers + 1) + [s.n_actions]
+        dims_c = [critic_in] + [s.critic_hidden] * (s.critic_layers + 1) + [1]
+        flat = []
+        for dims in (dims_a, dims_c):
+            for i in range(len(dims) - 1):
+                lin = nn.Linear(dims[i], dims[i + 1])
+                flat += [lin.weight.detach().reshape(-1), lin.bias.detach().reshape(-1)]
+        flat = torch.cat(flat)
+        assert flat.numel() == engine.n_params
+        self.engine = engine
+        self.flat = flat.to(engine.device).contiguous()
+        self.n_actor = engine.n_actor
+
+    @property
+    def actor(self):
+        return self.flat[:self.n_actor]
+
+    @property
+    def critic(self):
+        return self.flat[self.n_actor:]
+
+
+class SpreadVecEnv:
+    """B device-resident simple_spread_v3 envs behind the reference's env duck-type
+    (``env/common_interface.py:5-23``), with a leading env axis and tensors that stay in HBM."""
+
+    def __init__(self, engine: Engine, agent_ids: bool = True, seed: int = 0):
+        self.engine = engine
+        s = engine.shapes
+        self.n_agents = s.n_agents
+        self.n_envs = s.n_envs
+        self.agent_ids = agent_ids
+        self.seed = seed
+        self.episode = 0
+        self.env = engine.empty(18, s.n_envs, dtype=torch.float64)
+        self._state = engine.empty(s.state_dim, s.n_envs)
+        self._reward = engine.empty(s.n_envs)
+        self.steps = 0
+
+    def get_obs_size(self):
+        return 18 + self.agent_ids * self.n_agents
+
+    def get_state_size(self):
+        return 18 * self.n_agents
+
+    def get_action_size(self):
+        return 5
+
+    def get_avail_actions(self):
+        return torch.ones(self.n_envs, self.n_agents, 5, dtype=torch.bool, device=self.engine.device)
+
+    def get_state(self):
+        return self._state.t()                                   # [B, 54]
+
+    def _obs(self):
+        o = obs_from_state(self._state[None], self.n_agents, self.agent_ids)[0]     # [N][O][B]
+        return o.permute(2, 0, 1)                                # [B, N, O]
+
+    def reset(self, seed=None):
+        if seed is not None:
+            self.seed = seed
+        self.engine.env_reset(self.env, self.seed, self.episode)
+        self.episode += 1
+        self.steps = 0
+        self.engine.env_observe(self.env, self._state)
+        return self._obs(), {}
+
+    def step(self, actions):
+        """actions int [B, N] -> (obs [B,N,O], reward [B], done, truncated, info)"""
+        a = actions.to(torch.int32).t().contiguous()
+        self.engine.env_step(self.env, a, self._state, self._reward)
+        self.steps += 1
+        return self._obs(), self._reward.clone(), False, self.steps >= self.engine.shapes.n_steps, {}
+
+    def sample(self):
+        return torch.randint(0, 5, (self.n_envs, self.n_agents), device=self.engine.device)
+
+    def close(self):
+        pass
+
+
+# ---------------------------------------------------------------------------------------------
+class MAPPO:
+    """One trainer per GPU (one process per GPU).  ``iteration()`` = one pass of the reference's
+    outer loop: rollout (MME:380-453) -> TD(lambda) (MME:484-512) -> ``epochs`` x [loss + grads
+    (MME:522-582), gradient all-reduce across GPUs, clip + Adam (MME:584-594)]."""
+
+    def __init__(self, args: Args, device_index: int = 0, rank: int = 0, world_size: int = 1, ippo: bool = False,
+                 process_group=None):
+        validate_args(args)
+        if args.batch_size % world_size:
+            raise SystemExit(f"--batch_size {args.batch_size} must be divisible by the number of GPUs {world_size}")
+        self.args, self.rank, self.world, self.ippo, self.pg = args, rank, world_size, ippo, process_group
+        self.B = args.batch_size // world_size
+        self.T = 25                                              # simple_spread_v3 max_cycles (kwargs = {}, MME:297)
+        shapes = Shapes(n_envs=self.B, n_steps=self.T, obs_dim=18 + 3 * bool(args.agent_ids),
+                        actor_hidden=args.actor_hidden_dim, actor_layers=args.actor_num_layers,
+                        critic_hidden=args.critic_hidden_dim, critic_layers=args.critic_num_layers,
+                        critic_on_obs=ippo)
+        self.engine = eng = Engine(shapes, device_index)
+        self.net = ActorCritic(eng, args.seed)                   # identical on every rank (same seed)
+        self.exp_avg = torch.zeros_like(self.net.flat)
+        self.exp_avg_sq = torch.zeros_like(self.net.flat)
+        self.adam_step = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        self.grads = eng.empty(eng.n_params + 8)
+        self.epoch_stats = eng.empty(args.epochs, 8)
+        self.norm_stats = eng.empty(4, dtype=torch.float64)
+        self.buf = eng.alloc_rollout()
+        self.env = eng.empty(18, self.B, dtype=torch.float64)
+        # every rank draws from its own Philox key so shards are independent
+        self.rng_key = (args.seed + 0x9E3779B97F4A7C15 * (rank + 1)) & (2**64 - 1)
+        self.episode = 0
+        self.step = 0                                            # env steps over all GPUs (MME:435)
+        self.training_step = 0
+        self.num_episodes = 0
+
+    # -- rollout -------------------------------------------------------------------------------
+    def collect(self, env_init=None, noise=None):
+        """MME:380-458.  ``env_init`` f64 [18][B] / ``noise`` f32 [T][N][A][B] make the rollout a
+        function of its inputs (parity, end-to-end benchmark); default: device Philox draws."""
+        eng, buf = self.engine, self.buf
+        if env_init is None:
+            eng.env_reset(self.env, self.rng_key, self.episode)
+        else:
+            self.env.copy_(env_init, non_blocking=True)
+        eng.rollout(self.net.actor, self.env, buf["state"], buf["actions"], buf["logp"], buf["reward"], noise=noise,
+                    ep_return=buf["ep_return"], seed=self.rng_key, episode=self.episode)
+        self.episode += 1
+        self.step += self.B * self.T * self.world
+        self.num_episodes += self.B * self.world
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.pg)
+
+    def _normalize(self, x, heads, mode):
+        eng = self.engine
+        eng.normalize(x, heads, mode, 0, self.norm_stats)
+        self._allreduce(self.norm_stats)                         # global statistics (MME:143-146, 505-512)
+        eng.normalize(x, heads, mode, 1, self.norm_stats)
+
+    # -- returns -------------------------------------------------------------------------------
+    def advantages(self):
+        """MME:143-146 (reward normalisation happens at collate time) then MME:484-512."""
+        eng, buf, a = self.engine, self.buf, self.args
+        if a.normalize_reward:
+            self._normalize(buf["reward"], 1, 0)
+        eng.critic_values(self.net.critic, buf["values"], state=buf["state"])
+        eng.td_lambda(buf["values"], buf["reward"], buf["returns"], buf["adv"], a.gamma, a.td_lambda)
+        if a.normalize_advantage:
+            self._normalize(buf["adv"], eng.n_heads, 1)
+        if a.normalize_return:
+            self._normalize(buf["returns"], eng.n_heads, 1)
+
+    # -- PPO epochs ----------------------------------------------------------------------------
+    def update(self):
+        """MME:521-603: one NCCL all-reduce of the flat gradient (+8 statistics) per epoch."""
+        eng, buf, a = self.engine, self.buf, self.args
+        for ep in range(a.epochs):
+            eng.ppo_epoch_grads(self.net.flat, self.grads, state=buf["state"], actions=buf["actions"],
+                                logp_old=buf["logp"], adv=buf["adv"], returns=buf["returns"], clip=a.ppo_clip,
+                                ent_coef=a.entropy_coef)
+            self._allreduce(self.grads)
+            eng.clip_adam_step(self.net.flat, self.grads, self.exp_avg, self.exp_avg_sq, step_dev=self.adam_step,
+                               lr_actor=a.learning_rate_actor, lr_critic=a.learning_rate_critic,
+                               max_norm=a.clip_gradients, stats_out=self.epoch_stats[ep])
+            self.training_step += 1
+
+    def iteration(self, env_init=None, noise=None):
+        self.collect(env_init, noise)
+        self.advantages()
+        self.update()
+
+    # -- read-backs (each is one small D2H copy; nothing else synchronises) ---------------------
+    def train_scalars(self) -> dict:
+        """Means over the epochs of the scalars logged at MME:605-612."""
+        s = self.epoch_stats.mean(dim=0).cpu()
+        keys = ("actor_loss", "critic_loss", "entropy", "kl_divergence", "clipped_ratios", "actor_gradients",
+                "critic_gradients")
+        return {k: float(s[i]) for i, k in enumerate(keys)}
+
+    def rollout_scalars(self) -> dict:
+        r = self.buf["ep_return"]
+        tot = torch.stack([r.sum(), (r * r).sum()])
+        self._allreduce(tot)
+        n = self.B * self.world
+        mean = float(tot[0]) / n
+        return {"ep_reward": mean, "ep_length": float(self.T)}
+
+    def get_batch(self):
+        """The reference's ``RolloutBuffer.get_batch()`` 8-tuple (MME:148-157) for the last rollout."""
+        return to_reference_layout(self.buf, 3, 5, bool(self.args.agent_ids))
+
+
+def evaluate(trainer: MAPPO, num_episodes: int, seed: int):
+    """MME:614-644: ``num_eval_ep`` episodes with the *sampling* policy (``actor.act``), run as
+    ``num_eval_ep`` parallel device envs.  Returns (mean, std, length) of the episode reward."""
+    s = trainer.engine.shapes
+    eng = Engine(Shapes(n_envs=num_episodes, n_steps=s.n_steps, obs_dim=s.obs_dim, actor_hidden=s.actor_hidden,
+                        critic_hidden=s.critic_hidden, critic_on_obs=s.critic_on_obs), trainer.engine.device.index)
+    buf = eng.alloc_rollout()
+    env = eng.empty(18, num_episodes, dtype=torch.float64)
+    eng.env_reset(env, seed, 0)
+    eng.rollout(trainer.net.actor, env, buf["state"], buf["actions"], buf["logp"], buf["reward"],
+                ep_return=buf["ep_return"], seed=seed, episode=0)
+    r = buf["ep_return"].cpu()
+    eng.close()
+    return float(r.mean()), float(r.std(unbiased=False)), float(s.n_steps)
+
+
+def init_distributed():
+    """One process per GPU (torchrun): returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not torch.distributed.is_initialized():
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local

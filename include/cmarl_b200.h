@@ -75,11 +75,28 @@ int cmarl_value_heads(const cmarl_ctx* ctx);          /* V */
 size_t cmarl_workspace_bytes(const cmarl_ctx* ctx);   /* scratch for cmarl_ppo_epoch_grads */
 int cmarl_launch_count(const cmarl_ctx* ctx);         /* kernels launched through this ctx so far */
 
+/* Per-kernel device timing (measurement aid for bench.py, off by default): when enabled every launch
+ * is bracketed by a cudaEvent pair on its own stream.  cmarl_timing_read synchronises the device and
+ * returns, per kernel id, the summed duration in ms and the number of launches since the last read. */
+#define CMARL_NK 11
+int cmarl_timing_enable(cmarl_ctx* ctx, int on);
+int cmarl_timing_read(cmarl_ctx* ctx, double* sum_ms /* HOST [CMARL_NK] */, int64_t* launches /* HOST [CMARL_NK] */);
+const char* cmarl_kernel_name(int id);
+
 /* -- K1: env reset.  Replaces the ("reset", None) round trip MME:393-401 -> env_worker MME:250-255
  * -> PettingZooWrapper.reset pettingzoo_wrapper.py:32-38 -> simple_spread reset_world: agent
  * positions then landmark positions ~ U(-1,1), velocities 0.  Draws come from Philox4x32-10
  * keyed by (seed, episode); callers that need given start positions write `env` themselves. */
 int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, void* stream);
+
+/* -- K1 alone: the env duck-type one call at a time (cleanmarl/env/common_interface.py:5-23).
+ * cmarl_env_observe: raw observations of the current state, state_out f32 [S][B]  (get_state /
+ * the obs returned by reset, pettingzoo_wrapper.py:32-38, 93-98).
+ * cmarl_env_step: one World.step for given actions i32 [N][B] (PettingZooWrapper.step,
+ * pettingzoo_wrapper.py:44-66): updates env, writes the new raw observations and agent 0's reward. */
+int cmarl_env_observe(cmarl_ctx* ctx, const double* env, float* state_out, void* stream);
+int cmarl_env_step(cmarl_ctx* ctx, double* env, const int32_t* actions, float* state_out, float* reward_out,
+                   void* stream);
 
 /* -- K1+K2+K3: one rollout of T lock-step steps for the B envs, entirely on the device.
  * Replaces the whole `while len(alive_envs) > 0` loop MME:408-453: Actor.act (MME:172-183,
