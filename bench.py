@@ -66,42 +66,49 @@ def workload_config(a, world):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + clock-event (throttle) reasons sampled through NVML every 50 ms during the timed region."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_sm = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:           # noqa: BLE001
+            print(f"clock sampling unavailable: {e}", file=sys.stderr)
+            return
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake_slowdown": 0x80}
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    try:
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except AttributeError:
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:        # noqa: BLE001
+                    pass
+                time.sleep(0.05)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        reasons = set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            for i, n in enumerate(names):
-                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+        return {"sm_mhz": int(statistics.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline

@@ -290,34 +290,57 @@ chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict_
 }
 
 // Fixed-order sum of the per-CTA partials -> flat gradient vector + statistics (deterministic).
+// 64 output columns per CTA; 4 thread groups each sum a quarter of the partial rows (independent
+// loads, 4 in flight per thread) and are combined in a fixed order.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ pa, int grid_a, int Pa,
                                                               const float* __restrict__ pc, int grid_c, int Pc,
                                                               float n_groups, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float part[4][64];
+    __shared__ double dpart[4];
+    const int col_l = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + col_l;
     const int P = Pa + Pc;
-    if (i >= P + CMARL_N_STATS) return;
-    const float* src;
-    int n, stride, col;
-    float scale = 1.0f;
-    if (i < Pa) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = i; }
-    else if (i < P) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = i - Pa; }
-    else {
-        const int k = i - P;   // out stats: 0 actor loss 1 critic loss 2 entropy 3 kl 4 clipfrac 5 n_valid(b,t)
-        if (k == 0) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = Pa + 0; }
-        else if (k == 1) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = Pc + 0; }
-        else if (k <= 4) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = Pa + (k - 1); }
-        else if (k == 5) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = Pa + 4; scale = 1.0f / n_groups; }
-        else { out[i] = 0.0f; return; }
+    const bool valid = i < P + CMARL_N_STATS;
+    const float* src = pa;
+    int n = 0, stride = 1, col = 0;
+    bool zero = false;
+    if (valid) {
+        if (i < Pa) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = i; }
+        else if (i < P) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = i - Pa; }
+        else {
+            const int k = i - P;   // out stats: 0 actor loss 1 critic loss 2 entropy 3 kl 4 clipfrac 5 n_valid(b,t)
+            if (k == 1) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = Pc + 0; }
+            else if (k <= 5) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = Pa + (k == 0 ? 0 : k - 1); }
+            else zero = true;
+        }
     }
-    if (i == P + 5) {      // the sample count can exceed 2^24: sum it in double
-        double d = 0.0;
-        for (int c = 0; c < n; ++c) d += (double)src[(size_t)c * stride + col];
-        out[i] = (float)(d / (double)n_groups);
-        return;
+    const int per = (n + 3) / 4;
+    const int c0 = grp * per, c1 = min(n, c0 + per);
+    const bool is_count = valid && (i == P + 5);
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    double d = 0.0;
+    if (valid && !zero) {
+        int c = c0;
+        if (is_count) {
+            for (; c < c1; ++c) d += (double)src[(size_t)c * stride + col];   // can exceed 2^24: sum in double
+        } else {
+            for (; c + 3 < c1; c += 4) {
+                a0 += src[(size_t)c * stride + col];
+                a1 += src[(size_t)(c + 1) * stride + col];
+                a2 += src[(size_t)(c + 2) * stride + col];
+                a3 += src[(size_t)(c + 3) * stride + col];
+            }
+            for (; c < c1; ++c) a0 += src[(size_t)c * stride + col];
+        }
     }
-    float a = 0.0f;
-    for (int c = 0; c < n; ++c) a += src[(size_t)c * stride + col];
-    out[i] = a * scale;
+    part[grp][col_l] = (a0 + a1) + (a2 + a3);
+    if (is_count) dpart[grp] = d;
+    __syncthreads();
+    if (grp == 0 && valid) {
+        if (zero) out[i] = 0.0f;
+        else if (is_count) out[i] = (float)((((dpart[0] + dpart[1]) + dpart[2]) + dpart[3]) / (double)n_groups);
+        else out[i] = ((part[0][col_l] + part[1][col_l]) + part[2][col_l]) + part[3][col_l];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -476,7 +499,7 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     const int n_out = Pa + Pc + CMARL_N_STATS;
     {
         KernelTimer kt(ctx, K_PPO_REDUCE, st);
-        reduce_partials_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(part_a, grid_a, Pa, part_c, grid_c, Pc,
+        reduce_partials_kernel<<<ceil_div(n_out, 64), 256, 0, st>>>(part_a, grid_a, Pa, part_c, grid_c, Pc,
                                                                      (float)c.n_agents, grads_out);
     }
     return cmarl_check_cuda(cudaGetLastError(), "reduce_partials_kernel");

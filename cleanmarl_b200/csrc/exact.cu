@@ -180,42 +180,50 @@ struct AdamArgs {
     double lr[2], beta1, beta2, eps, max_norm;
 };
 
-__device__ float block_sum(float x, float* sh) {
-    x = warp_sum(x);
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
-    if (lane == 0) sh[w] = x;
-    __syncthreads();
-    float r = 0.0f;
-    if (threadIdx.x < 32) {
-        r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0f;
-        r = warp_sum(r);
-        if (threadIdx.x == 0) sh[32] = r;
-    }
-    __syncthreads();
-    return sh[32];
-}
+// Single CTA of 1024 threads: 9 670 parameters is <= 10 per thread, so every gradient is loaded once
+// into registers, the 12 per-tensor sums of squares are block-reduced together (fixed order =>
+// deterministic), and scale / clip / Adam / statistics all happen in this one launch.
+constexpr int ADAM_THREADS = 1024;
+constexpr int ADAM_PER_THREAD = 12;      // supports up to 12 288 parameters
 
-// Single CTA: 9 670 parameters is ~10 per thread; everything between the all-reduce and the next
-// epoch's forward pass happens in this one launch (scale, per-tensor norms, clip, Adam, stats).
-__global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
-    __shared__ float sh[33];
-    __shared__ float tnorm[16];
+__global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
+    __shared__ float wsum[ADAM_THREADS / 32][12];
+    __shared__ float tnorm[12];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.tensor_off[a.n_tensors];
     const float* stats = a.grads + P;
     const float count = stats[5];
+    float g[ADAM_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < ADAM_PER_THREAD; ++j) {
+        const int i = tid + j * ADAM_THREADS;
+        g[j] = i < P ? a.grads[i] / count : 0.0f;
+    }
     // norm of the per-tensor norms (norm_d, MME:221-224) for each network
-    for (int k = 0; k < a.n_tensors; ++k) {
+    float ss[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
         float s = 0.0f;
-        for (int i = a.tensor_off[k] + threadIdx.x; i < a.tensor_off[k + 1]; i += blockDim.x) {
-            const float g = a.grads[i] / count;
-            s += g * g;
+#pragma unroll
+        for (int j = 0; j < ADAM_PER_THREAD; ++j) {
+            const int i = tid + j * ADAM_THREADS;
+            if (i >= a.tensor_off[k] && i < a.tensor_off[k + 1]) s += g[j] * g[j];
         }
-        s = block_sum(s, sh);
-        if (threadIdx.x == 0) tnorm[k] = sqrtf(s);
+        ss[k] = warp_sum(s);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) wsum[warp][k] = ss[k];
+    }
+    __syncthreads();
+    if (tid < 12) {
+        float s = 0.0f;
+        for (int w = 0; w < ADAM_THREADS / 32; ++w) s += wsum[w][tid];
+        tnorm[tid] = sqrtf(s);
     }
     __syncthreads();
     float net_norm[2], coef[2];
+#pragma unroll
     for (int net = 0; net < 2; ++net) {
         float s = 0.0f;
         const int k0 = net == 0 ? 0 : a.n_actor_tensors, k1 = net == 0 ? a.n_actor_tensors : a.n_tensors;
@@ -237,21 +245,25 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(AdamArgs a) {
     const float b2 = (float)a.beta2, w2 = (float)(1.0 - a.beta2);
     const float eps = (float)a.eps;
     const int actor_end = a.tensor_off[a.n_actor_tensors];
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float nss[2] = {(float)(-(a.lr[0] / bc1)), (float)(-(a.lr[1] / bc1))};
+#pragma unroll
+    for (int j = 0; j < ADAM_PER_THREAD; ++j) {
+        const int i = tid + j * ADAM_THREADS;
+        if (i >= P) continue;
         const int net = i < actor_end ? 0 : 1;
-        const float neg_step_size = (float)(-(a.lr[net] / bc1));
-        float g = a.grads[i] / count;
-        if (a.max_norm > 0.0) g = g * coef[net];
+        float gi = g[j];
+        if (a.max_norm > 0.0) gi = gi * coef[net];
         float m = a.m[i], v = a.v[i];
-        m = fmaf(w1, g - m, m);                 // exp_avg.lerp_(grad, 1 - beta1): ATen's lerp is an fma
+        m = fmaf(w1, gi - m, m);                // exp_avg.lerp_(grad, 1 - beta1): ATen's lerp is an fma
         v = v * b2;                             // exp_avg_sq.mul_(beta2)
-        v = v + (w2 * g) * g;                   //            .addcmul_(grad, grad, value=1 - beta2)
+        v = v + (w2 * gi) * gi;                 //            .addcmul_(grad, grad, value=1 - beta2)
         const float denom = sqrtf(v) / bc2_sqrt + eps;
-        a.params[i] = a.params[i] + (neg_step_size * m) / denom;   // param.addcdiv_(m, denom, value=-step_size)
+        a.params[i] = a.params[i] + (nss[net] * m) / denom;   // param.addcdiv_(m, denom, value=-step_size)
         a.m[i] = m;
         a.v[i] = v;
     }
-    if (threadIdx.x == 0) {
+    __syncthreads();
+    if (tid == 0) {
         if (a.stats_out) {
             for (int k = 0; k < 5; ++k) a.stats_out[k] = stats[k] / count;
             a.stats_out[5] = net_norm[0];
@@ -268,6 +280,7 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
                                     float* stats_out, void* stream) {
     CMARL_ARG(ctx && params && grads && exp_avg && exp_avg_sq, "null argument");
     CMARL_ARG(step_dev || step >= 1, "step must be >= 1");
+    CMARL_ARG(ctx->actor.count + ctx->critic.count <= ADAM_THREADS * ADAM_PER_THREAD, "too many parameters for clip_adam_kernel");
     AdamArgs a;
     a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
     a.step_dev = step_dev; a.step = step;
@@ -284,7 +297,7 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     a.lr[0] = lr_actor; a.lr[1] = lr_critic; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
-        clip_adam_kernel<<<1, 1024, 0, as_stream(stream)>>>(a);
+        clip_adam_kernel<<<1, ADAM_THREADS, 0, as_stream(stream)>>>(a);
     }
     return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
 }
