@@ -28,6 +28,7 @@ _SIGNATURES = {
     "cmarl_last_error": (C.c_char_p, []),
     "cmarl_ctx_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     "cmarl_ctx_destroy": (C.c_int, [_P]),
+    "cmarl_ctx_set_tensor_cores": (C.c_int, [_P, C.c_int]),
     "cmarl_actor_param_count": (C.c_int, [_P]),
     "cmarl_critic_param_count": (C.c_int, [_P]),
     "cmarl_value_heads": (C.c_int, [_P]),

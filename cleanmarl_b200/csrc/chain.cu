@@ -1,106 +1,9 @@
 // K4 (batched critic forward) and K7 (PPO epoch: fused forward + backward of actor and critic).
 // See chain.cuh for the tile pipeline.  Reference arithmetic: MME:527-582 (loss), MME:178-200 (nets).
 #include "chain.cuh"
+#include "heads.cuh"
 
 namespace chain {
-
-// ------------------------------------------------------------------------------------------------
-// Heads: what happens to the network output z of one sample
-// ------------------------------------------------------------------------------------------------
-struct PolicyHead {
-    static constexpr int OUT = 5;
-    static constexpr int NSTAT = 5;     // loss, entropy, kl, clip fraction, valid samples
-    using Args = PolicyHeadArgs;
-    // MME:530-551, 561-570 for one (b, t, agent) sample; all sums carry the 1/N of `.mean(dim=-1)`.
-    __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
-                                                 bool inb, bool train, float (&dz)[OUT], float (&st)[NSTAT]) {
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) dz[a] = 0.0f;
-        if (!inb) return;
-        const size_t tb = (size_t)t * B + b;
-        if (h.mask && !h.mask[tb]) return;
-        const size_t tgb = ((size_t)t * G + g) * B + b;
-        if (h.avail) {
-#pragma unroll
-            for (int a = 0; a < OUT; ++a)
-                if (!h.avail[(((size_t)t * G + g) * h.A + a) * B + b]) z[a] = -1e9f;   // masked_fill, MME:182
-        }
-        // Categorical(logits=z): logits = z - logsumexp(z); probs = softmax(logits)
-        float mx = z[0];
-#pragma unroll
-        for (int a = 1; a < OUT; ++a) mx = fmaxf(mx, z[a]);
-        float se = 0.0f;
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) se += expf(z[a] - mx);
-        const float lse = mx + logf(se);
-        float l[OUT], p[OUT];
-        float mx2 = -INFINITY;
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) { l[a] = z[a] - lse; mx2 = fmaxf(mx2, l[a]); }
-        float se2 = 0.0f;
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) { p[a] = expf(l[a] - mx2); se2 += p[a]; }
-        float ent = 0.0f;
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) { p[a] = p[a] / se2; ent -= l[a] * p[a]; }
-        const int act = h.actions[tgb];
-        float logp = l[0];
-#pragma unroll
-        for (int a = 1; a < OUT; ++a) logp = (act == a) ? l[a] : logp;
-        const float log_ratio = logp - h.logp_old[tgb];
-        const float ratio = expf(log_ratio);
-        const float A = h.adv[h.V == 1 ? tb : tgb];
-        const float lo = 1.0f - h.clip, hi = 1.0f + h.clip;
-        const float pg1 = A * ratio;
-        const float pg2 = A * fminf(fmaxf(ratio, lo), hi);
-        const float pg = fminf(pg1, pg2);
-        const float w = h.inv_groups;
-        st[0] += w * (-pg - h.ent_coef * ent);
-        st[1] += w * ent;
-        st[2] += w * ((ratio - 1.0f) - log_ratio);
-        st[3] += (fabsf(ratio - 1.0f) > h.clip) ? w : 0.0f;
-        st[4] += 1.0f;
-        if (!train) return;
-        // d(-min(pg1,pg2))/d(ratio): clamp passes the gradient inside [lo,hi] (ties of torch.min split
-        // 1/2 + 1/2 and recombine); outside, only the unclipped branch carries one.
-        const bool inside = (ratio >= lo) && (ratio <= hi);
-        const float dmin = (inside || pg1 < pg2) ? A : ((pg1 == pg2) ? 0.5f * A : 0.0f);
-        const float dlogp = -w * dmin * ratio;
-        const float we = w * h.ent_coef;
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) {
-            const float onehot = (act == a) ? 1.0f : 0.0f;
-            dz[a] = dlogp * (onehot - p[a]) + we * p[a] * (l[a] + ent);
-        }
-        if (h.avail) {
-#pragma unroll
-            for (int a = 0; a < OUT; ++a)
-                if (!h.avail[(((size_t)t * G + g) * h.A + a) * B + b]) dz[a] = 0.0f;
-        }
-    }
-};
-
-struct ValueHead {
-    static constexpr int OUT = 1;
-    static constexpr int NSTAT = 2;     // loss, valid samples
-    using Args = ValueHeadArgs;
-    // MME:554-558: sum_env mean_agent (V - R)^2 ; forward-only mode just stores V (MME:495,502).
-    __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
-                                                 bool inb, bool train, float (&dz)[OUT], float (&st)[NSTAT]) {
-        dz[0] = 0.0f;
-        if (!inb) return;
-        const size_t tgb = ((size_t)t * G + g) * B + b;
-        if (!train) {
-            h.values_out[tgb] = z[0];
-            return;
-        }
-        if (h.mask && !h.mask[(size_t)t * B + b]) return;
-        const float diff = z[0] - h.returns[tgb];
-        st[0] += h.inv_heads * diff * diff;
-        st[1] += 1.0f;
-        dz[0] = h.inv_heads * 2.0f * diff;
-    }
-};
 
 // ------------------------------------------------------------------------------------------------
 // The kernel
@@ -412,6 +315,25 @@ static void critic_desc(const cmarl_ctx* ctx, const float* params, const float* 
 
 using namespace chain;
 
+// tc_chain.cu
+int cmarl_tc_setup();
+int cmarl_tc_tile();
+template <class Head, bool TRAIN>
+int cmarl_tc_dispatch(int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
+                      int p_net, int grid, cudaStream_t st);
+
+template <class Head, bool TRAIN>
+static int run_chain(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha,
+                     float* partials, int p_net, int* grid_out, cudaStream_t st) {
+    const int kin = nd.in_rows <= 24 ? 24 : 56;
+    const int m = ctx->use_tc ? cmarl_tc_tile() : tile_m(H, kin);
+    const int units = units_of(src, m);
+    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    if (grid_out) *grid_out = grid;
+    if (ctx->use_tc) return cmarl_tc_dispatch<Head, TRAIN>(H, nd, src, ha, partials, p_net, grid, st);
+    return dispatch<Head, TRAIN>(ctx, H, nd, src, ha, partials, p_net, grid, st);
+}
+
 int cmarl_chain_setup(cmarl_ctx* ctx) {
     int e = 0;
 #define SET(Hh, Kk)                                                        \
@@ -420,6 +342,7 @@ int cmarl_chain_setup(cmarl_ctx* ctx) {
     if (!e) e = set_attr<Cfg<Hh, Kk>, ValueHead, false>();
     SET(32, 24) SET(32, 56) SET(64, 24) SET(64, 56)
 #undef SET
+    if (!e) e = cmarl_tc_setup();
     if (e) return e;
     const cmarl_config& c = ctx->cfg;
     NetDesc nd; TileSrc src;
@@ -448,11 +371,8 @@ extern "C" int cmarl_critic_values(cmarl_ctx* ctx, const float* critic_params, c
     critic_desc(ctx, critic_params, state, obs, nd, src);
     ValueHeadArgs ha;
     ha.returns = nullptr; ha.mask = nullptr; ha.values_out = values; ha.inv_heads = 1.0f / (float)ctx->n_heads;
-    const int kin = nd.in_rows <= 24 ? 24 : 56;
-    const int units = units_of(src, tile_m(ctx->cfg.critic_hidden, kin));
-    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
     KernelTimer kt(ctx, K_CRITIC, as_stream(stream));
-    return dispatch<ValueHead, false>(ctx, ctx->cfg.critic_hidden, nd, src, ha, nullptr, 0, grid, as_stream(stream));
+    return run_chain<ValueHead, false>(ctx, ctx->cfg.critic_hidden, nd, src, ha, nullptr, 0, nullptr, as_stream(stream));
 }
 
 extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const float* state, const float* obs,
@@ -474,12 +394,11 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     pa.actions = actions; pa.logp_old = logp_old; pa.adv = adv; pa.mask = mask; pa.avail = avail;
     pa.V = ctx->n_heads; pa.A = c.n_actions;
     pa.clip = (float)clip; pa.ent_coef = (float)ent_coef; pa.inv_groups = 1.0f / (float)c.n_agents;
-    const int ua = units_of(srca, tile_m(c.actor_hidden, 24));
-    const int grid_a = ua < ctx->sm_count ? ua : ctx->sm_count;
+    int grid_a = 0, grid_c = 0;
     int e;
     {
         KernelTimer kt(ctx, K_PPO_ACTOR, st);
-        e = dispatch<PolicyHead, true>(ctx, c.actor_hidden, nda, srca, pa, part_a, Pa, grid_a, st);
+        e = run_chain<PolicyHead, true>(ctx, c.actor_hidden, nda, srca, pa, part_a, Pa, &grid_a, st);
     }
     if (e) return e;
 
@@ -487,12 +406,9 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     critic_desc(ctx, params + Pa, state, obs, ndc, srcc);
     ValueHeadArgs va;
     va.returns = returns; va.mask = mask; va.values_out = nullptr; va.inv_heads = 1.0f / (float)ctx->n_heads;
-    const int kin = ndc.in_rows <= 24 ? 24 : 56;
-    const int uc = units_of(srcc, tile_m(c.critic_hidden, kin));
-    const int grid_c = uc < ctx->sm_count ? uc : ctx->sm_count;
     {
         KernelTimer kt(ctx, K_PPO_CRITIC, st);
-        e = dispatch<ValueHead, true>(ctx, c.critic_hidden, ndc, srcc, va, part_c, Pc, grid_c, st);
+        e = run_chain<ValueHead, true>(ctx, c.critic_hidden, ndc, srcc, va, part_c, Pc, &grid_c, st);
     }
     if (e) return e;
 

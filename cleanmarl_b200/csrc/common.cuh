@@ -48,6 +48,7 @@ struct cmarl_ctx {
     int ppo_grid_actor, ppo_grid_critic;
     int launches;
     int timing_on;
+    int use_tc;         // 1: tcgen05 (3xTF32) chain kernels, 0: fp32 FFMA chain kernels
     cmarl_timing* timing;
 };
 

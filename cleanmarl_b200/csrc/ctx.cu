@@ -137,6 +137,12 @@ extern "C" int cmarl_ctx_destroy(cmarl_ctx* ctx) {
     return 0;
 }
 
+extern "C" int cmarl_ctx_set_tensor_cores(cmarl_ctx* ctx, int on) {
+    CMARL_ARG(ctx, "null ctx");
+    ctx->use_tc = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int cmarl_actor_param_count(const cmarl_ctx* ctx) { return ctx ? ctx->actor.count : -1; }
 extern "C" int cmarl_critic_param_count(const cmarl_ctx* ctx) { return ctx ? ctx->critic.count : -1; }
 extern "C" int cmarl_value_heads(const cmarl_ctx* ctx) { return ctx ? ctx->n_heads : -1; }

@@ -1,0 +1,107 @@
+// Per-sample heads shared by the FFMA chain (chain.cu) and the tcgen05 chain (tc_chain.cu):
+// what happens to the network output z of one sample (loss terms, statistics, dz).
+#pragma once
+
+#include "chain.cuh"
+
+namespace chain {
+
+// ------------------------------------------------------------------------------------------------
+// Heads: what happens to the network output z of one sample
+// ------------------------------------------------------------------------------------------------
+struct PolicyHead {
+    static constexpr int OUT = 5;
+    static constexpr int NSTAT = 5;     // loss, entropy, kl, clip fraction, valid samples
+    using Args = PolicyHeadArgs;
+    // MME:530-551, 561-570 for one (b, t, agent) sample; all sums carry the 1/N of `.mean(dim=-1)`.
+    __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
+                                                 bool inb, bool train, float (&dz)[OUT], float (&st)[NSTAT]) {
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) dz[a] = 0.0f;
+        if (!inb) return;
+        const size_t tb = (size_t)t * B + b;
+        if (h.mask && !h.mask[tb]) return;
+        const size_t tgb = ((size_t)t * G + g) * B + b;
+        if (h.avail) {
+#pragma unroll
+            for (int a = 0; a < OUT; ++a)
+                if (!h.avail[(((size_t)t * G + g) * h.A + a) * B + b]) z[a] = -1e9f;   // masked_fill, MME:182
+        }
+        // Categorical(logits=z): logits = z - logsumexp(z); probs = softmax(logits)
+        float mx = z[0];
+#pragma unroll
+        for (int a = 1; a < OUT; ++a) mx = fmaxf(mx, z[a]);
+        float se = 0.0f;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) se += expf(z[a] - mx);
+        const float lse = mx + logf(se);
+        float l[OUT], p[OUT];
+        float mx2 = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) { l[a] = z[a] - lse; mx2 = fmaxf(mx2, l[a]); }
+        float se2 = 0.0f;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) { p[a] = expf(l[a] - mx2); se2 += p[a]; }
+        float ent = 0.0f;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) { p[a] = p[a] / se2; ent -= l[a] * p[a]; }
+        const int act = h.actions[tgb];
+        float logp = l[0];
+#pragma unroll
+        for (int a = 1; a < OUT; ++a) logp = (act == a) ? l[a] : logp;
+        const float log_ratio = logp - h.logp_old[tgb];
+        const float ratio = expf(log_ratio);
+        const float A = h.adv[h.V == 1 ? tb : tgb];
+        const float lo = 1.0f - h.clip, hi = 1.0f + h.clip;
+        const float pg1 = A * ratio;
+        const float pg2 = A * fminf(fmaxf(ratio, lo), hi);
+        const float pg = fminf(pg1, pg2);
+        const float w = h.inv_groups;
+        st[0] += w * (-pg - h.ent_coef * ent);
+        st[1] += w * ent;
+        st[2] += w * ((ratio - 1.0f) - log_ratio);
+        st[3] += (fabsf(ratio - 1.0f) > h.clip) ? w : 0.0f;
+        st[4] += 1.0f;
+        if (!train) return;
+        // d(-min(pg1,pg2))/d(ratio): clamp passes the gradient inside [lo,hi] (ties of torch.min split
+        // 1/2 + 1/2 and recombine); outside, only the unclipped branch carries one.
+        const bool inside = (ratio >= lo) && (ratio <= hi);
+        const float dmin = (inside || pg1 < pg2) ? A : ((pg1 == pg2) ? 0.5f * A : 0.0f);
+        const float dlogp = -w * dmin * ratio;
+        const float we = w * h.ent_coef;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) {
+            const float onehot = (act == a) ? 1.0f : 0.0f;
+            dz[a] = dlogp * (onehot - p[a]) + we * p[a] * (l[a] + ent);
+        }
+        if (h.avail) {
+#pragma unroll
+            for (int a = 0; a < OUT; ++a)
+                if (!h.avail[(((size_t)t * G + g) * h.A + a) * B + b]) dz[a] = 0.0f;
+        }
+    }
+};
+
+struct ValueHead {
+    static constexpr int OUT = 1;
+    static constexpr int NSTAT = 2;     // loss, valid samples
+    using Args = ValueHeadArgs;
+    // MME:554-558: sum_env mean_agent (V - R)^2 ; forward-only mode just stores V (MME:495,502).
+    __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
+                                                 bool inb, bool train, float (&dz)[OUT], float (&st)[NSTAT]) {
+        dz[0] = 0.0f;
+        if (!inb) return;
+        const size_t tgb = ((size_t)t * G + g) * B + b;
+        if (!train) {
+            h.values_out[tgb] = z[0];
+            return;
+        }
+        if (h.mask && !h.mask[(size_t)t * B + b]) return;
+        const float diff = z[0] - h.returns[tgb];
+        st[0] += h.inv_heads * diff * diff;
+        st[1] += 1.0f;
+        dz[0] = h.inv_heads * 2.0f * diff;
+    }
+};
+
+}  // namespace chain

@@ -8,6 +8,7 @@ from/to the reference's batch-major ``RolloutBuffer.get_batch`` tuple (MME:148-1
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -48,7 +49,7 @@ def _ptr(t, dtype, device, name):
 
 
 class Engine:
-    def __init__(self, shapes: Shapes, device: int | torch.device = 0):
+    def __init__(self, shapes: Shapes, device: int | torch.device = 0, tensor_cores: bool | None = None):
         if not torch.cuda.is_available():
             raise RuntimeError("cleanmarl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -60,6 +61,10 @@ class Engine:
         h = C.c_void_p()
         _lib.check(self.lib.cmarl_ctx_create(C.byref(cfg), C.byref(h)), "cmarl_ctx_create")
         self._h = h
+        if tensor_cores is None:
+            tensor_cores = os.environ.get("CMARL_TENSOR_CORES", "0") != "0"
+        self.tensor_cores = bool(tensor_cores)
+        _lib.check(self.lib.cmarl_ctx_set_tensor_cores(h, int(self.tensor_cores)), "cmarl_ctx_set_tensor_cores")
         self.n_actor = self.lib.cmarl_actor_param_count(h)
         self.n_critic = self.lib.cmarl_critic_param_count(h)
         self.n_params = self.n_actor + self.n_critic

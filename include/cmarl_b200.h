@@ -69,6 +69,10 @@ const char* cmarl_last_error(void);
  * it is the handle the entries below share. */
 int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out);
 int cmarl_ctx_destroy(cmarl_ctx* ctx);
+/* Selects the implementation of the fused MLP chains (cmarl_critic_values, cmarl_ppo_epoch_grads):
+ * 1 = tcgen05 tensor cores, kind::tf32 with a 3-term split (fp32-level accuracy, csrc/tc_chain.cu);
+ * 0 = fp32 FFMA block GEMMs (csrc/chain.cu).  Both produce the same quantities to the stated tolerances. */
+int cmarl_ctx_set_tensor_cores(cmarl_ctx* ctx, int on);
 int cmarl_actor_param_count(const cmarl_ctx* ctx);    /* 1 925 for the default shapes */
 int cmarl_critic_param_count(const cmarl_ctx* ctx);   /* 7 745 */
 int cmarl_value_heads(const cmarl_ctx* ctx);          /* V */

@@ -1,0 +1,310 @@
+"""Probe tcgen05.mma.kind::tf32 operand layouts / accumulator layouts on a B200 (uses libcmarl_umma_probe.so).
+
+Each experiment builds a shared-memory image on the host under a layout hypothesis, runs the MMA(s) and
+compares the dumped TMEM accumulator with a host GEMM.  Output: one line per experiment.
+"""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parents[2]
+lib = C.CDLL(str(REPO / "cleanmarl_b200" / "libcmarl_umma_probe.so"))
+
+
+class ProbeArgs(C.Structure):
+    _fields_ = [("image", C.c_void_p), ("image_bytes", C.c_uint32), ("a_off", C.c_uint32), ("b_off", C.c_uint32),
+                ("a_lbo", C.c_uint32), ("a_sbo", C.c_uint32), ("b_lbo", C.c_uint32), ("b_sbo", C.c_uint32),
+                ("a_layout", C.c_uint32), ("b_layout", C.c_uint32), ("idesc", C.c_uint32), ("ksteps", C.c_uint32),
+                ("a_kstep", C.c_uint32), ("b_kstep", C.c_uint32), ("n_cols", C.c_uint32), ("passes", C.c_uint32),
+                ("a_off2", C.c_uint32), ("b_off2", C.c_uint32), ("a_off3", C.c_uint32), ("b_off3", C.c_uint32),
+                ("out", C.c_void_p), ("status", C.c_void_p)]
+
+
+lib.cmarl_umma_probe.argtypes = [C.POINTER(ProbeArgs), C.c_uint32, C.c_void_p]
+lib.cmarl_umma_probe.restype = C.c_int
+
+
+def idesc(M, N, a_mn, b_mn):
+    return (1 << 4) | (2 << 7) | (2 << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
+
+
+def trunc_tf32(x):
+    return (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def round_tf32(x):
+    u = x.view(np.uint32).astype(np.uint64)
+    u = (u + 0x0FFF + ((u >> 13) & 1)) & 0xFFFFE000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def core_offsets(R, K, lbo, sbo):
+    """byte offset of element (r, k) of an [R][K] fp32 matrix in the no-swizzle K-major canonical layout"""
+    r = np.arange(R)[:, None]
+    k = np.arange(K)[None, :]
+    return (r % 8) * 16 + (r // 8) * sbo + (k // 4) * lbo + (k % 4) * 4
+
+
+def put(image, off, mat, offsets):
+    flat = image[off:].view(np.float32)
+    flat[(offsets // 4).reshape(-1)] = mat.reshape(-1)
+
+
+def run(image, a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo, a_layout, b_layout, idesc_, ksteps, a_kstep, b_kstep,
+        n_cols, passes=1, offs2=(0, 0), offs3=(0, 0)):
+    dev = torch.device("cuda", 0)
+    img = torch.from_numpy(image).to(dev)
+    out = torch.zeros(128, n_cols, device=dev)
+    status = torch.full((1,), -7, dtype=torch.int32, device=dev)
+    a = ProbeArgs(img.data_ptr(), image.nbytes, a_off, b_off, a_lbo, a_sbo, b_lbo, b_sbo, a_layout, b_layout, idesc_,
+                  ksteps, a_kstep, b_kstep, n_cols, passes, offs2[0], offs2[1], offs3[0], offs3[1], out.data_ptr(),
+                  status.data_ptr())
+    rc = lib.cmarl_umma_probe(C.byref(a), max(image.nbytes, 1024), None)
+    torch.cuda.synchronize()
+    return rc, int(status.item()), out.cpu().numpy()
+
+
+def report(name, got, want, rows=None):
+    rows = slice(0, want.shape[0]) if rows is None else rows
+    g = got[rows, :want.shape[1]]
+    err = np.abs(g - want).max() / max(np.abs(want).max(), 1e-30)
+    print(f"{name:70s} rel_err={err:.3e}  {'MATCH' if err < 2e-3 else 'no'}", flush=True)
+    return err
+
+
+def setup():
+    rng = np.random.default_rng(0)
+    M, N, K = 128, 64, 64
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    ref = (trunc_tf32(A).astype(np.float64) @ trunc_tf32(B).astype(np.float64).T).astype(np.float32)
+    ref_rn = (round_tf32(A).astype(np.float64) @ round_tf32(B).astype(np.float64).T).astype(np.float32)
+    exact = (A.astype(np.float64) @ B.astype(np.float64).T)
+
+    lbo, sbo = 128, (K // 4) * 128
+    return dict(locals())
+
+
+def exp_E1(env):
+    globals().update(env)
+    # ---- E1: K-major, no swizzle: A [128][64], B [64][64]; LBO = 128 (adjacent K chunks), SBO = K/4*128
+    lbo, sbo = 128, (K // 4) * 128
+    image = np.zeros(96 * 1024, dtype=np.uint8)
+    a_off, b_off = 0, 40 * 1024
+    put(image, a_off, A, core_offsets(M, K, lbo, sbo))
+    put(image, b_off, B, core_offsets(N, K, lbo, sbo))
+    rc, st, out = run(image, a_off, b_off, lbo, sbo, lbo, sbo, 0, 0, idesc(128, 64, 0, 0), K // 8, 2 * lbo, 2 * lbo, 64)
+    print("E1 rc", rc, "status", st)
+    report("E1 K-major/no-swizzle M128 N64 K64 vs trunc model", out, ref)
+    report("E1 ... vs round-to-nearest model", out, ref_rn)
+    report("E1 ... vs exact fp64", out, exact.astype(np.float32))
+
+
+def exp_E1b(env):
+    globals().update(env)
+    # ---- E1b: same buffers with swapped LBO/SBO roles (LBO = stride between 8-row groups?) -- should NOT match
+    image = np.zeros(96 * 1024, dtype=np.uint8)
+    a_off, b_off = 0, 40 * 1024
+    put(image, a_off, A, core_offsets(M, K, lbo, sbo))
+    put(image, b_off, B, core_offsets(N, K, lbo, sbo))
+    rc, st, out = run(image, a_off, b_off, sbo, lbo, sbo, lbo, 0, 0, idesc(128, 64, 0, 0), K // 8, 2 * lbo, 2 * lbo, 64)
+    report("E1b swapped LBO/SBO (expected mismatch)", out, ref)
+
+
+def exp_E2(env):
+    globals().update(env)
+    # ---- E2: 3xTF32: passes (A, B), (A_lo, B), (A, B_lo), hi = raw fp32 (hardware drops the low 13 bits)
+    A_lo = (A - trunc_tf32(A)).astype(np.float32)
+    B_lo = (B - trunc_tf32(B)).astype(np.float32)
+    image2 = np.zeros(160 * 1024, dtype=np.uint8)
+    offs = [0, 32 * 1024, 64 * 1024, 96 * 1024]          # A, A_lo, B, B_lo
+    put(image2, offs[0], A, core_offsets(M, K, lbo, sbo))
+    put(image2, offs[1], A_lo, core_offsets(M, K, lbo, sbo))
+    put(image2, offs[2], B, core_offsets(N, K, lbo, sbo))
+    put(image2, offs[3], B_lo, core_offsets(N, K, lbo, sbo))
+    rc, st, out = run(image2, offs[0], offs[2], lbo, sbo, lbo, sbo, 0, 0, idesc(128, 64, 0, 0), K // 8, 2 * lbo, 2 * lbo,
+                      64, passes=3, offs2=(offs[1], offs[2]), offs3=(offs[0], offs[3]))
+    e = np.abs(out[:, :64] - exact).max() / np.abs(exact).max()
+    f32 = (A @ B.T)
+    e32 = np.abs(f32 - exact).max() / np.abs(exact).max()
+    print(f"E2 3xTF32 (trunc split) rel err vs fp64 = {e:.3e}   (plain fp32 GEMM: {e32:.3e})", flush=True)
+    A_lo_r = (A - round_tf32(A)).astype(np.float32)
+    B_lo_r = (B - round_tf32(B)).astype(np.float32)
+    A_hi_r, B_hi_r = round_tf32(A), round_tf32(B)
+    put(image2, offs[0], A_hi_r, core_offsets(M, K, lbo, sbo))
+    put(image2, offs[1], A_lo_r, core_offsets(M, K, lbo, sbo))
+    put(image2, offs[2], B_hi_r, core_offsets(N, K, lbo, sbo))
+    put(image2, offs[3], B_lo_r, core_offsets(N, K, lbo, sbo))
+    rc, st, out = run(image2, offs[0], offs[2], lbo, sbo, lbo, sbo, 0, 0, idesc(128, 64, 0, 0), K // 8, 2 * lbo, 2 * lbo,
+                      64, passes=3, offs2=(offs[1], offs[2]), offs3=(offs[0], offs[3]))
+    e = np.abs(out[:, :64] - exact).max() / np.abs(exact).max()
+    print(f"E2b 3xTF32 (round-to-nearest split, hi pre-rounded) rel err vs fp64 = {e:.3e}", flush=True)
+
+
+def exp_E3(env):
+    globals().update(env)
+    # ---- E3: MN-major, no swizzle, SAME buffers read transposed:  D[j][n] = sum_s At[j][s] Bt[n][s]
+    #      where the smem holds X = A [s=128][j=64] in K-major core layout (rows = s).  As an MN-major operand
+    #      (MN = j, K = s): SBO_mn = LBO_k (stride between 4-element MN vectors), LBO_mn = SBO_k (stride between 8-k groups)
+    #      D = A^T (64 x 128) * (B2^T)  with B2 [s=128][n=64] stored the same way.
+    B2 = rng.standard_normal((128, 64)).astype(np.float32)
+    image3 = np.zeros(96 * 1024, dtype=np.uint8)
+    put(image3, 0, A, core_offsets(128, 64, lbo, sbo))
+    put(image3, 40 * 1024, B2, core_offsets(128, 64, lbo, sbo))
+    ref3 = (trunc_tf32(A).astype(np.float64).T @ trunc_tf32(B2).astype(np.float64)).astype(np.float32)   # [64 j][64 n]
+    for (nm, l, s, kst) in (("LBO_mn=SBO_k,SBO_mn=LBO_k,kstep=LBO_mn", sbo, lbo, sbo),
+                            ("LBO_mn=LBO_k,SBO_mn=SBO_k,kstep=SBO", lbo, sbo, sbo)):
+        rc, st, out = run(image3, 0, 40 * 1024, l, s, l, s, 0, 0, idesc(64, 64, 1, 1), 128 // 8, kst, kst, 64)
+        print("E3", nm, "rc", rc, "status", st)
+        # M = 64: find which lanes hold the 64 rows
+        for lanes_name, lanes in (("lanes 0-63", np.arange(64)),
+                                  ("lanes 0-15,32-47,64-79,96-111", np.concatenate([np.arange(16) + 32 * q for q in range(4)])),
+                                  ("lanes 0-31,64-95", np.concatenate([np.arange(32), np.arange(32) + 64]))):
+            report(f"E3 MN-major/no-swizzle M64 N64 K128 [{nm}] rows in {lanes_name}", out[lanes], ref3)
+        untouched = np.where((out[:, 0] == -12345.0))[0]
+        print("   untouched lanes:", untouched[:8], "... n =", len(untouched), flush=True)
+
+
+def exp_E4(env):
+    globals().update(env)
+    # ---- E4: M = 64, K-major (for reference: which lanes hold the rows)
+    A64 = A[:64]
+    image4 = np.zeros(96 * 1024, dtype=np.uint8)
+    put(image4, 0, A64, core_offsets(64, K, lbo, sbo))
+    put(image4, 40 * 1024, B, core_offsets(N, K, lbo, sbo))
+    ref4 = (trunc_tf32(A64).astype(np.float64) @ trunc_tf32(B).astype(np.float64).T).astype(np.float32)
+    rc, st, out = run(image4, 0, 40 * 1024, lbo, sbo, lbo, sbo, 0, 0, idesc(64, 64, 0, 0), K // 8, 2 * lbo, 2 * lbo, 64)
+    print("E4 rc", rc, "status", st)
+    for lanes_name, lanes in (("lanes 0-63", np.arange(64)),
+                              ("lanes 0-15,32-47,64-79,96-111", np.concatenate([np.arange(16) + 32 * q for q in range(4)])),
+                              ("lanes 0-31,64-95", np.concatenate([np.arange(32), np.arange(32) + 64]))):
+        report(f"E4 K-major M64 N64 rows in {lanes_name}", out[lanes], ref4)
+    untouched = np.where((out[:, 0] == -12345.0))[0]
+    print("   untouched lanes:", untouched[:8], "... n =", len(untouched), flush=True)
+
+
+def exp_E5(env, pairs=((128, 16), (128, 32), (64, 8), (64, 56), (64, 24), (64, 32))):
+    globals().update(env)
+    # ---- E5: narrow N: M128 N16 (logits), M64 N8, M64 N56, M64 N24
+    for (m_, n_) in pairs:
+        Bn = B[:n_]
+        Am = A[:m_]
+        img = np.zeros(96 * 1024, dtype=np.uint8)
+        put(img, 0, Am, core_offsets(m_, K, lbo, sbo))
+        put(img, 40 * 1024, Bn, core_offsets(n_, K, lbo, sbo))
+        refn = (trunc_tf32(Am).astype(np.float64) @ trunc_tf32(Bn).astype(np.float64).T).astype(np.float32)
+        rc, st, out = run(img, 0, 40 * 1024, lbo, sbo, lbo, sbo, 0, 0, idesc(m_, n_, 0, 0), K // 8, 2 * lbo, 2 * lbo, 64)
+        lanes = np.arange(128) if m_ == 128 else None
+        if m_ == 128:
+            report(f"E5 M{m_} N{n_} (rc {rc} st {st})", out, refn)
+        else:
+            best = min(
+                (np.abs(out[l][:, :n_] - refn).max() / np.abs(refn).max(), nm) for nm, l in
+                (("0-63", np.arange(64)), ("16/quadrant", np.concatenate([np.arange(16) + 32 * q for q in range(4)])),
+                 ("0-31,64-95", np.concatenate([np.arange(32), np.arange(32) + 64]))))
+            print(f"E5 M{m_} N{n_} (rc {rc} st {st}) best lane map {best[1]} rel_err={best[0]:.3e}", flush=True)
+
+
+def exp_E6(env):
+    globals().update(env)
+    # ---- E6: padded strides (bank-conflict-free writer): LBO = 128 + 16 K-major
+    lbo6, sbo6 = 144, (K // 4) * 144
+    img = np.zeros(96 * 1024, dtype=np.uint8)
+    put(img, 0, A, core_offsets(M, K, lbo6, sbo6))
+    put(img, 48 * 1024, B, core_offsets(N, K, lbo6, sbo6))
+    rc, st, out = run(img, 0, 48 * 1024, lbo6, sbo6, lbo6, sbo6, 0, 0, idesc(128, 64, 0, 0), K // 8, 2 * lbo6, 2 * lbo6, 64)
+    report(f"E6 K-major padded LBO=144 (rc {rc} st {st})", out, ref)
+
+
+def exp_E7(env):
+    globals().update(env)
+    # ---- E7: mixed: A K-major (M = s), B MN-major (N = j from a [k][j]-stored weight, i.e. W^T use)
+    #      D[s][n] = sum_k A[s][k] * W[k][n], W stored as [k=64][n=64] in core layout with rows = k.
+    W = rng.standard_normal((64, 64)).astype(np.float32)
+    img = np.zeros(96 * 1024, dtype=np.uint8)
+    put(img, 0, A, core_offsets(128, 64, lbo, sbo))
+    put(img, 40 * 1024, W, core_offsets(64, 64, lbo, sbo))
+    ref7 = (trunc_tf32(A).astype(np.float64) @ trunc_tf32(W).astype(np.float64)).astype(np.float32)
+    rc, st, out = run(img, 0, 40 * 1024, lbo, sbo, sbo, lbo, 0, 0, idesc(128, 64, 0, 1), 64 // 8, 2 * lbo, sbo, 64)
+    report(f"E7 A K-major, B MN-major no-swizzle (rc {rc} st {st})", out, ref7)
+
+
+
+
+
+def rna_tf32(x):
+    """cvt.rna.tf32.f32: round to nearest, ties away from zero, low 13 bits cleared"""
+    u = x.view(np.uint32).astype(np.uint64)
+    u = (u + 0x1000) & 0xFFFFE000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def exp_E8(env):
+    globals().update(env)
+    # ---- E8: RN split 3xTF32, hi = rna(x), lo = rna(x - hi), all operands from smem (K-major)
+    Ah, Bh = rna_tf32(A), rna_tf32(B)
+    Al, Bl = rna_tf32((A - Ah).astype(np.float32)), rna_tf32((B - Bh).astype(np.float32))
+    image2 = np.zeros(160 * 1024, dtype=np.uint8)
+    offs = [0, 32 * 1024, 64 * 1024, 96 * 1024]
+    for o, m_, r_ in ((offs[0], Ah, M), (offs[1], Al, M), (offs[2], Bh, N), (offs[3], Bl, N)):
+        put(image2, o, m_, core_offsets(r_, K, lbo, sbo))
+    rc, st, out = run(image2, offs[0], offs[2], lbo, sbo, lbo, sbo, 0, 0, idesc(128, 64, 0, 0), K // 8, 2 * lbo, 2 * lbo,
+                      64, passes=3, offs2=(offs[1], offs[2]), offs3=(offs[0], offs[3]))
+    e = np.abs(out[:, :64] - exact).max() / np.abs(exact).max()
+    e32 = np.abs((A @ B.T) - exact).max() / np.abs(exact).max()
+    print(f"E8 3xTF32 RN split (hi=rna(x), lo=rna(x-hi)) rel err vs fp64 = {e:.3e}   (plain fp32 GEMM: {e32:.3e})", flush=True)
+    # small terms first: (lo,hi), (hi,lo), (hi,hi)
+    rc, st, out = run(image2, offs[1], offs[2], lbo, sbo, lbo, sbo, 0, 0, idesc(128, 64, 0, 0), K // 8, 2 * lbo, 2 * lbo,
+                      64, passes=3, offs2=(offs[0], offs[3]), offs3=(offs[0], offs[2]))
+    e = np.abs(out[:, :64] - exact).max() / np.abs(exact).max()
+    print(f"E8b same, small terms first rel err vs fp64 = {e:.3e}", flush=True)
+
+
+def exp_E9(env):
+    globals().update(env)
+    # ---- E9: A from TMEM (row-major per lane, one element per column), B K-major smem; 3 passes RN split
+    Ah, Bh = rna_tf32(A), rna_tf32(B)
+    Al, Bl = rna_tf32((A - Ah).astype(np.float32)), rna_tf32((B - Bh).astype(np.float32))
+    image2 = np.zeros(160 * 1024, dtype=np.uint8)
+    offs = [0, 32 * 1024, 64 * 1024, 96 * 1024]
+    image2[offs[0]:offs[0] + A.nbytes] = Ah.view(np.uint8).reshape(-1)
+    image2[offs[1]:offs[1] + A.nbytes] = Al.view(np.uint8).reshape(-1)
+    put(image2, offs[2], Bh, core_offsets(N, K, lbo, sbo))
+    put(image2, offs[3], Bl, core_offsets(N, K, lbo, sbo))
+    rc, st, out = run(image2, offs[0], offs[2], 0, 0, lbo, sbo, 99, 0, idesc(128, 64, 0, 0), K // 8, 0, 2 * lbo, 64)
+    refh = (Ah.astype(np.float64) @ Bh.astype(np.float64).T).astype(np.float32)
+    report(f"E9 A from TMEM (hi only) (rc {rc} st {st})", out, refh)
+    rc, st, out = run(image2, offs[0], offs[2], 0, 0, lbo, sbo, 99, 0, idesc(128, 64, 0, 0), K // 8, 0, 2 * lbo, 64,
+                      passes=3, offs2=(offs[1], offs[2]), offs3=(offs[0], offs[3]))
+    e = np.abs(out[:, :64] - exact).max() / np.abs(exact).max()
+    print(f"E9b A from TMEM 3xTF32 RN split rel err vs fp64 = {e:.3e}", flush=True)
+
+
+def exp_E5x1(env):
+    exp_E5(env, ((128, 8),))
+
+
+def exp_E5x2(env):
+    exp_E5(env, ((128, 24),))
+
+
+def exp_E5x3(env):
+    exp_E5(env, ((128, 56),))
+
+
+EXPERIMENTS = ["E8", "E9", "E1", "E1b", "E2", "E3", "E4", "E5", "E6", "E7", "E5x1", "E5x2", "E5x3"]
+
+
+if __name__ == "__main__":
+    import subprocess
+    if len(sys.argv) > 1:
+        globals()["exp_" + sys.argv[1]](setup())
+    else:   # one process per experiment: an illegal descriptor poisons the CUDA context
+        for e in EXPERIMENTS:
+            r = subprocess.run([sys.executable, __file__, e], capture_output=True, text=True, timeout=300)
+            print(r.stdout, end="")
+            if r.returncode:
+                print(f"{e}: FAILED rc={r.returncode}: {r.stderr.strip().splitlines()[-1] if r.stderr.strip() else ''}", flush=True)

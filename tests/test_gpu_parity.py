@@ -23,8 +23,11 @@ def cm():
     return cm
 
 
-def make_engine(cm, B, T_=25, **kw):
-    return cm.Engine(cm.Shapes(n_envs=B, n_steps=T_, **kw), device=0)
+TC = [False, True]      # fp32 FFMA chain / tcgen05 3xTF32 chain: the same tolerances hold for both
+
+
+def make_engine(cm, B, T_=25, tc=None, **kw):
+    return cm.Engine(cm.Shapes(n_envs=B, n_steps=T_, **kw), device=0, tensor_cores=tc)
 
 
 def flat_params(actor, critic, device):
@@ -64,8 +67,9 @@ def test_td_lambda_scan_bit_exact(cm, B, V):
 
 
 # ----------------------------------------------------------------------------------------- K4 (+K5) on the golden run
+@pytest.mark.parametrize("tc", TC, ids=["ffma", "tc"])
 @pytest.mark.parametrize("name,ippo", [("g8_mappo", False), ("g8_ippo", True)])
-def test_critic_td_lambda_vs_reference_run(cm, golden, name, ippo):
+def test_critic_td_lambda_vs_reference_run(cm, golden, name, ippo, tc):
     """K4+K5 on the batch of a real reference iteration: returns/advantages within 1e-5 (north star)."""
     from cleanmarl_b200 import engine as E
     g = golden(name)
@@ -75,7 +79,7 @@ def test_critic_td_lambda_vs_reference_run(cm, golden, name, ippo):
     else:
         actor, critic = om.build_networks(seed)
     B = int(g["B"])
-    eng = make_engine(cm, B, critic_on_obs=ippo, critic_hidden=int(g["critic_hidden_dim"]))
+    eng = make_engine(cm, B, tc=tc, critic_on_obs=ippo, critic_hidden=int(g["critic_hidden_dim"]))
     dev = eng.device
     batch = tuple(T(g[k]) for k in ("obs", "actions", "log_probs", "reward", "states", "avail", "done", "mask"))
     d = E.to_device_layout(batch, dev)
@@ -139,8 +143,9 @@ def _check_epoch(eng, E, actor, critic, batch, adv, ret, ippo, use_obs, use_mask
     return grads
 
 
+@pytest.mark.parametrize("tc", TC, ids=["ffma", "tc"])
 @pytest.mark.parametrize("name,ippo", [("g8_mappo", False), ("g8_ippo", True)])
-def test_ppo_epoch_grads_vs_reference_loop(cm, golden, name, ippo):
+def test_ppo_epoch_grads_vs_reference_loop(cm, golden, name, ippo, tc):
     """K7 on the batch of a real reference iteration vs autograd through the reference's own loop form."""
     from cleanmarl_b200 import engine as E
     g = golden(name)
@@ -148,14 +153,15 @@ def test_ppo_epoch_grads_vs_reference_loop(cm, golden, name, ippo):
     actor, critic = (om.build_networks(seed, state_dim=21, critic_hidden=int(g["critic_hidden_dim"])) if ippo
                      else om.build_networks(seed))
     batch = tuple(T(g[k]) for k in ("obs", "actions", "log_probs", "reward", "states", "avail", "done", "mask"))
-    eng = make_engine(cm, int(g["B"]), critic_on_obs=ippo, critic_hidden=int(g["critic_hidden_dim"]))
+    eng = make_engine(cm, int(g["B"]), tc=tc, critic_on_obs=ippo, critic_hidden=int(g["critic_hidden_dim"]))
     for use_obs in (False, True):
         _check_epoch(eng, E, actor, critic, batch, T(g["advantages"]), T(g["return_lambda"]), ippo, use_obs, flat=False)
 
 
+@pytest.mark.parametrize("tc", TC, ids=["ffma", "tc"])
 @pytest.mark.parametrize("B,ippo,hid", [(300, False, (32, 64)), (1024, False, (32, 64)), (515, True, (32, 32)),
                                         (256, False, (64, 32)), (260, True, (64, 64))])
-def test_ppo_epoch_grads_synthetic(cm, B, ippo, hid):
+def test_ppo_epoch_grads_synthetic(cm, B, ippo, hid, tc):
     """K7 on seeded synthetic batches: full TMA tiles + ragged tail tile, ragged masks, random avail,
     obs rebuilt from state vs explicit obs, both hidden widths."""
     from cleanmarl_b200 import engine as E
@@ -173,7 +179,7 @@ def test_ppo_epoch_grads_synthetic(cm, B, ippo, hid):
     V = 3 if ippo else 1
     adv = torch.randn(B, 25, V, generator=gen).expand(B, 25, 3).contiguous() * 3
     ret = torch.randn(B, 25, V, generator=gen).expand(B, 25, 3).contiguous() * 5
-    eng = make_engine(cm, B, critic_on_obs=ippo, actor_hidden=ha, critic_hidden=hc)
+    eng = make_engine(cm, B, tc=tc, critic_on_obs=ippo, actor_hidden=ha, critic_hidden=hc)
     for use_obs in (False, True):
         _check_epoch(eng, E, actor, critic, tuple(batch), adv, ret, ippo, use_obs)
     g1 = _check_epoch(eng, E, actor, critic, tuple(batch), adv, ret, ippo, False).clone()
@@ -345,8 +351,9 @@ def test_rollout_device_rng_and_reset(cm):
 
 
 # ----------------------------------------------------------------------------------------- whole iteration
+@pytest.mark.parametrize("tc", TC, ids=["ffma", "tc"])
 @pytest.mark.parametrize("name,ippo", [("g8_mappo", False), ("g8_mappo_flags", False), ("g8_ippo", True)])
-def test_whole_update_vs_reference_run(cm, golden, name, ippo):
+def test_whole_update_vs_reference_run(cm, golden, name, ippo, tc):
     """K4+K5(+K6)+3x(K7+K8) from the reference's initial parameters on the reference's batch: per-epoch
     statistics and the final parameters follow the unmodified reference run."""
     from cleanmarl_b200 import engine as E
@@ -354,7 +361,7 @@ def test_whole_update_vs_reference_run(cm, golden, name, ippo):
     seed, B = int(g["seed"]), int(g["B"])
     actor, critic = (om.build_networks(seed, state_dim=21, critic_hidden=int(g["critic_hidden_dim"])) if ippo
                      else om.build_networks(seed))
-    eng = make_engine(cm, B, critic_on_obs=ippo, critic_hidden=int(g["critic_hidden_dim"]))
+    eng = make_engine(cm, B, tc=tc, critic_on_obs=ippo, critic_hidden=int(g["critic_hidden_dim"]))
     dev = eng.device
     batch = tuple(T(g[k]) for k in ("obs", "actions", "log_probs", "reward", "states", "avail", "done", "mask"))
     d = E.to_device_layout(batch, dev)
