@@ -318,6 +318,7 @@ using namespace chain;
 // tc_chain.cu
 int cmarl_tc_setup();
 int cmarl_tc_tile();
+int cmarl_tc_ctas_per_sm(int H, int in_rows, bool train, int out);
 template <class Head, bool TRAIN>
 int cmarl_tc_dispatch(int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
                       int p_net, int grid, cudaStream_t st);
@@ -328,7 +329,8 @@ static int run_chain(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileS
     const int kin = nd.in_rows <= 24 ? 24 : 56;
     const int m = ctx->use_tc ? cmarl_tc_tile() : tile_m(H, kin);
     const int units = units_of(src, m);
-    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    const int slots = ctx->sm_count * (ctx->use_tc ? cmarl_tc_ctas_per_sm(H, nd.in_rows, TRAIN, Head::OUT) : 1);
+    const int grid = units < slots ? units : slots;
     if (grid_out) *grid_out = grid;
     if (ctx->use_tc) return cmarl_tc_dispatch<Head, TRAIN>(H, nd, src, ha, partials, p_net, grid, st);
     return dispatch<Head, TRAIN>(ctx, H, nd, src, ha, partials, p_net, grid, st);
@@ -358,8 +360,9 @@ int cmarl_chain_setup(cmarl_ctx* ctx) {
 extern "C" size_t cmarl_workspace_bytes(const cmarl_ctx* ctx) {
     if (!ctx) return 0;
     // the actor grid may be larger when obs is passed explicitly (21 rows still use the 24-row config)
-    const size_t a = (size_t)ctx->sm_count * (ctx->actor.count + CMARL_N_STATS);
-    const size_t c = (size_t)ctx->sm_count * (ctx->critic.count + CMARL_N_STATS);
+    // up to two persistent CTAs per SM (tensor-core kernels of the 32-wide networks), one partial row per CTA
+    const size_t a = (size_t)2 * ctx->sm_count * (ctx->actor.count + CMARL_N_STATS);
+    const size_t c = (size_t)2 * ctx->sm_count * (ctx->critic.count + CMARL_N_STATS);
     return (a + c) * sizeof(float);
 }
 
@@ -386,7 +389,7 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     cudaStream_t st = as_stream(stream);
     const int Pa = ctx->actor.count, Pc = ctx->critic.count;
     float* part_a = reinterpret_cast<float*>(workspace);
-    float* part_c = part_a + (size_t)ctx->sm_count * (Pa + CMARL_N_STATS);
+    float* part_c = part_a + (size_t)2 * ctx->sm_count * (Pa + CMARL_N_STATS);
 
     NetDesc nda; TileSrc srca;
     actor_desc(ctx, params, state, obs, nda, srca);

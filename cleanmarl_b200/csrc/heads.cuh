@@ -14,19 +14,44 @@ struct PolicyHead {
     static constexpr int NSTAT = 5;     // loss, entropy, kl, clip fraction, valid samples
     using Args = PolicyHeadArgs;
     // MME:530-551, 561-570 for one (b, t, agent) sample; all sums carry the 1/N of `.mean(dim=-1)`.
-    __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
-                                                 bool inb, bool train, float (&dz)[OUT], float (&st)[NSTAT]) {
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) dz[a] = 0.0f;
-        if (!inb) return;
+    // Per-sample inputs, loadable ahead of the network output (the loads' latency then hides behind the GEMMs).
+    struct In {
+        bool live;          // in range and mask == 1
+        uint32_t unavail;   // bit a set: action a is masked out (MME:182)
+        int act;
+        float logp_old, adv;
+    };
+    __device__ static __forceinline__ In load(const Args& h, int t, int g, int b, int G, int B, bool inb) {
+        In in;
+        in.live = false; in.unavail = 0u; in.act = 0; in.logp_old = 0.0f; in.adv = 0.0f;
+        if (!inb) return in;
         const size_t tb = (size_t)t * B + b;
-        if (h.mask && !h.mask[tb]) return;
+        if (h.mask && !h.mask[tb]) return in;
+        in.live = true;
         const size_t tgb = ((size_t)t * G + g) * B + b;
         if (h.avail) {
 #pragma unroll
             for (int a = 0; a < OUT; ++a)
-                if (!h.avail[(((size_t)t * G + g) * h.A + a) * B + b]) z[a] = -1e9f;   // masked_fill, MME:182
+                if (!h.avail[(((size_t)t * G + g) * h.A + a) * B + b]) in.unavail |= 1u << a;
         }
+        in.act = h.actions[tgb];
+        in.logp_old = h.logp_old[tgb];
+        in.adv = h.adv[h.V == 1 ? tb : tgb];
+        return in;
+    }
+    __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
+                                                 bool inb, bool train, float (&dz)[OUT], float (&st)[NSTAT]) {
+        const In in = load(h, t, g, b, G, B, inb);
+        compute(h, in, z, train, dz, st);
+    }
+    __device__ static __forceinline__ void compute(const Args& h, const In& in, float (&z)[OUT], bool train,
+                                                   float (&dz)[OUT], float (&st)[NSTAT]) {
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) dz[a] = 0.0f;
+        if (!in.live) return;
+#pragma unroll
+        for (int a = 0; a < OUT; ++a)
+            if (in.unavail & (1u << a)) z[a] = -1e9f;   // masked_fill, MME:182
         // Categorical(logits=z): logits = z - logsumexp(z); probs = softmax(logits)
         float mx = z[0];
 #pragma unroll
@@ -45,13 +70,13 @@ struct PolicyHead {
         float ent = 0.0f;
 #pragma unroll
         for (int a = 0; a < OUT; ++a) { p[a] = p[a] / se2; ent -= l[a] * p[a]; }
-        const int act = h.actions[tgb];
+        const int act = in.act;
         float logp = l[0];
 #pragma unroll
         for (int a = 1; a < OUT; ++a) logp = (act == a) ? l[a] : logp;
-        const float log_ratio = logp - h.logp_old[tgb];
+        const float log_ratio = logp - in.logp_old;
         const float ratio = expf(log_ratio);
-        const float A = h.adv[h.V == 1 ? tb : tgb];
+        const float A = in.adv;
         const float lo = 1.0f - h.clip, hi = 1.0f + h.clip;
         const float pg1 = A * ratio;
         const float pg2 = A * fminf(fmaxf(ratio, lo), hi);
@@ -74,11 +99,9 @@ struct PolicyHead {
             const float onehot = (act == a) ? 1.0f : 0.0f;
             dz[a] = dlogp * (onehot - p[a]) + we * p[a] * (l[a] + ent);
         }
-        if (h.avail) {
 #pragma unroll
-            for (int a = 0; a < OUT; ++a)
-                if (!h.avail[(((size_t)t * G + g) * h.A + a) * B + b]) dz[a] = 0.0f;
-        }
+        for (int a = 0; a < OUT; ++a)
+            if (in.unavail & (1u << a)) dz[a] = 0.0f;
     }
 };
 
@@ -87,17 +110,37 @@ struct ValueHead {
     static constexpr int NSTAT = 2;     // loss, valid samples
     using Args = ValueHeadArgs;
     // MME:554-558: sum_env mean_agent (V - R)^2 ; forward-only mode just stores V (MME:495,502).
+    struct In {
+        bool inb, live;     // in range; in range and mask == 1
+        float ret;
+        float* vout;        // forward mode: where V goes
+    };
+    __device__ static __forceinline__ In load(const Args& h, int t, int g, int b, int G, int B, bool inb) {
+        In in;
+        in.inb = inb; in.live = false; in.ret = 0.0f; in.vout = nullptr;
+        if (!inb) return in;
+        const size_t tgb = ((size_t)t * G + g) * B + b;
+        if (h.values_out) { in.vout = h.values_out + tgb; return in; }
+        if (h.mask && !h.mask[(size_t)t * B + b]) return in;
+        in.live = true;
+        in.ret = h.returns[tgb];
+        return in;
+    }
     __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
                                                  bool inb, bool train, float (&dz)[OUT], float (&st)[NSTAT]) {
+        const In in = load(h, t, g, b, G, B, inb);
+        compute(h, in, z, train, dz, st);
+    }
+    __device__ static __forceinline__ void compute(const Args& h, const In& in, float (&z)[OUT], bool train,
+                                                   float (&dz)[OUT], float (&st)[NSTAT]) {
         dz[0] = 0.0f;
-        if (!inb) return;
-        const size_t tgb = ((size_t)t * G + g) * B + b;
+        if (!in.inb) return;
         if (!train) {
-            h.values_out[tgb] = z[0];
+            *in.vout = z[0];
             return;
         }
-        if (h.mask && !h.mask[(size_t)t * B + b]) return;
-        const float diff = z[0] - h.returns[tgb];
+        if (!in.live) return;
+        const float diff = z[0] - in.ret;
         st[0] += h.inv_heads * diff * diff;
         st[1] += 1.0f;
         dz[0] = h.inv_heads * 2.0f * diff;

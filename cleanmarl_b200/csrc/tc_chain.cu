@@ -29,18 +29,19 @@ namespace tcchain {
 using namespace chain;
 
 constexpr int M = 128;                        // samples per tile = UMMA M = TMEM lanes
-constexpr int NT = 128;                       // threads per CTA
 constexpr int LBO_K = 128;                    // feature-major (weights): next chunk of 4 K elements
 constexpr int LBO_S = 144;                    // sample-major: next chunk of 4 samples (128 B + 16 B pad: conflict-free STS.32)
 constexpr int SBO_S = (M / 4) * LBO_S;        // 4608: next group of 8 feature rows
 constexpr int KSTEP_S = 2 * LBO_S;            // one MMA consumes 8 samples
-constexpr int A_GROUPS = 8;                   // dH operand: 64 feature rows
 constexpr int B_GROUPS = 5;                   // H1 / X operand: 32 feature rows + the ones group
-constexpr int A_S_BYTES = A_GROUPS * SBO_S;   // per hi / lo image
 constexpr int B_S_BYTES = B_GROUPS * SBO_S;
 
-template <int H_, int K1P_, bool TRAIN_>
+template <int H_, int K1P_, bool TRAIN_, int OUT_>
 struct TCfg {
+    static constexpr int ZX_BYTES = OUT_ * 128 * 4;
+    // dH operand of the weight-gradient GEMMs: H feature rows are stored; an M = 64 MMA also reads rows H..63, which
+    // for H = 32 alias whatever follows (finite or not, they only reach accumulator rows that are never read)
+    static constexpr int A_S_BYTES = (H_ / 8) * SBO_S;        // per hi / lo image
     static constexpr int H = H_, K1P = K1P_;
     static constexpr bool TRAIN = TRAIN_;
     static constexpr int NR2 = H / 32;                    // rounds of the dW2 GEMM (32 H1 features each)
@@ -55,8 +56,8 @@ struct TCfg {
     static constexpr int TMEM_COLS = cEnd <= 32 ? 32 : cEnd <= 64 ? 64 : cEnd <= 128 ? 128 : cEnd <= 256 ? 256 : 512;
     static_assert(cEnd <= 512, "TMEM budget");
     // shared memory (bytes)
-    static constexpr int oBar = 0;                        // mbarrier (8 B) + tmem base (4 B)
-    static constexpr int oW1 = 64;                        // W1 hi | lo   [H][K1P]   K-major core-matrix image
+    static constexpr int oBar = 0;                        // 13 mbarriers + tmem base
+    static constexpr int oW1 = 128;                        // W1 hi | lo   [H][K1P]   K-major core-matrix image
     static constexpr int szW1 = H * K1P * 4;
     static constexpr int oW2 = oW1 + 2 * szW1;            // W2 hi | lo   [H][H]
     static constexpr int szW2 = H * H * 4;
@@ -68,10 +69,12 @@ struct TCfg {
     static constexpr int oDW3 = oB3 + 32;                 // f32 [4 warps][8][H] + [4][8]: dW3 / db3 partial sums per warp
     static constexpr int oDId = oDW3 + (TRAIN ? (4 * 8 * H + 32) * 4 : 0);       // f32 [4][H] folded id-column gradients per agent group
     static constexpr int oRed = oDId + (TRAIN ? 4 * H * 4 : 0);                 // f32 [64]
-    static constexpr int oAs = ((oRed + 256 + 127) / 128) * 128;                // dH sample-major hi | lo
+    static constexpr int oZx = oRed + 64;                                       // f32 [OUT][128]: partial outputs half 1 -> half 0, then dz half 0 -> half 1
+    static constexpr int oAs = ((oZx + ZX_BYTES + 127) / 128) * 128;            // dH sample-major hi | lo
     static constexpr int oBs = oAs + (TRAIN ? 2 * A_S_BYTES : 0);               // H1 / X sample-major hi | lo
     static constexpr int smem_bytes = oBs + (TRAIN ? 2 * B_S_BYTES : 0);
     static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
+    static constexpr int CTAS_PER_SM = smem_bytes <= 113 * 1024 ? 2 : 1;   // two co-resident CTAs double the warps that hide latency
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -101,11 +104,12 @@ __device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// MMA issue (ONE thread).  3xTF32 pass order: (lo,hi), (hi,lo), (hi,hi).
+// MMA issue: called by the whole (converged) issue warp so that descriptors stay in uniform registers; one
+// elected lane executes each tcgen05.mma.  3xTF32 pass order: (lo,hi), (hi,lo), (hi,hi).
 // ------------------------------------------------------------------------------------------------
 // D[128 x N] = A(TMEM, K columns at a_hi / a_lo) * B(smem K-major image [N][K])^T
 template <int N, int K>
-__device__ __forceinline__ void issue_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+__device__ __forceinline__ void issue_ts(bool leader, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
     constexpr uint32_t idesc = tc::make_idesc_tf32(128, N, 0, 0);
     constexpr uint32_t sbo = (K / 4) * LBO_K;
     uint32_t acc = 0;
@@ -115,14 +119,14 @@ __device__ __forceinline__ void issue_ts(uint32_t d, uint32_t a_hi, uint32_t a_l
         const uint64_t db0 = tc::make_smem_desc(pass == 1 ? b_lo : b_hi, LBO_K, sbo, 0);
 #pragma unroll
         for (int ks = 0; ks < K / 8; ++ks) {
-            tc::mma_tf32_ts(d, a + ks * 8, db0 + (uint64_t)((ks * 2 * LBO_K) >> 4), idesc, acc);
+            if (leader) tc::mma_tf32_ts(d, a + ks * 8, db0 + (uint64_t)((ks * 2 * LBO_K) >> 4), idesc, acc);
             acc = 1;
         }
     }
 }
 // D[64 x N] = A(smem sample-major [64][128]) * B(smem sample-major [N][128])^T, contraction over the 128 samples
 template <int N>
-__device__ __forceinline__ void issue_ss(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+__device__ __forceinline__ void issue_ss(bool leader, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
     constexpr uint32_t idesc = tc::make_idesc_tf32(64, N, 0, 0);
     uint32_t acc = 0;
 #pragma unroll
@@ -132,7 +136,7 @@ __device__ __forceinline__ void issue_ss(uint32_t d, uint32_t a_hi, uint32_t a_l
 #pragma unroll
         for (int ks = 0; ks < M / 8; ++ks) {
             const uint64_t off = (uint64_t)((ks * KSTEP_S) >> 4);
-            tc::mma_tf32(d, da0 + off, db0 + off, idesc, acc);
+            if (leader) tc::mma_tf32(d, da0 + off, db0 + off, idesc, acc);
             acc = 1;
         }
     }
@@ -152,7 +156,7 @@ __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
     const float* b2 = W2 + H * H;
     const float* W3 = b2 + H;
     const float* b3 = W3 + nd.out_dim * H;
-    for (int i = threadIdx.x; i < H * K1P; i += NT) {
+    for (int i = threadIdx.x; i < H * K1P; i += 288) {
         const int j = i / K1P, k = i - j * K1P;
         const float w = (k < nd.in_rows) ? W1[j * in_dim + k] : 0.0f;
         float hi, lo;
@@ -161,7 +165,7 @@ __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
         *reinterpret_cast<float*>(sm + C::oW1 + o) = hi;
         *reinterpret_cast<float*>(sm + C::oW1 + C::szW1 + o) = lo;
     }
-    for (int i = threadIdx.x; i < H * H; i += NT) {
+    for (int i = threadIdx.x; i < H * H; i += 288) {
         const int j = i / H, k = i - j * H;
         float hi, lo;
         tc::split_tf32(W2[i], hi, lo);
@@ -175,16 +179,16 @@ __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
         }
     }
     float* fb1 = reinterpret_cast<float*>(sm + C::oB1);
-    for (int i = threadIdx.x; i < 4 * H; i += NT) {
+    for (int i = threadIdx.x; i < 4 * H; i += 288) {
         const int g = i / H, j = i - g * H;
         float v = b1[j];
         if (nd.fold_ids && g < n_groups) v += W1[j * in_dim + nd.in_rows + g];
         fb1[i] = v;
     }
     float* fb2 = reinterpret_cast<float*>(sm + C::oB2);
-    for (int i = threadIdx.x; i < H; i += NT) fb2[i] = b2[i];
+    for (int i = threadIdx.x; i < H; i += 288) fb2[i] = b2[i];
     float* fw3 = reinterpret_cast<float*>(sm + C::oW3T);
-    for (int i = threadIdx.x; i < H * 8; i += NT) {
+    for (int i = threadIdx.x; i < H * 8; i += 288) {
         const int j = i / 8, a = i - j * 8;
         fw3[i] = (a < nd.out_dim) ? W3[a * H + j] : 0.0f;
     }
@@ -192,419 +196,566 @@ __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
     if (threadIdx.x < 8) fb3[threadIdx.x] = (threadIdx.x < nd.out_dim) ? b3[threadIdx.x] : 0.0f;
 }
 
-// sum over the 32 lanes of NV per-lane values: afterwards lane l holds the totals of values
-// {l, l + 32, ...} in v[0], v[1], ... (butterfly reduce-scatter: NV/2 + NV/4 + ... shuffles)
-template <int NV>
-__device__ __forceinline__ void warp_reduce_scatter(float (&v)[NV], int lane) {
-    static_assert(NV % 32 == 0, "NV must be a multiple of 32");
-#pragma unroll
-    for (int w = 16, n = NV; w >= 1; w >>= 1, n >>= 1) {
-        const bool upper = (lane & w) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            // lanes with bit w clear keep the even half [i], the others the odd half [i + n/2]
-            const float send = upper ? v[i] : v[i + n / 2];
-            const float keep = upper ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-        }
-    }
+// ------------------------------------------------------------------------------------------------
+// The kernel: 8 compute warps + 1 MMA-issue warp.
+//   compute thread (cw, lane): TMEM quadrant q = cw & 3, sample s = 32 q + lane, column half hf = cw >> 2:
+//   it owns the 16-column chunks c of the H-wide matrices with (c & 1) == hf and the 8-column chunks of X
+//   with (c & 1) == hf, so both halves carry the same load in every round of the weight-gradient GEMMs.
+//   Hand-offs: compute -> issuer through "ready" mbarriers (256 arrivals), issuer -> compute through
+//   tcgen05.commit on "done" mbarriers; every barrier completes exactly one phase per tile.
+// ------------------------------------------------------------------------------------------------
+// debug timeline: clock64 stamps of CTA 0 (compute thread 0: slots 0..31, issue thread: slots 32..63) for its 2nd tile
+__device__ long long g_tc_timeline[64];
+__device__ int g_tc_timeline_on = 0;
+#define TL_STAMP(slot) do { if (tl_on) g_tc_timeline[slot] = clock64(); } while (0)
+
+constexpr int NCOMP = 256;                    // compute threads
+constexpr int NTHREADS = NCOMP + 32;          // + the issue warp
+enum { R_X = 0, R_H1, R_DH2, R_W2B, R_W1A, R_W1B, D_F1, D_F2, D_B1, D_W2A, D_W2B, D_W1A, D_W1B, N_BARS };
+
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// operands written by this thread (TMEM stores and/or generic-proxy shared stores) -> visible to the issuer's MMAs
+__device__ __forceinline__ void publish(uint64_t* bar) {
+    tc::tmem_wait_st();
+    tc::fence_proxy_async_smem();
+    tc::tcgen05_fence_before();
+    tc::mbar_arrive(bar);
+}
+__device__ __forceinline__ void acquire(uint64_t* bar, uint32_t parity) {
+    mbar_wait_trap(bar, parity);
+    tc::tcgen05_fence_after();
 }
 
-// ------------------------------------------------------------------------------------------------
-// The kernel
-// ------------------------------------------------------------------------------------------------
+// Sum over the 32 lanes of NV per-lane values: butterfly reduce-scatter while more than one value is left
+// (N/2 shuffles per step), plain butterfly afterwards.  v[0] ends up as the total of original index `idx`
+// (every lane a different one when NV == 32; for NV == 16 lanes 2i and 2i+1 hold the same index).
+// Template recursion keeps every array index a compile-time constant (registers, no local memory).
+template <int N, int W, int NV>
+__device__ __forceinline__ void rs_step(float (&v)[NV], int lane, int& idx) {
+    const bool upper = (lane & W) != 0;
+    if constexpr (N > 1) {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float send = upper ? v[i] : v[i + N / 2];
+            const float keep = upper ? v[i + N / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, W);
+        }
+        if (upper) idx += N / 2;
+        if constexpr (W > 1) rs_step<N / 2, W / 2, NV>(v, lane, idx);
+    } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], W);
+        if constexpr (W > 1) rs_step<1, W / 2, NV>(v, lane, idx);
+    }
+}
+template <int NV>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[NV], int lane, int& idx_out) {
+    static_assert(NV == 16 || NV == 32, "16 or 32 values per lane");
+    int idx = 0;
+    rs_step<NV, 16, NV>(v, lane, idx);
+    idx_out = idx;
+}
+
 template <class C, class Head>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NTHREADS, C::CTAS_PER_SM)
 tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict__ partials, int p_net) {
     extern __shared__ __align__(1024) uint8_t sm[];
     constexpr int H = C::H, K1P = C::K1P, OUT = Head::OUT;
     constexpr bool TRAIN = C::TRAIN;
+    constexpr int NOWN = H / 32;                 // 16-column chunks of an H-wide matrix owned by a thread
+    constexpr int NCX = K1P / 8;                 // 8-column chunks of X
+    constexpr int NXO = (NCX + 1) / 2;           // ... owned by a thread (at most)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + C::oBar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::oBar + 16);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::oBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::oBar + N_BARS * 8);
     const int tiles_b = (src.B + M - 1) / M;
     const int units = src.T * src.G * tiles_b;
 
+    // ---- one-time setup (all 288 threads) -------------------------------------------------------------
     load_weights_tc<C>(sm, nd, src.G);
     if (TRAIN) {
-        for (int i = tid * 16; i < 2 * A_S_BYTES + 2 * B_S_BYTES; i += NT * 16)
+        for (int i = tid * 16; i < 2 * C::A_S_BYTES + 2 * B_S_BYTES; i += NTHREADS * 16)
             *reinterpret_cast<uint4*>(sm + C::oAs + i) = make_uint4(0, 0, 0, 0);
         float* z0 = reinterpret_cast<float*>(sm + C::oDW3);
-        for (int i = tid; i < 4 * 8 * H + 32 + 4 * H; i += NT) z0[i] = 0.0f;
+        for (int i = tid; i < 4 * 8 * H + 32 + 4 * H; i += NTHREADS) z0[i] = 0.0f;
     }
     if (tid == 0) {
-        tc::mbar_init(bar, 1);
+        for (int i = 0; i < N_BARS; ++i) tc::mbar_init(&bars[i], i < D_F1 ? NCOMP : 1);
         tc::fence_mbar_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (warp == 8) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
     __syncthreads();
-    if (TRAIN) {
+    if (TRAIN && tid < M) {
         // the ones row (row 0 of group 4 of the B image, hi = 1, lo = 0): its product with dH is the bias gradient
-        float* ones = reinterpret_cast<float*>(sm + C::oBs + smaj(32, tid));
-        *ones = 1.0f;
+        *reinterpret_cast<float*>(sm + C::oBs + smaj(32, tid)) = 1.0f;
     }
     tc::fence_proxy_async_smem();
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);       // this thread's lane
     const uint32_t sbase = tc::smem_u32(sm);
-    uint32_t phase = 0;
 
-    if (TRAIN) {   // running gradient sums (lanes 16-31 of each quadrant) start at zero
-        uint32_t zero[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) zero[i] = 0u;
-        for (int c = C::cW2; c < C::cEnd; c += 8) tmem_st8(tl + c, zero);
-        tc::tmem_wait_st();
-    }
-
-    const float* fb1 = reinterpret_cast<const float*>(sm + C::oB1);
-    const float* fb2 = reinterpret_cast<const float*>(sm + C::oB2);
-    const float* fw3 = reinterpret_cast<const float*>(sm + C::oW3T);
-    const float* fb3 = reinterpret_cast<const float*>(sm + C::oB3);
-    float* dw3acc = reinterpret_cast<float*>(sm + C::oDW3) + warp * 8 * H;                 // [8][H] of this warp
-    float* db3acc = reinterpret_cast<float*>(sm + C::oDW3) + 4 * 8 * H + warp * 8;
-    float* didacc = reinterpret_cast<float*>(sm + C::oDId);
-
-    float st[Head::NSTAT];
-#pragma unroll
-    for (int k = 0; k < Head::NSTAT; ++k) st[k] = 0.0f;
-
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int bt = u % tiles_b, r = u / tiles_b;
-        const int t = r / src.G, g = r % src.G, b0 = bt * M;
-        const int b = b0 + tid;
-        const bool inb = b < src.B;
-
-        // ---- X: coalesced loads (row k of the tile = 128 consecutive floats), split, TMEM ------------
+    if (warp == 8) {
+        // ================================ MMA issue warp ==================================================
         {
-            const float* xp = src.x + (size_t)t * src.stride_t + (size_t)g * src.stride_g + b;
-            float x[K1P];
-#pragma unroll
-            for (int k = 0; k < K1P; ++k) x[k] = (inb && k < nd.in_rows) ? __ldg(xp + (size_t)k * src.B) : 0.0f;
-#pragma unroll
-            for (int c0 = 0; c0 < K1P; c0 += 8) {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float h, l;
-                    tc::split_tf32(x[c0 + i], h, l);
-                    hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(l);
+            const uint32_t As_h = sbase + C::oAs, As_l = As_h + C::A_S_BYTES, Bs_h = sbase + C::oBs, Bs_l = Bs_h + B_S_BYTES;
+            uint32_t par = 0;
+            int it = 0;
+            const bool leader = tc::elect_one();
+            for (int u = blockIdx.x; u < units; u += gridDim.x, par ^= 1, ++it) {
+                const bool tl_on = g_tc_timeline_on == (OUT > 1 ? 2 : 1) && blockIdx.x == 0 && it == 1 && lane == 0;
+                TL_STAMP(32);
+                acquire(&bars[R_X], par);
+                TL_STAMP(33);
+                issue_ts<H, K1P>(leader, tmem + C::cD1, tmem + C::cXh, tmem + C::cXl, sbase + C::oW1, sbase + C::oW1 + C::szW1);
+                if (leader) tc::mma_commit(&bars[D_F1]);
+                TL_STAMP(34);
+                acquire(&bars[R_H1], par);
+                TL_STAMP(35);
+                issue_ts<H, H>(leader, tmem + C::cD2, tmem + C::cAh, tmem + C::cAl, sbase + C::oW2, sbase + C::oW2 + C::szW2);
+                if (leader) tc::mma_commit(&bars[D_F2]);
+                TL_STAMP(36);
+                if (TRAIN) {
+                    acquire(&bars[R_DH2], par);
+                    TL_STAMP(37);
+                    issue_ts<H, H>(leader, tmem + C::cD2, tmem + C::cAh, tmem + C::cAl, sbase + C::oW2T, sbase + C::oW2T + C::szW2);
+                    if (leader) tc::mma_commit(&bars[D_B1]);
+                    TL_STAMP(38);
+                    if (C::NR2 == 1) issue_ss<40>(leader, tmem + C::cW2, As_h, As_l, Bs_h, Bs_l);
+                    else             issue_ss<32>(leader, tmem + C::cW2, As_h, As_l, Bs_h, Bs_l);
+                    if (leader) tc::mma_commit(&bars[D_W2A]);
+                    TL_STAMP(39);
+                    if (C::NR2 == 2) {
+                        acquire(&bars[R_W2B], par);
+                        TL_STAMP(40);
+                        issue_ss<40>(leader, tmem + C::cW2 + 32, As_h, As_l, Bs_h, Bs_l);
+                        if (leader) tc::mma_commit(&bars[D_W2B]);
+                        TL_STAMP(41);
+                    }
+                    acquire(&bars[R_W1A], par);
+                    TL_STAMP(42);
+                    if (C::NR1 == 1) issue_ss<40>(leader, tmem + C::cW1, As_h, As_l, Bs_h, Bs_l);
+                    else             issue_ss<32>(leader, tmem + C::cW1, As_h, As_l, Bs_h, Bs_l);
+                    if (leader) tc::mma_commit(&bars[D_W1A]);
+                    TL_STAMP(43);
+                    if (C::NR1 == 2) {
+                        acquire(&bars[R_W1B], par);
+                        TL_STAMP(44);
+                        issue_ss<40>(leader, tmem + C::cW1 + 32, As_h, As_l, Bs_h, Bs_l);
+                        if (leader) tc::mma_commit(&bars[D_W1B]);
+                        TL_STAMP(45);
+                    }
                 }
-                tmem_st8(tl + C::cXh + c0, hi);
-                tmem_st8(tl + C::cXl + c0, lo);
-            }
-            tc::tmem_wait_st();
-        }
-        tc::tcgen05_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tcgen05_fence_after();
-            issue_ts<H, K1P>(tmem + C::cD1, tmem + C::cXh, tmem + C::cXl, sbase + C::oW1, sbase + C::oW1 + C::szW1);
-            tc::mma_commit(bar);
-        }
-        mbar_wait_trap(bar, phase); phase ^= 1;
-        tc::tcgen05_fence_after();
-
-        // ---- E1: H1 = relu(D1 + b1[g]) -> split -> TMEM A; (train) round-0 features also sample-major into B ----
-#pragma unroll
-        for (int c0 = 0; c0 < H; c0 += 16) {
-            uint32_t v[16], hi[16], lo[16];
-            tc::tmem_ld16(tl + C::cD1 + c0, v);
-            tc::tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float h1 = fmaxf(__uint_as_float(v[i]) + fb1[g * H + c0 + i], 0.0f);
-                float h, l;
-                tc::split_tf32(h1, h, l);
-                hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(l);
-                if (TRAIN && c0 < 32) {
-                    *reinterpret_cast<float*>(sm + C::oBs + smaj(c0 + i, tid)) = h;
-                    *reinterpret_cast<float*>(sm + C::oBs + B_S_BYTES + smaj(c0 + i, tid)) = l;
-                }
-            }
-            tmem_st16(tl + C::cAh + c0, hi);
-            tmem_st16(tl + C::cAl + c0, lo);
-        }
-        tc::tmem_wait_st();
-        tc::tcgen05_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tcgen05_fence_after();
-            issue_ts<H, H>(tmem + C::cD2, tmem + C::cAh, tmem + C::cAl, sbase + C::oW2, sbase + C::oW2 + C::szW2);
-            tc::mma_commit(bar);
-        }
-        mbar_wait_trap(bar, phase); phase ^= 1;
-        tc::tcgen05_fence_after();
-
-        // ---- E2: H2, output layer, head ------------------------------------------------------------------
-        float h2[H];
-#pragma unroll
-        for (int c0 = 0; c0 < H; c0 += 16) {
-            uint32_t v[16];
-            tc::tmem_ld16(tl + C::cD2 + c0, v);
-            tc::tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) h2[c0 + i] = fmaxf(__uint_as_float(v[i]) + fb2[c0 + i], 0.0f);
-        }
-        float z[OUT], dz[OUT];
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) z[a] = fb3[a];
-#pragma unroll
-        for (int j = 0; j < H; ++j) {
-            if (OUT > 1) {
-                const float4 w = *reinterpret_cast<const float4*>(fw3 + j * 8);
-                const float w4 = fw3[j * 8 + 4];
-                z[0] = fmaf(w.x, h2[j], z[0]);
-                z[OUT > 1 ? 1 : 0] = fmaf(w.y, h2[j], z[OUT > 1 ? 1 : 0]);
-                z[OUT > 2 ? 2 : 0] = fmaf(w.z, h2[j], z[OUT > 2 ? 2 : 0]);
-                z[OUT > 3 ? 3 : 0] = fmaf(w.w, h2[j], z[OUT > 3 ? 3 : 0]);
-                z[OUT > 4 ? 4 : 0] = fmaf(w4, h2[j], z[OUT > 4 ? 4 : 0]);
-            } else {
-                z[0] = fmaf(fw3[j * 8], h2[j], z[0]);
             }
         }
-        Head::apply(ha, z, t, g, b, src.G, src.B, inb, TRAIN, dz, st);
         __syncwarp();
+    } else {
+        // ================================ compute warps ====================================================
+        const int q = warp & 3, hf = warp >> 2;
+        const int s = q * 32 + lane;                                    // sample within the tile = TMEM lane
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+        const float* fb1 = reinterpret_cast<const float*>(sm + C::oB1);
+        const float* fb2 = reinterpret_cast<const float*>(sm + C::oB2);
+        const float* fw3 = reinterpret_cast<const float*>(sm + C::oW3T);
+        const float* fb3 = reinterpret_cast<const float*>(sm + C::oB3);
+        float* zx = reinterpret_cast<float*>(sm + C::oZx);              // [2][OUT][128] partial outputs of the two halves
+        float* dw3acc = reinterpret_cast<float*>(sm + C::oDW3) + q * 8 * H;                     // [8][H] of this quadrant
+        float* db3acc = reinterpret_cast<float*>(sm + C::oDW3) + 4 * 8 * H + q * 8;
+        float* didacc = reinterpret_cast<float*>(sm + C::oDId);
+        uint8_t* As_h = sm + C::oAs; uint8_t* As_l = As_h + C::A_S_BYTES;
+        uint8_t* Bs_h = sm + C::oBs; uint8_t* Bs_l = Bs_h + B_S_BYTES;
+        const int so = smaj(0, s);                                      // this sample's offset inside a feature row
 
-        if (TRAIN) {
-            // dW3[a][j] += sum_s dz[s][a] h2[s][j], db3[a] += sum_s dz[s][a]: warp reduce-scatter, per-warp sums
+        if (TRAIN) {   // running gradient sums (lanes 16-31 of each quadrant) start at zero
+            uint32_t zero[8];
 #pragma unroll
-            for (int a = 0; a < OUT; ++a) {
-                float p[H];
-#pragma unroll
-                for (int j = 0; j < H; ++j) p[j] = dz[a] * h2[j];
-                warp_reduce_scatter<H>(p, lane);
-#pragma unroll
-                for (int i = 0; i < H / 32; ++i) {
-                    // after the butterfly lane l holds feature index bit-reversed order: recover it
-                    // (lane bit 4 selected the low index bit of the first split, ...)
-                    int j = 0;
-                    {
-                        // value index path: at step with width w (16,8,4,2,1) and remaining n (H, H/2, ...),
-                        // upper lanes kept the odd half [i + n/2]; so the original index is
-                        // i + sum over steps of (bit ? n_step/2 : 0)
-                        int n = H;
-#pragma unroll
-                        for (int w = 16; w >= 1; w >>= 1) {
-                            if (lane & w) j += n / 2;
-                            n >>= 1;
-                        }
-                        j += i;
-                    }
-                    dw3acc[a * H + j] += p[i];
-                }
-                float d = dz[a];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                if (lane == 0) db3acc[a] += d;
-            }
-            // dH2 = (W3^T dz) . relu'(H2) -> split -> TMEM A (operand of B1) and sample-major A image (operand of dW2)
-#pragma unroll
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int j = c0 + i;
-                    float acc;
-                    if (OUT > 1) {
-                        const float4 w = *reinterpret_cast<const float4*>(fw3 + j * 8);
-                        const float w4 = fw3[j * 8 + 4];
-                        acc = w.x * dz[0];
-                        acc = fmaf(w.y, dz[OUT > 1 ? 1 : 0], acc);
-                        acc = fmaf(w.z, dz[OUT > 2 ? 2 : 0], acc);
-                        acc = fmaf(w.w, dz[OUT > 3 ? 3 : 0], acc);
-                        acc = fmaf(w4, dz[OUT > 4 ? 4 : 0], acc);
-                    } else {
-                        acc = fw3[j * 8] * dz[0];
-                    }
-                    const float d = h2[j] > 0.0f ? acc : 0.0f;
-                    float h, l;
-                    tc::split_tf32(d, h, l);
-                    hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(l);
-                    *reinterpret_cast<float*>(sm + C::oAs + smaj(j, tid)) = h;
-                    *reinterpret_cast<float*>(sm + C::oAs + A_S_BYTES + smaj(j, tid)) = l;
-                }
-                tmem_st16(tl + C::cAh + c0, hi);
-                tmem_st16(tl + C::cAl + c0, lo);
-            }
+            for (int i = 0; i < 8; ++i) zero[i] = 0u;
+            if (hf == 0)
+                for (int c = C::cW2; c < C::cEnd; c += 8) tmem_st8(tl + c, zero);
             tc::tmem_wait_st();
-            tc::fence_proxy_async_smem();
-            tc::tcgen05_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc::tcgen05_fence_after();
-                // B1: D3 (D2's columns) = dH2 W2
-                issue_ts<H, H>(tmem + C::cD2, tmem + C::cAh, tmem + C::cAl, sbase + C::oW2T, sbase + C::oW2T + C::szW2);
-                // dW2 round 0: features 0..31 of H1 (+ the ones group when it is the only round)
-                if (C::NR2 == 1)
-                    issue_ss<40>(tmem + C::cW2, sbase + C::oAs, sbase + C::oAs + A_S_BYTES, sbase + C::oBs, sbase + C::oBs + B_S_BYTES);
-                else
-                    issue_ss<32>(tmem + C::cW2, sbase + C::oAs, sbase + C::oAs + A_S_BYTES, sbase + C::oBs, sbase + C::oBs + B_S_BYTES);
-                tc::mma_commit(bar);
-            }
-            mbar_wait_trap(bar, phase); phase ^= 1;
-            tc::tcgen05_fence_after();
+        }
 
-            // ---- E3: dH1 = D3 . relu'(H1) (H1 > 0  <=>  D1 + b1 > 0) -------------------------------------
-            float dh1[H];
+        float st[Head::NSTAT];
 #pragma unroll
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                uint32_t v[16], d1[16];
-                tc::tmem_ld16(tl + C::cD2 + c0, v);
-                tc::tmem_ld16(tl + C::cD1 + c0, d1);
-                tc::tmem_wait_ld();
+        for (int k = 0; k < Head::NSTAT; ++k) st[k] = 0.0f;
+
+        // X chunks owned by this thread: chunk c = 2 i + hf, i < NXO (chunks >= NCX do not exist)
+        float xr[NXO * 8];
+        auto load_x = [&](int u) {
+            const int bt = u % tiles_b, r = u / tiles_b;
+            const int t = r / src.G, g = r % src.G;
+            const int b = bt * M + s;
+            const float* xp = src.x + (size_t)t * src.stride_t + (size_t)g * src.stride_g + b + (size_t)(8 * hf) * src.B;
+            const size_t step = (size_t)src.B;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float pre = __uint_as_float(d1[i]) + fb1[g * H + c0 + i];
-                    dh1[c0 + i] = pre > 0.0f ? __uint_as_float(v[i]) : 0.0f;
-                    if (C::NR2 == 2 && c0 >= 32) {      // round-1 features of H1, sample-major
+            for (int i = 0; i < NXO; ++i) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int k = 16 * i + 8 * hf + e;
+                    xr[i * 8 + e] = (b < src.B && k < nd.in_rows) ? __ldg(xp + (size_t)(16 * i + e) * step) : 0.0f;
+                }
+            }
+        };
+        if ((int)blockIdx.x < units) load_x(blockIdx.x);
+
+        uint32_t par = 0;
+        int it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, par ^= 1, ++it) {
+            const int bt = u % tiles_b, r = u / tiles_b;
+            const int t = r / src.G, g = r % src.G;
+            const int b = bt * M + s;
+            const bool inb = b < src.B;
+            const bool tl_on = g_tc_timeline_on == (OUT > 1 ? 2 : 1) && blockIdx.x == 0 && it == 1 && tid == 0;
+            TL_STAMP(0);
+
+            // ---- X -> split -> TMEM ------------------------------------------------------------------------
+#pragma unroll
+            for (int i = 0; i < NXO; ++i) {
+                const int c = 2 * i + hf;
+                if (c < NCX) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
                         float h, l;
-                        tc::split_tf32(fmaxf(pre, 0.0f), h, l);
-                        *reinterpret_cast<float*>(sm + C::oBs + smaj(c0 - 32 + i, tid)) = h;
-                        *reinterpret_cast<float*>(sm + C::oBs + B_S_BYTES + smaj(c0 - 32 + i, tid)) = l;
+                        tc::split_tf32(xr[i * 8 + e], h, l);
+                        hi[e] = __float_as_uint(h); lo[e] = __float_as_uint(l);
                     }
+                    tmem_st8(tl + C::cXh + 8 * c, hi);
+                    tmem_st8(tl + C::cXl + 8 * c, lo);
                 }
             }
-            if (C::NR2 == 2) {
-                tc::fence_proxy_async_smem();
-                tc::tcgen05_fence_before();
-                __syncthreads();
-                if (tid == 0) {
-                    tc::tcgen05_fence_after();
-                    issue_ss<40>(tmem + C::cW2 + 32, sbase + C::oAs, sbase + C::oAs + A_S_BYTES, sbase + C::oBs, sbase + C::oBs + B_S_BYTES);
-                    tc::mma_commit(bar);
-                }
-                mbar_wait_trap(bar, phase); phase ^= 1;
-                tc::tcgen05_fence_after();
-            }
-            // ---- dW1 = dH1^T X: A image <- dH1 (dW2 is complete), B image <- X in rounds of 32 features ----
+            publish(&bars[R_X]);
+            TL_STAMP(1);
+            if (u + (int)gridDim.x < units) load_x(u + gridDim.x);       // next tile's rows: latency hidden behind this tile
+            // the head's per-sample inputs (half 0 evaluates the head): loaded now, used after F2
+            const typename Head::In hin = Head::load(ha, t, g, b, src.G, src.B, inb && hf == 0);
+
+            // ---- E1: H1 = relu(D1 + b1[g]) -> split -> TMEM A ---------------------------------------------
+            acquire(&bars[D_F1], par);
+            TL_STAMP(2);
+            uint32_t h1h[NOWN][16], h1l[NOWN][16];                       // kept for the sample-major copies
 #pragma unroll
-            for (int j = 0; j < H; ++j) {
-                float h, l;
-                tc::split_tf32(dh1[j], h, l);
-                *reinterpret_cast<float*>(sm + C::oAs + smaj(j, tid)) = h;
-                *reinterpret_cast<float*>(sm + C::oAs + A_S_BYTES + smaj(j, tid)) = l;
-            }
-#pragma unroll
-            for (int rd = 0; rd < C::NR1; ++rd) {
-#pragma unroll
-                for (int c0 = 0; c0 < 32; c0 += 8) {
-                    const int k0 = rd * 32 + c0;
-                    uint32_t xh[8], xl[8];
-                    if (k0 < K1P) {
-                        tc::tmem_ld8(tl + C::cXh + k0, xh);
-                        tc::tmem_ld8(tl + C::cXl + k0, xl);
-                        tc::tmem_wait_ld();
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { xh[i] = 0u; xl[i] = 0u; }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        *reinterpret_cast<uint32_t*>(sm + C::oBs + smaj(c0 + i, tid)) = xh[i];
-                        *reinterpret_cast<uint32_t*>(sm + C::oBs + B_S_BYTES + smaj(c0 + i, tid)) = xl[i];
-                    }
-                }
-                tc::fence_proxy_async_smem();
-                tc::tcgen05_fence_before();
-                __syncthreads();
-                if (tid == 0) {
-                    tc::tcgen05_fence_after();
-                    if (rd == C::NR1 - 1)
-                        issue_ss<40>(tmem + C::cW1 + 32 * rd, sbase + C::oAs, sbase + C::oAs + A_S_BYTES, sbase + C::oBs, sbase + C::oBs + B_S_BYTES);
-                    else
-                        issue_ss<32>(tmem + C::cW1 + 32 * rd, sbase + C::oAs, sbase + C::oAs + A_S_BYTES, sbase + C::oBs, sbase + C::oBs + B_S_BYTES);
-                    tc::mma_commit(bar);
-                }
-                mbar_wait_trap(bar, phase); phase ^= 1;
-                tc::tcgen05_fence_after();
-            }
-            // ---- per-tile sums (lanes 0-15 of the quadrant) -> running sums (lanes 16-31) ------------------
-#pragma unroll 1
-            for (int c = C::cW2; c < C::cEnd; c += 8) {
-                uint32_t v[8];
-                tc::tmem_ld8(tl + c, v);
+            for (int ci = 0; ci < NOWN; ++ci) {
+                const int c0 = 16 * (2 * ci + hf);
+                uint32_t v[16];
+                tc::tmem_ld16(tl + C::cD1 + c0, v);
                 tc::tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float part = __shfl_sync(0xffffffffu, __uint_as_float(v[i]), lane & 15);
-                    if (lane >= 16) v[i] = __float_as_uint(__uint_as_float(v[i]) + part);
-                }
-                // folded one-hot id column of this agent group: gradient = bias-gradient column of dW1
-                if (nd.fold_ids && c == C::cW1 + 32 * C::NR1 && lane < 16) {
-                    const int row = warp * 16 + lane;
-                    if (row < H) didacc[g * H + row] += __uint_as_float(v[0]);
-                }
-                tmem_st8(tl + c, v);
-            }
-            tc::tmem_wait_st();
-        }
-        // every thread is done with this tile's TMEM / shared operands before the next tile overwrites them
-        tc::tcgen05_fence_before();
-        __syncthreads();
-        tc::tcgen05_fence_after();
-    }
-
-    // ---- write this CTA's partial: gradients in torch parameter order, then the statistics ------------
-    if (TRAIN) {
-        float* out = partials + (size_t)blockIdx.x * (p_net + CMARL_N_STATS);
-        const int in_dim = nd.in_dim;
-        float* gW1 = out;
-        float* gb1 = gW1 + H * in_dim;
-        float* gW2 = gb1 + H;
-        float* gb2 = gW2 + H * H;
-        float* gW3 = gb2 + H;
-        float* gb3 = gW3 + nd.out_dim * H;
-        {
-            // running sums live in lanes 16-31 of each quadrant; every lane executes the (warp-aligned) loads
-            const int row = warp * 16 + (lane - 16);           // gradient row j held by this lane
-            const bool valid = lane >= 16 && row < H;
-            for (int c = 0; c < C::nW2; ++c) {
-                const float v = __uint_as_float(tc::tmem_ld1(tl + C::cW2 + c));
-                if (valid) {
-                    if (c < H) gW2[row * H + c] = v;
-                    else if (c == 32 * C::NR2) gb2[row] = v;
-                }
-            }
-            for (int c = 0; c < C::nW1; ++c) {
-                const float v = __uint_as_float(tc::tmem_ld1(tl + C::cW1 + c));
-                if (valid) {
-                    if (c < nd.in_rows) gW1[row * in_dim + c] = v;
-                    else if (c == 32 * C::NR1) gb1[row] = v;
-                }
-            }
-        }
-        __syncthreads();
-        if (nd.fold_ids)
-            for (int i = tid; i < src.G * H; i += NT) {
-                const int g = i / H, j = i - g * H;
-                gW1[j * in_dim + nd.in_rows + g] = didacc[i];
-            }
-        const float* w3all = reinterpret_cast<const float*>(sm + C::oDW3);
-        for (int i = tid; i < nd.out_dim * H; i += NT)
-            gW3[i] = ((w3all[i] + w3all[8 * H + i]) + w3all[2 * 8 * H + i]) + w3all[3 * 8 * H + i];
-        if (tid < nd.out_dim) {
-            const float* b3all = w3all + 4 * 8 * H;
-            gb3[tid] = ((b3all[tid] + b3all[8 + tid]) + b3all[16 + tid]) + b3all[24 + tid];
-        }
-        float* red = reinterpret_cast<float*>(sm + C::oRed);
+                for (int i4 = 0; i4 < 16; i4 += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(fb1 + g * H + c0 + i4);
+                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-        for (int k = 0; k < Head::NSTAT; ++k) {
-            const float v = warp_sum_f(st[k]);
-            __syncthreads();
-            if (lane == 0) red[warp] = v;
-            __syncthreads();
-            if (tid == 0) out[p_net + k] = ((red[0] + red[1]) + red[2]) + red[3];
+                    for (int e = 0; e < 4; ++e) {
+                        const float h1 = fmaxf(__uint_as_float(v[i4 + e]) + bv[e], 0.0f);
+                        float h, l;
+                        tc::split_tf32(h1, h, l);
+                        h1h[ci][i4 + e] = __float_as_uint(h); h1l[ci][i4 + e] = __float_as_uint(l);
+                    }
+                }
+                tmem_st16(tl + C::cAh + c0, h1h[ci]);
+                tmem_st16(tl + C::cAl + c0, h1l[ci]);
+            }
+            publish(&bars[R_H1]);
+            TL_STAMP(3);
+            if (TRAIN) {
+                // round-0 features of H1 (chunk hf), sample-major, while F2 runs (B image is free: the previous
+                // tile's last weight-gradient round has completed)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    *reinterpret_cast<uint32_t*>(Bs_h + smaj(16 * hf + i, 0) + so) = h1h[0][i];
+                    *reinterpret_cast<uint32_t*>(Bs_l + smaj(16 * hf + i, 0) + so) = h1l[0][i];
+                }
+            }
+
+            // ---- E2: H2, output layer, head ---------------------------------------------------------------
+            TL_STAMP(4);
+            acquire(&bars[D_F2], par);
+            TL_STAMP(5);
+            float h2[NOWN * 16];
+            float z[OUT], dz[OUT];
+#pragma unroll
+            for (int a = 0; a < OUT; ++a) z[a] = 0.0f;
+#pragma unroll
+            for (int ci = 0; ci < NOWN; ++ci) {
+                const int c0 = 16 * (2 * ci + hf);
+                uint32_t v[16];
+                tc::tmem_ld16(tl + C::cD2 + c0, v);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int i4 = 0; i4 < 16; i4 += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(fb2 + c0 + i4);
+                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = c0 + i4 + e;
+                        const float hv = fmaxf(__uint_as_float(v[i4 + e]) + bv[e], 0.0f);
+                        h2[ci * 16 + i4 + e] = hv;
+                        if (OUT > 1) {
+                            const float4 w = *reinterpret_cast<const float4*>(fw3 + j * 8);
+                            const float w4 = fw3[j * 8 + 4];
+                            z[0] = fmaf(w.x, hv, z[0]);
+                            z[OUT > 1 ? 1 : 0] = fmaf(w.y, hv, z[OUT > 1 ? 1 : 0]);
+                            z[OUT > 2 ? 2 : 0] = fmaf(w.z, hv, z[OUT > 2 ? 2 : 0]);
+                            z[OUT > 3 ? 3 : 0] = fmaf(w.w, hv, z[OUT > 3 ? 3 : 0]);
+                            z[OUT > 4 ? 4 : 0] = fmaf(w4, hv, z[OUT > 4 ? 4 : 0]);
+                        } else {
+                            z[0] = fmaf(fw3[j * 8], hv, z[0]);
+                        }
+                    }
+                }
+            }
+            // half 1 hands its partial outputs to half 0, which evaluates the head and hands dz back
+            if (hf == 1) {
+#pragma unroll
+                for (int a = 0; a < OUT; ++a) zx[a * M + s] = z[a];
+            }
+            compute_bar();
+            if (hf == 0) {
+#pragma unroll
+                for (int a = 0; a < OUT; ++a) z[a] = (z[a] + zx[a * M + s]) + fb3[a];
+                Head::compute(ha, hin, z, TRAIN, dz, st);
+                if (TRAIN) {
+#pragma unroll
+                    for (int a = 0; a < OUT; ++a) zx[a * M + s] = dz[a];
+                }
+            }
+            if (TRAIN) {
+                compute_bar();
+                if (hf == 1) {
+#pragma unroll
+                    for (int a = 0; a < OUT; ++a) dz[a] = zx[a * M + s];
+                }
+            }
+            __syncwarp();
+            TL_STAMP(6);
+
+            if (TRAIN) {
+                // dW3[a][j] += sum_s dz[s][a] h2[s][j] over this thread's columns; db3[a] += sum_s dz[s][a]
+#pragma unroll
+                for (int a = 0; a < OUT; ++a) {
+                    float p[NOWN * 16];
+#pragma unroll
+                    for (int i = 0; i < NOWN * 16; ++i) p[i] = dz[a] * h2[i];
+                    int idx;
+                    warp_reduce_scatter<NOWN * 16>(p, lane, idx);
+                    const int j = 16 * (2 * (idx >> 4) + hf) + (idx & 15);
+                    if (NOWN * 16 >= 32 || (lane & 1) == 0) dw3acc[a * H + j] += p[0];
+                    if (hf == 0) {
+                        float d = dz[a];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                        if (lane == 0) db3acc[a] += d;
+                    }
+                }
+                TL_STAMP(7);
+                // dH2 = (W3^T dz) . relu'(H2) -> split -> TMEM A (operand of B1) + sample-major A image (operand of dW2)
+#pragma unroll
+                for (int ci = 0; ci < NOWN; ++ci) {
+                    const int c0 = 16 * (2 * ci + hf);
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int j = c0 + i;
+                        float acc;
+                        if (OUT > 1) {
+                            const float4 w = *reinterpret_cast<const float4*>(fw3 + j * 8);
+                            const float w4 = fw3[j * 8 + 4];
+                            acc = w.x * dz[0];
+                            acc = fmaf(w.y, dz[OUT > 1 ? 1 : 0], acc);
+                            acc = fmaf(w.z, dz[OUT > 2 ? 2 : 0], acc);
+                            acc = fmaf(w.w, dz[OUT > 3 ? 3 : 0], acc);
+                            acc = fmaf(w4, dz[OUT > 4 ? 4 : 0], acc);
+                        } else {
+                            acc = fw3[j * 8] * dz[0];
+                        }
+                        const float d = h2[ci * 16 + i] > 0.0f ? acc : 0.0f;
+                        float h, l;
+                        tc::split_tf32(d, h, l);
+                        hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(l);
+                        *reinterpret_cast<uint32_t*>(As_h + smaj(j, 0) + so) = hi[i];
+                        *reinterpret_cast<uint32_t*>(As_l + smaj(j, 0) + so) = lo[i];
+                    }
+                    tmem_st16(tl + C::cAh + c0, hi);
+                    tmem_st16(tl + C::cAl + c0, lo);
+                }
+                publish(&bars[R_DH2]);          // issuer: B1, then dW2 round 0
+                TL_STAMP(8);
+
+                // ---- E3: dH1 = D3 . relu'(H1) (H1 > 0 <=> D1 + b1 > 0) --------------------------------------
+                acquire(&bars[D_B1], par);
+                TL_STAMP(9);
+                float dh1[NOWN * 16];
+                uint32_t r1h[16], r1l[16];                               // round-1 features of H1 (NR2 == 2)
+#pragma unroll
+                for (int ci = 0; ci < NOWN; ++ci) {
+                    const int c0 = 16 * (2 * ci + hf);
+                    uint32_t v[16], d1[16];
+                    tc::tmem_ld16(tl + C::cD2 + c0, v);
+                    tc::tmem_ld16(tl + C::cD1 + c0, d1);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int i4 = 0; i4 < 16; i4 += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(fb1 + g * H + c0 + i4);
+                        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float pre = __uint_as_float(d1[i4 + e]) + bv[e];
+                            dh1[ci * 16 + i4 + e] = pre > 0.0f ? __uint_as_float(v[i4 + e]) : 0.0f;
+                            if (C::NR2 == 2 && ci == 1) {
+                                float h, l;
+                                tc::split_tf32(fmaxf(pre, 0.0f), h, l);
+                                r1h[i4 + e] = __float_as_uint(h); r1l[i4 + e] = __float_as_uint(l);
+                            }
+                        }
+                    }
+                }
+                TL_STAMP(10);
+                acquire(&bars[D_W2A], par);     // dW2 round 0 complete: the B image is free
+                TL_STAMP(11);
+                if (C::NR2 == 2) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        *reinterpret_cast<uint32_t*>(Bs_h + smaj(16 * hf + i, 0) + so) = r1h[i];
+                        *reinterpret_cast<uint32_t*>(Bs_l + smaj(16 * hf + i, 0) + so) = r1l[i];
+                    }
+                    publish(&bars[R_W2B]);
+                    TL_STAMP(12);
+                    acquire(&bars[D_W2B], par);
+                    TL_STAMP(13);
+                }
+                // ---- dW1 = dH1^T X: A image <- dH1, B image <- X in rounds of 32 features -----------------------
+#pragma unroll
+                for (int ci = 0; ci < NOWN; ++ci) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int j = 16 * (2 * ci + hf) + i;
+                        float h, l;
+                        tc::split_tf32(dh1[ci * 16 + i], h, l);
+                        *reinterpret_cast<float*>(As_h + smaj(j, 0) + so) = h;
+                        *reinterpret_cast<float*>(As_l + smaj(j, 0) + so) = l;
+                    }
+                }
+#pragma unroll
+                for (int rd = 0; rd < C::NR1; ++rd) {
+                    // this thread's X chunks of the round: 4 rd + hf and 4 rd + 2 + hf -> B rows 8 hf.. and 16 + 8 hf..
+#pragma unroll
+                    for (int h2i = 0; h2i < 2; ++h2i) {
+                        const int c = 4 * rd + 2 * h2i + hf;             // X chunk (may not exist: zeros)
+                        uint32_t xh[8], xl[8];
+                        if (c < NCX) {
+                            tc::tmem_ld8(tl + C::cXh + 8 * c, xh);
+                            tc::tmem_ld8(tl + C::cXl + 8 * c, xl);
+                            tc::tmem_wait_ld();
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { xh[i] = 0u; xl[i] = 0u; }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = 16 * h2i + 8 * hf + i;
+                            *reinterpret_cast<uint32_t*>(Bs_h + smaj(row, 0) + so) = xh[i];
+                            *reinterpret_cast<uint32_t*>(Bs_l + smaj(row, 0) + so) = xl[i];
+                        }
+                    }
+                    publish(&bars[rd == 0 ? R_W1A : R_W1B]);
+                    TL_STAMP(14 + 2 * rd);
+                    acquire(&bars[rd == 0 ? D_W1A : D_W1B], par);
+                    TL_STAMP(15 + 2 * rd);
+                }
+                // ---- per-tile sums (lanes 0-15 of the quadrant) -> running sums (lanes 16-31) ------------------
+                // half 0 folds the dW2 | db2 columns, half 1 the dW1 | db1 columns
+                {
+                    const int cb = hf == 0 ? C::cW2 : C::cW1;
+                    const int cn = hf == 0 ? C::nW2 : C::nW1;
+#pragma unroll 1
+                    for (int c = 0; c < cn; c += 8) {
+                        uint32_t v[8];
+                        tc::tmem_ld8(tl + cb + c, v);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float part = __shfl_sync(0xffffffffu, __uint_as_float(v[i]), lane & 15);
+                            if (lane >= 16) v[i] = __float_as_uint(__uint_as_float(v[i]) + part);
+                        }
+                        // folded one-hot id column of this agent group: gradient = bias-gradient column of dW1
+                        if (nd.fold_ids && hf == 1 && c == 32 * C::NR1 && lane < 16) {
+                            const int row = q * 16 + lane;
+                            if (row < H) didacc[g * H + row] += __uint_as_float(v[0]);
+                        }
+                        tmem_st8(tl + cb + c, v);
+                    }
+                    tc::tmem_wait_st();
+                    TL_STAMP(18);
+                    // the next tile's dW MMAs (accumulate = 0) are issued only after every compute thread's next
+                    // R_DH2 arrival, i.e. after this fold: publish() there carries the fence
+                }
+            }
         }
-        if (tid == 0)
-            for (int k = Head::NSTAT; k < CMARL_N_STATS; ++k) out[p_net + k] = 0.0f;
+
+        // ---- write this CTA's partial: gradients in torch parameter order, then the statistics ------------
+        if (TRAIN) {
+            compute_bar();
+            float* out = partials + (size_t)blockIdx.x * (p_net + CMARL_N_STATS);
+            const int in_dim = nd.in_dim;
+            float* gW1 = out;
+            float* gb1 = gW1 + H * in_dim;
+            float* gW2 = gb1 + H;
+            float* gb2 = gW2 + H * H;
+            float* gW3 = gb2 + H;
+            float* gb3 = gW3 + nd.out_dim * H;
+            {
+                // running sums live in lanes 16-31 of each quadrant; every lane executes the (warp-aligned) loads
+                const int row = q * 16 + (lane - 16);               // gradient row j held by this lane
+                const bool valid = lane >= 16 && row < H;
+                if (hf == 0) {
+                    for (int c = 0; c < C::nW2; ++c) {
+                        const float v = __uint_as_float(tc::tmem_ld1(tl + C::cW2 + c));
+                        if (valid) {
+                            if (c < H) gW2[row * H + c] = v;
+                            else if (c == 32 * C::NR2) gb2[row] = v;
+                        }
+                    }
+                } else {
+                    for (int c = 0; c < C::nW1; ++c) {
+                        const float v = __uint_as_float(tc::tmem_ld1(tl + C::cW1 + c));
+                        if (valid) {
+                            if (c < nd.in_rows) gW1[row * in_dim + c] = v;
+                            else if (c == 32 * C::NR1) gb1[row] = v;
+                        }
+                    }
+                }
+            }
+            compute_bar();
+            const int ct = warp * 32 + lane;                        // 0..255
+            if (nd.fold_ids)
+                for (int i = ct; i < src.G * H; i += NCOMP) {
+                    const int gg = i / H, j = i - gg * H;
+                    gW1[j * in_dim + nd.in_rows + gg] = didacc[i];
+                }
+            const float* w3all = reinterpret_cast<const float*>(sm + C::oDW3);
+            for (int i = ct; i < nd.out_dim * H; i += NCOMP)
+                gW3[i] = ((w3all[i] + w3all[8 * H + i]) + w3all[2 * 8 * H + i]) + w3all[3 * 8 * H + i];
+            if (ct < nd.out_dim) {
+                const float* b3all = w3all + 4 * 8 * H;
+                gb3[ct] = ((b3all[ct] + b3all[8 + ct]) + b3all[16 + ct]) + b3all[24 + ct];
+            }
+            float* red = reinterpret_cast<float*>(sm + C::oRed);
+#pragma unroll
+            for (int k = 0; k < Head::NSTAT; ++k) {
+                const float v = warp_sum_f(st[k]);                  // half-1 warps carry zeros
+                compute_bar();
+                if (lane == 0) red[warp] = v;
+                compute_bar();
+                if (ct == 0) out[p_net + k] = ((red[0] + red[1]) + red[2]) + red[3];
+            }
+            if (ct == 0)
+                for (int k = Head::NSTAT; k < CMARL_N_STATS; ++k) out[p_net + k] = 0.0f;
+        }
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, C::TMEM_COLS);
+    if (warp == 8) tc::tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 template <class C, class Head>
@@ -617,7 +768,7 @@ static int tc_set_attr() {
 template <class C, class Head>
 static int tc_launch(const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials, int p_net,
                      int grid, cudaStream_t st) {
-    tc_chain_kernel<C, Head><<<grid, NT, C::smem_bytes, st>>>(nd, src, ha, partials, p_net);
+    tc_chain_kernel<C, Head><<<grid, NTHREADS, C::smem_bytes, st>>>(nd, src, ha, partials, p_net);
     return cmarl_check_cuda(cudaGetLastError(), "tc_chain_kernel launch");
 }
 
@@ -628,9 +779,9 @@ using namespace tcchain;
 int cmarl_tc_setup() {
     int e = 0;
 #define SET(Hh, Kk)                                                             \
-    if (!e) e = tc_set_attr<TCfg<Hh, Kk, true>, PolicyHead>();                  \
-    if (!e) e = tc_set_attr<TCfg<Hh, Kk, true>, ValueHead>();                   \
-    if (!e) e = tc_set_attr<TCfg<Hh, Kk, false>, ValueHead>();
+    if (!e) e = tc_set_attr<TCfg<Hh, Kk, true, 5>, PolicyHead>();               \
+    if (!e) e = tc_set_attr<TCfg<Hh, Kk, true, 1>, ValueHead>();                \
+    if (!e) e = tc_set_attr<TCfg<Hh, Kk, false, 1>, ValueHead>();
     SET(32, 24) SET(32, 56) SET(64, 24) SET(64, 56)
 #undef SET
     return e;
@@ -638,14 +789,33 @@ int cmarl_tc_setup() {
 
 int cmarl_tc_tile() { return M; }
 
+// co-resident CTAs per SM of the kernel that dispatch<Head, TRAIN> would launch (sizes the persistent grid)
+int cmarl_tc_ctas_per_sm(int H, int in_rows, bool train, int out) {
+    const int kin = in_rows <= 24 ? 24 : 56;
+#define CPS(Hh, Kk)                                                                                         \
+    if (H == Hh && kin == Kk)                                                                               \
+        return train ? (out > 1 ? TCfg<Hh, Kk, true, 5>::CTAS_PER_SM : TCfg<Hh, Kk, true, 1>::CTAS_PER_SM)  \
+                     : TCfg<Hh, Kk, false, 1>::CTAS_PER_SM;
+    CPS(32, 24) CPS(32, 56) CPS(64, 24) CPS(64, 56)
+#undef CPS
+    return 1;
+}
+
+// debug aid (not in the public header): enable / read the clock64 timeline of CTA 0's second tile
+extern "C" int cmarl_debug_tc_timeline(int enable, long long* out_host64) {
+    cudaError_t e = cudaMemcpyToSymbol(g_tc_timeline_on, &enable, sizeof(int));
+    if (e == cudaSuccess && out_host64) e = cudaMemcpyFromSymbol(out_host64, g_tc_timeline, sizeof(long long) * 64);
+    return (int)e;
+}
+
 template <class Head, bool TRAIN>
 int cmarl_tc_dispatch(int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
                       int p_net, int grid, cudaStream_t st) {
     const int kin = nd.in_rows <= 24 ? 24 : 56;
-    if (H == 32 && kin == 24) return tc_launch<TCfg<32, 24, TRAIN>, Head>(nd, src, ha, partials, p_net, grid, st);
-    if (H == 32 && kin == 56) return tc_launch<TCfg<32, 56, TRAIN>, Head>(nd, src, ha, partials, p_net, grid, st);
-    if (H == 64 && kin == 24) return tc_launch<TCfg<64, 24, TRAIN>, Head>(nd, src, ha, partials, p_net, grid, st);
-    if (H == 64 && kin == 56) return tc_launch<TCfg<64, 56, TRAIN>, Head>(nd, src, ha, partials, p_net, grid, st);
+    if (H == 32 && kin == 24) return tc_launch<TCfg<32, 24, TRAIN, Head::OUT>, Head>(nd, src, ha, partials, p_net, grid, st);
+    if (H == 32 && kin == 56) return tc_launch<TCfg<32, 56, TRAIN, Head::OUT>, Head>(nd, src, ha, partials, p_net, grid, st);
+    if (H == 64 && kin == 24) return tc_launch<TCfg<64, 24, TRAIN, Head::OUT>, Head>(nd, src, ha, partials, p_net, grid, st);
+    if (H == 64 && kin == 56) return tc_launch<TCfg<64, 56, TRAIN, Head::OUT>, Head>(nd, src, ha, partials, p_net, grid, st);
     cmarl_set_error("tc dispatch: unsupported hidden=%d in_rows=%d", H, nd.in_rows);
     return -1;
 }

@@ -107,6 +107,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+// one lane of the (converged) warp: lets the surrounding code stay warp-uniform so that descriptors live in
+// uniform registers instead of being moved there (R2UR) in front of every MMA
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- descriptors --------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit): start address [0,14) >> 4, leading byte offset [16,30) >> 4,
 // stride byte offset [32,46) >> 4, version [46,48) = 1 (sm_100), base offset [49,52) = 0,

@@ -100,3 +100,62 @@ extern "C" int cmarl_umma_probe(const ProbeArgs* args, uint32_t smem_bytes, void
     umma_probe_kernel<<<1, 128, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(*args);
     return (int)cudaGetLastError();
 }
+
+// ---- micro-benchmark: cycles for `count` back-to-back MMAs rotating over `nacc` accumulators -----------------
+struct BenchArgs {
+    uint32_t m, n, a_tmem, count, nacc, lbo, sbo, kstep;
+    long long* out;     // [2]: cycles from first issue to completion seen, cycles spent issuing
+};
+
+__global__ void __launch_bounds__(128, 1) umma_bench_kernel(BenchArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (uint32_t i = tid * 4; i < 96 * 1024; i += 128 * 4) *reinterpret_cast<float*>(smem + i) = 1.0f;
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async_smem();
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    for (uint32_t c = 0; c < 512; ++c) tc::tmem_st1(tmem + ((uint32_t)(warp * 32) << 16) + c, 0u);
+    tc::tmem_wait_st();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    if (warp == 0) {     // warp-uniform issue loop, one elected lane executes the MMA itself
+        const uint32_t base = tc::smem_u32(smem);
+        const uint32_t idesc = tc::make_idesc_tf32(p.m, p.n, 0, 0);
+        const uint64_t db0 = tc::make_smem_desc(base + 48 * 1024, p.lbo, p.sbo, 0);
+        const uint64_t da0 = tc::make_smem_desc(base, p.lbo, p.sbo, 0);
+        const uint32_t kq = p.kstep >> 4;
+        const long long t0 = clock64();
+        uint32_t acc_i = 0;
+        for (uint32_t i = 0; i < p.count; i += 8) {
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) {
+                const uint32_t d = tmem + acc_i * p.n;
+                if (p.a_tmem) { if (tc::elect_one()) tc::mma_tf32_ts(d, tmem + 384 + k * 8, db0 + k * kq, idesc, 1); }
+                else { if (tc::elect_one()) tc::mma_tf32(d, da0 + k * kq, db0 + k * kq, idesc, 1); }
+                acc_i = acc_i + 1 == p.nacc ? 0 : acc_i + 1;
+            }
+        }
+        const long long t1 = clock64();
+        if (tc::elect_one()) tc::mma_commit(&bar);
+        tc::mbar_wait_bounded(&bar, 0, 1u << 24);
+        const long long t2 = clock64();
+        if (tid == 0) { p.out[0] = t2 - t0; p.out[1] = t1 - t0; }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+extern "C" int cmarl_umma_bench(const BenchArgs* args, void* stream) {
+    cudaError_t e = cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    umma_bench_kernel<<<1, 128, 96 * 1024, reinterpret_cast<cudaStream_t>(stream)>>>(*args);
+    return (int)cudaGetLastError();
+}

@@ -62,7 +62,7 @@ class Engine:
         _lib.check(self.lib.cmarl_ctx_create(C.byref(cfg), C.byref(h)), "cmarl_ctx_create")
         self._h = h
         if tensor_cores is None:
-            tensor_cores = os.environ.get("CMARL_TENSOR_CORES", "0") != "0"
+            tensor_cores = os.environ.get("CMARL_TENSOR_CORES", "1") != "0"
         self.tensor_cores = bool(tensor_cores)
         _lib.check(self.lib.cmarl_ctx_set_tensor_cores(h, int(self.tensor_cores)), "cmarl_ctx_set_tensor_cores")
         self.n_actor = self.lib.cmarl_actor_param_count(h)
