@@ -193,15 +193,16 @@ chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict_
 }
 
 // Fixed-order sum of the per-CTA partials -> flat gradient vector + statistics (deterministic).
-// 64 output columns per CTA; 4 thread groups each sum a quarter of the partial rows (independent
-// loads, 4 in flight per thread) and are combined in a fixed order.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ pa, int grid_a, int Pa,
-                                                              const float* __restrict__ pc, int grid_c, int Pc,
-                                                              float n_groups, float* __restrict__ out) {
-    __shared__ float part[4][64];
-    __shared__ double dpart[4];
-    const int col_l = threadIdx.x & 63, grp = threadIdx.x >> 6;
-    const int i = blockIdx.x * 64 + col_l;
+// 32 output columns per CTA (a warp reads 128 contiguous bytes of one partial row); 32 thread groups each sum
+// 1/32 of the partial rows with 4 independent accumulators, then a fixed-order tree over the groups.
+constexpr int RED_COLS = 32, RED_GROUPS = 32;
+__global__ void __launch_bounds__(RED_COLS * RED_GROUPS) reduce_partials_kernel(const float* __restrict__ pa, int grid_a, int Pa,
+                                                                                const float* __restrict__ pc, int grid_c, int Pc,
+                                                                                float n_groups, float* __restrict__ out) {
+    __shared__ float part[RED_GROUPS][RED_COLS + 1];
+    __shared__ double dpart[RED_GROUPS];
+    const int col_l = threadIdx.x % RED_COLS, grp = threadIdx.x / RED_COLS;
+    const int i = blockIdx.x * RED_COLS + col_l;
     const int P = Pa + Pc;
     const bool valid = i < P + CMARL_N_STATS;
     const float* src = pa;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
             else zero = true;
         }
     }
-    const int per = (n + 3) / 4;
+    const int per = (n + RED_GROUPS - 1) / RED_GROUPS;
     const int c0 = grp * per, c1 = min(n, c0 + per);
     const bool is_count = valid && (i == P + 5);
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
@@ -239,10 +240,18 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     part[grp][col_l] = (a0 + a1) + (a2 + a3);
     if (is_count) dpart[grp] = d;
     __syncthreads();
+    // fixed-order pairwise tree over the 32 groups
+    for (int w = RED_GROUPS / 2; w >= 1; w >>= 1) {
+        if (grp < w) {
+            part[grp][col_l] += part[grp + w][col_l];
+            if (is_count) dpart[grp] += dpart[grp + w];
+        }
+        __syncthreads();
+    }
     if (grp == 0 && valid) {
         if (zero) out[i] = 0.0f;
-        else if (is_count) out[i] = (float)((((dpart[0] + dpart[1]) + dpart[2]) + dpart[3]) / (double)n_groups);
-        else out[i] = ((part[0][col_l] + part[1][col_l]) + part[2][col_l]) + part[3][col_l];
+        else if (is_count) out[i] = (float)(dpart[0] / (double)n_groups);
+        else out[i] = part[0][col_l];
     }
 }
 
@@ -418,7 +427,7 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     const int n_out = Pa + Pc + CMARL_N_STATS;
     {
         KernelTimer kt(ctx, K_PPO_REDUCE, st);
-        reduce_partials_kernel<<<ceil_div(n_out, 64), 256, 0, st>>>(part_a, grid_a, Pa, part_c, grid_c, Pc,
+        reduce_partials_kernel<<<ceil_div(n_out, RED_COLS), RED_COLS * RED_GROUPS, 0, st>>>(part_a, grid_a, Pa, part_c, grid_c, Pc,
                                                                      (float)c.n_agents, grads_out);
     }
     return cmarl_check_cuda(cudaGetLastError(), "reduce_partials_kernel");

@@ -189,16 +189,28 @@ constexpr int ADAM_PER_THREAD = 12;      // supports up to 12 288 parameters
 __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
     __shared__ float wsum[ADAM_THREADS / 32][12];
     __shared__ float tnorm[12];
+    __shared__ double bc_sh[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.tensor_off[a.n_tensors];
     const float* stats = a.grads + P;
     const float count = stats[5];
-    float g[ADAM_PER_THREAD];
+    // every global load is issued up front (one L2 round trip instead of two around the norm reduction)
+    float g[ADAM_PER_THREAD], pm[ADAM_PER_THREAD], pv[ADAM_PER_THREAD], pp[ADAM_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < ADAM_PER_THREAD; ++j) {
         const int i = tid + j * ADAM_THREADS;
-        g[j] = i < P ? a.grads[i] / count : 0.0f;
+        g[j] = i < P ? a.grads[i] : 0.0f;
+        pm[j] = i < P ? a.m[i] : 0.0f;
+        pv[j] = i < P ? a.v[i] : 0.0f;
+        pp[j] = i < P ? a.params[i] : 0.0f;
     }
+    const int step = a.step_dev ? (*a.step_dev + 1) : a.step;
+    if (tid == ADAM_THREADS - 1) {      // a thread of the last warp: the first warps finish the reductions below
+        bc_sh[0] = 1.0 - pow(a.beta1, (double)step);
+        bc_sh[1] = sqrt(1.0 - pow(a.beta2, (double)step));
+    }
+#pragma unroll
+    for (int j = 0; j < ADAM_PER_THREAD; ++j) g[j] = g[j] / count;
     // norm of the per-tensor norms (norm_d, MME:221-224) for each network
     float ss[12];
 #pragma unroll
@@ -236,11 +248,10 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
             coef[net] = c < 1.0f ? c : 1.0f;
         }
     }
-    const int step = a.step_dev ? (*a.step_dev + 1) : a.step;
-    // bias corrections in double, as torch's python-float arithmetic (_single_tensor_adam)
-    const double bc1 = 1.0 - pow(a.beta1, (double)step);
-    const double bc2 = 1.0 - pow(a.beta2, (double)step);
-    const float bc2_sqrt = (float)sqrt(bc2);
+    // bias corrections in double, as torch's python-float arithmetic (_single_tensor_adam); pow() is ~1 000 fp64
+    // instructions, so ONE thread evaluates it (it was done at the top, overlapping the norm reductions)
+    const double bc1 = bc_sh[0];
+    const float bc2_sqrt = (float)bc_sh[1];
     const float w1 = (float)(1.0 - a.beta1);
     const float b2 = (float)a.beta2, w2 = (float)(1.0 - a.beta2);
     const float eps = (float)a.eps;
@@ -253,12 +264,12 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
         const int net = i < actor_end ? 0 : 1;
         float gi = g[j];
         if (a.max_norm > 0.0) gi = gi * coef[net];
-        float m = a.m[i], v = a.v[i];
+        float m = pm[j], v = pv[j];
         m = fmaf(w1, gi - m, m);                // exp_avg.lerp_(grad, 1 - beta1): ATen's lerp is an fma
         v = v * b2;                             // exp_avg_sq.mul_(beta2)
         v = v + (w2 * gi) * gi;                 //            .addcmul_(grad, grad, value=1 - beta2)
         const float denom = sqrtf(v) / bc2_sqrt + eps;
-        a.params[i] = a.params[i] + (nss[net] * m) / denom;   // param.addcdiv_(m, denom, value=-step_size)
+        a.params[i] = pp[j] + (nss[net] * m) / denom;   // param.addcdiv_(m, denom, value=-step_size)
         a.m[i] = m;
         a.v[i] = v;
     }

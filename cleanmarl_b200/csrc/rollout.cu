@@ -2,10 +2,9 @@
 // stand-alone Actor.act / env reset entries.  Compiled with -fmad=false (float64 physics must follow
 // the oracle's rounding); the MLP uses explicit fmaf.
 //
-// Thread mapping: one thread per (env, agent); a CTA owns EPB = 32 envs as 3 warps, warp n = agent n,
-// so every global access is a 128-B coalesced row of the [..][B] layout and the agent index is
-// warp-uniform.  The env state (18 doubles per env) lives in shared memory for the whole episode;
-// the T steps run inside ONE launch (no host round trip per step, MME:408-453).
+// The env state (18 doubles per env) lives in shared memory for the whole episode; the T steps run inside
+// ONE launch (no host round trip per step, MME:408-453).  Thread mapping of the rollout: see rollout_kernel;
+// the stand-alone Actor.act entry keeps one thread per (env, agent).
 #include "common.cuh"
 #include "spread.cuh"
 
@@ -158,91 +157,266 @@ struct RolloutArgs {
     int T, B, O;
 };
 
-template <int H>
-__global__ void __launch_bounds__(RT) rollout_kernel(RolloutArgs a) {
-    extern __shared__ __align__(16) float smf[];
-    using S = ActorSmem<H>;
-    __shared__ double es[18][EPB];
-    __shared__ int acts[NAG][EPB];
+// Rollout kernel.  CTA = 32 envs = 12 warps; warp w = (agent n = w / 4, quarter qq = w % 4), lane = env.
+// The four warps of an agent each own H/4 hidden units of both hidden layers, so every lane of a warp multiplies
+// by the SAME weight: weights are warp-uniform LDS.128 broadcasts (one wavefront per four weights -- the
+// 128 B/clk shared-memory path then sustains the full FFMA rate, which it cannot when every lane needs its own
+// weights), and the 4-way split gives 4x more warps with 4x shorter dependent chains than one thread per
+// (env, agent): B = 4096 is only 12 288 samples per step, a latency problem.  (Measured alternatives, all
+// 0.18-0.21 ms: thread per sample 0.20, four lanes per sample with per-lane weights 0.18 (LSU-bound),
+// constant-bank weights 0.19-0.21 (7.7 KB of weights thrash the uniform cache: ~20 cycles per FFMA).)
+// Hidden activations cross the four warps through shared memory (conflict-free, lane = env).  Per agent the
+// quarter-0 warp samples the action, the quarter-2 warp prepares the race noise meanwhile, and the quarter-1
+// warps run the float64 physics lane-dense ((pair, env), then (agent, env)).
+// The env state (18 doubles per env) lives in shared memory for the whole episode; T steps in ONE launch.
+constexpr int REPB = 32;                 // envs per CTA
+constexpr int NQ = 4;                    // warps per agent
+constexpr int RTHREADS = REPB * NAG * NQ;   // 384
+constexpr int W1LD = 16;                 // layer-1 rows padded to 16 inputs (14 non-zero observation entries)
+
+// debug timeline of CTA 0, step 10 (clock64): slots 0-7 warp (0,0) [sampler], 8-15 warp (0,1) [physics]
+__device__ long long g_roll_tl[16];
+#define RTL(slot, cond) do { if (blockIdx.x == 0 && t == 10 && e == 0 && (cond)) g_roll_tl[slot] = clock64(); } while (0)
+
+__device__ __forceinline__ void agent_bar(int n) { asm volatile("bar.sync %0, 128;" ::"r"(1 + n) : "memory"); }
+
+// reward of agent 0 (pettingzoo_wrapper.py:66) from the distance table: d[3 l + a] = |agent a - landmark l|,
+// d[9], d[10] = |agent 1 - agent 0|, |agent 2 - agent 0|; same operation order as spread::reward_agent0
+__device__ __forceinline__ double reward_from_table(const double* d) {
+    double g = 0.0;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) g = g - fmin(fmin(d[3 * l], d[3 * l + 1]), d[3 * l + 2]);
+    double loc = 0.0;
+    loc = loc - 1.0 * (d[9] < spread::DIST_MIN ? 1.0 : 0.0);
+    loc = loc - 1.0 * (d[10] < spread::DIST_MIN ? 1.0 : 0.0);
+    return g * (1 - spread::LOCAL_RATIO) + loc * spread::LOCAL_RATIO;
+}
+
+template <int H, int O>
+__global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
+    // parameter offsets in the flat actor vector (torch order) and in the shared-memory image
+    constexpr int pW1 = 0, pB1 = pW1 + H * O, pW2 = pB1 + H, pB2 = pW2 + H * H, pW3 = pB2 + H, pB3 = pW3 + NACT * H;
+    constexpr int sW1 = 0, sB1 = sW1 + H * W1LD, sW2 = sB1 + NAG * H, sB2 = sW2 + H * H, sW3 = sB2 + H,
+                  sB3 = sW3 + NACT * H, sEnd = sB3 + 8;
+    constexpr bool FOLD = O > CMARL_RAW_OBS;                   // one-hot agent ids appended to the observation
+    constexpr int JL = H / NQ;                                // hidden units per warp
+    extern __shared__ __align__(16) float dyn[];
+    float* sw = dyn;                                          // W1[H][16] | b1 (+ id column) [3][H] | W2[H][H] | b2 | W3[5][H] | b3
+    float (*hx)[H][REPB] = reinterpret_cast<float (*)[H][REPB]>(dyn + sEnd);                       // [NAG] layer-1 activations of an agent's four warps
+    float (*zp)[NQ][NACT][REPB] = reinterpret_cast<float (*)[NQ][NACT][REPB]>(dyn + sEnd + NAG * H * REPB);   // [NAG] partial logits of the four warps
+    float (*qs)[NACT][REPB] = reinterpret_cast<float (*)[NACT][REPB]>(dyn + sEnd + NAG * H * REPB + NAG * NQ * NACT * REPB);   // [NAG] race noise prepared by the quarter-2 warp
+    __shared__ double es[18][REPB];
+    __shared__ int acts[NAG][REPB];
+    __shared__ double pf[3][REPB][2];                         // contact force of pair (0,1), (0,2), (1,2) on its first entity
+    __shared__ double rd[REPB][12];                           // distance table of the team reward
     const int tid = threadIdx.x;
-    const int n = tid / EPB, e = tid - n * EPB;          // warp n handles agent n
-    const int b = blockIdx.x * EPB + e;
+    const int w = tid >> 5, e = tid & 31;                     // lane = env within the CTA
+    const int n = w >> 2, qq = w & 3;                         // agent, quarter (warp-uniform)
+    const int b = blockIdx.x * REPB + e;
     const bool live = b < a.B;
     const int B = a.B;
-    const bool fold = a.O > CMARL_RAW_OBS;
+    const int j0 = qq * JL;
 
-    load_actor<H>(smf, a.actor, a.O, fold, RT);
-    for (int i = tid; i < 18 * EPB; i += RT) {
-        const int r = i / EPB, c = i - r * EPB;
-        const int bb = blockIdx.x * EPB + c;
+    for (int i = tid; i < 18 * REPB; i += RTHREADS) {
+        const int r = i / REPB, c = i - r * REPB;
+        const int bb = blockIdx.x * REPB + c;
         es[r][c] = (bb < B) ? a.env[(size_t)r * B + bb] : 0.0;
     }
+    {
+        const float* P = a.actor;
+        for (int i = tid; i < H * W1LD; i += RTHREADS) {
+            const int j = i / W1LD, k = i - j * W1LD;
+            sw[sW1 + i] = (k < CMARL_RAW_OBS - 4) ? P[pW1 + j * O + k] : 0.0f;
+        }
+        for (int i = tid; i < NAG * H; i += RTHREADS) {
+            const int g = i / H, j = i - g * H;
+            sw[sB1 + i] = P[pB1 + j] + (FOLD ? P[pW1 + j * O + CMARL_RAW_OBS + g] : 0.0f);   // one-hot id column of agent g
+        }
+        for (int i = tid; i < H * H; i += RTHREADS) sw[sW2 + i] = P[pW2 + i];
+        for (int i = tid; i < H; i += RTHREADS) sw[sB2 + i] = P[pB2 + i];
+        for (int i = tid; i < NACT * H; i += RTHREADS) sw[sW3 + i] = P[pW3 + i];
+        if (tid < 8) sw[sB3 + tid] = tid < NACT ? P[pB3 + tid] : 0.0f;
+    }
     __syncthreads();
-
-    float* col = smf + S::oAct + tid;
-    const float* b1 = smf + S::oB1 + (fold ? n : 3) * H;   // row 3 holds the plain bias
-    double ep_ret = 0.0;
+    double ep_acc = 0.0;                                     // threads 0..REPB-1: episode return of env tid
 
     for (int t = 0; t < a.T; ++t) {
-        double p[6], v[6], lm[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { p[i] = es[i][e]; v[i] = es[6 + i][e]; lm[i] = es[12 + i][e]; }
-        // observation before the action (what the reference stores, MME:426-430)
+        // ---- observation before the action (what the reference stores, MME:426-430): vel, pos, landmarks - pos,
+        //      other agents - pos, 4 zeros (spread::observe); dynamic indices go to shared memory ------------------
+        RTL(0, w == 0); RTL(8, w == 1);
+        const double opx = es[2 * n][e], opy = es[2 * n + 1][e], ovx = es[6 + 2 * n][e], ovy = es[6 + 2 * n + 1][e];
+        const int oj0 = (n == 0) ? 1 : 0, oj1 = (n == 2) ? 1 : 2;          // the other two agents, index order
         float x[CMARL_RAW_OBS];
-        spread::observe(n, p, v, lm, x);
-        if (live) {
+        x[0] = (float)ovx; x[1] = (float)ovy; x[2] = (float)opx; x[3] = (float)opy;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            x[4 + 2 * l] = (float)(es[12 + 2 * l][e] - opx);
+            x[5 + 2 * l] = (float)(es[13 + 2 * l][e] - opy);
+        }
+        x[10] = (float)(es[2 * oj0][e] - opx); x[11] = (float)(es[2 * oj0 + 1][e] - opy);
+        x[12] = (float)(es[2 * oj1][e] - opx); x[13] = (float)(es[2 * oj1 + 1][e] - opy);
+        x[14] = 0.0f; x[15] = 0.0f; x[16] = 0.0f; x[17] = 0.0f;
+        if (live) {   // the agent's four warps share the stores (row k by warp k % 4)
 #pragma unroll
             for (int k = 0; k < CMARL_RAW_OBS; ++k)
-                __stcs(a.state + ((size_t)t * 54 + n * CMARL_RAW_OBS + k) * B + b, x[k]);
+                if ((k & 3) == qq) __stcs(a.state + ((size_t)t * 54 + n * CMARL_RAW_OBS + k) * B + b, x[k]);
             if (a.obs) {
-                float* o = a.obs + ((size_t)t * NAG + n) * a.O * B + b;
+                float* o = a.obs + ((size_t)t * NAG + n) * O * B + b;
 #pragma unroll
-                for (int k = 0; k < CMARL_RAW_OBS; ++k) __stcs(o + (size_t)k * B, x[k]);
-                if (fold)
-                    for (int m = 0; m < NAG; ++m) __stcs(o + (size_t)(CMARL_RAW_OBS + m) * B, m == n ? 1.0f : 0.0f);
+                for (int k = 0; k < CMARL_RAW_OBS; ++k)
+                    if ((k & 3) == qq) __stcs(o + (size_t)k * B, x[k]);
+                if (FOLD && qq < NAG) __stcs(o + (size_t)(CMARL_RAW_OBS + qq) * B, qq == n ? 1.0f : 0.0f);
             }
         }
+        RTL(1, w == 0);
+        // ---- Actor.logits (MME:178-183): layer 1, this warp's JL hidden units; weights = constant-bank operands --
+        {   // JL independent accumulator chains advance together (k outer, j inner)
+            float acc[JL];
+#pragma unroll
+            for (int i = 0; i < JL; ++i) acc[i] = sw[sB1 + n * H + j0 + i];
+#pragma unroll
+            for (int k4 = 0; k4 < W1LD; k4 += 4) {                           // x[14..17] == 0; padded weights are 0
+#pragma unroll
+                for (int i = 0; i < JL; ++i) {
+                    const float4 wv = *reinterpret_cast<const float4*>(sw + sW1 + (j0 + i) * W1LD + k4);   // warp-uniform address
+                    acc[i] = fmaf(x[k4], wv.x, acc[i]); acc[i] = fmaf(x[k4 + 1], wv.y, acc[i]);
+                    acc[i] = fmaf(x[k4 + 2], wv.z, acc[i]); acc[i] = fmaf(x[k4 + 3], wv.w, acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < JL; ++i) hx[n][j0 + i][e] = fmaxf(acc[i], 0.0f);
+        }
+        if (qq == 2) {   // meanwhile: the race noise of this (t, agent, env)
+            float q[NACT];
+            if (a.noise) {
+#pragma unroll
+                for (int k = 0; k < NACT; ++k)
+                    q[k] = live ? __ldcs(a.noise + (((size_t)t * NAG + n) * NACT + k) * B + b) : 1.0f;
+            } else {
+                philox_exp5(a.seed, a.episode, (uint32_t)t, (uint32_t)n, (uint32_t)b, q);
+            }
+#pragma unroll
+            for (int k = 0; k < NACT; ++k) qs[n][k][e] = q[k];
+        }
+        RTL(2, w == 0);
+        agent_bar(n);
+        RTL(3, w == 0);
+        // ---- layer 2 (all H inputs, this warp's JL outputs) and this warp's share of the output layer --------------
+        float h1[H];
+#pragma unroll
+        for (int k = 0; k < H; ++k) h1[k] = hx[n][k][e];
         float z[NACT];
-        actor_mlp<H, CMARL_RAW_OBS>(x, smf, b1, col, RT, z);
-        float q[NACT];
-        if (a.noise) {
 #pragma unroll
-            for (int k = 0; k < NACT; ++k)
-                q[k] = live ? __ldcs(a.noise + (((size_t)t * NAG + n) * NACT + k) * B + b) : 1.0f;
-        } else {
-            philox_exp5(a.seed, a.episode, (uint32_t)t, (uint32_t)n, (uint32_t)b, q);
+        for (int k = 0; k < NACT; ++k) z[k] = 0.0f;
+        {
+            float acc[JL];
+#pragma unroll
+            for (int i = 0; i < JL; ++i) acc[i] = sw[sB2 + j0 + i];
+#pragma unroll
+            for (int k4 = 0; k4 < H; k4 += 4) {
+#pragma unroll
+                for (int i = 0; i < JL; ++i) {
+                    const float4 wv = *reinterpret_cast<const float4*>(sw + sW2 + (j0 + i) * H + k4);      // warp-uniform address
+                    acc[i] = fmaf(h1[k4], wv.x, acc[i]); acc[i] = fmaf(h1[k4 + 1], wv.y, acc[i]);
+                    acc[i] = fmaf(h1[k4 + 2], wv.z, acc[i]); acc[i] = fmaf(h1[k4 + 3], wv.w, acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < JL; ++i) {
+                const float h2 = fmaxf(acc[i], 0.0f);
+#pragma unroll
+                for (int k = 0; k < NACT; ++k) z[k] = fmaf(h2, sw[sW3 + k * H + j0 + i], z[k]);
+            }
         }
-        int action; float lp;
-        race_sample(z, q, action, lp);
-        acts[n][e] = action;
-        if (live) {
-            __stcs(a.actions + ((size_t)t * NAG + n) * B + b, action);
-            __stcs(a.logp + ((size_t)t * NAG + n) * B + b, lp);
+#pragma unroll
+        for (int k = 0; k < NACT; ++k) zp[n][qq][k][e] = z[k];
+        RTL(4, w == 0);
+        agent_bar(n);
+        RTL(5, w == 0);
+        int action = 0;
+        if (qq == 0) {
+            // ---- Categorical sample: quarter sums in fixed order, then the exponential race ------------------------
+            float q[NACT];
+#pragma unroll
+            for (int k = 0; k < NACT; ++k) {
+                z[k] = ((zp[n][0][k][e] + zp[n][1][k][e]) + (zp[n][2][k][e] + zp[n][3][k][e])) + sw[sB3 + k];
+                q[k] = qs[n][k][e];
+            }
+            float lp;
+            race_sample(z, q, action, lp);
+            acts[n][e] = action;
+            if (live) {
+                __stcs(a.actions + ((size_t)t * NAG + n) * B + b, action);
+                __stcs(a.logp + ((size_t)t * NAG + n) * B + b, lp);
+            }
+        }
+        RTL(6, w == 0); RTL(9, w == 1);
+        __syncthreads();
+        RTL(10, w == 1);
+        // ---- physics (World.step), lane-dense float64 on the quarter-1 warps ----------------------------------------
+        // (a) last step's team reward from the distance table (written after the previous state update)
+        if (t > 0 && tid < REPB) {
+            const double r = reward_from_table(rd[tid]);
+            ep_acc += r;
+            if (live) __stcs(a.reward + (size_t)(t - 1) * B + b, (float)r);
+        }
+        if (qq == 1) {
+            // (b) the 3 contact pairs of every env, each evaluated ONCE: warp (n, 1) takes pair n: (0,1), (0,2), (1,2)
+            const int ia = (n == 2) ? 1 : 0, ib = (n == 0) ? 1 : 2;
+            double gx, gy;
+            spread::pair_force(es[2 * ia][e], es[2 * ia + 1][e], es[2 * ib][e], es[2 * ib + 1][e], gx, gy);
+            pf[n][e][0] = gx; pf[n][e][1] = gy;
+            RTL(11, w == 1);
+            asm volatile("bar.sync 4, 96;" ::: "memory");               // the three physics warps
+            RTL(12, w == 1);
+            // (c) integration of agent n; forces added in the reference's pair order (0,1),(0,2),(1,2)
+            const int act = acts[n][e];
+            double ux = 0.0, uy = 0.0;
+            if (act == 1) ux = -1.0;
+            if (act == 2) ux = +1.0;
+            if (act == 3) uy = -1.0;
+            if (act == 4) uy = +1.0;
+            double fx = ux * spread::SENSITIVITY + 0.0;
+            double fy = uy * spread::SENSITIVITY + 0.0;
+            const int p1 = (n == 2) ? 1 : 0, p2 = (n == 0) ? 1 : 2;     // the agent's first / second pair
+            const bool neg1 = (n != 0), neg2 = (n == 2);                // agent is entity b of that pair
+            const double g1x = pf[p1][e][0], g1y = pf[p1][e][1], g2x = pf[p2][e][0], g2y = pf[p2][e][1];
+            fx = (neg1 ? -g1x : g1x) + fx; fy = (neg1 ? -g1y : g1y) + fy;
+            fx = (neg2 ? -g2x : g2x) + fx; fy = (neg2 ? -g2y : g2y) + fy;
+            double px = opx, py = opy, vx = ovx, vy = ovy;
+            spread::integrate(px, py, vx, vy, fx, fy);
+            // every reader of the old state in this phase is a physics warp and passed the bar.sync above
+            es[2 * n][e] = px; es[2 * n + 1][e] = py;
+            es[6 + 2 * n][e] = vx; es[6 + 2 * n + 1][e] = vy;
+            RTL(13, w == 1);
         }
         __syncthreads();
-        // physics: this thread integrates agent n (World.step), forces in the reference's pair order
-        double fx, fy;
-        spread::agent_force(n, p, acts[n][e], fx, fy);
-        double px = p[2 * n], py = p[2 * n + 1], vx = v[2 * n], vy = v[2 * n + 1];
-        spread::integrate(px, py, vx, vy, fx, fy);
-        es[2 * n][e] = px; es[2 * n + 1][e] = py;
-        es[6 + 2 * n][e] = vx; es[6 + 2 * n + 1][e] = vy;
-        __syncthreads();
-        if (n == 0) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) p[i] = es[i][e];
-            const double r = spread::reward_agent0(p, lm);
-            ep_ret += r;
-            if (live) __stcs(a.reward + (size_t)t * B + b, (float)r);
+        RTL(14, w == 1);
+        // (d) distance table of the new state for the team reward: (task, env); tasks 0-8: agent a to landmark l
+        //     (task = 3 l + a), 9-10: agents 1, 2 to agent 0; consumed after the next barrier
+        if (w < 11) {
+            const int task = w;
+            int ea, eb;                                                // rows of es holding the two points
+            if (task < 9) { ea = 2 * (task % 3); eb = 12 + 2 * (task / 3); }
+            else { ea = 2 * (task - 8); eb = 0; }
+            rd[e][task] = spread::dist2d(es[ea][e], es[ea + 1][e], es[eb][e], es[eb + 1][e]);
         }
+        RTL(15, w == 1); RTL(7, w == 0);
     }
     __syncthreads();
-    for (int i = tid; i < 12 * EPB; i += RT) {
-        const int r = i / EPB, c = i - r * EPB;
-        const int bb = blockIdx.x * EPB + c;
+    if (tid < REPB) {
+        const double r = reward_from_table(rd[tid]);
+        ep_acc += r;
+        if (live) {
+            __stcs(a.reward + (size_t)(a.T - 1) * B + b, (float)r);
+            if (a.ep_return) a.ep_return[b] = ep_acc;
+        }
+    }
+    for (int i = tid; i < 12 * REPB; i += RTHREADS) {
+        const int r = i / REPB, c = i - r * REPB;
+        const int bb = blockIdx.x * REPB + c;
         if (bb < B) a.env[(size_t)r * B + bb] = es[r][c];
     }
-    if (n == 0 && live && a.ep_return) a.ep_return[b] = ep_ret;
 }
 
 // ---- K2 alone ------------------------------------------------------------------------------
@@ -351,6 +525,10 @@ size_t actor_smem_bytes() { return (size_t)ActorSmem<H>::oEnd * sizeof(float); }
 
 }  // namespace
 
+extern "C" int cmarl_debug_rollout_timeline(long long* out_host16) {
+    return (int)cudaMemcpyFromSymbol(out_host16, g_roll_tl, sizeof(long long) * 16);
+}
+
 extern "C" int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, void* stream) {
     CMARL_ARG(ctx && env, "null argument");
     const int B = ctx->cfg.n_envs;
@@ -391,16 +569,25 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
     a.actor = actor_params; a.env = env; a.noise = noise; a.seed = seed; a.episode = episode;
     a.state = state; a.obs = obs; a.actions = actions; a.logp = logp; a.reward = reward; a.ep_return = ep_return;
     a.T = ctx->cfg.n_steps; a.B = ctx->cfg.n_envs; a.O = ctx->cfg.obs_dim;
-    const int grid = ceil_div(a.B, EPB);
+    const int grid = ceil_div(a.B, REPB);
     cudaStream_t st = as_stream(stream);
-    if (ctx->cfg.actor_hidden == 32) {
+    const bool ids = a.O > CMARL_RAW_OBS;
+    const int H = ctx->cfg.actor_hidden;
+    const size_t smem = (size_t)(H * W1LD + NAG * H + H * H + H + NACT * H + 8 + NAG * H * REPB + NAG * NQ * NACT * REPB +
+                                 NAG * NACT * REPB) * sizeof(float);
+    if (H == 64) {
+        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    {
         KernelTimer kt(ctx, K_ROLLOUT, st);
-        rollout_kernel<32><<<grid, RT, actor_smem_bytes<32>(), st>>>(a);
-    } else {
-        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)actor_smem_bytes<64>()));
-        KernelTimer kt(ctx, K_ROLLOUT, st);
-        rollout_kernel<64><<<grid, RT, actor_smem_bytes<64>(), st>>>(a);
+        if (H == 32) {
+            if (ids) rollout_kernel<32, 21><<<grid, RTHREADS, smem, st>>>(a);
+            else rollout_kernel<32, 18><<<grid, RTHREADS, smem, st>>>(a);
+        } else {
+            if (ids) rollout_kernel<64, 21><<<grid, RTHREADS, smem, st>>>(a);
+            else rollout_kernel<64, 18><<<grid, RTHREADS, smem, st>>>(a);
+        }
     }
     return cmarl_check_cuda(cudaGetLastError(), "rollout_kernel");
 }

@@ -1,0 +1,18 @@
+import ctypes as C, sys, torch
+sys.path.insert(0, "/root/repo")
+from cleanmarl_b200 import _lib
+from cleanmarl_b200.mappo import MAPPO, Args
+lib = _lib.load()
+tr = MAPPO(Args(batch_size=4096, seed=1))
+for _ in range(3): tr.collect()
+torch.cuda.synchronize()
+buf = (C.c_longlong * 16)()
+lib.cmarl_debug_rollout_timeline(buf)
+v = list(buf)
+names = {0: "S: step start", 1: "S: obs+stores done", 2: "S: L1 done", 3: "S: after agent bar 1", 4: "S: L2+L3 done", 5: "S: after agent bar 2",
+         6: "S: sampling done", 7: "S: step end", 8: "P: step start", 9: "P: before B1", 10: "P: after B1", 11: "P: pair force done",
+         12: "P: after physics bar", 13: "P: integrate done", 14: "P: after B3", 15: "P: dist done"}
+ev = sorted((v[k], k) for k in names if v[k] > 0)
+t0 = ev[0][0]; prev = t0
+for t, k in ev:
+    print(f"{t - t0:8d} (+{t - prev:6d})  {names[k]}"); prev = t
