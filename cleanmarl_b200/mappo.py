@@ -203,7 +203,10 @@ class MAPPO:
     (MME:522-582), gradient all-reduce across GPUs, clip + Adam (MME:584-594)]."""
 
     def __init__(self, args: Args, device_index: int = 0, rank: int = 0, world_size: int = 1, ippo: bool = False,
-                 process_group=None):
+                 process_group=None, engine_factory=Engine):
+        """``engine_factory(shapes, device_index)`` builds the per-GPU kernel front end; the default (and only
+        product) value is ``Engine`` = libcmarl_b200.so.  tests/ pass a CPU test double there to exercise the
+        sharding / all-reduce logic under ``gloo`` without a GPU."""
         validate_args(args)
         if args.batch_size % world_size:
             raise SystemExit(f"--batch_size {args.batch_size} must be divisible by the number of GPUs {world_size}")
@@ -214,7 +217,7 @@ class MAPPO:
                         actor_hidden=args.actor_hidden_dim, actor_layers=args.actor_num_layers,
                         critic_hidden=args.critic_hidden_dim, critic_layers=args.critic_num_layers,
                         critic_on_obs=ippo)
-        self.engine = eng = Engine(shapes, device_index)
+        self.engine = eng = engine_factory(shapes, device_index)
         self.net = ActorCritic(eng, args.seed)                   # identical on every rank (same seed)
         self.exp_avg = torch.zeros_like(self.net.flat)
         self.exp_avg_sq = torch.zeros_like(self.net.flat)

@@ -1,0 +1,179 @@
+"""CPU test double of ``cleanmarl_b200.engine.Engine`` built on the oracle (TEST INFRASTRUCTURE).
+
+It exists so that the host-side logic of ``cleanmarl_b200.mappo.MAPPO`` -- env sharding across ranks, the
+"unnormalised sums + one all-reduce per epoch + identical Adam on every rank" protocol, step counters --
+can run under ``gloo`` with world_size 2 on a machine without a GPU.  It lives in tests/ and is injected
+through ``MAPPO(engine_factory=...)``; nothing in the product imports it.  Same tensors, same device
+layout ([T][.][B], env-minor) and same call signatures as the real engine.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import mappo as om
+from oracle import spread as osp
+
+
+class OracleEngine:
+    tensor_cores = False
+
+    def __init__(self, shapes, device=None):
+        self.shapes = shapes
+        self.device = torch.device("cpu")
+        s = shapes
+        cin = s.obs_dim if s.critic_on_obs else s.state_dim
+        self.n_actor = s.obs_dim * s.actor_hidden + s.actor_hidden + s.actor_hidden ** 2 + s.actor_hidden + \
+            s.n_actions * s.actor_hidden + s.n_actions
+        self.n_critic = cin * s.critic_hidden + s.critic_hidden + s.critic_hidden ** 2 + s.critic_hidden + s.critic_hidden + 1
+        self.n_params = self.n_actor + self.n_critic
+        self.n_heads = s.n_agents if s.critic_on_obs else 1
+        self.launches = 0
+
+    # -- helpers -------------------------------------------------------------------------------
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=dtype)
+
+    def alloc_rollout(self, with_obs=False):
+        s = self.shapes
+        T, B, N = s.n_steps, s.n_envs, s.n_agents
+        return {"state": self.empty(T, s.state_dim, B), "actions": self.empty(T, N, B, dtype=torch.int32),
+                "logp": self.empty(T, N, B), "reward": self.empty(T, B), "ep_return": self.empty(B, dtype=torch.float64),
+                "values": self.empty(T, self.n_heads, B), "returns": self.empty(T, self.n_heads, B),
+                "adv": self.empty(T, self.n_heads, B), "obs": None}
+
+    def _nets(self, flat_actor=None, flat_critic=None):
+        s = self.shapes
+        cin = s.obs_dim if s.critic_on_obs else s.state_dim
+        actor = om.MLP(s.obs_dim, s.actor_hidden, 1, s.n_actions)
+        critic = om.MLP(cin, s.critic_hidden, 1, 1)
+        if flat_actor is not None:
+            actor.load_flat(flat_actor)
+        if flat_critic is not None:
+            critic.load_flat(flat_critic)
+        return actor, critic
+
+    def _obs(self, state):                          # [T][S][B] -> [B,T,N,O]
+        from cleanmarl_b200.engine import obs_from_state
+        return obs_from_state(state, self.shapes.n_agents, self.shapes.obs_dim > 18).permute(3, 0, 1, 2).contiguous()
+
+    # -- entries -------------------------------------------------------------------------------
+    def env_reset(self, env, seed, episode):
+        rng = np.random.default_rng([seed & 0xFFFFFFFF, episode])
+        B = env.shape[1]
+        env[0:6] = torch.from_numpy(rng.uniform(-1, 1, (6, B)))
+        env[6:12] = 0
+        env[12:18] = torch.from_numpy(rng.uniform(-1, 1, (6, B)))
+
+    def rollout(self, actor_params, env, state, actions, logp, reward, *, noise=None, obs=None, ep_return=None,
+                seed=0, episode=0):
+        assert noise is not None, "the CPU test double needs explicit race noise"
+        s = self.shapes
+        B, T = s.n_envs, s.n_steps
+        actor, _ = self._nets(actor_params)
+        e = env.numpy()
+        pos = e[0:6].T.reshape(B, 3, 2).copy(); vel = e[6:12].T.reshape(B, 3, 2).copy(); lm = e[12:18].T.reshape(B, 3, 2).copy()
+        ids = np.broadcast_to(np.eye(3), (B, 3, 3))
+        ret = np.zeros(B)
+        for t in range(T):
+            raw = osp.observe_batched(pos, vel, lm)                                   # [B,3,18] f32
+            o = np.concatenate([raw, ids], -1) if s.obs_dim > 18 else raw
+            with torch.no_grad():
+                z = om.actor_logits(actor, torch.from_numpy(o).float())
+                a, lp = om.race_sample(z, noise[t].permute(2, 0, 1))                   # [B,N,A]
+            state[t] = torch.from_numpy(raw.reshape(B, 54).T.copy())
+            actions[t] = a.t().to(torch.int32)
+            logp[t] = lp.t()
+            pos, vel, rew = osp.step_batched(pos, vel, lm, a.numpy())
+            reward[t] = torch.from_numpy(rew[:, 0].astype(np.float32))
+            ret += rew[:, 0]
+        env[0:6] = torch.from_numpy(pos.reshape(B, 6).T.copy()); env[6:12] = torch.from_numpy(vel.reshape(B, 6).T.copy())
+        if ep_return is not None:
+            ep_return.copy_(torch.from_numpy(ret))
+        self.launches += 1
+
+    def critic_values(self, critic_params, values, *, state=None, obs=None):
+        _, critic = self._nets(None, critic_params)
+        with torch.no_grad():
+            if self.shapes.critic_on_obs:
+                v = critic(self._obs(state)).squeeze(-1)                               # [B,T,N]
+                values.copy_(v.permute(1, 2, 0))
+            else:
+                v = critic(state.permute(2, 0, 1)).squeeze(-1)                          # [B,T]
+                values.copy_(v.t().unsqueeze(1))
+        self.launches += 1
+
+    def td_lambda(self, values, reward, returns, adv, gamma, lam, *, mask=None):
+        B = reward.shape[1]
+        m = torch.ones(B, reward.shape[0], dtype=torch.bool) if mask is None else mask.t().bool()
+        r, a = om.td_lambda_scan(values.permute(2, 0, 1).contiguous(), reward.t().contiguous(), m, gamma, lam)
+        returns.copy_(r.permute(1, 2, 0)); adv.copy_(a.permute(1, 2, 0))
+        self.launches += 1
+
+    def normalize(self, x, n_heads, mode, phase, stats, *, mask=None):
+        T, V, B = (x.shape[0], 1, x.shape[1]) if x.dim() == 2 else x.shape
+        xv = x.reshape(T, V, B)
+        m = torch.ones(T, B, dtype=torch.bool) if mask is None else mask.bool()
+        if phase == 0:
+            hm = xv.mean(dim=1)[m].double()
+            stats[0], stats[1], stats[2], stats[3] = hm.sum(), (hm * hm).sum(), float(hm.numel()), 0.0
+            return
+        n = stats[2]; mean = stats[0] / n
+        var = torch.clamp((stats[1] - stats[0] * mean) / (n - 1.0), min=0.0)
+        mu, sd = mean.float(), torch.sqrt(var).float()
+        if mode == 0:
+            sel = m.unsqueeze(1).expand(T, V, B)
+            xv[sel] = (xv[sel] - mu) / (sd + 1e-6)
+        else:
+            xv.copy_((xv - mu) / sd)
+
+    def ppo_epoch_grads(self, params, grads, *, state=None, obs=None, actions, logp_old, adv, returns, mask=None,
+                        avail=None, clip=0.2, ent_coef=0.001):
+        s = self.shapes
+        actor, critic = self._nets(params[:self.n_actor], params[self.n_actor:])
+        T, B, N = s.n_steps, s.n_envs, s.n_agents
+        o = self._obs(state)
+        m = torch.ones(B, T, dtype=torch.bool) if mask is None else mask.t().bool()
+        av = torch.ones(B, T, N, s.n_actions, dtype=torch.bool) if avail is None else avail.permute(3, 0, 1, 2).bool()
+        exp = lambda x: x.permute(2, 0, 1).expand(B, T, N) if x.shape[1] == 1 else x.permute(2, 0, 1)
+        out = om.ppo_epoch_flat(actor, critic, o, actions.permute(2, 0, 1).long(), logp_old.permute(2, 0, 1),
+                                o if s.critic_on_obs else state.permute(2, 0, 1), av, m, exp(adv), exp(returns), clip, ent_coef)
+        out.actor_loss.backward(); out.critic_loss.backward()
+        n = float(m.sum())
+        grads[:self.n_actor] = actor.flat_grads() * n
+        grads[self.n_actor:self.n_params] = critic.flat_grads() * n
+        st = torch.tensor([out.actor_loss.item(), out.critic_loss.item(), out.entropy.item(), out.kl.item(),
+                           float(out.clipfrac), 1.0, 0.0, 0.0]) * n
+        st[6:] = 0
+        grads[self.n_params:] = st
+        self.launches += 3
+
+    def clip_adam_step(self, params, grads, exp_avg, exp_avg_sq, *, step=1, step_dev=None, lr_actor=8e-4,
+                       lr_critic=8e-4, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=-1.0, stats_out=None):
+        P, na = self.n_params, self.n_actor
+        count = grads[P + 5]
+        g = grads[:P] / count
+        k = int(step_dev.item()) + 1 if step_dev is not None else step
+        actor, critic = self._nets()
+        norms = []
+        for net, lo in ((actor, 0), (critic, na)):
+            off, sq = lo, []
+            for p in net.parameters():
+                sq.append(torch.linalg.vector_norm(g[off:off + p.numel()])); off += p.numel()
+            norms.append(torch.linalg.vector_norm(torch.stack(sq)))
+        for (lo, hi, lr, nrm) in ((0, na, lr_actor, norms[0]), (na, P, lr_critic, norms[1])):
+            gi = g[lo:hi]
+            if max_norm > 0:
+                gi = gi * torch.clamp(max_norm / (nrm + 1e-6), max=1.0)
+            m, v = exp_avg[lo:hi], exp_avg_sq[lo:hi]
+            m.lerp_(gi, 1 - beta1)
+            v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
+            bc1, bc2 = 1 - beta1 ** k, 1 - beta2 ** k
+            denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+            params[lo:hi].addcdiv_(m, denom, value=-(lr / bc1))
+        if stats_out is not None:
+            stats_out[:5] = grads[P:P + 5] / count
+            stats_out[5], stats_out[6], stats_out[7] = norms[0], norms[1], count
+        if step_dev is not None:
+            step_dev.fill_(k)
+        self.launches += 1

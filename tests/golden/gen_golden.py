@@ -6,6 +6,7 @@ Needs ``/root/reference`` (or ``$CMARL_REFERENCE_DIR``); the GPU box never runs 
 reads the committed ``*.npz``.  The reference has no tests or golden vectors of its own
 (SURVEY.md section 4), so every fixture is produced by executing the reference's real code:
 
+g0_args.json       the ``Args`` dataclasses of mappo_multienvs.py / ippo_multienvs.py (names, types, defaults).
 g1_params.npz      ``Actor``/``Critic`` of MME:160-200 built after ``torch.manual_seed`` in the
                    order of MME:329-339 (MAPPO and IPPO shapes).
 g3_sample.npz      ``Actor.act`` (MME:172-176) under a known generator state + the exponential
@@ -37,6 +38,17 @@ from oracle import ref_loader  # noqa: E402
 
 def flat(module):
     return torch.cat([p.detach().reshape(-1) for p in module.parameters()]).numpy()
+
+
+def g0(ref, ref_ippo):
+    """The reference's CLI dataclasses (MME:18-79, ippo_multienvs.py:18-79): field names, types, defaults."""
+    import dataclasses
+    import json
+    out = {}
+    for name, mod in (("mappo_multienvs", ref), ("ippo_multienvs", ref_ippo)):
+        out[name] = [{"name": f.name, "type": getattr(f.type, "__name__", str(f.type)), "default": f.default}
+                     for f in dataclasses.fields(mod.Args)]
+    (HERE / "g0_args.json").write_text(json.dumps(out, indent=1))
 
 
 def g1(ref, ref_ippo):
@@ -143,6 +155,9 @@ def main():
         raise SystemExit("reference sources not found")
     ref = ref_loader.load_module("mappo_multienvs.py")
     ref_ippo = ref_loader.load_module("ippo_multienvs.py")
+    g0(ref, ref_ippo)
+    if "--only-args" in sys.argv:
+        return
     g1(ref, ref_ippo)
     g3(ref)
     g4(ref)

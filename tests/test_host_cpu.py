@@ -1,0 +1,198 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol of include/cmarl_b200.h, the host mirror of
+the reference's CLI / objects behaves like the reference's, missing-GPU paths fail loudly, and the multi-GPU host
+logic (env sharding, one all-reduce of unnormalised sums per epoch, identical Adam on every rank) is exercised
+under ``gloo`` with world_size 2 on a CPU test double of the engine (tests/fake_engine.py)."""
+import ctypes as C
+import dataclasses
+import json
+import os
+import re
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO / "tests"))
+
+
+# ------------------------------------------------------------------------------------------ C ABI
+def header_symbols():
+    text = (REPO / "include" / "cmarl_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cmarl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    from cleanmarl_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 22
+    lib = C.CDLL(str(_lib.LIB_PATH))
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/cmarl_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == syms, "cleanmarl_b200/_lib.py must bind exactly the header's entry points"
+    _lib.load()
+    assert _lib.load().cmarl_version() == 100
+
+
+def test_no_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from cleanmarl_b200 import _lib
+    import cleanmarl_b200 as cm
+    lib = _lib.load()
+    cfg = _lib.Config(0, 64, 25, 3, 21, 54, 5, 32, 1, 64, 1, 0)
+    h = C.c_void_p()
+    rc = lib.cmarl_ctx_create(C.byref(cfg), C.byref(h))
+    assert rc != 0 and not h.value and lib.cmarl_last_error()          # no CPU fallback inside the library
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cm.Engine(cm.Shapes(n_envs=64))
+
+
+def test_ctx_rejects_unsupported_configurations():
+    from cleanmarl_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    for bad in (dict(n_agents=4), dict(n_actions=6), dict(actor_layers=2), dict(actor_hidden=48), dict(obs_dim=20),
+                dict(state_dim=50), dict(n_envs=0)):
+        base = dict(device=0, n_envs=64, n_steps=25, n_agents=3, obs_dim=21, state_dim=54, n_actions=5, actor_hidden=32,
+                    actor_layers=1, critic_hidden=64, critic_layers=1, critic_on_obs=0)
+        base.update(bad)
+        cfg = _lib.Config(*base.values())
+        assert lib.cmarl_ctx_create(C.byref(cfg), C.byref(h)) < 0, bad      # argument error, before any CUDA call
+        assert lib.cmarl_last_error()
+
+
+# ------------------------------------------------------------------------------------------ CLI mirror
+def test_args_mirror_the_reference_dataclass():
+    """Same fields, order, types and defaults as MME:18-79 / ippo_multienvs.py (fixture made from the reference by
+    tests/golden/gen_golden.py); documented deviations: env_type/env_name default to the one implemented env, device
+    defaults to cuda."""
+    from cleanmarl_b200.mappo import Args
+    from cleanmarl_b200.ippo_multienvs import Args as IppoArgs
+    ref = json.loads((REPO / "tests" / "golden" / "g0_args.json").read_text())
+    deviations = {"env_type": "pz", "env_name": "simple_spread_v3", "device": "cuda"}
+    for name, cls in (("mappo_multienvs", Args), ("ippo_multienvs", IppoArgs)):
+        ours = {f.name: f for f in dataclasses.fields(cls)}
+        theirs = {f["name"]: f for f in ref[name]}
+        assert sorted(ours) == sorted(theirs)            # (ippo_multienvs.py lists ppo_clip/entropy_coef before epochs;
+        if name == "mappo_multienvs":                    #  flag order is irrelevant to the keyword CLI)
+            assert list(ours) == list(theirs)
+        for k, f in ours.items():
+            assert getattr(f.type, "__name__", str(f.type)) == theirs[k]["type"], k
+            assert f.default == deviations.get(k, theirs[k]["default"]), k
+
+
+def test_cli_parses_like_tyro_reference_and_rejects_what_is_not_built():
+    import tyro
+    from cleanmarl_b200.mappo import Args, validate_args
+    a = tyro.cli(Args, args=["--batch_size", "4096", "--no-agent-ids", "--td-lambda", "0.9", "--normalize_advantage"])
+    assert a.batch_size == 4096 and a.agent_ids is False and a.td_lambda == 0.9 and a.normalize_advantage is True
+    validate_args(a)
+    for bad in (dict(env_type="smaclite"), dict(env_name="simple_tag_v3"), dict(device="cpu"), dict(optimizer="SGD"),
+                dict(actor_num_layers=2), dict(batch_size=0)):
+        with pytest.raises(SystemExit):
+            validate_args(dataclasses.replace(a, **bad))
+
+
+def test_layout_round_trip_is_bit_exact():
+    """Device layout ([T][.][B], env-minor) <-> the reference's get_batch 8-tuple (MME:148-157): pure transposes."""
+    from cleanmarl_b200 import engine as E
+    from oracle import mappo as om
+    actor, _ = om.build_networks(1)
+    batch = om.synthetic_batch(37, seed=5, actor=actor)
+    d = E.to_device_layout(batch, torch.device("cpu"))
+    back = E.to_reference_layout(d)
+    for i, (x, y) in enumerate(zip(batch, back)):
+        assert x.dtype == y.dtype and torch.equal(x, y), i
+    d2 = {k: v for k, v in d.items() if k != "obs"}
+    back2 = E.to_reference_layout(d2)                     # obs rebuilt from state + one-hot ids
+    assert torch.equal(back2[0], batch[0])
+    adv = torch.randn(37, 25, 1).expand(37, 25, 3).contiguous()
+    assert torch.equal(E.heads_to_reference(E.heads_to_device(adv, 1, "cpu"), 3), adv)
+
+
+# ------------------------------------------------------------------------------------------ host logic on the CPU double
+def _trainer(batch_size, rank=0, world=1, **kw):
+    from cleanmarl_b200.mappo import MAPPO, Args
+    from fake_engine import OracleEngine
+    return MAPPO(Args(batch_size=batch_size, seed=3, **kw), rank=rank, world_size=world,
+                 engine_factory=lambda shapes, dev: OracleEngine(shapes))
+
+
+def _inputs(B, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    env = torch.zeros(18, B, dtype=torch.float64)
+    env[0:6] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    env[12:18] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    noise = torch.empty(25, 3, 5, B).exponential_(1, generator=g)
+    return env, noise
+
+
+def test_trainer_iteration_matches_oracle_update():
+    """MAPPO.iteration (collect -> advantages -> epochs) on the CPU double == the oracle's ppo_update on the same batch."""
+    from oracle import mappo as om
+    B = 12
+    env, noise = _inputs(B)
+    tr = _trainer(B)
+    p0 = tr.net.flat.clone()
+    tr.iteration(env.clone(), noise)
+    assert tr.step == B * 25 and tr.training_step == 3 and tr.num_episodes == B
+    batch = tr.get_batch()
+    actor, critic = om.build_networks(3)
+    assert torch.equal(torch.cat([actor.flat_params(), critic.flat_params()]), p0)      # reference init (seed 3)
+    ret, adv = om.td_lambda_batched(critic, batch[4], batch[3], batch[7], 0.99, 0.95, 3)
+    aopt, copt = om.make_optimizers(actor, critic)
+    st = om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001, flat=True)
+    final = torch.cat([actor.flat_params(), critic.flat_params()])
+    assert (tr.net.flat - final).abs().max() < 1e-6
+    sc = tr.train_scalars()
+    assert abs(sc["actor_loss"] - np.mean(st["actor_loss"])) < 1e-5 * abs(np.mean(st["actor_loss"])) + 1e-7
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _rank_main(rank, world, port, B, out_dir, flags):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    sys.path.insert(0, str(REPO)); sys.path.insert(0, str(REPO / "tests"))
+    env, noise = _inputs(B)
+    per = B // world
+    sl = slice(rank * per, (rank + 1) * per)
+    tr = _trainer(B, rank, world, **flags)
+    assert tr.B == per
+    for _ in range(2):
+        tr.iteration(env[:, sl].clone(), noise[..., sl].contiguous())
+    roll = tr.rollout_scalars()
+    torch.save({"params": tr.net.flat, "stats": tr.epoch_stats, "step": tr.step, "ep_reward": roll["ep_reward"],
+                "episodes": tr.num_episodes}, Path(out_dir) / f"rank{rank}.pt")
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("flags", [{}, {"normalize_advantage": True, "normalize_reward": True, "clip_gradients": 0.5}],
+                         ids=["plain", "normalised+clip"])
+def test_two_ranks_gloo_equal_one_rank(tmp_path, flags):
+    """Envs sharded over 2 ranks (gloo, CPU double) == 1 rank on all envs: same parameters (fp32 reassociation only),
+    identical replicas, global step / episode counters and global normalisation statistics."""
+    import torch.multiprocessing as mp
+    B, world = 16, 2
+    mp.spawn(_rank_main, args=(world, _free_port(), B, str(tmp_path), flags), nprocs=world, join=True)
+    r0, r1 = (torch.load(tmp_path / f"rank{r}.pt") for r in range(world))
+    assert torch.equal(r0["params"], r1["params"]), "replicas must stay bit-identical"
+    assert torch.equal(r0["stats"], r1["stats"])
+    env, noise = _inputs(B)
+    tr = _trainer(B, **flags)
+    for _ in range(2):
+        tr.iteration(env.clone(), noise)
+    assert r0["step"] == tr.step == 2 * B * 25 and r0["episodes"] == tr.num_episodes
+    assert (r0["params"] - tr.net.flat).abs().max() < 2e-6
+    assert (r0["stats"] - tr.epoch_stats).abs().max() < 1e-4 * tr.epoch_stats.abs().max()
+    assert abs(r0["ep_reward"] - tr.rollout_scalars()["ep_reward"]) < 1e-9
