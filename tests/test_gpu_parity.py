@@ -417,3 +417,31 @@ def test_reward_normalisation(cm):
     out = r.permute(1, 0).cpu()
     assert (out - ref)[mask].abs().max() < 2e-6
     assert torch.equal(out[~mask], reward[~mask])
+
+
+# ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
+@pytest.mark.parametrize("flags", ["plain", "flags"])
+def test_two_gpus_nccl_equal_one(cm, tmp_path, flags):
+    """Envs sharded over 2 GPUs (one process per GPU, one NCCL all-reduce of 9 678 floats per epoch) == 1 GPU on all
+    envs: replicas bit-identical to each other, parameters within fp32 reassociation of the single-GPU run."""
+    import socket
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import mgpu_worker
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    B = 1024
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(Path(__file__).resolve().parent / "mgpu_worker.py"), str(tmp_path), str(B), flags]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    two = torch.load(tmp_path / "mgpu.pt")
+    kw = {"normalize_advantage": True, "clip_gradients": 0.5} if flags == "flags" else {}
+    one = mgpu_worker.run(B, 0, 1, 0, **kw)
+    assert two["step"] == one.step
+    assert (two["params"] - one.net.flat.cpu()).abs().max() < 2e-6
+    ref = one.epoch_stats.cpu()
+    assert (two["stats"] - ref).abs().max() < 1e-4 * ref.abs().max()
