@@ -19,6 +19,14 @@ g8_mappo*.npz      one whole iteration of ``mappo_multienvs.py`` executed with `
                    per-epoch statistics and the updated parameters.  ``_flags`` = all
                    normalize_* flags on + gradient clipping.
 g8_ippo.npz        the same for ``ippo_multienvs.py``.
+g1_params.npz      also holds the recurrent ``Actor`` (fc1 + GRUCell + fc2) / ``Critic`` of
+                   ``mappo_lstm_multienvs.py:162-200, 327-338`` (keys ``lstm_*``).
+g3_recurrent.npz   five consecutive ``Actor.act(x, h, avail)`` calls of the recurrent actor
+                   (``mappo_lstm_multienvs.py:170-184``) with the hidden state carried, under a known
+                   generator state + the exponential noise that state produces.
+g8_mappo_lstm*.npz one whole iteration of ``mappo_lstm_multienvs.py`` (rollout with the GRU actor, TD(lambda),
+                   3 epochs of truncated BPTT with an actor Adam step per chunk, ``mappo_lstm_multienvs.py:551-664``);
+                   ``_flags`` = tbptt 7, advantage normalisation, gradient clipping.
 """
 from __future__ import annotations
 
@@ -40,12 +48,15 @@ def flat(module):
     return torch.cat([p.detach().reshape(-1) for p in module.parameters()]).numpy()
 
 
-def g0(ref, ref_ippo):
+def g0(ref, ref_ippo, ref_lstm=None):
     """The reference's CLI dataclasses (MME:18-79, ippo_multienvs.py:18-79): field names, types, defaults."""
     import dataclasses
     import json
     out = {}
-    for name, mod in (("mappo_multienvs", ref), ("ippo_multienvs", ref_ippo)):
+    mods = [("mappo_multienvs", ref), ("ippo_multienvs", ref_ippo)]
+    if ref_lstm is not None:
+        mods.append(("mappo_lstm_multienvs", ref_lstm))
+    for name, mod in mods:
         out[name] = [{"name": f.name, "type": getattr(f.type, "__name__", str(f.type)), "default": f.default}
                      for f in dataclasses.fields(mod.Args)]
     (HERE / "g0_args.json").write_text(json.dumps(out, indent=1))
@@ -70,6 +81,42 @@ def g1(ref, ref_ippo):
     out["mappo_actor_wide"] = flat(a)
     out["mappo_critic_wide"] = flat(c)
     np.savez_compressed(HERE / "g1_params.npz", **out)
+
+
+def g1_lstm(ref_lstm):
+    out = dict(np.load(HERE / "g1_params.npz"))
+    for seed in (1, 7):
+        torch.manual_seed(seed)
+        a = ref_lstm.Actor(21, 32, 5)
+        c = ref_lstm.Critic(54, 64, 1)
+        out[f"lstm_actor_s{seed}"] = flat(a)
+        out[f"lstm_critic_s{seed}"] = flat(c)
+    out["lstm_actor_names"] = np.array([n for n, _ in a.named_parameters()])
+    np.savez_compressed(HERE / "g1_params.npz", **out)
+
+
+def g3_recurrent(ref_lstm):
+    torch.manual_seed(13)
+    actor = ref_lstm.Actor(21, 32, 5)
+    M, steps = 768, 5
+    x = torch.randn(steps, M, 21)
+    avail = torch.ones(steps, M, 5, dtype=torch.bool)
+    avail[:, ::5, 2] = False
+    out = {"params": flat(actor), "x": x.numpy(), "avail": avail.numpy()}
+    with torch.no_grad():
+        torch.manual_seed(77)
+        h = None
+        for t in range(steps):
+            actions, logp, h = actor.act(x[t], h=h, avail_action=avail[t])
+            out[f"actions{t}"] = actions.numpy(); out[f"logp{t}"] = logp.numpy(); out[f"h{t}"] = h.numpy()
+        torch.manual_seed(77)
+        q = torch.stack([torch.empty(M, 5).exponential_(1) for _ in range(steps)])
+        h = None
+        for t in range(steps):
+            z, h = actor.logits(x[t], h, avail[t])
+            out[f"logits{t}"] = z.numpy()
+    out["q"] = q.numpy()
+    np.savez_compressed(HERE / "g3_recurrent.npz", **out)
 
 
 def g3(ref):
@@ -146,6 +193,8 @@ def g8(script, tag, extra, B=6, seed=1):
         "critic_grad_norms": np.array([float(x) for x in g["critic_gradients"]]),
         "step": np.array(g["step"]), "training_step": np.array(g["training_step"]),
     }
+    if hasattr(args, "tbptt"):
+        out["tbptt"] = np.array(args.tbptt)
     np.savez_compressed(HERE / f"g8_{tag}.npz", **out)
     print(tag, "step", g["step"], "actor_losses", g["actor_losses"])
 
@@ -155,8 +204,16 @@ def main():
         raise SystemExit("reference sources not found")
     ref = ref_loader.load_module("mappo_multienvs.py")
     ref_ippo = ref_loader.load_module("ippo_multienvs.py")
-    g0(ref, ref_ippo)
+    g0(ref, ref_ippo, ref_loader.load_module("mappo_lstm_multienvs.py"))
     if "--only-args" in sys.argv:
+        return
+    if "--only-lstm" in sys.argv:
+        ref_lstm = ref_loader.load_module("mappo_lstm_multienvs.py")
+        g1_lstm(ref_lstm)
+        g3_recurrent(ref_lstm)
+        g8("mappo_lstm_multienvs.py", "mappo_lstm", [], seed=4)
+        g8("mappo_lstm_multienvs.py", "mappo_lstm_flags",
+           ["--tbptt", "7", "--normalize_advantage", "--clip_gradients", "0.5"], seed=5)
         return
     g1(ref, ref_ippo)
     g3(ref)
@@ -165,6 +222,12 @@ def main():
     g8("mappo_multienvs.py", "mappo_flags",
        ["--normalize_reward", "--normalize_advantage", "--normalize_return", "--clip_gradients", "0.5"], seed=2)
     g8("ippo_multienvs.py", "ippo", [], seed=3)
+    ref_lstm = ref_loader.load_module("mappo_lstm_multienvs.py")
+    g1_lstm(ref_lstm)
+    g3_recurrent(ref_lstm)
+    g8("mappo_lstm_multienvs.py", "mappo_lstm", [], seed=4)
+    g8("mappo_lstm_multienvs.py", "mappo_lstm_flags",
+       ["--tbptt", "7", "--normalize_advantage", "--clip_gradients", "0.5"], seed=5)
 
 
 if __name__ == "__main__":

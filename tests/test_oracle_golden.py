@@ -138,3 +138,67 @@ def test_scan_matches_loop_bit_exact_given_values(golden):
     ret, adv = om.td_lambda_scan(v.expand(B, Tn, 3), reward, mask, float(g["gamma"]), float(g["td_lambda"]))
     assert np.array_equal(ret.numpy(), g["return_lambda"])
     assert np.array_equal(adv.numpy(), g["advantages"])
+
+
+# ------------------------------------------------------------------ recurrent actor (mappo_lstm_multienvs.py)
+from oracle import mappo_lstm as ol  # noqa: E402
+
+
+def test_g1_recurrent_param_init_bit_exact(golden):
+    g = golden("g1_params")
+    for seed in (1, 7):
+        a, c = ol.build_networks(seed)
+        assert np.array_equal(a.flat_params().numpy(), g[f"lstm_actor_s{seed}"])
+        assert np.array_equal(c.flat_params().numpy(), g[f"lstm_critic_s{seed}"])
+    assert a.flat_params().numel() == 7205
+    assert [n for n, _ in a.named_parameters()] == list(g["lstm_actor_names"])
+
+
+def test_g3_recurrent_act_carries_hidden_state(golden):
+    g = golden("g3_recurrent")
+    actor = ol.GRUActor(21, 32, 5)
+    actor.load_flat(T(g["params"]))
+    h = None
+    for t in range(5):
+        x, avail, q = T(g["x"][t]), T(g["avail"][t]), T(g["q"][t])
+        a, lp, h, z = ol.rollout_act(actor, x[:, None, :], h, avail[:, None, :], q[:, None, :])
+        assert np.array_equal(z[:, 0].numpy(), g[f"logits{t}"])
+        assert np.array_equal(h.numpy(), g[f"h{t}"])
+        assert np.array_equal(a[:, 0].numpy(), g[f"actions{t}"])
+        assert np.array_equal(lp[:, 0].numpy(), g[f"logp{t}"])
+
+
+def test_tbptt_chunks():
+    assert ol.tbptt_chunks(25, 10) == [(0, 10), (10, 20), (20, 25)]
+    assert ol.tbptt_chunks(25, 7) == [(0, 7), (7, 14), (14, 21), (21, 25)]
+    assert ol.tbptt_chunks(25, 25) == [(0, 25)]
+    assert ol.tbptt_chunks(25, 40) == [(0, 25)]
+
+
+@pytest.mark.parametrize("name", ["g8_mappo_lstm", "g8_mappo_lstm_flags"])
+def test_g8_recurrent_whole_iteration(golden, name):
+    """TD(lambda) + truncated-BPTT epochs (actor Adam step per chunk) reproduce the reference run bit for bit."""
+    g = golden(name)
+    actor, critic = ol.build_networks(int(g["seed"]))
+    batch = _batch(g)
+    obs, actions, logp, reward, states, avail, done, mask = batch
+    ret, adv = om.td_lambda_loop(critic, states, reward, mask, float(g["gamma"]), float(g["td_lambda"]), 3)
+    if bool(g["normalize_advantage"]):
+        adv = om.normalize_masked(adv, mask)
+    if bool(g["normalize_return"]):
+        ret = om.normalize_masked(ret, mask)
+    assert np.array_equal(ret.numpy(), g["return_lambda"])
+    assert np.array_equal(adv.numpy(), g["advantages"])
+    aopt, copt = om.make_optimizers(actor, critic, float(g["lr_actor"]), float(g["lr_critic"]))
+    stats = ol.ppo_update_tbptt(actor, critic, aopt, copt, batch, adv, ret, epochs=int(g["epochs"]),
+                                clip=float(g["ppo_clip"]), ent_coef=float(g["entropy_coef"]),
+                                tbptt=int(g["tbptt"]), clip_gradients=float(g["clip_gradients"]))
+    np.testing.assert_array_equal(np.array(stats["actor_loss"]), g["actor_losses"])
+    np.testing.assert_array_equal(np.array(stats["critic_loss"]), g["critic_losses"])
+    np.testing.assert_array_equal(np.array(stats["entropy"]), g["entropies"])
+    np.testing.assert_array_equal(np.array(stats["kl"]), g["kls"])
+    np.testing.assert_array_equal(np.array(stats["clipfrac"]), g["clipfracs"])
+    np.testing.assert_allclose(np.array(stats["actor_grad_norm"]), g["actor_grad_norms"], rtol=1e-7)
+    np.testing.assert_array_equal(np.array(stats["critic_grad_norm"]), g["critic_grad_norms"])
+    assert np.array_equal(actor.flat_params().numpy(), g["actor_final"])
+    assert np.array_equal(critic.flat_params().numpy(), g["critic_final"])
