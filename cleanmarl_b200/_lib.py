@@ -15,7 +15,7 @@ LIB_PATH = Path(os.environ.get("CMARL_B200_LIB", PKG / "libcmarl_b200.so"))
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "device", "n_envs", "n_steps", "n_agents", "obs_dim", "state_dim", "n_actions",
-        "actor_hidden", "actor_layers", "critic_hidden", "critic_layers", "critic_on_obs")]
+        "actor_hidden", "actor_layers", "critic_hidden", "critic_layers", "critic_on_obs", "actor_recurrent")]
 
 
 class CmarlError(RuntimeError):
@@ -48,9 +48,18 @@ _SIGNATURES = {
     "cmarl_ppo_epoch_grads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
     "cmarl_clip_adam_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, C.c_double, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_double, _P, _P]),
+    # recurrent-actor path (mappo_lstm_multienvs.py)
+    "cmarl_actor_act_recurrent": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cmarl_tbptt_chunk_grads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int32,
+                                          C.c_int32, _P, _P, _P, _P]),
+    "cmarl_critic_epoch_grads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cmarl_adam_step_net": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, C.c_double, C.c_double,
+                                      C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
+VERSION = 101          # CMARL_VERSION of include/cmarl_b200.h
+N_KERNEL_IDS = 12      # CMARL_NK
 
 _lib = None
 
@@ -69,8 +78,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.cmarl_version() != 100:
-        raise ImportError(f"libcmarl_b200.so version {lib.cmarl_version()} != 100 (stale build)")
+    if lib.cmarl_version() != VERSION:
+        raise ImportError(f"libcmarl_b200.so version {lib.cmarl_version()} != {VERSION} (stale build)")
     _lib = lib
     return lib
 

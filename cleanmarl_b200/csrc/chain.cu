@@ -198,7 +198,8 @@ chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict_
 constexpr int RED_COLS = 32, RED_GROUPS = 32;
 __global__ void __launch_bounds__(RED_COLS * RED_GROUPS) reduce_partials_kernel(const float* __restrict__ pa, int grid_a, int Pa,
                                                                                 const float* __restrict__ pc, int grid_c, int Pc,
-                                                                                float n_groups, float* __restrict__ out) {
+                                                                                float n_groups, int count_from_c,
+                                                                                float* __restrict__ out) {
     __shared__ float part[RED_GROUPS][RED_COLS + 1];
     __shared__ double dpart[RED_GROUPS];
     const int col_l = threadIdx.x % RED_COLS, grp = threadIdx.x / RED_COLS;
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_GROUPS) reduce_partials_kernel(
         else {
             const int k = i - P;   // out stats: 0 actor loss 1 critic loss 2 entropy 3 kl 4 clipfrac 5 n_valid(b,t)
             if (k == 1) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = Pc + 0; }
+            else if (k == 5 && count_from_c) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = Pc + 1; }   // ValueHead stat 1
             else if (k <= 5) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = Pa + (k == 0 ? 0 : k - 1); }
             else zero = true;
         }
@@ -370,6 +372,7 @@ extern "C" size_t cmarl_workspace_bytes(const cmarl_ctx* ctx) {
     if (!ctx) return 0;
     // the actor grid may be larger when obs is passed explicitly (21 rows still use the 24-row config)
     // up to two persistent CTAs per SM (tensor-core kernels of the 32-wide networks), one partial row per CTA
+    // (the recurrent chunk kernel, gru.cu, launches at most one CTA per SM: covered as well)
     const size_t a = (size_t)2 * ctx->sm_count * (ctx->actor.count + CMARL_N_STATS);
     const size_t c = (size_t)2 * ctx->sm_count * (ctx->critic.count + CMARL_N_STATS);
     return (a + c) * sizeof(float);
@@ -392,6 +395,7 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
                                      const float* returns, const uint8_t* mask, const uint8_t* avail,
                                      double clip, double ent_coef, float* grads_out, void* workspace, void* stream) {
     CMARL_ARG(ctx && params && actions && logp_old && adv && returns && grads_out && workspace, "null argument");
+    CMARL_ARG(!ctx->cfg.actor_recurrent, "recurrent actor: use cmarl_tbptt_chunk_grads + cmarl_critic_epoch_grads");
     CMARL_ARG(state || obs, "state or obs required");
     CMARL_ARG(ctx->cfg.critic_on_obs || state, "MAPPO critic needs state");
     const cmarl_config& c = ctx->cfg;
@@ -428,7 +432,42 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     {
         KernelTimer kt(ctx, K_PPO_REDUCE, st);
         reduce_partials_kernel<<<ceil_div(n_out, RED_COLS), RED_COLS * RED_GROUPS, 0, st>>>(part_a, grid_a, Pa, part_c, grid_c, Pc,
-                                                                     (float)c.n_agents, grads_out);
+                                                                     (float)c.n_agents, 0, grads_out);
     }
     return cmarl_check_cuda(cudaGetLastError(), "reduce_partials_kernel");
+}
+
+// Fixed-order reduction of one network's per-CTA partials (used by the recurrent path, gru.cu): actor-only
+// (pc == nullptr) or critic-only (pa == nullptr; the valid count then comes from the value head's sample count).
+int cmarl_reduce_one_net(cmarl_ctx* ctx, const float* pa, int grid_a, int Pa, const float* pc, int grid_c, int Pc,
+                         float count_div, float* out, cudaStream_t st) {
+    const int n_out = Pa + Pc + CMARL_N_STATS;
+    {
+        KernelTimer kt(ctx, K_PPO_REDUCE, st);
+        reduce_partials_kernel<<<ceil_div(n_out, RED_COLS), RED_COLS * RED_GROUPS, 0, st>>>(pa, grid_a, Pa, pc, grid_c, Pc, count_div,
+                                                                                         pa == nullptr, out);
+    }
+    return cmarl_check_cuda(cudaGetLastError(), "reduce_partials_kernel");
+}
+
+extern "C" int cmarl_critic_epoch_grads(cmarl_ctx* ctx, const float* critic_params, const float* state, const float* obs,
+                                        const float* returns, const uint8_t* mask, float* grads_out, void* workspace,
+                                        void* stream) {
+    CMARL_ARG(ctx && critic_params && returns && grads_out && workspace, "null argument");
+    CMARL_ARG(ctx->cfg.critic_on_obs ? (state || obs) : (state != nullptr), "critic input missing");
+    cudaStream_t st = as_stream(stream);
+    const int Pc = ctx->critic.count;
+    float* part_c = reinterpret_cast<float*>(workspace);
+    NetDesc ndc; TileSrc srcc;
+    critic_desc(ctx, critic_params, state, obs, ndc, srcc);
+    ValueHeadArgs va;
+    va.returns = returns; va.mask = mask; va.values_out = nullptr; va.inv_heads = 1.0f / (float)ctx->n_heads;
+    int grid_c = 0, e;
+    {
+        KernelTimer kt(ctx, K_PPO_CRITIC, st);
+        e = run_chain<ValueHead, true>(ctx, ctx->cfg.critic_hidden, ndc, srcc, va, part_c, Pc, &grid_c, st);
+    }
+    if (e) return e;
+    // the value head counts one sample per (t, head, b): divide by the number of heads for the (b,t) count
+    return cmarl_reduce_one_net(ctx, nullptr, 0, 0, part_c, grid_c, Pc, (float)ctx->n_heads, grads_out, st);
 }

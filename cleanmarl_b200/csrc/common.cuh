@@ -27,9 +27,27 @@ struct NetLayout {
     }
 };
 
+// Offsets of the recurrent actor (fc1 + GRUCell + fc2, mappo_lstm_multienvs.py:162-184) in torch parameters() order.
+struct GruLayout {
+    int in, hid, out;
+    int w1, b1, wih, whh, bih, bhh, w2, b2, count;
+    __host__ __device__ void set(int in_, int hid_, int out_) {
+        in = in_; hid = hid_; out = out_;
+        w1 = 0;
+        b1 = w1 + hid * in;
+        wih = b1 + hid;
+        whh = wih + 3 * hid * hid;
+        bih = whh + 3 * hid * hid;
+        bhh = bih + 3 * hid;
+        w2 = bhh + 3 * hid;
+        b2 = w2 + out * hid;
+        count = b2 + out;
+    }
+};
+
 enum KernelId { K_RESET = 0, K_ENVSTEP, K_ROLLOUT, K_ACT, K_CRITIC, K_TD, K_NORM, K_PPO_ACTOR, K_PPO_CRITIC,
-                K_PPO_REDUCE, K_ADAM };
-static_assert(K_ADAM + 1 == CMARL_NK, "kernel id table");
+                K_PPO_REDUCE, K_ADAM, K_TBPTT };
+static_assert(K_TBPTT + 1 == CMARL_NK, "kernel id table");
 constexpr int CMARL_TIMING_POOL = 256;
 
 struct cmarl_timing {
@@ -42,6 +60,7 @@ struct cmarl_timing {
 struct cmarl_ctx {
     cmarl_config cfg;
     NetLayout actor, critic;
+    GruLayout gru;      // recurrent actor (cfg.actor_recurrent): then actor.count == gru.count
     int n_heads;        // V
     int critic_in;      // S (MAPPO) or O (IPPO)
     int sm_count;

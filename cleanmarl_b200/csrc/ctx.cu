@@ -20,6 +20,7 @@ int cmarl_check_cuda(cudaError_t e, const char* what) {
 }
 
 int cmarl_chain_setup(cmarl_ctx* ctx);   // chain.cu: shared-memory attributes + grid sizes
+int cmarl_gru_setup(cmarl_ctx* ctx);     // gru.cu: shared-memory attributes of the recurrent kernels
 
 extern "C" int cmarl_version(void) { return CMARL_VERSION; }
 extern "C" const char* cmarl_last_error(void) { return g_err; }
@@ -38,6 +39,8 @@ extern "C" int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out) {
     CMARL_ARG(cfg->actor_hidden == 32 || cfg->actor_hidden == 64, "actor_hidden_dim must be 32 or 64");
     CMARL_ARG(cfg->critic_hidden == 32 || cfg->critic_hidden == 64, "critic_hidden_dim must be 32 or 64");
     CMARL_ARG(cfg->critic_on_obs == 0 || cfg->critic_on_obs == 1, "critic_on_obs must be 0 or 1");
+    CMARL_ARG(cfg->actor_recurrent == 0 || cfg->actor_recurrent == 1, "actor_recurrent must be 0 or 1");
+    CMARL_ARG(!cfg->actor_recurrent || cfg->actor_hidden == 32, "the recurrent actor is built for actor_hidden_dim 32 only");
     int ndev = 0;
     CMARL_CUDA(cudaGetDeviceCount(&ndev));
     CMARL_ARG(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device (there is no CPU fallback)");
@@ -56,8 +59,11 @@ extern "C" int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out) {
     ctx->critic_in = cfg->critic_on_obs ? cfg->obs_dim : cfg->state_dim;
     ctx->actor.set(cfg->obs_dim, cfg->actor_hidden, cfg->n_actions);
     ctx->critic.set(ctx->critic_in, cfg->critic_hidden, 1);
+    ctx->gru.set(cfg->obs_dim, cfg->actor_hidden, cfg->n_actions);
+    if (cfg->actor_recurrent) ctx->actor.count = ctx->gru.count;
     ctx->sm_count = prop.multiProcessorCount;
     int e = cmarl_chain_setup(ctx);
+    if (!e) e = cmarl_gru_setup(ctx);
     if (e) { free(ctx); return e; }
     *out = ctx;
     return 0;
@@ -121,7 +127,7 @@ extern "C" int cmarl_timing_read(cmarl_ctx* ctx, double* sum_ms, int64_t* launch
 extern "C" const char* cmarl_kernel_name(int id) {
     static const char* names[CMARL_NK] = {"env_reset", "env_step", "rollout", "actor_act", "critic_values",
                                           "td_lambda_scan", "normalize", "ppo_actor_chain", "ppo_critic_chain",
-                                          "ppo_reduce_partials", "clip_adam"};
+                                          "ppo_reduce_partials", "clip_adam", "ppo_tbptt_chunk"};
     return (id >= 0 && id < CMARL_NK) ? names[id] : "?";
 }
 

@@ -178,6 +178,8 @@ struct AdamArgs {
     int tensor_off[13];     // prefix offsets of the 12 parameter tensors, [12] = P
     int n_actor_tensors;    // 6
     double lr[2], beta1, beta2, eps, max_norm;
+    float extra_div;        // grads are divided by stats[5] * extra_div (T_chunk of a truncated-BPTT chunk, else 1)
+    int raw_stats;          // 1: stats_out = the five sums undivided, this step's norm, the valid count (single-net mode)
 };
 
 // Single CTA of 1024 threads: 9 670 parameters is <= 10 per thread, so every gradient is loaded once
@@ -193,7 +195,8 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.tensor_off[a.n_tensors];
     const float* stats = a.grads + P;
-    const float count = stats[5];
+    const float n_valid = stats[5];
+    const float count = n_valid * a.extra_div;
     // every global load is issued up front (one L2 round trip instead of two around the norm reduction)
     float g[ADAM_PER_THREAD], pm[ADAM_PER_THREAD], pv[ADAM_PER_THREAD], pp[ADAM_PER_THREAD];
 #pragma unroll
@@ -275,7 +278,12 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
     }
     __syncthreads();
     if (tid == 0) {
-        if (a.stats_out) {
+        if (a.stats_out && a.raw_stats) {
+            for (int k = 0; k < 5; ++k) a.stats_out[k] = stats[k];
+            a.stats_out[5] = net_norm[0];
+            a.stats_out[6] = n_valid;
+            a.stats_out[7] = 0.0f;
+        } else if (a.stats_out) {
             for (int k = 0; k < 5; ++k) a.stats_out[k] = stats[k] / count;
             a.stats_out[5] = net_norm[0];
             a.stats_out[6] = net_norm[1];
@@ -291,6 +299,7 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
                                     float* stats_out, void* stream) {
     CMARL_ARG(ctx && params && grads && exp_avg && exp_avg_sq, "null argument");
     CMARL_ARG(step_dev || step >= 1, "step must be >= 1");
+    CMARL_ARG(!ctx->cfg.actor_recurrent, "recurrent actor: use cmarl_adam_step_net");
     CMARL_ARG(ctx->actor.count + ctx->critic.count <= ADAM_THREADS * ADAM_PER_THREAD, "too many parameters for clip_adam_kernel");
     AdamArgs a;
     a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
@@ -306,6 +315,44 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     }
     a.tensor_off[12] = base;
     a.lr[0] = lr_actor; a.lr[1] = lr_critic; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
+    a.extra_div = 1.0f; a.raw_stats = 0;
+    {
+        KernelTimer kt(ctx, K_ADAM, as_stream(stream));
+        clip_adam_kernel<<<1, ADAM_THREADS, 0, as_stream(stream)>>>(a);
+    }
+    return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
+}
+
+// One network at a time (recurrent path: the actor is stepped once per truncated-BPTT chunk, the critic once
+// per epoch; mappo_lstm_multienvs.py:605-619, 646-655).  Same kernel: every tensor belongs to "net 0".
+extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, const float* grads, float* exp_avg,
+                                   float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr, double beta1,
+                                   double beta2, double eps, double max_norm, double extra_div, float* stats_out,
+                                   void* stream) {
+    CMARL_ARG(ctx && params && grads && exp_avg && exp_avg_sq, "null argument");
+    CMARL_ARG(net == 0 || net == 1, "net must be 0 (actor) or 1 (critic)");
+    CMARL_ARG(step_dev || step >= 1, "step must be >= 1");
+    CMARL_ARG(extra_div >= 1.0, "extra_div must be >= 1");
+    AdamArgs a;
+    a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
+    a.step_dev = step_dev; a.step = step;
+    int k = 0;
+    if (net == 0 && ctx->cfg.actor_recurrent) {
+        const GruLayout& L = ctx->gru;
+        const int offs[8] = {L.w1, L.b1, L.wih, L.whh, L.bih, L.bhh, L.w2, L.b2};
+        for (int j = 0; j < 8; ++j) a.tensor_off[k++] = offs[j];
+        a.tensor_off[k] = L.count;
+    } else {
+        const NetLayout& L = net == 0 ? ctx->actor : ctx->critic;
+        const int offs[6] = {L.w1, L.b1, L.w2, L.b2, L.w3, L.b3};
+        for (int j = 0; j < 6; ++j) a.tensor_off[k++] = offs[j];
+        a.tensor_off[k] = L.count;
+    }
+    for (int j = k + 1; j < 13; ++j) a.tensor_off[j] = a.tensor_off[k];
+    a.n_tensors = k; a.n_actor_tensors = k;
+    CMARL_ARG(a.tensor_off[k] <= ADAM_THREADS * ADAM_PER_THREAD, "too many parameters for clip_adam_kernel");
+    a.lr[0] = lr; a.lr[1] = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
+    a.extra_div = (float)extra_div; a.raw_stats = 1;
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
         clip_adam_kernel<<<1, ADAM_THREADS, 0, as_stream(stream)>>>(a);

@@ -192,12 +192,30 @@ __device__ __forceinline__ double reward_from_table(const double* d) {
     return g * (1 - spread::LOCAL_RATIO) + loc * spread::LOCAL_RATIO;
 }
 
-template <int H, int O>
+// GRU = true: the recurrent actor of mappo_lstm_multienvs.py:162-184 (fc1 + GRUCell + fc2); the hidden state of every
+// (agent, env) lives in shared memory for the whole episode (zeros at t = 0, mappo_lstm_multienvs.py:406), double
+// buffered because each of an agent's four warps reads all H old values and writes its own H/4 new ones.
+template <int H, int O, bool GRU>
+struct RolloutLayout {
+    // parameter offsets in the flat actor vector (torch order)
+    static constexpr int pW1 = 0, pB1 = pW1 + H * O;
+    static constexpr int pW2 = pB1 + H, pB2 = pW2 + H * H;                                    // MLP: layer 2
+    static constexpr int pWih = pB1 + H, pWhh = pWih + 3 * H * H, pBih = pWhh + 3 * H * H, pBhh = pBih + 3 * H;   // GRU
+    static constexpr int pW3 = GRU ? pBhh + 3 * H : pB2 + H, pB3 = pW3 + NACT * H;            // output layer (fc2)
+    // shared-memory image (float offsets)
+    static constexpr int sW1 = 0, sB1 = sW1 + H * W1LD;
+    static constexpr int sW2 = sB1 + NAG * H, sB2 = sW2 + H * H;                              // MLP
+    static constexpr int sWih = sB1 + NAG * H, sWhh = sWih + 3 * H * H, sBg = sWhh + 3 * H * H;   // GRU: native [3H][H] x2, bias [H][4]
+    static constexpr int sW3 = GRU ? sBg + 4 * H : sB2 + H, sB3 = sW3 + NACT * H, sEnd = sB3 + 8;
+    static constexpr int nHS = GRU ? 2 * NAG * H * REPB : 0;                                  // hidden state, double buffered
+    static constexpr int floats = sEnd + NAG * H * REPB + NAG * NQ * NACT * REPB + NAG * NACT * REPB + nHS;
+};
+
+template <int H, int O, bool GRU>
 __global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
-    // parameter offsets in the flat actor vector (torch order) and in the shared-memory image
-    constexpr int pW1 = 0, pB1 = pW1 + H * O, pW2 = pB1 + H, pB2 = pW2 + H * H, pW3 = pB2 + H, pB3 = pW3 + NACT * H;
-    constexpr int sW1 = 0, sB1 = sW1 + H * W1LD, sW2 = sB1 + NAG * H, sB2 = sW2 + H * H, sW3 = sB2 + H,
-                  sB3 = sW3 + NACT * H, sEnd = sB3 + 8;
+    using RL = RolloutLayout<H, O, GRU>;
+    constexpr int pW1 = RL::pW1, pB1 = RL::pB1, pW2 = RL::pW2, pB2 = RL::pB2, pW3 = RL::pW3, pB3 = RL::pB3;
+    constexpr int sW1 = RL::sW1, sB1 = RL::sB1, sW2 = RL::sW2, sB2 = RL::sB2, sW3 = RL::sW3, sB3 = RL::sB3, sEnd = RL::sEnd;
     constexpr bool FOLD = O > CMARL_RAW_OBS;                   // one-hot agent ids appended to the observation
     constexpr int JL = H / NQ;                                // hidden units per warp
     extern __shared__ __align__(16) float dyn[];
@@ -205,6 +223,7 @@ __global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
     float (*hx)[H][REPB] = reinterpret_cast<float (*)[H][REPB]>(dyn + sEnd);                       // [NAG] layer-1 activations of an agent's four warps
     float (*zp)[NQ][NACT][REPB] = reinterpret_cast<float (*)[NQ][NACT][REPB]>(dyn + sEnd + NAG * H * REPB);   // [NAG] partial logits of the four warps
     float (*qs)[NACT][REPB] = reinterpret_cast<float (*)[NACT][REPB]>(dyn + sEnd + NAG * H * REPB + NAG * NQ * NACT * REPB);   // [NAG] race noise prepared by the quarter-2 warp
+    float (*hs)[NAG][H][REPB] = reinterpret_cast<float (*)[NAG][H][REPB]>(dyn + sEnd + NAG * H * REPB + NAG * NQ * NACT * REPB + NAG * NACT * REPB);   // [2] GRU hidden state
     __shared__ double es[18][REPB];
     __shared__ int acts[NAG][REPB];
     __shared__ double pf[3][REPB][2];                         // contact force of pair (0,1), (0,2), (1,2) on its first entity
@@ -232,8 +251,19 @@ __global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
             const int g = i / H, j = i - g * H;
             sw[sB1 + i] = P[pB1 + j] + (FOLD ? P[pW1 + j * O + CMARL_RAW_OBS + g] : 0.0f);   // one-hot id column of agent g
         }
-        for (int i = tid; i < H * H; i += RTHREADS) sw[sW2 + i] = P[pW2 + i];
-        for (int i = tid; i < H; i += RTHREADS) sw[sB2 + i] = P[pB2 + i];
+        if (GRU) {
+            for (int i = tid; i < 3 * H * H; i += RTHREADS) { sw[RL::sWih + i] = P[RL::pWih + i]; sw[RL::sWhh + i] = P[RL::pWhh + i]; }
+            for (int j = tid; j < H; j += RTHREADS) {     // bir + bhr, biz + bhz, bin, bhn
+                sw[RL::sBg + 4 * j + 0] = P[RL::pBih + j] + P[RL::pBhh + j];
+                sw[RL::sBg + 4 * j + 1] = P[RL::pBih + H + j] + P[RL::pBhh + H + j];
+                sw[RL::sBg + 4 * j + 2] = P[RL::pBih + 2 * H + j];
+                sw[RL::sBg + 4 * j + 3] = P[RL::pBhh + 2 * H + j];
+            }
+            for (int i = tid; i < 2 * NAG * H * REPB; i += RTHREADS) (&hs[0][0][0][0])[i] = 0.0f;   // h = None
+        } else {
+            for (int i = tid; i < H * H; i += RTHREADS) sw[sW2 + i] = P[pW2 + i];
+            for (int i = tid; i < H; i += RTHREADS) sw[sB2 + i] = P[pB2 + i];
+        }
         for (int i = tid; i < NACT * H; i += RTHREADS) sw[sW3 + i] = P[pW3 + i];
         if (tid < 8) sw[sB3 + tid] = tid < NACT ? P[pB3 + tid] : 0.0f;
     }
@@ -308,7 +338,54 @@ __global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
         float z[NACT];
 #pragma unroll
         for (int k = 0; k < NACT; ++k) z[k] = 0.0f;
-        {
+        if (GRU) {
+            // GRUCell (gate order r, z, n; ATen gru_cell): this warp's JL units; x1 = h1, old hidden state from hs[t & 1]
+            const int cur = t & 1;
+            float ar[JL], az[JL], ai[JL], ah[JL];
+#pragma unroll
+            for (int i = 0; i < JL; ++i) {
+                const float4 bg = *reinterpret_cast<const float4*>(sw + RL::sBg + 4 * (j0 + i));
+                ar[i] = bg.x; az[i] = bg.y; ai[i] = bg.z; ah[i] = bg.w;
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < H; k4 += 4) {
+#pragma unroll
+                for (int i = 0; i < JL; ++i) {
+                    const float4 wr = *reinterpret_cast<const float4*>(sw + RL::sWih + (0 * H + j0 + i) * H + k4);   // warp-uniform
+                    const float4 wz = *reinterpret_cast<const float4*>(sw + RL::sWih + (1 * H + j0 + i) * H + k4);
+                    const float4 wn = *reinterpret_cast<const float4*>(sw + RL::sWih + (2 * H + j0 + i) * H + k4);
+                    ar[i] = fmaf(h1[k4], wr.x, ar[i]); ar[i] = fmaf(h1[k4 + 1], wr.y, ar[i]);
+                    ar[i] = fmaf(h1[k4 + 2], wr.z, ar[i]); ar[i] = fmaf(h1[k4 + 3], wr.w, ar[i]);
+                    az[i] = fmaf(h1[k4], wz.x, az[i]); az[i] = fmaf(h1[k4 + 1], wz.y, az[i]);
+                    az[i] = fmaf(h1[k4 + 2], wz.z, az[i]); az[i] = fmaf(h1[k4 + 3], wz.w, az[i]);
+                    ai[i] = fmaf(h1[k4], wn.x, ai[i]); ai[i] = fmaf(h1[k4 + 1], wn.y, ai[i]);
+                    ai[i] = fmaf(h1[k4 + 2], wn.z, ai[i]); ai[i] = fmaf(h1[k4 + 3], wn.w, ai[i]);
+                }
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < H; k4 += 4) {
+                const float p0 = hs[cur][n][k4][e], p1 = hs[cur][n][k4 + 1][e], p2 = hs[cur][n][k4 + 2][e], p3 = hs[cur][n][k4 + 3][e];
+#pragma unroll
+                for (int i = 0; i < JL; ++i) {
+                    const float4 wr = *reinterpret_cast<const float4*>(sw + RL::sWhh + (0 * H + j0 + i) * H + k4);
+                    const float4 wz = *reinterpret_cast<const float4*>(sw + RL::sWhh + (1 * H + j0 + i) * H + k4);
+                    const float4 wn = *reinterpret_cast<const float4*>(sw + RL::sWhh + (2 * H + j0 + i) * H + k4);
+                    ar[i] = fmaf(p0, wr.x, ar[i]); ar[i] = fmaf(p1, wr.y, ar[i]); ar[i] = fmaf(p2, wr.z, ar[i]); ar[i] = fmaf(p3, wr.w, ar[i]);
+                    az[i] = fmaf(p0, wz.x, az[i]); az[i] = fmaf(p1, wz.y, az[i]); az[i] = fmaf(p2, wz.z, az[i]); az[i] = fmaf(p3, wz.w, az[i]);
+                    ah[i] = fmaf(p0, wn.x, ah[i]); ah[i] = fmaf(p1, wn.y, ah[i]); ah[i] = fmaf(p2, wn.z, ah[i]); ah[i] = fmaf(p3, wn.w, ah[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < JL; ++i) {
+                const float r = 1.0f / (1.0f + expf(-ar[i])), zg = 1.0f / (1.0f + expf(-az[i]));
+                const float nn = tanhf(ai[i] + r * ah[i]);
+                const float hn = (hs[cur][n][j0 + i][e] - nn) * zg + nn;
+                hs[cur ^ 1][n][j0 + i][e] = hn;
+                const float h2 = fmaxf(hn, 0.0f);
+#pragma unroll
+                for (int k = 0; k < NACT; ++k) z[k] = fmaf(h2, sw[sW3 + k * H + j0 + i], z[k]);
+            }
+        } else {
             float acc[JL];
 #pragma unroll
             for (int i = 0; i < JL; ++i) acc[i] = sw[sB2 + j0 + i];
@@ -573,20 +650,30 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
     cudaStream_t st = as_stream(stream);
     const bool ids = a.O > CMARL_RAW_OBS;
     const int H = ctx->cfg.actor_hidden;
+    if (ctx->cfg.actor_recurrent) {
+        constexpr size_t smem21 = (size_t)RolloutLayout<32, 21, true>::floats * sizeof(float);
+        constexpr size_t smem18 = (size_t)RolloutLayout<32, 18, true>::floats * sizeof(float);
+        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<32, 21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem21));
+        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<32, 18, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem18));
+        KernelTimer kt(ctx, K_ROLLOUT, st);
+        if (ids) rollout_kernel<32, 21, true><<<grid, RTHREADS, smem21, st>>>(a);
+        else rollout_kernel<32, 18, true><<<grid, RTHREADS, smem18, st>>>(a);
+        return cmarl_check_cuda(cudaGetLastError(), "rollout_kernel (recurrent)");
+    }
     const size_t smem = (size_t)(H * W1LD + NAG * H + H * H + H + NACT * H + 8 + NAG * H * REPB + NAG * NQ * NACT * REPB +
                                  NAG * NACT * REPB) * sizeof(float);
     if (H == 64) {
-        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 21, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 18, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     {
         KernelTimer kt(ctx, K_ROLLOUT, st);
         if (H == 32) {
-            if (ids) rollout_kernel<32, 21><<<grid, RTHREADS, smem, st>>>(a);
-            else rollout_kernel<32, 18><<<grid, RTHREADS, smem, st>>>(a);
+            if (ids) rollout_kernel<32, 21, false><<<grid, RTHREADS, smem, st>>>(a);
+            else rollout_kernel<32, 18, false><<<grid, RTHREADS, smem, st>>>(a);
         } else {
-            if (ids) rollout_kernel<64, 21><<<grid, RTHREADS, smem, st>>>(a);
-            else rollout_kernel<64, 18><<<grid, RTHREADS, smem, st>>>(a);
+            if (ids) rollout_kernel<64, 21, false><<<grid, RTHREADS, smem, st>>>(a);
+            else rollout_kernel<64, 18, false><<<grid, RTHREADS, smem, st>>>(a);
         }
     }
     return cmarl_check_cuda(cudaGetLastError(), "rollout_kernel");

@@ -32,6 +32,7 @@ class Shapes:
     critic_hidden: int = 64
     critic_layers: int = 1
     critic_on_obs: bool = False
+    actor_recurrent: bool = False     # fc1 + GRUCell + fc2 (mappo_lstm_multienvs.py:162-184)
 
 
 def _ptr(t, dtype, device, name):
@@ -57,7 +58,8 @@ class Engine:
         self.shapes = shapes
         cfg = _lib.Config(self.device.index, shapes.n_envs, shapes.n_steps, shapes.n_agents, shapes.obs_dim,
                           shapes.state_dim, shapes.n_actions, shapes.actor_hidden, shapes.actor_layers,
-                          shapes.critic_hidden, shapes.critic_layers, int(shapes.critic_on_obs))
+                          shapes.critic_hidden, shapes.critic_layers, int(shapes.critic_on_obs),
+                          int(shapes.actor_recurrent))
         h = C.c_void_p()
         _lib.check(self.lib.cmarl_ctx_create(C.byref(cfg), C.byref(h)), "cmarl_ctx_create")
         self._h = h
@@ -92,7 +94,7 @@ class Engine:
 
     def read_timing(self) -> dict:
         """{kernel name: (total ms, launches)} since the last read (synchronises the device)."""
-        nk = 11
+        nk = _lib.N_KERNEL_IDS
         ms = (C.c_double * nk)()
         cnt = (C.c_int64 * nk)()
         _lib.check(self.lib.cmarl_timing_read(self._h, ms, cnt), "cmarl_timing_read")
@@ -187,6 +189,43 @@ class Engine:
             self._f(exp_avg_sq, "exp_avg_sq"), int(step), _ptr(step_dev, torch.int32, self.device, "step_dev"),
             float(lr_actor), float(lr_critic), float(beta1), float(beta2), float(eps), float(max_norm),
             self._f(stats_out, "stats_out"), self._stream()), "cmarl_clip_adam_step")
+
+
+    # ------------------------------------------------------------------ recurrent-actor entries
+    def alloc_h_seq(self):
+        """f32 [T+1][N][H][B]: hidden state before every step of one epoch (slice 0 = zeros, never read)."""
+        s = self.shapes
+        return torch.zeros(s.n_steps + 1, s.n_agents, s.actor_hidden, s.n_envs, dtype=torch.float32, device=self.device)
+
+    def actor_act_recurrent(self, actor_params, obs, noise, actions, logp, h_out, *, h_in=None, avail=None, logits=None):
+        _lib.check(self.lib.cmarl_actor_act_recurrent(
+            self._h, self._f(actor_params, "actor_params"), self._f(obs, "obs"), self._f(h_in, "h_in"),
+            _ptr(avail, torch.uint8, self.device, "avail"), self._f(noise, "noise"),
+            _ptr(actions, torch.int32, self.device, "actions"), self._f(logp, "logp"), self._f(logits, "logits"),
+            self._f(h_out, "h_out"), self._stream()), "cmarl_actor_act_recurrent")
+
+    def tbptt_chunk_grads(self, actor_params, grads, h_seq, t0, t1, *, state=None, obs=None, actions, logp_old, adv,
+                          mask=None, avail=None, clip=0.2, ent_coef=0.001):
+        _lib.check(self.lib.cmarl_tbptt_chunk_grads(
+            self._h, self._f(actor_params, "actor_params"), self._f(state, "state"), self._f(obs, "obs"),
+            _ptr(actions, torch.int32, self.device, "actions"), self._f(logp_old, "logp_old"), self._f(adv, "adv"),
+            _ptr(mask, torch.uint8, self.device, "mask"), _ptr(avail, torch.uint8, self.device, "avail"),
+            float(clip), float(ent_coef), int(t0), int(t1), self._f(h_seq, "h_seq"), self._f(grads, "grads"),
+            C.c_void_p(self.workspace.data_ptr()), self._stream()), "cmarl_tbptt_chunk_grads")
+
+    def critic_epoch_grads(self, critic_params, grads, *, state=None, obs=None, returns, mask=None):
+        _lib.check(self.lib.cmarl_critic_epoch_grads(
+            self._h, self._f(critic_params, "critic_params"), self._f(state, "state"), self._f(obs, "obs"),
+            self._f(returns, "returns"), _ptr(mask, torch.uint8, self.device, "mask"), self._f(grads, "grads"),
+            C.c_void_p(self.workspace.data_ptr()), self._stream()), "cmarl_critic_epoch_grads")
+
+    def adam_step_net(self, net, params, grads, exp_avg, exp_avg_sq, *, step=1, step_dev=None, lr=8e-4, beta1=0.9,
+                      beta2=0.999, eps=1e-8, max_norm=-1.0, extra_div=1.0, stats_out=None):
+        _lib.check(self.lib.cmarl_adam_step_net(
+            self._h, int(net), self._f(params, "params"), self._f(grads, "grads"), self._f(exp_avg, "exp_avg"),
+            self._f(exp_avg_sq, "exp_avg_sq"), int(step), _ptr(step_dev, torch.int32, self.device, "step_dev"),
+            float(lr), float(beta1), float(beta2), float(eps), float(max_norm), float(extra_div),
+            self._f(stats_out, "stats_out"), self._stream()), "cmarl_adam_step_net")
 
 
 # ---------------------------------------------------------------------- layout conversion

@@ -86,6 +86,16 @@ class Args:
     """ Random seed"""
 
 
+@dataclass
+class ArgsRecurrent(Args):
+    """``Args`` of ``cleanmarl/mappo_lstm_multienvs.py:18-81``: MME's plus ``tbptt``; ``num_eval_ep`` defaults to 5.
+    (``actor_num_layers`` is accepted and unused, as in the reference: its recurrent ``Actor`` takes no layer count.)"""
+    tbptt: int = 10
+    """Chunck size for Truncated Backpropagation Through Time tbptt"""
+    num_eval_ep: int = 5
+    """ Number of evaluation episodes"""
+
+
 def validate_args(args: Args):
     """Fail loudly at start-up on anything the device path does not implement (no fallbacks)."""
     if args.env_type != "pz" or args.env_family != "mpe" or args.env_name != "simple_spread_v3":
@@ -95,8 +105,13 @@ def validate_args(args: Args):
         raise SystemExit(f"--device {args.device}: cleanmarl_b200 runs on CUDA (sm_100a) only; there is no CPU path")
     if args.optimizer != "Adam":
         raise SystemExit("only --optimizer Adam is implemented")
-    if args.actor_num_layers != 1 or args.critic_num_layers != 1:
+    recurrent = hasattr(args, "tbptt")
+    if (not recurrent and args.actor_num_layers != 1) or args.critic_num_layers != 1:
         raise SystemExit("only *_num_layers 1 (the reference default) is implemented")
+    if recurrent and args.tbptt < 1:
+        raise SystemExit("--tbptt must be positive")
+    if recurrent and args.actor_hidden_dim != 32:
+        raise SystemExit("the recurrent actor is built for --actor_hidden_dim 32 (the reference default) only")
     if args.batch_size < 1 or args.epochs < 1:
         raise SystemExit("batch_size and epochs must be positive")
 
@@ -118,6 +133,12 @@ class ActorCritic:
         dims_a = [s.obs_dim] + [s.actor_hidden] * (s.actor_layers + 1) + [s.n_actions]
         dims_c = [critic_in] + [s.critic_hidden] * (s.critic_layers + 1) + [1]
         flat = []
+        if getattr(s, "actor_recurrent", False):
+            # mappo_lstm_multienvs.py:165-168: fc1 Linear, GRUCell, fc2 Linear -- constructed (= initialised) in that order
+            mods = [nn.Linear(s.obs_dim, s.actor_hidden), nn.GRUCell(s.actor_hidden, s.actor_hidden),
+                    nn.Linear(s.actor_hidden, s.n_actions)]
+            flat += [p.detach().reshape(-1) for m in mods for p in m.parameters()]
+            dims_a = []
         for dims in (dims_a, dims_c):
             for i in range(len(dims) - 1):
                 lin = nn.Linear(dims[i], dims[i + 1])
@@ -213,10 +234,11 @@ class MAPPO:
         self.args, self.rank, self.world, self.ippo, self.pg = args, rank, world_size, ippo, process_group
         self.B = args.batch_size // world_size
         self.T = 25                                              # simple_spread_v3 max_cycles (kwargs = {}, MME:297)
+        self.recurrent = hasattr(args, "tbptt")
         shapes = Shapes(n_envs=self.B, n_steps=self.T, obs_dim=18 + 3 * bool(args.agent_ids),
-                        actor_hidden=args.actor_hidden_dim, actor_layers=args.actor_num_layers,
+                        actor_hidden=args.actor_hidden_dim, actor_layers=1 if self.recurrent else args.actor_num_layers,
                         critic_hidden=args.critic_hidden_dim, critic_layers=args.critic_num_layers,
-                        critic_on_obs=ippo)
+                        critic_on_obs=ippo, actor_recurrent=self.recurrent)
         self.engine = eng = engine_factory(shapes, device_index)
         self.net = ActorCritic(eng, args.seed)                   # identical on every rank (same seed)
         self.exp_avg = torch.zeros_like(self.net.flat)
@@ -226,6 +248,14 @@ class MAPPO:
         self.epoch_stats = eng.empty(args.epochs, 8)
         self.norm_stats = eng.empty(4, dtype=torch.float64)
         self.buf = eng.alloc_rollout()
+        if self.recurrent:
+            self.chunks = tbptt_chunks(self.T, args.tbptt)
+            self.h_seq = eng.alloc_h_seq()
+            self.grads_a = eng.empty(eng.n_actor + 8)
+            self.grads_c = eng.empty(eng.n_critic + 8)
+            self.adam_step_a = torch.zeros(1, dtype=torch.int32, device=eng.device)
+            self.chunk_stats = eng.empty(args.epochs, len(self.chunks), 8)
+            self.critic_stats = eng.empty(args.epochs, 8)
         self.env = eng.empty(18, self.B, dtype=torch.float64)
         # every rank draws from its own Philox key so shards are independent
         self.rng_key = (args.seed + 0x9E3779B97F4A7C15 * (rank + 1)) & (2**64 - 1)
@@ -273,8 +303,42 @@ class MAPPO:
             self._normalize(buf["returns"], eng.n_heads, 1)
 
     # -- PPO epochs ----------------------------------------------------------------------------
+    def update_recurrent(self):
+        """mappo_lstm_multienvs.py:551-664: per epoch, one actor step per truncated-BPTT chunk (gradients of the chunk's
+        loss / (n_valid_chunk * T_chunk), hidden state carried detached from chunk to chunk) and one critic step; one
+        all-reduce of unnormalised sums before every step, so shards add and replicas stay identical."""
+        eng, buf, a = self.engine, self.buf, self.args
+        na = eng.n_actor
+        p_a, p_c = self.net.flat[:na], self.net.flat[na:]
+        m_a, m_c = self.exp_avg[:na], self.exp_avg[na:]
+        v_a, v_c = self.exp_avg_sq[:na], self.exp_avg_sq[na:]
+        for ep in range(a.epochs):
+            for ci, (t0, t1) in enumerate(self.chunks):
+                eng.tbptt_chunk_grads(p_a, self.grads_a, self.h_seq, t0, t1, state=buf["state"], actions=buf["actions"],
+                                      logp_old=buf["logp"], adv=buf["adv"], clip=a.ppo_clip, ent_coef=a.entropy_coef)
+                self._allreduce(self.grads_a)
+                eng.adam_step_net(0, p_a, self.grads_a, m_a, v_a, step_dev=self.adam_step_a, lr=a.learning_rate_actor,
+                                  max_norm=a.clip_gradients, extra_div=t1 - t0, stats_out=self.chunk_stats[ep, ci])
+            eng.critic_epoch_grads(p_c, self.grads_c, state=buf["state"], returns=buf["returns"])
+            self._allreduce(self.grads_c)
+            eng.adam_step_net(1, p_c, self.grads_c, m_c, v_c, step_dev=self.adam_step, lr=a.learning_rate_critic,
+                              max_norm=a.clip_gradients, stats_out=self.critic_stats[ep])
+            self.training_step += 1
+        # per-epoch scalars of LSTM:640-662 in the layout of the MLP path's epoch_stats (logging only)
+        cs, ks = self.chunk_stats, self.critic_stats
+        n = cs[:, :, 6].sum(dim=1)                                  # b_mask.sum()
+        es = self.epoch_stats
+        es[:, 0] = cs[:, :, 0].sum(dim=1) / n
+        es[:, 1] = ks[:, 1] / ks[:, 6]
+        es[:, 2:5] = cs[:, :, 2:5].sum(dim=1) / n[:, None]
+        es[:, 5] = cs[:, :, 5].mean(dim=1)                          # np.mean(actor_gradient), LSTM:662
+        es[:, 6] = ks[:, 5]
+        es[:, 7] = n
+
     def update(self):
         """MME:521-603: one NCCL all-reduce of the flat gradient (+8 statistics) per epoch."""
+        if self.recurrent:
+            return self.update_recurrent()
         eng, buf, a = self.engine, self.buf, self.args
         for ep in range(a.epochs):
             eng.ppo_epoch_grads(self.net.flat, self.grads, state=buf["state"], actions=buf["actions"],
@@ -312,12 +376,24 @@ class MAPPO:
         return to_reference_layout(self.buf, 3, 5, bool(self.args.agent_ids))
 
 
+def tbptt_chunks(T: int, tbptt: int):
+    """[(t0, t1)) step ranges after whose last step the reference back-propagates and steps the actor
+    (``(t + 1) % tbptt == 0 or t == T - 1``, mappo_lstm_multienvs.py:603)."""
+    out, t0 = [], 0
+    for t in range(T):
+        if ((t + 1) % tbptt == 0) or (t == T - 1):
+            out.append((t0, t + 1))
+            t0 = t + 1
+    return out
+
+
 def evaluate(trainer: MAPPO, num_episodes: int, seed: int):
     """MME:614-644: ``num_eval_ep`` episodes with the *sampling* policy (``actor.act``), run as
     ``num_eval_ep`` parallel device envs.  Returns (mean, std, length) of the episode reward."""
     s = trainer.engine.shapes
     eng = Engine(Shapes(n_envs=num_episodes, n_steps=s.n_steps, obs_dim=s.obs_dim, actor_hidden=s.actor_hidden,
-                        critic_hidden=s.critic_hidden, critic_on_obs=s.critic_on_obs), trainer.engine.device.index)
+                        critic_hidden=s.critic_hidden, critic_on_obs=s.critic_on_obs,
+                        actor_recurrent=s.actor_recurrent), trainer.engine.device.index)
     buf = eng.alloc_rollout()
     env = eng.empty(18, num_episodes, dtype=torch.float64)
     eng.env_reset(env, seed, 0)

@@ -23,12 +23,13 @@ ALGO = "MAPPO"
 IPPO = False
 
 
-def main(argv=None, algo=ALGO, ippo=IPPO, args_cls=Args):
+def main(argv=None, algo=ALGO, ippo=IPPO, args_cls=Args, run_prefix=None):
     args = tyro.cli(args_cls, args=argv)
     validate_args(args)
     rank, world, local = init_distributed()
     trainer = MAPPO(args, device_index=local, rank=rank, world_size=world, ippo=ippo)
     writer = None
+    run_prefix = run_prefix or f"{algo}-multienvs"
     if rank == 0:
         from torch.utils.tensorboard import SummaryWriter
         time_token = datetime.datetime.now().strftime("%Y-%m-%d_%H-%M-%S")
@@ -36,8 +37,8 @@ def main(argv=None, algo=ALGO, ippo=IPPO, args_cls=Args):
         if args.use_wnb:
             import wandb
             wandb.init(project=args.wnb_project, entity=args.wnb_entity, sync_tensorboard=True, config=vars(args),
-                       name=f"{algo}-multienvs-{run_name}")
-        writer = SummaryWriter(f"runs/{algo}-multienvs-{run_name}")
+                       name=f"{run_prefix}-{run_name}")
+        writer = SummaryWriter(f"runs/{run_prefix}-{run_name}")
         writer.add_text("hyperparameters", "|param|value|\n|-|-|\n%s" % (
             "\n".join([f"|{key}|{value}|" for key, value in vars(args).items()])))
     pending_rewards = 0

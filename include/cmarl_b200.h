@@ -28,6 +28,10 @@
  *  Parameters are ONE flat f32 vector in the order of torch's module.parameters():
  *    actor  W1[Ha][O] b1[Ha] W2[Ha][Ha] b2[Ha] W3[A][Ha] b3[A]   then
  *    critic W1[Hc][Sin] b1[Hc] W2[Hc][Hc] b2[Hc] W3[1][Hc] b3[1]   (row-major W[out][in], y = x W^T + b)
+ *  Recurrent actor (cmarl_config.actor_recurrent = 1; mappo_lstm_multienvs.py:162-184), 7 205 floats:
+ *    fc1.W[H][O] fc1.b[H] gru.weight_ih[3H][H] gru.weight_hh[3H][H] gru.bias_ih[3H] gru.bias_hh[3H]
+ *    fc2.W[A][H] fc2.b[A]      (torch.nn.GRUCell gate order r, z, n)
+ *    hidden  f32 [N][H][B]     one hidden state per (agent, env); h_seq f32 [T+1][N][H][B]: slice t = state BEFORE step t
  */
 #ifndef CMARL_B200_H
 #define CMARL_B200_H
@@ -39,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CMARL_VERSION 100
+#define CMARL_VERSION 101
 #define CMARL_N_STATS 8          /* floats appended to the flat gradient vector, see cmarl_ppo_epoch_grads */
 #define CMARL_RAW_OBS 18
 
@@ -58,6 +62,8 @@ typedef struct cmarl_config {
     int32_t critic_hidden;   /* MME Args.critic_hidden_dim (64; ippo_multienvs.py:34 -> 32) */
     int32_t critic_layers;   /* MME Args.critic_num_layers (1)  */
     int32_t critic_on_obs;   /* 0: MAPPO critic(state) MME:336; 1: IPPO critic(obs) ippo_multienvs.py:336 */
+    int32_t actor_recurrent; /* 0: MLP actor MME:160-183; 1: fc1 + GRUCell + fc2, mappo_lstm_multienvs.py:162-184
+                                (actor_layers is then ignored, as in the reference; actor_hidden must be 32) */
 } cmarl_config;
 
 /* -- library ---------------------------------------------------------------------------- */
@@ -82,7 +88,7 @@ int cmarl_launch_count(const cmarl_ctx* ctx);         /* kernels launched throug
 /* Per-kernel device timing (measurement aid for bench.py, off by default): when enabled every launch
  * is bracketed by a cudaEvent pair on its own stream.  cmarl_timing_read synchronises the device and
  * returns, per kernel id, the summed duration in ms and the number of launches since the last read. */
-#define CMARL_NK 11
+#define CMARL_NK 12
 int cmarl_timing_enable(cmarl_ctx* ctx, int on);
 int cmarl_timing_read(cmarl_ctx* ctx, double* sum_ms /* HOST [CMARL_NK] */, int64_t* launches /* HOST [CMARL_NK] */);
 const char* cmarl_kernel_name(int id);
@@ -171,6 +177,50 @@ int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, floa
                          float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor,
                          double lr_critic, double beta1, double beta2, double eps, double max_norm,
                          float* stats_out, void* stream);
+
+/* ======================================================================================================
+ * Recurrent-actor path (BASELINE config 4): cleanmarl/mappo_lstm_multienvs.py ("LSTM" below).
+ * cmarl_rollout, cmarl_critic_values, cmarl_td_lambda and cmarl_normalize serve it unchanged (a context
+ * created with actor_recurrent = 1 runs the GRU actor inside cmarl_rollout, hidden state 0 at episode start,
+ * LSTM:406); the entries below replace what differs.
+ * ====================================================================================================== */
+
+/* -- K2 (recurrent) alone: Actor.act(x, h, avail) LSTM:170-184 for one time step; used by the parity tests and
+ * the eval loop (LSTM:683-705).  obs [N][O][B]; h_in [N][H][B] or NULL (= zeros, LSTM:178-179); avail u8
+ * [N][A][B] or NULL; noise [N][A][B]; h_out [N][H][B] (may alias h_in); logits_out [N][A][B] optional. */
+int cmarl_actor_act_recurrent(cmarl_ctx* ctx, const float* actor_params, const float* obs, const float* h_in,
+                              const uint8_t* avail, const float* noise, int32_t* actions, float* logp,
+                              float* logits_out, float* h_out, void* stream);
+
+/* -- K7a: actor loss + gradients of ONE truncated-BPTT chunk, steps [t0, t1) (LSTM:563-607): forward through the
+ * chunk from the detached hidden state h_seq[t0], per-step clipped-PPO / entropy head (LSTM:574-593), backward
+ * through time inside the chunk.  Output = UNNORMALISED sums so that shards add:
+ *   grads_out f32 [Pa + CMARL_N_STATS]:  d/d(actor params) of sum_{t in chunk} sum_b mean_n(-min(A r, A clamp r) - ent H),
+ *   stats [0] that loss sum [2] entropy sum [3] kl sum [4] clip-fraction sum [5] valid (b,t) in the chunk, others 0.
+ * The reference's division by (n_valid_chunk * T_chunk) (LSTM:605-607) happens in cmarl_adam_step_net after the
+ * caller's all-reduce.  h_seq f32 [T+1][N][H][B] is caller-owned scratch that carries the hidden state from chunk
+ * to chunk inside one epoch: t0 == 0 starts from zeros (LSTM:558, the kernel ignores slice 0); on return slices
+ * t0+1..t1 hold the hidden states after each step (computed with the weights of THIS call, LSTM:620 detach). */
+int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params, const float* state, const float* obs,
+                            const int32_t* actions, const float* logp_old, const float* adv, const uint8_t* mask,
+                            const uint8_t* avail, double clip, double ent_coef, int32_t t0, int32_t t1,
+                            float* h_seq, float* grads_out, void* workspace, void* stream);
+
+/* -- K7b: critic loss + gradients of one epoch alone (LSTM:621-626, 646-649; the critic is stepped once per
+ * epoch while the actor is stepped once per chunk).  grads_out f32 [Pc + CMARL_N_STATS]: unnormalised sums,
+ * stats [1] critic loss sum, [5] valid (b,t). */
+int cmarl_critic_epoch_grads(cmarl_ctx* ctx, const float* critic_params, const float* state, const float* obs,
+                             const float* returns, const uint8_t* mask, float* grads_out, void* workspace,
+                             void* stream);
+
+/* -- K8 for ONE network (net 0 = actor, 1 = critic): g = grads / (stats[5] * extra_div), norm of per-tensor norms,
+ * optional clip, Adam (LSTM:605-619 with extra_div = T_chunk; LSTM:646-655 with extra_div = 1).  params/exp_avg/
+ * exp_avg_sq are that network's own flat vectors; step_dev as in cmarl_clip_adam_step.
+ *   stats_out f32 [8]: the five input sums [0..4] UNdivided, [5] this step's gradient norm, [6] valid count, [7] 0
+ *   (the host adds the chunk sums and divides by b_mask.sum(), LSTM:640-644). */
+int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, const float* grads, float* exp_avg,
+                        float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr, double beta1, double beta2,
+                        double eps, double max_norm, double extra_div, float* stats_out, void* stream);
 
 #ifdef __cplusplus
 }

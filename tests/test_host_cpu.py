@@ -29,13 +29,13 @@ def header_symbols():
 def test_library_exports_every_header_symbol():
     from cleanmarl_b200 import _lib
     syms = header_symbols()
-    assert len(syms) >= 22
+    assert len(syms) >= 26
     lib = C.CDLL(str(_lib.LIB_PATH))
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/cmarl_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == syms, "cleanmarl_b200/_lib.py must bind exactly the header's entry points"
     _lib.load()
-    assert _lib.load().cmarl_version() == 100
+    assert _lib.load().cmarl_version() == _lib.VERSION == 101
 
 
 def test_no_gpu_fails_loudly():
@@ -57,9 +57,9 @@ def test_ctx_rejects_unsupported_configurations():
     lib = _lib.load()
     h = C.c_void_p()
     for bad in (dict(n_agents=4), dict(n_actions=6), dict(actor_layers=2), dict(actor_hidden=48), dict(obs_dim=20),
-                dict(state_dim=50), dict(n_envs=0)):
+                dict(state_dim=50), dict(n_envs=0), dict(actor_recurrent=2), dict(actor_recurrent=1, actor_hidden=64)):
         base = dict(device=0, n_envs=64, n_steps=25, n_agents=3, obs_dim=21, state_dim=54, n_actions=5, actor_hidden=32,
-                    actor_layers=1, critic_hidden=64, critic_layers=1, critic_on_obs=0)
+                    actor_layers=1, critic_hidden=64, critic_layers=1, critic_on_obs=0, actor_recurrent=0)
         base.update(bad)
         cfg = _lib.Config(*base.values())
         assert lib.cmarl_ctx_create(C.byref(cfg), C.byref(h)) < 0, bad      # argument error, before any CUDA call
@@ -73,9 +73,10 @@ def test_args_mirror_the_reference_dataclass():
     defaults to cuda."""
     from cleanmarl_b200.mappo import Args
     from cleanmarl_b200.ippo_multienvs import Args as IppoArgs
+    from cleanmarl_b200.mappo_lstm_multienvs import Args as LstmArgs
     ref = json.loads((REPO / "tests" / "golden" / "g0_args.json").read_text())
     deviations = {"env_type": "pz", "env_name": "simple_spread_v3", "device": "cuda"}
-    for name, cls in (("mappo_multienvs", Args), ("ippo_multienvs", IppoArgs)):
+    for name, cls in (("mappo_multienvs", Args), ("ippo_multienvs", IppoArgs), ("mappo_lstm_multienvs", LstmArgs)):
         ours = {f.name: f for f in dataclasses.fields(cls)}
         theirs = {f["name"]: f for f in ref[name]}
         assert sorted(ours) == sorted(theirs)            # (ippo_multienvs.py lists ppo_clip/entropy_coef before epochs;
@@ -96,6 +97,13 @@ def test_cli_parses_like_tyro_reference_and_rejects_what_is_not_built():
                 dict(actor_num_layers=2), dict(batch_size=0)):
         with pytest.raises(SystemExit):
             validate_args(dataclasses.replace(a, **bad))
+    from cleanmarl_b200.mappo import ArgsRecurrent
+    r = tyro.cli(ArgsRecurrent, args=["--batch_size", "8192", "--tbptt", "5"])
+    assert r.tbptt == 5 and r.num_eval_ep == 5
+    validate_args(r)
+    for bad in (dict(tbptt=0), dict(actor_hidden_dim=64), dict(critic_num_layers=2)):
+        with pytest.raises(SystemExit):
+            validate_args(dataclasses.replace(r, **bad))
 
 
 def test_layout_round_trip_is_bit_exact():
