@@ -35,12 +35,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=4096)
-    ap.add_argument("--algo", default="mappo", choices=["mappo", "ippo"])
+    ap.add_argument("--envs-per-gpu", type=int, default=None,
+                    help="default 4096 (BASELINE configs[1], [2]); 8192 for --algo mappo_lstm (configs[3])")
+    ap.add_argument("--algo", default="mappo", choices=["mappo", "ippo", "mappo_lstm"])
     ap.add_argument("--ref-envs", type=int, default=32, help="envs in the reference arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gae-envs", type=int, default=1 << 20, help="envs for the stand-alone GAE roofline probe")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.envs_per_gpu is None:
+        a.envs_per_gpu = 8192 if a.algo == "mappo_lstm" else 4096
+    return a
+
+
+SCRIPTS = {"mappo": "mappo_multienvs.py", "ippo": "ippo_multienvs.py", "mappo_lstm": "mappo_lstm_multienvs.py"}
 
 
 def peaks():
@@ -55,13 +62,15 @@ def peaks():
 
 def workload_config(a, world):
     return {
-        "workload": f"{a.algo}_multienvs.py simple_spread_v3, 3 agents, T=25, num_envs={a.envs_per_gpu * world} "
-                    f"({a.envs_per_gpu}/GPU), 3 PPO epochs, actor 21-32-32-5, critic "
-                    f"{'21-32-32-1 per agent' if a.algo == 'ippo' else '54-64-64-1'}",
+        "workload": f"{SCRIPTS[a.algo]} simple_spread_v3, 3 agents, T=25, num_envs={a.envs_per_gpu * world} "
+                    f"({a.envs_per_gpu}/GPU), 3 PPO epochs, actor "
+                    f"{'21-32-GRU(32)-5, truncated BPTT 10 (3 actor steps per epoch)' if a.algo == 'mappo_lstm' else '21-32-32-5'}"
+                    f", critic {'21-32-32-1 per agent' if a.algo == 'ippo' else '54-64-64-1'}",
         "global_batch": a.envs_per_gpu * world,
         "envs_per_gpu": a.envs_per_gpu,
         "agent_env_steps_per_step": a.envs_per_gpu * world * T_STEPS * N_AGENTS,
-        "parallelism": f"dp{world} (envs sharded, 1 all-reduce of 9678 floats per epoch)" if world > 1 else "single GPU",
+        "parallelism": (f"dp{world} (envs sharded, " + ("1 all-reduce of 7213 floats per TBPTT chunk + 1 of 7753 per epoch)"
+                        if a.algo == "mappo_lstm" else "1 all-reduce of 9678 floats per epoch)")) if world > 1 else "single GPU",
         "l2": "flushed between timed iterations (256 MiB write, outside the per-step event pairs)",
     }
 
@@ -114,25 +123,40 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_port_iteration(B, seed=1):
-    """One full iteration of the oracle port (reference arithmetic, torch CPU) on B envs; returns seconds."""
+def cpu_port_iteration(B, seed=1, algo="mappo"):
+    """One full iteration of the reference's arithmetic on the host (oracle port, torch CPU): rollout on the
+    vectorised numpy env, the reference's TD(lambda) loop, 3 PPO epochs + Adam.  Returns seconds."""
     import numpy as np
     import torch
     from oracle import mappo as om
+    from oracle import mappo_lstm as ol
     from oracle import spread as osp
-    actor, critic = om.build_networks(seed)
+    lstm = algo == "mappo_lstm"
+    ippo = algo == "ippo"
+    if lstm:
+        actor, critic = ol.build_networks(seed)
+    elif ippo:
+        actor, critic = om.build_networks(seed, state_dim=21, critic_hidden=32)
+    else:
+        actor, critic = om.build_networks(seed)
     aopt, copt = om.make_optimizers(actor, critic)
     rng = np.random.default_rng(seed)
     t0 = time.perf_counter()
     pos = rng.uniform(-1, 1, (B, 3, 2)); vel = np.zeros_like(pos); lm = rng.uniform(-1, 1, (B, 3, 2))
     eps = {k: [] for k in ("obs", "actions", "log_prob", "reward", "states")}
     ids = np.broadcast_to(np.eye(3), (B, 3, 3))
+    avail1 = torch.ones(B, 3, 5, dtype=torch.bool)
+    h = None
     for t in range(T_STEPS):
         raw = osp.observe_batched(pos, vel, lm)
         obs = np.concatenate([raw, ids], axis=-1)
         with torch.no_grad():
-            logits = om.actor_logits(actor, torch.from_numpy(obs).float())
-            a, lp = om.race_sample(logits, om.draw_race_noise(logits.shape))
+            if lstm:
+                a, lp, h, _ = ol.rollout_act(actor, torch.from_numpy(obs).float(), h, avail1,
+                                             om.draw_race_noise((B, 3, 5)))
+            else:
+                logits = om.actor_logits(actor, torch.from_numpy(obs).float())
+                a, lp = om.race_sample(logits, om.draw_race_noise(logits.shape))
         pos, vel, rew = osp.step_batched(pos, vel, lm, a.numpy())
         eps["obs"].append(obs); eps["actions"].append(a); eps["log_prob"].append(lp)
         eps["reward"].append(rew[:, 0]); eps["states"].append(raw.reshape(B, 54))
@@ -144,15 +168,18 @@ def cpu_port_iteration(B, seed=1):
     mask = torch.ones(B, T_STEPS, dtype=torch.bool)
     avail = torch.ones(B, T_STEPS, 3, 5, dtype=torch.bool)
     batch = (obs, actions, logp, reward, states, avail, torch.zeros(B, T_STEPS), mask)
-    ret, adv = om.td_lambda_loop(critic, states, reward, mask, 0.99, 0.95, 3)      # the reference's loop form
-    om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001)
+    ret, adv = om.td_lambda_loop(critic, obs if ippo else states, reward, mask, 0.99, 0.95, 3)      # the reference's loop form
+    if lstm:
+        ol.ppo_update_tbptt(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001, tbptt=10)
+    else:
+        om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001, critic_on_obs=ippo)
     return time.perf_counter() - t0
 
 
-def cpu_baseline(sample_envs=64, reps=2):
+def cpu_baseline(sample_envs=64, reps=2, algo="mappo"):
     import torch
-    cpu_port_iteration(8)
-    ts = [cpu_port_iteration(sample_envs) for _ in range(reps)]
+    cpu_port_iteration(8, algo=algo)
+    ts = [cpu_port_iteration(sample_envs, algo=algo) for _ in range(reps)]
     t = min(ts)
     return {"value": sample_envs * T_STEPS * N_AGENTS / t, "unit": UNIT, "cores": torch.get_num_threads(),
             "kind": "port",
@@ -175,7 +202,7 @@ def run_reference(a):
     W = min(W, 1)
     cfg = workload_config(a, world)
     per_step = B * T_STEPS * N_AGENTS
-    script = f"{a.algo}_multienvs.py"
+    script = SCRIPTS[a.algo]
     if ref_loader.reference_dir() is not None:
         import tempfile
         import torch.utils.tensorboard as tb
@@ -213,7 +240,7 @@ def run_reference(a):
                   f"on oracle/env_stub (numpy simple_spread; PettingZoo not installed), --batch_size {B}, "
                   f"{K} iterations after {max(W, 1)} warm-up: {dt:.2f} s per iteration")
     else:
-        ts = [cpu_port_iteration(B) for _ in range(W + K)][W:]
+        ts = [cpu_port_iteration(B, algo=a.algo) for _ in range(W + K)][W:]
         dt = sum(ts) / len(ts)
         kind = "port"
         sample = f"oracle port, full iteration on {B} envs (reference sources not present on this box)"
@@ -231,7 +258,7 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------ our arm
 def run_b200(a):
     import torch
-    from cleanmarl_b200.mappo import MAPPO, Args, init_distributed
+    from cleanmarl_b200.mappo import MAPPO, Args, ArgsRecurrent, init_distributed
     import cleanmarl_b200 as cm
 
     rank, world, local = init_distributed()
@@ -240,7 +267,8 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = a.envs_per_gpu
-    args = Args(batch_size=B * world, seed=1)
+    lstm = a.algo == "mappo_lstm"
+    args = (ArgsRecurrent if lstm else Args)(batch_size=B * world, seed=1, critic_hidden_dim=32 if a.algo == "ippo" else 64)
     tr = MAPPO(args, device_index=local, rank=rank, world_size=world, ippo=(a.algo == "ippo"))
     eng = tr.engine
     hbm_peak, bf16_peak, sm_max, peak_src = peaks()
@@ -333,6 +361,13 @@ def run_b200(a):
         "rollout": (bt * (216 + 12 + 12 + 4), bt * 3 * 3712),
         "td_lambda_scan": (bt * 16 * (3 if ippo else 1), bt * 6),
     }
+    if lstm:
+        # per launch = one truncated-BPTT chunk (10, 10, 5 steps: B*T/3 env-steps on average); 41 856 FLOP per
+        # agent-step = forward 13 952 (fc1 21x32, gates 2x96x32, fc2 32x5) + backward 2x that, recompute not counted
+        nch = len(tr.chunks)
+        alg["ppo_tbptt_chunk"] = (bt // nch * (216 + 12 + 12 + 4), bt // nch * 3 * 41856)
+        alg["rollout"] = (bt * (216 + 12 + 12 + 4), bt * 3 * 13952)
+        alg["ppo_critic_chain"] = (bt * (216 + 4), bt * 38784)
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12            # TFLOP/s FFMA at max clock
     for k, (by, fl) in alg.items():
         if k in kernels:
@@ -341,7 +376,7 @@ def run_b200(a):
                                "hbm_frac": by / t / 1e9 / hbm_peak, "fp32_frac": fl / t / 1e12 / fp32_peak})
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     tc = bool(eng.tensor_cores)
-    chain = dom in ("ppo_actor_chain", "ppo_critic_chain", "critic_values")
+    chain = dom in ("ppo_actor_chain", "ppo_critic_chain", "critic_values") and not lstm
     if tc and chain:
         # the dominant kernel runs its GEMMs on tcgen05 (kind::tf32, 3 MMAs per product for fp32-level accuracy):
         # achieved = ALGORITHMIC flops / launch time; peak = measured dense bf16 (tf32 runs at half of it, and the
@@ -387,7 +422,7 @@ def run_b200(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = cpu_baseline()
+        cpu = cpu_baseline(algo=a.algo, sample_envs=32 if lstm else 64)
 
     if rank == 0:
         cfg = workload_config(a, world)
