@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from oracle import mappo as om
+from oracle import mappo_lstm as ol
 from oracle import spread as osp
 
 
@@ -23,8 +24,12 @@ class OracleEngine:
         self.device = torch.device("cpu")
         s = shapes
         cin = s.obs_dim if s.critic_on_obs else s.state_dim
+        self.recurrent = bool(getattr(s, "actor_recurrent", False))
         self.n_actor = s.obs_dim * s.actor_hidden + s.actor_hidden + s.actor_hidden ** 2 + s.actor_hidden + \
             s.n_actions * s.actor_hidden + s.n_actions
+        if self.recurrent:
+            Hh = s.actor_hidden
+            self.n_actor = s.obs_dim * Hh + Hh + 2 * 3 * Hh * Hh + 2 * 3 * Hh + s.n_actions * Hh + s.n_actions
         self.n_critic = cin * s.critic_hidden + s.critic_hidden + s.critic_hidden ** 2 + s.critic_hidden + s.critic_hidden + 1
         self.n_params = self.n_actor + self.n_critic
         self.n_heads = s.n_agents if s.critic_on_obs else 1
@@ -45,7 +50,8 @@ class OracleEngine:
     def _nets(self, flat_actor=None, flat_critic=None):
         s = self.shapes
         cin = s.obs_dim if s.critic_on_obs else s.state_dim
-        actor = om.MLP(s.obs_dim, s.actor_hidden, 1, s.n_actions)
+        actor = (ol.GRUActor(s.obs_dim, s.actor_hidden, s.n_actions) if self.recurrent
+                 else om.MLP(s.obs_dim, s.actor_hidden, 1, s.n_actions))
         critic = om.MLP(cin, s.critic_hidden, 1, 1)
         if flat_actor is not None:
             actor.load_flat(flat_actor)
@@ -75,12 +81,17 @@ class OracleEngine:
         pos = e[0:6].T.reshape(B, 3, 2).copy(); vel = e[6:12].T.reshape(B, 3, 2).copy(); lm = e[12:18].T.reshape(B, 3, 2).copy()
         ids = np.broadcast_to(np.eye(3), (B, 3, 3))
         ret = np.zeros(B)
+        h = None
         for t in range(T):
             raw = osp.observe_batched(pos, vel, lm)                                   # [B,3,18] f32
             o = np.concatenate([raw, ids], -1) if s.obs_dim > 18 else raw
             with torch.no_grad():
-                z = om.actor_logits(actor, torch.from_numpy(o).float())
-                a, lp = om.race_sample(z, noise[t].permute(2, 0, 1))                   # [B,N,A]
+                if self.recurrent:
+                    a, lp, h, _ = ol.rollout_act(actor, torch.from_numpy(o).float(), h,
+                                                 torch.ones(B, 3, s.n_actions, dtype=torch.bool), noise[t].permute(2, 0, 1))
+                else:
+                    z = om.actor_logits(actor, torch.from_numpy(o).float())
+                    a, lp = om.race_sample(z, noise[t].permute(2, 0, 1))               # [B,N,A]
             state[t] = torch.from_numpy(raw.reshape(B, 54).T.copy())
             actions[t] = a.t().to(torch.int32)
             logp[t] = lp.t()
@@ -174,6 +185,91 @@ class OracleEngine:
         if stats_out is not None:
             stats_out[:5] = grads[P:P + 5] / count
             stats_out[5], stats_out[6], stats_out[7] = norms[0], norms[1], count
+        if step_dev is not None:
+            step_dev.fill_(k)
+        self.launches += 1
+
+    # -- recurrent-actor entries (mappo_lstm_multienvs.py) ---------------------------------------------------
+    def alloc_h_seq(self):
+        s = self.shapes
+        return torch.zeros(s.n_steps + 1, s.n_agents, s.actor_hidden, s.n_envs)
+
+    def tbptt_chunk_grads(self, actor_params, grads, h_seq, t0, t1, *, state=None, obs=None, actions, logp_old, adv,
+                          mask=None, avail=None, clip=0.2, ent_coef=0.001):
+        """Unnormalised sums of one truncated-BPTT chunk (autograd through the oracle's GRU actor), hidden state
+        carried through ``h_seq`` exactly like the device kernel."""
+        from torch.distributions.categorical import Categorical
+        s = self.shapes
+        T, B, N = s.n_steps, s.n_envs, s.n_agents
+        actor, _ = self._nets(actor_params)
+        o = self._obs(state)
+        m = torch.ones(B, T, dtype=torch.bool) if mask is None else mask.t().bool()
+        A = adv.permute(2, 0, 1).expand(B, T, N) if adv.shape[1] == 1 else adv.permute(2, 0, 1)
+        acts = actions.permute(2, 0, 1).long()
+        old = logp_old.permute(2, 0, 1)
+        h = None if t0 == 0 else h_seq[t0].permute(2, 0, 1).reshape(B * N, -1).clone()
+        loss = ent_s = kl_s = clip_s = 0.0
+        for t in range(t0, t1):
+            z, h = actor.logits(o[:, t].reshape(B * N, -1), h, None)
+            with torch.no_grad():
+                h_seq[t + 1] = h.reshape(B, N, -1).permute(1, 2, 0)
+            dist = Categorical(logits=z.reshape(B, N, -1))
+            lr = dist.log_prob(acts[:, t]) - old[:, t]
+            ratio = torch.exp(lr)
+            mt = m[:, t]
+            pg = torch.min(A[:, t] * ratio, A[:, t] * torch.clamp(ratio, 1 - clip, 1 + clip))[mt].mean(dim=-1).sum()
+            ent = dist.entropy()[mt].mean(dim=-1).sum()
+            loss = loss + (-pg - ent_coef * ent)
+            ent_s = ent_s + ent.detach()
+            kl_s = kl_s + ((ratio - 1) - lr)[mt].mean(dim=-1).sum().detach()
+            clip_s = clip_s + ((ratio - 1.0).abs() > clip)[mt].float().mean(dim=-1).sum()
+        actor.zero_grad()
+        loss.backward()
+        na = self.n_actor
+        grads[:na] = actor.flat_grads()
+        grads[na:] = torch.tensor([loss.item(), 0.0, float(ent_s), float(kl_s), float(clip_s), float(m[:, t0:t1].sum()), 0.0, 0.0])
+        self.launches += 2
+
+    def critic_epoch_grads(self, critic_params, grads, *, state=None, obs=None, returns, mask=None):
+        s = self.shapes
+        T, B, N = s.n_steps, s.n_envs, s.n_agents
+        _, critic = self._nets(None, critic_params)
+        m = torch.ones(B, T, dtype=torch.bool) if mask is None else mask.t().bool()
+        R = returns.permute(2, 0, 1)
+        if s.critic_on_obs:
+            v = critic(self._obs(state)).squeeze(-1)
+        else:
+            v = critic(state.permute(2, 0, 1))
+        loss = (((v - R) ** 2).mean(dim=-1) * m.float()).sum()
+        critic.zero_grad()
+        loss.backward()
+        nc = self.n_critic
+        grads[:nc] = critic.flat_grads()
+        grads[nc:] = torch.tensor([0.0, loss.item(), 0.0, 0.0, 0.0, float(m.sum()), 0.0, 0.0])
+        self.launches += 2
+
+    def adam_step_net(self, net, params, grads, exp_avg, exp_avg_sq, *, step=1, step_dev=None, lr=8e-4, beta1=0.9,
+                      beta2=0.999, eps=1e-8, max_norm=-1.0, extra_div=1.0, stats_out=None):
+        P = params.numel()
+        count = grads[P + 5]
+        g = grads[:P] / (count * extra_div)
+        k = int(step_dev.item()) + 1 if step_dev is not None else step
+        actor, critic = self._nets()
+        module = actor if net == 0 else critic
+        off, sq = 0, []
+        for p in module.parameters():
+            sq.append(torch.linalg.vector_norm(g[off:off + p.numel()])); off += p.numel()
+        nrm = torch.linalg.vector_norm(torch.stack(sq))
+        if max_norm > 0:
+            g = g * torch.clamp(max_norm / (nrm + 1e-6), max=1.0)
+        exp_avg.lerp_(g, 1 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** k, 1 - beta2 ** k
+        denom = (exp_avg_sq.sqrt() / (bc2 ** 0.5)).add_(eps)
+        params.addcdiv_(exp_avg, denom, value=-(lr / bc1))
+        if stats_out is not None:
+            stats_out[:5] = grads[P:P + 5]
+            stats_out[5], stats_out[6], stats_out[7] = nrm, count, 0.0
         if step_dev is not None:
             step_dev.fill_(k)
         self.launches += 1

@@ -8,7 +8,7 @@ import torch
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
 
-from cleanmarl_b200.mappo import MAPPO, Args, init_distributed  # noqa: E402
+from cleanmarl_b200.mappo import MAPPO, Args, ArgsRecurrent, init_distributed  # noqa: E402
 
 
 def inputs(B, seed=11):
@@ -20,8 +20,9 @@ def inputs(B, seed=11):
     return env, noise
 
 
-def run(B, rank, world, local, iters=2, **flags):
-    tr = MAPPO(Args(batch_size=B, seed=3, **flags), device_index=local, rank=rank, world_size=world)
+def run(B, rank, world, local, iters=2, recurrent=False, **flags):
+    tr = MAPPO((ArgsRecurrent if recurrent else Args)(batch_size=B, seed=3, **flags), device_index=local, rank=rank,
+               world_size=world)
     env, noise = inputs(B)
     per = B // world
     sl = slice(rank * per, (rank + 1) * per)
@@ -34,7 +35,8 @@ def run(B, rank, world, local, iters=2, **flags):
 
 if __name__ == "__main__":
     out, B = Path(sys.argv[1]), int(sys.argv[2])
-    flags = {"normalize_advantage": True, "clip_gradients": 0.5} if len(sys.argv) > 3 and sys.argv[3] == "flags" else {}
+    mode = sys.argv[3] if len(sys.argv) > 3 else "plain"
+    flags = {"flags": {"normalize_advantage": True, "clip_gradients": 0.5}, "recurrent": {"recurrent": True}}.get(mode, {})
     rank, world, local = init_distributed()
     tr = run(B, rank, world, local, **flags)
     gathered = [torch.empty_like(tr.net.flat) for _ in range(world)]

@@ -420,7 +420,7 @@ def test_reward_normalisation(cm):
 
 
 # ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
-@pytest.mark.parametrize("flags", ["plain", "flags"])
+@pytest.mark.parametrize("flags", ["plain", "flags", "recurrent"])
 def test_two_gpus_nccl_equal_one(cm, tmp_path, flags):
     """Envs sharded over 2 GPUs (one process per GPU, one NCCL all-reduce of 9 678 floats per epoch) == 1 GPU on all
     envs: replicas bit-identical to each other, parameters within fp32 reassociation of the single-GPU run."""
@@ -439,9 +439,13 @@ def test_two_gpus_nccl_equal_one(cm, tmp_path, flags):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     two = torch.load(tmp_path / "mgpu.pt")
-    kw = {"normalize_advantage": True, "clip_gradients": 0.5} if flags == "flags" else {}
+    kw = {"flags": {"normalize_advantage": True, "clip_gradients": 0.5}, "recurrent": {"recurrent": True}}.get(flags, {})
     one = mgpu_worker.run(B, 0, 1, 0, **kw)
     assert two["step"] == one.step
-    assert (two["params"] - one.net.flat.cpu()).abs().max() < 2e-6
+    dp = (two["params"] - one.net.flat.cpu()).abs()
+    if flags == "recurrent":       # 24 actor Adam steps: near-eps gradients amplify reassociation differences
+        assert (dp < 3e-6).float().mean() > 0.995 and dp.max() < 1e-4
+    else:
+        assert dp.max() < 2e-6
     ref = one.epoch_stats.cpu()
     assert (two["stats"] - ref).abs().max() < 1e-4 * ref.abs().max()

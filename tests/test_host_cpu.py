@@ -124,10 +124,10 @@ def test_layout_round_trip_is_bit_exact():
 
 
 # ------------------------------------------------------------------------------------------ host logic on the CPU double
-def _trainer(batch_size, rank=0, world=1, **kw):
-    from cleanmarl_b200.mappo import MAPPO, Args
+def _trainer(batch_size, rank=0, world=1, recurrent=False, **kw):
+    from cleanmarl_b200.mappo import MAPPO, Args, ArgsRecurrent
     from fake_engine import OracleEngine
-    return MAPPO(Args(batch_size=batch_size, seed=3, **kw), rank=rank, world_size=world,
+    return MAPPO((ArgsRecurrent if recurrent else Args)(batch_size=batch_size, seed=3, **kw), rank=rank, world_size=world,
                  engine_factory=lambda shapes, dev: OracleEngine(shapes))
 
 
@@ -161,6 +161,32 @@ def test_trainer_iteration_matches_oracle_update():
     assert abs(sc["actor_loss"] - np.mean(st["actor_loss"])) < 1e-5 * abs(np.mean(st["actor_loss"])) + 1e-7
 
 
+def test_recurrent_trainer_iteration_matches_oracle_update():
+    """MAPPO(ArgsRecurrent).iteration on the CPU double (truncated-BPTT chunks, actor step per chunk, hidden state carried
+    through h_seq, critic step per epoch, mappo_lstm_multienvs.py:551-664) == the oracle's ppo_update_tbptt."""
+    from oracle import mappo as om
+    from oracle import mappo_lstm as ol
+    B = 10
+    env, noise = _inputs(B)
+    tr = _trainer(B, recurrent=True, tbptt=7)
+    assert tr.chunks == [(0, 7), (7, 14), (14, 21), (21, 25)] and tr.engine.n_actor == 7205
+    p0 = tr.net.flat.clone()
+    tr.iteration(env.clone(), noise)
+    batch = tr.get_batch()
+    actor, critic = ol.build_networks(3)
+    assert torch.equal(torch.cat([actor.flat_params(), critic.flat_params()]), p0)      # reference init (seed 3)
+    ret, adv = om.td_lambda_batched(critic, batch[4], batch[3], batch[7], 0.99, 0.95, 3)
+    aopt, copt = om.make_optimizers(actor, critic)
+    st = ol.ppo_update_tbptt(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001, tbptt=7)
+    final = torch.cat([actor.flat_params(), critic.flat_params()])
+    assert (tr.net.flat - final).abs().max() < 2e-6
+    sc = tr.train_scalars()
+    assert abs(sc["actor_loss"] - np.mean(st["actor_loss"])) < 1e-5 * abs(np.mean(st["actor_loss"])) + 1e-7
+    assert abs(sc["critic_loss"] - np.mean(st["critic_loss"])) < 1e-5 * abs(np.mean(st["critic_loss"]))
+    assert abs(sc["actor_gradients"] - np.mean(st["actor_grad_norm"])) < 1e-5 * np.mean(st["actor_grad_norm"])
+    assert tr.training_step == 3 and int(tr.adam_step_a) == 12 and int(tr.adam_step) == 3
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
     return p
@@ -185,8 +211,9 @@ def _rank_main(rank, world, port, B, out_dir, flags):
     torch.distributed.destroy_process_group()
 
 
-@pytest.mark.parametrize("flags", [{}, {"normalize_advantage": True, "normalize_reward": True, "clip_gradients": 0.5}],
-                         ids=["plain", "normalised+clip"])
+@pytest.mark.parametrize("flags", [{}, {"normalize_advantage": True, "normalize_reward": True, "clip_gradients": 0.5},
+                                   {"recurrent": True}],
+                         ids=["plain", "normalised+clip", "recurrent"])
 def test_two_ranks_gloo_equal_one_rank(tmp_path, flags):
     """Envs sharded over 2 ranks (gloo, CPU double) == 1 rank on all envs: same parameters (fp32 reassociation only),
     identical replicas, global step / episode counters and global normalisation statistics."""
