@@ -297,7 +297,7 @@ def run_b200(a):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t) / 1e3, wall, ms
 
-    # ---- device-resident throughput (value) ----
+    # ---- device-resident throughput (value): the iteration as the trainer runs it (CUDA-graph replay at N=1) ----
     for _ in range(max(a.warmup, 3)):
         tr.iteration()
     clocks = ClockSampler(local)
@@ -306,22 +306,22 @@ def run_b200(a):
     l0 = eng.launches
     secs, wall, ms = timed(tr.iteration, a.steps)
     launches = eng.launches - l0
+    if tr.use_graph and tr.launches_per_iteration:
+        launches = tr.launches_per_iteration * a.steps           # replayed kernel nodes (the library counter only sees eager launches)
     per_step = B * world * T_STEPS * N_AGENTS
     value = per_step * a.steps / secs
 
-    # ---- end to end through the public API with HOST inputs (start states + race noise), D2H of results ----
+    # ---- end to end through the public API: every step the start states of all envs come from pinned HOST memory
+    #      and the step's results (per-epoch statistics, per-env episode returns) are read back to the host ----
     env_h = torch.empty(18, B, dtype=torch.float64).uniform_(-1, 1).pin_memory()
     env_h[6:12] = 0
-    noise_h = torch.empty(T_STEPS, N_AGENTS, N_ACT, B).exponential_(1).pin_memory()
     env_d = torch.empty_like(env_h, device=dev)
-    noise_d = torch.empty_like(noise_h, device=dev)
     stats_h = torch.empty(args.epochs, 8).pin_memory()
     ret_h = torch.empty(B, dtype=torch.float64).pin_memory()
 
     def e2e_step():
         env_d.copy_(env_h, non_blocking=True)
-        noise_d.copy_(noise_h, non_blocking=True)
-        tr.iteration(env_init=env_d, noise=noise_d)
+        tr.iteration(env_init=env_d)
         stats_h.copy_(tr.epoch_stats, non_blocking=True)
         ret_h.copy_(tr.buf["ep_return"], non_blocking=True)
         torch.cuda.current_stream().synchronize()               # the caller reads the results every step
@@ -334,11 +334,34 @@ def run_b200(a):
         tw = torch.tensor([e_wall], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(tw, op=torch.distributed.ReduceOp.MAX)
         e_wall = float(tw)
-    clk = clocks.stop() if rank == 0 else None
-    h2d = env_h.numel() * 8 + noise_h.numel() * 4
+    h2d = env_h.numel() * 8
     d2h = stats_h.numel() * 4 + ret_h.numel() * 8
 
+    # ---- the same with the categorical race noise supplied by the host as well (what the parity tests do; eager) ----
+    noise_h = torch.empty(T_STEPS, N_AGENTS, N_ACT, B).exponential_(1).pin_memory()
+    noise_d = torch.empty_like(noise_h, device=dev)
+
+    def e2e_noise_step():
+        env_d.copy_(env_h, non_blocking=True)
+        noise_d.copy_(noise_h, non_blocking=True)
+        tr.iteration(env_init=env_d, noise=noise_d)
+        stats_h.copy_(tr.epoch_stats, non_blocking=True)
+        ret_h.copy_(tr.buf["ep_return"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_noise_step()
+    n_steps2 = max(3, a.steps // 4)
+    _, e2_wall, _ = timed(e2e_noise_step, n_steps2)
+    if world > 1:
+        tw = torch.tensor([e2_wall], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(tw, op=torch.distributed.ReduceOp.MAX)
+        e2_wall = float(tw)
+    clk = clocks.stop() if rank == 0 else None
+
     # ---- per-kernel device times over a few iterations (library-internal event pairs) ----
+    graph_mode = tr.use_graph
+    tr.use_graph = False                                         # event pairs live in the eager launch path
     eng.timing(True)
     nb = 5
     for _ in range(nb):
@@ -346,6 +369,7 @@ def run_b200(a):
         tr.iteration()
     kt = eng.read_timing()
     eng.timing(False)
+    tr.use_graph = graph_mode
     kernels = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / nb, "ms_per_step": v[0] / nb}
                for k, v in kt.items()}
     step_kernel_ms = sum(v["ms_per_step"] for v in kernels.values())
@@ -433,9 +457,14 @@ def run_b200(a):
                "e2e": {"value": per_step * a.steps / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": e_wall / a.steps * 1e3,
                        "device_ms_per_step": e_secs / a.steps * 1e3,
-                       "inputs": "start states f64 [18][B] + Exp(1) race noise f32 [T][N][A][B] from pinned host "
-                                 "memory every step; D2H: per-epoch stats + per-env episode return"},
-               "gpu_launches": launches, "clocks": clk, "roofline": roofline, "gae_roofline": gae,
+                       "inputs": "start states f64 [18][B] of every env from pinned host memory every step (race noise "
+                                 "drawn on the device, the trainer's default); D2H: per-epoch stats + per-env episode return",
+                       "with_host_noise": {"value": per_step * n_steps2 / e2_wall, "ms_per_step": e2_wall / n_steps2 * 1e3,
+                                           "h2d_bytes_per_step": h2d + noise_h.numel() * 4,
+                                           "note": "Exp(1) race noise f32 [T][N][A][B] also copied from the host (eager launches)"}},
+               "gpu_launches": launches,
+               "launch_mode": "CUDA graph replay of the iteration" if graph_mode else "eager stream launches",
+               "clocks": clk, "roofline": roofline, "gae_roofline": gae,
                "kernels": kernels, "cpu_baseline": cpu, "wall_ms_per_step": wall / a.steps * 1e3}
         print(json.dumps(out), flush=True)
     if world > 1:

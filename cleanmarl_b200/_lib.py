@@ -37,6 +37,8 @@ _SIGNATURES = {
     "cmarl_timing_enable": (C.c_int, [_P, C.c_int]),
     "cmarl_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "cmarl_kernel_name": (C.c_char_p, [C.c_int]),
+    "cmarl_ctx_set_episode_counter": (C.c_int, [_P, _P]),
+    "cmarl_episode_advance": (C.c_int, [_P, _P]),
     "cmarl_env_reset": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "cmarl_env_observe": (C.c_int, [_P, _P, _P, _P]),
     "cmarl_env_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),

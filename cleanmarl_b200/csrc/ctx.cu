@@ -20,6 +20,7 @@ int cmarl_check_cuda(cudaError_t e, const char* what) {
 }
 
 int cmarl_chain_setup(cmarl_ctx* ctx);   // chain.cu: shared-memory attributes + grid sizes
+int cmarl_rollout_setup(cmarl_ctx* ctx); // rollout.cu: shared-memory attributes
 int cmarl_gru_setup(cmarl_ctx* ctx);     // gru.cu: shared-memory attributes of the recurrent kernels
 
 extern "C" int cmarl_version(void) { return CMARL_VERSION; }
@@ -64,6 +65,7 @@ extern "C" int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     int e = cmarl_chain_setup(ctx);
     if (!e) e = cmarl_gru_setup(ctx);
+    if (!e) e = cmarl_rollout_setup(ctx);
     if (e) { free(ctx); return e; }
     *out = ctx;
     return 0;

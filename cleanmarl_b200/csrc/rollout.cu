@@ -148,6 +148,7 @@ struct RolloutArgs {
     double* env;            // [18][B]
     const float* noise;     // [T][N][A][B] or null
     uint64_t seed, episode;
+    const uint64_t* episode_dev;   // optional device-resident episode counter (CUDA-graph replay): used instead of `episode`
     float* state;           // [T][54][B]
     float* obs;             // [T][N][O][B] or null
     int32_t* actions;       // [T][N][B]
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
     }
     __syncthreads();
     double ep_acc = 0.0;                                     // threads 0..REPB-1: episode return of env tid
+    const uint64_t episode = a.episode_dev ? *a.episode_dev : a.episode;
 
     for (int t = 0; t < a.T; ++t) {
         // ---- observation before the action (what the reference stores, MME:426-430): vel, pos, landmarks - pos,
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
                 for (int k = 0; k < NACT; ++k)
                     q[k] = live ? __ldcs(a.noise + (((size_t)t * NAG + n) * NACT + k) * B + b) : 1.0f;
             } else {
-                philox_exp5(a.seed, a.episode, (uint32_t)t, (uint32_t)n, (uint32_t)b, q);
+                philox_exp5(a.seed, episode, (uint32_t)t, (uint32_t)n, (uint32_t)b, q);
             }
 #pragma unroll
             for (int k = 0; k < NACT; ++k) qs[n][k][e] = q[k];
@@ -538,9 +540,11 @@ __global__ void __launch_bounds__(RT) actor_act_kernel(ActArgs a) {
 }
 
 // ---- K1 reset ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) env_reset_kernel(double* __restrict__ env, int B, uint64_t seed, uint64_t episode) {
+__global__ void __launch_bounds__(256) env_reset_kernel(double* __restrict__ env, int B, uint64_t seed, uint64_t episode,
+                                                        const uint64_t* __restrict__ episode_dev) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    if (episode_dev) episode = *episode_dev;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     // 12 uniforms in reset_world order: agent positions (x,y) x3, then landmark positions x3
     double u[12];
@@ -606,12 +610,43 @@ extern "C" int cmarl_debug_rollout_timeline(long long* out_host16) {
     return (int)cudaMemcpyFromSymbol(out_host16, g_roll_tl, sizeof(long long) * 16);
 }
 
+__global__ void episode_advance_kernel(uint64_t* e) { *e += 1; }
+
+// shared-memory opt-ins, once per context (not inside the launch path: keeps cmarl_rollout CUDA-graph capturable)
+int cmarl_rollout_setup(cmarl_ctx* ctx) {
+    (void)ctx;
+    const size_t smem64 = (size_t)(64 * W1LD + NAG * 64 + 64 * 64 + 64 + NACT * 64 + 8 + NAG * 64 * REPB + NAG * NQ * NACT * REPB +
+                                   NAG * NACT * REPB) * sizeof(float);
+    CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 21, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+    CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 18, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+    CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<32, 21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(RolloutLayout<32, 21, true>::floats * sizeof(float))));
+    CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<32, 18, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(RolloutLayout<32, 18, true>::floats * sizeof(float))));
+    CMARL_CUDA(cudaFuncSetAttribute(actor_act_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)actor_smem_bytes<64>()));
+    return 0;
+}
+
+extern "C" int cmarl_ctx_set_episode_counter(cmarl_ctx* ctx, uint64_t* episode_dev) {
+    CMARL_ARG(ctx, "null ctx");
+    ctx->episode_dev = episode_dev;
+    return 0;
+}
+
+extern "C" int cmarl_episode_advance(cmarl_ctx* ctx, void* stream) {
+    CMARL_ARG(ctx && ctx->episode_dev, "no device episode counter set (cmarl_ctx_set_episode_counter)");
+    ctx->launches++;
+    episode_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(ctx->episode_dev);
+    return cmarl_check_cuda(cudaGetLastError(), "episode_advance_kernel");
+}
+
 extern "C" int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, void* stream) {
     CMARL_ARG(ctx && env, "null argument");
     const int B = ctx->cfg.n_envs;
     {
         KernelTimer kt(ctx, K_RESET, as_stream(stream));
-        env_reset_kernel<<<ceil_div(B, 256), 256, 0, as_stream(stream)>>>(env, B, seed, episode);
+        env_reset_kernel<<<ceil_div(B, 256), 256, 0, as_stream(stream)>>>(env, B, seed, episode, ctx->episode_dev);
     }
     return cmarl_check_cuda(cudaGetLastError(), "env_reset_kernel");
 }
@@ -644,6 +679,7 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
     CMARL_ARG(ctx && actor_params && env && state && actions && logp && reward, "null argument");
     RolloutArgs a;
     a.actor = actor_params; a.env = env; a.noise = noise; a.seed = seed; a.episode = episode;
+    a.episode_dev = ctx->episode_dev;
     a.state = state; a.obs = obs; a.actions = actions; a.logp = logp; a.reward = reward; a.ep_return = ep_return;
     a.T = ctx->cfg.n_steps; a.B = ctx->cfg.n_envs; a.O = ctx->cfg.obs_dim;
     const int grid = ceil_div(a.B, REPB);
@@ -653,8 +689,6 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
     if (ctx->cfg.actor_recurrent) {
         constexpr size_t smem21 = (size_t)RolloutLayout<32, 21, true>::floats * sizeof(float);
         constexpr size_t smem18 = (size_t)RolloutLayout<32, 18, true>::floats * sizeof(float);
-        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<32, 21, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem21));
-        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<32, 18, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem18));
         KernelTimer kt(ctx, K_ROLLOUT, st);
         if (ids) rollout_kernel<32, 21, true><<<grid, RTHREADS, smem21, st>>>(a);
         else rollout_kernel<32, 18, true><<<grid, RTHREADS, smem18, st>>>(a);
@@ -662,10 +696,6 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
     }
     const size_t smem = (size_t)(H * W1LD + NAG * H + H * H + H + NACT * H + 8 + NAG * H * REPB + NAG * NQ * NACT * REPB +
                                  NAG * NACT * REPB) * sizeof(float);
-    if (H == 64) {
-        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 21, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CMARL_CUDA(cudaFuncSetAttribute(rollout_kernel<64, 18, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
     {
         KernelTimer kt(ctx, K_ROLLOUT, st);
         if (H == 32) {
@@ -691,8 +721,6 @@ extern "C" int cmarl_actor_act(cmarl_ctx* ctx, const float* actor_params, const 
         KernelTimer kt(ctx, K_ACT, st);
         actor_act_kernel<32><<<grid, RT, actor_smem_bytes<32>(), st>>>(a);
     } else {
-        CMARL_CUDA(cudaFuncSetAttribute(actor_act_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)actor_smem_bytes<64>()));
         KernelTimer kt(ctx, K_ACT, st);
         actor_act_kernel<64><<<grid, RT, actor_smem_bytes<64>(), st>>>(a);
     }

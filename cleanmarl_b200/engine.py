@@ -126,6 +126,15 @@ class Engine:
         return buf
 
     # ------------------------------------------------------------------ entries
+    def set_episode_counter(self, counter):
+        """``counter``: int64 device tensor [1] (or None) -- see cmarl_ctx_set_episode_counter."""
+        ptr = None if counter is None else _ptr(counter, torch.int64, self.device, "episode counter")
+        self._episode_counter = counter            # keep the tensor alive
+        _lib.check(self.lib.cmarl_ctx_set_episode_counter(self._h, ptr), "cmarl_ctx_set_episode_counter")
+
+    def episode_advance(self):
+        _lib.check(self.lib.cmarl_episode_advance(self._h, self._stream()), "cmarl_episode_advance")
+
     def env_reset(self, env, seed: int, episode: int):
         _lib.check(self.lib.cmarl_env_reset(self._h, _ptr(env, torch.float64, self.device, "env"),
                                             seed & (2**64 - 1), episode & (2**64 - 1), self._stream()), "cmarl_env_reset")

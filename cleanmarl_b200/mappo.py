@@ -224,7 +224,7 @@ class MAPPO:
     (MME:522-582), gradient all-reduce across GPUs, clip + Adam (MME:584-594)]."""
 
     def __init__(self, args: Args, device_index: int = 0, rank: int = 0, world_size: int = 1, ippo: bool = False,
-                 process_group=None, engine_factory=Engine):
+                 process_group=None, engine_factory=Engine, use_graph: bool | None = None):
         """``engine_factory(shapes, device_index)`` builds the per-GPU kernel front end; the default (and only
         product) value is ``Engine`` = libcmarl_b200.so.  tests/ pass a CPU test double there to exercise the
         sharding / all-reduce logic under ``gloo`` without a GPU."""
@@ -263,6 +263,14 @@ class MAPPO:
         self.step = 0                                            # env steps over all GPUs (MME:435)
         self.training_step = 0
         self.num_episodes = 0
+        # One iteration is a fixed sequence of ~15 launches: replaying it as a CUDA graph removes the host launch
+        # path from the loop.  Needs the device episode counter; single-GPU only (the NCCL all-reduce stays eager).
+        if use_graph is None:
+            use_graph = os.environ.get("CMARL_GRAPH", "1") != "0"
+        self.use_graph = bool(use_graph) and world_size == 1 and engine_factory is Engine
+        self._graphs = {}
+        self._episode_dev = None
+        self.launches_per_iteration = None                       # kernel nodes of the captured graph (library launches)
 
     # -- rollout -------------------------------------------------------------------------------
     def collect(self, env_init=None, noise=None):
@@ -275,6 +283,8 @@ class MAPPO:
             self.env.copy_(env_init, non_blocking=True)
         eng.rollout(self.net.actor, self.env, buf["state"], buf["actions"], buf["logp"], buf["reward"], noise=noise,
                     ep_return=buf["ep_return"], seed=self.rng_key, episode=self.episode)
+        if self._episode_dev is not None:
+            eng.episode_advance()
         self.episode += 1
         self.step += self.B * self.T * self.world
         self.num_episodes += self.B * self.world
@@ -350,10 +360,65 @@ class MAPPO:
                                max_norm=a.clip_gradients, stats_out=self.epoch_stats[ep])
             self.training_step += 1
 
-    def iteration(self, env_init=None, noise=None):
+    def _iteration_eager(self, env_init=None, noise=None):
         self.collect(env_init, noise)
         self.advantages()
         self.update()
+
+    def _counters(self):
+        return (self.episode, self.step, self.num_episodes, self.training_step)
+
+    def _capture(self, reset: bool):
+        """Capture the launch sequence of one iteration (nothing executes; host counters are restored)."""
+        eng = self.engine
+        side = torch.cuda.Stream(device=eng.device)
+        side.wait_stream(torch.cuda.current_stream(eng.device))
+        graph = torch.cuda.CUDAGraph()
+        saved = self._counters()
+        with torch.cuda.graph(graph, stream=side):
+            self._launch_iteration(reset)
+        self.episode, self.step, self.num_episodes, self.training_step = saved
+        self._graphs[reset] = graph
+
+    def _launch_iteration(self, reset: bool):
+        """The kernels of one iteration; ``reset`` False = start states were already written to ``self.env``."""
+        eng, buf = self.engine, self.buf
+        if reset:
+            eng.env_reset(self.env, self.rng_key, self.episode)
+        eng.rollout(self.net.actor, self.env, buf["state"], buf["actions"], buf["logp"], buf["reward"],
+                    ep_return=buf["ep_return"], seed=self.rng_key, episode=self.episode)
+        if self._episode_dev is not None:
+            eng.episode_advance()
+        self.episode += 1
+        self.step += self.B * self.T * self.world
+        self.num_episodes += self.B * self.world
+        self.advantages()
+        self.update()
+
+    def iteration(self, env_init=None, noise=None):
+        """One pass of the reference's outer loop.  Device-drawn noise (the default) replays a captured CUDA graph;
+        explicit ``noise`` (parity tests) and multi-GPU runs launch eagerly."""
+        if not self.use_graph or noise is not None:
+            return self._iteration_eager(env_init, noise)
+        reset = env_init is None
+        if not reset:
+            self.env.copy_(env_init, non_blocking=True)
+        if self._episode_dev is None:
+            self._episode_dev = torch.full((1,), self.episode, dtype=torch.int64, device=self.engine.device)
+            self.engine.set_episode_counter(self._episode_dev)
+        graph = self._graphs.get(reset)
+        if graph is None:
+            # first use: this iteration runs eagerly (it is the warm-up), the following ones replay the capture
+            l0 = self.engine.launches
+            self._launch_iteration(reset)
+            self.launches_per_iteration = self.engine.launches - l0
+            self._capture(reset)
+            return
+        graph.replay()
+        self.episode += 1
+        self.step += self.B * self.T * self.world
+        self.num_episodes += self.B * self.world
+        self.training_step += self.args.epochs
 
     # -- read-backs (each is one small D2H copy; nothing else synchronises) ---------------------
     def train_scalars(self) -> dict:

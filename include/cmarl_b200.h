@@ -99,6 +99,13 @@ const char* cmarl_kernel_name(int id);
  * keyed by (seed, episode); callers that need given start positions write `env` themselves. */
 int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, void* stream);
 
+/* Device-resident episode counter (optional): when set, cmarl_env_reset and cmarl_rollout key their Philox draws by
+ * *episode_dev instead of their by-value `episode` argument, and cmarl_episode_advance increments it on the stream --
+ * so a whole training iteration is a fixed launch sequence that a CUDA graph can replay (the reference draws fresh
+ * resets / samples every iteration, MME:393-401, 410-414).  NULL restores the by-value behaviour. */
+int cmarl_ctx_set_episode_counter(cmarl_ctx* ctx, uint64_t* episode_dev);
+int cmarl_episode_advance(cmarl_ctx* ctx, void* stream);
+
 /* -- K1 alone: the env duck-type one call at a time (cleanmarl/env/common_interface.py:5-23).
  * cmarl_env_observe: raw observations of the current state, state_out f32 [S][B]  (get_state /
  * the obs returned by reset, pettingzoo_wrapper.py:32-38, 93-98).
