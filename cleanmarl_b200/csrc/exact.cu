@@ -182,53 +182,83 @@ struct AdamArgs {
     int raw_stats;          // 1: stats_out = the five sums undivided, this step's norm, the valid count (single-net mode)
 };
 
-// Single CTA of 1024 threads: 9 670 parameters is <= 10 per thread, so every gradient is loaded once
-// into registers, the 12 per-tensor sums of squares are block-reduced together (fixed order =>
-// deterministic), and scale / clip / Adam / statistics all happen in this one launch.
+// ceil(P / 1024) CTAs of 1024 threads (a single CTA was issue-bound: ~3 600 instructions x 32 warps on one SM = 21 us).
+// Every CTA redundantly derives the 12 per-tensor sums of squares from ALL gradients (<= 12 coalesced loads per thread,
+// fixed summation order => every CTA -- and every rank of a multi-GPU run -- gets bit-identical norms and clip
+// coefficients), then updates only its own 1 024 parameters.  A warp whose 32 consecutive elements lie in one tensor
+// (all but <= 11 warp-rows) adds a single shuffle-reduced value into its private shared-memory row.
 constexpr int ADAM_THREADS = 1024;
 constexpr int ADAM_PER_THREAD = 12;      // supports up to 12 288 parameters
+__device__ unsigned int g_adam_ticket = 0;   // CTAs that have read *step_dev (one context per GPU, launches serialised)
+
+__device__ __forceinline__ int tensor_of(const AdamArgs& a, int i) {
+    int k = 0;
+#pragma unroll
+    for (int q = 1; q < 12; ++q) k += (i >= a.tensor_off[q]) ? 1 : 0;
+    return k;
+}
 
 __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
     __shared__ float wsum[ADAM_THREADS / 32][12];
     __shared__ float tnorm[12];
     __shared__ double bc_sh[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int P = a.tensor_off[a.n_tensors];
+    const int P = a.tensor_off[12];
     const float* stats = a.grads + P;
-    const float n_valid = stats[5];
-    const float count = n_valid * a.extra_div;
+    const int mine = blockIdx.x * ADAM_THREADS + tid;          // the parameter this thread updates
     // every global load is issued up front (one L2 round trip instead of two around the norm reduction)
-    float g[ADAM_PER_THREAD], pm[ADAM_PER_THREAD], pv[ADAM_PER_THREAD], pp[ADAM_PER_THREAD];
+    float g[ADAM_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < ADAM_PER_THREAD; ++j) {
         const int i = tid + j * ADAM_THREADS;
         g[j] = i < P ? a.grads[i] : 0.0f;
-        pm[j] = i < P ? a.m[i] : 0.0f;
-        pv[j] = i < P ? a.v[i] : 0.0f;
-        pp[j] = i < P ? a.params[i] : 0.0f;
     }
-    const int step = a.step_dev ? (*a.step_dev + 1) : a.step;
+    const float g_mine = mine < P ? a.grads[mine] : 0.0f;
+    const float pm = mine < P ? a.m[mine] : 0.0f;
+    const float pv = mine < P ? a.v[mine] : 0.0f;
+    const float pp = mine < P ? a.params[mine] : 0.0f;
+    const float n_valid = stats[5];
+    const float count = n_valid * a.extra_div;
     if (tid == ADAM_THREADS - 1) {      // a thread of the last warp: the first warps finish the reductions below
-        bc_sh[0] = 1.0 - pow(a.beta1, (double)step);
-        bc_sh[1] = sqrt(1.0 - pow(a.beta2, (double)step));
-    }
-#pragma unroll
-    for (int j = 0; j < ADAM_PER_THREAD; ++j) g[j] = g[j] / count;
-    // norm of the per-tensor norms (norm_d, MME:221-224) for each network
-    float ss[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) {
-        float s = 0.0f;
-#pragma unroll
-        for (int j = 0; j < ADAM_PER_THREAD; ++j) {
-            const int i = tid + j * ADAM_THREADS;
-            if (i >= a.tensor_off[k] && i < a.tensor_off[k + 1]) s += g[j] * g[j];
+        // the step count is read by this ONE thread per CTA; the last CTA to have read it publishes the new value
+        int step = a.step;
+        if (a.step_dev) {
+            step = *reinterpret_cast<volatile int32_t*>(a.step_dev) + 1;
+            __threadfence();
+            const unsigned t = atomicAdd(&g_adam_ticket, 1u);
+            if (t == gridDim.x - 1) { g_adam_ticket = 0; *a.step_dev = step; }
         }
-        ss[k] = warp_sum(s);
+        // beta^step by repeated squaring (<= 2 log2(step) fp64 multiplies, within a few ulp of pow(): no float32-visible
+        // difference in bc1, sqrt(bc2) or lr / bc1 for step <= 10^6)
+        double p1 = 1.0, p2 = 1.0, b1 = a.beta1, b2 = a.beta2;
+        for (unsigned e = (unsigned)step; e; e >>= 1) {
+            if (e & 1u) { p1 *= b1; p2 *= b2; }
+            b1 *= b1; b2 *= b2;
+        }
+        bc_sh[0] = 1.0 - p1;
+        bc_sh[1] = sqrt(1.0 - p2);
     }
-    if (lane == 0) {
+    if (lane < 12) wsum[warp][lane] = 0.0f;
+    __syncwarp();
+    // norm of the per-tensor norms (norm_d, MME:221-224): sums of squares of g / count per tensor
 #pragma unroll
-        for (int k = 0; k < 12; ++k) wsum[warp][k] = ss[k];
+    for (int j = 0; j < ADAM_PER_THREAD; ++j) {
+        const int i0 = warp * 32 + j * ADAM_THREADS;           // this warp's 32 consecutive elements
+        if (i0 >= P) break;                                     // warp-uniform
+        const float gs = g[j] / count;
+        const float sq = gs * gs;                               // 0 beyond P (g = 0)
+        const int k_lo = tensor_of(a, i0), k_hi = tensor_of(a, min(i0 + 31, P - 1));
+        if (k_lo == k_hi) {
+            const float t = warp_sum(sq);
+            if (lane == 0) wsum[warp][k_lo] += t;
+        } else {
+            const int k = tensor_of(a, min(i0 + lane, P - 1));
+            for (int q = k_lo; q <= k_hi; ++q) {                // a tensor boundary inside the warp: masked sums
+                const float t = warp_sum(k == q ? sq : 0.0f);
+                if (lane == 0) wsum[warp][q] += t;
+            }
+        }
+        __syncwarp();
     }
     __syncthreads();
     if (tid < 12) {
@@ -251,33 +281,28 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
             coef[net] = c < 1.0f ? c : 1.0f;
         }
     }
-    // bias corrections in double, as torch's python-float arithmetic (_single_tensor_adam); pow() is ~1 000 fp64
-    // instructions, so ONE thread evaluates it (it was done at the top, overlapping the norm reductions)
+    // bias corrections in double, as torch's python-float arithmetic (_single_tensor_adam)
     const double bc1 = bc_sh[0];
     const float bc2_sqrt = (float)bc_sh[1];
     const float w1 = (float)(1.0 - a.beta1);
     const float b2 = (float)a.beta2, w2 = (float)(1.0 - a.beta2);
     const float eps = (float)a.eps;
     const int actor_end = a.tensor_off[a.n_actor_tensors];
-    const float nss[2] = {(float)(-(a.lr[0] / bc1)), (float)(-(a.lr[1] / bc1))};
-#pragma unroll
-    for (int j = 0; j < ADAM_PER_THREAD; ++j) {
-        const int i = tid + j * ADAM_THREADS;
-        if (i >= P) continue;
-        const int net = i < actor_end ? 0 : 1;
-        float gi = g[j];
+    if (mine < P) {
+        const int net = mine < actor_end ? 0 : 1;
+        const float nss = (float)(-(a.lr[net] / bc1));
+        float gi = g_mine / count;
         if (a.max_norm > 0.0) gi = gi * coef[net];
-        float m = pm[j], v = pv[j];
+        float m = pm, v = pv;
         m = fmaf(w1, gi - m, m);                // exp_avg.lerp_(grad, 1 - beta1): ATen's lerp is an fma
         v = v * b2;                             // exp_avg_sq.mul_(beta2)
         v = v + (w2 * gi) * gi;                 //            .addcmul_(grad, grad, value=1 - beta2)
         const float denom = sqrtf(v) / bc2_sqrt + eps;
-        a.params[i] = pp[j] + (nss[net] * m) / denom;   // param.addcdiv_(m, denom, value=-step_size)
-        a.m[i] = m;
-        a.v[i] = v;
+        a.params[mine] = pp + (nss * m) / denom;   // param.addcdiv_(m, denom, value=-step_size)
+        a.m[mine] = m;
+        a.v[mine] = v;
     }
-    __syncthreads();
-    if (tid == 0) {
+    if (blockIdx.x == 0 && tid == 0) {
         if (a.stats_out && a.raw_stats) {
             for (int k = 0; k < 5; ++k) a.stats_out[k] = stats[k];
             a.stats_out[5] = net_norm[0];
@@ -289,7 +314,6 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
             a.stats_out[6] = net_norm[1];
             a.stats_out[7] = count;
         }
-        if (a.step_dev) *a.step_dev = step;
     }
 }
 
@@ -318,7 +342,7 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     a.extra_div = 1.0f; a.raw_stats = 0;
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
-        clip_adam_kernel<<<1, ADAM_THREADS, 0, as_stream(stream)>>>(a);
+        clip_adam_kernel<<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
     }
     return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
 }
@@ -355,7 +379,7 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     a.extra_div = (float)extra_div; a.raw_stats = 1;
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
-        clip_adam_kernel<<<1, ADAM_THREADS, 0, as_stream(stream)>>>(a);
+        clip_adam_kernel<<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
     }
     return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
 }
