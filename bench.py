@@ -256,6 +256,11 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def trace(msg):
+    if os.environ.get("CMARL_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_b200(a):
     import torch
     from cleanmarl_b200.mappo import MAPPO, Args, ArgsRecurrent, init_distributed
@@ -297,6 +302,7 @@ def run_b200(a):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t) / 1e3, wall, ms
 
+    trace("trainer ready")
     # ---- device-resident throughput (value): the iteration as the trainer runs it (CUDA-graph replay at N=1) ----
     for _ in range(max(a.warmup, 3)):
         tr.iteration()
@@ -311,6 +317,7 @@ def run_b200(a):
     per_step = B * world * T_STEPS * N_AGENTS
     value = per_step * a.steps / secs
 
+    trace("value timed")
     # ---- end to end through the public API: every step the start states of all envs come from pinned HOST memory
     #      and the step's results (per-epoch statistics, per-env episode returns) are read back to the host ----
     env_h = torch.empty(18, B, dtype=torch.float64).uniform_(-1, 1).pin_memory()
@@ -337,6 +344,7 @@ def run_b200(a):
     h2d = env_h.numel() * 8
     d2h = stats_h.numel() * 4 + ret_h.numel() * 8
 
+    trace("e2e timed")
     # ---- the same with the categorical race noise supplied by the host as well (what the parity tests do; eager) ----
     noise_h = torch.empty(T_STEPS, N_AGENTS, N_ACT, B).exponential_(1).pin_memory()
     noise_d = torch.empty_like(noise_h, device=dev)
@@ -360,6 +368,7 @@ def run_b200(a):
     clk = clocks.stop() if rank == 0 else None
 
     # ---- per-kernel device times over a few iterations (library-internal event pairs) ----
+    trace("e2e with host noise timed")
     graph_mode = tr.use_graph
     tr.use_graph = False                                         # event pairs live in the eager launch path
     eng.timing(True)
@@ -422,6 +431,7 @@ def run_b200(a):
                     "fp32_tflops": kernels[dom].get("tflops"), "fp32_peak_tflops": fp32_peak,
                     "fp32_frac": kernels[dom].get("fp32_frac")}
 
+    trace("per-kernel timing done")
     # ---- stand-alone GAE scan at a size that leaves L2 (the metric BASELINE.json names) ----
     gae = None
     if rank == 0 and a.gae_envs > 0:
