@@ -399,17 +399,11 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         };
         if ((int)blockIdx.x < units) load_x(blockIdx.x);
 
-        uint32_t par = 0;
-        int it = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, par ^= 1, ++it) {
-            const int bt = u % tiles_b, r = u / tiles_b;
-            const int t = r / src.G, g = r % src.G;
-            const int b = bt * M + s;
-            const bool inb = b < src.B;
-            const bool tl_on = g_tc_timeline_on == (OUT > 1 ? 2 : 1) && blockIdx.x == 0 && it == 1 && tid == 0;
-            TL_STAMP(0);
-
-            // ---- X -> split -> TMEM ------------------------------------------------------------------------
+        // X stage: the prefetched rows (xr) -> split -> TMEM X columns, hand-off to the issuer (F1), then prefetch the
+        // rows of the tile after.  It runs one tile AHEAD of the rest of the chain: as soon as the current tile no longer
+        // reads the X columns (forward: after F1; train: after the last dW1 round has been staged) the next tile's X is
+        // published, so its F1 runs under this tile's remaining epilogues instead of after them.
+        auto stage_x = [&](int u_next_next) {
 #pragma unroll
             for (int i = 0; i < NXO; ++i) {
                 const int c = 2 * i + hf;
@@ -426,8 +420,21 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 }
             }
             publish(&bars[R_X]);
+            if (u_next_next < units) load_x(u_next_next);               // latency hidden behind a whole tile
+        };
+        if ((int)blockIdx.x < units) stage_x(blockIdx.x + gridDim.x);
+
+        uint32_t par = 0;
+        int it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, par ^= 1, ++it) {
+            const int bt = u % tiles_b, r = u / tiles_b;
+            const int t = r / src.G, g = r % src.G;
+            const int b = bt * M + s;
+            const bool inb = b < src.B;
+            const bool tl_on = g_tc_timeline_on == (OUT > 1 ? 2 : 1) && blockIdx.x == 0 && it == 1 && tid == 0;
+            const bool has_next = u + (int)gridDim.x < units;
+            TL_STAMP(0);
             TL_STAMP(1);
-            if (u + (int)gridDim.x < units) load_x(u + gridDim.x);       // next tile's rows: latency hidden behind this tile
             // the head's per-sample inputs (half 0 evaluates the head): loaded now, used after F2
             const typename Head::In hin = Head::load(ha, t, g, b, src.G, src.B, inb && hf == 0);
 
@@ -458,6 +465,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             }
             publish(&bars[R_H1]);
             TL_STAMP(3);
+            if (!TRAIN && has_next) stage_x(u + 2 * gridDim.x);          // F1 of this tile has completed: X columns are free
             if (TRAIN) {
                 // round-0 features of H1 (chunk hf), sample-major, while F2 runs (B image is free: the previous
                 // tile's last weight-gradient round has completed)
@@ -531,24 +539,6 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             TL_STAMP(6);
 
             if (TRAIN) {
-                // dW3[a][j] += sum_s dz[s][a] h2[s][j] over this thread's columns; db3[a] += sum_s dz[s][a]
-#pragma unroll
-                for (int a = 0; a < OUT; ++a) {
-                    float p[NOWN * 16];
-#pragma unroll
-                    for (int i = 0; i < NOWN * 16; ++i) p[i] = dz[a] * h2[i];
-                    int idx;
-                    warp_reduce_scatter<NOWN * 16>(p, lane, idx);
-                    const int j = 16 * (2 * (idx >> 4) + hf) + (idx & 15);
-                    if (NOWN * 16 >= 32 || (lane & 1) == 0) dw3acc[a * H + j] += p[0];
-                    if (hf == 0) {
-                        float d = dz[a];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                        if (lane == 0) db3acc[a] += d;
-                    }
-                }
-                TL_STAMP(7);
                 // dH2 = (W3^T dz) . relu'(H2) -> split -> TMEM A (operand of B1) + sample-major A image (operand of dW2)
 #pragma unroll
                 for (int ci = 0; ci < NOWN; ++ci) {
@@ -581,6 +571,25 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 }
                 publish(&bars[R_DH2]);          // issuer: B1, then dW2 round 0
                 TL_STAMP(8);
+                // (runs under B1 / dW2 round 0 on the tensor pipe)
+                // dW3[a][j] += sum_s dz[s][a] h2[s][j] over this thread's columns; db3[a] += sum_s dz[s][a]
+#pragma unroll
+                for (int a = 0; a < OUT; ++a) {
+                    float p[NOWN * 16];
+#pragma unroll
+                    for (int i = 0; i < NOWN * 16; ++i) p[i] = dz[a] * h2[i];
+                    int idx;
+                    warp_reduce_scatter<NOWN * 16>(p, lane, idx);
+                    const int j = 16 * (2 * (idx >> 4) + hf) + (idx & 15);
+                    if (NOWN * 16 >= 32 || (lane & 1) == 0) dw3acc[a * H + j] += p[0];
+                    if (hf == 0) {
+                        float d = dz[a];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                        if (lane == 0) db3acc[a] += d;
+                    }
+                }
+                TL_STAMP(7);
 
                 // ---- E3: dH1 = D3 . relu'(H1) (H1 > 0 <=> D1 + b1 > 0) --------------------------------------
                 acquire(&bars[D_B1], par);
@@ -660,6 +669,8 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                     }
                     publish(&bars[rd == 0 ? R_W1A : R_W1B]);
                     TL_STAMP(14 + 2 * rd);
+                    // last read of this tile's X columns is behind us: stage the next tile's X under this round's MMAs
+                    if (rd == C::NR1 - 1 && has_next) stage_x(u + 2 * gridDim.x);
                     acquire(&bars[rd == 0 ? D_W1A : D_W1B], par);
                     TL_STAMP(15 + 2 * rd);
                 }
