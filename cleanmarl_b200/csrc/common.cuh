@@ -68,6 +68,7 @@ struct cmarl_ctx {
     int launches;
     int timing_on;
     int use_tc;         // 1: tcgen05 (3xTF32) chain kernels, 0: fp32 FFMA chain kernels
+    double weight_decay[2];  // actor, critic: decoupled weight decay of the Adam entries (AdamW); 0 = plain Adam
     uint64_t* episode_dev;   // optional device episode counter for the Philox draws (CUDA-graph replay)
     cmarl_timing* timing;
 };

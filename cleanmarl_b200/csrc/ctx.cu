@@ -151,6 +151,14 @@ extern "C" int cmarl_ctx_set_tensor_cores(cmarl_ctx* ctx, int on) {
     return 0;
 }
 
+extern "C" int cmarl_ctx_set_weight_decay(cmarl_ctx* ctx, double actor_wd, double critic_wd) {
+    CMARL_ARG(ctx, "null ctx");
+    CMARL_ARG(actor_wd >= 0.0 && critic_wd >= 0.0, "weight decay must be >= 0");
+    ctx->weight_decay[0] = actor_wd;
+    ctx->weight_decay[1] = critic_wd;
+    return 0;
+}
+
 extern "C" int cmarl_actor_param_count(const cmarl_ctx* ctx) { return ctx ? ctx->actor.count : -1; }
 extern "C" int cmarl_critic_param_count(const cmarl_ctx* ctx) { return ctx ? ctx->critic.count : -1; }
 extern "C" int cmarl_value_heads(const cmarl_ctx* ctx) { return ctx ? ctx->n_heads : -1; }

@@ -178,6 +178,7 @@ struct AdamArgs {
     int tensor_off[13];     // prefix offsets of the 12 parameter tensors, [12] = P
     int n_actor_tensors;    // 6
     double lr[2], beta1, beta2, eps, max_norm;
+    double wd[2];           // decoupled weight decay (torch.optim.AdamW: param.mul_(1 - lr * weight_decay)); 0 = Adam
     float extra_div;        // grads are divided by stats[5] * extra_div (T_chunk of a truncated-BPTT chunk, else 1)
     int raw_stats;          // 1: stats_out = the five sums undivided, this step's norm, the valid count (single-net mode)
 };
@@ -298,7 +299,9 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
         v = v * b2;                             // exp_avg_sq.mul_(beta2)
         v = v + (w2 * gi) * gi;                 //            .addcmul_(grad, grad, value=1 - beta2)
         const float denom = sqrtf(v) / bc2_sqrt + eps;
-        a.params[mine] = pp + (nss * m) / denom;   // param.addcdiv_(m, denom, value=-step_size)
+        float pw = pp;
+        if (a.wd[net] != 0.0) pw = pw * (float)(1.0 - a.lr[net] * a.wd[net]);   // AdamW: param.mul_(1 - lr * weight_decay)
+        a.params[mine] = pw + (nss * m) / denom;   // param.addcdiv_(m, denom, value=-step_size)
         a.m[mine] = m;
         a.v[mine] = v;
     }
@@ -340,6 +343,7 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     a.tensor_off[12] = base;
     a.lr[0] = lr_actor; a.lr[1] = lr_critic; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
     a.extra_div = 1.0f; a.raw_stats = 0;
+    a.wd[0] = ctx->weight_decay[0]; a.wd[1] = ctx->weight_decay[1];
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
         clip_adam_kernel<<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
@@ -377,6 +381,7 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     CMARL_ARG(a.tensor_off[k] <= ADAM_THREADS * ADAM_PER_THREAD, "too many parameters for clip_adam_kernel");
     a.lr[0] = lr; a.lr[1] = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
     a.extra_div = (float)extra_div; a.raw_stats = 1;
+    a.wd[0] = a.wd[1] = ctx->weight_decay[net];
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
         clip_adam_kernel<<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);

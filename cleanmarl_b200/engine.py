@@ -126,6 +126,11 @@ class Engine:
         return buf
 
     # ------------------------------------------------------------------ entries
+    def set_weight_decay(self, actor_wd: float, critic_wd: float):
+        """AdamW's decoupled weight decay for the Adam entries (0 = Adam)."""
+        _lib.check(self.lib.cmarl_ctx_set_weight_decay(self._h, float(actor_wd), float(critic_wd)),
+                   "cmarl_ctx_set_weight_decay")
+
     def set_episode_counter(self, counter):
         """``counter``: int64 device tensor [1] (or None) -- see cmarl_ctx_set_episode_counter."""
         ptr = None if counter is None else _ptr(counter, torch.int64, self.device, "episode counter")

@@ -96,6 +96,19 @@ class ArgsRecurrent(Args):
     """ Number of evaluation episodes"""
 
 
+@dataclass
+class ArgsRecurrentIPPO(ArgsRecurrent):
+    """``Args`` of ``cleanmarl/ippo_lstm_multienvs.py:18-81``: decentralised critic (hidden 32), AdamW, tbptt 5."""
+    critic_hidden_dim: int = 32
+    """ Hidden dimension of critic network"""
+    optimizer: str = "AdamW"
+    """ The optimizer"""
+    tbptt: int = 5
+    """Chunck size for Truncated Backpropagation Through Time tbptt"""
+    num_eval_ep: int = 10
+    """ Number of evaluation episodes"""
+
+
 def validate_args(args: Args):
     """Fail loudly at start-up on anything the device path does not implement (no fallbacks)."""
     if args.env_type != "pz" or args.env_family != "mpe" or args.env_name != "simple_spread_v3":
@@ -103,8 +116,8 @@ def validate_args(args: Args):
                          f"(got {args.env_type}/{args.env_family}/{args.env_name})")
     if not str(args.device).startswith("cuda"):
         raise SystemExit(f"--device {args.device}: cleanmarl_b200 runs on CUDA (sm_100a) only; there is no CPU path")
-    if args.optimizer != "Adam":
-        raise SystemExit("only --optimizer Adam is implemented")
+    if args.optimizer not in ("Adam", "AdamW"):
+        raise SystemExit("only --optimizer Adam and AdamW are implemented")
     recurrent = hasattr(args, "tbptt")
     if (not recurrent and args.actor_num_layers != 1) or args.critic_num_layers != 1:
         raise SystemExit("only *_num_layers 1 (the reference default) is implemented")
@@ -240,6 +253,8 @@ class MAPPO:
                         critic_hidden=args.critic_hidden_dim, critic_layers=args.critic_num_layers,
                         critic_on_obs=ippo, actor_recurrent=self.recurrent)
         self.engine = eng = engine_factory(shapes, device_index)
+        if args.optimizer == "AdamW":
+            eng.set_weight_decay(0.01, 0.01)                     # torch.optim.AdamW default weight_decay
         self.net = ActorCritic(eng, args.seed)                   # identical on every rank (same seed)
         self.exp_avg = torch.zeros_like(self.net.flat)
         self.exp_avg_sq = torch.zeros_like(self.net.flat)
@@ -329,7 +344,7 @@ class MAPPO:
                 self._allreduce(self.grads_a)
                 eng.adam_step_net(0, p_a, self.grads_a, m_a, v_a, step_dev=self.adam_step_a, lr=a.learning_rate_actor,
                                   max_norm=a.clip_gradients, extra_div=t1 - t0, stats_out=self.chunk_stats[ep, ci])
-            eng.critic_epoch_grads(p_c, self.grads_c, state=buf["state"], returns=buf["returns"])
+            eng.critic_epoch_grads(p_c, self.grads_c, state=buf["state"], returns=buf["returns"])   # IPPO: obs rebuilt from state
             self._allreduce(self.grads_c)
             eng.adam_step_net(1, p_c, self.grads_c, m_c, v_c, step_dev=self.adam_step, lr=a.learning_rate_critic,
                               max_norm=a.clip_gradients, stats_out=self.critic_stats[ep])

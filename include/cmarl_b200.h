@@ -79,6 +79,10 @@ int cmarl_ctx_destroy(cmarl_ctx* ctx);
  * 1 = tcgen05 tensor cores, kind::tf32 with a 3-term split (fp32-level accuracy, csrc/tc_chain.cu);
  * 0 = fp32 FFMA block GEMMs (csrc/chain.cu).  Both produce the same quantities to the stated tolerances. */
 int cmarl_ctx_set_tensor_cores(cmarl_ctx* ctx, int on);
+/* Decoupled weight decay for cmarl_clip_adam_step / cmarl_adam_step_net: torch.optim.AdamW's param.mul_(1 - lr * wd)
+ * before the Adam update (--optimizer AdamW, the default of ippo_lstm_multienvs.py:38; torch default wd = 0.01).
+ * 0 (the initial value) = torch.optim.Adam. */
+int cmarl_ctx_set_weight_decay(cmarl_ctx* ctx, double actor_weight_decay, double critic_weight_decay);
 int cmarl_actor_param_count(const cmarl_ctx* ctx);    /* 1 925 for the default shapes */
 int cmarl_critic_param_count(const cmarl_ctx* ctx);   /* 7 745 */
 int cmarl_value_heads(const cmarl_ctx* ctx);          /* V */

@@ -62,7 +62,7 @@ class GRUActor(nn.Module):
 
 
 def build_networks(seed, obs_dim=21, state_dim=54, n_actions=5, actor_hidden=32, critic_hidden=64, critic_layers=1):
-    """Seed, then Actor, then Critic -- LSTM:291-294, 327-338."""
+    """Seed, then Actor, then Critic -- LSTM:291-294, 327-338 (ippo_lstm_multienvs.py: state_dim = obs_dim, hidden 32)."""
     torch.manual_seed(seed)
     actor = GRUActor(obs_dim, actor_hidden, n_actions)
     critic = om.MLP(state_dim, critic_hidden, critic_layers, 1)
@@ -90,7 +90,7 @@ def tbptt_chunks(T: int, tbptt: int):
 
 
 def ppo_update_tbptt(actor: GRUActor, critic, actor_opt, critic_opt, batch, adv, ret, *, epochs, clip, ent_coef,
-                     tbptt=10, clip_gradients=-1.0, record_grads=False):
+                     tbptt=10, clip_gradients=-1.0, record_grads=False, critic_on_obs=False):
     """LSTM:551-664, line for line.  Returns per-epoch statistics (and, optionally, the per-chunk actor
     gradients / per-epoch critic gradients that autograd produced)."""
     obs, actions, old_logp, reward, states, avail, done, mask = batch
@@ -142,7 +142,10 @@ def ppo_update_tbptt(actor: GRUActor, critic, actor_opt, critic_opt, batch, adv,
                 actor_opt.step()
                 truncated = None
                 h = h.detach()
-            values = critic(states[:, t]).expand(-1, N)
+            if critic_on_obs:                      # ippo_lstm_multienvs.py:623 (Critic.forward ends with .squeeze(), :201)
+                values = critic(obs[:, t]).squeeze()
+            else:
+                values = critic(states[:, t]).expand(-1, N)
             critic_loss = critic_loss + F.mse_loss(values[m], ret[:, t][m]) * m.sum()
             kl_divergence = kl_divergence + ((ratio - 1) - log_ratio)[m].mean(dim=-1).sum()
             clipped_ratio = clipped_ratio + ((ratio - 1.0).abs() > clip)[m].float().mean(dim=-1).sum()

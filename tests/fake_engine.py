@@ -34,6 +34,10 @@ class OracleEngine:
         self.n_params = self.n_actor + self.n_critic
         self.n_heads = s.n_agents if s.critic_on_obs else 1
         self.launches = 0
+        self.weight_decay = (0.0, 0.0)
+
+    def set_weight_decay(self, actor_wd, critic_wd):
+        self.weight_decay = (float(actor_wd), float(critic_wd))
 
     # -- helpers -------------------------------------------------------------------------------
     def empty(self, *shape, dtype=torch.float32):
@@ -181,6 +185,9 @@ class OracleEngine:
             v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
             bc1, bc2 = 1 - beta1 ** k, 1 - beta2 ** k
             denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+            wd = self.weight_decay[0 if lo == 0 else 1]
+            if wd:
+                params[lo:hi].mul_(1 - lr * wd)
             params[lo:hi].addcdiv_(m, denom, value=-(lr / bc1))
         if stats_out is not None:
             stats_out[:5] = grads[P:P + 5] / count
@@ -266,6 +273,8 @@ class OracleEngine:
         exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
         bc1, bc2 = 1 - beta1 ** k, 1 - beta2 ** k
         denom = (exp_avg_sq.sqrt() / (bc2 ** 0.5)).add_(eps)
+        if self.weight_decay[net]:
+            params.mul_(1 - lr * self.weight_decay[net])
         params.addcdiv_(exp_avg, denom, value=-(lr / bc1))
         if stats_out is not None:
             stats_out[:5] = grads[P:P + 5]

@@ -24,6 +24,7 @@ g1_params.npz      also holds the recurrent ``Actor`` (fc1 + GRUCell + fc2) / ``
 g3_recurrent.npz   five consecutive ``Actor.act(x, h, avail)`` calls of the recurrent actor
                    (``mappo_lstm_multienvs.py:170-184``) with the hidden state carried, under a known
                    generator state + the exponential noise that state produces.
+g8_ippo_lstm.npz   the same for ``ippo_lstm_multienvs.py`` (decentralised critic on obs, AdamW, tbptt 5).
 g8_mappo_lstm*.npz one whole iteration of ``mappo_lstm_multienvs.py`` (rollout with the GRU actor, TD(lambda),
                    3 epochs of truncated BPTT with an actor Adam step per chunk, ``mappo_lstm_multienvs.py:551-664``);
                    ``_flags`` = tbptt 7, advantage normalisation, gradient clipping.
@@ -48,7 +49,7 @@ def flat(module):
     return torch.cat([p.detach().reshape(-1) for p in module.parameters()]).numpy()
 
 
-def g0(ref, ref_ippo, ref_lstm=None):
+def g0(ref, ref_ippo, ref_lstm=None, ref_ippo_lstm=None):
     """The reference's CLI dataclasses (MME:18-79, ippo_multienvs.py:18-79): field names, types, defaults."""
     import dataclasses
     import json
@@ -56,6 +57,8 @@ def g0(ref, ref_ippo, ref_lstm=None):
     mods = [("mappo_multienvs", ref), ("ippo_multienvs", ref_ippo)]
     if ref_lstm is not None:
         mods.append(("mappo_lstm_multienvs", ref_lstm))
+    if ref_ippo_lstm is not None:
+        mods.append(("ippo_lstm_multienvs", ref_ippo_lstm))
     for name, mod in mods:
         out[name] = [{"name": f.name, "type": getattr(f.type, "__name__", str(f.type)), "default": f.default}
                      for f in dataclasses.fields(mod.Args)]
@@ -195,6 +198,7 @@ def g8(script, tag, extra, B=6, seed=1):
     }
     if hasattr(args, "tbptt"):
         out["tbptt"] = np.array(args.tbptt)
+    out["optimizer"] = np.array(args.optimizer)
     np.savez_compressed(HERE / f"g8_{tag}.npz", **out)
     print(tag, "step", g["step"], "actor_losses", g["actor_losses"])
 
@@ -204,7 +208,7 @@ def main():
         raise SystemExit("reference sources not found")
     ref = ref_loader.load_module("mappo_multienvs.py")
     ref_ippo = ref_loader.load_module("ippo_multienvs.py")
-    g0(ref, ref_ippo, ref_loader.load_module("mappo_lstm_multienvs.py"))
+    g0(ref, ref_ippo, ref_loader.load_module("mappo_lstm_multienvs.py"), ref_loader.load_module("ippo_lstm_multienvs.py"))
     if "--only-args" in sys.argv:
         return
     if "--only-lstm" in sys.argv:
@@ -214,6 +218,10 @@ def main():
         g8("mappo_lstm_multienvs.py", "mappo_lstm", [], seed=4)
         g8("mappo_lstm_multienvs.py", "mappo_lstm_flags",
            ["--tbptt", "7", "--normalize_advantage", "--clip_gradients", "0.5"], seed=5)
+        g8("ippo_lstm_multienvs.py", "ippo_lstm", [], seed=6)
+        return
+    if "--only-ippo-lstm" in sys.argv:
+        g8("ippo_lstm_multienvs.py", "ippo_lstm", [], seed=6)
         return
     g1(ref, ref_ippo)
     g3(ref)
@@ -228,6 +236,7 @@ def main():
     g8("mappo_lstm_multienvs.py", "mappo_lstm", [], seed=4)
     g8("mappo_lstm_multienvs.py", "mappo_lstm_flags",
        ["--tbptt", "7", "--normalize_advantage", "--clip_gradients", "0.5"], seed=5)
+    g8("ippo_lstm_multienvs.py", "ippo_lstm", [], seed=6)
 
 
 if __name__ == "__main__":

@@ -120,9 +120,10 @@ def test_recurrent_rollout_matches_oracle(cm):
 
 # ----------------------------------------------------------------------------------------- K7a / K7b / K8 (TBPTT)
 def _device_update(eng, E, actor, critic, batch, adv, ret, *, epochs, tbptt, clip_gradients, lr_a, lr_c, use_mask=True,
-                   use_avail=True, use_obs=False):
+                   use_avail=True, use_obs=False, weight_decay=0.0):
     from cleanmarl_b200.mappo import tbptt_chunks
     dev = eng.device
+    eng.set_weight_decay(weight_decay, weight_decay)
     d = E.to_device_layout(batch, dev)
     na = eng.n_actor
     flat = torch.cat([actor.flat_params(), critic.flat_params()]).to(dev).contiguous()
@@ -158,20 +159,26 @@ def _device_update(eng, E, actor, critic, batch, adv, ret, *, epochs, tbptt, cli
     return out
 
 
-@pytest.mark.parametrize("name", ["g8_mappo_lstm", "g8_mappo_lstm_flags"])
+@pytest.mark.parametrize("name", ["g8_mappo_lstm", "g8_mappo_lstm_flags", "g8_ippo_lstm"])
 def test_tbptt_update_vs_reference_run(cm, golden, name):
     """The whole recurrent update on the batch of a real reference iteration (B = 6): per-epoch losses / statistics
     within 2e-5 relative, mean chunk gradient norm within 1e-4 relative, parameters after the reference's 3 epochs
     (9-12 actor Adam steps, 3 critic steps) within 3e-6."""
     from cleanmarl_b200 import engine as E
     g = golden(name)
-    actor, critic = ol.build_networks(int(g["seed"]))
+    ippo = name == "g8_ippo_lstm"        # ippo_lstm_multienvs.py: critic on obs (V = 3 heads), AdamW (wd 0.01), tbptt 5
     B = int(g["B"])
-    eng = make_engine(cm, B)
+    if ippo:
+        actor, critic = ol.build_networks(int(g["seed"]), state_dim=21, critic_hidden=32)
+        eng = make_engine(cm, B, critic_on_obs=True, critic_hidden=32)
+    else:
+        actor, critic = ol.build_networks(int(g["seed"]))
+        eng = make_engine(cm, B)
     batch = tuple(T(g[k]) for k in ("obs", "actions", "log_probs", "reward", "states", "avail", "done", "mask"))
     adv, ret = T(g["advantages"]), T(g["return_lambda"])
     out = _device_update(eng, E, actor, critic, batch, adv, ret, epochs=int(g["epochs"]), tbptt=int(g["tbptt"]),
-                         clip_gradients=float(g["clip_gradients"]), lr_a=float(g["lr_actor"]), lr_c=float(g["lr_critic"]))
+                         clip_gradients=float(g["clip_gradients"]), lr_a=float(g["lr_actor"]), lr_c=float(g["lr_critic"]),
+                         weight_decay=0.01 if ippo else 0.0)
     na = eng.n_actor
     for ep in range(int(g["epochs"])):
         cs, ks = out["chunk_stats"][ep], out["critic_stats"][ep]

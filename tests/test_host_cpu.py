@@ -74,9 +74,11 @@ def test_args_mirror_the_reference_dataclass():
     from cleanmarl_b200.mappo import Args
     from cleanmarl_b200.ippo_multienvs import Args as IppoArgs
     from cleanmarl_b200.mappo_lstm_multienvs import Args as LstmArgs
+    from cleanmarl_b200.ippo_lstm_multienvs import Args as IppoLstmArgs
     ref = json.loads((REPO / "tests" / "golden" / "g0_args.json").read_text())
     deviations = {"env_type": "pz", "env_name": "simple_spread_v3", "device": "cuda"}
-    for name, cls in (("mappo_multienvs", Args), ("ippo_multienvs", IppoArgs), ("mappo_lstm_multienvs", LstmArgs)):
+    for name, cls in (("mappo_multienvs", Args), ("ippo_multienvs", IppoArgs), ("mappo_lstm_multienvs", LstmArgs),
+                      ("ippo_lstm_multienvs", IppoLstmArgs)):
         ours = {f.name: f for f in dataclasses.fields(cls)}
         theirs = {f["name"]: f for f in ref[name]}
         assert sorted(ours) == sorted(theirs)            # (ippo_multienvs.py lists ppo_clip/entropy_coef before epochs;
@@ -97,6 +99,7 @@ def test_cli_parses_like_tyro_reference_and_rejects_what_is_not_built():
                 dict(actor_num_layers=2), dict(batch_size=0)):
         with pytest.raises(SystemExit):
             validate_args(dataclasses.replace(a, **bad))
+    validate_args(dataclasses.replace(a, optimizer="AdamW"))
     from cleanmarl_b200.mappo import ArgsRecurrent
     r = tyro.cli(ArgsRecurrent, args=["--batch_size", "8192", "--tbptt", "5"])
     assert r.tbptt == 5 and r.num_eval_ep == 5

@@ -175,24 +175,31 @@ def test_tbptt_chunks():
     assert ol.tbptt_chunks(25, 40) == [(0, 25)]
 
 
-@pytest.mark.parametrize("name", ["g8_mappo_lstm", "g8_mappo_lstm_flags"])
+@pytest.mark.parametrize("name", ["g8_mappo_lstm", "g8_mappo_lstm_flags", "g8_ippo_lstm"])
 def test_g8_recurrent_whole_iteration(golden, name):
-    """TD(lambda) + truncated-BPTT epochs (actor Adam step per chunk) reproduce the reference run bit for bit."""
+    """TD(lambda) + truncated-BPTT epochs (actor Adam step per chunk) reproduce the reference run bit for bit
+    (``g8_ippo_lstm``: ippo_lstm_multienvs.py -- critic on the observations, AdamW, tbptt 5)."""
     g = golden(name)
-    actor, critic = ol.build_networks(int(g["seed"]))
+    ippo = name == "g8_ippo_lstm"
+    if ippo:
+        actor, critic = ol.build_networks(int(g["seed"]), state_dim=21, critic_hidden=int(g["critic_hidden_dim"]))
+        assert str(g["optimizer"]) == "AdamW" and int(g["tbptt"]) == 5
+    else:
+        actor, critic = ol.build_networks(int(g["seed"]))
     batch = _batch(g)
     obs, actions, logp, reward, states, avail, done, mask = batch
-    ret, adv = om.td_lambda_loop(critic, states, reward, mask, float(g["gamma"]), float(g["td_lambda"]), 3)
+    ret, adv = om.td_lambda_loop(critic, obs if ippo else states, reward, mask, float(g["gamma"]), float(g["td_lambda"]), 3)
     if bool(g["normalize_advantage"]):
         adv = om.normalize_masked(adv, mask)
     if bool(g["normalize_return"]):
         ret = om.normalize_masked(ret, mask)
     assert np.array_equal(ret.numpy(), g["return_lambda"])
     assert np.array_equal(adv.numpy(), g["advantages"])
-    aopt, copt = om.make_optimizers(actor, critic, float(g["lr_actor"]), float(g["lr_critic"]))
+    aopt, copt = om.make_optimizers(actor, critic, float(g["lr_actor"]), float(g["lr_critic"]),
+                                    name=str(g["optimizer"]) if "optimizer" in g.files else "Adam")
     stats = ol.ppo_update_tbptt(actor, critic, aopt, copt, batch, adv, ret, epochs=int(g["epochs"]),
                                 clip=float(g["ppo_clip"]), ent_coef=float(g["entropy_coef"]),
-                                tbptt=int(g["tbptt"]), clip_gradients=float(g["clip_gradients"]))
+                                tbptt=int(g["tbptt"]), clip_gradients=float(g["clip_gradients"]), critic_on_obs=ippo)
     np.testing.assert_array_equal(np.array(stats["actor_loss"]), g["actor_losses"])
     np.testing.assert_array_equal(np.array(stats["critic_loss"]), g["critic_losses"])
     np.testing.assert_array_equal(np.array(stats["entropy"]), g["entropies"])
