@@ -480,3 +480,78 @@ def test_graph_replay_equals_eager_launches(cm, recurrent):
         tr2.iteration(env_init=env)
     torch.cuda.synchronize()
     assert torch.equal(tr.net.flat, tr2.net.flat) and torch.equal(tr.buf["actions"], tr2.buf["actions"])
+
+
+# ----------------------------------------------------------------------------------------- full size / tiny size
+def test_full_size_iteration_properties(cm):
+    """BASELINE's largest per-GPU size (65 536 envs, 1.6 M env-steps per rollout) through size-independent properties:
+    buffers finite and in range, physics consistent step to step, TD(lambda) recursion re-evaluated with separately
+    rounded torch ops on the device bit for bit, A == R - V bit for bit, valid count exact, parameters move."""
+    from cleanmarl_b200.mappo import MAPPO, Args
+    B, Tn = 65536, 25
+    tr = MAPPO(Args(batch_size=B, seed=2), use_graph=False)
+    p0 = tr.net.flat.clone()
+    tr.iteration()
+    torch.cuda.synchronize()
+    buf = tr.buf
+    st, acts, logp, rew = buf["state"], buf["actions"], buf["logp"], buf["reward"]
+    assert torch.isfinite(st).all() and torch.isfinite(logp).all() and torch.isfinite(rew).all()
+    assert int(acts.min()) >= 0 and int(acts.max()) <= 4 and float(logp.max()) <= 0.0
+    assert float(rew.max()) <= 0.0                                     # -distances - collisions
+    raw = st.reshape(Tn, 3, 18, B)
+    assert (raw[:, :, 14:18] == 0).all()                               # silent agents: 4 zero communication slots
+    # p_pos(t+1) = p_pos(t) + p_vel(t) * dt (positions first, fp64 inside the kernel; fp32 observations here)
+    pred = raw[:-1, :, 2:4].double() + raw[:-1, :, 0:2].double() * 0.1
+    assert (raw[1:, :, 2:4].double() - pred).abs().max() < 1e-6
+    # every agent sees the same landmarks: landmark_rel + own pos is agent-independent
+    lm = raw[:, :, 4:10].reshape(Tn, 3, 3, 2, B) + raw[:, :, None, 2:4]
+    assert (lm[:, 0] - lm[:, 1]).abs().max() < 1e-6 and (lm[:, 0] - lm[:, 2]).abs().max() < 1e-6
+    # action frequencies of the freshly initialised policy are near uniform
+    freq = torch.bincount(acts.flatten().long(), minlength=5).float() / acts.numel()
+    assert (freq - 0.2).abs().max() < 0.05
+    # TD(lambda): R_t = r_t + g (l R_{t+1} + (1 - l) V_{t+1}), bootstrap 0 at the end; separately rounded fp32 ops
+    V, R, A = buf["values"][:, 0], buf["returns"][:, 0], buf["adv"][:, 0]
+    g = torch.tensor(0.99, device=V.device); l = torch.tensor(0.95, device=V.device)
+    oml = torch.tensor(1 - 0.95, dtype=torch.float32, device=V.device)
+    last = torch.zeros(B, device=V.device)
+    for t in reversed(range(Tn)):
+        nv = V[t + 1] if t + 1 < Tn else torch.zeros(B, device=V.device)
+        inner = l * last
+        inner = inner + oml * nv
+        rt = rew[t] + g * inner
+        assert torch.equal(rt, R[t]), t
+        last = rt
+    assert torch.equal(A, R - V)
+    s = tr.epoch_stats.cpu()
+    assert (s[:, 7] == B * Tn).all() and torch.isfinite(s).all()
+    assert not torch.equal(tr.net.flat, p0) and torch.isfinite(tr.net.flat).all()
+    assert abs(float(buf["ep_return"].mean()) - float(rew.double().sum(0).mean())) < 1e-5
+
+
+@pytest.mark.parametrize("B", [1, 5, 33])
+@pytest.mark.parametrize("recurrent", [False, True], ids=["mlp", "recurrent"])
+def test_tiny_and_ragged_env_counts(cm, B, recurrent):
+    """One env, a handful, one more than a warp: every kernel's ragged-tile path against the oracle (whole iteration)."""
+    from cleanmarl_b200.mappo import MAPPO, Args, ArgsRecurrent
+    from cleanmarl_b200 import engine as E
+    from oracle import mappo_lstm as ol
+    tr = MAPPO((ArgsRecurrent if recurrent else Args)(batch_size=B, seed=6), use_graph=False)
+    actor, critic = (ol if recurrent else om).build_networks(6)
+    g = torch.Generator().manual_seed(B)
+    env = torch.zeros(18, B, dtype=torch.float64)
+    env[0:6] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    env[12:18] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    noise = torch.empty(25, 3, 5, B).exponential_(1, generator=g)
+    tr.iteration(env.cuda(), noise.cuda())
+    torch.cuda.synchronize()
+    batch = tuple(t.cpu() for t in tr.get_batch())
+    ret, adv = om.td_lambda_batched(critic, batch[4], batch[3], batch[7], 0.99, 0.95, 3)
+    assert (E.heads_to_reference(tr.buf["adv"], 3).cpu() - adv).abs().max() < 1e-5
+    aopt, copt = om.make_optimizers(actor, critic)
+    if recurrent:
+        ol.ppo_update_tbptt(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001, tbptt=10)
+    else:
+        om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001)
+    final = torch.cat([actor.flat_params(), critic.flat_params()])
+    dp = (tr.net.flat.cpu() - final).abs()
+    assert (dp < 3e-6).float().mean() > 0.99 and dp.max() < 2e-4       # near-eps Adam gradients: see test_gpu_recurrent
