@@ -172,7 +172,12 @@ struct RolloutArgs {
 // The env state (18 doubles per env) lives in shared memory for the whole episode; T steps in ONE launch.
 constexpr int REPB = 32;                 // envs per CTA
 constexpr int NQ = 4;                    // warps per agent
-constexpr int RTHREADS = REPB * NAG * NQ;   // 384
+constexpr int RTHREADS = REPB * NAG * NQ;   // 384 actor threads
+// + one warp per agent pair that evaluates the float64 contact force (exp / log1p / sqrt, ~2 000 cycles) WHILE the actor
+// warps run the network: the force depends only on the positions, not on the action, so it leaves the critical path
+// of a step (obs -> layers -> sample -> integrate).  The recurrent variant keeps 12 warps (168 registers per thread).
+constexpr int RPHYS = 3;
+template <bool GRU> struct RolloutThreads { static constexpr int N = GRU ? RTHREADS : RTHREADS + 32 * RPHYS; };
 constexpr int W1LD = 16;                 // layer-1 rows padded to 16 inputs (14 non-zero observation entries)
 
 // debug timeline of CTA 0, step 10 (clock64): slots 0-7 warp (0,0) [sampler], 8-15 warp (0,1) [physics]
@@ -213,7 +218,9 @@ struct RolloutLayout {
 };
 
 template <int H, int O, bool GRU>
-__global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
+__global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(RolloutArgs a) {
+    constexpr int NTHR = RolloutThreads<GRU>::N;
+    constexpr bool PHYSW = NTHR > RTHREADS;                   // dedicated contact-force warps present
     using RL = RolloutLayout<H, O, GRU>;
     constexpr int pW1 = RL::pW1, pB1 = RL::pB1, pW2 = RL::pW2, pB2 = RL::pB2, pW3 = RL::pW3, pB3 = RL::pB3;
     constexpr int sW1 = RL::sW1, sB1 = RL::sB1, sW2 = RL::sW2, sB2 = RL::sB2, sW3 = RL::sW3, sB3 = RL::sB3, sEnd = RL::sEnd;
@@ -237,41 +244,55 @@ __global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
     const int B = a.B;
     const int j0 = qq * JL;
 
-    for (int i = tid; i < 18 * REPB; i += RTHREADS) {
+    for (int i = tid; i < 18 * REPB; i += NTHR) {
         const int r = i / REPB, c = i - r * REPB;
         const int bb = blockIdx.x * REPB + c;
         es[r][c] = (bb < B) ? a.env[(size_t)r * B + bb] : 0.0;
     }
     {
         const float* P = a.actor;
-        for (int i = tid; i < H * W1LD; i += RTHREADS) {
+        for (int i = tid; i < H * W1LD; i += NTHR) {
             const int j = i / W1LD, k = i - j * W1LD;
             sw[sW1 + i] = (k < CMARL_RAW_OBS - 4) ? P[pW1 + j * O + k] : 0.0f;
         }
-        for (int i = tid; i < NAG * H; i += RTHREADS) {
+        for (int i = tid; i < NAG * H; i += NTHR) {
             const int g = i / H, j = i - g * H;
             sw[sB1 + i] = P[pB1 + j] + (FOLD ? P[pW1 + j * O + CMARL_RAW_OBS + g] : 0.0f);   // one-hot id column of agent g
         }
         if (GRU) {
-            for (int i = tid; i < 3 * H * H; i += RTHREADS) { sw[RL::sWih + i] = P[RL::pWih + i]; sw[RL::sWhh + i] = P[RL::pWhh + i]; }
-            for (int j = tid; j < H; j += RTHREADS) {     // bir + bhr, biz + bhz, bin, bhn
+            for (int i = tid; i < 3 * H * H; i += NTHR) { sw[RL::sWih + i] = P[RL::pWih + i]; sw[RL::sWhh + i] = P[RL::pWhh + i]; }
+            for (int j = tid; j < H; j += NTHR) {     // bir + bhr, biz + bhz, bin, bhn
                 sw[RL::sBg + 4 * j + 0] = P[RL::pBih + j] + P[RL::pBhh + j];
                 sw[RL::sBg + 4 * j + 1] = P[RL::pBih + H + j] + P[RL::pBhh + H + j];
                 sw[RL::sBg + 4 * j + 2] = P[RL::pBih + 2 * H + j];
                 sw[RL::sBg + 4 * j + 3] = P[RL::pBhh + 2 * H + j];
             }
-            for (int i = tid; i < 2 * NAG * H * REPB; i += RTHREADS) (&hs[0][0][0][0])[i] = 0.0f;   // h = None
+            for (int i = tid; i < 2 * NAG * H * REPB; i += NTHR) (&hs[0][0][0][0])[i] = 0.0f;   // h = None
         } else {
-            for (int i = tid; i < H * H; i += RTHREADS) sw[sW2 + i] = P[pW2 + i];
-            for (int i = tid; i < H; i += RTHREADS) sw[sB2 + i] = P[pB2 + i];
+            for (int i = tid; i < H * H; i += NTHR) sw[sW2 + i] = P[pW2 + i];
+            for (int i = tid; i < H; i += NTHR) sw[sB2 + i] = P[pB2 + i];
         }
-        for (int i = tid; i < NACT * H; i += RTHREADS) sw[sW3 + i] = P[pW3 + i];
+        for (int i = tid; i < NACT * H; i += NTHR) sw[sW3 + i] = P[pW3 + i];
         if (tid < 8) sw[sB3 + tid] = tid < NACT ? P[pB3 + tid] : 0.0f;
     }
     __syncthreads();
     double ep_acc = 0.0;                                     // threads 0..REPB-1: episode return of env tid
     const uint64_t episode = a.episode_dev ? *a.episode_dev : a.episode;
 
+    if (PHYSW && w >= NAG * NQ) {
+        // contact-force warps: pair p = (0,1), (0,2), (1,2) of every env, each evaluated ONCE per step from the
+        // positions the integration of the previous step left in shared memory; two block barriers per step, like
+        // the actor warps below
+        const int p = w - NAG * NQ;
+        const int ia = (p == 2) ? 1 : 0, ib = (p == 0) ? 1 : 2;
+        for (int t = 0; t < a.T; ++t) {
+            double gx, gy;
+            spread::pair_force(es[2 * ia][e], es[2 * ia + 1][e], es[2 * ib][e], es[2 * ib + 1][e], gx, gy);
+            pf[p][e][0] = gx; pf[p][e][1] = gy;
+            __syncthreads();
+            __syncthreads();
+        }
+    } else
     for (int t = 0; t < a.T; ++t) {
         // ---- observation before the action (what the reference stores, MME:426-430): vel, pos, landmarks - pos,
         //      other agents - pos, 4 zeros (spread::observe); dynamic indices go to shared memory ------------------
@@ -440,13 +461,15 @@ __global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
             if (live) __stcs(a.reward + (size_t)(t - 1) * B + b, (float)r);
         }
         if (qq == 1) {
-            // (b) the 3 contact pairs of every env, each evaluated ONCE: warp (n, 1) takes pair n: (0,1), (0,2), (1,2)
-            const int ia = (n == 2) ? 1 : 0, ib = (n == 0) ? 1 : 2;
-            double gx, gy;
-            spread::pair_force(es[2 * ia][e], es[2 * ia + 1][e], es[2 * ib][e], es[2 * ib + 1][e], gx, gy);
-            pf[n][e][0] = gx; pf[n][e][1] = gy;
-            RTL(11, w == 1);
-            asm volatile("bar.sync 4, 96;" ::: "memory");               // the three physics warps
+            if (!PHYSW) {
+                // (b) the 3 contact pairs of every env, each evaluated ONCE: warp (n, 1) takes pair n: (0,1), (0,2), (1,2)
+                const int ia = (n == 2) ? 1 : 0, ib = (n == 0) ? 1 : 2;
+                double gx, gy;
+                spread::pair_force(es[2 * ia][e], es[2 * ia + 1][e], es[2 * ib][e], es[2 * ib + 1][e], gx, gy);
+                pf[n][e][0] = gx; pf[n][e][1] = gy;
+                RTL(11, w == 1);
+                asm volatile("bar.sync 4, 96;" ::: "memory");               // the three physics warps
+            }
             RTL(12, w == 1);
             // (c) integration of agent n; forces added in the reference's pair order (0,1),(0,2),(1,2)
             const int act = acts[n][e];
@@ -491,7 +514,7 @@ __global__ void __launch_bounds__(RTHREADS) rollout_kernel(RolloutArgs a) {
             if (a.ep_return) a.ep_return[b] = ep_acc;
         }
     }
-    for (int i = tid; i < 12 * REPB; i += RTHREADS) {
+    for (int i = tid; i < 12 * REPB; i += NTHR) {
         const int r = i / REPB, c = i - r * REPB;
         const int bb = blockIdx.x * REPB + c;
         if (bb < B) a.env[(size_t)r * B + bb] = es[r][c];
@@ -690,8 +713,8 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
         constexpr size_t smem21 = (size_t)RolloutLayout<32, 21, true>::floats * sizeof(float);
         constexpr size_t smem18 = (size_t)RolloutLayout<32, 18, true>::floats * sizeof(float);
         KernelTimer kt(ctx, K_ROLLOUT, st);
-        if (ids) rollout_kernel<32, 21, true><<<grid, RTHREADS, smem21, st>>>(a);
-        else rollout_kernel<32, 18, true><<<grid, RTHREADS, smem18, st>>>(a);
+        if (ids) rollout_kernel<32, 21, true><<<grid, RolloutThreads<true>::N, smem21, st>>>(a);
+        else rollout_kernel<32, 18, true><<<grid, RolloutThreads<true>::N, smem18, st>>>(a);
         return cmarl_check_cuda(cudaGetLastError(), "rollout_kernel (recurrent)");
     }
     const size_t smem = (size_t)(H * W1LD + NAG * H + H * H + H + NACT * H + 8 + NAG * H * REPB + NAG * NQ * NACT * REPB +
@@ -699,11 +722,11 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
     {
         KernelTimer kt(ctx, K_ROLLOUT, st);
         if (H == 32) {
-            if (ids) rollout_kernel<32, 21, false><<<grid, RTHREADS, smem, st>>>(a);
-            else rollout_kernel<32, 18, false><<<grid, RTHREADS, smem, st>>>(a);
+            if (ids) rollout_kernel<32, 21, false><<<grid, RolloutThreads<false>::N, smem, st>>>(a);
+            else rollout_kernel<32, 18, false><<<grid, RolloutThreads<false>::N, smem, st>>>(a);
         } else {
-            if (ids) rollout_kernel<64, 21, false><<<grid, RTHREADS, smem, st>>>(a);
-            else rollout_kernel<64, 18, false><<<grid, RTHREADS, smem, st>>>(a);
+            if (ids) rollout_kernel<64, 21, false><<<grid, RolloutThreads<false>::N, smem, st>>>(a);
+            else rollout_kernel<64, 18, false><<<grid, RolloutThreads<false>::N, smem, st>>>(a);
         }
     }
     return cmarl_check_cuda(cudaGetLastError(), "rollout_kernel");
