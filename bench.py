@@ -262,10 +262,19 @@ def run_reference(a):
                             "torch_threads": torch.get_num_threads()},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+_JSON_OUT = None
+
+
+def emit(obj):
+    f = _JSON_OUT or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
+
+
 def trace(msg):
     if os.environ.get("CMARL_BENCH_TRACE"):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
@@ -494,7 +503,7 @@ def run_b200(a):
                "launch_mode": "CUDA graph replay of the iteration" if graph_mode else "eager stream launches",
                "clocks": clk, "roofline": roofline, "gae_roofline": gae,
                "kernels": kernels, "cpu_baseline": cpu, "wall_ms_per_step": wall / a.steps * 1e3}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -502,6 +511,12 @@ def run_b200(a):
 
 def main():
     a = parse()
+    # stdout carries exactly ONE line (the JSON): everything else that writes to fd 1 -- NCCL's version banner, library
+    # chatter of the reference arm -- is sent to stderr for the whole run
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -282,6 +282,8 @@ class MAPPO:
         # path from the loop.  Needs the device episode counter; single-GPU only (the NCCL all-reduce stays eager).
         if use_graph is None:
             use_graph = os.environ.get("CMARL_GRAPH", "1") != "0"
+        # (multi-GPU stays eager: with the NCCL all-reduces captured into the graph the 2-GPU bench hung when it later
+        # mixed replays with eager collectives on the same communicator -- measured round 1, not pursued)
         self.use_graph = bool(use_graph) and world_size == 1 and engine_factory is Engine
         self._graphs = {}
         self._episode_dev = None
