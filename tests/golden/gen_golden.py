@@ -59,6 +59,8 @@ def g0(ref, ref_ippo, ref_lstm=None, ref_ippo_lstm=None):
         mods.append(("mappo_lstm_multienvs", ref_lstm))
     if ref_ippo_lstm is not None:
         mods.append(("ippo_lstm_multienvs", ref_ippo_lstm))
+        for single in ("mappo", "ippo", "mappo_lstm", "ippo_lstm"):          # the single-env scripts (same update code)
+            mods.append((single, ref_loader.load_module(single + ".py")))
     for name, mod in mods:
         out[name] = [{"name": f.name, "type": getattr(f.type, "__name__", str(f.type)), "default": f.default}
                      for f in dataclasses.fields(mod.Args)]

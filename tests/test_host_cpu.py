@@ -77,8 +77,10 @@ def test_args_mirror_the_reference_dataclass():
     from cleanmarl_b200.ippo_lstm_multienvs import Args as IppoLstmArgs
     ref = json.loads((REPO / "tests" / "golden" / "g0_args.json").read_text())
     deviations = {"env_type": "pz", "env_name": "simple_spread_v3", "device": "cuda"}
-    for name, cls in (("mappo_multienvs", Args), ("ippo_multienvs", IppoArgs), ("mappo_lstm_multienvs", LstmArgs),
-                      ("ippo_lstm_multienvs", IppoLstmArgs)):
+    import importlib
+    singles = [(n, importlib.import_module(f"cleanmarl_b200.single.{n}").Args) for n in ("mappo", "ippo", "mappo_lstm", "ippo_lstm")]
+    for name, cls in [("mappo_multienvs", Args), ("ippo_multienvs", IppoArgs), ("mappo_lstm_multienvs", LstmArgs),
+                      ("ippo_lstm_multienvs", IppoLstmArgs)] + singles:
         ours = {f.name: f for f in dataclasses.fields(cls)}
         theirs = {f["name"]: f for f in ref[name]}
         assert sorted(ours) == sorted(theirs)            # (ippo_multienvs.py lists ppo_clip/entropy_coef before epochs;
