@@ -450,32 +450,6 @@ int cmarl_reduce_one_net(cmarl_ctx* ctx, const float* pa, int grid_a, int Pa, co
     return cmarl_check_cuda(cudaGetLastError(), "reduce_partials_kernel");
 }
 
-extern "C" int cmarl_actor_epoch_grads(cmarl_ctx* ctx, const float* actor_params, const float* state, const float* obs,
-                                       const int32_t* actions, const float* logp_old, const float* adv,
-                                       const uint8_t* mask, const uint8_t* avail, double clip, double ent_coef,
-                                       float* grads_out, void* workspace, void* stream) {
-    CMARL_ARG(ctx && actor_params && actions && logp_old && adv && grads_out && workspace, "null argument");
-    CMARL_ARG(!ctx->cfg.actor_recurrent, "recurrent actor: use cmarl_tbptt_chunk_grads");
-    CMARL_ARG(state || obs, "state or obs required");
-    const cmarl_config& c = ctx->cfg;
-    cudaStream_t st = as_stream(stream);
-    const int Pa = ctx->actor.count;
-    float* part_a = reinterpret_cast<float*>(workspace);
-    NetDesc nda; TileSrc srca;
-    actor_desc(ctx, actor_params, state, obs, nda, srca);
-    PolicyHeadArgs pa;
-    pa.actions = actions; pa.logp_old = logp_old; pa.adv = adv; pa.mask = mask; pa.avail = avail;
-    pa.V = ctx->n_heads; pa.A = c.n_actions;
-    pa.clip = (float)clip; pa.ent_coef = (float)ent_coef; pa.inv_groups = 1.0f / (float)c.n_agents;
-    int grid_a = 0, e;
-    {
-        KernelTimer kt(ctx, K_PPO_ACTOR, st);
-        e = run_chain<PolicyHead, true>(ctx, c.actor_hidden, nda, srca, pa, part_a, Pa, &grid_a, st);
-    }
-    if (e) return e;
-    return cmarl_reduce_one_net(ctx, part_a, grid_a, Pa, nullptr, 0, 0, (float)c.n_agents, grads_out, st);
-}
-
 extern "C" int cmarl_critic_epoch_grads(cmarl_ctx* ctx, const float* critic_params, const float* state, const float* obs,
                                         const float* returns, const uint8_t* mask, float* grads_out, void* workspace,
                                         void* stream) {
@@ -483,9 +457,7 @@ extern "C" int cmarl_critic_epoch_grads(cmarl_ctx* ctx, const float* critic_para
     CMARL_ARG(ctx->cfg.critic_on_obs ? (state || obs) : (state != nullptr), "critic input missing");
     cudaStream_t st = as_stream(stream);
     const int Pc = ctx->critic.count;
-    // the critic's region of the workspace (same split as cmarl_ppo_epoch_grads): the actor-only entries may run
-    // concurrently on another stream
-    float* part_c = reinterpret_cast<float*>(workspace) + (size_t)2 * ctx->sm_count * (ctx->actor.count + CMARL_N_STATS);
+    float* part_c = reinterpret_cast<float*>(workspace);
     NetDesc ndc; TileSrc srcc;
     critic_desc(ctx, critic_params, state, obs, ndc, srcc);
     ValueHeadArgs va;

@@ -227,15 +227,6 @@ class Engine:
             float(clip), float(ent_coef), int(t0), int(t1), self._f(h_seq, "h_seq"), self._f(grads, "grads"),
             C.c_void_p(self.workspace.data_ptr()), self._stream()), "cmarl_tbptt_chunk_grads")
 
-    def actor_epoch_grads(self, actor_params, grads, *, state=None, obs=None, actions, logp_old, adv, mask=None,
-                          avail=None, clip=0.2, ent_coef=0.001):
-        _lib.check(self.lib.cmarl_actor_epoch_grads(
-            self._h, self._f(actor_params, "actor_params"), self._f(state, "state"), self._f(obs, "obs"),
-            _ptr(actions, torch.int32, self.device, "actions"), self._f(logp_old, "logp_old"), self._f(adv, "adv"),
-            _ptr(mask, torch.uint8, self.device, "mask"), _ptr(avail, torch.uint8, self.device, "avail"),
-            float(clip), float(ent_coef), self._f(grads, "grads"), C.c_void_p(self.workspace.data_ptr()),
-            self._stream()), "cmarl_actor_epoch_grads")
-
     def critic_epoch_grads(self, critic_params, grads, *, state=None, obs=None, returns, mask=None):
         _lib.check(self.lib.cmarl_critic_epoch_grads(
             self._h, self._f(critic_params, "critic_params"), self._f(state, "state"), self._f(obs, "obs"),

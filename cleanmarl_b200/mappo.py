@@ -271,18 +271,6 @@ class MAPPO:
             self.adam_step_a = torch.zeros(1, dtype=torch.int32, device=eng.device)
             self.chunk_stats = eng.empty(args.epochs, len(self.chunks), 8)
             self.critic_stats = eng.empty(args.epochs, 8)
-        # MLP path on one GPU: the actor's and the critic's epochs are independent (MME:530-551 vs 554-558), so each
-        # network gets its own stream -- the small reduce / Adam launches of one hide under the other's chain kernel
-        self.two_streams = (not self.recurrent and world_size == 1 and engine_factory is Engine
-                            and os.environ.get("CMARL_TWO_STREAMS", "1") != "0")
-        if self.two_streams:
-            self.grads_a = eng.empty(eng.n_actor + 8)
-            self.grads_c = eng.empty(eng.n_critic + 8)
-            self.adam_step_a = torch.zeros(1, dtype=torch.int32, device=eng.device)
-            self.actor_stats = eng.empty(args.epochs, 8)
-            self.critic_stats = eng.empty(args.epochs, 8)
-            self._stream_a = torch.cuda.Stream(device=eng.device)
-            self._stream_c = torch.cuda.Stream(device=eng.device)
         self.env = eng.empty(18, self.B, dtype=torch.float64)
         # every rank draws from its own Philox key so shards are independent
         self.rng_key = (args.seed + 0x9E3779B97F4A7C15 * (rank + 1)) & (2**64 - 1)
@@ -374,47 +362,10 @@ class MAPPO:
         es[:, 6] = ks[:, 5]
         es[:, 7] = n
 
-    def update_two_streams(self):
-        """MME:521-603 with the two networks on two streams (single GPU): per epoch and network one chain kernel, one
-        fixed-order reduction, one Adam launch; same kernels and arithmetic as ``update`` (bit-identical parameters)."""
-        eng, buf, a = self.engine, self.buf, self.args
-        na = eng.n_actor
-        p_a, p_c = self.net.flat[:na], self.net.flat[na:]
-        m_a, m_c = self.exp_avg[:na], self.exp_avg[na:]
-        v_a, v_c = self.exp_avg_sq[:na], self.exp_avg_sq[na:]
-        main = torch.cuda.current_stream(eng.device)
-        sa, sc = self._stream_a, self._stream_c
-        sa.wait_stream(main)
-        sc.wait_stream(main)
-        for ep in range(a.epochs):
-            with torch.cuda.stream(sa):
-                eng.actor_epoch_grads(p_a, self.grads_a, state=buf["state"], actions=buf["actions"], logp_old=buf["logp"],
-                                      adv=buf["adv"], clip=a.ppo_clip, ent_coef=a.entropy_coef)
-                eng.adam_step_net(0, p_a, self.grads_a, m_a, v_a, step_dev=self.adam_step_a, lr=a.learning_rate_actor,
-                                  max_norm=a.clip_gradients, stats_out=self.actor_stats[ep])
-            with torch.cuda.stream(sc):
-                eng.critic_epoch_grads(p_c, self.grads_c, state=buf["state"], returns=buf["returns"])
-                eng.adam_step_net(1, p_c, self.grads_c, m_c, v_c, step_dev=self.adam_step, lr=a.learning_rate_critic,
-                                  max_norm=a.clip_gradients, stats_out=self.critic_stats[ep])
-            self.training_step += 1
-        main.wait_stream(sa)
-        main.wait_stream(sc)
-        # the scalars of MME:572-576, 584-585 in the layout clip_adam_step writes (logging only)
-        s_a, s_c, es = self.actor_stats, self.critic_stats, self.epoch_stats
-        n = s_a[:, 6]
-        es[:, 0] = s_a[:, 0] / n
-        es[:, 1] = s_c[:, 1] / s_c[:, 6]
-        es[:, 2:5] = s_a[:, 2:5] / n[:, None]
-        es[:, 5] = s_a[:, 5]
-        es[:, 6] = s_c[:, 5]
-        es[:, 7] = n
-
     def update(self):
         """MME:521-603: one NCCL all-reduce of the flat gradient (+8 statistics) per epoch."""
         if self.recurrent:
             return self.update_recurrent()
-        if self.two_streams:
-            return self.update_two_streams()
         eng, buf, a = self.engine, self.buf, self.args
         for ep in range(a.epochs):
             eng.ppo_epoch_grads(self.net.flat, self.grads, state=buf["state"], actions=buf["actions"],

@@ -217,16 +217,6 @@ int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params, const flo
                             const uint8_t* avail, double clip, double ent_coef, int32_t t0, int32_t t1,
                             float* h_seq, float* grads_out, void* workspace, void* stream);
 
-/* -- K7 split per network (MLP actor): cmarl_actor_epoch_grads + cmarl_critic_epoch_grads + two cmarl_adam_step_net
- * produce exactly what cmarl_ppo_epoch_grads + cmarl_clip_adam_step produce, but the two networks' chains
- * (MME:530-551 vs MME:554-558) are independent until the logging, so a caller may run them on two streams: the
- * small reduce / Adam launches of one network then hide under the other's chain.  grads_out f32 [Pa + CMARL_N_STATS]:
- * unnormalised sums, stats [0] actor loss [2] entropy [3] kl [4] clip fraction [5] valid (b,t). */
-int cmarl_actor_epoch_grads(cmarl_ctx* ctx, const float* actor_params, const float* state, const float* obs,
-                            const int32_t* actions, const float* logp_old, const float* adv, const uint8_t* mask,
-                            const uint8_t* avail, double clip, double ent_coef, float* grads_out, void* workspace,
-                            void* stream);
-
 /* -- K7b: critic loss + gradients of one epoch alone (LSTM:621-626, 646-649; the critic is stepped once per
  * epoch while the actor is stepped once per chunk).  grads_out f32 [Pc + CMARL_N_STATS]: unnormalised sums,
  * stats [1] critic loss sum, [5] valid (b,t). */

@@ -555,23 +555,3 @@ def test_tiny_and_ragged_env_counts(cm, B, recurrent):
     final = torch.cat([actor.flat_params(), critic.flat_params()])
     dp = (tr.net.flat.cpu() - final).abs()
     assert (dp < 3e-6).float().mean() > 0.99 and dp.max() < 2e-4       # near-eps Adam gradients: see test_gpu_recurrent
-
-
-def test_two_stream_update_equals_single_stream(cm, monkeypatch):
-    """Actor and critic epochs on two streams (the single-GPU default) == the fused single-stream epoch entry:
-    bit-identical parameters, Adam moments and logged statistics after 3 iterations."""
-    from cleanmarl_b200.mappo import MAPPO, Args
-    outs = []
-    for two in ("1", "0"):
-        monkeypatch.setenv("CMARL_TWO_STREAMS", two)
-        tr = MAPPO(Args(batch_size=640, seed=8, clip_gradients=0.7 if two else -1), use_graph=False)
-        assert tr.two_streams == (two == "1")
-        for _ in range(3):
-            tr.iteration()
-        torch.cuda.synchronize()
-        outs.append((tr.net.flat.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone(), tr.epoch_stats.clone()))
-    for a, b in zip(*outs[:1] + outs[1:]):
-        pass
-    (p1, m1, v1, s1), (p0, m0, v0, s0) = outs
-    assert torch.equal(p1, p0) and torch.equal(m1, m0) and torch.equal(v1, v0)
-    assert (s1 - s0).abs().max() <= 1e-6 * s0.abs().max()
