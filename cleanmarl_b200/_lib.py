@@ -51,6 +51,11 @@ _SIGNATURES = {
     "cmarl_ppo_epoch_grads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
     "cmarl_clip_adam_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, C.c_double, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_double, _P, _P]),
+    # peer-memory gradient exchange
+    "cmarl_comm_bytes": (C.c_size_t, []),
+    "cmarl_comm_create": (C.c_int, [_P, _P]),
+    "cmarl_comm_attach": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "cmarl_comm_detach": (C.c_int, [_P]),
     # recurrent-actor path (mappo_lstm_multienvs.py)
     "cmarl_actor_act_recurrent": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cmarl_tbptt_chunk_grads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int32,

@@ -45,6 +45,27 @@ struct GruLayout {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// Peer-memory gradient exchange (multi-GPU, one process per GPU): every rank owns one cudaMalloc'ed, IPC-exported
+// block of CMARL_COMM_CHANNELS channels; peers map it (cudaIpcOpenMemHandle) and the Adam kernel reads the other
+// ranks' gradient sums straight over NVLink (comm.cu, exact.cu).
+// ------------------------------------------------------------------------------------------
+constexpr int CMARL_MAX_RANKS = 8;
+constexpr int CMARL_COMM_CHANNELS = 2;            // 0: combined / actor steps, 1: critic steps of the per-network path
+constexpr int CMARL_COMM_SLOT_FLOATS = 16384;     // >= P + CMARL_N_STATS
+struct CommChannel {
+    float slots[2][CMARL_COMM_SLOT_FLOATS];                 // this rank's gradient sums + statistics, parity = seq & 1
+    unsigned long long flags[CMARL_MAX_RANKS][16];          // flags[r][0]: written by rank r (own 128-B line): seq + 1 published
+    unsigned long long seq;                                 // local: exchanges completed on this channel
+    unsigned int ticket_pub;                                // local: CTAs that have copied their slice
+    unsigned int pad[29];
+};
+struct cmarl_comm {
+    int rank, world;                                        // world <= 1: no exchange
+    CommChannel* base[CMARL_MAX_RANKS];                     // base[r] = rank r's block mapped into this process
+    void* own;                                              // this rank's allocation (cudaFree at detach)
+};
+
 enum KernelId { K_RESET = 0, K_ENVSTEP, K_ROLLOUT, K_ACT, K_CRITIC, K_TD, K_NORM, K_PPO_ACTOR, K_PPO_CRITIC,
                 K_PPO_REDUCE, K_ADAM, K_TBPTT };
 static_assert(K_TBPTT + 1 == CMARL_NK, "kernel id table");
@@ -68,6 +89,7 @@ struct cmarl_ctx {
     int launches;
     int timing_on;
     int use_tc;         // 1: tcgen05 (3xTF32) chain kernels, 0: fp32 FFMA chain kernels
+    cmarl_comm comm;         // peer-memory gradient exchange (world <= 1: off)
     double weight_decay[2];  // actor, critic: decoupled weight decay of the Adam entries (AdamW); 0 = plain Adam
     uint64_t* episode_dev;   // optional device episode counter for the Philox draws (CUDA-graph replay)
     cmarl_timing* timing;

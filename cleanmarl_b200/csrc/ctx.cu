@@ -133,7 +133,10 @@ extern "C" const char* cmarl_kernel_name(int id) {
     return (id >= 0 && id < CMARL_NK) ? names[id] : "?";
 }
 
+extern "C" int cmarl_comm_detach(cmarl_ctx* ctx);
+
 extern "C" int cmarl_ctx_destroy(cmarl_ctx* ctx) {
+    cmarl_comm_detach(ctx);
     if (ctx && ctx->timing) {
         for (int k = 0; k < CMARL_NK; ++k)
             for (int i = 0; i < CMARL_TIMING_POOL; ++i)

@@ -181,7 +181,23 @@ struct AdamArgs {
     double wd[2];           // decoupled weight decay (torch.optim.AdamW: param.mul_(1 - lr * weight_decay)); 0 = Adam
     float extra_div;        // grads are divided by stats[5] * extra_div (T_chunk of a truncated-BPTT chunk, else 1)
     int raw_stats;          // 1: stats_out = the five sums undivided, this step's norm, the valid count (single-net mode)
+    CommChannel* ch[CMARL_MAX_RANKS];   // peer-memory exchange: channel of every rank (own included), rank order
+    int rank, world;        // world <= 1: `grads` already holds the global sums
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // ceil(P / 1024) CTAs of 1024 threads (a single CTA was issue-bound: ~3 600 instructions x 32 warps on one SM = 21 us).
 // Every CTA redundantly derives the 12 per-tensor sums of squares from ALL gradients (<= 12 coalesced loads per thread,
@@ -205,20 +221,58 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
     __shared__ double bc_sh[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.tensor_off[12];
-    const float* stats = a.grads + P;
     const int mine = blockIdx.x * ADAM_THREADS + tid;          // the parameter this thread updates
+    const bool xchg = a.world > 1;
+    int par = 0;
+    if (xchg) {
+        // ---- peer-memory all-reduce, fused: publish this rank's sums, flag the peers, wait for theirs --------------
+        __shared__ unsigned long long seq_sh;
+        CommChannel* me = a.ch[a.rank];
+        if (tid == 0) seq_sh = *reinterpret_cast<volatile unsigned long long*>(&me->seq);
+        __syncthreads();
+        const unsigned long long seq = seq_sh;
+        par = (int)(seq & 1ull);
+        if (mine < P) me->slots[par][mine] = a.grads[mine];
+        if (blockIdx.x == 0 && tid < CMARL_N_STATS) me->slots[par][P + tid] = a.grads[P + tid];
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned t = atomicAdd(&me->ticket_pub, 1u);
+            if (t == gridDim.x - 1) {            // every CTA has copied (and read seq): publish to the peers
+                me->ticket_pub = 0;
+                me->seq = seq + 1;
+                __threadfence_system();
+                for (int r = 0; r < a.world; ++r)
+                    if (r != a.rank) st_release_sys(&a.ch[r]->flags[a.rank][0], seq + 1);
+            }
+            for (int r = 0; r < a.world; ++r) {
+                if (r == a.rank) continue;
+                unsigned spins = 0;
+                while (ld_acquire_sys(&me->flags[r][0]) < seq + 1)
+                    if (++spins > (1u << 27)) __trap();      // a missing peer must surface as an error, not as a hang
+            }
+        }
+        __syncthreads();
+    }
+    // gradient sum i over the ranks in rank order (every rank computes the identical value); local when world <= 1
+    auto G = [&](int i) -> float {
+        if (!xchg) return a.grads[i];
+        float sum = 0.0f;
+        for (int r = 0; r < a.world; ++r) sum += ld_relaxed_sys(&a.ch[r]->slots[par][i]);
+        return sum;
+    };
     // every global load is issued up front (one L2 round trip instead of two around the norm reduction)
     float g[ADAM_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < ADAM_PER_THREAD; ++j) {
         const int i = tid + j * ADAM_THREADS;
-        g[j] = i < P ? a.grads[i] : 0.0f;
+        g[j] = i < P ? G(i) : 0.0f;
     }
-    const float g_mine = mine < P ? a.grads[mine] : 0.0f;
+    const float g_mine = mine < P ? G(mine) : 0.0f;
     const float pm = mine < P ? a.m[mine] : 0.0f;
     const float pv = mine < P ? a.v[mine] : 0.0f;
     const float pp = mine < P ? a.params[mine] : 0.0f;
-    const float n_valid = stats[5];
+    const float n_valid = G(P + 5);
     const float count = n_valid * a.extra_div;
     if (tid == ADAM_THREADS - 1) {      // a thread of the last warp: the first warps finish the reductions below
         // the step count is read by this ONE thread per CTA; the last CTA to have read it publishes the new value
@@ -307,17 +361,23 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
     }
     if (blockIdx.x == 0 && tid == 0) {
         if (a.stats_out && a.raw_stats) {
-            for (int k = 0; k < 5; ++k) a.stats_out[k] = stats[k];
+            for (int k = 0; k < 5; ++k) a.stats_out[k] = G(P + k);
             a.stats_out[5] = net_norm[0];
             a.stats_out[6] = n_valid;
             a.stats_out[7] = 0.0f;
         } else if (a.stats_out) {
-            for (int k = 0; k < 5; ++k) a.stats_out[k] = stats[k] / count;
+            for (int k = 0; k < 5; ++k) a.stats_out[k] = G(P + k) / count;
             a.stats_out[5] = net_norm[0];
             a.stats_out[6] = net_norm[1];
             a.stats_out[7] = count;
         }
     }
+}
+
+static void fill_comm(const cmarl_ctx* ctx, AdamArgs& a, int channel) {
+    a.rank = ctx->comm.rank;
+    a.world = ctx->comm.world;
+    for (int r = 0; r < CMARL_MAX_RANKS; ++r) a.ch[r] = (r < ctx->comm.world && ctx->comm.base[r]) ? ctx->comm.base[r] + channel : nullptr;
 }
 
 extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, float* exp_avg,
@@ -344,6 +404,7 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     a.lr[0] = lr_actor; a.lr[1] = lr_critic; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
     a.extra_div = 1.0f; a.raw_stats = 0;
     a.wd[0] = ctx->weight_decay[0]; a.wd[1] = ctx->weight_decay[1];
+    fill_comm(ctx, a, 0);
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
         clip_adam_kernel<<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
@@ -382,6 +443,7 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     a.lr[0] = lr; a.lr[1] = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
     a.extra_div = (float)extra_div; a.raw_stats = 1;
     a.wd[0] = a.wd[1] = ctx->weight_decay[net];
+    fill_comm(ctx, a, net);
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
         clip_adam_kernel<<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);

@@ -131,6 +131,19 @@ class Engine:
         _lib.check(self.lib.cmarl_ctx_set_weight_decay(self._h, float(actor_wd), float(critic_wd)),
                    "cmarl_ctx_set_weight_decay")
 
+    def comm_setup(self, rank: int, world: int, group=None):
+        """Peer-memory gradient exchange: allocate + export this rank's block, gather every rank's IPC handle through
+        ``torch.distributed`` and map the peers.  Afterwards the Adam entries exchange the gradients themselves."""
+        import torch.distributed as dist
+        handle = (C.c_uint8 * 64)()
+        _lib.check(self.lib.cmarl_comm_create(self._h, handle), "cmarl_comm_create")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+        _lib.check(self.lib.cmarl_comm_attach(self._h, rank, world, blob), "cmarl_comm_attach")
+        dist.barrier(group=group)
+        self.comm_world = world
+
     def set_episode_counter(self, counter):
         """``counter``: int64 device tensor [1] (or None) -- see cmarl_ctx_set_episode_counter."""
         ptr = None if counter is None else _ptr(counter, torch.int64, self.device, "episode counter")

@@ -282,9 +282,19 @@ class MAPPO:
         # path from the loop.  Needs the device episode counter; single-GPU only (the NCCL all-reduce stays eager).
         if use_graph is None:
             use_graph = os.environ.get("CMARL_GRAPH", "1") != "0"
-        # (multi-GPU stays eager: with the NCCL all-reduces captured into the graph the 2-GPU bench hung when it later
-        # mixed replays with eager collectives on the same communicator -- measured round 1, not pursued)
-        self.use_graph = bool(use_graph) and world_size == 1 and engine_factory is Engine
+        # Multi-GPU gradient exchange: "p2p" = inside the Adam kernel over peer memory (NVLink; keeps the iteration a
+        # fixed launch sequence, so the graph replay also works across GPUs), "nccl" = torch.distributed.all_reduce
+        # between the gradient kernels and Adam (eager launches: NCCL collectives captured into the graph hung when the
+        # bench mixed replays with eager collectives -- measured round 1).  The normalisation statistics (3 doubles,
+        # flags off by default) always use the process group.
+        self.comm = "none"
+        if world_size > 1:
+            self.comm = os.environ.get("CMARL_COMM", "p2p") if engine_factory is Engine else "nccl"
+            if self.comm == "p2p":
+                eng.comm_setup(rank, world_size, process_group)
+        norm_flags = args.normalize_reward or args.normalize_advantage or args.normalize_return
+        graph_ok = world_size == 1 or (self.comm == "p2p" and not norm_flags)
+        self.use_graph = bool(use_graph) and graph_ok and engine_factory is Engine
         self._graphs = {}
         self._episode_dev = None
         self.launches_per_iteration = None                       # kernel nodes of the captured graph (library launches)
@@ -308,6 +318,11 @@ class MAPPO:
 
     def _allreduce(self, t):
         if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.pg)
+
+    def _allreduce_grads(self, t):
+        """Unnormalised gradient sums (+ statistics): summed by the Adam kernel itself in p2p mode."""
+        if self.world > 1 and self.comm != "p2p":
             torch.distributed.all_reduce(t, group=self.pg)
 
     def _normalize(self, x, heads, mode):
@@ -343,11 +358,11 @@ class MAPPO:
             for ci, (t0, t1) in enumerate(self.chunks):
                 eng.tbptt_chunk_grads(p_a, self.grads_a, self.h_seq, t0, t1, state=buf["state"], actions=buf["actions"],
                                       logp_old=buf["logp"], adv=buf["adv"], clip=a.ppo_clip, ent_coef=a.entropy_coef)
-                self._allreduce(self.grads_a)
+                self._allreduce_grads(self.grads_a)
                 eng.adam_step_net(0, p_a, self.grads_a, m_a, v_a, step_dev=self.adam_step_a, lr=a.learning_rate_actor,
                                   max_norm=a.clip_gradients, extra_div=t1 - t0, stats_out=self.chunk_stats[ep, ci])
             eng.critic_epoch_grads(p_c, self.grads_c, state=buf["state"], returns=buf["returns"])   # IPPO: obs rebuilt from state
-            self._allreduce(self.grads_c)
+            self._allreduce_grads(self.grads_c)
             eng.adam_step_net(1, p_c, self.grads_c, m_c, v_c, step_dev=self.adam_step, lr=a.learning_rate_critic,
                               max_norm=a.clip_gradients, stats_out=self.critic_stats[ep])
             self.training_step += 1
@@ -371,7 +386,7 @@ class MAPPO:
             eng.ppo_epoch_grads(self.net.flat, self.grads, state=buf["state"], actions=buf["actions"],
                                 logp_old=buf["logp"], adv=buf["adv"], returns=buf["returns"], clip=a.ppo_clip,
                                 ent_coef=a.entropy_coef)
-            self._allreduce(self.grads)
+            self._allreduce_grads(self.grads)
             eng.clip_adam_step(self.net.flat, self.grads, self.exp_avg, self.exp_avg_sq, step_dev=self.adam_step,
                                lr_actor=a.learning_rate_actor, lr_critic=a.learning_rate_critic,
                                max_norm=a.clip_gradients, stats_out=self.epoch_stats[ep])

@@ -233,6 +233,26 @@ int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, const float*
                         float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr, double beta1, double beta2,
                         double eps, double max_norm, double extra_div, float* stats_out, void* stream);
 
+/* ======================================================================================================
+ * C1: gradient exchange across the GPUs of one box (one process per GPU), over peer memory.
+ * The reference has no multi-GPU path; SURVEY 8e shards the envs and sums the unnormalised gradient sums once per
+ * epoch.  Instead of a separate collective between K7 and K8, the Adam kernel itself exchanges the 38.7 KB over
+ * NVLink: every rank publishes its sums into a block the peers have mapped (CUDA IPC), flags the peers, waits for
+ * their flags and reads all ranks' sums in rank order -- so every rank forms bit-identical totals, and a multi-GPU
+ * iteration stays a fixed launch sequence (CUDA-graph replayable, no NCCL call in the loop).
+ *   cmarl_comm_create   allocates this rank's block (the only device allocation the library makes: IPC export needs a
+ *                       whole cudaMalloc block) and returns its 64-byte cudaIpcMemHandle_t
+ *   cmarl_comm_attach   handles = [world][64] bytes, every rank's handle in rank order (exchanged by the caller, e.g.
+ *                       torch.distributed.all_gather_object); from then on cmarl_clip_adam_step / cmarl_adam_step_net
+ *                       treat `grads` as this rank's LOCAL sums and step with the global ones
+ *   cmarl_comm_detach   unmaps / frees (also done by cmarl_ctx_destroy)
+ * All ranks must issue the same sequence of Adam calls.  A peer that never arrives traps the kernel after ~1 s of
+ * polling (the call then reports a launch failure) instead of hanging the GPU. */
+size_t cmarl_comm_bytes(void);
+int cmarl_comm_create(cmarl_ctx* ctx, uint8_t* handle_out /* HOST [64] */);
+int cmarl_comm_attach(cmarl_ctx* ctx, int32_t rank, int32_t world, const uint8_t* handles /* HOST [world][64] */);
+int cmarl_comm_detach(cmarl_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,7 @@ if __name__ == "__main__":
     torch.distributed.all_gather(gathered, tr.net.flat)
     if rank == 0:
         assert all(torch.equal(gathered[0], g) for g in gathered), "replicas diverged"
-        torch.save({"params": tr.net.flat.cpu(), "stats": tr.epoch_stats.cpu(), "step": tr.step}, out / "mgpu.pt")
+        torch.save({"params": tr.net.flat.cpu(), "stats": tr.epoch_stats.cpu(), "step": tr.step,
+                    "comm": tr.comm, "graph": tr.use_graph}, out / "mgpu.pt")
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()

@@ -420,10 +420,13 @@ def test_reward_normalisation(cm):
 
 
 # ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
+@pytest.mark.parametrize("comm", ["p2p", "nccl"])
 @pytest.mark.parametrize("flags", ["plain", "flags", "recurrent"])
-def test_two_gpus_nccl_equal_one(cm, tmp_path, flags):
-    """Envs sharded over 2 GPUs (one process per GPU, one NCCL all-reduce of 9 678 floats per epoch) == 1 GPU on all
-    envs: replicas bit-identical to each other, parameters within fp32 reassociation of the single-GPU run."""
+def test_two_gpus_nccl_equal_one(cm, tmp_path, flags, comm):
+    """Envs sharded over 2 GPUs (one process per GPU; gradient sums exchanged inside the Adam kernel over peer memory
+    (p2p, the default) or by one NCCL all-reduce of 9 678 floats per epoch) == 1 GPU on all envs: replicas bit-identical
+    to each other, parameters within fp32 reassociation of the single-GPU run."""
+    import os
     import socket
     import subprocess
     import sys
@@ -436,9 +439,10 @@ def test_two_gpus_nccl_equal_one(cm, tmp_path, flags):
     B = 1024
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(Path(__file__).resolve().parent / "mgpu_worker.py"), str(tmp_path), str(B), flags]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, CMARL_COMM=comm))
     assert r.returncode == 0, r.stderr[-2000:]
     two = torch.load(tmp_path / "mgpu.pt")
+    assert two["comm"] == comm
     kw = {"flags": {"normalize_advantage": True, "clip_gradients": 0.5}, "recurrent": {"recurrent": True}}.get(flags, {})
     one = mgpu_worker.run(B, 0, 1, 0, **kw)
     assert two["step"] == one.step
