@@ -1,6 +1,6 @@
 // Peer-memory gradient exchange: setup side (allocation, CUDA IPC export / import).  The exchange itself happens
-// inside clip_adam_kernel (exact.cu): publish own sums -> flag every peer -> wait for every peer's flag -> read all
-// ranks' sums over NVLink in rank order (identical result on every rank) -> norms, clip, Adam.
+// inside clip_adam_kernel (exact.cu): push own sums into every peer's receive buffer (posted NVLink stores) -> flag every
+// peer -> wait for every peer's flag -> sum all ranks' rows (local reads) in rank order (identical on every rank) -> Adam.
 // Replaces the `torch.distributed.all_reduce(grads)` between K7 and K8: at 38.7 KB the collective is
 // pure latency, and a kernel-internal exchange also keeps the whole multi-GPU iteration CUDA-graph replayable.
 #include "common.cuh"

@@ -48,16 +48,17 @@ struct GruLayout {
 // ------------------------------------------------------------------------------------------
 // Peer-memory gradient exchange (multi-GPU, one process per GPU): every rank owns one cudaMalloc'ed, IPC-exported
 // block of CMARL_COMM_CHANNELS channels; peers map it (cudaIpcOpenMemHandle) and the Adam kernel reads the other
-// ranks' gradient sums straight over NVLink (comm.cu, exact.cu).
+// ranks' gradient sums that the peers pushed into it over NVLink (comm.cu, exact.cu).
 // ------------------------------------------------------------------------------------------
 constexpr int CMARL_MAX_RANKS = 8;
 constexpr int CMARL_COMM_CHANNELS = 2;            // 0: combined / actor steps, 1: critic steps of the per-network path
 constexpr int CMARL_COMM_SLOT_FLOATS = 16384;     // >= P + CMARL_N_STATS
 struct CommChannel {
-    float slots[2][CMARL_COMM_SLOT_FLOATS];                 // this rank's gradient sums + statistics, parity = seq & 1
-    unsigned long long flags[CMARL_MAX_RANKS][16];          // flags[r][0]: written by rank r (own 128-B line): seq + 1 published
+    // RECEIVE buffers: slots[parity][r][i] is written by rank r as ONE 64-bit word {flag = call number + 1, fp32 value}
+    // (posted NVLink stores; data and flag arrive together, like NCCL's LL protocol) and polled locally
+    unsigned long long slots[2][CMARL_MAX_RANKS][CMARL_COMM_SLOT_FLOATS];
     unsigned long long seq;                                 // local: exchanges completed on this channel
-    unsigned int ticket_pub;                                // local: CTAs that have copied their slice
+    unsigned int ticket_pub;                                // local: CTAs that have read seq
     unsigned int pad[29];
 };
 struct cmarl_comm {

@@ -237,8 +237,8 @@ int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, const float*
  * C1: gradient exchange across the GPUs of one box (one process per GPU), over peer memory.
  * The reference has no multi-GPU path; SURVEY 8e shards the envs and sums the unnormalised gradient sums once per
  * epoch.  Instead of a separate collective between K7 and K8, the Adam kernel itself exchanges the 38.7 KB over
- * NVLink: every rank publishes its sums into a block the peers have mapped (CUDA IPC), flags the peers, waits for
- * their flags and reads all ranks' sums in rank order -- so every rank forms bit-identical totals, and a multi-GPU
+ * NVLink: every rank pushes its sums into the receive buffers of all peers (blocks mapped through CUDA IPC), flags
+ * the peers, waits for their flags and adds all ranks' rows in rank order -- so every rank forms bit-identical totals, and a multi-GPU
  * iteration stays a fixed launch sequence (CUDA-graph replayable, no NCCL call in the loop).
  *   cmarl_comm_create   allocates this rank's block (the only device allocation the library makes: IPC export needs a
  *                       whole cudaMalloc block) and returns its 64-byte cudaIpcMemHandle_t
