@@ -59,7 +59,7 @@ _SIGNATURES = {
     # recurrent-actor path (mappo_lstm_multienvs.py)
     "cmarl_actor_act_recurrent": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cmarl_tbptt_chunk_grads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int32,
-                                          C.c_int32, _P, _P, _P, _P]),
+                                          C.c_int32, _P, _P, _P, _P, _P]),
     "cmarl_critic_epoch_grads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cmarl_adam_step_net": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, C.c_double, C.c_double,
                                       C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),

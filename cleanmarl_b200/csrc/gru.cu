@@ -61,7 +61,10 @@ constexpr int oZ = oDH + H * LD;                 // [8][LD]      dlogits
 constexpr int PMAXG = 7232;                      // >= 7 205 parameters, multiple of 4
 constexpr int oDW = oZ + 8 * LD;                 // [PMAXG]      gradient accumulators, torch parameter order
 constexpr int oScr = oDW + PMAXG;                // [4][H][KIN]  dW1 sample-split partials
-constexpr int oRed = oScr + 4 * H * KIN;         // [64]
+constexpr int GLD = H + 1;                       // row stride of the dWih / dWhh accumulators: lanes of a warp add to
+                                                 // rows jg, jg+1, .. at the same column -> distinct banks (32 would be 8-way)
+constexpr int oDG = oScr + 4 * H * KIN;          // [2][3H][GLD] dWih, dWhh accumulators
+constexpr int oRed = oDG + 2 * G3 * GLD + 4;     // [64]
 constexpr int oEnd = oRed + 64;
 constexpr size_t SMEM_BYTES = (size_t)oEnd * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -77,6 +80,8 @@ struct ChunkArgs {
     int T, N, B;
     int t0, t1;
     float* h_seq;             // [T+1][N][H][B]
+    float* stash;             // [T][N][5H][B] or null: x1, r, z, n, ghn of every step (pass 1 writes, pass 2 reads instead
+                              // of recomputing the gates: 640 B per sample-step through L2 / HBM for 27 % fewer instructions)
     float* partials;          // [grid][P + 8]
     PolicyHeadArgs head;
 };
@@ -266,6 +271,33 @@ __device__ __forceinline__ void logits_of(const float* __restrict__ sm, const fl
     }
 }
 
+// this thread's 4 consecutive samples (s0..s0+3 of the tile at b0) of one global row of B floats <-> shared memory
+__device__ __forceinline__ void row4_store(float* __restrict__ grow, int b0, int s0, int valid, int B, float4 v) {
+    float* dst = grow + b0 + s0;
+    if (s0 + 3 < valid && ((B & 3) == 0)) {
+        *reinterpret_cast<float4*>(dst) = v;
+    } else {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (s0 + c < valid) dst[c] = e[c];
+    }
+}
+__device__ __forceinline__ float4 row4_load(const float* __restrict__ grow, int b0, int s0, int valid, int B) {
+    const float* src = grow + b0 + s0;
+    if (s0 + 3 < valid && ((B & 3) == 0)) return *reinterpret_cast<const float4*>(src);
+    float e[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (s0 + c < valid) e[c] = src[c];
+    return make_float4(e[0], e[1], e[2], e[3]);
+}
+
+// debug timeline (clock64) of CTA 0, first tile: slots 0-3 = forward step 1, slots 4-15 = backward step 1
+__device__ long long g_gru_tl[16];
+#define GTL(slot, cond) do { if (blockIdx.x == 0 && u == 0 && i == 1 && tid == 0 && (cond)) g_gru_tl[slot] = clock64(); } while (0)
+
+template <bool STASH>
 __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
     extern __shared__ __align__(128) float sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oBar);
@@ -278,6 +310,7 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
     load_weights(sm, a);
     for (int i = tid; i < 2 * KIN * LD; i += NT) sm[oX + i] = 0.0f;
     for (int i = tid; i < PMAXG; i += NT) sm[oDW + i] = 0.0f;
+    for (int i = tid; i < 2 * G3 * GLD; i += NT) sm[oDG + i] = 0.0f;
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -320,10 +353,13 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
             const int t = a.t0 + i;
             issue_x(sm + oX + ((it + 1) & 1) * KIN * LD, &bars[(it + 1) & 1], a, t_of(i + 1), g, b0);
             const float* X = sm + oX + (it & 1) * KIN * LD;
+            GTL(0, true);
             mbar_wait(&bars[it & 1], (it >> 1) & 1);
             fc1(sm, X, a.in_rows, g, X1);
             __syncthreads();
-            gru_cell<false>(sm, X1, Hp, Hc, nullptr);
+            GTL(1, true);
+            gru_cell<STASH>(sm, X1, Hp, Hc, G);
+            GTL(2, true);
             // this thread's 2 x 4 block of h_{t+1} -> h_seq[t+1] and becomes Hp of the next step
             __syncthreads();                       // every read of Hp is done
 #pragma unroll
@@ -331,17 +367,19 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
                 const int j = j0 + q;
                 const float4 h = *reinterpret_cast<const float4*>(Hc + j * LD + s0);
                 *reinterpret_cast<float4*>(Hp + j * LD + s0) = h;
-                float* dst = a.h_seq + (((size_t)(t + 1) * a.N + g) * H + j) * a.B + b0 + s0;
-                if (s0 + 3 < valid && ((a.B & 3) == 0)) {
-                    *reinterpret_cast<float4*>(dst) = h;
-                } else {
-                    const float hv[4] = {h.x, h.y, h.z, h.w};
+                row4_store(a.h_seq + (((size_t)(t + 1) * a.N + g) * H + j) * a.B, b0, s0, valid, a.B, h);
+                if (STASH) {   // the blocks this thread itself computed: x1 and the four gate rows of its two units
+                    float* slab = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B;
+                    float4 v[5];
+                    v[0] = *reinterpret_cast<const float4*>(X1 + j * LD + s0);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (s0 + c < valid) dst[c] = hv[c];
+                    for (int k = 0; k < 4; ++k) v[k + 1] = *reinterpret_cast<const float4*>(G + (k * H + j) * LD + s0);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) row4_store(slab + (size_t)(k * H + j) * a.B, b0, s0, valid, a.B, v[k]);
                 }
             }
             __syncthreads();
+            GTL(3, true);
         }
 
         // ------------------------------------------------------------------ pass 2: recompute + backward
@@ -349,34 +387,48 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
         // Hp currently holds h_{t1}; the first backward step needs h_{t1-1}: reload below like every other step
         for (int i = 0; i < nsteps; ++i, ++it) {
             const int t = a.t1 - 1 - i;
+            GTL(4, true);
             if (i + 1 < nsteps)
                 issue_x(sm + oX + ((it + 1) & 1) * KIN * LD, &bars[(it + 1) & 1], a, t_of(nsteps + i + 1), g, b0);
             // Hp = h_seq[t] (zeros for t == 0): this thread's own 2 x 4 block, written by this CTA in pass 1
             // (t > t0) or by an earlier launch (t == t0)
+            {
+                // all global loads first (independent, one L2 round trip), then the shared-memory stores: interleaved,
+                // the compiler must assume the generic-pointer stores alias the next load and serialises 14 round trips
+                float4 hp4[2], hc4[2], st4[2][5];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int j = j0 + q;
-                float4 h = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (t > 0) {
-                    const float* src = a.h_seq + (((size_t)t * a.N + g) * H + j) * a.B + b0 + s0;
-                    if (s0 + 3 < valid && ((a.B & 3) == 0)) {
-                        h = *reinterpret_cast<const float4*>(src);
-                    } else {
-                        float hv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                for (int q = 0; q < 2; ++q) {
+                    const int j = j0 + q;
+                    hp4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (t > 0) hp4[q] = row4_load(a.h_seq + (((size_t)t * a.N + g) * H + j) * a.B, b0, s0, valid, a.B);
+                    if (STASH) {   // what pass 1 left for this step: h_{t+1}, x1 and the gates (this thread's own blocks)
+                        hc4[q] = row4_load(a.h_seq + (((size_t)(t + 1) * a.N + g) * H + j) * a.B, b0, s0, valid, a.B);
+                        const float* slab = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (s0 + c < valid) hv[c] = src[c];
-                        h = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                        for (int k = 0; k < 5; ++k) st4[q][k] = row4_load(slab + (size_t)(k * H + j) * a.B, b0, s0, valid, a.B);
                     }
                 }
-                *reinterpret_cast<float4*>(Hp + j * LD + s0) = h;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int j = j0 + q;
+                    *reinterpret_cast<float4*>(Hp + j * LD + s0) = hp4[q];
+                    if (STASH) {
+                        *reinterpret_cast<float4*>(Hc + j * LD + s0) = hc4[q];
+                        *reinterpret_cast<float4*>(X1 + j * LD + s0) = st4[q][0];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(G + (k * H + j) * LD + s0) = st4[q][k + 1];
+                    }
+                }
             }
             const float* X = sm + oX + (it & 1) * KIN * LD;
             mbar_wait(&bars[it & 1], (it >> 1) & 1);
-            fc1(sm, X, a.in_rows, g, X1);
+            if (!STASH) {
+                fc1(sm, X, a.in_rows, g, X1);
+                __syncthreads();
+                gru_cell<true>(sm, X1, Hp, Hc, G);
+            }
             __syncthreads();
-            gru_cell<true>(sm, X1, Hp, Hc, G);
-            __syncthreads();
+            GTL(5, true);
 
             // head: logits of this step, loss terms / statistics / dlogits (LSTM:574-593, 628-638)
             {
@@ -390,6 +442,7 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
                 }
             }
             __syncthreads();
+            GTL(6, true);
 
             // (a) dW2 += dz relu(h')^T, db2 ; (b) gate gradients in place of the stash, dh carry
             if (tid < NA * H) {
@@ -460,33 +513,47 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
                 }
             }
             __syncthreads();
+            GTL(7, true);
 
-            // (c) dWih += [da_r, da_z, da_n] x1^T ; dWhh += [da_r, da_z, da_hn] h^T : 192 register patches of
-            //     4 rows x 8 columns over all 64 samples (fixed order); the last two warps sum the bias rows meanwhile
-            if (tid < 192) {
-                const int mi = tid / 96, p = tid - mi * 96;
-                const int jg = p >> 2, kg = p & 3;                      // rows jg + 24 a, columns kg + 4 b
-                const float* Xs = mi == 0 ? X1 : Hp;
-                float acc[4][8];
+            // (c) dWih += [da_r, da_z, da_n] x1^T ; dWhh += [da_r, da_z, da_hn] h^T and the bias-row sums.
+            //     Meanwhile the previous step's inputs are pulled into L2 (they are read at its start).
+            if (STASH && i + 1 < nsteps) {
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa)
+                for (int q = 0; q < 2; ++q) {
+                    const int j = j0 + q;
+                    const float* slab = a.stash + ((size_t)(t - 1) * a.N + g) * (5 * H) * a.B;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(slab + (size_t)(k * H + j) * a.B + b0 + s0));
+                    if (t > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h_seq + (((size_t)(t - 1) * a.N + g) * H + j) * a.B + b0 + s0));
+                }
+            }
+            if (tid < 128) {
+                // 128 register patches of 6 rows (the r, z, n rows of two units) x 8 columns over all 64 samples, fixed
+                // order.  The stage is bound by shared-memory operand traffic, not by threads: 3 x 8 patches on all 256
+                // threads, or the samples split over two thread halves, measured the same 7 700 - 8 900 cycles.
+                const int mi = tid >> 6, p = tid & 63;
+                const int jg = p >> 2, kg = p & 3;                      // units jg, jg + 16; columns kg + 4 b
+                const float* Xs = mi == 0 ? X1 : Hp;
+                float acc[6][8];
+#pragma unroll
+                for (int aa = 0; aa < 6; ++aa)
 #pragma unroll
                     for (int bb = 0; bb < 8; ++bb) acc[aa][bb] = 0.0f;
-                int grow[4];
+                // G rows: da_r (0..31), da_z (32..63), da_n (64..95, ih) / da_hn (96..127, hh)
+                const int gn = mi == 1 ? 3 * H : 2 * H;
+                int grow[6];
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa) {
-                    const int row = jg + 24 * aa;                        // 0..95 in (r, z, n) order
-                    grow[aa] = (mi == 1 && row >= 2 * H) ? row + H : row;   // hh uses da_hn (rows 96..127 of G) for the n gate
-                }
-#pragma unroll 2
+                for (int aa = 0; aa < 6; ++aa) grow[aa] = jg + 16 * (aa & 1) + ((aa >> 1) == 2 ? gn : (aa >> 1) * H);
+#pragma unroll 1
                 for (int q = 0; q < NQ; ++q) {
-                    float4 d[4], x[8];
+                    float4 d[6], x[8];
 #pragma unroll
-                    for (int aa = 0; aa < 4; ++aa) d[aa] = *reinterpret_cast<const float4*>(G + grow[aa] * LD + 4 * q);
+                    for (int aa = 0; aa < 6; ++aa) d[aa] = *reinterpret_cast<const float4*>(G + grow[aa] * LD + 4 * q);
 #pragma unroll
                     for (int bb = 0; bb < 8; ++bb) x[bb] = *reinterpret_cast<const float4*>(Xs + (kg + 4 * bb) * LD + 4 * q);
 #pragma unroll
-                    for (int aa = 0; aa < 4; ++aa)
+                    for (int aa = 0; aa < 6; ++aa)
 #pragma unroll
                         for (int bb = 0; bb < 8; ++bb) {
                             acc[aa][bb] = fmaf(d[aa].x, x[bb].x, acc[aa][bb]);
@@ -495,25 +562,26 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
                             acc[aa][bb] = fmaf(d[aa].w, x[bb].w, acc[aa][bb]);
                         }
                 }
-                float* dst = dW + (mi == 0 ? L.wih : L.whh);
+                float* dst = sm + oDG + mi * G3 * GLD;
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa)
+                for (int aa = 0; aa < 6; ++aa)
 #pragma unroll
-                    for (int bb = 0; bb < 8; ++bb) dst[(jg + 24 * aa) * H + kg + 4 * bb] += acc[aa][bb];
+                    for (int bb = 0; bb < 8; ++bb)
+                        dst[(jg + 16 * (aa & 1) + (aa >> 1) * H) * GLD + kg + 4 * bb] += acc[aa][bb];
             } else {
-                // 64 threads: dbih rows 0..95 (+ dbhh rows 0..63 are the same sums), dbhh rows 64..95 from da_hn
-                for (int row = tid - 192; row < 4 * H; row += 64) {
-                    float acc = 0.0f;
-                    for (int q = 0; q < NQ; ++q) {
-                        const float4 d = *reinterpret_cast<const float4*>(G + row * LD + 4 * q);
-                        acc += (d.x + d.y) + (d.z + d.w);
-                    }
-                    if (row < G3) dW[L.bih + row] += acc;
-                    if (row < 2 * H) dW[L.bhh + row] += acc;
-                    if (row >= G3) dW[L.bhh + row - H] += acc;
+                // dbih rows 0..95 (dbhh rows 0..63 are the same sums), dbhh rows 64..95 from da_hn
+                const int row = tid - 128;
+                float sum = 0.0f;
+                for (int q = 0; q < NQ; ++q) {
+                    const float4 d = *reinterpret_cast<const float4*>(G + row * LD + 4 * q);
+                    sum += (d.x + d.y) + (d.z + d.w);
                 }
+                if (row < G3) dW[L.bih + row] += sum;
+                if (row < 2 * H) dW[L.bhh + row] += sum;
+                if (row >= G3) dW[L.bhh + row - H] += sum;
             }
             __syncthreads();
+            GTL(8, true);
 
             // (d) dx1 = (Wih^T da_i) . relu'(x1) in place ; dh carry += Whh^T da_h
             {
@@ -561,6 +629,7 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
                 }
             }
             __syncthreads();
+            GTL(9, true);
 
             // (e) dW1 += dx1 x^T, db1 (+ folded id column): 48 patches of 4 x 4, samples split 4 ways, fixed-order combine
             {
@@ -614,12 +683,20 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
                 }
             }
             __syncthreads();
+            GTL(10, true);
         }
     }
 
     // per-CTA partial: gradients + statistics (fixed-order reduction follows in reduce_partials_kernel)
     float* out = a.partials + (size_t)blockIdx.x * (L.count + CMARL_N_STATS);
-    for (int i = tid; i < L.count; i += NT) out[i] = dW[i];
+    for (int i = tid; i < L.count; i += NT) {
+        float v = dW[i];
+        if (i >= L.wih && i < L.bih) {            // dWih | dWhh live in the padded accumulators
+            const int k = i - L.wih, mi = k / (G3 * H), rc = k - mi * (G3 * H);
+            v = sm[oDG + mi * G3 * GLD + (rc / H) * GLD + (rc % H)];
+        }
+        out[i] = v;
+    }
     float* red = sm + oRed;
 #pragma unroll
     for (int k = 0; k < PolicyHead::NSTAT; ++k) {
@@ -738,18 +815,24 @@ __global__ void __launch_bounds__(128) actor_act_gru_kernel(ActGruArgs a) {
 
 }  // namespace gru
 
+extern "C" int cmarl_debug_gru_timeline(long long* out_host16) {
+    return (int)cudaMemcpyFromSymbol(out_host16, gru::g_gru_tl, sizeof(long long) * 16);
+}
+
 int cmarl_gru_setup(cmarl_ctx* ctx) {
     (void)ctx;
-    return cmarl_check_cuda(cudaFuncSetAttribute(gru::tbptt_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)gru::SMEM_BYTES),
-                            "cudaFuncSetAttribute(tbptt_chunk_kernel)");
+    int e = cmarl_check_cuda(cudaFuncSetAttribute(gru::tbptt_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)gru::SMEM_BYTES), "cudaFuncSetAttribute(tbptt_chunk_kernel)");
+    if (e) return e;
+    return cmarl_check_cuda(cudaFuncSetAttribute(gru::tbptt_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)gru::SMEM_BYTES), "cudaFuncSetAttribute(tbptt_chunk_kernel)");
 }
 
 extern "C" int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params, const float* state, const float* obs,
                                        const int32_t* actions, const float* logp_old, const float* adv,
                                        const uint8_t* mask, const uint8_t* avail, double clip, double ent_coef,
-                                       int32_t t0, int32_t t1, float* h_seq, float* grads_out, void* workspace,
-                                       void* stream) {
+                                       int32_t t0, int32_t t1, float* h_seq, float* stash, float* grads_out,
+                                       void* workspace, void* stream) {
     CMARL_ARG(ctx && actor_params && actions && logp_old && adv && h_seq && grads_out && workspace, "null argument");
     CMARL_ARG(ctx->cfg.actor_recurrent, "context was not created with actor_recurrent = 1");
     CMARL_ARG(state || obs, "state or obs required");
@@ -767,6 +850,7 @@ extern "C" int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params
         a.stride_t = (size_t)c.state_dim * c.n_envs; a.stride_g = (size_t)CMARL_RAW_OBS * c.n_envs;
     }
     a.h_seq = h_seq;
+    a.stash = stash;
     a.partials = reinterpret_cast<float*>(workspace);
     a.head.actions = actions; a.head.logp_old = logp_old; a.head.adv = adv; a.head.mask = mask; a.head.avail = avail;
     a.head.V = ctx->n_heads; a.head.A = c.n_actions;
@@ -775,7 +859,8 @@ extern "C" int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params
     const int grid = units < ctx->sm_count ? units : ctx->sm_count;
     {
         KernelTimer kt(ctx, K_TBPTT, st);
-        gru::tbptt_chunk_kernel<<<grid, gru::NT, gru::SMEM_BYTES, st>>>(a);
+        if (stash) gru::tbptt_chunk_kernel<true><<<grid, gru::NT, gru::SMEM_BYTES, st>>>(a);
+        else gru::tbptt_chunk_kernel<false><<<grid, gru::NT, gru::SMEM_BYTES, st>>>(a);
     }
     int e = cmarl_check_cuda(cudaGetLastError(), "tbptt_chunk_kernel");
     if (e) return e;

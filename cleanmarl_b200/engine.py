@@ -231,13 +231,19 @@ class Engine:
             _ptr(actions, torch.int32, self.device, "actions"), self._f(logp, "logp"), self._f(logits, "logits"),
             self._f(h_out, "h_out"), self._stream()), "cmarl_actor_act_recurrent")
 
+    def alloc_gate_stash(self):
+        """f32 [T][N][5H][B]: forward-pass gate activations for the backward pass (optional, see cmarl_tbptt_chunk_grads)."""
+        s = self.shapes
+        return torch.empty(s.n_steps, s.n_agents, 5 * s.actor_hidden, s.n_envs, dtype=torch.float32, device=self.device)
+
     def tbptt_chunk_grads(self, actor_params, grads, h_seq, t0, t1, *, state=None, obs=None, actions, logp_old, adv,
-                          mask=None, avail=None, clip=0.2, ent_coef=0.001):
+                          mask=None, avail=None, clip=0.2, ent_coef=0.001, stash=None):
         _lib.check(self.lib.cmarl_tbptt_chunk_grads(
             self._h, self._f(actor_params, "actor_params"), self._f(state, "state"), self._f(obs, "obs"),
             _ptr(actions, torch.int32, self.device, "actions"), self._f(logp_old, "logp_old"), self._f(adv, "adv"),
             _ptr(mask, torch.uint8, self.device, "mask"), _ptr(avail, torch.uint8, self.device, "avail"),
-            float(clip), float(ent_coef), int(t0), int(t1), self._f(h_seq, "h_seq"), self._f(grads, "grads"),
+            float(clip), float(ent_coef), int(t0), int(t1), self._f(h_seq, "h_seq"), self._f(stash, "stash"),
+            self._f(grads, "grads"),
             C.c_void_p(self.workspace.data_ptr()), self._stream()), "cmarl_tbptt_chunk_grads")
 
     def critic_epoch_grads(self, critic_params, grads, *, state=None, obs=None, returns, mask=None):

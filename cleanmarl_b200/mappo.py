@@ -266,6 +266,9 @@ class MAPPO:
         if self.recurrent:
             self.chunks = tbptt_chunks(self.T, args.tbptt)
             self.h_seq = eng.alloc_h_seq()
+            # forward-pass gate activations for the backward pass (48 KB per env): skipped with CMARL_GATE_STASH=0
+            self.stash = (eng.alloc_gate_stash() if hasattr(eng, "alloc_gate_stash")
+                          and os.environ.get("CMARL_GATE_STASH", "1") != "0" else None)
             self.grads_a = eng.empty(eng.n_actor + 8)
             self.grads_c = eng.empty(eng.n_critic + 8)
             self.adam_step_a = torch.zeros(1, dtype=torch.int32, device=eng.device)
@@ -357,7 +360,8 @@ class MAPPO:
         for ep in range(a.epochs):
             for ci, (t0, t1) in enumerate(self.chunks):
                 eng.tbptt_chunk_grads(p_a, self.grads_a, self.h_seq, t0, t1, state=buf["state"], actions=buf["actions"],
-                                      logp_old=buf["logp"], adv=buf["adv"], clip=a.ppo_clip, ent_coef=a.entropy_coef)
+                                      logp_old=buf["logp"], adv=buf["adv"], clip=a.ppo_clip, ent_coef=a.entropy_coef,
+                                      stash=self.stash)
                 self._allreduce_grads(self.grads_a)
                 eng.adam_step_net(0, p_a, self.grads_a, m_a, v_a, step_dev=self.adam_step_a, lr=a.learning_rate_actor,
                                   max_norm=a.clip_gradients, extra_div=t1 - t0, stats_out=self.chunk_stats[ep, ci])

@@ -211,11 +211,14 @@ int cmarl_actor_act_recurrent(cmarl_ctx* ctx, const float* actor_params, const f
  * The reference's division by (n_valid_chunk * T_chunk) (LSTM:605-607) happens in cmarl_adam_step_net after the
  * caller's all-reduce.  h_seq f32 [T+1][N][H][B] is caller-owned scratch that carries the hidden state from chunk
  * to chunk inside one epoch: t0 == 0 starts from zeros (LSTM:558, the kernel ignores slice 0); on return slices
- * t0+1..t1 hold the hidden states after each step (computed with the weights of THIS call, LSTM:620 detach). */
+ * t0+1..t1 hold the hidden states after each step (computed with the weights of THIS call, LSTM:620 detach).
+ * stash: optional caller-owned scratch f32 [T][N][5H][B] (x1 and the gates r, z, n, W_hn h + b_hn of every step): with it
+ * the backward pass reads the forward pass's gate activations back instead of recomputing them (faster, 640 B per
+ * (agent, env, step) of extra traffic); NULL selects the recompute variant.  Both give the same results bit for bit. */
 int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params, const float* state, const float* obs,
                             const int32_t* actions, const float* logp_old, const float* adv, const uint8_t* mask,
                             const uint8_t* avail, double clip, double ent_coef, int32_t t0, int32_t t1,
-                            float* h_seq, float* grads_out, void* workspace, void* stream);
+                            float* h_seq, float* stash, float* grads_out, void* workspace, void* stream);
 
 /* -- K7b: critic loss + gradients of one epoch alone (LSTM:621-626, 646-649; the critic is stepped once per
  * epoch while the actor is stepped once per chunk).  grads_out f32 [Pc + CMARL_N_STATS]: unnormalised sums,

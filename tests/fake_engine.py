@@ -202,7 +202,7 @@ class OracleEngine:
         return torch.zeros(s.n_steps + 1, s.n_agents, s.actor_hidden, s.n_envs)
 
     def tbptt_chunk_grads(self, actor_params, grads, h_seq, t0, t1, *, state=None, obs=None, actions, logp_old, adv,
-                          mask=None, avail=None, clip=0.2, ent_coef=0.001):
+                          mask=None, avail=None, clip=0.2, ent_coef=0.001, stash=None):
         """Unnormalised sums of one truncated-BPTT chunk (autograd through the oracle's GRU actor), hidden state
         carried through ``h_seq`` exactly like the device kernel."""
         from torch.distributions.categorical import Categorical

@@ -120,7 +120,7 @@ def test_recurrent_rollout_matches_oracle(cm):
 
 # ----------------------------------------------------------------------------------------- K7a / K7b / K8 (TBPTT)
 def _device_update(eng, E, actor, critic, batch, adv, ret, *, epochs, tbptt, clip_gradients, lr_a, lr_c, use_mask=True,
-                   use_avail=True, use_obs=False, weight_decay=0.0):
+                   use_avail=True, use_obs=False, weight_decay=0.0, stash=True):
     from cleanmarl_b200.mappo import tbptt_chunks
     dev = eng.device
     eng.set_weight_decay(weight_decay, weight_decay)
@@ -130,6 +130,7 @@ def _device_update(eng, E, actor, critic, batch, adv, ret, *, epochs, tbptt, cli
     m, v = torch.zeros_like(flat), torch.zeros_like(flat)
     ga, gc = eng.empty(na + 8), eng.empty(eng.n_critic + 8)
     h_seq = eng.alloc_h_seq()
+    gate_stash = eng.alloc_gate_stash() if stash else None
     step_a = torch.zeros(1, dtype=torch.int32, device=dev)
     step_c = torch.zeros(1, dtype=torch.int32, device=dev)
     adv_d = E.heads_to_device(adv, eng.n_heads, dev)
@@ -142,7 +143,7 @@ def _device_update(eng, E, actor, critic, batch, adv, ret, *, epochs, tbptt, cli
             eng.tbptt_chunk_grads(flat[:na], ga, h_seq, t0, t1, state=d["state"], obs=d["obs"] if use_obs else None,
                                   actions=d["actions"], logp_old=d["logp"], adv=adv_d,
                                   mask=d["mask"] if use_mask else None, avail=d["avail"] if use_avail else None,
-                                  clip=0.2, ent_coef=0.001)
+                                  clip=0.2, ent_coef=0.001, stash=gate_stash)
             st = eng.empty(8)
             cg.append(ga.cpu().clone())
             eng.adam_step_net(0, flat[:na], ga, m[:na], v[:na], step_dev=step_a, lr=lr_a, max_norm=clip_gradients,
@@ -221,6 +222,11 @@ def test_tbptt_chunk_gradients_vs_oracle(cm, B, use_obs, tbptt):
     eng = make_engine(cm, B)
     out = _device_update(eng, E, actor, critic, batch, adv, ret, epochs=1, tbptt=tbptt, clip_gradients=-1.0,
                          lr_a=8e-4, lr_c=8e-4, use_obs=use_obs)
+    # the recompute variant (no gate stash) gives the same gradients and parameters bit for bit
+    out2 = _device_update(eng, E, actor, critic, batch, adv, ret, epochs=1, tbptt=tbptt, clip_gradients=-1.0,
+                          lr_a=8e-4, lr_c=8e-4, use_obs=use_obs, stash=False)
+    assert torch.equal(out["params"], out2["params"])
+    assert all(torch.equal(x, y) for x, y in zip(out["chunk_grads"][0], out2["chunk_grads"][0]))
     aopt, copt = om.make_optimizers(actor, critic)
     st = ol.ppo_update_tbptt(actor, critic, aopt, copt, batch, adv, ret, epochs=1, clip=0.2, ent_coef=0.001,
                              tbptt=tbptt, record_grads=True)
