@@ -47,8 +47,8 @@ constexpr int oW1T = 4;                          // [KIN][H]     fc1, in-major
 constexpr int oB1 = oW1T + KIN * H;              // [4][H]       b1 (+ folded id column) per agent
 constexpr int oWgT = oB1 + 4 * H;                // [2H][H][4]   k-major gate weights: k < H from x1 (Wir, Wiz, Win, 0), k >= H from h (Whr, Whz, Whn, 0)
 constexpr int oBg = oWgT + 2 * H * H * 4;        // [H][4]       bir+bhr, biz+bhz, bin, bhn
-constexpr int oWih = oBg + H * 4;                // [3H][H]      native (backward: dx1 = Wih^T da)
-constexpr int oWhh = oWih + G3 * H;              // [3H][H]
+constexpr int oWih = oBg + H * 4;                // [3H][H/2][4] backward weights, packed per (gate row, output pair k0 = 2 og):
+constexpr int oWhh = oWih + G3 * H;              //              (Wih[row][k0], Wih[row][k0+1], Whh[row][k0], Whh[row][k0+1]): one LDS.128
 constexpr int oW2T = oWhh + G3 * H;              // [H][8]
 constexpr int oB2 = oW2T + H * 8;                // [8]
 constexpr int oX = oB2 + 8;                      // [2][KIN][LD] input rows, double buffered
@@ -122,8 +122,9 @@ __device__ void load_weights(float* sm, const ChunkArgs& a) {
         *reinterpret_cast<float4*>(sm + oBg + j * 4) = b;
     }
     for (int i = threadIdx.x; i < G3 * H; i += NT) {
-        sm[oWih + i] = P[L.wih + i];
-        sm[oWhh + i] = P[L.whh + i];
+        const int row = i / H, k = i - row * H;
+        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + (k & 1)] = P[L.wih + i];
+        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + 2 + (k & 1)] = P[L.whh + i];
     }
     for (int i = threadIdx.x; i < H * 8; i += NT) {
         const int j = i / 8, c = i - j * 8;
@@ -593,8 +594,8 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
 #pragma unroll 4
                 for (int row = 0; row < 2 * H; ++row) {              // r and z gates feed both
                     const float4 d = *reinterpret_cast<const float4*>(G + row * LD + s0);
-                    const float2 wi = *reinterpret_cast<const float2*>(sm + oWih + row * H + j0);
-                    const float2 wh = *reinterpret_cast<const float2*>(sm + oWhh + row * H + j0);
+                    const float4 wv = *reinterpret_cast<const float4*>(sm + oWih + (row * (H / 2) + og) * 4);
+                    const float2 wi = make_float2(wv.x, wv.y), wh = make_float2(wv.z, wv.w);
                     const float ds[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -606,8 +607,8 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
                 for (int row = 2 * H; row < G3; ++row) {
                     const float4 di = *reinterpret_cast<const float4*>(G + row * LD + s0);         // da_n
                     const float4 dh = *reinterpret_cast<const float4*>(G + (row + H) * LD + s0);   // da_hn
-                    const float2 wi = *reinterpret_cast<const float2*>(sm + oWih + row * H + j0);
-                    const float2 wh = *reinterpret_cast<const float2*>(sm + oWhh + row * H + j0);
+                    const float4 wv = *reinterpret_cast<const float4*>(sm + oWih + (row * (H / 2) + og) * 4);
+                    const float2 wi = make_float2(wv.x, wv.y), wh = make_float2(wv.z, wv.w);
                     const float dis[4] = {di.x, di.y, di.z, di.w}, dhs[4] = {dh.x, dh.y, dh.z, dh.w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
