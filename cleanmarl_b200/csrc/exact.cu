@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
                 unsigned long long w = ld_probe_sys(row + (size_t)r * CMARL_COMM_SLOT_FLOATS);
                 unsigned spins = 0;
                 while ((unsigned int)(w >> 32) != tag) {
-                    if (++spins > (1u << 25)) __trap();          // a missing peer must surface as an error, not as a hang
+                    if (++spins > (1u << 28)) __trap();          // ~1 min of polling: a missing peer must surface as an error, not as a hang
                     w = ld_relaxed_sys(row + (size_t)r * CMARL_COMM_SLOT_FLOATS);
                 }
                 v[r] = __uint_as_float((unsigned int)w);

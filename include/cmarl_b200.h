@@ -249,8 +249,8 @@ int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, const float*
  *                       torch.distributed.all_gather_object); from then on cmarl_clip_adam_step / cmarl_adam_step_net
  *                       treat `grads` as this rank's LOCAL sums and step with the global ones
  *   cmarl_comm_detach   unmaps / frees (also done by cmarl_ctx_destroy)
- * All ranks must issue the same sequence of Adam calls.  A peer that never arrives traps the kernel after ~1 s of
- * polling (the call then reports a launch failure) instead of hanging the GPU. */
+ * All ranks must issue the same sequence of Adam calls.  A peer that never arrives traps the kernel after about a minute
+ * of polling (the call then reports a launch failure) instead of hanging the GPU. */
 size_t cmarl_comm_bytes(void);
 int cmarl_comm_create(cmarl_ctx* ctx, uint8_t* handle_out /* HOST [64] */);
 int cmarl_comm_attach(cmarl_ctx* ctx, int32_t rank, int32_t world, const uint8_t* handles /* HOST [world][64] */);
