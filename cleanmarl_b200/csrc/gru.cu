@@ -9,10 +9,11 @@
 //   logits = W2 relu(h') + b2
 //
 // tbptt_chunk_kernel: one CTA owns a tile of M = 64 consecutive envs of one agent and walks the chunk twice:
-//   pass 1 (t = t0 .. t1-1)  h_{t+1} from (x_t, h_t); only the hidden state is kept (h_seq[t+1], global, L2-resident)
-//   pass 2 (t = t1-1 .. t0)  recomputes the gates of step t from (x_t, h_seq[t]) -- 0.7x the cost of a forward, no
-//                            activation stash: the per-step stash would be 800 B per sample, 10x the chunk input --
-//                            then the head (loss terms, statistics, dlogits) and the backward step:
+//   pass 1 (t = t0 .. t1-1)  h_{t+1} from (x_t, h_t); the hidden state goes to h_seq[t+1] (global, L2-resident) and,
+//                            with a gate stash, x1 / r / z / n / ghn of the step to the stash (640 B per sample-step)
+//   pass 2 (t = t1-1 .. t0)  gets the gates of step t back -- from the stash, or (no stash) by recomputing them from
+//                            (x_t, h_seq[t]), 0.7x the cost of a forward -- then the head (loss terms, statistics,
+//                            dlogits) and the backward step:
 //     dh   = dh_carry + (W2^T dz) . relu'(h')            dW2 += dz relu(h')^T
 //     dn   = dh (1-z)   dz_g = dh (h - n)   dh_carry = dh z
 //     da_n = dn (1-n^2) da_hn = da_n r      da_r = da_n ghn r(1-r)     da_z = dz_g z(1-z)
