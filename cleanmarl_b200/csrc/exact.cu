@@ -215,14 +215,15 @@ __device__ __forceinline__ int tensor_of(const AdamArgs& a, int i) {
     return k;
 }
 
-__global__ void __launch_bounds__(ADAM_THREADS) clip_adam_kernel(AdamArgs a) {
+template <bool XCHG>
+__global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) {
     __shared__ float wsum[ADAM_THREADS / 32][12];
     __shared__ float tnorm[12];
     __shared__ double bc_sh[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.tensor_off[12];
     const int mine = blockIdx.x * ADAM_THREADS + tid;          // the parameter this thread updates
-    const bool xchg = a.world > 1;
+    constexpr bool xchg = XCHG;       // peer-memory exchange compiled in only for multi-GPU launches
     int par = 0;
     unsigned int tag = 0;
     if (xchg) {
@@ -421,7 +422,8 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     fill_comm(ctx, a, 0);
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
-        clip_adam_kernel<<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
+        if (a.world > 1) clip_adam_kernel<true><<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
+        else clip_adam_kernel<false><<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
     }
     return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
 }
@@ -460,7 +462,8 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     fill_comm(ctx, a, net);
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
-        clip_adam_kernel<<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
+        if (a.world > 1) clip_adam_kernel<true><<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
+        else clip_adam_kernel<false><<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
     }
     return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
 }

@@ -23,6 +23,8 @@
 // All activations are feature-major in shared memory ([row][sample], LD = 68): thread tiles of 4 samples x 2 units
 // read them as LDS.128 and the weights as warp-broadcast LDS.64/128.  Input rows arrive by cp.async.bulk (TMA
 // engine) + mbarrier, double buffered across steps; h_seq[t] of the next backward step is prefetched into registers.
+#include <stdlib.h>
+
 #include "chain.cuh"
 #include "heads.cuh"
 
@@ -36,7 +38,7 @@ using namespace chain;
 constexpr int H = 32;            // hidden units (fc1 out = GRU in = GRU hidden)
 constexpr int G3 = 3 * H;
 constexpr int M = 64;            // samples (envs) per tile
-constexpr int NT = 256;          // threads per CTA
+constexpr int NTMAX = 512;       // threads per CTA: 512 / NU (NU = hidden units per thread in the 4-sample x NU-unit tiles)
 constexpr int LD = M + 4;        // row stride in floats (16-B aligned rows, conflict-free LDS.128)
 constexpr int NA = 5;            // actions
 constexpr int KIN = 24;          // padded input rows (18 raw / 21 with explicit ids)
@@ -90,6 +92,7 @@ struct ChunkArgs {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ void load_weights(float* sm, const ChunkArgs& a) {
+    const int NT = blockDim.x;
     const GruLayout& L = a.L;
     const float* P = a.params;
     const int O = L.in;
@@ -139,6 +142,7 @@ __device__ __forceinline__ bool tile_bulk(const ChunkArgs& a, int b0) {
     return (b0 + M <= a.B) && ((a.B & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
 }
 __device__ void issue_x(float* xbuf, uint64_t* bar, const ChunkArgs& a, int t, int g, int b0) {
+    const int NT = blockDim.x;
     const float* base = a.x + (size_t)t * a.stride_t + (size_t)g * a.stride_g + b0;
     if (tile_bulk(a, b0)) {
         if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(a.in_rows * M * 4));
@@ -156,14 +160,15 @@ __device__ void issue_x(float* xbuf, uint64_t* bar, const ChunkArgs& a, int t, i
     }
 }
 
-// x1 = relu(W1 x + b1[g]) : thread (sg, og) = 4 samples x 2 units
+// x1 = relu(W1 x + b1[g]) : thread (sg, og) = 4 samples x NU units
+template <int NU>
 __device__ __forceinline__ void fc1(const float* __restrict__ sm, const float* __restrict__ X, int in_rows, int g,
                                     float* __restrict__ X1) {
     const int sg = threadIdx.x & 15, og = threadIdx.x >> 4;
-    const int s0 = 4 * sg, j0 = 2 * og;
-    float acc[2][4];
+    const int s0 = 4 * sg, j0 = NU * og;
+    float acc[NU][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NU; ++i) {
         const float b = sm[oB1 + g * H + j0 + i];
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[i][c] = b;
@@ -171,14 +176,15 @@ __device__ __forceinline__ void fc1(const float* __restrict__ sm, const float* _
 #pragma unroll 6
     for (int k = 0; k < in_rows; ++k) {
         const float4 x = *reinterpret_cast<const float4*>(X + k * LD + s0);
-        const float2 w = *reinterpret_cast<const float2*>(sm + oW1T + k * H + j0);
-        acc[0][0] = fmaf(w.x, x.x, acc[0][0]); acc[0][1] = fmaf(w.x, x.y, acc[0][1]);
-        acc[0][2] = fmaf(w.x, x.z, acc[0][2]); acc[0][3] = fmaf(w.x, x.w, acc[0][3]);
-        acc[1][0] = fmaf(w.y, x.x, acc[1][0]); acc[1][1] = fmaf(w.y, x.y, acc[1][1]);
-        acc[1][2] = fmaf(w.y, x.z, acc[1][2]); acc[1][3] = fmaf(w.y, x.w, acc[1][3]);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            const float w = sm[oW1T + k * H + j0 + i];
+            acc[i][0] = fmaf(w, x.x, acc[i][0]); acc[i][1] = fmaf(w, x.y, acc[i][1]);
+            acc[i][2] = fmaf(w, x.z, acc[i][2]); acc[i][3] = fmaf(w, x.w, acc[i][3]);
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NU; ++i) {
         float4 o;
         o.x = fmaxf(acc[i][0], 0.0f); o.y = fmaxf(acc[i][1], 0.0f); o.z = fmaxf(acc[i][2], 0.0f); o.w = fmaxf(acc[i][3], 0.0f);
         *reinterpret_cast<float4*>(X1 + (j0 + i) * LD + s0) = o;
@@ -186,14 +192,14 @@ __device__ __forceinline__ void fc1(const float* __restrict__ sm, const float* _
 }
 
 // GRUCell: (X1, Hp) -> Hc ; STASH also keeps r, z, n, ghn for the backward step
-template <bool STASH>
+template <int NU, bool STASH>
 __device__ __forceinline__ void gru_cell(const float* __restrict__ sm, const float* __restrict__ X1,
                                          const float* __restrict__ Hp, float* __restrict__ Hc, float* __restrict__ G) {
     const int sg = threadIdx.x & 15, og = threadIdx.x >> 4;
-    const int s0 = 4 * sg, j0 = 2 * og;
-    float ar[2][4], az[2][4], ai[2][4], ah[2][4];
+    const int s0 = 4 * sg, j0 = NU * og;
+    float ar[NU][4], az[NU][4], ai[NU][4], ah[NU][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NU; ++i) {
         const float4 b = *reinterpret_cast<const float4*>(sm + oBg + (j0 + i) * 4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) { ar[i][c] = b.x; az[i][c] = b.y; ai[i][c] = b.z; ah[i][c] = b.w; }
@@ -203,7 +209,7 @@ __device__ __forceinline__ void gru_cell(const float* __restrict__ sm, const flo
         const float4 x = *reinterpret_cast<const float4*>(X1 + k * LD + s0);
         const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NU; ++i) {
             const float4 w = *reinterpret_cast<const float4*>(sm + oWgT + ((size_t)k * H + j0 + i) * 4);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -218,7 +224,7 @@ __device__ __forceinline__ void gru_cell(const float* __restrict__ sm, const flo
         const float4 x = *reinterpret_cast<const float4*>(Hp + k * LD + s0);
         const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NU; ++i) {
             const float4 w = *reinterpret_cast<const float4*>(sm + oWgT + ((size_t)(H + k) * H + j0 + i) * 4);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -229,7 +235,7 @@ __device__ __forceinline__ void gru_cell(const float* __restrict__ sm, const flo
         }
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NU; ++i) {
         const int j = j0 + i;
         const float4 hp4 = *reinterpret_cast<const float4*>(Hp + j * LD + s0);
         const float hp[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
@@ -299,8 +305,9 @@ __device__ __forceinline__ float4 row4_load(const float* __restrict__ grow, int 
 __device__ long long g_gru_tl[16];
 #define GTL(slot, cond) do { if (blockIdx.x == 0 && u == 0 && i == 1 && tid == 0 && (cond)) g_gru_tl[slot] = clock64(); } while (0)
 
-template <bool STASH>
-__global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
+template <int NU, bool STASH>
+__global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a) {
+    constexpr int NT = NTMAX / NU;
     extern __shared__ __align__(128) float sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oBar);
     const int tid = threadIdx.x;
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
     for (int k = 0; k < PolicyHead::NSTAT; ++k) st[k] = 0.0f;
 
     const int sg = tid & 15, og = tid >> 4;
-    const int s0 = 4 * sg, j0 = 2 * og;
+    const int s0 = 4 * sg, j0 = NU * og;
     float* Hp = sm + oHp;
     float* X1 = sm + oX1;
     float* G = sm + oG;
@@ -357,15 +364,15 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
             const float* X = sm + oX + (it & 1) * KIN * LD;
             GTL(0, true);
             mbar_wait(&bars[it & 1], (it >> 1) & 1);
-            fc1(sm, X, a.in_rows, g, X1);
+            fc1<NU>(sm, X, a.in_rows, g, X1);
             __syncthreads();
             GTL(1, true);
-            gru_cell<STASH>(sm, X1, Hp, Hc, G);
+            gru_cell<NU, STASH>(sm, X1, Hp, Hc, G);
             GTL(2, true);
             // this thread's 2 x 4 block of h_{t+1} -> h_seq[t+1] and becomes Hp of the next step
             __syncthreads();                       // every read of Hp is done
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < NU; ++q) {
                 const int j = j0 + q;
                 const float4 h = *reinterpret_cast<const float4*>(Hc + j * LD + s0);
                 *reinterpret_cast<float4*>(Hp + j * LD + s0) = h;
@@ -397,9 +404,9 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
             {
                 // all global loads first (independent, one L2 round trip), then the shared-memory stores: interleaved,
                 // the compiler must assume the generic-pointer stores alias the next load and serialises 14 round trips
-                float4 hp4[2], hc4[2], st4[2][5];
+                float4 hp4[NU], hc4[NU], st4[NU][5];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < NU; ++q) {
                     const int j = j0 + q;
                     hp4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     if (t > 0) hp4[q] = row4_load(a.h_seq + (((size_t)t * a.N + g) * H + j) * a.B, b0, s0, valid, a.B);
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < NU; ++q) {
                     const int j = j0 + q;
                     *reinterpret_cast<float4*>(Hp + j * LD + s0) = hp4[q];
                     if (STASH) {
@@ -425,9 +432,9 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
             const float* X = sm + oX + (it & 1) * KIN * LD;
             mbar_wait(&bars[it & 1], (it >> 1) & 1);
             if (!STASH) {
-                fc1(sm, X, a.in_rows, g, X1);
+                fc1<NU>(sm, X, a.in_rows, g, X1);
                 __syncthreads();
-                gru_cell<true>(sm, X1, Hp, Hc, G);
+                gru_cell<NU, true>(sm, X1, Hp, Hc, G);
             }
             __syncthreads();
             GTL(5, true);
@@ -435,9 +442,9 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
             // head: logits of this step, loss terms / statistics / dlogits (LSTM:574-593, 628-638)
             {
                 float z[NA], dz[NA];
-                logits_of(sm, Hc, z);
+                if (tid < 4 * M) logits_of(sm, Hc, z);          // warp-uniform: 64 samples x 4 lanes = the first 8 warps
                 const int s = tid >> 2;
-                if ((tid & 3) == 0) {
+                if ((tid & 3) == 0 && tid < 4 * M) {
                     PolicyHead::apply(a.head, z, t, g, b0 + s, a.N, a.B, (b0 + s) < a.B, true, dz, st);
 #pragma unroll
                     for (int c = 0; c < NA; ++c) Z[c * LD + s] = dz[c];
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
 #pragma unroll
                 for (int c = 0; c < NA; ++c) dzv[c] = *reinterpret_cast<const float4*>(Z + c * LD + s0);
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < NU; ++q) {
                     const int j = j0 + q;
                     const float4 w = *reinterpret_cast<const float4*>(sm + oW2T + j * 8);
                     const float w4 = sm[oW2T + j * 8 + 4];
@@ -521,7 +528,7 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
             //     Meanwhile the previous step's inputs are pulled into L2 (they are read at its start).
             if (STASH && i + 1 < nsteps) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < NU; ++q) {
                     const int j = j0 + q;
                     const float* slab = a.stash + ((size_t)(t - 1) * a.N + g) * (5 * H) * a.B;
 #pragma unroll
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
 #pragma unroll
                     for (int bb = 0; bb < 8; ++bb)
                         dst[(jg + 16 * (aa & 1) + (aa >> 1) * H) * GLD + kg + 4 * bb] += acc[aa][bb];
-            } else {
+            } else if (tid < 128 + 4 * H) {
                 // dbih rows 0..95 (dbhh rows 0..63 are the same sums), dbhh rows 64..95 from da_hn
                 const int row = tid - 128;
                 float sum = 0.0f;
@@ -587,38 +594,46 @@ __global__ void __launch_bounds__(NT, 1) tbptt_chunk_kernel(ChunkArgs a) {
 
             // (d) dx1 = (Wih^T da_i) . relu'(x1) in place ; dh carry += Whh^T da_h
             {
-                float ax[2][4], ahh[2][4];
+                float ax[NU][4], ahh[NU][4];
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
+                for (int q = 0; q < NU; ++q)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) { ax[q][c] = 0.0f; ahh[q][c] = 0.0f; }
+                // packed backward weights: float4 per (gate row, output pair) = (Wih[row][2p], Wih[row][2p+1], Whh[..][2p], Whh[..][2p+1])
+                const int pair = (NU * og) >> 1, odd = (NU * og) & 1;
 #pragma unroll 4
                 for (int row = 0; row < 2 * H; ++row) {              // r and z gates feed both
                     const float4 d = *reinterpret_cast<const float4*>(G + row * LD + s0);
-                    const float4 wv = *reinterpret_cast<const float4*>(sm + oWih + (row * (H / 2) + og) * 4);
-                    const float2 wi = make_float2(wv.x, wv.y), wh = make_float2(wv.z, wv.w);
+                    const float4 wv = *reinterpret_cast<const float4*>(sm + oWih + (row * (H / 2) + pair) * 4);
+                    const float wi[2] = {NU == 2 ? wv.x : (odd ? wv.y : wv.x), wv.y};
+                    const float wh[2] = {NU == 2 ? wv.z : (odd ? wv.w : wv.z), wv.w};
                     const float ds[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        ax[0][c] = fmaf(wi.x, ds[c], ax[0][c]); ax[1][c] = fmaf(wi.y, ds[c], ax[1][c]);
-                        ahh[0][c] = fmaf(wh.x, ds[c], ahh[0][c]); ahh[1][c] = fmaf(wh.y, ds[c], ahh[1][c]);
-                    }
+                    for (int q = 0; q < NU; ++q)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            ax[q][c] = fmaf(wi[q], ds[c], ax[q][c]);
+                            ahh[q][c] = fmaf(wh[q], ds[c], ahh[q][c]);
+                        }
                 }
 #pragma unroll 4
                 for (int row = 2 * H; row < G3; ++row) {
                     const float4 di = *reinterpret_cast<const float4*>(G + row * LD + s0);         // da_n
                     const float4 dh = *reinterpret_cast<const float4*>(G + (row + H) * LD + s0);   // da_hn
-                    const float4 wv = *reinterpret_cast<const float4*>(sm + oWih + (row * (H / 2) + og) * 4);
-                    const float2 wi = make_float2(wv.x, wv.y), wh = make_float2(wv.z, wv.w);
+                    const float4 wv = *reinterpret_cast<const float4*>(sm + oWih + (row * (H / 2) + pair) * 4);
+                    const float wi[2] = {NU == 2 ? wv.x : (odd ? wv.y : wv.x), wv.y};
+                    const float wh[2] = {NU == 2 ? wv.z : (odd ? wv.w : wv.z), wv.w};
                     const float dis[4] = {di.x, di.y, di.z, di.w}, dhs[4] = {dh.x, dh.y, dh.z, dh.w};
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        ax[0][c] = fmaf(wi.x, dis[c], ax[0][c]); ax[1][c] = fmaf(wi.y, dis[c], ax[1][c]);
-                        ahh[0][c] = fmaf(wh.x, dhs[c], ahh[0][c]); ahh[1][c] = fmaf(wh.y, dhs[c], ahh[1][c]);
-                    }
+                    for (int q = 0; q < NU; ++q)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            ax[q][c] = fmaf(wi[q], dis[c], ax[q][c]);
+                            ahh[q][c] = fmaf(wh[q], dhs[c], ahh[q][c]);
+                        }
                 }
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < NU; ++q) {
                     const int j = j0 + q;
                     float4* px = reinterpret_cast<float4*>(X1 + j * LD + s0);
                     const float4 x = *px;
@@ -823,11 +838,12 @@ extern "C" int cmarl_debug_gru_timeline(long long* out_host16) {
 
 int cmarl_gru_setup(cmarl_ctx* ctx) {
     (void)ctx;
-    int e = cmarl_check_cuda(cudaFuncSetAttribute(gru::tbptt_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)gru::SMEM_BYTES), "cudaFuncSetAttribute(tbptt_chunk_kernel)");
-    if (e) return e;
-    return cmarl_check_cuda(cudaFuncSetAttribute(gru::tbptt_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)gru::SMEM_BYTES), "cudaFuncSetAttribute(tbptt_chunk_kernel)");
+    int e = 0;
+#define SETK(NU, ST) if (!e) e = cmarl_check_cuda(cudaFuncSetAttribute(gru::tbptt_chunk_kernel<NU, ST>, \
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru::SMEM_BYTES), "cudaFuncSetAttribute(tbptt_chunk_kernel)");
+    SETK(1, false) SETK(1, true) SETK(2, false) SETK(2, true)
+#undef SETK
+    return e;
 }
 
 extern "C" int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params, const float* state, const float* obs,
@@ -861,8 +877,17 @@ extern "C" int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params
     const int grid = units < ctx->sm_count ? units : ctx->sm_count;
     {
         KernelTimer kt(ctx, K_TBPTT, st);
-        if (stash) gru::tbptt_chunk_kernel<true><<<grid, gru::NT, gru::SMEM_BYTES, st>>>(a);
-        else gru::tbptt_chunk_kernel<false><<<grid, gru::NT, gru::SMEM_BYTES, st>>>(a);
+        // units per thread: 2 -> 256 threads (8 warps / SM, the default), 1 -> 512 threads (16 warps / SM).  Measured at
+        // 8 192 envs: 0.475 vs 0.533 ms per chunk -- twice the warps leave the gate GEMM at the same 7 900 cycles per
+        // step and slow the dx1/dh stage down (11.7 k vs 7.4 k cycles): the stages are not latency-bound.
+        static const int nu = [] { const char* v = getenv("CMARL_TBPTT_NU"); return (v && v[0] == '1') ? 1 : 2; }();
+        if (nu == 2) {
+            if (stash) gru::tbptt_chunk_kernel<2, true><<<grid, gru::NTMAX / 2, gru::SMEM_BYTES, st>>>(a);
+            else gru::tbptt_chunk_kernel<2, false><<<grid, gru::NTMAX / 2, gru::SMEM_BYTES, st>>>(a);
+        } else {
+            if (stash) gru::tbptt_chunk_kernel<1, true><<<grid, gru::NTMAX, gru::SMEM_BYTES, st>>>(a);
+            else gru::tbptt_chunk_kernel<1, false><<<grid, gru::NTMAX, gru::SMEM_BYTES, st>>>(a);
+        }
     }
     int e = cmarl_check_cuda(cudaGetLastError(), "tbptt_chunk_kernel");
     if (e) return e;
