@@ -341,15 +341,13 @@ def run_b200(a):
     #      and the step's results (per-epoch statistics, per-env episode returns) are read back to the host ----
     env_h = torch.empty(18, B, dtype=torch.float64).uniform_(-1, 1).pin_memory()
     env_h[6:12] = 0
-    env_d = torch.empty_like(env_h, device=dev)
-    stats_h = torch.empty(args.epochs, 8).pin_memory()
-    ret_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    res_h = torch.empty(tr.results.numel(), dtype=torch.uint8).pin_memory()
+    ret_h, stats_h = tr.split_results(res_h)                     # f64 [B] episode returns, f32 [epochs][8] statistics
 
     def e2e_step():
-        env_d.copy_(env_h, non_blocking=True)
-        tr.iteration(env_init=env_d)
-        stats_h.copy_(tr.epoch_stats, non_blocking=True)
-        ret_h.copy_(tr.buf["ep_return"], non_blocking=True)
+        tr.env.copy_(env_h, non_blocking=True)                   # H2D straight into the trainer's env-state buffer
+        tr.iteration(env_init=tr.env)
+        tr.results_to_host(res_h)                                # one D2H copy: episode returns + per-epoch statistics
         torch.cuda.current_stream().synchronize()               # the caller reads the results every step
 
     for _ in range(3):
@@ -361,19 +359,20 @@ def run_b200(a):
         torch.distributed.all_reduce(tw, op=torch.distributed.ReduceOp.MAX)
         e_wall = float(tw)
     h2d = env_h.numel() * 8
-    d2h = stats_h.numel() * 4 + ret_h.numel() * 8
+    d2h = res_h.numel()
 
     trace("e2e timed")
     # ---- the same with the categorical race noise supplied by the host as well (what the parity tests do; eager) ----
     noise_h = torch.empty(T_STEPS, N_AGENTS, N_ACT, B).exponential_(1).pin_memory()
     noise_d = torch.empty_like(noise_h, device=dev)
 
+    env_d = torch.empty_like(env_h, device=dev)
+
     def e2e_noise_step():
         env_d.copy_(env_h, non_blocking=True)
         noise_d.copy_(noise_h, non_blocking=True)
         tr.iteration(env_init=env_d, noise=noise_d)
-        stats_h.copy_(tr.epoch_stats, non_blocking=True)
-        ret_h.copy_(tr.buf["ep_return"], non_blocking=True)
+        tr.results_to_host(res_h)
         torch.cuda.current_stream().synchronize()
 
     for _ in range(3):

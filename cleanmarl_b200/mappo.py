@@ -260,9 +260,13 @@ class MAPPO:
         self.exp_avg_sq = torch.zeros_like(self.net.flat)
         self.adam_step = torch.zeros(1, dtype=torch.int32, device=eng.device)
         self.grads = eng.empty(eng.n_params + 8)
-        self.epoch_stats = eng.empty(args.epochs, 8)
+        # the per-step results a caller reads back (per-env episode returns f64 [B], per-epoch statistics f32 [epochs][8])
+        # live in ONE device block so that `results_to_host` is a single D2H copy
+        self.results = torch.zeros(self.B * 8 + args.epochs * 32, dtype=torch.uint8, device=eng.device)
+        self.epoch_stats = self.results[self.B * 8:].view(torch.float32).view(args.epochs, 8)
         self.norm_stats = eng.empty(4, dtype=torch.float64)
         self.buf = eng.alloc_rollout()
+        self.buf["ep_return"] = self.results[:self.B * 8].view(torch.float64)
         if self.recurrent:
             self.chunks = tbptt_chunks(self.T, args.tbptt)
             self.h_seq = eng.alloc_h_seq()
@@ -309,7 +313,7 @@ class MAPPO:
         eng, buf = self.engine, self.buf
         if env_init is None:
             eng.env_reset(self.env, self.rng_key, self.episode)
-        else:
+        elif env_init is not self.env:
             self.env.copy_(env_init, non_blocking=True)
         eng.rollout(self.net.actor, self.env, buf["state"], buf["actions"], buf["logp"], buf["reward"], noise=noise,
                     ep_return=buf["ep_return"], seed=self.rng_key, episode=self.episode)
@@ -437,7 +441,7 @@ class MAPPO:
         if not self.use_graph or noise is not None:
             return self._iteration_eager(env_init, noise)
         reset = env_init is None
-        if not reset:
+        if not reset and env_init is not self.env:          # callers may write the start states into `self.env` directly
             self.env.copy_(env_init, non_blocking=True)
         if self._episode_dev is None:
             self._episode_dev = torch.full((1,), self.episode, dtype=torch.int64, device=self.engine.device)
@@ -455,6 +459,15 @@ class MAPPO:
         self.step += self.B * self.T * self.world
         self.num_episodes += self.B * self.world
         self.training_step += self.args.epochs
+
+    def results_to_host(self, pinned: torch.Tensor):
+        """One asynchronous D2H copy of this step's results into a pinned uint8 buffer of ``self.results.numel()`` bytes;
+        ``split_results`` gives the (episode returns f64 [B], epoch statistics f32 [epochs][8]) views of it."""
+        pinned.copy_(self.results, non_blocking=True)
+
+    def split_results(self, host: torch.Tensor):
+        return (host[:self.B * 8].view(torch.float64),
+                host[self.B * 8:].view(torch.float32).view(self.args.epochs, 8))
 
     # -- read-backs (each is one small D2H copy; nothing else synchronises) ---------------------
     def train_scalars(self) -> dict:
