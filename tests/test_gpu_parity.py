@@ -456,15 +456,17 @@ def test_two_gpus_nccl_equal_one(cm, tmp_path, flags, comm):
 
 
 # ----------------------------------------------------------------------------------------- CUDA-graph replay
+@pytest.mark.parametrize("flags", [{}, {"normalize_reward": True, "normalize_advantage": True, "normalize_return": True,
+                                        "clip_gradients": 0.5}], ids=["plain", "normalised+clip"])
 @pytest.mark.parametrize("recurrent", [False, True], ids=["mlp", "recurrent"])
-def test_graph_replay_equals_eager_launches(cm, recurrent):
+def test_graph_replay_equals_eager_launches(cm, recurrent, flags):
     """The trainer's default mode (one captured CUDA graph per iteration, Philox keyed by a device episode counter)
     produces bit-identical parameters, statistics and rollouts to eager launches with the by-value episode argument."""
     from cleanmarl_b200.mappo import MAPPO, Args, ArgsRecurrent
     cls = ArgsRecurrent if recurrent else Args
     out = []
     for graph in (False, True):
-        tr = MAPPO(cls(batch_size=512, seed=4), use_graph=graph)
+        tr = MAPPO(cls(batch_size=512, seed=4, **flags), use_graph=graph)
         for _ in range(4):
             tr.iteration()
         torch.cuda.synchronize()
