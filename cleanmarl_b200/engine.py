@@ -131,18 +131,36 @@ class Engine:
         _lib.check(self.lib.cmarl_ctx_set_weight_decay(self._h, float(actor_wd), float(critic_wd)),
                    "cmarl_ctx_set_weight_decay")
 
-    def comm_setup(self, rank: int, world: int, group=None):
+    def comm_setup(self, rank: int, world: int, group=None) -> bool:
         """Peer-memory gradient exchange: allocate + export this rank's block, gather every rank's IPC handle through
-        ``torch.distributed`` and map the peers.  Afterwards the Adam entries exchange the gradients themselves."""
+        ``torch.distributed`` and map the peers.  Afterwards the Adam entries exchange the gradients themselves.
+        Returns False (after undoing the setup on every rank) if any rank could not map its peers -- e.g. GPUs without
+        peer access -- so that the caller can use the NCCL transport instead; every step is a collective decision."""
         import torch.distributed as dist
+        ok = 1
         handle = (C.c_uint8 * 64)()
-        _lib.check(self.lib.cmarl_comm_create(self._h, handle), "cmarl_comm_create")
+        try:
+            _lib.check(self.lib.cmarl_comm_create(self._h, handle), "cmarl_comm_create")
+        except _lib.CmarlError as e:
+            ok, err = 0, str(e)
         handles = [None] * world
         dist.all_gather_object(handles, bytes(handle), group=group)
-        blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
-        _lib.check(self.lib.cmarl_comm_attach(self._h, rank, world, blob), "cmarl_comm_attach")
-        dist.barrier(group=group)
+        if ok:
+            try:
+                blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+                _lib.check(self.lib.cmarl_comm_attach(self._h, rank, world, blob), "cmarl_comm_attach")
+            except _lib.CmarlError as e:
+                ok, err = 0, str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.lib.cmarl_comm_detach(self._h)
+            if not ok:
+                import sys
+                print(f"cleanmarl_b200: peer-memory exchange unavailable on rank {rank} ({err}); using NCCL", file=sys.stderr)
+            return False
         self.comm_world = world
+        return True
 
     def set_episode_counter(self, counter):
         """``counter``: int64 device tensor [1] (or None) -- see cmarl_ctx_set_episode_counter."""

@@ -297,8 +297,8 @@ class MAPPO:
         self.comm = "none"
         if world_size > 1:
             self.comm = os.environ.get("CMARL_COMM", "p2p") if engine_factory is Engine else "nccl"
-            if self.comm == "p2p":
-                eng.comm_setup(rank, world_size, process_group)
+            if self.comm == "p2p" and not eng.comm_setup(rank, world_size, process_group):
+                self.comm = "nccl"
         norm_flags = args.normalize_reward or args.normalize_advantage or args.normalize_return
         graph_ok = world_size == 1 or (self.comm == "p2p" and not norm_flags)
         self.use_graph = bool(use_graph) and graph_ok and engine_factory is Engine
