@@ -1,5 +1,7 @@
 // K4 (batched critic forward) and K7 (PPO epoch: fused forward + backward of actor and critic).
 // See chain.cuh for the tile pipeline.  Reference arithmetic: MME:527-582 (loss), MME:178-200 (nets).
+#include <stdlib.h>
+
 #include "chain.cuh"
 #include "heads.cuh"
 
@@ -329,6 +331,7 @@ using namespace chain;
 // tc_chain.cu
 int cmarl_tc_setup();
 int cmarl_tc_tile();
+void cmarl_tc_next_launch_pdl();
 int cmarl_tc_ctas_per_sm(int H, int in_rows, bool train, int out);
 template <class Head, bool TRAIN>
 int cmarl_tc_dispatch(int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
@@ -423,6 +426,12 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     ValueHeadArgs va;
     va.returns = returns; va.mask = mask; va.values_out = nullptr; va.inv_heads = 1.0f / (float)ctx->n_heads;
     {
+        // the critic chain reads nothing the actor chain writes (parameters come from the previous Adam step, which the
+        // actor chain has waited for): launched as its programmatic dependent it starts on every SM the actor chain's
+        // uneven last round of tiles leaves idle, with its prologue (weight images, TMEM) already done.  Not while the
+        // per-kernel event timing is on (the bracketing events would separate the two launches anyway).
+        static const bool pdl_ok = [] { const char* v = getenv("CMARL_PDL"); return !(v && v[0] == '0'); }();
+        if (ctx->use_tc && pdl_ok && !ctx->timing_on) cmarl_tc_next_launch_pdl();
         KernelTimer kt(ctx, K_PPO_CRITIC, st);
         e = run_chain<ValueHead, true>(ctx, c.critic_hidden, ndc, srcc, va, part_c, Pc, &grid_c, st);
     }

@@ -266,6 +266,8 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     constexpr int NCX = K1P / 8;                 // 8-column chunks of X
     constexpr int NXO = (NCX + 1) / 2;           // ... owned by a thread (at most)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // a kernel launched behind this one as a programmatic dependent may start filling SMs as they free up
+    asm volatile("griddepcontrol.launch_dependents;");
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::oBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::oBar + N_BARS * 8);
     const int tiles_b = (src.B + M - 1) / M;
@@ -767,6 +769,9 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     tc::tcgen05_fence_before();
     __syncthreads();
     if (warp == 8) tc::tmem_dealloc(tmem, C::TMEM_COLS);
+    // launched as a programmatic dependent (see tc_launch): this grid has not consumed anything of the kernel in front
+    // of it, but whoever follows must see BOTH complete -- so it completes only after that kernel (no-op otherwise)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 template <class C, class Head>
@@ -776,9 +781,27 @@ static int tc_set_attr() {
                             "cudaFuncSetAttribute(tc_chain_kernel)");
 }
 
+// One-shot flag (single host thread per context): the NEXT tc_chain launch is a programmatic dependent launch of the
+// kernel in front of it -- its CTAs may become resident as soon as every CTA of that kernel has passed
+// griddepcontrol.launch_dependents (the first instruction of tc_chain_kernel), i.e. as SMs free up.  Used for the critic
+// chain of an epoch, which reads nothing the actor chain in front of it writes.
+static bool g_next_launch_pdl = false;
+
 template <class C, class Head>
 static int tc_launch(const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials, int p_net,
                      int grid, cudaStream_t st) {
+    const bool pdl = g_next_launch_pdl;
+    g_next_launch_pdl = false;
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C::smem_bytes; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cmarl_check_cuda(cudaLaunchKernelEx(&cfg, tc_chain_kernel<C, Head>, nd, src, ha, partials, p_net),
+                                "tc_chain_kernel launch (programmatic dependent)");
+    }
     tc_chain_kernel<C, Head><<<grid, NTHREADS, C::smem_bytes, st>>>(nd, src, ha, partials, p_net);
     return cmarl_check_cuda(cudaGetLastError(), "tc_chain_kernel launch");
 }
@@ -799,6 +822,7 @@ int cmarl_tc_setup() {
 }
 
 int cmarl_tc_tile() { return M; }
+void cmarl_tc_next_launch_pdl() { g_next_launch_pdl = true; }
 
 // co-resident CTAs per SM of the kernel that dispatch<Head, TRAIN> would launch (sizes the persistent grid)
 int cmarl_tc_ctas_per_sm(int H, int in_rows, bool train, int out) {
