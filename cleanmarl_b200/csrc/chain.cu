@@ -331,7 +331,7 @@ using namespace chain;
 // tc_chain.cu
 int cmarl_tc_setup();
 int cmarl_tc_tile();
-void cmarl_tc_next_launch_pdl();
+void cmarl_tc_next_launch_pdl(bool on);
 int cmarl_tc_ctas_per_sm(int H, int in_rows, bool train, int out);
 template <class Head, bool TRAIN>
 int cmarl_tc_dispatch(int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
@@ -431,9 +431,10 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
         // uneven last round of tiles leaves idle, with its prologue (weight images, TMEM) already done.  Not while the
         // per-kernel event timing is on (the bracketing events would separate the two launches anyway).
         static const bool pdl_ok = [] { const char* v = getenv("CMARL_PDL"); return !(v && v[0] == '0'); }();
-        if (ctx->use_tc && pdl_ok && !ctx->timing_on) cmarl_tc_next_launch_pdl();
+        if (ctx->use_tc && pdl_ok && !ctx->timing_on) cmarl_tc_next_launch_pdl(true);
         KernelTimer kt(ctx, K_PPO_CRITIC, st);
         e = run_chain<ValueHead, true>(ctx, c.critic_hidden, ndc, srcc, va, part_c, Pc, &grid_c, st);
+        cmarl_tc_next_launch_pdl(false);      // never leaks to another launch, whatever path run_chain took
     }
     if (e) return e;
 

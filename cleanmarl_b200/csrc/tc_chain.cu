@@ -822,7 +822,7 @@ int cmarl_tc_setup() {
 }
 
 int cmarl_tc_tile() { return M; }
-void cmarl_tc_next_launch_pdl() { g_next_launch_pdl = true; }
+void cmarl_tc_next_launch_pdl(bool on) { g_next_launch_pdl = on; }
 
 // co-resident CTAs per SM of the kernel that dispatch<Head, TRAIN> would launch (sizes the persistent grid)
 int cmarl_tc_ctas_per_sm(int H, int in_rows, bool train, int out) {
