@@ -204,7 +204,7 @@ __device__ __forceinline__ void gru_cell(const float* __restrict__ sm, const flo
 #pragma unroll
         for (int c = 0; c < 4; ++c) { ar[i][c] = b.x; az[i][c] = b.y; ai[i][c] = b.z; ah[i][c] = b.w; }
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < H; ++k) {
         const float4 x = *reinterpret_cast<const float4*>(X1 + k * LD + s0);
         const float xs[4] = {x.x, x.y, x.z, x.w};
@@ -219,7 +219,7 @@ __device__ __forceinline__ void gru_cell(const float* __restrict__ sm, const flo
             }
         }
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < H; ++k) {
         const float4 x = *reinterpret_cast<const float4*>(Hp + k * LD + s0);
         const float xs[4] = {x.x, x.y, x.z, x.w};
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a)
                 int grow[6];
 #pragma unroll
                 for (int aa = 0; aa < 6; ++aa) grow[aa] = jg + 16 * (aa & 1) + ((aa >> 1) == 2 ? gn : (aa >> 1) * H);
-#pragma unroll 1
+#pragma unroll 2
                 for (int q = 0; q < NQ; ++q) {
                     float4 d[6], x[8];
 #pragma unroll
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a)
                     for (int c = 0; c < 4; ++c) { ax[q][c] = 0.0f; ahh[q][c] = 0.0f; }
                 // packed backward weights: float4 per (gate row, output pair) = (Wih[row][2p], Wih[row][2p+1], Whh[..][2p], Whh[..][2p+1])
                 const int pair = (NU * og) >> 1, odd = (NU * og) & 1;
-#pragma unroll 4
+#pragma unroll 8
                 for (int row = 0; row < 2 * H; ++row) {              // r and z gates feed both
                     const float4 d = *reinterpret_cast<const float4*>(G + row * LD + s0);
                     const float4 wv = *reinterpret_cast<const float4*>(sm + oWih + (row * (H / 2) + pair) * 4);
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a)
                             ahh[q][c] = fmaf(wh[q], ds[c], ahh[q][c]);
                         }
                 }
-#pragma unroll 4
+#pragma unroll 8
                 for (int row = 2 * H; row < G3; ++row) {
                     const float4 di = *reinterpret_cast<const float4*>(G + row * LD + s0);         // da_n
                     const float4 dh = *reinterpret_cast<const float4*>(G + (row + H) * LD + s0);   // da_hn
