@@ -1,6 +1,6 @@
 // Diagnostic: issues tcgen05.mma.kind::tf32 on a caller-supplied shared-memory image with
 // caller-supplied matrix / instruction descriptors and dumps the TMEM accumulator.  Built as its own
-// library (libcmarl_umma_probe.so); tests/test_umma_layouts.py uses it to pin the descriptor and
+// library (libcmarl_umma_probe.so); profiles/tools/umma_explore.py uses it to pin the descriptor and
 // canonical-layout conventions that tc_chain.cu relies on (K-major / MN-major, swizzle modes, M = 64
 // vs 128 accumulator layouts) against a host GEMM.  Not part of the training path.
 #include <cuda_runtime.h>
