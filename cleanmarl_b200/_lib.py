@@ -29,6 +29,7 @@ _SIGNATURES = {
     "cmarl_ctx_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     "cmarl_ctx_destroy": (C.c_int, [_P]),
     "cmarl_ctx_set_tensor_cores": (C.c_int, [_P, C.c_int]),
+    "cmarl_ctx_set_launch_chaining": (C.c_int, [_P, C.c_int]),
     "cmarl_ctx_set_weight_decay": (C.c_int, [_P, C.c_double, C.c_double]),
     "cmarl_actor_param_count": (C.c_int, [_P]),
     "cmarl_critic_param_count": (C.c_int, [_P]),
@@ -66,7 +67,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-VERSION = 101          # CMARL_VERSION of include/cmarl_b200.h
+VERSION = 102          # CMARL_VERSION of include/cmarl_b200.h
 N_KERNEL_IDS = 12      # CMARL_NK
 
 _lib = None

@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_GROUPS) reduce_partials_kernel(
                                                                                 float* __restrict__ out) {
     __shared__ float part[RED_GROUPS][RED_COLS + 1];
     __shared__ double dpart[RED_GROUPS];
+    pdl_wait_then_trigger();
     const int col_l = threadIdx.x % RED_COLS, grp = threadIdx.x / RED_COLS;
     const int i = blockIdx.x * RED_COLS + col_l;
     const int P = Pa + Pc;
@@ -300,7 +301,7 @@ static void actor_desc(const cmarl_ctx* ctx, const float* params, const float* s
     nd.params = params;
     nd.in_dim = c.obs_dim;
     nd.out_dim = c.n_actions;
-    src.T = c.n_steps; src.G = c.n_agents; src.B = c.n_envs;
+    src.T = c.n_steps; src.G = c.n_agents; src.B = c.n_envs; src.indep = 0;
     if (obs) {
         nd.in_rows = c.obs_dim; nd.fold_ids = 0;
         src.x = obs; src.stride_t = (size_t)c.n_agents * c.obs_dim * c.n_envs; src.stride_g = (size_t)c.obs_dim * c.n_envs;
@@ -320,7 +321,7 @@ static void critic_desc(const cmarl_ctx* ctx, const float* params, const float* 
     }
     nd.params = params;
     nd.in_rows = c.state_dim; nd.in_dim = c.state_dim; nd.fold_ids = 0; nd.out_dim = 1;
-    src.x = state; src.T = c.n_steps; src.G = 1; src.B = c.n_envs;
+    src.x = state; src.T = c.n_steps; src.G = 1; src.B = c.n_envs; src.indep = 0;
     src.stride_t = (size_t)c.state_dim * c.n_envs; src.stride_g = 0;
 }
 
@@ -331,11 +332,10 @@ using namespace chain;
 // tc_chain.cu
 int cmarl_tc_setup();
 int cmarl_tc_tile();
-void cmarl_tc_next_launch_pdl(bool on);
 int cmarl_tc_ctas_per_sm(int H, int in_rows, bool train, int out);
 template <class Head, bool TRAIN>
-int cmarl_tc_dispatch(int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
-                      int p_net, int grid, cudaStream_t st);
+int cmarl_tc_dispatch(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha,
+                      float* partials, int p_net, int grid, cudaStream_t st);
 
 template <class Head, bool TRAIN>
 static int run_chain(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha,
@@ -346,7 +346,7 @@ static int run_chain(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileS
     const int slots = ctx->sm_count * (ctx->use_tc ? cmarl_tc_ctas_per_sm(H, nd.in_rows, TRAIN, Head::OUT) : 1);
     const int grid = units < slots ? units : slots;
     if (grid_out) *grid_out = grid;
-    if (ctx->use_tc) return cmarl_tc_dispatch<Head, TRAIN>(H, nd, src, ha, partials, p_net, grid, st);
+    if (ctx->use_tc) return cmarl_tc_dispatch<Head, TRAIN>(ctx, H, nd, src, ha, partials, p_net, grid, st);
     return dispatch<Head, TRAIN>(ctx, H, nd, src, ha, partials, p_net, grid, st);
 }
 
@@ -427,24 +427,23 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
     va.returns = returns; va.mask = mask; va.values_out = nullptr; va.inv_heads = 1.0f / (float)ctx->n_heads;
     {
         // the critic chain reads nothing the actor chain writes (parameters come from the previous Adam step, which the
-        // actor chain has waited for): launched as its programmatic dependent it starts on every SM the actor chain's
-        // uneven last round of tiles leaves idle, with its prologue (weight images, TMEM) already done.  Not while the
-        // per-kernel event timing is on (the bracketing events would separate the two launches anyway).
+        // actor chain has waited for): launched as its programmatic dependent with `indep` set it starts on every SM the
+        // actor chain's uneven last round of tiles leaves idle.  Not while the per-kernel event timing is on (the
+        // bracketing events would separate the two launches anyway).
         static const bool pdl_ok = [] { const char* v = getenv("CMARL_PDL"); return !(v && v[0] == '0'); }();
-        if (ctx->use_tc && pdl_ok && !ctx->timing_on) cmarl_tc_next_launch_pdl(true);
+        srcc.indep = (ctx->use_tc && pdl_ok && !ctx->timing_on) ? 1 : 0;
         KernelTimer kt(ctx, K_PPO_CRITIC, st);
         e = run_chain<ValueHead, true>(ctx, c.critic_hidden, ndc, srcc, va, part_c, Pc, &grid_c, st);
-        cmarl_tc_next_launch_pdl(false);      // never leaks to another launch, whatever path run_chain took
     }
     if (e) return e;
 
     const int n_out = Pa + Pc + CMARL_N_STATS;
     {
         KernelTimer kt(ctx, K_PPO_REDUCE, st);
-        reduce_partials_kernel<<<ceil_div(n_out, RED_COLS), RED_COLS * RED_GROUPS, 0, st>>>(part_a, grid_a, Pa, part_c, grid_c, Pc,
-                                                                     (float)c.n_agents, 0, grads_out);
+        CMARL_CUDA(cmarl_launch(ctx, reduce_partials_kernel, dim3(ceil_div(n_out, RED_COLS)), dim3(RED_COLS * RED_GROUPS), 0, st,
+                                part_a, grid_a, Pa, part_c, grid_c, Pc, (float)c.n_agents, 0, grads_out));
     }
-    return cmarl_check_cuda(cudaGetLastError(), "reduce_partials_kernel");
+    return 0;
 }
 
 // Fixed-order reduction of one network's per-CTA partials (used by the recurrent path, gru.cu): actor-only
@@ -454,10 +453,10 @@ int cmarl_reduce_one_net(cmarl_ctx* ctx, const float* pa, int grid_a, int Pa, co
     const int n_out = Pa + Pc + CMARL_N_STATS;
     {
         KernelTimer kt(ctx, K_PPO_REDUCE, st);
-        reduce_partials_kernel<<<ceil_div(n_out, RED_COLS), RED_COLS * RED_GROUPS, 0, st>>>(pa, grid_a, Pa, pc, grid_c, Pc, count_div,
-                                                                                         pa == nullptr, out);
+        CMARL_CUDA(cmarl_launch(ctx, reduce_partials_kernel, dim3(ceil_div(n_out, RED_COLS)), dim3(RED_COLS * RED_GROUPS), 0, st,
+                                pa, grid_a, Pa, pc, grid_c, Pc, count_div, (int)(pa == nullptr), out));
     }
-    return cmarl_check_cuda(cudaGetLastError(), "reduce_partials_kernel");
+    return 0;
 }
 
 extern "C" int cmarl_critic_epoch_grads(cmarl_ctx* ctx, const float* critic_params, const float* state, const float* obs,

@@ -120,6 +120,7 @@ struct TileSrc {
     const float* x;        // row r of tile (t, g, b0) lives at x + t*stride_t + g*stride_g + r*B + b0
     size_t stride_t, stride_g;
     int T, G, B;
+    int indep;             // tc_chain_kernel only: 1 = reads nothing the launch in front of it writes (see tc_chain.cu)
 };
 
 struct PolicyHeadArgs {

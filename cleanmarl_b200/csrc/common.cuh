@@ -93,6 +93,7 @@ struct cmarl_ctx {
     cmarl_comm comm;         // peer-memory gradient exchange (world <= 1: off)
     double weight_decay[2];  // actor, critic: decoupled weight decay of the Adam entries (AdamW); 0 = plain Adam
     uint64_t* episode_dev;   // optional device episode counter for the Philox draws (CUDA-graph replay)
+    int launch_chaining;     // 1: launches carry the programmatic-stream-serialization attribute (cmarl_ctx_set_launch_chaining)
     cmarl_timing* timing;
 };
 
@@ -125,6 +126,42 @@ int cmarl_check_cuda(cudaError_t e, const char* what);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (launch chaining, cmarl_ctx_set_launch_chaining).  Every kernel of the library begins
+// with pdl_wait_then_trigger(): `griddepcontrol.wait` blocks until the grid in front of it on the stream has completed
+// and flushed (immediately when the launch carried no programmatic attribute), `griddepcontrol.launch_dependents`
+// then lets the NEXT launch become resident.  Waiting BEFORE triggering makes completion transitive along the chain:
+// by the time a kernel's dependent starts, everything in front of that kernel has completed, and the dependent's own
+// wait covers the kernel itself -- so only launch latency and pre-wait prologues (shared-memory zeroing, barrier
+// init, TMEM allocation) overlap, never a read with the write it depends on.
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_then_trigger() { pdl_wait(); pdl_trigger(); }
+
+// Launch `kernel` on `st`, as a programmatic dependent of the launch in front of it when `pdl` is set.
+template <class... KArgs, class... Args>
+static inline cudaError_t cmarl_launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// ... while launch chaining is on (and the per-kernel event timing is off: the bracketing events would separate the
+// launches anyway)
+static inline bool cmarl_chained(const cmarl_ctx* ctx) { return ctx && ctx->launch_chaining && !ctx->timing_on; }
+template <class... KArgs, class... Args>
+static inline cudaError_t cmarl_launch(const cmarl_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t st, Args... args) {
+    return cmarl_launch_pdl(cmarl_chained(ctx), kernel, grid, block, smem, st, args...);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011) -- counter-based, so a draw is a pure function of

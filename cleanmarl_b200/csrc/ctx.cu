@@ -154,6 +154,12 @@ extern "C" int cmarl_ctx_set_tensor_cores(cmarl_ctx* ctx, int on) {
     return 0;
 }
 
+extern "C" int cmarl_ctx_set_launch_chaining(cmarl_ctx* ctx, int on) {
+    CMARL_ARG(ctx, "null ctx");
+    ctx->launch_chaining = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int cmarl_ctx_set_weight_decay(cmarl_ctx* ctx, double actor_wd, double critic_wd) {
     CMARL_ARG(ctx, "null ctx");
     CMARL_ARG(actor_wd >= 0.0 && critic_wd >= 0.0, "weight decay must be >= 0");

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) td_lambda_kernel(const float* __restrict_
                                                         float* __restrict__ returns,
                                                         float* __restrict__ adv,
                                                         int T, int V, int B, float g, float l, float oml) {
+    pdl_wait_then_trigger();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= V * B) return;
     const int v = idx / B, b = idx - v * B;
@@ -79,10 +80,10 @@ extern "C" int cmarl_td_lambda(cmarl_ctx* ctx, const float* values, const float*
     const float g = (float)gamma, l = (float)lambda, oml = (float)(1.0 - lambda);
     {
         KernelTimer kt(ctx, K_TD, as_stream(stream));
-        td_lambda_kernel<5><<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(values, reward, mask, returns, adv,
-                                                                            T, V, B, g, l, oml);
+        CMARL_CUDA(cmarl_launch(ctx, td_lambda_kernel<5>, dim3(ceil_div(n, 256)), dim3(256), 0, as_stream(stream), values, reward,
+                                mask, returns, adv, T, V, B, g, l, oml));
     }
-    return cmarl_check_cuda(cudaGetLastError(), "td_lambda_kernel");
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------- K6
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.tensor_off[12];
     const int mine = blockIdx.x * ADAM_THREADS + tid;          // the parameter this thread updates
+    pdl_wait_then_trigger();
     constexpr bool xchg = XCHG;       // peer-memory exchange compiled in only for multi-GPU launches
     int par = 0;
     unsigned int tag = 0;
@@ -422,10 +424,11 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     fill_comm(ctx, a, 0);
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
-        if (a.world > 1) clip_adam_kernel<true><<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
-        else clip_adam_kernel<false><<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
+        const dim3 grid(ceil_div(a.tensor_off[12], ADAM_THREADS)), block(ADAM_THREADS);
+        CMARL_CUDA(a.world > 1 ? cmarl_launch(ctx, clip_adam_kernel<true>, grid, block, 0, as_stream(stream), a)
+                               : cmarl_launch(ctx, clip_adam_kernel<false>, grid, block, 0, as_stream(stream), a));
     }
-    return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
+    return 0;
 }
 
 // One network at a time (recurrent path: the actor is stepped once per truncated-BPTT chunk, the critic once
@@ -462,8 +465,9 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     fill_comm(ctx, a, net);
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
-        if (a.world > 1) clip_adam_kernel<true><<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
-        else clip_adam_kernel<false><<<ceil_div(a.tensor_off[12], ADAM_THREADS), ADAM_THREADS, 0, as_stream(stream)>>>(a);
+        const dim3 grid(ceil_div(a.tensor_off[12], ADAM_THREADS)), block(ADAM_THREADS);
+        CMARL_CUDA(a.world > 1 ? cmarl_launch(ctx, clip_adam_kernel<true>, grid, block, 0, as_stream(stream), a)
+                               : cmarl_launch(ctx, clip_adam_kernel<false>, grid, block, 0, as_stream(stream), a));
     }
-    return cmarl_check_cuda(cudaGetLastError(), "clip_adam_kernel");
+    return 0;
 }

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a)
     const int nsteps = a.t1 - a.t0;
     const GruLayout& L = a.L;
 
-    load_weights(sm, a);
+    // shared-memory zeroing first: under launch chaining it runs while the kernel in front (an Adam step) still does
     for (int i = tid; i < 2 * KIN * LD; i += NT) sm[oX + i] = 0.0f;
     for (int i = tid; i < PMAXG; i += NT) sm[oDW + i] = 0.0f;
     for (int i = tid; i < 2 * G3 * GLD; i += NT) sm[oDG + i] = 0.0f;
@@ -325,6 +325,8 @@ __global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a)
         mbar_init(&bars[1], 1);
         mbar_fence_init();
     }
+    pdl_wait_then_trigger();
+    load_weights(sm, a);
     __syncthreads();
 
     float* dW = sm + oDW;
@@ -881,16 +883,18 @@ extern "C" int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params
         // 8 192 envs: 0.475 vs 0.533 ms per chunk -- twice the warps leave the gate GEMM at the same 7 900 cycles per
         // step and slow the dx1/dh stage down (11.7 k vs 7.4 k cycles): the stages are not latency-bound.
         static const int nu = [] { const char* v = getenv("CMARL_TBPTT_NU"); return (v && v[0] == '1') ? 1 : 2; }();
+        cudaError_t ce;
         if (nu == 2) {
-            if (stash) gru::tbptt_chunk_kernel<2, true><<<grid, gru::NTMAX / 2, gru::SMEM_BYTES, st>>>(a);
-            else gru::tbptt_chunk_kernel<2, false><<<grid, gru::NTMAX / 2, gru::SMEM_BYTES, st>>>(a);
+            const dim3 block(gru::NTMAX / 2);
+            ce = stash ? cmarl_launch(ctx, gru::tbptt_chunk_kernel<2, true>, dim3(grid), block, gru::SMEM_BYTES, st, a)
+                       : cmarl_launch(ctx, gru::tbptt_chunk_kernel<2, false>, dim3(grid), block, gru::SMEM_BYTES, st, a);
         } else {
-            if (stash) gru::tbptt_chunk_kernel<1, true><<<grid, gru::NTMAX, gru::SMEM_BYTES, st>>>(a);
-            else gru::tbptt_chunk_kernel<1, false><<<grid, gru::NTMAX, gru::SMEM_BYTES, st>>>(a);
+            const dim3 block(gru::NTMAX);
+            ce = stash ? cmarl_launch(ctx, gru::tbptt_chunk_kernel<1, true>, dim3(grid), block, gru::SMEM_BYTES, st, a)
+                       : cmarl_launch(ctx, gru::tbptt_chunk_kernel<1, false>, dim3(grid), block, gru::SMEM_BYTES, st, a);
         }
+        CMARL_CUDA(ce);
     }
-    int e = cmarl_check_cuda(cudaGetLastError(), "tbptt_chunk_kernel");
-    if (e) return e;
     return cmarl_reduce_one_net(ctx, a.partials, grid, ctx->gru.count, nullptr, 0, 0, (float)c.n_agents, grads_out, st);
 }
 

@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
     const int B = a.B;
     const int j0 = qq * JL;
 
+    pdl_wait_then_trigger();
     for (int i = tid; i < 18 * REPB; i += NTHR) {
         const int r = i / REPB, c = i - r * REPB;
         const int bb = blockIdx.x * REPB + c;
@@ -566,6 +567,7 @@ __global__ void __launch_bounds__(RT) actor_act_kernel(ActArgs a) {
 // ---- K1 reset ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) env_reset_kernel(double* __restrict__ env, int B, uint64_t seed, uint64_t episode,
                                                         const uint64_t* __restrict__ episode_dev) {
+    pdl_wait_then_trigger();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     if (episode_dev) episode = *episode_dev;
@@ -634,7 +636,7 @@ extern "C" int cmarl_debug_rollout_timeline(long long* out_host16) {
     return (int)cudaMemcpyFromSymbol(out_host16, g_roll_tl, sizeof(long long) * 16);
 }
 
-__global__ void episode_advance_kernel(uint64_t* e) { *e += 1; }
+__global__ void episode_advance_kernel(uint64_t* e) { pdl_wait_then_trigger(); *e += 1; }
 
 // shared-memory opt-ins, once per context (not inside the launch path: keeps cmarl_rollout CUDA-graph capturable)
 int cmarl_rollout_setup(cmarl_ctx* ctx) {
@@ -661,8 +663,8 @@ extern "C" int cmarl_ctx_set_episode_counter(cmarl_ctx* ctx, uint64_t* episode_d
 extern "C" int cmarl_episode_advance(cmarl_ctx* ctx, void* stream) {
     CMARL_ARG(ctx && ctx->episode_dev, "no device episode counter set (cmarl_ctx_set_episode_counter)");
     ctx->launches++;
-    episode_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(ctx->episode_dev);
-    return cmarl_check_cuda(cudaGetLastError(), "episode_advance_kernel");
+    return cmarl_check_cuda(cmarl_launch(ctx, episode_advance_kernel, dim3(1), dim3(1), 0, as_stream(stream), ctx->episode_dev),
+                            "episode_advance_kernel");
 }
 
 extern "C" int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, void* stream) {
@@ -670,9 +672,10 @@ extern "C" int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint6
     const int B = ctx->cfg.n_envs;
     {
         KernelTimer kt(ctx, K_RESET, as_stream(stream));
-        env_reset_kernel<<<ceil_div(B, 256), 256, 0, as_stream(stream)>>>(env, B, seed, episode, ctx->episode_dev);
+        CMARL_CUDA(cmarl_launch(ctx, env_reset_kernel, dim3(ceil_div(B, 256)), dim3(256), 0, as_stream(stream), env, B, seed, episode,
+                                (const uint64_t*)ctx->episode_dev));
     }
-    return cmarl_check_cuda(cudaGetLastError(), "env_reset_kernel");
+    return 0;
 }
 
 extern "C" int cmarl_env_observe(cmarl_ctx* ctx, const double* env, float* state_out, void* stream) {
@@ -714,23 +717,19 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
         constexpr size_t smem21 = (size_t)RolloutLayout<32, 21, true>::floats * sizeof(float);
         constexpr size_t smem18 = (size_t)RolloutLayout<32, 18, true>::floats * sizeof(float);
         KernelTimer kt(ctx, K_ROLLOUT, st);
-        if (ids) rollout_kernel<32, 21, true><<<grid, RolloutThreads<true>::N, smem21, st>>>(a);
-        else rollout_kernel<32, 18, true><<<grid, RolloutThreads<true>::N, smem18, st>>>(a);
-        return cmarl_check_cuda(cudaGetLastError(), "rollout_kernel (recurrent)");
+        return cmarl_check_cuda(ids ? cmarl_launch(ctx, rollout_kernel<32, 21, true>, dim3(grid), dim3(RolloutThreads<true>::N), smem21, st, a)
+                                    : cmarl_launch(ctx, rollout_kernel<32, 18, true>, dim3(grid), dim3(RolloutThreads<true>::N), smem18, st, a),
+                                "rollout_kernel (recurrent)");
     }
     const size_t smem = (size_t)(H * W1LD + NAG * H + H * H + H + NACT * H + 8 + NAG * H * REPB + NAG * NQ * NACT * REPB +
                                  NAG * NACT * REPB) * sizeof(float);
-    {
-        KernelTimer kt(ctx, K_ROLLOUT, st);
-        if (H == 32) {
-            if (ids) rollout_kernel<32, 21, false><<<grid, RolloutThreads<false>::N, smem, st>>>(a);
-            else rollout_kernel<32, 18, false><<<grid, RolloutThreads<false>::N, smem, st>>>(a);
-        } else {
-            if (ids) rollout_kernel<64, 21, false><<<grid, RolloutThreads<false>::N, smem, st>>>(a);
-            else rollout_kernel<64, 18, false><<<grid, RolloutThreads<false>::N, smem, st>>>(a);
-        }
-    }
-    return cmarl_check_cuda(cudaGetLastError(), "rollout_kernel");
+    const dim3 block(RolloutThreads<false>::N);
+    KernelTimer kt(ctx, K_ROLLOUT, st);
+    if (H == 32)
+        return cmarl_check_cuda(ids ? cmarl_launch(ctx, rollout_kernel<32, 21, false>, dim3(grid), block, smem, st, a)
+                                    : cmarl_launch(ctx, rollout_kernel<32, 18, false>, dim3(grid), block, smem, st, a), "rollout_kernel");
+    return cmarl_check_cuda(ids ? cmarl_launch(ctx, rollout_kernel<64, 21, false>, dim3(grid), block, smem, st, a)
+                                : cmarl_launch(ctx, rollout_kernel<64, 18, false>, dim3(grid), block, smem, st, a), "rollout_kernel");
 }
 
 extern "C" int cmarl_actor_act(cmarl_ctx* ctx, const float* actor_params, const float* obs, const uint8_t* avail,

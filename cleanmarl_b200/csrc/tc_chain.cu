@@ -266,15 +266,16 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     constexpr int NCX = K1P / 8;                 // 8-column chunks of X
     constexpr int NXO = (NCX + 1) / 2;           // ... owned by a thread (at most)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // a kernel launched behind this one as a programmatic dependent may start filling SMs as they free up
-    asm volatile("griddepcontrol.launch_dependents;");
+    // `src.indep` (the critic chain of an epoch, launched as a programmatic dependent of the actor chain): this grid
+    // reads nothing the grid in front of it writes, so whatever is launched behind it may be scheduled right away ...
+    if (src.indep) pdl_trigger();
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::oBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::oBar + N_BARS * 8);
     const int tiles_b = (src.B + M - 1) / M;
     const int units = src.T * src.G * tiles_b;
 
     // ---- one-time setup (all 288 threads) -------------------------------------------------------------
-    load_weights_tc<C>(sm, nd, src.G);
+    // first what touches no global memory: under launch chaining this part runs while the kernel in front still does
     if (TRAIN) {
         for (int i = tid * 16; i < 2 * C::A_S_BYTES + 2 * B_S_BYTES; i += NTHREADS * 16)
             *reinterpret_cast<uint4*>(sm + C::oAs + i) = make_uint4(0, 0, 0, 0);
@@ -286,6 +287,9 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         tc::fence_mbar_init();
     }
     if (warp == 8) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    // the grid in front of this one (and, transitively, everything before it) has completed past this point
+    if (!src.indep) pdl_wait_then_trigger();
+    load_weights_tc<C>(sm, nd, src.G);
     __syncthreads();
     if (TRAIN && tid < M) {
         // the ones row (row 0 of group 4 of the B image, hi = 1, lo = 0): its product with dH is the bias gradient
@@ -769,9 +773,8 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     tc::tcgen05_fence_before();
     __syncthreads();
     if (warp == 8) tc::tmem_dealloc(tmem, C::TMEM_COLS);
-    // launched as a programmatic dependent (see tc_launch): this grid has not consumed anything of the kernel in front
-    // of it, but whoever follows must see BOTH complete -- so it completes only after that kernel (no-op otherwise)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ... but whoever follows must see BOTH this grid and the one in front of it complete: it completes only after that one
+    if (src.indep) pdl_wait();
 }
 
 template <class C, class Head>
@@ -781,29 +784,14 @@ static int tc_set_attr() {
                             "cudaFuncSetAttribute(tc_chain_kernel)");
 }
 
-// One-shot flag (single host thread per context): the NEXT tc_chain launch is a programmatic dependent launch of the
-// kernel in front of it -- its CTAs may become resident as soon as every CTA of that kernel has passed
-// griddepcontrol.launch_dependents (the first instruction of tc_chain_kernel), i.e. as SMs free up.  Used for the critic
-// chain of an epoch, which reads nothing the actor chain in front of it writes.
-static bool g_next_launch_pdl = false;
-
+// `src.indep` launches (the critic chain of an epoch) are programmatic dependents of the kernel in front of them whatever
+// the context's launch-chaining switch says; everything else follows the switch (cmarl_launch).
 template <class C, class Head>
-static int tc_launch(const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials, int p_net,
-                     int grid, cudaStream_t st) {
-    const bool pdl = g_next_launch_pdl;
-    g_next_launch_pdl = false;
-    if (pdl) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C::smem_bytes; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        return cmarl_check_cuda(cudaLaunchKernelEx(&cfg, tc_chain_kernel<C, Head>, nd, src, ha, partials, p_net),
-                                "tc_chain_kernel launch (programmatic dependent)");
-    }
-    tc_chain_kernel<C, Head><<<grid, NTHREADS, C::smem_bytes, st>>>(nd, src, ha, partials, p_net);
-    return cmarl_check_cuda(cudaGetLastError(), "tc_chain_kernel launch");
+static int tc_launch(const cmarl_ctx* ctx, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
+                     int p_net, int grid, cudaStream_t st) {
+    return cmarl_check_cuda(cmarl_launch_pdl(src.indep || cmarl_chained(ctx), tc_chain_kernel<C, Head>, dim3(grid), dim3(NTHREADS),
+                                             C::smem_bytes, st, nd, src, ha, partials, p_net),
+                            "tc_chain_kernel launch");
 }
 
 }  // namespace tcchain
@@ -822,7 +810,6 @@ int cmarl_tc_setup() {
 }
 
 int cmarl_tc_tile() { return M; }
-void cmarl_tc_next_launch_pdl(bool on) { g_next_launch_pdl = on; }
 
 // co-resident CTAs per SM of the kernel that dispatch<Head, TRAIN> would launch (sizes the persistent grid)
 int cmarl_tc_ctas_per_sm(int H, int in_rows, bool train, int out) {
@@ -844,17 +831,17 @@ extern "C" int cmarl_debug_tc_timeline(int enable, long long* out_host64) {
 }
 
 template <class Head, bool TRAIN>
-int cmarl_tc_dispatch(int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
-                      int p_net, int grid, cudaStream_t st) {
+int cmarl_tc_dispatch(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha,
+                      float* partials, int p_net, int grid, cudaStream_t st) {
     const int kin = nd.in_rows <= 24 ? 24 : 56;
-    if (H == 32 && kin == 24) return tc_launch<TCfg<32, 24, TRAIN, Head::OUT>, Head>(nd, src, ha, partials, p_net, grid, st);
-    if (H == 32 && kin == 56) return tc_launch<TCfg<32, 56, TRAIN, Head::OUT>, Head>(nd, src, ha, partials, p_net, grid, st);
-    if (H == 64 && kin == 24) return tc_launch<TCfg<64, 24, TRAIN, Head::OUT>, Head>(nd, src, ha, partials, p_net, grid, st);
-    if (H == 64 && kin == 56) return tc_launch<TCfg<64, 56, TRAIN, Head::OUT>, Head>(nd, src, ha, partials, p_net, grid, st);
+    if (H == 32 && kin == 24) return tc_launch<TCfg<32, 24, TRAIN, Head::OUT>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
+    if (H == 32 && kin == 56) return tc_launch<TCfg<32, 56, TRAIN, Head::OUT>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
+    if (H == 64 && kin == 24) return tc_launch<TCfg<64, 24, TRAIN, Head::OUT>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
+    if (H == 64 && kin == 56) return tc_launch<TCfg<64, 56, TRAIN, Head::OUT>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
     cmarl_set_error("tc dispatch: unsupported hidden=%d in_rows=%d", H, nd.in_rows);
     return -1;
 }
 
-template int cmarl_tc_dispatch<PolicyHead, true>(int, const NetDesc&, const TileSrc&, const PolicyHeadArgs&, float*, int, int, cudaStream_t);
-template int cmarl_tc_dispatch<ValueHead, true>(int, const NetDesc&, const TileSrc&, const ValueHeadArgs&, float*, int, int, cudaStream_t);
-template int cmarl_tc_dispatch<ValueHead, false>(int, const NetDesc&, const TileSrc&, const ValueHeadArgs&, float*, int, int, cudaStream_t);
+template int cmarl_tc_dispatch<PolicyHead, true>(const cmarl_ctx*, int, const NetDesc&, const TileSrc&, const PolicyHeadArgs&, float*, int, int, cudaStream_t);
+template int cmarl_tc_dispatch<ValueHead, true>(const cmarl_ctx*, int, const NetDesc&, const TileSrc&, const ValueHeadArgs&, float*, int, int, cudaStream_t);
+template int cmarl_tc_dispatch<ValueHead, false>(const cmarl_ctx*, int, const NetDesc&, const TileSrc&, const ValueHeadArgs&, float*, int, int, cudaStream_t);

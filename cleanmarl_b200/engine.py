@@ -131,6 +131,11 @@ class Engine:
         _lib.check(self.lib.cmarl_ctx_set_weight_decay(self._h, float(actor_wd), float(critic_wd)),
                    "cmarl_ctx_set_weight_decay")
 
+    def set_launch_chaining(self, on: bool):
+        """Programmatic dependent launches between consecutive kernels of this context (cmarl_ctx_set_launch_chaining):
+        on only between two launches of the library on one stream, off before foreign work is enqueued."""
+        _lib.check(self.lib.cmarl_ctx_set_launch_chaining(self._h, int(bool(on))), "cmarl_ctx_set_launch_chaining")
+
     def comm_setup(self, rank: int, world: int, group=None) -> bool:
         """Peer-memory gradient exchange: allocate + export this rank's block, gather every rank's IPC handle through
         ``torch.distributed`` and map the peers.  Afterwards the Adam entries exchange the gradients themselves.

@@ -302,21 +302,27 @@ class MAPPO:
         norm_flags = args.normalize_reward or args.normalize_advantage or args.normalize_return
         graph_ok = world_size == 1 or (self.comm == "p2p" and not norm_flags)
         self.use_graph = bool(use_graph) and graph_ok and engine_factory is Engine
+        # Launch chaining: after the first kernel of an iteration every launch is a programmatic dependent of the one in
+        # front of it (launch latency and kernel prologues hide under the predecessor; results unchanged).
+        self.chain = os.environ.get("CMARL_LAUNCH_CHAIN", "0") != "0"
         self._graphs = {}
         self._episode_dev = None
         self.launches_per_iteration = None                       # kernel nodes of the captured graph (library launches)
 
     # -- rollout -------------------------------------------------------------------------------
-    def collect(self, env_init=None, noise=None):
+    def collect(self, env_init=None, noise=None, chain=False):
         """MME:380-458.  ``env_init`` f64 [18][B] / ``noise`` f32 [T][N][A][B] make the rollout a
-        function of its inputs (parity, end-to-end benchmark); default: device Philox draws."""
+        function of its inputs (parity, end-to-end benchmark); default: device Philox draws.
+        ``chain``: switch launch chaining on behind the first kernel (the caller switches it off again)."""
         eng, buf = self.engine, self.buf
         if env_init is None:
             eng.env_reset(self.env, self.rng_key, self.episode)
+            eng.set_launch_chaining(chain)
         elif env_init is not self.env:
             self.env.copy_(env_init, non_blocking=True)
         eng.rollout(self.net.actor, self.env, buf["state"], buf["actions"], buf["logp"], buf["reward"], noise=noise,
                     ep_return=buf["ep_return"], seed=self.rng_key, episode=self.episode)
+        eng.set_launch_chaining(chain)
         if self._episode_dev is not None:
             eng.episode_advance()
         self.episode += 1
@@ -401,9 +407,12 @@ class MAPPO:
             self.training_step += 1
 
     def _iteration_eager(self, env_init=None, noise=None):
-        self.collect(env_init, noise)
-        self.advantages()
-        self.update()
+        try:
+            self.collect(env_init, noise, chain=self.chain)
+            self.advantages()
+            self.update()
+        finally:
+            self.engine.set_launch_chaining(False)
 
     def _counters(self):
         return (self.episode, self.step, self.num_episodes, self.training_step)
@@ -423,17 +432,22 @@ class MAPPO:
     def _launch_iteration(self, reset: bool):
         """The kernels of one iteration; ``reset`` False = start states were already written to ``self.env``."""
         eng, buf = self.engine, self.buf
-        if reset:
-            eng.env_reset(self.env, self.rng_key, self.episode)
-        eng.rollout(self.net.actor, self.env, buf["state"], buf["actions"], buf["logp"], buf["reward"],
-                    ep_return=buf["ep_return"], seed=self.rng_key, episode=self.episode)
-        if self._episode_dev is not None:
-            eng.episode_advance()
-        self.episode += 1
-        self.step += self.B * self.T * self.world
-        self.num_episodes += self.B * self.world
-        self.advantages()
-        self.update()
+        try:
+            if reset:
+                eng.env_reset(self.env, self.rng_key, self.episode)
+                eng.set_launch_chaining(self.chain)
+            eng.rollout(self.net.actor, self.env, buf["state"], buf["actions"], buf["logp"], buf["reward"],
+                        ep_return=buf["ep_return"], seed=self.rng_key, episode=self.episode)
+            eng.set_launch_chaining(self.chain)
+            if self._episode_dev is not None:
+                eng.episode_advance()
+            self.episode += 1
+            self.step += self.B * self.T * self.world
+            self.num_episodes += self.B * self.world
+            self.advantages()
+            self.update()
+        finally:
+            eng.set_launch_chaining(False)
 
     def iteration(self, env_init=None, noise=None):
         """One pass of the reference's outer loop.  Device-drawn noise (the default) replays a captured CUDA graph;

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CMARL_VERSION 101
+#define CMARL_VERSION 102
 #define CMARL_N_STATS 8          /* floats appended to the flat gradient vector, see cmarl_ppo_epoch_grads */
 #define CMARL_RAW_OBS 18
 
@@ -79,6 +79,14 @@ int cmarl_ctx_destroy(cmarl_ctx* ctx);
  * 1 = tcgen05 tensor cores, kind::tf32 with a 3-term split (fp32-level accuracy, csrc/tc_chain.cu);
  * 0 = fp32 FFMA block GEMMs (csrc/chain.cu).  Both produce the same quantities to the stated tolerances. */
 int cmarl_ctx_set_tensor_cores(cmarl_ctx* ctx, int on);
+/* Launch chaining (off initially): while on, every kernel this context launches carries CUDA's programmatic-stream-
+ * serialization attribute, i.e. it may become resident while the launch in front of it ON THE SAME STREAM is still
+ * running and blocks (griddepcontrol.wait) until that launch has completed before touching global memory -- launch
+ * latency and kernel prologues then hide under the predecessor.  Results are unchanged.  Contract for the caller:
+ * switch it on only between two launches of this library with nothing else enqueued on the stream in between
+ * (a training iteration after its first kernel, MME:379-594), and off again before enqueuing foreign work.
+ * Ignored while cmarl_timing_enable is on. */
+int cmarl_ctx_set_launch_chaining(cmarl_ctx* ctx, int on);
 /* Decoupled weight decay for cmarl_clip_adam_step / cmarl_adam_step_net: torch.optim.AdamW's param.mul_(1 - lr * wd)
  * before the Adam update (--optimizer AdamW, the default of ippo_lstm_multienvs.py:38; torch default wd = 0.01).
  * 0 (the initial value) = torch.optim.Adam. */

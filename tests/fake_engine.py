@@ -36,6 +36,9 @@ class OracleEngine:
         self.launches = 0
         self.weight_decay = (0.0, 0.0)
 
+    def set_launch_chaining(self, on):
+        pass                                        # a launch-scheduling hint of the CUDA library: no arithmetic
+
     def set_weight_decay(self, actor_wd, critic_wd):
         self.weight_decay = (float(actor_wd), float(critic_wd))
 

@@ -488,6 +488,29 @@ def test_graph_replay_equals_eager_launches(cm, recurrent, flags):
     assert torch.equal(tr.net.flat, tr2.net.flat) and torch.equal(tr.buf["actions"], tr2.buf["actions"])
 
 
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+@pytest.mark.parametrize("kind", ["mlp", "ippo", "recurrent", "mlp_flags"])
+def test_launch_chaining_changes_nothing(cm, kind, graph):
+    """Launch chaining (cmarl_ctx_set_launch_chaining: every kernel of an iteration a programmatic dependent of the one in
+    front of it) only moves launch latency and prologues under the predecessor: parameters, statistics and rollouts are
+    bit-identical to normally serialised launches, iteration after iteration (a kernel reading its predecessor's output
+    too early would show up here)."""
+    from cleanmarl_b200.mappo import MAPPO, Args, ArgsRecurrent
+    cls = ArgsRecurrent if kind == "recurrent" else Args
+    flags = dict(normalize_advantage=True, normalize_reward=True, clip_gradients=0.5) if kind == "mlp_flags" else {}
+    out = []
+    for chain in (False, True):
+        tr = MAPPO(cls(batch_size=4096 if kind == "mlp" else 640, seed=7, **flags), ippo=kind == "ippo", use_graph=graph)
+        tr.chain = chain
+        for _ in range(6):
+            tr.iteration()
+        torch.cuda.synchronize()
+        out.append((tr.net.flat.clone(), tr.exp_avg_sq.clone(), tr.epoch_stats.clone(), tr.buf["actions"].clone(),
+                    tr.buf["returns"].clone(), tr.buf["ep_return"].clone()))
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+
+
 # ----------------------------------------------------------------------------------------- full size / tiny size
 def test_full_size_iteration_properties(cm):
     """BASELINE's largest per-GPU size (65 536 envs, 1.6 M env-steps per rollout) through size-independent properties:
