@@ -91,50 +91,51 @@ struct ChunkArgs {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+template <int NT>
 __device__ void load_weights(float* sm, const ChunkArgs& a) {
-    const int NT = blockDim.x;
     const GruLayout& L = a.L;
-    const float* P = a.params;
+    const float* __restrict__ P = a.params;
     const int O = L.in;
-    for (int i = threadIdx.x; i < KIN * H; i += NT) {
+    // every loop is straight-line code (CMARL_STRIDED): the ~30 global loads of a thread are in flight together
+    CMARL_STRIDED(i, KIN * H, NT) {
         const int k = i / H, j = i - k * H;
-        sm[oW1T + i] = (k < a.in_rows) ? P[L.w1 + j * O + k] : 0.0f;
+        sm[oW1T + i] = (k < a.in_rows) ? __ldg(P + L.w1 + j * O + k) : 0.0f;
     }
-    for (int i = threadIdx.x; i < 4 * H; i += NT) {
+    CMARL_STRIDED(i, 4 * H, NT) {
         const int g = i / H, j = i - g * H;
-        float v = P[L.b1 + j];
-        if (a.fold_ids && g < a.N) v += P[L.w1 + j * O + a.in_rows + g];
+        float v = __ldg(P + L.b1 + j);
+        if (a.fold_ids && g < a.N) v += __ldg(P + L.w1 + j * O + a.in_rows + g);
         sm[oB1 + i] = v;
     }
-    for (int i = threadIdx.x; i < 2 * H * H; i += NT) {
+    CMARL_STRIDED(i, 2 * H * H, NT) {
         const int k = i / H, j = i - k * H;           // k: input index (x1 then h), j: unit
         const float* W = (k < H) ? P + L.wih : P + L.whh;
         const int kk = (k < H) ? k : k - H;
         float4 w;
-        w.x = W[(0 * H + j) * H + kk];
-        w.y = W[(1 * H + j) * H + kk];
-        w.z = W[(2 * H + j) * H + kk];
+        w.x = __ldg(W + (0 * H + j) * H + kk);
+        w.y = __ldg(W + (1 * H + j) * H + kk);
+        w.z = __ldg(W + (2 * H + j) * H + kk);
         w.w = 0.0f;
         *reinterpret_cast<float4*>(sm + oWgT + (size_t)i * 4) = w;
     }
-    for (int j = threadIdx.x; j < H; j += NT) {
+    CMARL_STRIDED(j, H, NT) {
         float4 b;
-        b.x = P[L.bih + j] + P[L.bhh + j];
-        b.y = P[L.bih + H + j] + P[L.bhh + H + j];
-        b.z = P[L.bih + 2 * H + j];
-        b.w = P[L.bhh + 2 * H + j];
+        b.x = __ldg(P + L.bih + j) + __ldg(P + L.bhh + j);
+        b.y = __ldg(P + L.bih + H + j) + __ldg(P + L.bhh + H + j);
+        b.z = __ldg(P + L.bih + 2 * H + j);
+        b.w = __ldg(P + L.bhh + 2 * H + j);
         *reinterpret_cast<float4*>(sm + oBg + j * 4) = b;
     }
-    for (int i = threadIdx.x; i < G3 * H; i += NT) {
+    CMARL_STRIDED(i, G3 * H, NT) {
         const int row = i / H, k = i - row * H;
-        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + (k & 1)] = P[L.wih + i];
-        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + 2 + (k & 1)] = P[L.whh + i];
+        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + (k & 1)] = __ldg(P + L.wih + i);
+        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + 2 + (k & 1)] = __ldg(P + L.whh + i);
     }
-    for (int i = threadIdx.x; i < H * 8; i += NT) {
+    CMARL_STRIDED(i, H * 8, NT) {
         const int j = i / 8, c = i - j * 8;
-        sm[oW2T + i] = (c < NA) ? P[L.w2 + c * H + j] : 0.0f;
+        sm[oW2T + i] = (c < NA) ? __ldg(P + L.w2 + c * H + j) : 0.0f;
     }
-    if (threadIdx.x < 8) sm[oB2 + threadIdx.x] = (threadIdx.x < NA) ? P[L.b2 + threadIdx.x] : 0.0f;
+    if (threadIdx.x < 8) sm[oB2 + threadIdx.x] = (threadIdx.x < NA) ? __ldg(P + L.b2 + threadIdx.x) : 0.0f;
 }
 
 // input rows of (t, g, b0) -> xbuf; full aligned tiles by TMA bulk copies, ragged ones by guarded loads
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a)
         mbar_fence_init();
     }
     pdl_wait_then_trigger();
-    load_weights(sm, a);
+    load_weights<NT>(sm, a);
     __syncthreads();
 
     float* dW = sm + oDW;

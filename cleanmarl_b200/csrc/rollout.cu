@@ -246,36 +246,36 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
     const int j0 = qq * JL;
 
     pdl_wait_then_trigger();
-    for (int i = tid; i < 18 * REPB; i += NTHR) {
+    CMARL_STRIDED(i, 18 * REPB, NTHR) {
         const int r = i / REPB, c = i - r * REPB;
         const int bb = blockIdx.x * REPB + c;
         es[r][c] = (bb < B) ? a.env[(size_t)r * B + bb] : 0.0;
     }
     {
-        const float* P = a.actor;
-        for (int i = tid; i < H * W1LD; i += NTHR) {
+        const float* __restrict__ P = a.actor;
+        CMARL_STRIDED(i, H * W1LD, NTHR) {
             const int j = i / W1LD, k = i - j * W1LD;
-            sw[sW1 + i] = (k < CMARL_RAW_OBS - 4) ? P[pW1 + j * O + k] : 0.0f;
+            sw[sW1 + i] = (k < CMARL_RAW_OBS - 4) ? __ldg(P + pW1 + j * O + k) : 0.0f;
         }
-        for (int i = tid; i < NAG * H; i += NTHR) {
+        CMARL_STRIDED(i, NAG * H, NTHR) {
             const int g = i / H, j = i - g * H;
-            sw[sB1 + i] = P[pB1 + j] + (FOLD ? P[pW1 + j * O + CMARL_RAW_OBS + g] : 0.0f);   // one-hot id column of agent g
+            sw[sB1 + i] = __ldg(P + pB1 + j) + (FOLD ? __ldg(P + pW1 + j * O + CMARL_RAW_OBS + g) : 0.0f);   // one-hot id column of agent g
         }
         if (GRU) {
-            for (int i = tid; i < 3 * H * H; i += NTHR) { sw[RL::sWih + i] = P[RL::pWih + i]; sw[RL::sWhh + i] = P[RL::pWhh + i]; }
-            for (int j = tid; j < H; j += NTHR) {     // bir + bhr, biz + bhz, bin, bhn
-                sw[RL::sBg + 4 * j + 0] = P[RL::pBih + j] + P[RL::pBhh + j];
-                sw[RL::sBg + 4 * j + 1] = P[RL::pBih + H + j] + P[RL::pBhh + H + j];
-                sw[RL::sBg + 4 * j + 2] = P[RL::pBih + 2 * H + j];
-                sw[RL::sBg + 4 * j + 3] = P[RL::pBhh + 2 * H + j];
+            CMARL_STRIDED(i, 3 * H * H, NTHR) { sw[RL::sWih + i] = __ldg(P + RL::pWih + i); sw[RL::sWhh + i] = __ldg(P + RL::pWhh + i); }
+            CMARL_STRIDED(j, H, NTHR) {     // bir + bhr, biz + bhz, bin, bhn
+                sw[RL::sBg + 4 * j + 0] = __ldg(P + RL::pBih + j) + __ldg(P + RL::pBhh + j);
+                sw[RL::sBg + 4 * j + 1] = __ldg(P + RL::pBih + H + j) + __ldg(P + RL::pBhh + H + j);
+                sw[RL::sBg + 4 * j + 2] = __ldg(P + RL::pBih + 2 * H + j);
+                sw[RL::sBg + 4 * j + 3] = __ldg(P + RL::pBhh + 2 * H + j);
             }
             for (int i = tid; i < 2 * NAG * H * REPB; i += NTHR) (&hs[0][0][0][0])[i] = 0.0f;   // h = None
         } else {
-            for (int i = tid; i < H * H; i += NTHR) sw[sW2 + i] = P[pW2 + i];
-            for (int i = tid; i < H; i += NTHR) sw[sB2 + i] = P[pB2 + i];
+            CMARL_STRIDED(i, H * H, NTHR) sw[sW2 + i] = __ldg(P + pW2 + i);
+            CMARL_STRIDED(i, H, NTHR) sw[sB2 + i] = __ldg(P + pB2 + i);
         }
-        for (int i = tid; i < NACT * H; i += NTHR) sw[sW3 + i] = P[pW3 + i];
-        if (tid < 8) sw[sB3 + tid] = tid < NACT ? P[pB3 + tid] : 0.0f;
+        CMARL_STRIDED(i, NACT * H, NTHR) sw[sW3 + i] = __ldg(P + pW3 + i);
+        if (tid < 8) sw[sB3 + tid] = tid < NACT ? __ldg(P + pB3 + tid) : 0.0f;
     }
     __syncthreads();
     double ep_acc = 0.0;                                     // threads 0..REPB-1: episode return of env tid

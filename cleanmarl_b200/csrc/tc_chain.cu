@@ -145,9 +145,13 @@ __device__ __forceinline__ void issue_ss(bool leader, uint32_t d, uint32_t a_hi,
 // ------------------------------------------------------------------------------------------------
 // Weights -> shared memory images (hi | lo)
 // ------------------------------------------------------------------------------------------------
+// Every global load of a thread is issued before the first value is used: as a plain strided loop the compiler keeps one
+// load in flight per iteration, i.e. ~27 serial L2 round trips (~12 us) in front of the critic chain's first tile.
 template <class C>
 __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
-    constexpr int H = C::H, K1P = C::K1P;
+    constexpr int H = C::H, K1P = C::K1P, NT = 288;
+    constexpr int N1 = (H * K1P + NT - 1) / NT, N2 = (H * H + NT - 1) / NT, N3 = (H * 8 + NT - 1) / NT;
+    static_assert(4 * H <= NT, "one b1 element per thread");
     const float* P = nd.params;
     const int in_dim = nd.in_dim;
     const float* W1 = P;
@@ -156,44 +160,67 @@ __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
     const float* b2 = W2 + H * H;
     const float* W3 = b2 + H;
     const float* b3 = W3 + nd.out_dim * H;
-    for (int i = threadIdx.x; i < H * K1P; i += 288) {
-        const int j = i / K1P, k = i - j * K1P;
-        const float w = (k < nd.in_rows) ? W1[j * in_dim + k] : 0.0f;
-        float hi, lo;
-        tc::split_tf32(w, hi, lo);
-        const int o = kmaj(j, k, K1P);
-        *reinterpret_cast<float*>(sm + C::oW1 + o) = hi;
-        *reinterpret_cast<float*>(sm + C::oW1 + C::szW1 + o) = lo;
+    const int tid = threadIdx.x;
+    float w1[N1], w2[N2], w3[N3], vb1 = 0.0f, vid = 0.0f, vb2 = 0.0f, vb3 = 0.0f;
+#pragma unroll
+    for (int r = 0; r < N1; ++r) {
+        const int i = tid + r * NT, j = i / K1P, k = i - j * K1P;
+        w1[r] = (i < H * K1P && k < nd.in_rows) ? __ldg(W1 + j * in_dim + k) : 0.0f;
     }
-    for (int i = threadIdx.x; i < H * H; i += 288) {
-        const int j = i / H, k = i - j * H;
-        float hi, lo;
-        tc::split_tf32(W2[i], hi, lo);
-        const int o = kmaj(j, k, H);                     // B of F2: N = j, K = k
-        *reinterpret_cast<float*>(sm + C::oW2 + o) = hi;
-        *reinterpret_cast<float*>(sm + C::oW2 + C::szW2 + o) = lo;
-        if (C::TRAIN) {
-            const int ot = kmaj(k, j, H);                // B of B1: N = k, K = j
-            *reinterpret_cast<float*>(sm + C::oW2T + ot) = hi;
-            *reinterpret_cast<float*>(sm + C::oW2T + C::szW2 + ot) = lo;
+#pragma unroll
+    for (int r = 0; r < N2; ++r) {
+        const int i = tid + r * NT;
+        w2[r] = i < H * H ? __ldg(W2 + i) : 0.0f;
+    }
+#pragma unroll
+    for (int r = 0; r < N3; ++r) {
+        const int i = tid + r * NT, j = i / 8, a = i - j * 8;
+        w3[r] = (i < H * 8 && a < nd.out_dim) ? __ldg(W3 + a * H + j) : 0.0f;
+    }
+    if (tid < 4 * H) {
+        const int g = tid / H, j = tid - g * H;
+        vb1 = __ldg(b1 + j);
+        if (nd.fold_ids && g < n_groups) vid = __ldg(W1 + j * in_dim + nd.in_rows + g);
+    }
+    if (tid < H) vb2 = __ldg(b2 + tid);
+    if (tid < 8 && tid < nd.out_dim) vb3 = __ldg(b3 + tid);
+
+#pragma unroll
+    for (int r = 0; r < N1; ++r) {
+        const int i = tid + r * NT, j = i / K1P, k = i - j * K1P;
+        if (i < H * K1P) {
+            float hi, lo;
+            tc::split_tf32(w1[r], hi, lo);
+            const int o = kmaj(j, k, K1P);
+            *reinterpret_cast<float*>(sm + C::oW1 + o) = hi;
+            *reinterpret_cast<float*>(sm + C::oW1 + C::szW1 + o) = lo;
         }
     }
-    float* fb1 = reinterpret_cast<float*>(sm + C::oB1);
-    for (int i = threadIdx.x; i < 4 * H; i += 288) {
-        const int g = i / H, j = i - g * H;
-        float v = b1[j];
-        if (nd.fold_ids && g < n_groups) v += W1[j * in_dim + nd.in_rows + g];
-        fb1[i] = v;
+#pragma unroll
+    for (int r = 0; r < N2; ++r) {
+        const int i = tid + r * NT, j = i / H, k = i - j * H;
+        if (i < H * H) {
+            float hi, lo;
+            tc::split_tf32(w2[r], hi, lo);
+            const int o = kmaj(j, k, H);                     // B of F2: N = j, K = k
+            *reinterpret_cast<float*>(sm + C::oW2 + o) = hi;
+            *reinterpret_cast<float*>(sm + C::oW2 + C::szW2 + o) = lo;
+            if (C::TRAIN) {
+                const int ot = kmaj(k, j, H);                // B of B1: N = k, K = j
+                *reinterpret_cast<float*>(sm + C::oW2T + ot) = hi;
+                *reinterpret_cast<float*>(sm + C::oW2T + C::szW2 + ot) = lo;
+            }
+        }
     }
-    float* fb2 = reinterpret_cast<float*>(sm + C::oB2);
-    for (int i = threadIdx.x; i < H; i += 288) fb2[i] = b2[i];
     float* fw3 = reinterpret_cast<float*>(sm + C::oW3T);
-    for (int i = threadIdx.x; i < H * 8; i += 288) {
-        const int j = i / 8, a = i - j * 8;
-        fw3[i] = (a < nd.out_dim) ? W3[a * H + j] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < N3; ++r) {
+        const int i = tid + r * NT;
+        if (i < H * 8) fw3[i] = w3[r];
     }
-    float* fb3 = reinterpret_cast<float*>(sm + C::oB3);
-    if (threadIdx.x < 8) fb3[threadIdx.x] = (threadIdx.x < nd.out_dim) ? b3[threadIdx.x] : 0.0f;
+    if (tid < 4 * H) reinterpret_cast<float*>(sm + C::oB1)[tid] = vb1 + vid;
+    if (tid < H) reinterpret_cast<float*>(sm + C::oB2)[tid] = vb2;
+    if (tid < 8) reinterpret_cast<float*>(sm + C::oB3)[tid] = vb3;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -445,29 +472,44 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             const typename Head::In hin = Head::load(ha, t, g, b, src.G, src.B, inb && hf == 0);
 
             // ---- E1: H1 = relu(D1 + b1[g]) -> split -> TMEM A ---------------------------------------------
+            // (every asm statement is a compiler barrier for memory operations: shared-memory constants are read BEFORE the
+            // wait / TMEM load they would otherwise queue behind, so their latency hides under it)
+            float bv1[NOWN][16];
+            auto load_b1 = [&]() {
+#pragma unroll
+                for (int ci = 0; ci < NOWN; ++ci) {
+#pragma unroll
+                    for (int i4 = 0; i4 < 16; i4 += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(fb1 + g * H + 16 * (2 * ci + hf) + i4);
+                        bv1[ci][i4] = bb.x; bv1[ci][i4 + 1] = bb.y; bv1[ci][i4 + 2] = bb.z; bv1[ci][i4 + 3] = bb.w;
+                    }
+                }
+            };
+            load_b1();
             acquire(&bars[D_F1], par);
             TL_STAMP(2);
             uint32_t h1h[NOWN][16], h1l[NOWN][16];                       // kept for the sample-major copies
+            {
+                uint32_t v[NOWN][16];
 #pragma unroll
-            for (int ci = 0; ci < NOWN; ++ci) {
-                const int c0 = 16 * (2 * ci + hf);
-                uint32_t v[16];
-                tc::tmem_ld16(tl + C::cD1 + c0, v);
+                for (int ci = 0; ci < NOWN; ++ci) tc::tmem_ld16(tl + C::cD1 + 16 * (2 * ci + hf), v[ci]);
                 tc::tmem_wait_ld();
 #pragma unroll
-                for (int i4 = 0; i4 < 16; i4 += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(fb1 + g * H + c0 + i4);
-                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                for (int ci = 0; ci < NOWN; ++ci) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float h1 = fmaxf(__uint_as_float(v[i4 + e]) + bv[e], 0.0f);
+                    for (int i = 0; i < 16; ++i) {
+                        const float h1 = fmaxf(__uint_as_float(v[ci][i]) + bv1[ci][i], 0.0f);
                         float h, l;
                         tc::split_tf32(h1, h, l);
-                        h1h[ci][i4 + e] = __float_as_uint(h); h1l[ci][i4 + e] = __float_as_uint(l);
+                        h1h[ci][i] = __float_as_uint(h); h1l[ci][i] = __float_as_uint(l);
                     }
                 }
-                tmem_st16(tl + C::cAh + c0, h1h[ci]);
-                tmem_st16(tl + C::cAl + c0, h1l[ci]);
+#pragma unroll
+                for (int ci = 0; ci < NOWN; ++ci) {
+                    const int c0 = 16 * (2 * ci + hf);
+                    tmem_st16(tl + C::cAh + c0, h1h[ci]);
+                    tmem_st16(tl + C::cAl + c0, h1l[ci]);
+                }
             }
             publish(&bars[R_H1]);
             TL_STAMP(3);
@@ -484,27 +526,33 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
 
             // ---- E2: H2, output layer, head ---------------------------------------------------------------
             TL_STAMP(4);
+            float bv2[NOWN][16];
+#pragma unroll
+            for (int ci = 0; ci < NOWN; ++ci) {
+#pragma unroll
+                for (int i4 = 0; i4 < 16; i4 += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(fb2 + 16 * (2 * ci + hf) + i4);
+                    bv2[ci][i4] = bb.x; bv2[ci][i4 + 1] = bb.y; bv2[ci][i4 + 2] = bb.z; bv2[ci][i4 + 3] = bb.w;
+                }
+            }
             acquire(&bars[D_F2], par);
             TL_STAMP(5);
             float h2[NOWN * 16];
             float z[OUT], dz[OUT];
 #pragma unroll
             for (int a = 0; a < OUT; ++a) z[a] = 0.0f;
+            {
+                uint32_t v[NOWN][16];
 #pragma unroll
-            for (int ci = 0; ci < NOWN; ++ci) {
-                const int c0 = 16 * (2 * ci + hf);
-                uint32_t v[16];
-                tc::tmem_ld16(tl + C::cD2 + c0, v);
+                for (int ci = 0; ci < NOWN; ++ci) tc::tmem_ld16(tl + C::cD2 + 16 * (2 * ci + hf), v[ci]);
                 tc::tmem_wait_ld();
 #pragma unroll
-                for (int i4 = 0; i4 < 16; i4 += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(fb2 + c0 + i4);
-                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                for (int ci = 0; ci < NOWN; ++ci) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = c0 + i4 + e;
-                        const float hv = fmaxf(__uint_as_float(v[i4 + e]) + bv[e], 0.0f);
-                        h2[ci * 16 + i4 + e] = hv;
+                    for (int i = 0; i < 16; ++i) {
+                        const int j = 16 * (2 * ci + hf) + i;
+                        const float hv = fmaxf(__uint_as_float(v[ci][i]) + bv2[ci][i], 0.0f);
+                        h2[ci * 16 + i] = hv;
                         if (OUT > 1) {
                             const float4 w = *reinterpret_cast<const float4*>(fw3 + j * 8);
                             const float w4 = fw3[j * 8 + 4];
@@ -545,7 +593,9 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             TL_STAMP(6);
 
             if (TRAIN) {
-                // dH2 = (W3^T dz) . relu'(H2) -> split -> TMEM A (operand of B1) + sample-major A image (operand of dW2)
+                // dH2 = (W3^T dz) . relu'(H2) -> split -> TMEM A (operand of B1) + sample-major A image (operand of dW2).
+                // A chunk of 16 is computed before its first store: a shared-memory store in between would pin every later
+                // W3 load behind it (the compiler cannot prove they do not alias) and serialise 16 LDS round trips per chunk.
 #pragma unroll
                 for (int ci = 0; ci < NOWN; ++ci) {
                     const int c0 = 16 * (2 * ci + hf);
@@ -569,8 +619,11 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                         float h, l;
                         tc::split_tf32(d, h, l);
                         hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(l);
-                        *reinterpret_cast<uint32_t*>(As_h + smaj(j, 0) + so) = hi[i];
-                        *reinterpret_cast<uint32_t*>(As_l + smaj(j, 0) + so) = lo[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        *reinterpret_cast<uint32_t*>(As_h + smaj(c0 + i, 0) + so) = hi[i];
+                        *reinterpret_cast<uint32_t*>(As_l + smaj(c0 + i, 0) + so) = lo[i];
                     }
                     tmem_st16(tl + C::cAh + c0, hi);
                     tmem_st16(tl + C::cAl + c0, lo);
@@ -598,6 +651,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 TL_STAMP(7);
 
                 // ---- E3: dH1 = D3 . relu'(H1) (H1 > 0 <=> D1 + b1 > 0) --------------------------------------
+                load_b1();
                 acquire(&bars[D_B1], par);
                 TL_STAMP(9);
                 float dh1[NOWN * 16];
@@ -610,18 +664,13 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                     tc::tmem_ld16(tl + C::cD1 + c0, d1);
                     tc::tmem_wait_ld();
 #pragma unroll
-                    for (int i4 = 0; i4 < 16; i4 += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(fb1 + g * H + c0 + i4);
-                        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float pre = __uint_as_float(d1[i4 + e]) + bv[e];
-                            dh1[ci * 16 + i4 + e] = pre > 0.0f ? __uint_as_float(v[i4 + e]) : 0.0f;
-                            if (C::NR2 == 2 && ci == 1) {
-                                float h, l;
-                                tc::split_tf32(fmaxf(pre, 0.0f), h, l);
-                                r1h[i4 + e] = __float_as_uint(h); r1l[i4 + e] = __float_as_uint(l);
-                            }
+                    for (int i = 0; i < 16; ++i) {
+                        const float pre = __uint_as_float(d1[i]) + bv1[ci][i];
+                        dh1[ci * 16 + i] = pre > 0.0f ? __uint_as_float(v[i]) : 0.0f;
+                        if (C::NR2 == 2 && ci == 1) {
+                            float h, l;
+                            tc::split_tf32(fmaxf(pre, 0.0f), h, l);
+                            r1h[i] = __float_as_uint(h); r1l[i] = __float_as_uint(l);
                         }
                     }
                 }
@@ -685,22 +734,30 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 {
                     const int cb = hf == 0 ? C::cW2 : C::cW1;
                     const int cn = hf == 0 ? C::nW2 : C::nW1;
+                    constexpr int FU = 5;                                // 8-column chunks in flight (cn = 40 or 72)
 #pragma unroll 1
-                    for (int c = 0; c < cn; c += 8) {
-                        uint32_t v[8];
-                        tc::tmem_ld8(tl + cb + c, v);
+                    for (int c = 0; c < cn; c += 8 * FU) {
+                        uint32_t v[FU][8];
+#pragma unroll
+                        for (int k = 0; k < FU; ++k)
+                            if (c + 8 * k < cn) tc::tmem_ld8(tl + cb + c + 8 * k, v[k]);      // warp-uniform guard
                         tc::tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float part = __shfl_sync(0xffffffffu, __uint_as_float(v[i]), lane & 15);
-                            if (lane >= 16) v[i] = __float_as_uint(__uint_as_float(v[i]) + part);
+                        for (int k = 0; k < FU; ++k) {
+                            if (c + 8 * k < cn) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float part = __shfl_sync(0xffffffffu, __uint_as_float(v[k][i]), lane & 15);
+                                    if (lane >= 16) v[k][i] = __float_as_uint(__uint_as_float(v[k][i]) + part);
+                                }
+                                // folded one-hot id column of this agent group: gradient = bias-gradient column of dW1
+                                if (nd.fold_ids && hf == 1 && c + 8 * k == 32 * C::NR1 && lane < 16) {
+                                    const int row = q * 16 + lane;
+                                    if (row < H) didacc[g * H + row] += __uint_as_float(v[k][0]);
+                                }
+                                tmem_st8(tl + cb + c + 8 * k, v[k]);
+                            }
                         }
-                        // folded one-hot id column of this agent group: gradient = bias-gradient column of dW1
-                        if (nd.fold_ids && hf == 1 && c == 32 * C::NR1 && lane < 16) {
-                            const int row = q * 16 + lane;
-                            if (row < H) didacc[g * H + row] += __uint_as_float(v[0]);
-                        }
-                        tmem_st8(tl + cb + c, v);
                     }
                     tc::tmem_wait_st();
                     TL_STAMP(18);
@@ -726,19 +783,31 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 const int row = q * 16 + (lane - 16);               // gradient row j held by this lane
                 const bool valid = lane >= 16 && row < H;
                 if (hf == 0) {
-                    for (int c = 0; c < C::nW2; ++c) {
-                        const float v = __uint_as_float(tc::tmem_ld1(tl + C::cW2 + c));
-                        if (valid) {
-                            if (c < H) gW2[row * H + c] = v;
-                            else if (c == 32 * C::NR2) gb2[row] = v;
+#pragma unroll 1
+                    for (int c = 0; c < C::nW2; c += 8) {
+                        uint32_t v[8];
+                        tc::tmem_ld8(tl + C::cW2 + c, v);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (valid) {
+                                if (c + i < H) gW2[row * H + c + i] = __uint_as_float(v[i]);
+                                else if (c + i == 32 * C::NR2) gb2[row] = __uint_as_float(v[i]);
+                            }
                         }
                     }
                 } else {
-                    for (int c = 0; c < C::nW1; ++c) {
-                        const float v = __uint_as_float(tc::tmem_ld1(tl + C::cW1 + c));
-                        if (valid) {
-                            if (c < nd.in_rows) gW1[row * in_dim + c] = v;
-                            else if (c == 32 * C::NR1) gb1[row] = v;
+#pragma unroll 1
+                    for (int c = 0; c < C::nW1; c += 8) {
+                        uint32_t v[8];
+                        tc::tmem_ld8(tl + C::cW1 + c, v);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (valid) {
+                                if (c + i < nd.in_rows) gW1[row * in_dim + c + i] = __uint_as_float(v[i]);
+                                else if (c + i == 32 * C::NR1) gb1[row] = __uint_as_float(v[i]);
+                            }
                         }
                     }
                 }
