@@ -107,20 +107,22 @@ __device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
 // MMA issue: called by the whole (converged) issue warp so that descriptors stay in uniform registers; one
 // elected lane executes each tcgen05.mma.  3xTF32 pass order: (lo,hi), (hi,lo), (hi,hi).
 // ------------------------------------------------------------------------------------------------
+// The loops stay ROLLED (two MMAs per iteration): fully unrolled, the 261 MMAs of a critic tile are 36 KB of straight-line
+// code that the issue warp streams through the instruction cache once per tile, next to the compute warps' own ~90 KB.
 // D[128 x N] = A(TMEM, K columns at a_hi / a_lo) * B(smem K-major image [N][K])^T
 template <int N, int K>
 __device__ __forceinline__ void issue_ts(bool leader, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
     constexpr uint32_t idesc = tc::make_idesc_tf32(128, N, 0, 0);
     constexpr uint32_t sbo = (K / 4) * LBO_K;
-    uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 1
     for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = pass == 0 ? a_lo : a_hi;
-        const uint64_t db0 = tc::make_smem_desc(pass == 1 ? b_lo : b_hi, LBO_K, sbo, 0);
-#pragma unroll
+        uint32_t a = pass == 0 ? a_lo : a_hi;
+        uint64_t db = tc::make_smem_desc(pass == 1 ? b_lo : b_hi, LBO_K, sbo, 0);
+#pragma unroll 2
         for (int ks = 0; ks < K / 8; ++ks) {
-            if (leader) tc::mma_tf32_ts(d, a + ks * 8, db0 + (uint64_t)((ks * 2 * LBO_K) >> 4), idesc, acc);
-            acc = 1;
+            if (leader) tc::mma_tf32_ts(d, a, db, idesc, (uint32_t)(pass | ks));
+            a += 8;
+            db += (uint64_t)((2 * LBO_K) >> 4);
         }
     }
 }
@@ -128,16 +130,15 @@ __device__ __forceinline__ void issue_ts(bool leader, uint32_t d, uint32_t a_hi,
 template <int N>
 __device__ __forceinline__ void issue_ss(bool leader, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
     constexpr uint32_t idesc = tc::make_idesc_tf32(64, N, 0, 0);
-    uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 1
     for (int pass = 0; pass < 3; ++pass) {
-        const uint64_t da0 = tc::make_smem_desc(pass == 0 ? a_lo : a_hi, LBO_S, SBO_S, 0);
-        const uint64_t db0 = tc::make_smem_desc(pass == 1 ? b_lo : b_hi, LBO_S, SBO_S, 0);
-#pragma unroll
+        uint64_t da = tc::make_smem_desc(pass == 0 ? a_lo : a_hi, LBO_S, SBO_S, 0);
+        uint64_t db = tc::make_smem_desc(pass == 1 ? b_lo : b_hi, LBO_S, SBO_S, 0);
+#pragma unroll 2
         for (int ks = 0; ks < M / 8; ++ks) {
-            const uint64_t off = (uint64_t)((ks * KSTEP_S) >> 4);
-            if (leader) tc::mma_tf32(d, da0 + off, db0 + off, idesc, acc);
-            acc = 1;
+            if (leader) tc::mma_tf32(d, da, db, idesc, (uint32_t)(pass | ks));
+            da += (uint64_t)(KSTEP_S >> 4);
+            db += (uint64_t)(KSTEP_S >> 4);
         }
     }
 }

@@ -38,6 +38,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // returns 0 if the phase did not complete within `spins` polls (diagnostics: never hang the GPU)
 __device__ __forceinline__ int mbar_wait_bounded(uint64_t* bar, uint32_t parity, uint32_t spins) {
+    // a rolled loop: unrolled polls are straight-line code a waiting warp walks through, evicting the tile loop from the
+    // instruction cache (ncu: "no instruction" was the second largest stall reason of the critic chain)
+#pragma unroll 1
     for (uint32_t i = 0; i < spins; ++i)
         if (mbar_try_wait(bar, parity)) return 1;
     return 0;
@@ -174,9 +177,17 @@ __device__ __forceinline__ float tf32_rna(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// cvt.rna.tf32.f32 for FINITE x in two integer instructions: add half a tf32 ulp to the magnitude bits, drop the low 13
+// bits (round to nearest, ties away; a mantissa carry moves into the exponent as it should).  ptxas expands the cvt into
+// the same two plus an inf/nan test and a select -- 9 instructions per split instead of 5, and the splits are a third of
+// the chain kernels' compute-warp instructions.  Bit-identical for finite inputs; a non-finite activation is garbage
+// on either path.
+__device__ __forceinline__ float tf32_rna_finite(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = tf32_rna(x);
-    lo = tf32_rna(x - hi);
+    hi = tf32_rna_finite(x);
+    lo = tf32_rna_finite(x - hi);
 }
 // makes the mbarrier track completion of all MMAs issued so far by this thread (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
