@@ -346,6 +346,10 @@ static int run_chain(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileS
     const int slots = ctx->sm_count * (ctx->use_tc ? cmarl_tc_ctas_per_sm(H, nd.in_rows, TRAIN, Head::OUT) : 1);
     const int grid = units < slots ? units : slots;
     if (grid_out) *grid_out = grid;
+    if (ctx->use_tc && units >= (1 << 24)) {      // tc_chain_kernel decodes tile indices with fast_divmod (exact below 2^24)
+        cmarl_set_error("chain: %d tiles in one launch (limit 2^24)", units);
+        return -1;
+    }
     if (ctx->use_tc) return cmarl_tc_dispatch<Head, TRAIN>(ctx, H, nd, src, ha, partials, p_net, grid, st);
     return dispatch<Head, TRAIN>(ctx, H, nd, src, ha, partials, p_net, grid, st);
 }

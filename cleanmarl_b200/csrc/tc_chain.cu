@@ -98,6 +98,15 @@ __device__ __forceinline__ int smaj(int r, int s) { return (r >> 3) * SBO_S + (r
 // byte offset of element (row n, k) in a K-major weight image with KTOT columns
 __device__ __forceinline__ int kmaj(int n, int k, int ktot) { return (n >> 3) * (ktot / 4) * LBO_K + (n & 7) * 16 + (k >> 2) * LBO_K + (k & 3) * 4; }
 
+// u / d and u % d for u < 2^24 from a precomputed 1.0f / d (the estimate is within one of the quotient; the compiler's
+// own 32-bit division is ~30 instructions, and every tile decodes its index twice)
+__device__ __forceinline__ void fast_divmod(int u, int d, float inv, int& q, int& r) {
+    q = __float2int_rz(__int2float_rz(u) * inv);
+    r = u - q * d;
+    if (r < 0) { --q; r += d; }
+    else if (r >= d) { ++q; r -= d; }
+}
+
 __device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
     // bounded: a descriptor / protocol bug must surface as a launch failure, never as a hung GPU
     if (!tc::mbar_wait_bounded(bar, parity, 1u << 26)) __trap();
@@ -301,6 +310,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::oBar + N_BARS * 8);
     const int tiles_b = (src.B + M - 1) / M;
     const int units = src.T * src.G * tiles_b;
+    const float inv_tb = 1.0f / (float)tiles_b, inv_g = 1.0f / (float)src.G;
 
     // ---- one-time setup (all 288 threads) -------------------------------------------------------------
     // first what touches no global memory: under launch chaining this part runs while the kernel in front still does
@@ -417,17 +427,21 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         // X chunks owned by this thread: chunk c = 2 i + hf, i < NXO (chunks >= NCX do not exist)
         float xr[NXO * 8];
         auto load_x = [&](int u) {
-            const int bt = u % tiles_b, r = u / tiles_b;
-            const int t = r / src.G, g = r % src.G;
+            int bt, r, t, g;
+            fast_divmod(u, tiles_b, inv_tb, r, bt);
+            fast_divmod(r, src.G, inv_g, t, g);
             const int b = bt * M + s;
+            // 32-bit row offsets from one 64-bit base and one bound per thread: ~5 instructions per load (the 64-bit
+            // products and double predicates of the obvious form were 14, a fifth of the critic kernel's instructions)
             const float* xp = src.x + (size_t)t * src.stride_t + (size_t)g * src.stride_g + b + (size_t)(8 * hf) * src.B;
-            const size_t step = (size_t)src.B;
+            const uint32_t step = (uint32_t)src.B;
+            const int rmax = (b < src.B) ? nd.in_rows - 8 * hf : 0;     // this thread reads rows 16 i + e < rmax of its half
 #pragma unroll
             for (int i = 0; i < NXO; ++i) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int k = 16 * i + 8 * hf + e;
-                    xr[i * 8 + e] = (b < src.B && k < nd.in_rows) ? __ldg(xp + (size_t)(16 * i + e) * step) : 0.0f;
+                    const int rr = 16 * i + e;
+                    xr[i * 8 + e] = (rr < rmax) ? __ldg(xp + (uint32_t)rr * step) : 0.0f;
                 }
             }
         };
@@ -461,8 +475,9 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         uint32_t par = 0;
         int it = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x, par ^= 1, ++it) {
-            const int bt = u % tiles_b, r = u / tiles_b;
-            const int t = r / src.G, g = r % src.G;
+            int bt, r, t, g;
+            fast_divmod(u, tiles_b, inv_tb, r, bt);
+            fast_divmod(r, src.G, inv_g, t, g);
             const int b = bt * M + s;
             const bool inb = b < src.B;
             const bool tl_on = g_tc_timeline_on == (OUT > 1 ? 2 : 1) && blockIdx.x == 0 && it == 1 && tid == 0;
