@@ -236,3 +236,69 @@ def test_two_ranks_gloo_equal_one_rank(tmp_path, flags):
     assert (r0["params"] - tr.net.flat).abs().max() < 2e-6
     assert (r0["stats"] - tr.epoch_stats).abs().max() < 1e-4 * tr.epoch_stats.abs().max()
     assert abs(r0["ep_reward"] - tr.rollout_scalars()["ep_reward"]) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------ the script's outer loop
+def test_cli_main_loop_logs_like_the_reference(tmp_path, monkeypatch):
+    """The drop-in script's ``while step < total_timesteps`` loop on the CPU double with a recording writer: tag names,
+    x-axis (env steps, MME:435) and cadence of MME:454-468 (mean over ALL episodes pending since the last line, logged
+    once more than ``log_every`` are pending), MME:605-612 (eight train scalars every iteration) and MME:614 (eval when
+    ``training_step / epochs`` is a multiple of ``eval_steps``)."""
+    from cleanmarl_b200 import mappo_multienvs as cli
+    from cleanmarl_b200.mappo import MAPPO
+    from fake_engine import OracleEngine
+    monkeypatch.chdir(tmp_path)
+    returns, evals, log = [], [], []
+
+    class CpuTrainer(MAPPO):
+        def __init__(self, args, device_index=0, rank=0, world_size=1, ippo=False):
+            super().__init__(args, rank=rank, world_size=world_size, ippo=ippo,
+                             engine_factory=lambda shapes, dev: OracleEngine(shapes))
+            self._g = torch.Generator().manual_seed(5)
+
+        def iteration(self):
+            noise = torch.empty(25, 3, 5, self.B).exponential_(1, generator=self._g)
+            super().iteration(None, noise)
+            returns.append(self.buf["ep_return"].clone())
+
+    class Recorder:
+        def __init__(self, logdir):
+            log.append(("dir", logdir))
+
+        def add_text(self, tag, text):
+            log.append(("text", tag, text))
+
+        def add_scalar(self, tag, value, step):
+            log.append(("scalar", tag, float(value), int(step)))
+
+        def close(self):
+            log.append(("close",))
+
+    def fake_eval(trainer, n, seed):
+        evals.append((trainer.training_step, n, seed))
+        return -30.0, 2.0, 25.0
+
+    tr = cli.main(["--batch_size", "4", "--total_timesteps", "600", "--log_every", "10", "--eval_steps", "2",
+                   "--num_eval_ep", "3", "--seed", "3"], trainer_cls=CpuTrainer, evaluate_fn=fake_eval,
+                  SummaryWriter=Recorder)
+    assert tr.step == 600 and tr.training_step == 18 and tr.num_episodes == 24 and len(returns) == 6
+    assert re.fullmatch(r"runs/MAPPO-multienvs-pz__simple_spread_v3__\d{4}-\d\d-\d\d_\d\d-\d\d-\d\d", log[0][1])   # MME:345-357
+    assert log[1][:2] == ("text", "hyperparameters") and "|batch_size|4|" in log[1][2] and log[-1] == ("close",)
+    scalars = [e[1:] for e in log if e[0] == "scalar"]
+    by_step = {s: [(t, v) for t, v, st in scalars if st == s] for s in range(100, 700, 100)}
+    train_tags = ["train/actor_loss", "train/critic_loss", "train/entropy", "train/kl_divergence", "train/clipped_ratios",
+                  "train/actor_gradients", "train/critic_gradients", "train/num_updates"]
+    for k, step in enumerate(range(100, 700, 100), start=1):
+        tags = [t for t, _ in by_step[step]]
+        assert sorted(t for t in tags if t.startswith("train/")) == sorted(train_tags)
+        assert dict(by_step[step])["train/num_updates"] == 3 * k
+        assert ("eval/ep_reward" in tags) == (k % 2 == 0)
+        assert ("rollout/ep_reward" in tags) == (k % 3 == 0)         # 4, 8, 12 > 10 episodes pending
+        if k % 2 == 0:
+            assert [dict(by_step[step])[t] for t in ("eval/ep_reward", "eval/std_ep_reward", "eval/ep_length")] == [-30.0, 2.0, 25.0]
+        if k % 3 == 0:
+            d = dict(by_step[step])
+            pending = torch.cat(returns[k - 3:k]).double()
+            assert abs(d["rollout/ep_reward"] - float(pending.mean())) < 1e-9
+            assert d["rollout/ep_length"] == 25.0 and d["rollout/num_episodes"] == 4 * k
+    assert [e[0] for e in evals] == [6, 12, 18] and all(e[1] == 3 for e in evals)
