@@ -78,6 +78,26 @@ class OracleEngine:
         env[6:12] = 0
         env[12:18] = torch.from_numpy(rng.uniform(-1, 1, (6, B)))
 
+    @staticmethod
+    def _unpack(env):
+        e = env.numpy()
+        B = e.shape[1]
+        return e[0:6].T.reshape(B, 3, 2).copy(), e[6:12].T.reshape(B, 3, 2).copy(), e[12:18].T.reshape(B, 3, 2).copy()
+
+    def env_observe(self, env, state_out):
+        pos, vel, lm = self._unpack(env)
+        state_out.copy_(torch.from_numpy(osp.observe_batched(pos, vel, lm).reshape(env.shape[1], 54).T.copy()))
+
+    def env_step(self, env, actions, state_out=None, reward_out=None):
+        pos, vel, lm = self._unpack(env)
+        B = env.shape[1]
+        pos, vel, rew = osp.step_batched(pos, vel, lm, actions.t().numpy())
+        env[0:6] = torch.from_numpy(pos.reshape(B, 6).T.copy()); env[6:12] = torch.from_numpy(vel.reshape(B, 6).T.copy())
+        if reward_out is not None:
+            reward_out.copy_(torch.from_numpy(rew[:, 0].astype(np.float32)))
+        if state_out is not None:
+            state_out.copy_(torch.from_numpy(osp.observe_batched(pos, vel, lm).reshape(B, 54).T.copy()))
+
     def rollout(self, actor_params, env, state, actions, logp, reward, *, noise=None, obs=None, ep_return=None,
                 seed=0, episode=0):
         assert noise is not None, "the CPU test double needs explicit race noise"

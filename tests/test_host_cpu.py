@@ -302,3 +302,15 @@ def test_cli_main_loop_logs_like_the_reference(tmp_path, monkeypatch):
             assert abs(d["rollout/ep_reward"] - float(pending.mean())) < 1e-9
             assert d["rollout/ep_length"] == 25.0 and d["rollout/num_episodes"] == 4 * k
     assert [e[0] for e in evals] == [6, 12, 18] and all(e[1] == 3 for e in evals)
+
+
+def test_env_duck_type_on_the_cpu_double():
+    """SpreadVecEnv (env/common_interface.py:5-23 with a leading env axis) on the engine double; the same body runs against
+    the CUDA library in tests/test_gpu_vecenv.py."""
+    from cleanmarl_b200.engine import Shapes
+    from cleanmarl_b200.mappo import SpreadVecEnv
+    from env_contract import check_env_duck_type
+    from fake_engine import OracleEngine
+    B = 300
+    check_env_duck_type(lambda seed: SpreadVecEnv(OracleEngine(Shapes(n_envs=B)), agent_ids=True, seed=seed), B,
+                        state_tol=0.0, obs_tol=0.0)
