@@ -205,6 +205,8 @@ def run_reference(a):
         return
     import torch
     from oracle import ref_loader
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: give the reference every host core it can use, as when run alone
+    torch.set_num_threads(os.cpu_count() or 1)
     B = a.ref_envs
     K, W = a.steps, a.warmup
     # keep the CPU arm inside a few minutes: one reference iteration at B=32 takes ~1.5-3 s on 8 cores
