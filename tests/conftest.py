@@ -8,7 +8,8 @@ REPO = Path(__file__).resolve().parent.parent
 if str(REPO) not in sys.path:
     sys.path.insert(0, str(REPO))
 
-GOLDEN = REPO / "tests" / "golden"
+# CMARL_GOLDEN_DIR: run the fixture-based tests against a freshly regenerated set (tests/golden/compare_golden.py)
+GOLDEN = Path(os.environ.get("CMARL_GOLDEN_DIR") or REPO / "tests" / "golden")
 
 
 def pytest_configure(config):

@@ -38,8 +38,9 @@ from pathlib import Path
 import numpy as np
 import torch
 
-HERE = Path(__file__).resolve().parent
-REPO = HERE.parent.parent
+REPO = Path(__file__).resolve().parent.parent.parent
+# CMARL_GOLDEN_OUT=<dir>: regenerate into another directory (tests/golden/compare_golden.py checks the result against the committed files)
+HERE = Path(__import__("os").environ.get("CMARL_GOLDEN_OUT") or Path(__file__).resolve().parent)
 sys.path.insert(0, str(REPO))
 
 from oracle import ref_loader  # noqa: E402
