@@ -314,3 +314,31 @@ def test_env_duck_type_on_the_cpu_double():
     B = 300
     check_env_duck_type(lambda seed: SpreadVecEnv(OracleEngine(Shapes(n_envs=B)), agent_ids=True, seed=seed), B,
                         state_tol=0.0, obs_tol=0.0)
+
+
+def test_fast_divmod_model_is_exact_below_2_pow_24():
+    """csrc/tc_chain.cu:101-108 decodes tile indices as q = trunc(float(u) * (1.0f / d)) with one correction step either
+    way; csrc/chain.cu:349 refuses launches with 2^24 tiles or more.  numpy float32 performs the same IEEE operations
+    (exact int -> float below 2^24, round-to-nearest multiply and divide, truncating conversion), so the claim 'the
+    estimate is within one of the quotient' can be checked here: multiples of d and their neighbours, the top of the range
+    and random indices, for every divisor the kernels can meet (tiles per time step <= 2^19 at 64 Mi envs, agent groups <= 3)
+    and a sweep of others."""
+    rng = np.random.default_rng(0)
+    top = (1 << 24) - 1
+    divisors = np.unique(np.concatenate([np.arange(1, 4100), 2 ** np.arange(12, 24), 2 ** np.arange(12, 24) - 1,
+                                         2 ** np.arange(12, 24) + 1, rng.integers(4100, 1 << 23, 2000)])).astype(np.int64)
+    for d in divisors:
+        inv = np.float32(1.0) / np.float32(d)
+        k = rng.integers(0, top // d + 1, 64)
+        u = np.unique(np.clip(np.concatenate([k * d, k * d - 1, k * d + 1, k * d + d - 1, [0, top, top - 1, top - d]]), 0, top))
+        q = np.trunc(u.astype(np.float32) * inv).astype(np.int64)
+        assert (np.abs(q - u // d) <= 1).all(), d                    # what the single correction step relies on
+        r = u - q * d
+        q = np.where(r < 0, q - 1, np.where(r >= d, q + 1, q))
+        r = np.where(r < 0, r + d, np.where(r >= d, r - d, r))
+        assert np.array_equal(q, u // d) and np.array_equal(r, u % d), d
+    u = rng.integers(0, top + 1, 200000)
+    for d in (1, 2, 3, 32, 512, 8192, 524288):
+        inv = np.float32(1.0) / np.float32(d)
+        q = np.trunc(u.astype(np.float32) * inv).astype(np.int64)
+        assert (np.abs(q - u // d) <= 1).all(), d
