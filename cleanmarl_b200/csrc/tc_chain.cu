@@ -2,7 +2,7 @@
 // (actor and critic forward + head + backward) with every GEMM on the 5th-gen tensor cores.
 //
 // Precision: kind::tf32 with a 3-term split ("3xTF32"): x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi)
-// (residual <= 2^-24 |x|), D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation in TMEM, the two
+// (residual <= 2^-23 |x|), D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation in TMEM, the two
 // small products issued FIRST (the accumulator add truncates, so the big term goes last: measured
 // 2.4e-7 vs fp64 on K = 64, plain fp32 GEMM 1.8e-7; profiles/umma_layouts_r1.md).
 //

@@ -171,7 +171,7 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// RN split for 3xTF32: hi = rna_tf32(x) (low 13 bits zero), lo = rna_tf32(x - hi); x - hi - lo <= 2^-24 |x|
+// RN split for 3xTF32: hi = rna_tf32(x) (low 13 bits zero), lo = rna_tf32(x - hi); |x - hi - lo| <= 2^-23 |x|
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
