@@ -372,3 +372,27 @@ def test_tf32_split_model():
     assert hi[-4] == np.float32(2.0) and hi[-3] == np.float32(-2.0)                                  # mantissa carry rounds up
     assert hi[-6] == np.float32(1.0 + 2.0 ** -10) and lo[-6] == np.float32(-(2.0 ** -11))            # tie: away from zero
     assert np.array_equal(np.signbit(hi[-10:-8]), [False, True]) and not hi[-10:-8].any()            # +-0 stay +-0
+
+
+def test_adam_bias_correction_model():
+    """csrc/exact.cu:303-311 forms beta^step by repeated squaring in fp64 where torch's ``_single_tensor_adam`` (MME:593-594)
+    evaluates the python-float ``beta ** step``; the kernel then uses ``(float)(-(lr / bc1))`` and ``(float)sqrt(bc2)``.
+    Same fp64 operations here: the float32 values the update sees are identical for the steps a run can reach (every step
+    to 4096, then a sweep to 10^6)."""
+    def by_squaring(beta, step):
+        p, b, e = 1.0, beta, step
+        while e:
+            if e & 1:
+                p *= b
+            b *= b
+            e >>= 1
+        return p
+
+    rng = np.random.default_rng(2)
+    steps = np.unique(np.concatenate([np.arange(1, 4097), rng.integers(4097, 10 ** 6 + 1, 4000), [10 ** 6]]))
+    for lr in (8e-4, 1e-3, 5e-4):
+        for step in steps.tolist():
+            bc1_t, bc2_t = 1 - 0.9 ** step, 1 - 0.999 ** step
+            bc1_k, bc2_k = 1.0 - by_squaring(0.9, step), 1.0 - by_squaring(0.999, step)
+            assert np.float32(-(lr / bc1_t)) == np.float32(-(lr / bc1_k)), step
+            assert np.float32(np.sqrt(bc2_t)) == np.float32(np.sqrt(bc2_k)), step
