@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--algo", default="mappo", choices=["mappo", "ippo", "mappo_lstm"])
     ap.add_argument("--ref-envs", type=int, default=32, help="envs in the reference arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the short IPPO / recurrent runs at N=1")
     ap.add_argument("--gae-envs", type=int, default=1 << 20, help="envs for the stand-alone GAE roofline probe")
     a = ap.parse_args()
     if a.envs_per_gpu is None:
@@ -63,24 +64,30 @@ def peaks():
 def ncu_traffic():
     """DRAM bytes per launch measured by ncu for this round's kernels (committed under profiles/; ncu cannot run inside
     the timed bench).  {} when the file is missing."""
-    p = REPO / "profiles" / "traffic_r1.json"
-    try:
-        return json.loads(p.read_text())
-    except Exception:        # noqa: BLE001
-        return {}
+    for name in ("traffic_r2.json", "traffic_r1.json"):
+        p = REPO / "profiles" / name
+        try:
+            d = json.loads(p.read_text())
+            d["_file"] = f"profiles/{name}"
+            return d
+        except Exception:        # noqa: BLE001
+            continue
+    return {}
 
 
-def workload_config(a, world):
+def workload_config(a, world, envs_per_gpu=None, algo=None, note=""):
+    algo = algo or a.algo
+    epg = envs_per_gpu or a.envs_per_gpu
     return {
-        "workload": f"{SCRIPTS[a.algo]} simple_spread_v3, 3 agents, T=25, num_envs={a.envs_per_gpu * world} "
-                    f"({a.envs_per_gpu}/GPU), 3 PPO epochs, actor "
-                    f"{'21-32-GRU(32)-5, truncated BPTT 10 (3 actor steps per epoch)' if a.algo == 'mappo_lstm' else '21-32-32-5'}"
-                    f", critic {'21-32-32-1 per agent' if a.algo == 'ippo' else '54-64-64-1'}",
-        "global_batch": a.envs_per_gpu * world,
-        "envs_per_gpu": a.envs_per_gpu,
-        "agent_env_steps_per_step": a.envs_per_gpu * world * T_STEPS * N_AGENTS,
+        "workload": f"{SCRIPTS[algo]} simple_spread_v3, 3 agents, T=25, num_envs={epg * world} "
+                    f"({epg}/GPU){note}, 3 PPO epochs, actor "
+                    f"{'21-32-GRU(32)-5, truncated BPTT 10 (3 actor steps per epoch)' if algo == 'mappo_lstm' else '21-32-32-5'}"
+                    f", critic {'21-32-32-1 per agent' if algo == 'ippo' else '54-64-64-1'}",
+        "global_batch": epg * world,
+        "envs_per_gpu": epg,
+        "agent_env_steps_per_step": epg * world * T_STEPS * N_AGENTS,
         "parallelism": (f"dp{world} (envs sharded, " + ("1 all-reduce of 7213 floats per TBPTT chunk + 1 of 7753 per epoch)"
-                        if a.algo == "mappo_lstm" else "1 all-reduce of 9678 floats per epoch)")) if world > 1 else "single GPU",
+                        if algo == "mappo_lstm" else "1 all-reduce of 9678 floats per epoch)")) if world > 1 else "single GPU",
         "l2": "flushed between timed iterations (256 MiB write, outside the per-step event pairs)",
     }
 
@@ -212,7 +219,15 @@ def run_reference(a):
     # keep the CPU arm inside a few minutes: one reference iteration at B=32 takes ~1.5-3 s on 8 cores
     K = min(K, 5)
     W = min(W, 1)
-    cfg = workload_config(a, world)
+    # The reference forks one interpreter + one pipe per env (MME:299-319): the 4096-env configuration cannot be launched
+    # as written, so this arm runs --batch_size `B` and SAYS so -- its `config` names the envs it ran, not the GPU arm's.
+    cfg = workload_config(a, 1, envs_per_gpu=B,
+                          note=f"; reference arm: one worker process per env caps num_envs, the GPU arm runs "
+                               f"{a.envs_per_gpu}/GPU")
+    cfg["parallelism"] = f"{B} env worker processes + torch CPU ({os.cpu_count()} host cores)"
+    cfg["l2"] = "n/a (CPU)"
+    cfg["reference_envs"] = B
+    cfg["gpu_arm_envs_per_gpu"] = a.envs_per_gpu
     per_step = B * T_STEPS * N_AGENTS
     script = SCRIPTS[a.algo]
     if ref_loader.reference_dir() is not None:
@@ -282,6 +297,28 @@ def trace(msg):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
+def reference_math(B=4096):
+    """the reference's TD(lambda) loop (MME:484-504: two batch-of-1 critic calls per (episode, step))
+    and its PPO epoch loop (MME:521-594, 3 epochs incl. backward, norms and Adam) on the SURVEY 8(d) synthetic batch at
+    the REAL configuration size -- the part of the reference that does run at num_envs = 4096 (no env workers involved).
+    Loop-form restatement in oracle/mappo.py (the reference's loops live inline under ``__main__``).  Seconds per phase."""
+    import torch
+    from oracle import mappo as om
+    actor, critic = om.build_networks(1)
+    batch = om.synthetic_batch(B, seed=1, actor=actor)
+    t0 = time.perf_counter()
+    ret, adv = om.td_lambda_loop(critic, batch[4], batch[3], batch[7], 0.99, 0.95, 3)
+    t1 = time.perf_counter()
+    aopt, copt = om.make_optimizers(actor, critic)
+    om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001, flat=False)
+    t2 = time.perf_counter()
+    n = B * T_STEPS * N_AGENTS
+    return {"envs": B, "td_lambda_loop_s": t1 - t0, "ppo_3_epochs_s": t2 - t1, "torch_threads": torch.get_num_threads(),
+            "agent_env_steps_per_s_math_only": n / (t2 - t0),
+            "what": "loop forms of MME:484-504 and MME:521-594 (oracle port) on the synthetic [4096, 25, ...] batch; "
+                    "no rollout, no env workers"}
+
+
 def run_b200(a):
     import torch
     from cleanmarl_b200.mappo import MAPPO, Args, ArgsRecurrent, init_distributed
@@ -292,24 +329,31 @@ def run_b200(a):
         print(f"warning: --gpus {a.gpus} but WORLD_SIZE={world}", file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    B = a.envs_per_gpu
-    lstm = a.algo == "mappo_lstm"
-    args = (ArgsRecurrent if lstm else Args)(batch_size=B * world, seed=1, critic_hidden_dim=32 if a.algo == "ippo" else 64)
-    tr = MAPPO(args, device_index=local, rank=rank, world_size=world, ippo=(a.algo == "ippo"))
-    eng = tr.engine
     hbm_peak, bf16_peak, sm_max, peak_src = peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def make_trainer(algo, envs_per_gpu, **kw):
+        args = (ArgsRecurrent if algo == "mappo_lstm" else Args)(batch_size=envs_per_gpu * world, seed=1,
+                                                                 critic_hidden_dim=32 if algo == "ippo" else 64)
+        return MAPPO(args, device_index=local, rank=rank, world_size=world, ippo=(algo == "ippo"), **kw)
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t)
+
     def timed(fn, steps, host_visible=False):
         """K steps, each bracketed by an event pair on the launching stream; L2 flushed in between (the flush is outside
         the event pairs).  host_visible=True additionally clocks every step on the host, from after the flush has
         drained to the return of ``fn`` (which ends with a stream synchronise): the latency a caller sees, without
-        the flush kernel that only the benchmark needs.  Returns (device s, wall s, per-step ms)."""
+        the flush kernel that only the benchmark needs.  Returns (device s [max over ranks], wall s, per-step ms)."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         w0 = time.perf_counter()
@@ -327,13 +371,56 @@ def run_b200(a):
         barrier()
         wall = host if host_visible else time.perf_counter() - w0
         ms = [s.elapsed_time(e) for s, e in evs]
-        t = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
-        if world > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        return float(t) / 1e3, wall, ms
+        return max_over_ranks(sum(ms)) / 1e3, wall, ms
 
+    def kernel_breakdown(tr, algo, nb=5):
+        """Per-kernel device times over a few eager iterations (library-internal event pairs) + algorithmic bytes / flops
+        per launch (DESIGN.md "kernels": per env-step figures x B*T)."""
+        eng = tr.engine
+        graph_mode = tr.use_graph
+        tr.use_graph = False                                     # event pairs live in the eager launch path
+        eng.timing(True)
+        for _ in range(nb):
+            flush.zero_()
+            tr.iteration()
+        kt = eng.read_timing()
+        eng.timing(False)
+        tr.use_graph = graph_mode
+        kernels = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / nb, "ms_per_step": v[0] / nb}
+                   for k, v in kt.items()}
+        total = sum(v["ms_per_step"] for v in kernels.values())
+        for v in kernels.values():
+            v["share"] = v["ms_per_step"] / total
+        bt = tr.B * T_STEPS
+        ippo, lstm = algo == "ippo", algo == "mappo_lstm"
+        alg = {
+            "ppo_actor_chain": (bt * (216 + 12 + 12 + (12 if ippo else 4)), bt * 3 * 9792),
+            "ppo_critic_chain": (bt * (216 + (12 if ippo else 4)), bt * (27072 if ippo else 38784)),
+            "critic_values": (bt * (216 + (12 if ippo else 4)), bt * (3 * 3456 if ippo else 15232)),
+            "rollout": (bt * (216 + 12 + 12 + 4), bt * 3 * 3712),
+            "td_lambda_scan": (bt * 16 * (3 if ippo else 1), bt * 6),
+        }
+        if lstm:
+            # per launch = one truncated-BPTT chunk (10, 10, 5 steps: B*T/3 env-steps on average); 41 856 FLOP per
+            # agent-step = forward 13 952 (fc1 21x32, gates 2x96x32, fc2 32x5) + backward 2x that, recompute not counted
+            nch = len(tr.chunks)
+            alg["ppo_tbptt_chunk"] = (bt // nch * (216 + 12 + 12 + 4), bt // nch * 3 * 41856)
+            alg["rollout"] = (bt * (216 + 12 + 12 + 4), bt * 3 * 13952)
+            alg["ppo_critic_chain"] = (bt * (216 + 4), bt * 38784)
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12            # TFLOP/s FFMA at max clock
+        for k, (by, fl) in alg.items():
+            if k in kernels:
+                t = kernels[k]["ms_per_launch"] * 1e-3
+                kernels[k].update({"alg_bytes": by, "alg_flops": fl, "gbs": by / t / 1e9, "tflops": fl / t / 1e12,
+                                   "hbm_frac": by / t / 1e9 / hbm_peak, "fp32_frac": fl / t / 1e12 / fp32_peak})
+        return kernels, fp32_peak
+
+    B = a.envs_per_gpu
+    lstm = a.algo == "mappo_lstm"
+    tr = make_trainer(a.algo, B)
+    eng = tr.engine
     trace("trainer ready")
-    # ---- device-resident throughput (value): the iteration as the trainer runs it (CUDA-graph replay at N=1) ----
+    # ---- device-resident throughput (value): the iteration as the trainer runs it (CUDA-graph replay) ----
     for _ in range(max(a.warmup, 3)):
         tr.iteration()
     clocks = ClockSampler(local)
@@ -353,7 +440,6 @@ def run_b200(a):
     env_h = torch.empty(18, B, dtype=torch.float64).uniform_(-1, 1).pin_memory()
     env_h[6:12] = 0
     res_h = torch.empty(tr.results.numel(), dtype=torch.uint8).pin_memory()
-    ret_h, stats_h = tr.split_results(res_h)                     # f64 [B] episode returns, f32 [epochs][8] statistics
 
     def e2e_step():
         tr.env.copy_(env_h, non_blocking=True)                   # H2D straight into the trainer's env-state buffer
@@ -366,10 +452,7 @@ def run_b200(a):
     e_secs, e_wall, _ = timed(e2e_step, a.steps, host_visible=True)
     # host-visible time: the results are read on the host every step, so the host clock around each step (input copy ..
     # results on the host) is the honest number; the L2 flush between steps is outside it
-    if world > 1:
-        tw = torch.tensor([e_wall], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(tw, op=torch.distributed.ReduceOp.MAX)
-        e_wall = float(tw)
+    e_wall = max_over_ranks(e_wall)
     h2d = env_h.numel() * 8
     d2h = res_h.numel()
 
@@ -377,7 +460,6 @@ def run_b200(a):
     # ---- the same with the categorical race noise supplied by the host as well (what the parity tests do; eager) ----
     noise_h = torch.empty(T_STEPS, N_AGENTS, N_ACT, B).exponential_(1).pin_memory()
     noise_d = torch.empty_like(noise_h, device=dev)
-
     env_d = torch.empty_like(env_h, device=dev)
 
     def e2e_noise_step():
@@ -391,68 +473,33 @@ def run_b200(a):
         e2e_noise_step()
     n_steps2 = max(3, a.steps // 4)
     _, e2_wall, _ = timed(e2e_noise_step, n_steps2, host_visible=True)
-    if world > 1:
-        tw = torch.tensor([e2_wall], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(tw, op=torch.distributed.ReduceOp.MAX)
-        e2_wall = float(tw)
+    e2_wall = max_over_ranks(e2_wall)
     clk = clocks.stop() if rank == 0 else None
-
-    # ---- per-kernel device times over a few iterations (library-internal event pairs) ----
     trace("e2e with host noise timed")
-    graph_mode = tr.use_graph
-    tr.use_graph = False                                         # event pairs live in the eager launch path
-    eng.timing(True)
-    nb = 5
-    for _ in range(nb):
-        flush.zero_()
-        tr.iteration()
-    kt = eng.read_timing()
-    eng.timing(False)
-    tr.use_graph = graph_mode
-    kernels = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / nb, "ms_per_step": v[0] / nb}
-               for k, v in kt.items()}
-    step_kernel_ms = sum(v["ms_per_step"] for v in kernels.values())
-    for v in kernels.values():
-        v["share"] = v["ms_per_step"] / step_kernel_ms
-    # algorithmic bytes / flops per launch (DESIGN.md "kernels"): per env-step figures x B*T
-    bt = B * T_STEPS
-    ippo = a.algo == "ippo"
-    alg = {
-        "ppo_actor_chain": (bt * (216 + 12 + 12 + (12 if ippo else 4)), bt * 3 * 9792),
-        "ppo_critic_chain": (bt * (216 + (12 if ippo else 4)), bt * (27072 if ippo else 38784)),
-        "critic_values": (bt * (216 + (12 if ippo else 4)), bt * (3 * 3456 if ippo else 15232)),
-        "rollout": (bt * (216 + 12 + 12 + 4), bt * 3 * 3712),
-        "td_lambda_scan": (bt * 16 * (3 if ippo else 1), bt * 6),
-    }
-    if lstm:
-        # per launch = one truncated-BPTT chunk (10, 10, 5 steps: B*T/3 env-steps on average); 41 856 FLOP per
-        # agent-step = forward 13 952 (fc1 21x32, gates 2x96x32, fc2 32x5) + backward 2x that, recompute not counted
-        nch = len(tr.chunks)
-        alg["ppo_tbptt_chunk"] = (bt // nch * (216 + 12 + 12 + 4), bt // nch * 3 * 41856)
-        alg["rollout"] = (bt * (216 + 12 + 12 + 4), bt * 3 * 13952)
-        alg["ppo_critic_chain"] = (bt * (216 + 4), bt * 38784)
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12            # TFLOP/s FFMA at max clock
-    for k, (by, fl) in alg.items():
-        if k in kernels:
-            t = kernels[k]["ms_per_launch"] * 1e-3
-            kernels[k].update({"alg_bytes": by, "alg_flops": fl, "gbs": by / t / 1e9, "tflops": fl / t / 1e12,
-                               "hbm_frac": by / t / 1e9 / hbm_peak, "fp32_frac": fl / t / 1e12 / fp32_peak})
+
+    kernels, fp32_peak = kernel_breakdown(tr, a.algo)
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     tc = bool(eng.tensor_cores)
-    chain = dom in ("ppo_actor_chain", "ppo_critic_chain", "critic_values") and not lstm
+    chain = dom in ("ppo_actor_chain", "ppo_critic_chain", "critic_values")
+    tf32_peak = bf16_peak / 2.0                                  # dense tf32 = half the dense bf16 rate on tcgen05
     if tc and chain:
         # the dominant kernel runs its GEMMs on tcgen05 (kind::tf32, 3 MMAs per product for fp32-level accuracy):
-        # achieved = ALGORITHMIC flops / launch time; peak = measured dense bf16 (tf32 runs at half of it, and the
-        # 3-term split triples the issued MMA work), so frac is a deliberately conservative tensor-roofline fraction
+        # achieved = ALGORITHMIC flops / launch time; peak = measured dense bf16, so `frac` is a deliberately conservative
+        # tensor-roofline fraction.  Beside it: the same against dense TF32 (half the bf16 rate) and the ISSUED MMA rate
+        # (3 tf32 MMAs per algorithmic product) -- the figure ncu's sm__pipe_tensor_cycles_active corresponds to.
         ach = kernels[dom].get("tflops")
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": (ach / bf16_peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "tf32_dense_peak": tf32_peak, "frac_of_tf32_dense": (ach / tf32_peak) if ach else None,
+                    "issued_tf32_tflops": 3 * ach if ach else None,
+                    "issued_frac_of_tf32_dense": (3 * ach / tf32_peak) if ach else None,
                     "hbm_gbs": kernels[dom].get("gbs"), "hbm_frac": kernels[dom].get("hbm_frac"),
                     "fp32_ffma_equiv_frac": kernels[dom].get("fp32_frac"),
-                    "note": "tiny contractions (K 24..64, N 32..64): the kernel is bound by CUDA-core epilogue "
-                            "instructions and MMA hand-off latency, not by the tensor pipe (ncu: "
-                            "profiles/prof_tc_chain_r1.md); hbm_frac is the same launch against the HBM roofline; the "
-                            "HBM-bound GAE kernel is `gae_roofline`"}
+                    "note": "tiny contractions (K 24..64, N 32..64, M = 128 samples per tile): the kernel is bound by the "
+                            "CUDA-core stages between its GEMMs and by MMA issue, not by tensor-pipe throughput (ncu "
+                            "summaries under profiles/); issued_frac_of_tf32_dense is what sm__pipe_tensor_cycles_active "
+                            "measures; hbm_frac is the same launch against the HBM roofline; the HBM-bound GAE kernel is "
+                            "`gae_roofline`"}
     else:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom].get("gbs"), "peak": hbm_peak, "unit": "GB/s",
                     "frac": kernels[dom].get("hbm_frac"), "traffic": None, "peak_source": peak_src,
@@ -465,7 +512,7 @@ def run_b200(a):
     traffic = ncu_traffic() if (B == 4096 and not lstm) else {}
     if dom in traffic:
         roofline["traffic"] = traffic[dom]
-        roofline["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/traffic_r1.json"
+        roofline["traffic_source"] = f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, {traffic.get('_file')}"
         roofline["alg_bytes"] = kernels[dom].get("alg_bytes")
     # ---- stand-alone GAE scan at a size that leaves L2 (the metric BASELINE.json names) ----
     gae = None
@@ -483,18 +530,59 @@ def run_b200(a):
         torch.cuda.synchronize()
         tg = statistics.median(s.elapsed_time(e) for s, e in evs) * 1e-3
         by = 16 * Bg * T_STEPS
+        tr_bytes = ncu_traffic().get(f"td_lambda_scan@{Bg}")
         gae = {"kernel": "td_lambda_scan", "bound": "hbm", "envs": Bg, "alg_bytes": by, "ms": tg * 1e3,
                "achieved": by / tg / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": by / tg / 1e9 / hbm_peak,
-               "traffic": traffic.get(f"td_lambda_scan@{Bg}"),
-               "note": "16 B per env-step (r, V in; R, A out), inputs larger than L2 (419 MB), L2 flushed; traffic = ncu "
-                       "DRAM bytes of the same launch (reads == algorithmic reads; 26 % of the writes are still in L2 "
-                       "when the kernel ends)"}
+               "traffic": tr_bytes,
+               "frac_dram": (tr_bytes / tg / 1e9 / hbm_peak) if tr_bytes else None,
+               "note": "16 B per env-step (r, V in; R, A out), inputs larger than L2 (419 MB), L2 flushed. `frac` counts the "
+                       "algorithmic bytes; `frac_dram` counts the DRAM bytes ncu saw inside the launch (reads == algorithmic "
+                       "reads; part of the writes is still in L2 when the kernel ends and drains after it)"}
         e2.close()
         del v, r, R, A
+
+    # ---- other BASELINE configurations, short runs next to the headline (driver-visible) ----
+    def short_run(algo, envs_per_gpu, steps):
+        t2 = make_trainer(algo, envs_per_gpu)
+        for _ in range(4):
+            t2.iteration()
+        sc, _, _ = timed(t2.iteration, steps)
+        n = envs_per_gpu * world * T_STEPS * N_AGENTS
+        out = {"config": workload_config(a, world, envs_per_gpu=envs_per_gpu, algo=algo), "value": n * steps / sc, "unit": UNIT,
+               "ms_per_step": sc / steps * 1e3, "steps": steps,
+               "launch_mode": "CUDA graph replay of the iteration" if t2.use_graph else "eager stream launches"}
+        if world == 1:
+            ks, _ = kernel_breakdown(t2, algo, nb=3)
+            d = max(ks, key=lambda k: ks[k]["ms_per_step"])
+            out["dominant_kernel"] = {"name": d, **ks[d]}
+        del t2
+        return out
+
+    variants = None
+    if world == 1 and a.algo == "mappo" and not a.no_variants:
+        vs = max(20, min(50, a.steps))
+        variants = {"ippo": short_run("ippo", 4096, vs),                 # BASELINE configs[2]
+                    "mappo_lstm": short_run("mappo_lstm", 8192, vs)}    # BASELINE configs[3]
+        trace("variants timed")
+    config5 = None
+    if world == 8 and a.algo == "mappo" and a.envs_per_gpu != 8192:
+        config5 = short_run("mappo", 8192, a.steps)                      # BASELINE configs[4]: 65 536 envs over 8 GPUs
+        trace("config5 timed")
+
+    # ---- N ranks == 1 rank on the same envs (outside every timed region) ----
+    mgpu_check = None
+    if world > 1:
+        try:
+            mgpu_check = multi_gpu_check(MAPPO, Args, rank, world, local)
+        except Exception as e:       # noqa: BLE001
+            mgpu_check = {"error": f"{type(e).__name__}: {e}"}
+        trace("mgpu check done")
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline(algo=a.algo, sample_envs=32 if lstm else 64)
+        if a.algo == "mappo":
+            cpu["reference_math_4096"] = reference_math(4096)
 
     if rank == 0:
         cfg = workload_config(a, world)
@@ -511,13 +599,57 @@ def run_b200(a):
                                            "h2d_bytes_per_step": h2d + noise_h.numel() * 4,
                                            "note": "Exp(1) race noise f32 [T][N][A][B] also copied from the host (eager launches)"}},
                "gpu_launches": launches,
-               "launch_mode": "CUDA graph replay of the iteration" if graph_mode else "eager stream launches",
+               "launch_mode": "CUDA graph replay of the iteration" if tr.use_graph else "eager stream launches",
                "clocks": clk, "roofline": roofline, "gae_roofline": gae,
                "kernels": kernels, "cpu_baseline": cpu, "wall_ms_per_step": wall / a.steps * 1e3}
+        if variants is not None:
+            out["variants"] = variants
+        if config5 is not None:
+            out["config5"] = config5
+        if mgpu_check is not None:
+            out["mgpu_check"] = mgpu_check
         emit(out)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+
+
+def multi_gpu_check(MAPPO, Args, rank, world, local, envs_per_rank=256, iters=3):
+    """N ranks (envs sharded, gradient sums exchanged) against ONE rank on the same envs, start states and race noise
+    for `iters` iterations: replicas bit-identical to each other, parameters within fp32 reassociation of the single-rank
+    run.  (The driver's pytest box has one GPU, so this is where the equivalence reaches a driver record.)"""
+    import torch
+    dev = torch.device("cuda", local)
+    B = envs_per_rank * world
+    g = torch.Generator().manual_seed(11)
+    env = torch.zeros(18, B, dtype=torch.float64)
+    env[0:6] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    env[12:18] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    noise = torch.empty(T_STEPS, N_AGENTS, N_ACT, B).exponential_(1, generator=g)
+    sl = slice(rank * envs_per_rank, (rank + 1) * envs_per_rank)
+    trn = MAPPO(Args(batch_size=B, seed=3), device_index=local, rank=rank, world_size=world)
+    e_n, q_n = env[:, sl].contiguous().to(dev), noise[..., sl].contiguous().to(dev)
+    for _ in range(iters):
+        trn.iteration(e_n, q_n)
+    torch.cuda.synchronize()
+    gathered = [torch.empty_like(trn.net.flat) for _ in range(world)]
+    torch.distributed.all_gather(gathered, trn.net.flat)
+    out = None
+    if rank == 0:
+        tr1 = MAPPO(Args(batch_size=B, seed=3), device_index=local, rank=0, world_size=1)
+        e_1, q_1 = env.to(dev), noise.to(dev)
+        for _ in range(iters):
+            tr1.iteration(e_1, q_1)
+        torch.cuda.synchronize()
+        diff = (trn.net.flat - tr1.net.flat).abs().max().item()
+        moved = (tr1.net.flat - MAPPO(Args(batch_size=B, seed=3), device_index=local).net.flat).abs().max().item()
+        sd = (trn.epoch_stats - tr1.epoch_stats).abs().max().item() / max(tr1.epoch_stats.abs().max().item(), 1e-30)
+        out = {"replicas_identical": all(torch.equal(gathered[0], x) for x in gathered), "max_param_diff": diff,
+               "max_param_change_over_run": moved, "max_rel_stat_diff": sd, "comm": trn.comm, "ranks": world,
+               "envs": B, "iterations": iters, "adam_steps": iters * 3, "step_counter_equal": trn.step == tr1.step,
+               "ok": bool(all(torch.equal(gathered[0], x) for x in gathered) and diff < 2e-6 and trn.step == tr1.step)}
+    torch.distributed.barrier()
+    return out
 
 
 def main():

@@ -95,7 +95,10 @@ struct cmarl_ctx {
     uint64_t* episode_dev;   // optional device episode counter for the Philox draws (CUDA-graph replay)
     int launch_chaining;     // 1: launches carry the programmatic-stream-serialization attribute (cmarl_ctx_set_launch_chaining)
     cmarl_timing* timing;
+    unsigned int* dev_words; // CMARL_DEV_WORDS zero-initialised device words owned by the context (tickets of the kernels' last-CTA protocols)
 };
+enum { CMARL_DW_ADAM_TICKET = 0, CMARL_DW_CHAIN_TICKET_A = 1, CMARL_DW_CHAIN_TICKET_C = 2, CMARL_DEV_WORDS = 64 };
+constexpr int CMARL_MAX_PARAMS = 16384;     // per context (clip_adam_kernel: 1024 threads x 16; = CMARL_COMM_SLOT_FLOATS)
 
 void cmarl_time_begin(cmarl_ctx* ctx, int id, cudaStream_t st);
 void cmarl_time_end(cmarl_ctx* ctx, int id, cudaStream_t st);

@@ -63,10 +63,20 @@ extern "C" int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out) {
     ctx->gru.set(cfg->obs_dim, cfg->actor_hidden, cfg->n_actions);
     if (cfg->actor_recurrent) ctx->actor.count = ctx->gru.count;
     ctx->sm_count = prop.multiProcessorCount;
+    if (ctx->actor.count + ctx->critic.count + CMARL_N_STATS > CMARL_MAX_PARAMS) {
+        cmarl_set_error("cmarl_ctx_create: %d parameters (limit %d)", ctx->actor.count + ctx->critic.count, CMARL_MAX_PARAMS - CMARL_N_STATS);
+        free(ctx);
+        return -1;
+    }
+    {
+        int me = cmarl_check_cuda(cudaMalloc(&ctx->dev_words, CMARL_DEV_WORDS * sizeof(unsigned int)), "cudaMalloc(dev_words)");
+        if (!me) me = cmarl_check_cuda(cudaMemset(ctx->dev_words, 0, CMARL_DEV_WORDS * sizeof(unsigned int)), "cudaMemset(dev_words)");
+        if (me) { free(ctx); return me; }
+    }
     int e = cmarl_chain_setup(ctx);
     if (!e) e = cmarl_gru_setup(ctx);
     if (!e) e = cmarl_rollout_setup(ctx);
-    if (e) { free(ctx); return e; }
+    if (e) { cudaFree(ctx->dev_words); free(ctx); return e; }
     *out = ctx;
     return 0;
 }
@@ -144,6 +154,7 @@ extern "C" int cmarl_ctx_destroy(cmarl_ctx* ctx) {
                     if (ctx->timing->ev[k][i][j]) cudaEventDestroy(ctx->timing->ev[k][i][j]);
         free(ctx->timing);
     }
+    if (ctx && ctx->dev_words) cudaFree(ctx->dev_words);
     free(ctx);
     return 0;
 }

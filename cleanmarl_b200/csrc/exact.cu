@@ -174,6 +174,7 @@ struct AdamArgs {
     float* v;
     float* stats_out;
     int32_t* step_dev;
+    unsigned int* ticket;   // per-context device word: CTAs that have read *step_dev (launches of one context are serialised)
     int step;
     int n_tensors;          // 12
     int tensor_off[13];     // prefix offsets of the 12 parameter tensors, [12] = P
@@ -206,8 +207,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
 // coefficients), then updates only its own 1 024 parameters.  A warp whose 32 consecutive elements lie in one tensor
 // (all but <= 11 warp-rows) adds a single shuffle-reduced value into its private shared-memory row.
 constexpr int ADAM_THREADS = 1024;
-constexpr int ADAM_PER_THREAD = 12;      // supports up to 12 288 parameters
-__device__ unsigned int g_adam_ticket = 0;   // CTAs that have read *step_dev (one context per GPU, launches serialised)
+constexpr int ADAM_PER_THREAD = 16;      // supports up to 16 384 parameters (= CMARL_COMM_SLOT_FLOATS; checked in cmarl_ctx_create)
 
 __device__ __forceinline__ int tensor_of(const AdamArgs& a, int i) {
     int k = 0;
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
         if (a.step_dev) {
             step = *reinterpret_cast<volatile int32_t*>(a.step_dev) + 1;
             __threadfence();
-            const unsigned t = atomicAdd(&g_adam_ticket, 1u);
-            if (t == gridDim.x - 1) { g_adam_ticket = 0; *a.step_dev = step; }
+            const unsigned t = atomicAdd(a.ticket, 1u);
+            if (t == gridDim.x - 1) { *a.ticket = 0; *a.step_dev = step; }
         }
         // beta^step by repeated squaring (<= 2 log2(step) fp64 multiplies, within a few ulp of pow(): no float32-visible
         // difference in bc1, sqrt(bc2) or lr / bc1 for step <= 10^6)
@@ -407,7 +407,7 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     CMARL_ARG(ctx->actor.count + ctx->critic.count <= ADAM_THREADS * ADAM_PER_THREAD, "too many parameters for clip_adam_kernel");
     AdamArgs a;
     a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
-    a.step_dev = step_dev; a.step = step;
+    a.step_dev = step_dev; a.step = step; a.ticket = ctx->dev_words + CMARL_DW_ADAM_TICKET;
     a.n_tensors = 12; a.n_actor_tensors = 6;
     const NetLayout* nets[2] = {&ctx->actor, &ctx->critic};
     int base = 0, k = 0;
@@ -443,7 +443,7 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     CMARL_ARG(extra_div >= 1.0, "extra_div must be >= 1");
     AdamArgs a;
     a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
-    a.step_dev = step_dev; a.step = step;
+    a.step_dev = step_dev; a.step = step; a.ticket = ctx->dev_words + CMARL_DW_ADAM_TICKET;
     int k = 0;
     if (net == 0 && ctx->cfg.actor_recurrent) {
         const GruLayout& L = ctx->gru;

@@ -247,6 +247,11 @@ class MAPPO:
         self.args, self.rank, self.world, self.ippo, self.pg = args, rank, world_size, ippo, process_group
         self.B = args.batch_size // world_size
         self.T = 25                                              # simple_spread_v3 max_cycles (kwargs = {}, MME:297)
+        if args.batch_size * self.T >= 1 << 24:
+            # the valid (b, t) count travels through the gradient exchange as ONE fp32 word (exact below 2^24): beyond
+            # that the 1/n gradient scale and every logged mean would be silently rounded
+            raise SystemExit(f"--batch_size {args.batch_size}: batch_size * {self.T} steps must stay below 2^24 "
+                             f"(the sample count is exchanged as an exact fp32 integer)")
         self.recurrent = hasattr(args, "tbptt")
         shapes = Shapes(n_envs=self.B, n_steps=self.T, obs_dim=18 + 3 * bool(args.agent_ids),
                         actor_hidden=args.actor_hidden_dim, actor_layers=1 if self.recurrent else args.actor_num_layers,
@@ -262,8 +267,12 @@ class MAPPO:
         self.grads = eng.empty(eng.n_params + 8)
         # the per-step results a caller reads back (per-env episode returns f64 [B], per-epoch statistics f32 [epochs][8])
         # live in ONE device block so that `results_to_host` is a single D2H copy
-        self.results = torch.zeros(self.B * 8 + args.epochs * 32, dtype=torch.uint8, device=eng.device)
-        self.epoch_stats = self.results[self.B * 8:].view(torch.float32).view(args.epochs, 8)
+        # (+ one f64: the sum of the episode returns over ALL ranks, filled by `stage_scalars` on multi-GPU runs)
+        self.results = torch.zeros(self.B * 8 + args.epochs * 32 + 8, dtype=torch.uint8, device=eng.device)
+        self.epoch_stats = self.results[self.B * 8:self.B * 8 + args.epochs * 32].view(torch.float32).view(args.epochs, 8)
+        self.return_sum = self.results[self.B * 8 + args.epochs * 32:].view(torch.float64)
+        self._host_blocks, self._host_turn = None, 0
+        self._eval_ctx = {}
         self.norm_stats = eng.empty(4, dtype=torch.float64)
         self.buf = eng.alloc_rollout()
         self.buf["ep_return"] = self.results[:self.B * 8].view(torch.float64)
@@ -480,8 +489,51 @@ class MAPPO:
         pinned.copy_(self.results, non_blocking=True)
 
     def split_results(self, host: torch.Tensor):
+        n = self.B * 8 + self.args.epochs * 32
         return (host[:self.B * 8].view(torch.float64),
-                host[self.B * 8:].view(torch.float32).view(self.args.epochs, 8))
+                host[self.B * 8:n].view(torch.float32).view(self.args.epochs, 8))
+
+    # -- the CLI's logging path: ONE D2H copy per iteration, read one iteration late -------------------
+    def stage_scalars(self):
+        """Enqueue -- without synchronising the host -- the copy of everything the script logs for the iteration just
+        launched (per-epoch statistics of MME:597-612, episode returns of MME:454-468) into one of two pinned host
+        blocks.  Multi-GPU: the sum of the episode returns is all-reduced on the device first (collective: every rank
+        calls this every iteration).  Returns a handle for `read_scalars`."""
+        if self.world > 1:
+            torch.sum(self.buf["ep_return"], dim=0, keepdim=True, out=self.return_sum)
+            self._allreduce(self.return_sum)
+        cuda = self.results.is_cuda
+        if self._host_blocks is None:
+            mk = (lambda: torch.empty(self.results.numel(), dtype=torch.uint8).pin_memory()) if cuda else \
+                 (lambda: torch.empty(self.results.numel(), dtype=torch.uint8))
+            self._host_blocks = [mk(), mk()]
+        host = self._host_blocks[self._host_turn]
+        self._host_turn ^= 1
+        host.copy_(self.results, non_blocking=True)
+        event = None
+        if cuda:
+            event = torch.cuda.Event()
+            event.record(torch.cuda.current_stream(self.results.device))
+        return host, event
+
+    def read_scalars(self, handle) -> dict:
+        """Wait for a `stage_scalars` copy and decode it: the seven train scalars (means over the epochs) and the mean
+        episode return over the envs of all ranks."""
+        host, event = handle
+        if event is not None:
+            event.synchronize()
+        ret, stats = self.split_results(host)
+        s = stats.mean(dim=0)
+        keys = ("actor_loss", "critic_loss", "entropy", "kl_divergence", "clipped_ratios", "actor_gradients",
+                "critic_gradients")
+        out = {k: float(s[i]) for i, k in enumerate(keys)}
+        if self.world > 1:
+            total = float(host[self.B * 8 + self.args.epochs * 32:].view(torch.float64)[0])
+        else:
+            total = float(ret.sum())
+        out["ep_reward"] = total / (self.B * self.world)
+        out["ep_length"] = float(self.T)
+        return out
 
     # -- read-backs (each is one small D2H copy; nothing else synchronises) ---------------------
     def train_scalars(self) -> dict:
@@ -515,21 +567,25 @@ def tbptt_chunks(T: int, tbptt: int):
     return out
 
 
-def evaluate(trainer: MAPPO, num_episodes: int, seed: int):
-    """MME:614-644: ``num_eval_ep`` episodes with the *sampling* policy (``actor.act``), run as
-    ``num_eval_ep`` parallel device envs.  Returns (mean, std, length) of the episode reward."""
-    s = trainer.engine.shapes
-    eng = Engine(Shapes(n_envs=num_episodes, n_steps=s.n_steps, obs_dim=s.obs_dim, actor_hidden=s.actor_hidden,
-                        critic_hidden=s.critic_hidden, critic_on_obs=s.critic_on_obs,
-                        actor_recurrent=s.actor_recurrent), trainer.engine.device.index)
-    buf = eng.alloc_rollout()
-    env = eng.empty(18, num_episodes, dtype=torch.float64)
-    eng.env_reset(env, seed, 0)
-    eng.rollout(trainer.net.actor, env, buf["state"], buf["actions"], buf["logp"], buf["reward"],
+def evaluate(trainer: MAPPO, num_episodes: int, seed: int, env_init=None, noise=None):
+    """MME:614-644: ``num_eval_ep`` episodes with the *sampling* policy (``actor.act``), run as ``num_eval_ep`` parallel
+    device envs on a context kept for the trainer's lifetime.  Returns (mean, population std, mean length) of the
+    episode reward -- ``np.mean`` / ``np.std`` / ``np.mean`` of MME:642-644.  ``env_init`` f64 [18][n] / ``noise``
+    f32 [T][N][A][n] make the evaluation a function of its inputs (parity test); default: device Philox draws."""
+    ctx = trainer._eval_ctx.get(num_episodes)
+    if ctx is None:
+        import dataclasses
+        eng = Engine(dataclasses.replace(trainer.engine.shapes, n_envs=num_episodes), trainer.engine.device.index)
+        ctx = trainer._eval_ctx[num_episodes] = (eng, eng.alloc_rollout(), eng.empty(18, num_episodes, dtype=torch.float64))
+    eng, buf, env = ctx
+    if env_init is None:
+        eng.env_reset(env, seed, 0)
+    else:
+        env.copy_(env_init, non_blocking=True)
+    eng.rollout(trainer.net.actor, env, buf["state"], buf["actions"], buf["logp"], buf["reward"], noise=noise,
                 ep_return=buf["ep_return"], seed=seed, episode=0)
     r = buf["ep_return"].cpu()
-    eng.close()
-    return float(r.mean()), float(r.std(unbiased=False)), float(s.n_steps)
+    return float(r.mean()), float(r.std(unbiased=False)), float(trainer.engine.shapes.n_steps)
 
 
 def init_distributed():

@@ -48,26 +48,46 @@ def main(argv=None, algo=ALGO, ippo=IPPO, args_cls=Args, run_prefix=None, traine
     # the reference keeps every episode return since the last log line and logs their mean once MORE than
     # ``log_every`` of them are pending (MME:454-468): the same mean from the per-rollout means
     pending_episodes, pending_reward_sum = 0, 0.0
+
+    def log(record):
+        """Scalars of one iteration, in the reference's order (MME:460-468, 605-612, 642-644)."""
+        nonlocal pending_episodes, pending_reward_sum
+        handle, step, training_step, num_episodes, ev = record
+        sc = trainer.read_scalars(handle)                           # the only host synchronisation of the loop
+        pending_episodes += args.batch_size
+        pending_reward_sum += sc["ep_reward"] * args.batch_size
+        if writer is None:
+            return
+        if pending_episodes > args.log_every:
+            writer.add_scalar("rollout/ep_reward", pending_reward_sum / pending_episodes, step)
+            writer.add_scalar("rollout/ep_length", sc["ep_length"], step)
+            writer.add_scalar("rollout/num_episodes", num_episodes, step)
+            pending_episodes, pending_reward_sum = 0, 0.0
+        for k in ("actor_loss", "critic_loss", "entropy", "kl_divergence", "clipped_ratios", "actor_gradients",
+                  "critic_gradients"):                              # MME:605-612
+            writer.add_scalar(f"train/{k}", sc[k], step)
+        writer.add_scalar("train/num_updates", training_step, step)
+        if ev is not None:
+            writer.add_scalar("eval/ep_reward", ev[0], step)
+            writer.add_scalar("eval/std_ep_reward", ev[1], step)
+            writer.add_scalar("eval/ep_length", ev[2], step)
+
+    # The scalars of iteration k are written AFTER iteration k + 1 has been launched: TensorBoard / W&B I/O on rank 0
+    # then overlaps device work instead of keeping the other ranks' gradient exchange waiting for rank 0's next launch,
+    # and the loop has one D2H copy and one host synchronisation per iteration.  Evaluation runs on EVERY rank (same seed,
+    # same parameters: same result) so that the ranks stay in step; rank 0 logs it.
+    pending = None
     while trainer.step < args.total_timesteps:
         trainer.iteration()
-        step = trainer.step
-        roll = trainer.rollout_scalars()            # collective: every rank calls it
-        pending_episodes += args.batch_size
-        pending_reward_sum += roll["ep_reward"] * args.batch_size
-        if writer is not None:
-            if pending_episodes > args.log_every:
-                writer.add_scalar("rollout/ep_reward", pending_reward_sum / pending_episodes, step)
-                writer.add_scalar("rollout/ep_length", roll["ep_length"], step)
-                writer.add_scalar("rollout/num_episodes", trainer.num_episodes, step)
-                pending_episodes, pending_reward_sum = 0, 0.0
-            for k, v in trainer.train_scalars().items():            # MME:605-612
-                writer.add_scalar(f"train/{k}", v, step)
-            writer.add_scalar("train/num_updates", trainer.training_step, step)
-            if (trainer.training_step / args.epochs) % args.eval_steps == 0:       # MME:614
-                mean, std, length = evaluate_fn(trainer, args.num_eval_ep, seed=args.seed + 7919 * trainer.training_step)
-                writer.add_scalar("eval/ep_reward", mean, step)
-                writer.add_scalar("eval/std_ep_reward", std, step)
-                writer.add_scalar("eval/ep_length", length, step)
+        handle = trainer.stage_scalars()            # collective on multi-GPU runs: every rank calls it
+        ev = None
+        if (trainer.training_step / args.epochs) % args.eval_steps == 0:           # MME:614
+            ev = evaluate_fn(trainer, args.num_eval_ep, seed=args.seed + 7919 * trainer.training_step)
+        if pending is not None:
+            log(pending)
+        pending = (handle, trainer.step, trainer.training_step, trainer.num_episodes, ev)
+    if pending is not None:
+        log(pending)
     if writer is not None:
         writer.close()
         if args.use_wnb:

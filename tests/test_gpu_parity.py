@@ -584,3 +584,142 @@ def test_tiny_and_ragged_env_counts(cm, B, recurrent):
     final = torch.cat([actor.flat_params(), critic.flat_params()])
     dp = (tr.net.flat.cpu() - final).abs()
     assert (dp < 3e-6).float().mean() > 0.99 and dp.max() < 2e-4       # near-eps Adam gradients: see test_gpu_recurrent
+
+
+# ----------------------------------------------------------------------------------------- evaluation loop (MME:614-644)
+def test_evaluate_matches_oracle_closed_loop(cm):
+    """``evaluate()`` (sampled policy on ``num_eval_ep`` parallel device envs, MME:614-644) against the oracle rolling the
+    SAME start states and race noise closed loop (oracle env + oracle actor + exponential race): per-env episode returns
+    equal to 1e-9 wherever every race of the episode was decided identically (ties excepted, > 90 % of the envs), and
+    (mean, population std, length) as np.mean / np.std / np.mean of MME:642-644.  The eval context is built once."""
+    from cleanmarl_b200.mappo import MAPPO, Args, evaluate
+    n, Tn = 64, 25
+    tr = MAPPO(Args(batch_size=256, seed=9), use_graph=False)
+    tr.iteration()                                                   # one update: the policy is no longer the initial one
+    torch.cuda.synchronize()
+    actor, _ = om.build_networks(9)
+    actor.load_flat(tr.net.actor.cpu())
+    g = torch.Generator().manual_seed(21)
+    env = torch.zeros(18, n, dtype=torch.float64)
+    env[0:6] = torch.rand(6, n, generator=g, dtype=torch.float64) * 2 - 1
+    env[12:18] = torch.rand(6, n, generator=g, dtype=torch.float64) * 2 - 1
+    noise = torch.empty(Tn, 3, 5, n).exponential_(1, generator=g)
+    mean, std, length = evaluate(tr, n, seed=0, env_init=env.cuda(), noise=noise.cuda())
+    eng_eval, buf, _ = tr._eval_ctx[n]
+    acts_dev = buf["actions"].permute(0, 2, 1).cpu().long()          # [T,B,N]
+    ret_dev = buf["ep_return"].cpu().numpy()
+    # oracle, closed loop
+    e = env.numpy()
+    pos = e[0:6].T.reshape(n, 3, 2).copy(); vel = np.zeros_like(pos); lm = e[12:18].T.reshape(n, 3, 2).copy()
+    ids = np.broadcast_to(np.eye(3), (n, 3, 3))
+    total = np.zeros(n)
+    same = np.ones(n, dtype=bool)
+    for t in range(Tn):
+        raw = osp.observe_batched(pos, vel, lm)
+        obs = torch.from_numpy(np.concatenate([raw, ids], axis=-1)).float()
+        with torch.no_grad():
+            a, _ = om.race_sample(om.actor_logits(actor, obs), noise[t].permute(2, 0, 1))
+        same &= (a == acts_dev[t]).all(dim=1).numpy()
+        pos, vel, rew = osp.step_batched(pos, vel, lm, acts_dev[t].numpy())     # follow the device where a tie split them
+        total += rew[:, 0]
+    assert same.mean() > 0.9, same.mean()
+    assert np.abs(ret_dev - total).max() < 1e-9                      # physics + reward along the device's own actions
+    assert abs(mean - float(np.mean(ret_dev))) < 1e-12 and abs(std - float(np.std(ret_dev))) < 1e-9 and length == 25.0
+    if same.all():
+        # (the oracle's own closed loop took exactly these actions: its mean / std are the ones above)
+        assert abs(mean - float(np.mean(total))) < 1e-9
+    # one context per evaluation size, reused; device-drawn evaluations are a function of the seed
+    r1 = evaluate(tr, n, seed=5)
+    assert tr._eval_ctx[n][0] is eng_eval and len(tr._eval_ctx) == 1
+    assert evaluate(tr, n, seed=5) == r1 and evaluate(tr, n, seed=6) != r1
+    assert -60.0 < r1[0] < -5.0 and r1[1] > 0.0
+
+
+def test_trainer_wide_actor_and_critic(cm):
+    """--actor_hidden_dim 64 with the default 64-wide MAPPO critic: 13 638 parameters, more than one clip_adam_kernel
+    thread row of 12 288 (the kernel holds 16 384) -- the whole iteration against the oracle, as the tiny-size test."""
+    from cleanmarl_b200.mappo import MAPPO, Args
+    from cleanmarl_b200 import engine as E
+    B = 130
+    tr = MAPPO(Args(batch_size=B, seed=6, actor_hidden_dim=64, critic_hidden_dim=64, clip_gradients=0.5), use_graph=False)
+    assert tr.engine.n_params == 13638
+    actor, critic = om.build_networks(6, actor_hidden=64, critic_hidden=64)
+    assert torch.equal(tr.net.flat.cpu(), torch.cat([actor.flat_params(), critic.flat_params()]))
+    g = torch.Generator().manual_seed(B)
+    env = torch.zeros(18, B, dtype=torch.float64)
+    env[0:6] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    env[12:18] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    noise = torch.empty(25, 3, 5, B).exponential_(1, generator=g)
+    tr.iteration(env.cuda(), noise.cuda())
+    torch.cuda.synchronize()
+    batch = tuple(t.cpu() for t in tr.get_batch())
+    ret, adv = om.td_lambda_batched(critic, batch[4], batch[3], batch[7], 0.99, 0.95, 3)
+    assert (E.heads_to_reference(tr.buf["adv"], 3).cpu() - adv).abs().max() < 1e-5
+    aopt, copt = om.make_optimizers(actor, critic)
+    st = om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001, clip_gradients=0.5)
+    final = torch.cat([actor.flat_params(), critic.flat_params()])
+    dp = (tr.net.flat.cpu() - final).abs()
+    assert (dp < 3e-6).float().mean() > 0.99 and dp.max() < 2e-4
+    s = tr.epoch_stats.cpu()
+    for ep in range(3):
+        assert abs(s[ep, 0].item() - st["actor_loss"][ep]) < 2e-5 * abs(st["actor_loss"][ep]) + 1e-7
+        assert abs(s[ep, 1].item() - st["critic_loss"][ep]) < 2e-5 * abs(st["critic_loss"][ep]) + 1e-7
+
+
+# ----------------------------------------------------------------------------------------- BASELINE configs[1] / [2] size
+@pytest.mark.parametrize("ippo", [False, True], ids=["mappo", "ippo"])
+def test_whole_update_at_baseline_size(cm, ippo):
+    """The whole update at BASELINE.json's own size (num_envs = 4096: 800 critic / 2 400 actor tiles over the persistent
+    148 / 296-CTA grids, several rounds per CTA) on the SURVEY 8(d) synthetic batch against the oracle
+    (``td_lambda_batched`` + ``ppo_update(flat=True)``): advantages <= 1e-5, first-epoch gradients per tensor
+    <= 2e-5 of the tensor's max, per-epoch statistics <= 2e-5 relative, parameters <= 1e-6 after the 3 epochs --
+    the tolerances of ``test_whole_update_vs_reference_run``."""
+    from cleanmarl_b200 import engine as E
+    B, Tn = 4096, 25
+    actor, critic = (om.build_networks(1, state_dim=21, critic_hidden=32) if ippo else om.build_networks(1))
+    batch = om.synthetic_batch(B, seed=1, actor=actor)
+    eng = make_engine(cm, B, tc=True, critic_on_obs=ippo, critic_hidden=32 if ippo else 64)
+    dev = eng.device
+    d = E.to_device_layout(batch, dev, with_obs=False)
+    params = flat_params(actor, critic, dev)
+    values = eng.empty(Tn, eng.n_heads, B)
+    ret, adv = torch.empty_like(values), torch.empty_like(values)
+    eng.critic_values(params[eng.n_actor:], values, state=d["state"])
+    eng.td_lambda(values, d["reward"], ret, adv, 0.99, 0.95)
+    ret_o, adv_o = om.td_lambda_batched(critic, batch[0] if ippo else batch[4], batch[3], batch[7], 0.99, 0.95, 3)
+    assert (E.heads_to_reference(adv, 3).cpu() - adv_o).abs().max() < 1e-5
+    assert (E.heads_to_reference(ret, 3).cpu() - ret_o).abs().max() < 1e-5
+    aopt, copt = om.make_optimizers(actor, critic)
+    st = om.ppo_update(actor, critic, aopt, copt, batch, adv_o, ret_o, epochs=3, clip=0.2, ent_coef=0.001,
+                       critic_on_obs=ippo, flat=True, record_grads=True)
+    adv_d, ret_d = E.heads_to_device(adv_o, eng.n_heads, dev), E.heads_to_device(ret_o, eng.n_heads, dev)
+    m, v = torch.zeros_like(params), torch.zeros_like(params)
+    grads, stats = eng.empty(eng.n_params + 8), eng.empty(8)
+    n = float(B * Tn)
+    for ep in range(3):
+        eng.ppo_epoch_grads(params, grads, state=d["state"], actions=d["actions"], logp_old=d["logp"], adv=adv_d,
+                            returns=ret_d, clip=0.2, ent_coef=0.001)
+        if ep == 0:
+            gcpu = grads.cpu()
+            assert gcpu[eng.n_params + 5].item() == n
+            ga, gc = st["grads"][0]
+            ref = torch.cat([ga, gc])
+            off = 0
+            for net in (actor, critic):
+                for p in net.parameters():
+                    k = p.numel()
+                    a, b = gcpu[off:off + k] / n, ref[off:off + k]
+                    scale = max(b.abs().max().item(), 1e-6)
+                    assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-9, (tuple(p.shape), (a - b).abs().max().item(), scale)
+                    off += k
+        eng.clip_adam_step(params, grads, m, v, step=ep + 1, stats_out=stats)
+        s = stats.cpu().numpy()
+        ref = [st["actor_loss"][ep], st["critic_loss"][ep], st["entropy"][ep], st["kl"][ep], st["clipfrac"][ep],
+               st["actor_grad_norm"][ep], st["critic_grad_norm"][ep]]
+        for k in (0, 1, 2, 5, 6):
+            assert abs(s[k] - ref[k]) <= 2e-5 * abs(ref[k]) + 1e-7, (ep, k, s[k], ref[k])
+        assert abs(s[3] - ref[3]) < 1e-6 + 1e-3 * abs(ref[3]) and abs(s[4] - ref[4]) < 1e-6
+    final = torch.cat([actor.flat_params(), critic.flat_params()])
+    dp = (params.cpu() - final).abs()
+    # (a gradient within ~1e-7 of Adam's eps = 1e-8 turns a 1e-9 reassociation difference into a visible fraction of lr)
+    assert (dp < 1e-6).float().mean() > 0.995 and dp.max().item() < 2e-5, (dp.max().item(), (dp < 1e-6).float().mean().item())
