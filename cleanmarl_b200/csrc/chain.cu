@@ -344,7 +344,11 @@ static int run_chain(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileS
     const int m = ctx->use_tc ? cmarl_tc_tile() : tile_m(H, kin);
     const int units = units_of(src, m);
     const int slots = ctx->sm_count * (ctx->use_tc ? cmarl_tc_ctas_per_sm(H, nd.in_rows, TRAIN, Head::OUT) : 1);
-    const int grid = units < slots ? units : slots;
+    int grid = units < slots ? units : slots;
+    {   // diagnostics only (profiles/tools/grad_accuracy.py): fewer persistent CTAs = more tiles per CTA at a given size
+        static const int cap = [] { const char* v = getenv("CMARL_DEBUG_GRID_CAP"); return v ? atoi(v) : 0; }();
+        if (cap > 0 && grid > cap) grid = cap;
+    }
     if (grid_out) *grid_out = grid;
     if (ctx->use_tc && units >= (1 << 24)) {      // tc_chain_kernel decodes tile indices with fast_divmod (exact below 2^24)
         cmarl_set_error("chain: %d tiles in one launch (limit 2^24)", units);

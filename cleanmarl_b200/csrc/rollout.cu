@@ -186,6 +186,9 @@ __device__ long long g_roll_tl[16];
 #define RTL(slot, cond) do { if (blockIdx.x == 0 && t == 10 && e == 0 && (cond)) g_roll_tl[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ void agent_bar(int n) { asm volatile("bar.sync %0, 128;" ::"r"(1 + n) : "memory"); }
+// the per-step block barriers: the actor warps and the contact-force warps arrive from DIFFERENT instructions (warp
+// specialisation), so the barrier names its thread count instead of being a __syncthreads()
+template <int NT> __device__ __forceinline__ void block_bar() { asm volatile("bar.sync 5, %0;" ::"n"(NT) : "memory"); }   // ids 1-3: agent_bar, 4: physics warps
 
 // reward of agent 0 (pettingzoo_wrapper.py:66) from the distance table: d[3 l + a] = |agent a - landmark l|,
 // d[9], d[10] = |agent 1 - agent 0|, |agent 2 - agent 0|; same operation order as spread::reward_agent0
@@ -291,8 +294,8 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
             double gx, gy;
             spread::pair_force(es[2 * ia][e], es[2 * ia + 1][e], es[2 * ib][e], es[2 * ib + 1][e], gx, gy);
             pf[p][e][0] = gx; pf[p][e][1] = gy;
-            __syncthreads();
-            __syncthreads();
+            block_bar<NTHR>();
+            block_bar<NTHR>();
         }
     } else
     for (int t = 0; t < a.T; ++t) {
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
             }
         }
         RTL(6, w == 0); RTL(9, w == 1);
-        __syncthreads();
+        block_bar<NTHR>();
         RTL(10, w == 1);
         // ---- physics (World.step), lane-dense float64 on the quarter-1 warps ----------------------------------------
         // (a) last step's team reward from the distance table (written after the previous state update)
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
             es[6 + 2 * n][e] = vx; es[6 + 2 * n + 1][e] = vy;
             RTL(13, w == 1);
         }
-        __syncthreads();
+        block_bar<NTHR>();
         RTL(14, w == 1);
         // (d) distance table of the new state for the team reward: (task, env); tasks 0-8: agent a to landmark l
         //     (task = 3 l + a), 9-10: agents 1, 2 to agent 0; consumed after the next barrier

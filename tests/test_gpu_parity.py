@@ -667,21 +667,43 @@ def test_trainer_wide_actor_and_critic(cm):
 
 
 # ----------------------------------------------------------------------------------------- BASELINE configs[1] / [2] size
+def _relu_kink_samples(actor, critic, obs, critic_in, tol=2e-6):
+    """(b, t) pairs in which some hidden unit's pre-activation lies within float rounding of zero (|pre| < tol * (|x||W| + |b|),
+    evaluated in fp64).  relu' is discontinuous there: two correct fp32 evaluations may disagree on the unit's mask, and ONE
+    flipped (sample, unit) changes a gradient that is a sum over n samples by ~1/sqrt(n) of its size (1.8e-3 at n = 307 200
+    -- measured: profiles/grad_accuracy_r2.md), far above any reassociation tolerance.  At 10^7 pre-activations per
+    network a handful of such samples always exists, so the full-size test masks them out (both sides) instead of widening
+    the tolerance."""
+    def kinks(net, x):
+        x = x.double()
+        amb = torch.zeros(x.shape[:-1], dtype=torch.bool)
+        for lin in list(net.linears)[:-1]:
+            W, b = lin.weight.double(), lin.bias.double()
+            pre = x @ W.T + b
+            amb |= (pre.abs() < tol * (x.abs() @ W.abs().T + b.abs())).any(-1)
+            x = torch.relu(pre)
+        return amb
+    with torch.no_grad():
+        a = kinks(actor, obs).any(-1)
+        c = kinks(critic, critic_in)
+    return a | (c.any(-1) if c.dim() == 3 else c)
+
+
 @pytest.mark.parametrize("ippo", [False, True], ids=["mappo", "ippo"])
 def test_whole_update_at_baseline_size(cm, ippo):
     """The whole update at BASELINE.json's own size (num_envs = 4096: 800 critic / 2 400 actor tiles over the persistent
     148 / 296-CTA grids, several rounds per CTA) on the SURVEY 8(d) synthetic batch against the oracle
     (``td_lambda_batched`` + ``ppo_update(flat=True)``): advantages <= 1e-5, first-epoch gradients per tensor
-    <= 2e-5 of the tensor's max, per-epoch statistics <= 2e-5 relative, parameters <= 1e-6 after the 3 epochs --
-    the tolerances of ``test_whole_update_vs_reference_run``."""
+    <= 2e-5 of the tensor's max (samples sitting on a relu kink masked out, see ``_relu_kink_samples``), per-epoch losses
+    <= 2e-5 relative, gradient norms <= 2e-4 (later epochs may flip a kink), parameters <= 1e-6 after the 3 epochs."""
     from cleanmarl_b200 import engine as E
     B, Tn = 4096, 25
     actor, critic = (om.build_networks(1, state_dim=21, critic_hidden=32) if ippo else om.build_networks(1))
-    batch = om.synthetic_batch(B, seed=1, actor=actor)
+    batch = list(om.synthetic_batch(B, seed=1, actor=actor))
     eng = make_engine(cm, B, tc=True, critic_on_obs=ippo, critic_hidden=32 if ippo else 64)
     dev = eng.device
-    d = E.to_device_layout(batch, dev, with_obs=False)
     params = flat_params(actor, critic, dev)
+    d = E.to_device_layout(tuple(batch), dev, with_obs=False)
     values = eng.empty(Tn, eng.n_heads, B)
     ret, adv = torch.empty_like(values), torch.empty_like(values)
     eng.critic_values(params[eng.n_actor:], values, state=d["state"])
@@ -689,16 +711,20 @@ def test_whole_update_at_baseline_size(cm, ippo):
     ret_o, adv_o = om.td_lambda_batched(critic, batch[0] if ippo else batch[4], batch[3], batch[7], 0.99, 0.95, 3)
     assert (E.heads_to_reference(adv, 3).cpu() - adv_o).abs().max() < 1e-5
     assert (E.heads_to_reference(ret, 3).cpu() - ret_o).abs().max() < 1e-5
+    kink = _relu_kink_samples(actor, critic, batch[0], batch[0] if ippo else batch[4])
+    assert 0 < int(kink.sum()) < 0.01 * B * Tn, int(kink.sum())
+    batch[7] = batch[7] & ~kink
+    d = E.to_device_layout(tuple(batch), dev, with_obs=False)
     aopt, copt = om.make_optimizers(actor, critic)
-    st = om.ppo_update(actor, critic, aopt, copt, batch, adv_o, ret_o, epochs=3, clip=0.2, ent_coef=0.001,
+    st = om.ppo_update(actor, critic, aopt, copt, tuple(batch), adv_o, ret_o, epochs=3, clip=0.2, ent_coef=0.001,
                        critic_on_obs=ippo, flat=True, record_grads=True)
     adv_d, ret_d = E.heads_to_device(adv_o, eng.n_heads, dev), E.heads_to_device(ret_o, eng.n_heads, dev)
     m, v = torch.zeros_like(params), torch.zeros_like(params)
     grads, stats = eng.empty(eng.n_params + 8), eng.empty(8)
-    n = float(B * Tn)
+    n = float(batch[7].sum())
     for ep in range(3):
         eng.ppo_epoch_grads(params, grads, state=d["state"], actions=d["actions"], logp_old=d["logp"], adv=adv_d,
-                            returns=ret_d, clip=0.2, ent_coef=0.001)
+                            returns=ret_d, mask=d["mask"], clip=0.2, ent_coef=0.001)
         if ep == 0:
             gcpu = grads.cpu()
             assert gcpu[eng.n_params + 5].item() == n
@@ -716,8 +742,10 @@ def test_whole_update_at_baseline_size(cm, ippo):
         s = stats.cpu().numpy()
         ref = [st["actor_loss"][ep], st["critic_loss"][ep], st["entropy"][ep], st["kl"][ep], st["clipfrac"][ep],
                st["actor_grad_norm"][ep], st["critic_grad_norm"][ep]]
-        for k in (0, 1, 2, 5, 6):
+        for k in (0, 1, 2):
             assert abs(s[k] - ref[k]) <= 2e-5 * abs(ref[k]) + 1e-7, (ep, k, s[k], ref[k])
+        for k in (5, 6):
+            assert abs(s[k] - ref[k]) <= (2e-5 if ep == 0 else 2e-4) * abs(ref[k]) + 1e-7, (ep, k, s[k], ref[k])
         assert abs(s[3] - ref[3]) < 1e-6 + 1e-3 * abs(ref[3]) and abs(s[4] - ref[4]) < 1e-6
     final = torch.cat([actor.flat_params(), critic.flat_params()])
     dp = (params.cpu() - final).abs()
