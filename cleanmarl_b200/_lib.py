@@ -50,6 +50,8 @@ _SIGNATURES = {
     "cmarl_td_lambda": (C.c_int, [_P, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
     "cmarl_normalize": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P]),
     "cmarl_ppo_epoch_grads": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
+    "cmarl_ppo_epoch_grads_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double,
+                                           C.c_int32, C.c_int32, _P, _P, _P]),
     "cmarl_clip_adam_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, C.c_double, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_double, _P, _P]),
     # peer-memory gradient exchange
@@ -67,7 +69,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-VERSION = 102          # CMARL_VERSION of include/cmarl_b200.h
+VERSION = 103          # CMARL_VERSION of include/cmarl_b200.h
 N_KERNEL_IDS = 12      # CMARL_NK
 
 _lib = None

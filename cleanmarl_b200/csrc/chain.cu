@@ -18,7 +18,7 @@ chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict_
     static_assert(M == NT, "S3/S5 are thread-per-sample");
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::oBar);
     const int tid = threadIdx.x;
-    const int tiles_b = (src.B + M - 1) / M;
+    const int tiles_b = (src.nb + M - 1) / M;
     const int units = src.T * src.G * tiles_b;
 
     load_weights<C>(sm, nd, src.G);
@@ -95,7 +95,7 @@ chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict_
                 z[0] = fmaf(sm[C::oW3T + j * OUTP], h, z[0]);
             }
         }
-        Head::apply(ha, z, t, g, b0 + s, src.G, src.B, (b0 + s) < src.B, TRAIN, dz, st);
+        Head::apply(ha, z, t, g, b0 + s, src.G, src.B, (b0 + s) < src.nb, TRAIN, dz, st);
 
         if (TRAIN) {
 #pragma unroll
@@ -281,7 +281,7 @@ static int launch(const cmarl_ctx* ctx, const NetDesc& nd, const TileSrc& src, c
 
 static int tile_m(int H, int kin) { return (H == 32 && kin == 24) ? 256 : 128; }
 
-static int units_of(const TileSrc& s, int M) { return s.T * s.G * ceil_div(s.B, M); }
+static int units_of(const TileSrc& s, int M) { return s.T * s.G * ceil_div(s.nb, M); }
 
 template <class Head, bool TRAIN>
 static int dispatch(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileSrc& src,
@@ -301,7 +301,7 @@ static void actor_desc(const cmarl_ctx* ctx, const float* params, const float* s
     nd.params = params;
     nd.in_dim = c.obs_dim;
     nd.out_dim = c.n_actions;
-    src.T = c.n_steps; src.G = c.n_agents; src.B = c.n_envs; src.indep = 0;
+    src.T = c.n_steps; src.G = c.n_agents; src.B = c.n_envs; src.nb = c.n_envs; src.indep = 0;
     if (obs) {
         nd.in_rows = c.obs_dim; nd.fold_ids = 0;
         src.x = obs; src.stride_t = (size_t)c.n_agents * c.obs_dim * c.n_envs; src.stride_g = (size_t)c.obs_dim * c.n_envs;
@@ -321,7 +321,7 @@ static void critic_desc(const cmarl_ctx* ctx, const float* params, const float* 
     }
     nd.params = params;
     nd.in_rows = c.state_dim; nd.in_dim = c.state_dim; nd.fold_ids = 0; nd.out_dim = 1;
-    src.x = state; src.T = c.n_steps; src.G = 1; src.B = c.n_envs; src.indep = 0;
+    src.x = state; src.T = c.n_steps; src.G = 1; src.B = c.n_envs; src.nb = c.n_envs; src.indep = 0;
     src.stride_t = (size_t)c.state_dim * c.n_envs; src.stride_g = 0;
 }
 
@@ -397,6 +397,7 @@ extern "C" int cmarl_critic_values(cmarl_ctx* ctx, const float* critic_params, c
     critic_desc(ctx, critic_params, state, obs, nd, src);
     ValueHeadArgs ha;
     ha.returns = nullptr; ha.mask = nullptr; ha.values_out = values; ha.inv_heads = 1.0f / (float)ctx->n_heads;
+    ha.values_old = nullptr; ha.vclip = 0.0f;
     KernelTimer kt(ctx, K_CRITIC, as_stream(stream));
     return run_chain<ValueHead, false>(ctx, ctx->cfg.critic_hidden, nd, src, ha, nullptr, 0, nullptr, as_stream(stream));
 }
@@ -405,18 +406,41 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
                                      const int32_t* actions, const float* logp_old, const float* adv,
                                      const float* returns, const uint8_t* mask, const uint8_t* avail,
                                      double clip, double ent_coef, float* grads_out, void* workspace, void* stream) {
+    return cmarl_ppo_epoch_grads_ex(ctx, params, state, obs, actions, logp_old, adv, returns, nullptr, mask, avail, clip,
+                                    ent_coef, -1.0, 0, ctx ? ctx->cfg.n_envs : 0, grads_out, workspace, stream);
+}
+
+// One minibatch = the contiguous env block [env_begin, env_begin + env_count): every buffer keeps its row stride B, the
+// base pointers move by env_begin, and the kernels' bound is the block's env count (TileSrc.nb).
+extern "C" int cmarl_ppo_epoch_grads_ex(cmarl_ctx* ctx, const float* params, const float* state, const float* obs,
+                                        const int32_t* actions, const float* logp_old, const float* adv,
+                                        const float* returns, const float* values_old, const uint8_t* mask,
+                                        const uint8_t* avail, double clip, double ent_coef, double value_clip,
+                                        int32_t env_begin, int32_t env_count, float* grads_out, void* workspace,
+                                        void* stream) {
     CMARL_ARG(ctx && params && actions && logp_old && adv && returns && grads_out && workspace, "null argument");
     CMARL_ARG(!ctx->cfg.actor_recurrent, "recurrent actor: use cmarl_tbptt_chunk_grads + cmarl_critic_epoch_grads");
     CMARL_ARG(state || obs, "state or obs required");
     CMARL_ARG(ctx->cfg.critic_on_obs || state, "MAPPO critic needs state");
+    CMARL_ARG(env_begin >= 0 && env_count >= 1 && env_begin + env_count <= ctx->cfg.n_envs, "env range outside [0, n_envs)");
+    CMARL_ARG(value_clip <= 0.0 || values_old, "value clipping needs values_old");
     const cmarl_config& c = ctx->cfg;
     cudaStream_t st = as_stream(stream);
     const int Pa = ctx->actor.count, Pc = ctx->critic.count;
     float* part_a = reinterpret_cast<float*>(workspace);
     float* part_c = part_a + (size_t)2 * ctx->sm_count * (Pa + CMARL_N_STATS);
+    if (env_begin) {      // every buffer is env-minor: the block starts env_begin elements into each row
+        if (state) state += env_begin;
+        if (obs) obs += env_begin;
+        actions += env_begin; logp_old += env_begin; adv += env_begin; returns += env_begin;
+        if (values_old) values_old += env_begin;
+        if (mask) mask += env_begin;
+        if (avail) avail += env_begin;
+    }
 
     NetDesc nda; TileSrc srca;
     actor_desc(ctx, params, state, obs, nda, srca);
+    srca.nb = env_count;
     PolicyHeadArgs pa;
     pa.actions = actions; pa.logp_old = logp_old; pa.adv = adv; pa.mask = mask; pa.avail = avail;
     pa.V = ctx->n_heads; pa.A = c.n_actions;
@@ -431,8 +455,10 @@ extern "C" int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const 
 
     NetDesc ndc; TileSrc srcc;
     critic_desc(ctx, params + Pa, state, obs, ndc, srcc);
+    srcc.nb = env_count;
     ValueHeadArgs va;
     va.returns = returns; va.mask = mask; va.values_out = nullptr; va.inv_heads = 1.0f / (float)ctx->n_heads;
+    va.values_old = values_old; va.vclip = value_clip > 0.0 ? (float)value_clip : 0.0f;
     {
         // the critic chain reads nothing the actor chain writes (parameters come from the previous Adam step, which the
         // actor chain has waited for): launched as its programmatic dependent with `indep` set it starts on every SM the
@@ -479,6 +505,7 @@ extern "C" int cmarl_critic_epoch_grads(cmarl_ctx* ctx, const float* critic_para
     critic_desc(ctx, critic_params, state, obs, ndc, srcc);
     ValueHeadArgs va;
     va.returns = returns; va.mask = mask; va.values_out = nullptr; va.inv_heads = 1.0f / (float)ctx->n_heads;
+    va.values_old = nullptr; va.vclip = 0.0f;
     int grid_c = 0, e;
     {
         KernelTimer kt(ctx, K_PPO_CRITIC, st);

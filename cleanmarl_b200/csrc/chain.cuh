@@ -119,7 +119,9 @@ struct NetDesc {
 struct TileSrc {
     const float* x;        // row r of tile (t, g, b0) lives at x + t*stride_t + g*stride_g + r*B + b0
     size_t stride_t, stride_g;
-    int T, G, B;
+    int T, G, B;           // B = row stride (envs of the whole buffer)
+    int nb;                // envs of this launch: [0, nb) relative to the (pre-offset) base pointers -- the whole buffer
+                           // (nb == B) or one minibatch (contiguous env block, cmarl_ppo_epoch_grads_ex)
     int indep;             // tc_chain_kernel only: 1 = reads nothing the launch in front of it writes (see tc_chain.cu)
 };
 
@@ -138,6 +140,8 @@ struct ValueHeadArgs {
     const uint8_t* mask;
     float* values_out;         // [T][V][B]  (forward)
     float inv_heads;
+    const float* values_old;   // [T][V][B]  values at rollout time (value clipping only)
+    float vclip;               // <= 0: the reference's plain MSE (MME:554-558); > 0: PPO2-style clipped value loss
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -183,7 +187,7 @@ __device__ void load_weights(float* sm, const NetDesc& nd, int n_groups) {
 // ------------------------------------------------------------------------------------------------
 template <class C>
 __device__ __forceinline__ bool tile_is_bulk(const TileSrc& src, int b0) {
-    return (b0 + C::M <= src.B) && ((src.B & 3) == 0) && ((reinterpret_cast<uintptr_t>(src.x) & 15) == 0);
+    return (b0 + C::M <= src.nb) && ((src.B & 3) == 0) && ((reinterpret_cast<uintptr_t>(src.x) & 15) == 0);
 }
 
 template <class C>
@@ -197,7 +201,7 @@ __device__ void issue_tile(float* xbuf, uint64_t* bar, const TileSrc& src, int i
             bulk_g2s(xbuf + threadIdx.x * C::LD, base + (size_t)threadIdx.x * src.B, C::M * 4, bar);
         }
     } else {
-        const int valid = src.B - b0;
+        const int valid = src.nb - b0;
         for (int i = threadIdx.x; i < in_rows * C::M; i += C::NT) {
             const int r = i / C::M, s = i - r * C::M;
             xbuf[r * C::LD + s] = (s < valid) ? __ldg(base + (size_t)r * src.B + s) : 0.0f;

@@ -112,18 +112,19 @@ struct ValueHead {
     // MME:554-558: sum_env mean_agent (V - R)^2 ; forward-only mode just stores V (MME:495,502).
     struct In {
         bool inb, live;     // in range; in range and mask == 1
-        float ret;
+        float ret, vold;
         float* vout;        // forward mode: where V goes
     };
     __device__ static __forceinline__ In load(const Args& h, int t, int g, int b, int G, int B, bool inb) {
         In in;
-        in.inb = inb; in.live = false; in.ret = 0.0f; in.vout = nullptr;
+        in.inb = inb; in.live = false; in.ret = 0.0f; in.vold = 0.0f; in.vout = nullptr;
         if (!inb) return in;
         const size_t tgb = ((size_t)t * G + g) * B + b;
         if (h.values_out) { in.vout = h.values_out + tgb; return in; }
         if (h.mask && !h.mask[(size_t)t * B + b]) return in;
         in.live = true;
         in.ret = h.returns[tgb];
+        if (h.vclip > 0.0f) in.vold = h.values_old[tgb];
         return in;
     }
     __device__ static __forceinline__ void apply(const Args& h, float (&z)[OUT], int t, int g, int b, int G, int B,
@@ -141,8 +142,21 @@ struct ValueHead {
         }
         if (!in.live) return;
         const float diff = z[0] - in.ret;
-        st[0] += h.inv_heads * diff * diff;
         st[1] += 1.0f;
+        if (h.vclip > 0.0f) {
+            // beyond the reference (default off): max((V - R)^2, (V_old + clamp(V - V_old, +-c) - R)^2); the clipped branch
+            // carries a gradient only while V is inside the clip range (torch.clamp / torch.max autograd; ties 1/2 + 1/2)
+            const float dv = z[0] - in.vold;
+            const float dvc = fminf(fmaxf(dv, -h.vclip), h.vclip);
+            const float diffc = (in.vold + dvc) - in.ret;
+            const float l1 = diff * diff, l2 = diffc * diffc;
+            const bool inside = (dv >= -h.vclip) && (dv <= h.vclip);
+            st[0] += h.inv_heads * fmaxf(l1, l2);
+            const float g1 = 2.0f * diff, g2 = inside ? 2.0f * diffc : 0.0f;
+            dz[0] = h.inv_heads * (l1 > l2 ? g1 : (l1 == l2 ? 0.5f * (g1 + g2) : g2));
+            return;
+        }
+        st[0] += h.inv_heads * diff * diff;
         dz[0] = h.inv_heads * 2.0f * diff;
     }
 };

@@ -308,7 +308,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     if (src.indep) pdl_trigger();
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::oBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + C::oBar + N_BARS * 8);
-    const int tiles_b = (src.B + M - 1) / M;
+    const int tiles_b = (src.nb + M - 1) / M;
     const int units = src.T * src.G * tiles_b;
     const float inv_tb = 1.0f / (float)tiles_b, inv_g = 1.0f / (float)src.G;
 
@@ -435,7 +435,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             // products and double predicates of the obvious form were 14, a fifth of the critic kernel's instructions)
             const float* xp = src.x + (size_t)t * src.stride_t + (size_t)g * src.stride_g + b + (size_t)(8 * hf) * src.B;
             const uint32_t step = (uint32_t)src.B;
-            const int rmax = (b < src.B) ? nd.in_rows - 8 * hf : 0;     // this thread reads rows 16 i + e < rmax of its half
+            const int rmax = (b < src.nb) ? nd.in_rows - 8 * hf : 0;     // this thread reads rows 16 i + e < rmax of its half
 #pragma unroll
             for (int i = 0; i < NXO; ++i) {
 #pragma unroll
@@ -479,7 +479,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             fast_divmod(u, tiles_b, inv_tb, r, bt);
             fast_divmod(r, src.G, inv_g, t, g);
             const int b = bt * M + s;
-            const bool inb = b < src.B;
+            const bool inb = b < src.nb;
             const bool tl_on = g_tc_timeline_on == (OUT > 1 ? 2 : 1) && blockIdx.x == 0 && it == 1 && tid == 0;
             const bool has_next = u + (int)gridDim.x < units;
             TL_STAMP(0);

@@ -224,13 +224,25 @@ class Engine:
                    "cmarl_normalize")
 
     def ppo_epoch_grads(self, params, grads, *, state=None, obs=None, actions, logp_old, adv, returns, mask=None,
-                        avail=None, clip=0.2, ent_coef=0.001):
-        _lib.check(self.lib.cmarl_ppo_epoch_grads(
+                        avail=None, clip=0.2, ent_coef=0.001, value_clip=-1.0, values_old=None, env_begin=0,
+                        env_count=None):
+        """``value_clip`` / ``values_old`` and the env block ``[env_begin, env_begin + env_count)`` are the two default-off
+        extensions of cmarl_ppo_epoch_grads_ex (not in the reference); without them this is cmarl_ppo_epoch_grads."""
+        if value_clip <= 0 and env_begin == 0 and env_count in (None, self.shapes.n_envs):
+            _lib.check(self.lib.cmarl_ppo_epoch_grads(
+                self._h, self._f(params, "params"), self._f(state, "state"), self._f(obs, "obs"),
+                _ptr(actions, torch.int32, self.device, "actions"), self._f(logp_old, "logp_old"), self._f(adv, "adv"),
+                self._f(returns, "returns"), _ptr(mask, torch.uint8, self.device, "mask"),
+                _ptr(avail, torch.uint8, self.device, "avail"), float(clip), float(ent_coef), self._f(grads, "grads"),
+                C.c_void_p(self.workspace.data_ptr()), self._stream()), "cmarl_ppo_epoch_grads")
+            return
+        _lib.check(self.lib.cmarl_ppo_epoch_grads_ex(
             self._h, self._f(params, "params"), self._f(state, "state"), self._f(obs, "obs"),
             _ptr(actions, torch.int32, self.device, "actions"), self._f(logp_old, "logp_old"), self._f(adv, "adv"),
-            self._f(returns, "returns"), _ptr(mask, torch.uint8, self.device, "mask"),
-            _ptr(avail, torch.uint8, self.device, "avail"), float(clip), float(ent_coef), self._f(grads, "grads"),
-            C.c_void_p(self.workspace.data_ptr()), self._stream()), "cmarl_ppo_epoch_grads")
+            self._f(returns, "returns"), self._f(values_old, "values_old"), _ptr(mask, torch.uint8, self.device, "mask"),
+            _ptr(avail, torch.uint8, self.device, "avail"), float(clip), float(ent_coef), float(value_clip),
+            int(env_begin), int(self.shapes.n_envs - env_begin if env_count is None else env_count),
+            self._f(grads, "grads"), C.c_void_p(self.workspace.data_ptr()), self._stream()), "cmarl_ppo_epoch_grads_ex")
 
     def clip_adam_step(self, params, grads, exp_avg, exp_avg_sq, *, step=1, step_dev=None, lr_actor=8e-4,
                        lr_critic=8e-4, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=-1.0, stats_out=None):

@@ -84,6 +84,14 @@ class Args:
     """ Device: cuda only (the reference defaults to cpu; this implementation has no CPU path)"""
     seed: int = 1
     """ Random seed"""
+    value_clip: float = -1
+    """ (beyond the reference, default off) 0< : PPO2-style clipped value loss with this range; 0> : the reference's MSE"""
+    num_minibatches: int = 1
+    """ (beyond the reference, default 1 = full batch) optimizer steps per epoch, one per contiguous block of envs"""
+
+
+# the two fields above are the options BASELINE.json's north_star names that the reference does not have (SURVEY 0.5)
+EXTENSION_FIELDS = ("value_clip", "num_minibatches")
 
 
 @dataclass
@@ -127,6 +135,10 @@ def validate_args(args: Args):
         raise SystemExit("the recurrent actor is built for --actor_hidden_dim 32 (the reference default) only")
     if args.batch_size < 1 or args.epochs < 1:
         raise SystemExit("batch_size and epochs must be positive")
+    if args.num_minibatches < 1 or args.num_minibatches > args.batch_size:
+        raise SystemExit("--num_minibatches must be in [1, batch_size]")
+    if recurrent and (args.num_minibatches != 1 or args.value_clip > 0):
+        raise SystemExit("--num_minibatches / --value_clip are implemented for the MLP actor paths only")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -268,6 +280,10 @@ class MAPPO:
         # the per-step results a caller reads back (per-env episode returns f64 [B], per-epoch statistics f32 [epochs][8])
         # live in ONE device block so that `results_to_host` is a single D2H copy
         # (+ one f64: the sum of the episode returns over ALL ranks, filled by `stage_scalars` on multi-GPU runs)
+        self.n_mb = args.num_minibatches
+        if self.B < self.n_mb:
+            raise SystemExit(f"--num_minibatches {self.n_mb} exceeds the {self.B} envs of one GPU")
+        self.mb_stats = eng.empty(args.epochs, self.n_mb, 8) if self.n_mb > 1 else None
         self.results = torch.zeros(self.B * 8 + args.epochs * 32 + 8, dtype=torch.uint8, device=eng.device)
         self.epoch_stats = self.results[self.B * 8:self.B * 8 + args.epochs * 32].view(torch.float32).view(args.epochs, 8)
         self.return_sum = self.results[self.B * 8 + args.epochs * 32:].view(torch.float64)
@@ -405,15 +421,26 @@ class MAPPO:
         if self.recurrent:
             return self.update_recurrent()
         eng, buf, a = self.engine, self.buf, self.args
+        ext = {}
+        if a.value_clip > 0:                                     # beyond the reference: V at rollout time = buf["values"]
+            ext = dict(value_clip=a.value_clip, values_old=buf["values"])
+        M = self.n_mb
         for ep in range(a.epochs):
-            eng.ppo_epoch_grads(self.net.flat, self.grads, state=buf["state"], actions=buf["actions"],
-                                logp_old=buf["logp"], adv=buf["adv"], returns=buf["returns"], clip=a.ppo_clip,
-                                ent_coef=a.entropy_coef)
-            self._allreduce_grads(self.grads)
-            eng.clip_adam_step(self.net.flat, self.grads, self.exp_avg, self.exp_avg_sq, step_dev=self.adam_step,
-                               lr_actor=a.learning_rate_actor, lr_critic=a.learning_rate_critic,
-                               max_norm=a.clip_gradients, stats_out=self.epoch_stats[ep])
-            self.training_step += 1
+            for mb in range(M):
+                if M > 1:                                        # minibatch = contiguous block of this GPU's envs
+                    lo, hi = mb * self.B // M, (mb + 1) * self.B // M
+                    ext.update(env_begin=lo, env_count=hi - lo)
+                eng.ppo_epoch_grads(self.net.flat, self.grads, state=buf["state"], actions=buf["actions"],
+                                    logp_old=buf["logp"], adv=buf["adv"], returns=buf["returns"], clip=a.ppo_clip,
+                                    ent_coef=a.entropy_coef, **ext)
+                self._allreduce_grads(self.grads)
+                eng.clip_adam_step(self.net.flat, self.grads, self.exp_avg, self.exp_avg_sq, step_dev=self.adam_step,
+                                   lr_actor=a.learning_rate_actor, lr_critic=a.learning_rate_critic,
+                                   max_norm=a.clip_gradients,
+                                   stats_out=self.epoch_stats[ep] if M == 1 else self.mb_stats[ep, mb])
+                self.training_step += 1
+        if M > 1:                                                # logged per epoch: the mean over its optimizer steps
+            torch.mean(self.mb_stats, dim=1, out=self.epoch_stats)
 
     def _iteration_eager(self, env_init=None, noise=None):
         try:
@@ -481,7 +508,7 @@ class MAPPO:
         self.episode += 1
         self.step += self.B * self.T * self.world
         self.num_episodes += self.B * self.world
-        self.training_step += self.args.epochs
+        self.training_step += self.args.epochs * self.n_mb
 
     def results_to_host(self, pinned: torch.Tensor):
         """One asynchronous D2H copy of this step's results into a pinned uint8 buffer of ``self.results.numel()`` bytes;

@@ -81,7 +81,7 @@ def main(argv=None, algo=ALGO, ippo=IPPO, args_cls=Args, run_prefix=None, traine
         trainer.iteration()
         handle = trainer.stage_scalars()            # collective on multi-GPU runs: every rank calls it
         ev = None
-        if (trainer.training_step / args.epochs) % args.eval_steps == 0:           # MME:614
+        if (trainer.training_step / (args.epochs * args.num_minibatches)) % args.eval_steps == 0:   # MME:614
             ev = evaluate_fn(trainer, args.num_eval_ep, seed=args.seed + 7919 * trainer.training_step)
         if pending is not None:
             log(pending)

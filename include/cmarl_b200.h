@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CMARL_VERSION 102
+#define CMARL_VERSION 103
 #define CMARL_N_STATS 8          /* floats appended to the flat gradient vector, see cmarl_ppo_epoch_grads */
 #define CMARL_RAW_OBS 18
 
@@ -181,6 +181,17 @@ int cmarl_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const float* stat
                           const int32_t* actions, const float* logp_old, const float* adv,
                           const float* returns, const uint8_t* mask, const uint8_t* avail,
                           double clip, double ent_coef, float* grads_out, void* workspace, void* stream);
+/* The same with the two options BASELINE.json's north_star names and the reference does NOT have (both
+ * default off, cmarl_ppo_epoch_grads == this entry with value_clip <= 0 and the env range [0, n_envs)):
+ *   minibatches   the sums run over the contiguous env block [env_begin, env_begin + env_count) only (envs are i.i.d.,
+ *                 so a block is a random minibatch); the caller steps the optimizer once per block
+ *   value_clip    > 0: critic loss max((V - R)^2, (V_old + clamp(V - V_old, -c, c) - R)^2) with V_old = values_old
+ *                 f32 [T][V][B], the critic's values at rollout time (cmarl_critic_values); <= 0: MME:554-558 as is */
+int cmarl_ppo_epoch_grads_ex(cmarl_ctx* ctx, const float* params, const float* state, const float* obs,
+                             const int32_t* actions, const float* logp_old, const float* adv,
+                             const float* returns, const float* values_old, const uint8_t* mask,
+                             const uint8_t* avail, double clip, double ent_coef, double value_clip,
+                             int32_t env_begin, int32_t env_count, float* grads_out, void* workspace, void* stream);
 
 /* -- K8: grad scaling, grad norms, optional clipping and the Adam step for both networks
  * (MME:584-594; norm_d MME:221-224; torch.optim.Adam single-tensor defaults amsgrad=False, wd=0).

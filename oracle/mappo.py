@@ -211,8 +211,15 @@ class EpochOut:
     clipfrac: torch.Tensor
 
 
+def clipped_value_loss(values, ret, values_old, value_clip):
+    """Beyond the reference (default off, BASELINE.json north_star "value-clip"): PPO2's clipped value loss, elementwise
+    ``max((V - R)^2, (V_old + clamp(V - V_old, -c, c) - R)^2)``."""
+    vc = values_old + torch.clamp(values - values_old, -value_clip, value_clip)
+    return torch.max((values - ret) ** 2, (vc - ret) ** 2)
+
+
 def ppo_epoch_loop(actor, critic, obs, actions, old_logp, critic_in, avail, mask, adv, ret,
-                   clip, ent_coef) -> EpochOut:
+                   clip, ent_coef, value_clip=-1.0, values_old=None) -> EpochOut:
     """One epoch's loss accumulation, the reference's loop over t -- MME:522-576
     (IPPO: critic on ``b_obs`` without expand, ``ippo_multienvs.py:554``)."""
     ippo = critic_in.dim() == 4
@@ -234,7 +241,10 @@ def ppo_epoch_loop(actor, critic, obs, actions, old_logp, critic_in, avail, mask
             values = critic(critic_in[:, t]).squeeze(-1)
         else:
             values = critic(critic_in[:, t]).expand(-1, n_agents)
-        critic_loss = critic_loss + F.mse_loss(values[m], ret[:, t][m]) * m.sum()
+        if value_clip > 0:
+            critic_loss = critic_loss + clipped_value_loss(values[m], ret[:, t][m], values_old[:, t][m], value_clip).mean() * m.sum()
+        else:
+            critic_loss = critic_loss + F.mse_loss(values[m], ret[:, t][m]) * m.sum()
         kl = kl + ((ratio - 1) - log_ratio)[m].mean(dim=-1).sum()
         clipped = clipped + ((ratio - 1.0).abs() > clip)[m].float().mean(dim=-1).sum()
     n = mask.sum()
@@ -242,7 +252,7 @@ def ppo_epoch_loop(actor, critic, obs, actions, old_logp, critic_in, avail, mask
 
 
 def ppo_epoch_flat(actor, critic, obs, actions, old_logp, critic_in, avail, mask, adv, ret,
-                   clip, ent_coef) -> EpochOut:
+                   clip, ent_coef, value_clip=-1.0, values_old=None) -> EpochOut:
     """Algebraically the same losses as ``ppo_epoch_loop`` without the loop over t
     (one batched pass; sums reassociated).  For sizes where the loop is too slow."""
     ippo = critic_in.dim() == 4
@@ -259,7 +269,10 @@ def ppo_epoch_flat(actor, critic, obs, actions, old_logp, critic_in, avail, mask
     v = critic(critic_in).squeeze(-1)
     if not ippo:
         v = v.unsqueeze(-1).expand_as(ret)
-    critic_loss = (((v - ret) ** 2) * w).sum()
+    if value_clip > 0:
+        critic_loss = (clipped_value_loss(v, ret, values_old, value_clip) * w).sum()
+    else:
+        critic_loss = (((v - ret) ** 2) * w).sum()
     kl = (((ratio - 1) - log_ratio) * w).sum()
     clipped = (((ratio - 1.0).abs() > clip).float() * w).sum()
     return EpochOut(actor_loss, critic_loss, ent, kl, clipped)
@@ -272,18 +285,25 @@ def norm_d(grads, d=2):
 
 
 def ppo_update(actor, critic, actor_opt, critic_opt, batch, adv, ret, *, epochs, clip, ent_coef,
-               clip_gradients=-1.0, critic_on_obs=False, flat=False, record_grads=False):
+               clip_gradients=-1.0, critic_on_obs=False, flat=False, record_grads=False,
+               value_clip=-1.0, values_old=None, num_minibatches=1):
     """The training loop MME:521-603: ``epochs`` x (loss, backward x2, grad norms, optional
-    clip, Adam step x2).  ``batch`` is the ``get_batch`` 8-tuple.  Returns per-epoch stats."""
+    clip, Adam step x2).  ``batch`` is the ``get_batch`` 8-tuple.  Returns per-epoch stats
+    (one entry per optimizer step).  ``value_clip`` / ``num_minibatches`` are the default-off
+    extensions BASELINE.json names (not in the reference): minibatch m = the contiguous env
+    block ``[m * B / M, (m + 1) * B / M)``, one optimizer step per block."""
     obs, actions, old_logp, reward, states, avail, done, mask = batch
     critic_in = obs if critic_on_obs else states
     epoch_fn = ppo_epoch_flat if flat else ppo_epoch_loop
     stats = {k: [] for k in ("actor_loss", "critic_loss", "entropy", "kl", "clipfrac",
                              "actor_grad_norm", "critic_grad_norm")}
     grads = []
-    for _ in range(epochs):
-        out = epoch_fn(actor, critic, obs, actions, old_logp, critic_in, avail, mask, adv, ret,
-                       clip, ent_coef)
+    B = obs.shape[0]
+    blocks = [slice(m * B // num_minibatches, (m + 1) * B // num_minibatches) for m in range(num_minibatches)]
+    for sl in [s for _ in range(epochs) for s in blocks]:
+        kw = {} if value_clip <= 0 else dict(value_clip=value_clip, values_old=values_old[sl])
+        out = epoch_fn(actor, critic, obs[sl], actions[sl], old_logp[sl], critic_in[sl], avail[sl], mask[sl], adv[sl],
+                       ret[sl], clip, ent_coef, **kw)
         actor_opt.zero_grad()
         critic_opt.zero_grad()
         out.actor_loss.backward()

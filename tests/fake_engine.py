@@ -166,7 +166,8 @@ class OracleEngine:
             xv.copy_((xv - mu) / sd)
 
     def ppo_epoch_grads(self, params, grads, *, state=None, obs=None, actions, logp_old, adv, returns, mask=None,
-                        avail=None, clip=0.2, ent_coef=0.001):
+                        avail=None, clip=0.2, ent_coef=0.001, value_clip=-1.0, values_old=None, env_begin=0,
+                        env_count=None):
         s = self.shapes
         actor, critic = self._nets(params[:self.n_actor], params[self.n_actor:])
         T, B, N = s.n_steps, s.n_envs, s.n_agents
@@ -174,8 +175,12 @@ class OracleEngine:
         m = torch.ones(B, T, dtype=torch.bool) if mask is None else mask.t().bool()
         av = torch.ones(B, T, N, s.n_actions, dtype=torch.bool) if avail is None else avail.permute(3, 0, 1, 2).bool()
         exp = lambda x: x.permute(2, 0, 1).expand(B, T, N) if x.shape[1] == 1 else x.permute(2, 0, 1)
-        out = om.ppo_epoch_flat(actor, critic, o, actions.permute(2, 0, 1).long(), logp_old.permute(2, 0, 1),
-                                o if s.critic_on_obs else state.permute(2, 0, 1), av, m, exp(adv), exp(returns), clip, ent_coef)
+        sl = slice(env_begin, B if env_count is None else env_begin + env_count)
+        kw = {} if value_clip <= 0 else dict(value_clip=value_clip, values_old=exp(values_old)[sl])
+        out = om.ppo_epoch_flat(actor, critic, o[sl], actions.permute(2, 0, 1).long()[sl], logp_old.permute(2, 0, 1)[sl],
+                                (o if s.critic_on_obs else state.permute(2, 0, 1))[sl], av[sl], m[sl], exp(adv)[sl],
+                                exp(returns)[sl], clip, ent_coef, **kw)
+        m = m[sl]
         out.actor_loss.backward(); out.critic_loss.backward()
         n = float(m.sum())
         grads[:self.n_actor] = actor.flat_grads() * n

@@ -751,3 +751,95 @@ def test_whole_update_at_baseline_size(cm, ippo):
     dp = (params.cpu() - final).abs()
     # (a gradient within ~1e-7 of Adam's eps = 1e-8 turns a 1e-9 reassociation difference into a visible fraction of lr)
     assert (dp < 1e-6).float().mean() > 0.995 and dp.max().item() < 2e-5, (dp.max().item(), (dp < 1e-6).float().mean().item())
+
+
+# ----------------------------------------------------------------------------------------- beyond-reference options (north_star)
+@pytest.mark.parametrize("tc", TC, ids=["ffma", "tc"])
+@pytest.mark.parametrize("ippo", [False, True], ids=["mappo", "ippo"])
+def test_value_clip_and_minibatch_gradients(cm, ippo, tc):
+    """cmarl_ppo_epoch_grads_ex: the clipped value loss and the env-block (minibatch) range against the oracle's
+    autograd on the same block (ragged masks, random avail), blocks that start / end inside a 128-sample tile; and the
+    plain entry == the _ex entry with the options off, bit for bit."""
+    from cleanmarl_b200 import engine as E
+    B, Tn = 700, 25
+    actor, critic = om.build_networks(5, state_dim=21 if ippo else 54, critic_hidden=32 if ippo else 64)
+    batch = list(om.synthetic_batch(B, seed=3, actor=actor))
+    gen = torch.Generator().manual_seed(3)
+    batch[7] = ragged_mask(B, Tn, gen) & ~_relu_kink_samples(actor, critic, batch[0], batch[0] if ippo else batch[4])
+    V = 3 if ippo else 1
+    adv = (torch.randn(B, Tn, V, generator=gen) * 3).expand(B, Tn, 3).contiguous()
+    ret = (torch.randn(B, Tn, V, generator=gen) * 5).expand(B, Tn, 3).contiguous()
+    v_old = (ret[..., :V] + torch.randn(B, Tn, V, generator=gen) * 0.6).expand(B, Tn, 3).contiguous()   # |V - V_old| both sides of 0.2
+    eng = make_engine(cm, B, tc=tc, critic_on_obs=ippo, critic_hidden=32 if ippo else 64)
+    dev = eng.device
+    d = E.to_device_layout(tuple(batch), dev, with_obs=False)
+    params = flat_params(actor, critic, dev)
+    kw = dict(state=d["state"], actions=d["actions"], logp_old=d["logp"], adv=E.heads_to_device(adv, eng.n_heads, dev),
+              returns=E.heads_to_device(ret, eng.n_heads, dev), mask=d["mask"], clip=0.2, ent_coef=0.001)
+    vold_d = E.heads_to_device(v_old, eng.n_heads, dev)
+    g0, g1 = eng.empty(eng.n_params + 8), eng.empty(eng.n_params + 8)
+    eng.ppo_epoch_grads(params, g0, **kw)
+    eng.ppo_epoch_grads(params, g1, **kw, value_clip=-1.0, values_old=vold_d, env_begin=0, env_count=B)
+    assert torch.equal(g0, g1)
+    obs, actions, logp, reward, states, avail, done, mask = batch
+    for lo, hi, vc in ((0, B, 0.2), (0, 233, 0.2), (233, 466, -1.0), (466, 700, 0.2), (130, 131, 0.2)):
+        sl = slice(lo, hi)
+        eng.ppo_epoch_grads(params, g1, **kw, value_clip=vc, values_old=vold_d, env_begin=lo, env_count=hi - lo)
+        actor.zero_grad(); critic.zero_grad()
+        ext = {} if vc <= 0 else dict(value_clip=vc, values_old=v_old[sl])
+        out = om.ppo_epoch_flat(actor, critic, obs[sl], actions[sl], logp[sl], (obs if ippo else states)[sl], avail[sl],
+                                mask[sl], adv[sl], ret[sl], 0.2, 0.001, **ext)
+        out.actor_loss.backward(); out.critic_loss.backward()
+        g = g1.cpu()
+        n = g[eng.n_params + 5].item()
+        assert n == float(mask[sl].sum())
+        ref = torch.cat([actor.flat_grads(), critic.flat_grads()])
+        off = 0
+        for net in (actor, critic):
+            for p in net.parameters():
+                k = p.numel()
+                a, b = g[off:off + k] / n, ref[off:off + k]
+                scale = max(b.abs().max().item(), 1e-6)
+                assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-9, (lo, hi, vc, tuple(p.shape))
+                off += k
+        assert abs(g[eng.n_params + 1].item() / n - out.critic_loss.item()) < 1e-5 * abs(out.critic_loss.item())
+        assert abs(g[eng.n_params + 0].item() / n - out.actor_loss.item()) < 1e-5 * abs(out.actor_loss.item()) + 1e-7
+
+
+def test_trainer_with_value_clip_and_minibatches(cm):
+    """--value_clip 0.2 --num_minibatches 4 through the trainer (graph replay == eager, 12 optimizer steps per iteration)
+    against the oracle's update with the same options."""
+    from cleanmarl_b200.mappo import MAPPO, Args
+    from cleanmarl_b200 import engine as E
+    B = 520
+    g = torch.Generator().manual_seed(B)
+    env = torch.zeros(18, B, dtype=torch.float64)
+    env[0:6] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    env[12:18] = torch.rand(6, B, generator=g, dtype=torch.float64) * 2 - 1
+    noise = torch.empty(25, 3, 5, B).exponential_(1, generator=g)
+    tr = MAPPO(Args(batch_size=B, seed=6, value_clip=0.2, num_minibatches=4), use_graph=False)
+    tr.iteration(env.cuda(), noise.cuda())
+    torch.cuda.synchronize()
+    assert tr.training_step == 12
+    actor, critic = om.build_networks(6)
+    batch = tuple(t.cpu() for t in tr.get_batch())
+    ret, adv = om.td_lambda_batched(critic, batch[4], batch[3], batch[7], 0.99, 0.95, 3)
+    with torch.no_grad():
+        v_old = critic(batch[4]).expand(B, 25, 3).contiguous()
+    aopt, copt = om.make_optimizers(actor, critic)
+    st = om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001, flat=True,
+                       value_clip=0.2, values_old=v_old, num_minibatches=4)
+    dp = (tr.net.flat.cpu() - torch.cat([actor.flat_params(), critic.flat_params()])).abs()
+    assert (dp < 3e-6).float().mean() > 0.99 and dp.max() < 2e-4
+    s = tr.epoch_stats.cpu()
+    for ep in range(3):
+        assert abs(s[ep, 1].item() - np.mean(st["critic_loss"][4 * ep:4 * ep + 4])) < 2e-5 * abs(s[ep, 1].item())
+    # graph replay of the 12-step iteration == eager
+    outs = []
+    for graph in (False, True):
+        t2 = MAPPO(Args(batch_size=B, seed=6, value_clip=0.2, num_minibatches=4), use_graph=graph)
+        for _ in range(3):
+            t2.iteration()
+        torch.cuda.synchronize()
+        outs.append((t2.net.flat.clone(), t2.epoch_stats.clone(), t2.training_step))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2] == 36

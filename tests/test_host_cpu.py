@@ -35,7 +35,7 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, s), f"{s} declared in include/cmarl_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == syms, "cleanmarl_b200/_lib.py must bind exactly the header's entry points"
     _lib.load()
-    assert _lib.load().cmarl_version() == _lib.VERSION == 102
+    assert _lib.load().cmarl_version() == _lib.VERSION == 103
 
 
 def test_no_gpu_fails_loudly():
@@ -81,7 +81,9 @@ def test_args_mirror_the_reference_dataclass():
     singles = [(n, importlib.import_module(f"cleanmarl_b200.single.{n}").Args) for n in ("mappo", "ippo", "mappo_lstm", "ippo_lstm")]
     for name, cls in [("mappo_multienvs", Args), ("ippo_multienvs", IppoArgs), ("mappo_lstm_multienvs", LstmArgs),
                       ("ippo_lstm_multienvs", IppoLstmArgs)] + singles:
-        ours = {f.name: f for f in dataclasses.fields(cls)}
+        from cleanmarl_b200.mappo import EXTENSION_FIELDS
+        ours = {f.name: f for f in dataclasses.fields(cls) if f.name not in EXTENSION_FIELDS}
+        assert all(f.default in (-1, 1) for f in dataclasses.fields(cls) if f.name in EXTENSION_FIELDS)   # default off
         theirs = {f["name"]: f for f in ref[name]}
         assert sorted(ours) == sorted(theirs)            # (ippo_multienvs.py lists ppo_clip/entropy_coef before epochs;
         if name == "mappo_multienvs":                    #  flag order is irrelevant to the keyword CLI)
@@ -164,6 +166,37 @@ def test_trainer_iteration_matches_oracle_update():
     assert (tr.net.flat - final).abs().max() < 1e-6
     sc = tr.train_scalars()
     assert abs(sc["actor_loss"] - np.mean(st["actor_loss"])) < 1e-5 * abs(np.mean(st["actor_loss"])) + 1e-7
+
+
+def test_trainer_extensions_value_clip_and_minibatches():
+    """The two default-off options beyond the reference (--value_clip, --num_minibatches): the trainer's loop (one
+    optimizer step per contiguous env block, clipped value loss against the rollout-time values) on the CPU double ==
+    the oracle's ppo_update with the same options; and with the options at their defaults nothing changes."""
+    from oracle import mappo as om
+    B = 12
+    env, noise = _inputs(B)
+    tr = _trainer(B, value_clip=0.2, num_minibatches=3)
+    tr.iteration(env.clone(), noise)
+    assert tr.training_step == 9 and tr.step == B * 25
+    batch = tr.get_batch()
+    actor, critic = om.build_networks(3)
+    ret, adv = om.td_lambda_batched(critic, batch[4], batch[3], batch[7], 0.99, 0.95, 3)
+    with torch.no_grad():
+        v_old = critic(batch[4]).expand(B, 25, 3).contiguous()
+    aopt, copt = om.make_optimizers(actor, critic)
+    st = om.ppo_update(actor, critic, aopt, copt, batch, adv, ret, epochs=3, clip=0.2, ent_coef=0.001, flat=True,
+                       value_clip=0.2, values_old=v_old, num_minibatches=3)
+    assert len(st["actor_loss"]) == 9
+    assert (tr.net.flat - torch.cat([actor.flat_params(), critic.flat_params()])).abs().max() < 1e-6
+    sc = tr.train_scalars()
+    assert abs(sc["critic_loss"] - np.mean(st["critic_loss"])) < 1e-5 * abs(np.mean(st["critic_loss"])) + 1e-7
+    # the clipped loss really differs from the plain MSE on this batch
+    plain = _trainer(B)
+    plain.iteration(env.clone(), noise)
+    assert (plain.net.flat - tr.net.flat).abs().max() > 1e-5
+    off = _trainer(B, value_clip=-1, num_minibatches=1)
+    off.iteration(env.clone(), noise)
+    assert torch.equal(off.net.flat, plain.net.flat)
 
 
 def test_recurrent_trainer_iteration_matches_oracle_update():
