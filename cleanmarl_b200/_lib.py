@@ -15,7 +15,7 @@ LIB_PATH = Path(os.environ.get("CMARL_B200_LIB", PKG / "libcmarl_b200.so"))
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "device", "n_envs", "n_steps", "n_agents", "obs_dim", "state_dim", "n_actions",
-        "actor_hidden", "actor_layers", "critic_hidden", "critic_layers", "critic_on_obs", "actor_recurrent")]
+        "actor_hidden", "actor_layers", "critic_hidden", "critic_layers", "critic_on_obs", "actor_recurrent", "n_landmarks")]
 
 
 class CmarlError(RuntimeError):

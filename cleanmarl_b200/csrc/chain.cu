@@ -329,6 +329,14 @@ static void critic_desc(const cmarl_ctx* ctx, const float* params, const float* 
 
 using namespace chain;
 
+// generic.cu
+int cmarl_gen_critic_values(cmarl_ctx* ctx, const float* critic_params, const float* state, const float* obs, float* values,
+                            void* workspace, cudaStream_t st);
+int cmarl_gen_ppo_epoch_grads(cmarl_ctx* ctx, const float* params, const float* state, const float* obs, const int32_t* actions,
+                              const float* logp_old, const float* adv, const float* returns, const float* values_old,
+                              const uint8_t* mask, const uint8_t* avail, double clip, double ent_coef, double value_clip,
+                              int env_count, float* grads_out, void* workspace, cudaStream_t st);
+
 // tc_chain.cu
 int cmarl_tc_setup();
 int cmarl_tc_tile();
@@ -381,6 +389,7 @@ int cmarl_chain_setup(cmarl_ctx* ctx) {
 
 extern "C" size_t cmarl_workspace_bytes(const cmarl_ctx* ctx) {
     if (!ctx) return 0;
+    if (ctx->generic) return 256;      // the layered kernels use the context's own scratch block
     // the actor grid may be larger when obs is passed explicitly (21 rows still use the 24-row config)
     // up to two persistent CTAs per SM (tensor-core kernels of the 32-wide networks), one partial row per CTA
     // (the recurrent chunk kernel, gru.cu, launches at most one CTA per SM: covered as well)
@@ -393,6 +402,7 @@ extern "C" int cmarl_critic_values(cmarl_ctx* ctx, const float* critic_params, c
                                    float* values, void* stream) {
     CMARL_ARG(ctx && critic_params && values, "null argument");
     CMARL_ARG(ctx->cfg.critic_on_obs ? (state || obs) : (state != nullptr), "critic input missing");
+    if (ctx->generic) return cmarl_gen_critic_values(ctx, critic_params, state, obs, values, ctx->gen_ws, as_stream(stream));
     NetDesc nd; TileSrc src;
     critic_desc(ctx, critic_params, state, obs, nd, src);
     ValueHeadArgs ha;
@@ -437,6 +447,9 @@ extern "C" int cmarl_ppo_epoch_grads_ex(cmarl_ctx* ctx, const float* params, con
         if (mask) mask += env_begin;
         if (avail) avail += env_begin;
     }
+    if (ctx->generic)
+        return cmarl_gen_ppo_epoch_grads(ctx, params, state, obs, actions, logp_old, adv, returns, values_old, mask, avail, clip,
+                                         ent_coef, value_clip, env_count, grads_out, ctx->gen_ws, st);
 
     NetDesc nda; TileSrc srca;
     actor_desc(ctx, params, state, obs, nda, srca);
@@ -498,6 +511,7 @@ extern "C" int cmarl_critic_epoch_grads(cmarl_ctx* ctx, const float* critic_para
                                         void* stream) {
     CMARL_ARG(ctx && critic_params && returns && grads_out && workspace, "null argument");
     CMARL_ARG(ctx->cfg.critic_on_obs ? (state || obs) : (state != nullptr), "critic input missing");
+    CMARL_ARG(!ctx->generic, "the per-network entries serve the recurrent path (default shapes only)");
     cudaStream_t st = as_stream(stream);
     const int Pc = ctx->critic.count;
     float* part_c = reinterpret_cast<float*>(workspace);

@@ -12,6 +12,7 @@ extern "C" size_t cmarl_comm_bytes(void) { return sizeof(CommChannel) * CMARL_CO
 extern "C" int cmarl_comm_create(cmarl_ctx* ctx, uint8_t* handle_out) {
     CMARL_ARG(ctx && handle_out, "null argument");
     CMARL_ARG(ctx->comm.own == nullptr, "comm block already created");
+    CMARL_ARG(!ctx->generic, "the peer-memory exchange is fused into clip_adam_kernel (default shapes); layered shapes use the NCCL all-reduce");
     void* p = nullptr;
     CMARL_CUDA(cudaMalloc(&p, cmarl_comm_bytes()));          // the one device allocation the library makes: it must be
     CMARL_CUDA(cudaMemset(p, 0, cmarl_comm_bytes()));        // a whole cudaMalloc block to be IPC-exportable

@@ -67,6 +67,30 @@ struct cmarl_comm {
     void* own;                                              // this rank's allocation (cudaFree at detach)
 };
 
+// Generic ("layered") networks: any number of hidden layers / hidden width / agent count the reference's CLI accepts
+// beyond the shapes the fused kernels are built for (csrc/generic.cu).  n_lin Linear layers, dims[0] -> ... -> dims[n_lin];
+// parameters in torch parameters() order (W_l [dims[l+1]][dims[l]] then b_l).
+constexpr int CMARL_GEN_MAX_LIN = 8;        // hidden layers + 2 (MME:160-171: num_layer hidden->hidden blocks)
+constexpr int CMARL_GEN_MAX_DIM = 256;      // widest layer
+struct GenNet {
+    int n_lin;
+    int dims[CMARL_GEN_MAX_LIN + 1];
+    int w_off[CMARL_GEN_MAX_LIN], b_off[CMARL_GEN_MAX_LIN];
+    int count;
+    void set(int in, int hid, int hidden_layers, int out) {
+        n_lin = hidden_layers + 2;
+        dims[0] = in;
+        for (int l = 1; l < n_lin; ++l) dims[l] = hid;
+        dims[n_lin] = out;
+        int o = 0;
+        for (int l = 0; l < n_lin; ++l) {
+            w_off[l] = o; o += dims[l + 1] * dims[l];
+            b_off[l] = o; o += dims[l + 1];
+        }
+        count = o;
+    }
+};
+
 enum KernelId { K_RESET = 0, K_ENVSTEP, K_ROLLOUT, K_ACT, K_CRITIC, K_TD, K_NORM, K_PPO_ACTOR, K_PPO_CRITIC,
                 K_PPO_REDUCE, K_ADAM, K_TBPTT };
 static_assert(K_TBPTT + 1 == CMARL_NK, "kernel id table");
@@ -83,6 +107,10 @@ struct cmarl_ctx {
     cmarl_config cfg;
     NetLayout actor, critic;
     GruLayout gru;      // recurrent actor (cfg.actor_recurrent): then actor.count == gru.count
+    int generic;        // 1: shapes outside the fused kernels' set -> every entry runs the layered kernels of generic.cu
+    int n_landmarks;    // L (= n_agents in simple_spread_v3)
+    int raw_obs;        // R = 4 + 2 L + 4 (N - 1): vel, pos, landmarks - pos, others - pos, 2 silent comm slots per other
+    GenNet gactor, gcritic;
     int n_heads;        // V
     int critic_in;      // S (MAPPO) or O (IPPO)
     int sm_count;
@@ -95,9 +123,11 @@ struct cmarl_ctx {
     uint64_t* episode_dev;   // optional device episode counter for the Philox draws (CUDA-graph replay)
     int launch_chaining;     // 1: launches carry the programmatic-stream-serialization attribute (cmarl_ctx_set_launch_chaining)
     cmarl_timing* timing;
+    void* gen_ws;            // generic mode: scratch block of the layered kernels (activations, partials), owned by the context
+    float* dev_floats;       // CMARL_DEV_FLOATS device floats owned by the context (generic Adam: per-tensor sums of squares)
     unsigned int* dev_words; // CMARL_DEV_WORDS zero-initialised device words owned by the context (tickets of the kernels' last-CTA protocols)
 };
-enum { CMARL_DW_ADAM_TICKET = 0, CMARL_DW_CHAIN_TICKET_A = 1, CMARL_DW_CHAIN_TICKET_C = 2, CMARL_DEV_WORDS = 64 };
+enum { CMARL_DW_ADAM_TICKET = 0, CMARL_DW_CHAIN_TICKET_A = 1, CMARL_DW_CHAIN_TICKET_C = 2, CMARL_DEV_WORDS = 64, CMARL_DEV_FLOATS = 64 };
 constexpr int CMARL_MAX_PARAMS = 16384;     // per context (clip_adam_kernel: 1024 threads x 16; = CMARL_COMM_SLOT_FLOATS)
 
 void cmarl_time_begin(cmarl_ctx* ctx, int id, cudaStream_t st);

@@ -22,6 +22,8 @@ int cmarl_check_cuda(cudaError_t e, const char* what) {
 int cmarl_chain_setup(cmarl_ctx* ctx);   // chain.cu: shared-memory attributes + grid sizes
 int cmarl_rollout_setup(cmarl_ctx* ctx); // rollout.cu: shared-memory attributes
 int cmarl_gru_setup(cmarl_ctx* ctx);     // gru.cu: shared-memory attributes of the recurrent kernels
+int cmarl_gen_setup(cmarl_ctx* ctx);     // generic.cu: shared-memory attribute of the layered rollout kernel
+size_t cmarl_gen_workspace_bytes(const cmarl_ctx* ctx);
 
 extern "C" int cmarl_version(void) { return CMARL_VERSION; }
 extern "C" const char* cmarl_last_error(void) { return g_err; }
@@ -30,18 +32,23 @@ extern "C" int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out) {
     CMARL_ARG(cfg && out, "null argument");
     *out = nullptr;
     CMARL_ARG(cfg->n_envs >= 1 && cfg->n_steps >= 1, "n_envs and n_steps must be positive");
-    CMARL_ARG(cfg->n_agents == 3, "simple_spread_v3 has 3 agents (only N=3 is built)");
+    const int N = cfg->n_agents, L = cfg->n_landmarks > 0 ? cfg->n_landmarks : cfg->n_agents;
+    CMARL_ARG(N >= 1 && N <= 8 && L >= 1 && L <= 8, "simple_spread: 1 <= n_agents, n_landmarks <= 8");
+    const int R = 4 + 2 * L + 4 * (N - 1);      // vel, pos, landmarks - pos, others - pos, 2 silent comm slots per other agent
     CMARL_ARG(cfg->n_actions == 5, "simple_spread_v3 has 5 discrete actions (only A=5 is built)");
-    CMARL_ARG(cfg->state_dim == cfg->n_agents * CMARL_RAW_OBS, "state_dim must be n_agents*18");
-    CMARL_ARG(cfg->obs_dim == CMARL_RAW_OBS || cfg->obs_dim == CMARL_RAW_OBS + cfg->n_agents,
-              "obs_dim must be 18 (no ids) or 18+n_agents (agent ids)");
-    CMARL_ARG(cfg->actor_layers == 1 && cfg->critic_layers == 1,
-              "only *_num_layers == 1 (the reference default) is built");
-    CMARL_ARG(cfg->actor_hidden == 32 || cfg->actor_hidden == 64, "actor_hidden_dim must be 32 or 64");
-    CMARL_ARG(cfg->critic_hidden == 32 || cfg->critic_hidden == 64, "critic_hidden_dim must be 32 or 64");
+    CMARL_ARG(cfg->state_dim == N * R, "state_dim must be n_agents * (4 + 2 L + 4 (N - 1))  (54 for N = L = 3)");
+    CMARL_ARG(cfg->obs_dim == R || cfg->obs_dim == R + N, "obs_dim must be the raw width (no ids) or raw + n_agents (agent ids)");
+    CMARL_ARG(cfg->actor_layers >= 1 && cfg->actor_layers <= CMARL_GEN_MAX_LIN - 2 && cfg->critic_layers >= 1 &&
+                  cfg->critic_layers <= CMARL_GEN_MAX_LIN - 2, "*_num_layers must be in [1, 6]");
+    CMARL_ARG(cfg->actor_hidden >= 1 && cfg->actor_hidden <= CMARL_GEN_MAX_DIM && cfg->critic_hidden >= 1 &&
+                  cfg->critic_hidden <= CMARL_GEN_MAX_DIM, "*_hidden_dim must be in [1, 256]");
     CMARL_ARG(cfg->critic_on_obs == 0 || cfg->critic_on_obs == 1, "critic_on_obs must be 0 or 1");
     CMARL_ARG(cfg->actor_recurrent == 0 || cfg->actor_recurrent == 1, "actor_recurrent must be 0 or 1");
-    CMARL_ARG(!cfg->actor_recurrent || cfg->actor_hidden == 32, "the recurrent actor is built for actor_hidden_dim 32 only");
+    // the fused kernels' problem: N = L = 3, one hidden->hidden block, hidden 32 or 64; everything else is layered (generic.cu)
+    const bool fused = N == 3 && L == 3 && cfg->actor_layers == 1 && cfg->critic_layers == 1 &&
+                       (cfg->actor_hidden == 32 || cfg->actor_hidden == 64) && (cfg->critic_hidden == 32 || cfg->critic_hidden == 64);
+    CMARL_ARG(!cfg->actor_recurrent || (fused && cfg->actor_hidden == 32),
+              "the recurrent actor is built for the reference's default shapes only (3 agents, actor_hidden_dim 32, critic_num_layers 1)");
     int ndev = 0;
     CMARL_CUDA(cudaGetDeviceCount(&ndev));
     CMARL_ARG(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device (there is no CPU fallback)");
@@ -56,14 +63,20 @@ extern "C" int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out) {
     cmarl_ctx* ctx = (cmarl_ctx*)calloc(1, sizeof(cmarl_ctx));
     CMARL_ARG(ctx, "out of host memory");
     ctx->cfg = *cfg;
+    ctx->generic = fused ? 0 : 1;
+    ctx->n_landmarks = L;
+    ctx->raw_obs = R;
     ctx->n_heads = cfg->critic_on_obs ? cfg->n_agents : 1;
     ctx->critic_in = cfg->critic_on_obs ? cfg->obs_dim : cfg->state_dim;
     ctx->actor.set(cfg->obs_dim, cfg->actor_hidden, cfg->n_actions);
     ctx->critic.set(ctx->critic_in, cfg->critic_hidden, 1);
     ctx->gru.set(cfg->obs_dim, cfg->actor_hidden, cfg->n_actions);
     if (cfg->actor_recurrent) ctx->actor.count = ctx->gru.count;
+    ctx->gactor.set(cfg->obs_dim, cfg->actor_hidden, cfg->actor_layers, cfg->n_actions);
+    ctx->gcritic.set(ctx->critic_in, cfg->critic_hidden, cfg->critic_layers, 1);
+    if (ctx->generic) { ctx->actor.count = ctx->gactor.count; ctx->critic.count = ctx->gcritic.count; }
     ctx->sm_count = prop.multiProcessorCount;
-    if (ctx->actor.count + ctx->critic.count + CMARL_N_STATS > CMARL_MAX_PARAMS) {
+    if (!ctx->generic && ctx->actor.count + ctx->critic.count + CMARL_N_STATS > CMARL_MAX_PARAMS) {
         cmarl_set_error("cmarl_ctx_create: %d parameters (limit %d)", ctx->actor.count + ctx->critic.count, CMARL_MAX_PARAMS - CMARL_N_STATS);
         free(ctx);
         return -1;
@@ -71,12 +84,21 @@ extern "C" int cmarl_ctx_create(const cmarl_config* cfg, cmarl_ctx** out) {
     {
         int me = cmarl_check_cuda(cudaMalloc(&ctx->dev_words, CMARL_DEV_WORDS * sizeof(unsigned int)), "cudaMalloc(dev_words)");
         if (!me) me = cmarl_check_cuda(cudaMemset(ctx->dev_words, 0, CMARL_DEV_WORDS * sizeof(unsigned int)), "cudaMemset(dev_words)");
-        if (me) { free(ctx); return me; }
+        if (!me) me = cmarl_check_cuda(cudaMalloc(&ctx->dev_floats, CMARL_DEV_FLOATS * sizeof(float)), "cudaMalloc(dev_floats)");
+        if (me) { cudaFree(ctx->dev_words); free(ctx); return me; }
     }
-    int e = cmarl_chain_setup(ctx);
-    if (!e) e = cmarl_gru_setup(ctx);
-    if (!e) e = cmarl_rollout_setup(ctx);
-    if (e) { cudaFree(ctx->dev_words); free(ctx); return e; }
+    int e = 0;
+    if (ctx->generic) {
+        // the layered kernels keep their activations in a scratch block owned by the context (the entry points of the
+        // fused path that have no workspace argument -- cmarl_critic_values -- need it too)
+        e = cmarl_gen_setup(ctx);
+        if (!e) e = cmarl_check_cuda(cudaMalloc(&ctx->gen_ws, cmarl_gen_workspace_bytes(ctx)), "cudaMalloc(generic workspace)");
+    } else {
+        e = cmarl_chain_setup(ctx);
+        if (!e) e = cmarl_gru_setup(ctx);
+        if (!e) e = cmarl_rollout_setup(ctx);
+    }
+    if (e) { cudaFree(ctx->gen_ws); cudaFree(ctx->dev_floats); cudaFree(ctx->dev_words); free(ctx); return e; }
     *out = ctx;
     return 0;
 }
@@ -155,6 +177,8 @@ extern "C" int cmarl_ctx_destroy(cmarl_ctx* ctx) {
         free(ctx->timing);
     }
     if (ctx && ctx->dev_words) cudaFree(ctx->dev_words);
+    if (ctx && ctx->dev_floats) cudaFree(ctx->dev_floats);
+    if (ctx && ctx->gen_ws) cudaFree(ctx->gen_ws);
     free(ctx);
     return 0;
 }

@@ -397,6 +397,11 @@ static void fill_comm(const cmarl_ctx* ctx, AdamArgs& a, int channel) {
     for (int r = 0; r < CMARL_MAX_RANKS; ++r) a.ch[r] = (r < ctx->comm.world && ctx->comm.base[r]) ? ctx->comm.base[r] + channel : nullptr;
 }
 
+// generic.cu
+int cmarl_gen_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t step,
+                             int32_t* step_dev, double lr_actor, double lr_critic, double beta1, double beta2, double eps,
+                             double max_norm, float* stats_out, cudaStream_t st);
+
 extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, float* exp_avg,
                                     float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor,
                                     double lr_critic, double beta1, double beta2, double eps, double max_norm,
@@ -404,6 +409,9 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     CMARL_ARG(ctx && params && grads && exp_avg && exp_avg_sq, "null argument");
     CMARL_ARG(step_dev || step >= 1, "step must be >= 1");
     CMARL_ARG(!ctx->cfg.actor_recurrent, "recurrent actor: use cmarl_adam_step_net");
+    if (ctx->generic)
+        return cmarl_gen_clip_adam_step(ctx, params, grads, exp_avg, exp_avg_sq, step, step_dev, lr_actor, lr_critic, beta1, beta2, eps,
+                                        max_norm, stats_out, as_stream(stream));
     CMARL_ARG(ctx->actor.count + ctx->critic.count <= ADAM_THREADS * ADAM_PER_THREAD, "too many parameters for clip_adam_kernel");
     AdamArgs a;
     a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
@@ -441,6 +449,7 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     CMARL_ARG(net == 0 || net == 1, "net must be 0 (actor) or 1 (critic)");
     CMARL_ARG(step_dev || step >= 1, "step must be >= 1");
     CMARL_ARG(extra_div >= 1.0, "extra_div must be >= 1");
+    CMARL_ARG(!ctx->generic, "the per-network entries serve the recurrent path (default shapes only)");
     AdamArgs a;
     a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
     a.step_dev = step_dev; a.step = step; a.ticket = ctx->dev_words + CMARL_DW_ADAM_TICKET;

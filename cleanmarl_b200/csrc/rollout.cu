@@ -7,12 +7,15 @@
 // the stand-alone Actor.act entry keeps one thread per (env, agent).
 #include "common.cuh"
 #include "spread.cuh"
+#include "sample.cuh"
 
 namespace {
 
 constexpr int EPB = 32;            // envs per CTA
 constexpr int NAG = 3;             // agents
-constexpr int NACT = 5;
+constexpr int NACT = sample::NACT;
+using sample::race_sample;
+using sample::philox_exp5;
 constexpr int RT = EPB * NAG;      // threads per CTA
 
 template <int H>
@@ -102,45 +105,6 @@ __device__ __forceinline__ void actor_mlp(const float (&x)[KX], const float* __r
         z[0] = fmaf(hk, w.x, z[0]); z[1] = fmaf(hk, w.y, z[1]); z[2] = fmaf(hk, w.z, z[2]);
         z[3] = fmaf(hk, w.w, z[3]); z[4] = fmaf(hk, w4, z[4]);
     }
-}
-
-// Categorical(logits=z).sample() as the exponential race torch.multinomial runs on CPU
-// (argmax(probs / q), first maximum wins) + log_prob of the drawn action (MME:174-176).
-__device__ __forceinline__ void race_sample(const float (&z)[NACT], const float (&q)[NACT], int& action, float& logp) {
-    float mx = z[0];
-#pragma unroll
-    for (int a = 1; a < NACT; ++a) mx = fmaxf(mx, z[a]);
-    float se = 0.0f;
-#pragma unroll
-    for (int a = 0; a < NACT; ++a) se += expf(z[a] - mx);
-    const float lse = mx + logf(se);
-    float l[NACT], p[NACT];
-    float mx2 = -INFINITY;
-#pragma unroll
-    for (int a = 0; a < NACT; ++a) { l[a] = z[a] - lse; mx2 = fmaxf(mx2, l[a]); }
-    float se2 = 0.0f;
-#pragma unroll
-    for (int a = 0; a < NACT; ++a) { p[a] = expf(l[a] - mx2); se2 += p[a]; }
-    float best = -1.0f;
-    action = 0;
-    logp = l[0];
-#pragma unroll
-    for (int a = 0; a < NACT; ++a) {
-        const float r = (p[a] / se2) / q[a];
-        if (r > best) { best = r; action = a; logp = l[a]; }
-    }
-}
-
-__device__ __forceinline__ void philox_exp5(uint64_t seed, uint64_t episode, uint32_t t, uint32_t n, uint32_t b,
-                                            float (&q)[NACT]) {
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const Philox4 r0 = philox4x32_10(b, t * 8u + n, (uint32_t)episode, (uint32_t)(episode >> 32) ^ 0x51u, k0, k1);
-    const Philox4 r1 = philox4x32_10(b, t * 8u + n, (uint32_t)episode, (uint32_t)(episode >> 32) ^ 0xA3u, k0, k1);
-    q[0] = -logf(u32_to_unit_open0(r0.x)); q[1] = -logf(u32_to_unit_open0(r0.y));
-    q[2] = -logf(u32_to_unit_open0(r0.z)); q[3] = -logf(u32_to_unit_open0(r0.w));
-    q[4] = -logf(u32_to_unit_open0(r1.x));
-#pragma unroll
-    for (int a = 0; a < NACT; ++a) q[a] = fmaxf(q[a], 1e-30f);
 }
 
 struct RolloutArgs {
@@ -639,6 +603,14 @@ extern "C" int cmarl_debug_rollout_timeline(long long* out_host16) {
     return (int)cudaMemcpyFromSymbol(out_host16, g_roll_tl, sizeof(long long) * 16);
 }
 
+// generic.cu: the layered kernels behind the same entries when cmarl_ctx.generic is set
+int cmarl_gen_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, cudaStream_t st);
+int cmarl_gen_env_step(cmarl_ctx* ctx, double* env, const int32_t* actions, float* state_out, float* reward_out, cudaStream_t st);
+int cmarl_gen_rollout(cmarl_ctx* ctx, const float* actor_params, double* env, const float* noise, uint64_t seed, uint64_t episode,
+                      float* state, float* obs, int32_t* actions, float* logp, float* reward, double* ep_return, cudaStream_t st);
+int cmarl_gen_actor_act(cmarl_ctx* ctx, const float* actor_params, const float* obs, const uint8_t* avail, const float* noise,
+                        int32_t* actions, float* logp, float* logits_out, cudaStream_t st);
+
 __global__ void episode_advance_kernel(uint64_t* e) { pdl_wait_then_trigger(); *e += 1; }
 
 // shared-memory opt-ins, once per context (not inside the launch path: keeps cmarl_rollout CUDA-graph capturable)
@@ -672,6 +644,7 @@ extern "C" int cmarl_episode_advance(cmarl_ctx* ctx, void* stream) {
 
 extern "C" int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, void* stream) {
     CMARL_ARG(ctx && env, "null argument");
+    if (ctx->generic) return cmarl_gen_env_reset(ctx, env, seed, episode, as_stream(stream));
     const int B = ctx->cfg.n_envs;
     {
         KernelTimer kt(ctx, K_RESET, as_stream(stream));
@@ -683,6 +656,7 @@ extern "C" int cmarl_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint6
 
 extern "C" int cmarl_env_observe(cmarl_ctx* ctx, const double* env, float* state_out, void* stream) {
     CMARL_ARG(ctx && env && state_out, "null argument");
+    if (ctx->generic) return cmarl_gen_env_step(ctx, const_cast<double*>(env), nullptr, state_out, nullptr, as_stream(stream));
     const int B = ctx->cfg.n_envs;
     {
         KernelTimer kt(ctx, K_ENVSTEP, as_stream(stream));
@@ -695,6 +669,7 @@ extern "C" int cmarl_env_observe(cmarl_ctx* ctx, const double* env, float* state
 extern "C" int cmarl_env_step(cmarl_ctx* ctx, double* env, const int32_t* actions, float* state_out,
                               float* reward_out, void* stream) {
     CMARL_ARG(ctx && env && actions, "null argument");
+    if (ctx->generic) return cmarl_gen_env_step(ctx, env, actions, state_out, reward_out, as_stream(stream));
     const int B = ctx->cfg.n_envs;
     {
         KernelTimer kt(ctx, K_ENVSTEP, as_stream(stream));
@@ -707,6 +682,8 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
                              uint64_t seed, uint64_t episode, float* state, float* obs, int32_t* actions,
                              float* logp, float* reward, double* ep_return, void* stream) {
     CMARL_ARG(ctx && actor_params && env && state && actions && logp && reward, "null argument");
+    if (ctx->generic)
+        return cmarl_gen_rollout(ctx, actor_params, env, noise, seed, episode, state, obs, actions, logp, reward, ep_return, as_stream(stream));
     RolloutArgs a;
     a.actor = actor_params; a.env = env; a.noise = noise; a.seed = seed; a.episode = episode;
     a.episode_dev = ctx->episode_dev;
@@ -738,6 +715,7 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
 extern "C" int cmarl_actor_act(cmarl_ctx* ctx, const float* actor_params, const float* obs, const uint8_t* avail,
                                const float* noise, int32_t* actions, float* logp, float* logits_out, void* stream) {
     CMARL_ARG(ctx && actor_params && obs && noise && actions && logp, "null argument");
+    if (ctx->generic) return cmarl_gen_actor_act(ctx, actor_params, obs, avail, noise, actions, logp, logits_out, as_stream(stream));
     ActArgs a;
     a.actor = actor_params; a.obs = obs; a.avail = avail; a.noise = noise; a.actions = actions; a.logp = logp;
     a.logits = logits_out; a.B = ctx->cfg.n_envs; a.O = ctx->cfg.obs_dim;

@@ -33,6 +33,21 @@ class Shapes:
     critic_layers: int = 1
     critic_on_obs: bool = False
     actor_recurrent: bool = False     # fc1 + GRUCell + fc2 (mappo_lstm_multienvs.py:162-184)
+    n_landmarks: int = 0              # 0 = n_agents (simple_spread_v3(N): N agents, N landmarks)
+
+    @staticmethod
+    def spread(n_envs, n_agents=3, agent_ids=True, n_landmarks=0, **kw):
+        """Shapes of simple_spread with N agents / L landmarks: raw observation R = 4 + 2 L + 4 (N - 1) (vel, pos, landmarks -
+        pos, other agents - pos, 2 silent communication slots per other agent), O = R (+ N ids), S = N R."""
+        L = n_landmarks or n_agents
+        R = 4 + 2 * L + 4 * (n_agents - 1)
+        return Shapes(n_envs=n_envs, n_agents=n_agents, n_landmarks=L, obs_dim=R + (n_agents if agent_ids else 0),
+                      state_dim=n_agents * R, **kw)
+
+    @property
+    def env_rows(self):
+        """rows of the f64 env state [rows][B]: agent positions, agent velocities, landmark positions"""
+        return 4 * self.n_agents + 2 * (self.n_landmarks or self.n_agents)
 
 
 def _ptr(t, dtype, device, name):
@@ -59,7 +74,7 @@ class Engine:
         cfg = _lib.Config(self.device.index, shapes.n_envs, shapes.n_steps, shapes.n_agents, shapes.obs_dim,
                           shapes.state_dim, shapes.n_actions, shapes.actor_hidden, shapes.actor_layers,
                           shapes.critic_hidden, shapes.critic_layers, int(shapes.critic_on_obs),
-                          int(shapes.actor_recurrent))
+                          int(shapes.actor_recurrent), int(shapes.n_landmarks))
         h = C.c_void_p()
         _lib.check(self.lib.cmarl_ctx_create(C.byref(cfg), C.byref(h)), "cmarl_ctx_create")
         self._h = h

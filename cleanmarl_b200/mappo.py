@@ -88,10 +88,12 @@ class Args:
     """ (beyond the reference, default off) 0< : PPO2-style clipped value loss with this range; 0> : the reference's MSE"""
     num_minibatches: int = 1
     """ (beyond the reference, default 1 = full batch) optimizer steps per epoch, one per contiguous block of envs"""
+    n_agents: int = 3
+    """ (beyond the reference, which passes no env kwargs: MME:297) simple_spread_v3(N=n_agents): N agents and N landmarks"""
 
 
 # the two fields above are the options BASELINE.json's north_star names that the reference does not have (SURVEY 0.5)
-EXTENSION_FIELDS = ("value_clip", "num_minibatches")
+EXTENSION_FIELDS = ("value_clip", "num_minibatches", "n_agents")
 
 
 @dataclass
@@ -127,12 +129,20 @@ def validate_args(args: Args):
     if args.optimizer not in ("Adam", "AdamW"):
         raise SystemExit("only --optimizer Adam and AdamW are implemented")
     recurrent = hasattr(args, "tbptt")
-    if (not recurrent and args.actor_num_layers != 1) or args.critic_num_layers != 1:
-        raise SystemExit("only *_num_layers 1 (the reference default) is implemented")
+    # MLP paths: any *_num_layers >= 1 and hidden width <= 256 (MME:160-171, 186-196); the default shapes run the fused
+    # kernels, everything else the layered ones (csrc/generic.cu)
+    if not (1 <= args.actor_num_layers <= 6 and 1 <= args.critic_num_layers <= 6):
+        raise SystemExit("*_num_layers must be in [1, 6]")
+    if not (1 <= args.actor_hidden_dim <= 256 and 1 <= args.critic_hidden_dim <= 256):
+        raise SystemExit("*_hidden_dim must be in [1, 256]")
+    if not 1 <= args.n_agents <= 8:
+        raise SystemExit("--n_agents must be in [1, 8]")
     if recurrent and args.tbptt < 1:
         raise SystemExit("--tbptt must be positive")
-    if recurrent and args.actor_hidden_dim != 32:
-        raise SystemExit("the recurrent actor is built for --actor_hidden_dim 32 (the reference default) only")
+    if recurrent and (args.actor_hidden_dim != 32 or args.critic_num_layers != 1 or args.n_agents != 3
+                      or args.critic_hidden_dim not in (32, 64)):
+        raise SystemExit("the recurrent actor is built for the reference's default shapes only (--actor_hidden_dim 32, "
+                         "--critic_num_layers 1, --critic_hidden_dim 32 / 64, 3 agents)")
     if args.batch_size < 1 or args.epochs < 1:
         raise SystemExit("batch_size and epochs must be positive")
     if args.num_minibatches < 1 or args.num_minibatches > args.batch_size:
@@ -195,16 +205,17 @@ class SpreadVecEnv:
         self.agent_ids = agent_ids
         self.seed = seed
         self.episode = 0
-        self.env = engine.empty(18, s.n_envs, dtype=torch.float64)
+        self.raw_obs = s.state_dim // s.n_agents
+        self.env = engine.empty(s.env_rows, s.n_envs, dtype=torch.float64)
         self._state = engine.empty(s.state_dim, s.n_envs)
         self._reward = engine.empty(s.n_envs)
         self.steps = 0
 
     def get_obs_size(self):
-        return 18 + self.agent_ids * self.n_agents
+        return self.raw_obs + self.agent_ids * self.n_agents
 
     def get_state_size(self):
-        return 18 * self.n_agents
+        return self.raw_obs * self.n_agents
 
     def get_action_size(self):
         return 5
@@ -265,10 +276,10 @@ class MAPPO:
             raise SystemExit(f"--batch_size {args.batch_size}: batch_size * {self.T} steps must stay below 2^24 "
                              f"(the sample count is exchanged as an exact fp32 integer)")
         self.recurrent = hasattr(args, "tbptt")
-        shapes = Shapes(n_envs=self.B, n_steps=self.T, obs_dim=18 + 3 * bool(args.agent_ids),
-                        actor_hidden=args.actor_hidden_dim, actor_layers=1 if self.recurrent else args.actor_num_layers,
-                        critic_hidden=args.critic_hidden_dim, critic_layers=args.critic_num_layers,
-                        critic_on_obs=ippo, actor_recurrent=self.recurrent)
+        shapes = Shapes.spread(self.B, args.n_agents, bool(args.agent_ids), n_steps=self.T,
+                               actor_hidden=args.actor_hidden_dim, actor_layers=1 if self.recurrent else args.actor_num_layers,
+                               critic_hidden=args.critic_hidden_dim, critic_layers=args.critic_num_layers,
+                               critic_on_obs=ippo, actor_recurrent=self.recurrent)
         self.engine = eng = engine_factory(shapes, device_index)
         if args.optimizer == "AdamW":
             eng.set_weight_decay(0.01, 0.01)                     # torch.optim.AdamW default weight_decay
@@ -303,7 +314,7 @@ class MAPPO:
             self.adam_step_a = torch.zeros(1, dtype=torch.int32, device=eng.device)
             self.chunk_stats = eng.empty(args.epochs, len(self.chunks), 8)
             self.critic_stats = eng.empty(args.epochs, 8)
-        self.env = eng.empty(18, self.B, dtype=torch.float64)
+        self.env = eng.empty(shapes.env_rows, self.B, dtype=torch.float64)
         # every rank draws from its own Philox key so shards are independent
         self.rng_key = (args.seed + 0x9E3779B97F4A7C15 * (rank + 1)) & (2**64 - 1)
         self.episode = 0
@@ -580,7 +591,7 @@ class MAPPO:
 
     def get_batch(self):
         """The reference's ``RolloutBuffer.get_batch()`` 8-tuple (MME:148-157) for the last rollout."""
-        return to_reference_layout(self.buf, 3, 5, bool(self.args.agent_ids))
+        return to_reference_layout(self.buf, self.engine.shapes.n_agents, 5, bool(self.args.agent_ids))
 
 
 def tbptt_chunks(T: int, tbptt: int):
@@ -603,7 +614,8 @@ def evaluate(trainer: MAPPO, num_episodes: int, seed: int, env_init=None, noise=
     if ctx is None:
         import dataclasses
         eng = Engine(dataclasses.replace(trainer.engine.shapes, n_envs=num_episodes), trainer.engine.device.index)
-        ctx = trainer._eval_ctx[num_episodes] = (eng, eng.alloc_rollout(), eng.empty(18, num_episodes, dtype=torch.float64))
+        ctx = trainer._eval_ctx[num_episodes] = (eng, eng.alloc_rollout(),
+                                                 eng.empty(eng.shapes.env_rows, num_episodes, dtype=torch.float64))
     eng, buf, env = ctx
     if env_init is None:
         eng.env_reset(env, seed, 0)

@@ -53,7 +53,7 @@ typedef struct cmarl_config {
     int32_t device;          /* CUDA ordinal */
     int32_t n_envs;          /* B on this GPU (MME Args.batch_size, sharded across GPUs) */
     int32_t n_steps;         /* T = 25 for simple_spread_v3 (max_cycles) */
-    int32_t n_agents;        /* N = 3 */
+    int32_t n_agents;        /* N (3 in the reference: kwargs = {} at MME:297) */
     int32_t obs_dim;         /* O = 21 with agent ids (MME:26), 18 without */
     int32_t state_dim;       /* S = 54 */
     int32_t n_actions;       /* A = 5 */
@@ -64,7 +64,14 @@ typedef struct cmarl_config {
     int32_t critic_on_obs;   /* 0: MAPPO critic(state) MME:336; 1: IPPO critic(obs) ippo_multienvs.py:336 */
     int32_t actor_recurrent; /* 0: MLP actor MME:160-183; 1: fc1 + GRUCell + fc2, mappo_lstm_multienvs.py:162-184
                                 (actor_layers is then ignored, as in the reference; actor_hidden must be 32) */
+    int32_t n_landmarks;     /* L; 0 = n_agents (simple_spread_v3(N): N agents, N landmarks) */
 } cmarl_config;
+/* Shapes.  The fused kernels (rollout_kernel, the tcgen05 / FFMA chain kernels, clip_adam_kernel) are built for the
+ * reference's default problem: N = L = 3, *_num_layers = 1, hidden 32 / 64.  Everything else the reference's CLI
+ * accepts -- any *_num_layers >= 1 (MME:160-171, 186-196), any hidden width <= 256, 1 <= N, L <= 8 -- runs through the
+ * layered kernels of csrc/generic.cu behind the SAME entry points (same layouts with S = N * R, R = 4 + 2 L + 4 (N - 1),
+ * O = R (+ N ids); env f64 [4 N + 2 L][B]: agent positions, agent velocities, landmark positions).  The recurrent
+ * actor exists for the default shapes only. */
 
 /* -- library ---------------------------------------------------------------------------- */
 int cmarl_version(void);

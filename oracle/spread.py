@@ -13,7 +13,9 @@ real library here.  The reference's own call sites that this file serves:
 ``cleanmarl/env/pettingzoo_wrapper.py:18-20`` (construct/reset), ``:36``
 (reset(seed)), ``:47`` (step), ``:23-30`` (spaces), ``:92`` (sample).
 
-Algorithm (N = 3 agents, 3 landmarks, everything float64):
+Algorithm (N agents, L = N landmarks -- ``simple_spread_v3(N=3)`` in the reference, which passes no env kwargs
+(MME:297); every function below takes N / L from the array shapes, so the N != 3 device envs are checked by the
+same restatement; everything float64):
 
 * world: dt 0.1, damping 0.25, contact_force 100, contact_margin 1e-3;
   agents size 0.15, mass 1, collide, silent, sensitivity 5; landmarks fixed,
@@ -21,15 +23,17 @@ Algorithm (N = 3 agents, 3 landmarks, everything float64):
 * reset: per agent ``p_pos ~ U(-1,1)^2``, ``p_vel = 0``; then per landmark
   ``p_pos ~ U(-1,1)^2`` -- drawn in that order from ``np_random``.
 * discrete action a: 0 noop, 1 -x, 2 +x, 3 -y, 4 +y; ``u = +-1 * 5.0``.
-* step: ``f_i = u_i``; for agent pairs (0,1),(0,2),(1,2):
+* step: ``f_i = u_i``; for agent pairs a < b in lexicographic order ((0,1),(0,2),(1,2) for N = 3):
   ``d = p_a - p_b; dist = sqrt(d.d); pen = logaddexp(0, -(dist-0.3)/k) * k;
   F = 100 * d / dist * pen; f_a += F; f_b -= F``; then per agent
   ``p_pos += p_vel*dt`` (old velocity -- ``INTEGRATE_POS_FIRST``),
   ``p_vel = p_vel*0.75 + f*dt``.
 * reward after the step: ``g = -sum_l min_a |p_a - p_l|``;
   ``loc_i = -#{j != i : |p_i-p_j| < 0.3}``; ``r_i = 0.5 g + 0.5 loc_i``.
-* obs_i = [vel_i, pos_i, lm_k - pos_i (k=0..2), pos_j - pos_i (j != i, index
-  order), 4 zeros] cast to float32; truncation when 25 steps were taken.
+* obs_i = [vel_i, pos_i, lm_k - pos_i (k < L), pos_j - pos_i (j != i, index
+  order), 2 zeros per other agent (their silent communication state)] cast to
+  float32 -- 4 + 2 L + 4 (N - 1) numbers, 18 for N = L = 3; truncation when 25
+  steps were taken.
 
 ``INTEGRATE_POS_FIRST`` mirrors the compile-time switch of the CUDA kernel
 (``CMARL_SPREAD_POS_FIRST``): the integration order is the one detail of the
@@ -52,11 +56,15 @@ SENSITIVITY = 5.0
 LOCAL_RATIO = 0.5
 INTEGRATE_POS_FIRST = True
 
-_PAIRS = ((0, 1), (0, 2), (1, 2))
+
+
+def raw_obs_dim(n_agents: int, n_landmarks: int | None = None) -> int:
+    L = n_agents if n_landmarks is None else n_landmarks
+    return 4 + 2 * L + 4 * (n_agents - 1)
 
 
 def action_force(actions: np.ndarray) -> np.ndarray:
-    """actions int [B,3] -> u float64 [B,3,2]."""
+    """actions int [B,N] -> u float64 [B,N,2]."""
     a = np.asarray(actions).astype(np.int64)
     u = np.zeros(a.shape + (2,), dtype=np.float64)
     u[..., 0] = np.where(a == 1, -1.0, np.where(a == 2, 1.0, 0.0))
@@ -67,8 +75,8 @@ def action_force(actions: np.ndarray) -> np.ndarray:
 def step_batched(pos, vel, lm, actions, pos_first: bool = INTEGRATE_POS_FIRST):
     """One world step for B independent envs.
 
-    pos, vel: float64 [B,3,2]; lm: float64 [B,3,2]; actions: int [B,3].
-    Returns (pos', vel', reward[B,3] float64).  Operation order follows the
+    pos, vel: float64 [B,N,2]; lm: float64 [B,L,2]; actions: int [B,N].
+    Returns (pos', vel', reward[B,N] float64).  Operation order follows the
     scalar algorithm in the module docstring exactly so the result is what a
     per-env Python loop would produce bit for bit.
     """
@@ -79,7 +87,8 @@ def step_batched(pos, vel, lm, actions, pos_first: bool = INTEGRATE_POS_FIRST):
     k = CONTACT_MARGIN
     dist_min = AGENT_SIZE + AGENT_SIZE
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
-        for a, b in _PAIRS:
+        n = pos.shape[1]
+        for a, b in ((a, b) for a in range(n) for b in range(a + 1, n)):
             d = pos[:, a] - pos[:, b]
             dist = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
             pen = np.logaddexp(0.0, -(dist - dist_min) / k) * k
@@ -103,17 +112,17 @@ def _dist(a, b):
 
 
 def rewards_batched(pos, lm):
-    """Per-agent reward float64 [B,3] = 0.5*global + 0.5*local."""
-    B = pos.shape[0]
+    """Per-agent reward float64 [B,N] = 0.5*global + 0.5*local."""
+    B, n_agents, n_landmarks = pos.shape[0], pos.shape[1], lm.shape[1]
     g = np.zeros(B, dtype=np.float64)
-    for l in range(N_LANDMARKS):
-        dl = np.stack([_dist(pos[:, a], lm[:, l]) for a in range(N_AGENTS)], axis=0)
+    for l in range(n_landmarks):
+        dl = np.stack([_dist(pos[:, a], lm[:, l]) for a in range(n_agents)], axis=0)
         g = g - dl.min(axis=0)
     dist_min = AGENT_SIZE + AGENT_SIZE
-    rew = np.zeros((B, N_AGENTS), dtype=np.float64)
-    for i in range(N_AGENTS):
+    rew = np.zeros((B, n_agents), dtype=np.float64)
+    for i in range(n_agents):
         loc = np.zeros(B, dtype=np.float64)
-        for j in range(N_AGENTS):
+        for j in range(n_agents):
             if j == i:
                 continue
             loc = loc - 1.0 * (_dist(pos[:, j], pos[:, i]) < dist_min)
@@ -122,16 +131,16 @@ def rewards_batched(pos, lm):
 
 
 def observe_batched(pos, vel, lm):
-    """Raw observations float32 [B,3,18] (PettingZoo casts to float32)."""
-    B = pos.shape[0]
-    obs = np.zeros((B, N_AGENTS, RAW_OBS), dtype=np.float64)
-    for i in range(N_AGENTS):
+    """Raw observations float32 [B,N,4 + 2 L + 4 (N - 1)] (PettingZoo casts to float32)."""
+    B, n_agents, n_landmarks = pos.shape[0], pos.shape[1], lm.shape[1]
+    obs = np.zeros((B, n_agents, raw_obs_dim(n_agents, n_landmarks)), dtype=np.float64)
+    for i in range(n_agents):
         obs[:, i, 0:2] = vel[:, i]
         obs[:, i, 2:4] = pos[:, i]
-        for l in range(N_LANDMARKS):
+        for l in range(n_landmarks):
             obs[:, i, 4 + 2 * l : 6 + 2 * l] = lm[:, l] - pos[:, i]
-        c = 10
-        for j in range(N_AGENTS):
+        c = 4 + 2 * n_landmarks
+        for j in range(n_agents):
             if j == i:
                 continue
             obs[:, i, c : c + 2] = pos[:, j] - pos[:, i]
@@ -140,7 +149,7 @@ def observe_batched(pos, vel, lm):
 
 
 def rollout_batched(pos0, lm, actions_tbn, pos_first: bool = INTEGRATE_POS_FIRST):
-    """Open-loop rollout: actions int [T,B,3] -> dict of [T,...] arrays.
+    """Open-loop rollout: actions int [T,B,N] -> dict of [T,...] arrays.
 
     states[t] is the observation *before* action t (what the reference stores,
     ``mappo_multienvs.py:426-430``); reward[t] is agent 0's reward after it
@@ -156,7 +165,7 @@ def rollout_batched(pos0, lm, actions_tbn, pos_first: bool = INTEGRATE_POS_FIRST
         pos, vel, r = step_batched(pos, vel, lm, actions_tbn[t], pos_first)
         rew.append(r[:, 0])
     return {
-        "raw_obs": np.stack(raw),                       # [T,B,3,18] f32
+        "raw_obs": np.stack(raw),                       # [T,B,N,R] f32
         "reward": np.stack(rew),                        # [T,B] f64
         "final_pos": pos,
         "final_vel": vel,
@@ -182,9 +191,10 @@ class SimpleSpreadParallelEnv:
     """The slice of PettingZoo's ``parallel_env`` API the reference touches."""
 
     def __init__(self, N=3, local_ratio=0.5, max_cycles=MAX_CYCLES, **_unused):
-        assert N == N_AGENTS and local_ratio == LOCAL_RATIO
+        assert N >= 1 and local_ratio == LOCAL_RATIO
+        self.n_agents = N                               # simple_spread_v3(N): N agents and N landmarks
         self.max_cycles = max_cycles
-        self.possible_agents = [f"agent_{i}" for i in range(N_AGENTS)]
+        self.possible_agents = [f"agent_{i}" for i in range(N)]
         self.agents = list(self.possible_agents)
         self.np_random = np.random.Generator(np.random.PCG64(np.random.SeedSequence()))
         self._act_rng = np.random.default_rng()
@@ -198,14 +208,14 @@ class SimpleSpreadParallelEnv:
         return _Discrete(5, self._act_rng)
 
     def observation_space(self, agent):
-        return _Box((RAW_OBS,))
+        return _Box((raw_obs_dim(self.n_agents),))
 
     def _reset_world(self):
-        pos = np.zeros((1, N_AGENTS, 2))
-        lm = np.zeros((1, N_LANDMARKS, 2))
-        for i in range(N_AGENTS):
+        pos = np.zeros((1, self.n_agents, 2))
+        lm = np.zeros((1, self.n_agents, 2))
+        for i in range(self.n_agents):
             pos[0, i] = self.np_random.uniform(-1, +1, 2)
-        for l in range(N_LANDMARKS):
+        for l in range(self.n_agents):
             lm[0, l] = self.np_random.uniform(-1, +1, 2)
         self.pos, self.vel, self.lm = pos, np.zeros_like(pos), lm
         self.steps = 0

@@ -18,6 +18,7 @@ g8_mappo*.npz      one whole iteration of ``mappo_multienvs.py`` executed with `
                    loop MME:484-512, 3 PPO epochs MME:521-603): the batch, returns, advantages,
                    per-epoch statistics and the updated parameters.  ``_flags`` = all
                    normalize_* flags on + gradient clipping.
+g8_mappo_deep.npz  the same with ``--actor_num_layers 2 --critic_hidden_dim 128 --clip_gradients 0.5`` (``--only-deep``).
 g8_ippo.npz        the same for ``ippo_multienvs.py``.
 g1_params.npz      also holds the recurrent ``Actor`` (fc1 + GRUCell + fc2) / ``Critic`` of
                    ``mappo_lstm_multienvs.py:162-200, 327-338`` (keys ``lstm_*``).
@@ -187,6 +188,7 @@ def g8(script, tag, extra, B=6, seed=1):
         "normalize_advantage": np.array(args.normalize_advantage),
         "normalize_return": np.array(args.normalize_return),
         "actor_hidden_dim": np.array(args.actor_hidden_dim), "critic_hidden_dim": np.array(args.critic_hidden_dim),
+        "actor_num_layers": np.array(args.actor_num_layers), "critic_num_layers": np.array(args.critic_num_layers),
         "obs": g["b_obs"].numpy(), "actions": g["b_actions"].numpy(), "log_probs": g["b_log_probs"].numpy(),
         "reward": g["b_reward"].numpy(), "states": g["b_states"].numpy(),
         "avail": g["b_avail_actions"].numpy(), "done": g["b_done"].numpy(), "mask": g["b_mask"].numpy(),
@@ -222,6 +224,10 @@ def main():
         g8("mappo_lstm_multienvs.py", "mappo_lstm_flags",
            ["--tbptt", "7", "--normalize_advantage", "--clip_gradients", "0.5"], seed=5)
         g8("ippo_lstm_multienvs.py", "ippo_lstm", [], seed=6)
+        return
+    if "--only-deep" in sys.argv:
+        # shapes beyond the defaults (MME:160-171, 186-196): two hidden->hidden blocks in the actor, a 128-wide critic
+        g8("mappo_multienvs.py", "mappo_deep", ["--actor_num_layers", "2", "--critic_hidden_dim", "128", "--clip_gradients", "0.5"], seed=7)
         return
     if "--only-ippo-lstm" in sys.argv:
         g8("ippo_lstm_multienvs.py", "ippo_lstm", [], seed=6)

@@ -44,7 +44,7 @@ def test_no_gpu_fails_loudly():
     from cleanmarl_b200 import _lib
     import cleanmarl_b200 as cm
     lib = _lib.load()
-    cfg = _lib.Config(0, 64, 25, 3, 21, 54, 5, 32, 1, 64, 1, 0)
+    cfg = _lib.Config(0, 64, 25, 3, 21, 54, 5, 32, 1, 64, 1, 0, 0, 0)
     h = C.c_void_p()
     rc = lib.cmarl_ctx_create(C.byref(cfg), C.byref(h))
     assert rc != 0 and not h.value and lib.cmarl_last_error()          # no CPU fallback inside the library
@@ -56,10 +56,14 @@ def test_ctx_rejects_unsupported_configurations():
     from cleanmarl_b200 import _lib
     lib = _lib.load()
     h = C.c_void_p()
-    for bad in (dict(n_agents=4), dict(n_actions=6), dict(actor_layers=2), dict(actor_hidden=48), dict(obs_dim=20),
-                dict(state_dim=50), dict(n_envs=0), dict(actor_recurrent=2), dict(actor_recurrent=1, actor_hidden=64)):
+    # (layer counts / widths / agent counts beyond the fused kernels' defaults are served by the layered kernels; what stays
+    # invalid: inconsistent dimensions, out-of-range values, the recurrent actor on non-default shapes)
+    for bad in (dict(n_agents=4), dict(n_agents=9, state_dim=9 * 54, obs_dim=63), dict(n_actions=6), dict(actor_layers=0),
+                dict(critic_layers=7), dict(actor_hidden=300), dict(critic_hidden=0), dict(obs_dim=20), dict(state_dim=50),
+                dict(n_envs=0), dict(actor_recurrent=2), dict(actor_recurrent=1, actor_hidden=64),
+                dict(actor_recurrent=1, critic_layers=2), dict(n_landmarks=2)):
         base = dict(device=0, n_envs=64, n_steps=25, n_agents=3, obs_dim=21, state_dim=54, n_actions=5, actor_hidden=32,
-                    actor_layers=1, critic_hidden=64, critic_layers=1, critic_on_obs=0, actor_recurrent=0)
+                    actor_layers=1, critic_hidden=64, critic_layers=1, critic_on_obs=0, actor_recurrent=0, n_landmarks=0)
         base.update(bad)
         cfg = _lib.Config(*base.values())
         assert lib.cmarl_ctx_create(C.byref(cfg), C.byref(h)) < 0, bad      # argument error, before any CUDA call
@@ -83,7 +87,7 @@ def test_args_mirror_the_reference_dataclass():
                       ("ippo_lstm_multienvs", IppoLstmArgs)] + singles:
         from cleanmarl_b200.mappo import EXTENSION_FIELDS
         ours = {f.name: f for f in dataclasses.fields(cls) if f.name not in EXTENSION_FIELDS}
-        assert all(f.default in (-1, 1) for f in dataclasses.fields(cls) if f.name in EXTENSION_FIELDS)   # default off
+        assert all(f.default in (-1, 1, 3) for f in dataclasses.fields(cls) if f.name in EXTENSION_FIELDS)   # defaults = the reference (off; 3 agents)
         theirs = {f["name"]: f for f in ref[name]}
         assert sorted(ours) == sorted(theirs)            # (ippo_multienvs.py lists ppo_clip/entropy_coef before epochs;
         if name == "mappo_multienvs":                    #  flag order is irrelevant to the keyword CLI)
@@ -100,10 +104,11 @@ def test_cli_parses_like_tyro_reference_and_rejects_what_is_not_built():
     assert a.batch_size == 4096 and a.agent_ids is False and a.td_lambda == 0.9 and a.normalize_advantage is True
     validate_args(a)
     for bad in (dict(env_type="smaclite"), dict(env_name="simple_tag_v3"), dict(device="cpu"), dict(optimizer="SGD"),
-                dict(actor_num_layers=2), dict(batch_size=0)):
+                dict(actor_num_layers=0), dict(critic_hidden_dim=512), dict(n_agents=9), dict(num_minibatches=0), dict(batch_size=0)):
         with pytest.raises(SystemExit):
             validate_args(dataclasses.replace(a, **bad))
     validate_args(dataclasses.replace(a, optimizer="AdamW"))
+    validate_args(dataclasses.replace(a, actor_num_layers=2, critic_hidden_dim=128, n_agents=5))     # layered kernels
     from cleanmarl_b200.mappo import ArgsRecurrent
     r = tyro.cli(ArgsRecurrent, args=["--batch_size", "8192", "--tbptt", "5"])
     assert r.tbptt == 5 and r.num_eval_ep == 5

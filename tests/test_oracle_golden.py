@@ -66,15 +66,22 @@ def _batch(g):
             T(g["avail"]), T(g["done"]), T(g["mask"]))
 
 
-@pytest.mark.parametrize("name,ippo", [("g8_mappo", False), ("g8_mappo_flags", False), ("g8_ippo", True)])
-def test_g8_whole_iteration(golden, name, ippo):
-    """TD(lambda) + normalisation + 3 PPO epochs + Adam reproduce the reference run bit for bit."""
-    g = golden(name)
-    seed = int(g["seed"])
+def golden_networks(g, ippo=False):
+    """The reference's networks for a G8 fixture: seed, widths and (fixtures made with non-default shapes) layer counts."""
+    kw = dict(actor_hidden=int(g["actor_hidden_dim"]), critic_hidden=int(g["critic_hidden_dim"]))
+    if "actor_num_layers" in g:
+        kw.update(actor_layers=int(g["actor_num_layers"]), critic_layers=int(g["critic_num_layers"]))
     if ippo:
-        actor, critic = om.build_networks(seed, state_dim=21, critic_hidden=int(g["critic_hidden_dim"]))
-    else:
-        actor, critic = om.build_networks(seed)
+        kw.update(state_dim=21)
+    return om.build_networks(int(g["seed"]), **kw)
+
+
+@pytest.mark.parametrize("name,ippo", [("g8_mappo", False), ("g8_mappo_flags", False), ("g8_ippo", True), ("g8_mappo_deep", False)])
+def test_g8_whole_iteration(golden, name, ippo):
+    """TD(lambda) + normalisation + 3 PPO epochs + Adam reproduce the reference run bit for bit (g8_mappo_deep: the
+    reference run with --actor_num_layers 2 --critic_hidden_dim 128 --clip_gradients 0.5)."""
+    g = golden(name)
+    actor, critic = golden_networks(g, ippo)
     batch = _batch(g)
     obs, actions, logp, reward, states, avail, done, mask = batch
     critic_in = obs if ippo else states

@@ -26,7 +26,7 @@ def _logaddexp0(x):
 
 
 def scalar_step(pos, vel, lm, actions, pos_first=True):
-    n = 3
+    n = len(pos)
     force = []
     for a in actions:
         ux = -1.0 if a == 1 else (1.0 if a == 2 else 0.0)
@@ -58,7 +58,7 @@ def scalar_step(pos, vel, lm, actions, pos_first=True):
         return math.sqrt(ex * ex + ey * ey)
 
     g = 0.0
-    for l in range(3):
+    for l in range(len(lm)):
         g = g - min(d(npos[a], lm[l]) for a in range(n))
     rew = []
     for i in range(n):
@@ -72,12 +72,12 @@ def scalar_step(pos, vel, lm, actions, pos_first=True):
 
 def scalar_obs(pos, vel, lm, i):
     o = [vel[i][0], vel[i][1], pos[i][0], pos[i][1]]
-    for l in range(3):
+    for l in range(len(lm)):
         o += [lm[l][0] - pos[i][0], lm[l][1] - pos[i][1]]
-    for j in range(3):
+    for j in range(len(pos)):
         if j != i:
             o += [pos[j][0] - pos[i][0], pos[j][1] - pos[i][1]]
-    return np.asarray(o + [0.0] * 4, dtype=np.float64).astype(np.float32)
+    return np.asarray(o + [0.0] * (2 * (len(pos) - 1)), dtype=np.float64).astype(np.float32)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -158,26 +158,29 @@ def test_observation_layout():
     assert o[0, 1, 10] == np.float32(pos[0, 0, 0] - pos[0, 1, 0]) and o[0, 1, 12] == np.float32(pos[0, 2, 0] - pos[0, 1, 0])
 
 
+@pytest.mark.parametrize("n_agents", [3, 1, 2, 5])
 @pytest.mark.parametrize("pos_first", [True, False])
-def test_batched_numpy_equals_scalar_restatement_bit_for_bit(pos_first):
+def test_batched_numpy_equals_scalar_restatement_bit_for_bit(pos_first, n_agents):
+    """(N = 3 is the reference's env; the other agent counts are simple_spread_v3(N), served by the layered device path)"""
     rng = np.random.default_rng(11)
     B, T = 16, 25
-    pos0 = rng.uniform(-1, 1, (B, 3, 2))
+    pos0 = rng.uniform(-1, 1, (B, n_agents, 2))
     pos0[:4] *= 0.25                                                  # a few crowded envs so that contacts happen
-    lm = rng.uniform(-1, 1, (B, 3, 2))
-    acts = rng.integers(0, 5, (T, B, 3))
+    lm = rng.uniform(-1, 1, (B, n_agents, 2))
+    acts = rng.integers(0, 5, (T, B, n_agents))
     ref = osp.rollout_batched(pos0, lm, acts, pos_first=pos_first)
     contacts = 0
     for b in range(B):
-        pos, vel = pos0[b].tolist(), [[0.0, 0.0] for _ in range(3)]
+        pos, vel = pos0[b].tolist(), [[0.0, 0.0] for _ in range(n_agents)]
         for t in range(T):
-            for i in range(3):
-                assert np.array_equal(ref["raw_obs"][t, b, i], scalar_obs(pos, vel, lm[b].tolist(), i))
+            for i in range(n_agents):
+                o = scalar_obs(pos, vel, lm[b].tolist(), i)
+                assert o.shape == (osp.raw_obs_dim(n_agents),) and np.array_equal(ref["raw_obs"][t, b, i], o)
             pos, vel, rew = scalar_step(pos, vel, lm[b].tolist(), acts[t, b].tolist(), pos_first)
             assert rew[0] == ref["reward"][t, b]
-            contacts += rew[0] != rew[1] or rew[0] != rew[2]
+            contacts += any(math.hypot(pos[i][0] - pos[j][0], pos[i][1] - pos[j][1]) < 0.3 for i in range(n_agents) for j in range(i))
         assert pos == ref["final_pos"][b].tolist() and vel == ref["final_vel"][b].tolist()
-    assert contacts > 0                                               # the collision branch was exercised
+    assert (contacts > 0) == (n_agents > 1)                           # the collision branch was exercised
 
 
 def test_reset_draw_order_and_seeding():
