@@ -195,9 +195,10 @@ chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict_
 }
 
 // Fixed-order sum of the per-CTA partials -> flat gradient vector + statistics (deterministic).
-// 32 output columns per CTA (a warp reads 128 contiguous bytes of one partial row); 32 thread groups each sum
-// 1/32 of the partial rows with 4 independent accumulators, then a fixed-order tree over the groups.
-constexpr int RED_COLS = 32, RED_GROUPS = 32;
+// 32 output columns per CTA (a warp reads 128 contiguous bytes of one partial row); 16 thread groups each sum
+// 1/16 of the partial rows with 4 independent accumulators, then a fixed-order tree over the groups.  (512-thread CTAs:
+// the 303 CTAs of the default shapes are resident at once -- 4 per SM; with 1 024 threads 7 of them formed a second wave.)
+constexpr int RED_COLS = 32, RED_GROUPS = 16;
 __global__ void __launch_bounds__(RED_COLS * RED_GROUPS) reduce_partials_kernel(const float* __restrict__ pa, int grid_a, int Pa,
                                                                                 const float* __restrict__ pc, int grid_c, int Pc,
                                                                                 float n_groups, int count_from_c,

@@ -127,8 +127,10 @@ struct cmarl_ctx {
     float* dev_floats;       // CMARL_DEV_FLOATS device floats owned by the context (generic Adam: per-tensor sums of squares)
     unsigned int* dev_words; // CMARL_DEV_WORDS zero-initialised device words owned by the context (tickets of the kernels' last-CTA protocols)
 };
-enum { CMARL_DW_ADAM_TICKET = 0, CMARL_DW_CHAIN_TICKET_A = 1, CMARL_DW_CHAIN_TICKET_C = 2, CMARL_DEV_WORDS = 64, CMARL_DEV_FLOATS = 64 };
-constexpr int CMARL_MAX_PARAMS = 16384;     // per context (clip_adam_kernel: 1024 threads x 16; = CMARL_COMM_SLOT_FLOATS)
+enum { CMARL_DW_ADAM_TICKET = 0, CMARL_DW_ADAM_BARRIER = 1 /* 2 words: count, generation */, CMARL_DEV_WORDS = 64 };
+enum { CMARL_DF_GEN_TSQ = 0 /* 64 floats: generic Adam, per-tensor sums of squares */, CMARL_DF_ADAM_TSQ = 64 /* 16 x 12 */,
+       CMARL_DEV_FLOATS = 320 };
+constexpr int CMARL_MAX_PARAMS = 16384;     // per context on the fused path (clip_adam_kernel: <= 16 co-resident CTAs x 1024 threads; = CMARL_COMM_SLOT_FLOATS)
 
 void cmarl_time_begin(cmarl_ctx* ctx, int id, cudaStream_t st);
 void cmarl_time_end(cmarl_ctx* ctx, int id, cudaStream_t st);

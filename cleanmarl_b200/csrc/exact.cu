@@ -175,6 +175,8 @@ struct AdamArgs {
     float* stats_out;
     int32_t* step_dev;
     unsigned int* ticket;   // per-context device word: CTAs that have read *step_dev (launches of one context are serialised)
+    unsigned int* barrier;  // per-context device words [2]: arrivals at the kernel's grid barrier, barrier generation
+    float* tsq_part;        // per-context scratch [ADAM_MAX_CTAS][12]: per-CTA sums of squares per tensor
     int step;
     int n_tensors;          // 12
     int tensor_off[13];     // prefix offsets of the 12 parameter tensors, [12] = P
@@ -201,25 +203,27 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     return v;
 }
 
-// ceil(P / 1024) CTAs of 1024 threads (a single CTA was issue-bound: ~3 600 instructions x 32 warps on one SM = 21 us).
-// Every CTA redundantly derives the 12 per-tensor sums of squares from ALL gradients (<= 12 coalesced loads per thread,
-// fixed summation order => every CTA -- and every rank of a multi-GPU run -- gets bit-identical norms and clip
-// coefficients), then updates only its own 1 024 parameters.  A warp whose 32 consecutive elements lie in one tensor
-// (all but <= 11 warp-rows) adds a single shuffle-reduced value into its private shared-memory row.
+// ceil(P / 1024) CTAs of 1024 threads, one parameter per thread.  The norm of the per-tensor norms (norm_d, MME:221-224)
+// needs every gradient: each CTA reduces the squares of ITS 1 024 elements per tensor (a warp whose 32 consecutive elements
+// lie in one tensor -- all but <= 11 warp-rows -- adds one shuffle-reduced value), publishes <= 12 partial sums, and after a
+// grid barrier (the <= 16 CTAs are co-resident) every CTA adds the partials of all CTAs in CTA order: bit-identical norms and
+// clip coefficients in every CTA -- and on every rank of a multi-GPU run.  (Round 1 let every CTA reduce ALL gradients
+// redundantly: ~3 600 instructions per warp, 12.8 us per launch; this form is one gradient per thread.)
 constexpr int ADAM_THREADS = 1024;
-constexpr int ADAM_PER_THREAD = 16;      // supports up to 16 384 parameters (= CMARL_COMM_SLOT_FLOATS; checked in cmarl_ctx_create)
+constexpr int ADAM_MAX_CTAS = 16;        // = CMARL_MAX_PARAMS / ADAM_THREADS; all co-resident (grid barrier)
+constexpr int ADAM_MAX_TENSORS = 12;
 
 __device__ __forceinline__ int tensor_of(const AdamArgs& a, int i) {
     int k = 0;
 #pragma unroll
-    for (int q = 1; q < 12; ++q) k += (i >= a.tensor_off[q]) ? 1 : 0;
+    for (int q = 1; q < ADAM_MAX_TENSORS; ++q) k += (i >= a.tensor_off[q]) ? 1 : 0;
     return k;
 }
 
 template <bool XCHG>
 __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) {
-    __shared__ float wsum[ADAM_THREADS / 32][12];
-    __shared__ float tnorm[12];
+    __shared__ float wsum[ADAM_THREADS / 32][ADAM_MAX_TENSORS];
+    __shared__ float tnorm[ADAM_MAX_TENSORS];
     __shared__ double bc_sh[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.tensor_off[12];
@@ -278,13 +282,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
         for (int r = 0; r < CMARL_MAX_RANKS; ++r) sum += v[r];      // rank order; absent ranks add +0
         return sum;
     };
-    // every global load is issued up front (one L2 round trip instead of two around the norm reduction)
-    float g[ADAM_PER_THREAD];
-#pragma unroll
-    for (int j = 0; j < ADAM_PER_THREAD; ++j) {
-        const int i = tid + j * ADAM_THREADS;
-        g[j] = i < P ? G(i) : 0.0f;
-    }
+    // every global load is issued up front (one L2 round trip)
     const float g_mine = mine < P ? G(mine) : 0.0f;
     const float pm = mine < P ? a.m[mine] : 0.0f;
     const float pv = mine < P ? a.v[mine] : 0.0f;
@@ -310,33 +308,59 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
         bc_sh[0] = 1.0 - p1;
         bc_sh[1] = sqrt(1.0 - p2);
     }
-    if (lane < 12) wsum[warp][lane] = 0.0f;
+    if (lane < ADAM_MAX_TENSORS) wsum[warp][lane] = 0.0f;
     __syncwarp();
-    // norm of the per-tensor norms (norm_d, MME:221-224): sums of squares of g / count per tensor
-#pragma unroll
-    for (int j = 0; j < ADAM_PER_THREAD; ++j) {
-        const int i0 = warp * 32 + j * ADAM_THREADS;           // this warp's 32 consecutive elements
-        if (i0 >= P) break;                                     // warp-uniform
-        const float gs = g[j] / count;
-        const float sq = gs * gs;                               // 0 beyond P (g = 0)
-        const int k_lo = tensor_of(a, i0), k_hi = tensor_of(a, min(i0 + 31, P - 1));
-        if (k_lo == k_hi) {
-            const float t = warp_sum(sq);
-            if (lane == 0) wsum[warp][k_lo] += t;
-        } else {
-            const int k = tensor_of(a, min(i0 + lane, P - 1));
-            for (int q = k_lo; q <= k_hi; ++q) {                // a tensor boundary inside the warp: masked sums
-                const float t = warp_sum(k == q ? sq : 0.0f);
-                if (lane == 0) wsum[warp][q] += t;
+    // sums of squares of g / count per tensor over this CTA's elements
+    {
+        const int i0 = blockIdx.x * ADAM_THREADS + warp * 32;   // this warp's 32 consecutive elements
+        if (i0 < P) {                                           // warp-uniform
+            const float gs = g_mine / count;
+            const float sq = gs * gs;                           // 0 beyond P (g = 0)
+            const int k_lo = tensor_of(a, i0), k_hi = tensor_of(a, min(i0 + 31, P - 1));
+            if (k_lo == k_hi) {
+                const float t = warp_sum(sq);
+                if (lane == 0) wsum[warp][k_lo] = t;
+            } else {
+                const int k = tensor_of(a, min(i0 + lane, P - 1));
+                for (int q = k_lo; q <= k_hi; ++q) {            // a tensor boundary inside the warp: masked sums
+                    const float t = warp_sum(k == q ? sq : 0.0f);
+                    if (lane == 0) wsum[warp][q] = t;
+                }
             }
         }
-        __syncwarp();
     }
     __syncthreads();
-    if (tid < 12) {
+    if (tid < ADAM_MAX_TENSORS) {
         float s = 0.0f;
         for (int w = 0; w < ADAM_THREADS / 32; ++w) s += wsum[w][tid];
-        tnorm[tid] = sqrtf(s);
+        if (gridDim.x > 1) a.tsq_part[blockIdx.x * ADAM_MAX_TENSORS + tid] = s;
+        else tnorm[tid] = sqrtf(s);
+    }
+    if (gridDim.x > 1) {
+        // grid barrier (generation word + arrival count, both per context; the count is back at 0 when the launch ends, so
+        // launches with different grid sizes can follow each other; launches of one context are serialised on its stream)
+        __syncthreads();
+        if (tid == 0) {
+            volatile unsigned* gen = reinterpret_cast<volatile unsigned*>(a.barrier + 1);
+            const unsigned g0 = *gen;
+            __threadfence();
+            if (atomicAdd(a.barrier, 1u) == gridDim.x - 1) {
+                *reinterpret_cast<volatile unsigned*>(a.barrier) = 0u;
+                __threadfence();
+                atomicAdd(a.barrier + 1, 1u);
+            } else {
+                unsigned spins = 0;
+                while (*gen == g0)
+                    if (++spins > (1u << 30)) __trap();     // a protocol bug must surface as a launch failure, never as a hang
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid < ADAM_MAX_TENSORS) {
+            float s = 0.0f;
+            for (unsigned c = 0; c < gridDim.x; ++c) s += *reinterpret_cast<volatile float*>(&a.tsq_part[c * ADAM_MAX_TENSORS + tid]);   // CTA order
+            tnorm[tid] = sqrtf(s);
+        }
     }
     __syncthreads();
     float net_norm[2], coef[2];
@@ -412,10 +436,11 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     if (ctx->generic)
         return cmarl_gen_clip_adam_step(ctx, params, grads, exp_avg, exp_avg_sq, step, step_dev, lr_actor, lr_critic, beta1, beta2, eps,
                                         max_norm, stats_out, as_stream(stream));
-    CMARL_ARG(ctx->actor.count + ctx->critic.count <= ADAM_THREADS * ADAM_PER_THREAD, "too many parameters for clip_adam_kernel");
+    CMARL_ARG(ctx->actor.count + ctx->critic.count <= ADAM_THREADS * ADAM_MAX_CTAS, "too many parameters for clip_adam_kernel");
     AdamArgs a;
     a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
     a.step_dev = step_dev; a.step = step; a.ticket = ctx->dev_words + CMARL_DW_ADAM_TICKET;
+    a.barrier = ctx->dev_words + CMARL_DW_ADAM_BARRIER; a.tsq_part = ctx->dev_floats + CMARL_DF_ADAM_TSQ;
     a.n_tensors = 12; a.n_actor_tensors = 6;
     const NetLayout* nets[2] = {&ctx->actor, &ctx->critic};
     int base = 0, k = 0;
@@ -453,6 +478,7 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     AdamArgs a;
     a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
     a.step_dev = step_dev; a.step = step; a.ticket = ctx->dev_words + CMARL_DW_ADAM_TICKET;
+    a.barrier = ctx->dev_words + CMARL_DW_ADAM_BARRIER; a.tsq_part = ctx->dev_floats + CMARL_DF_ADAM_TSQ;
     int k = 0;
     if (net == 0 && ctx->cfg.actor_recurrent) {
         const GruLayout& L = ctx->gru;
@@ -467,7 +493,7 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     }
     for (int j = k + 1; j < 13; ++j) a.tensor_off[j] = a.tensor_off[k];
     a.n_tensors = k; a.n_actor_tensors = k;
-    CMARL_ARG(a.tensor_off[k] <= ADAM_THREADS * ADAM_PER_THREAD, "too many parameters for clip_adam_kernel");
+    CMARL_ARG(a.tensor_off[k] <= ADAM_THREADS * ADAM_MAX_CTAS, "too many parameters for clip_adam_kernel");
     a.lr[0] = lr; a.lr[1] = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
     a.extra_div = (float)extra_div; a.raw_stats = 1;
     a.wd[0] = a.wd[1] = ctx->weight_decay[net];

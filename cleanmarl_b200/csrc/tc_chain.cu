@@ -20,8 +20,6 @@
 //   of 32 feature rows (+ a constant "ones" row group whose product is the bias gradient), M = 64 MMAs
 //   into per-tile accumulators; the per-tile sums are added to running sums kept in the TMEM lanes the
 //   M = 64 accumulator layout leaves unused (lanes 16..31 of every quadrant).
-#include <stdlib.h>
-
 #include "chain.cuh"
 #include "heads.cuh"
 #include "tc_ptx.cuh"
@@ -38,16 +36,9 @@ constexpr int KSTEP_S = 2 * LBO_S;            // one MMA consumes 8 samples
 constexpr int B_GROUPS = 5;                   // H1 / X operand: 32 feature rows + the ones group
 constexpr int B_S_BYTES = B_GROUPS * SBO_S;
 
-// NG_ = column groups of the compute warps: a tile's 128 samples x H columns are worked on by NG_ x 4 warps (warp = (group,
-// TMEM quadrant)); 2 everywhere except the 64-wide training chain with one CTA per SM, where 4 groups (16 compute warps)
-// double the warps that hide the latencies of the CUDA-core stages between the GEMMs.
-template <int H_, int K1P_, bool TRAIN_, int OUT_, int NG_ = 2>
+template <int H_, int K1P_, bool TRAIN_, int OUT_>
 struct TCfg {
-    static constexpr int NG = NG_;
-    static constexpr int NCOMP = NG * 128;                // compute threads
-    static constexpr int NTHREADS = NCOMP + 32;           // + the issue warp
-    static_assert(H_ % (16 * NG_) == 0, "every group owns whole 16-column chunks");
-    static constexpr int ZX_BYTES = (NG - 1) * OUT_ * 128 * 4;
+    static constexpr int ZX_BYTES = OUT_ * 128 * 4;
     // dH operand of the weight-gradient GEMMs: H feature rows are stored; an M = 64 MMA also reads rows H..63, which
     // for H = 32 alias whatever follows (finite or not, they only reach accumulator rows that are never read)
     static constexpr int A_S_BYTES = (H_ / 8) * SBO_S;        // per hi / lo image
@@ -83,7 +74,7 @@ struct TCfg {
     static constexpr int oBs = oAs + (TRAIN ? 2 * A_S_BYTES : 0);               // H1 / X sample-major hi | lo
     static constexpr int smem_bytes = oBs + (TRAIN ? 2 * B_S_BYTES : 0);
     static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
-    static constexpr int CTAS_PER_SM = (smem_bytes <= 113 * 1024 && NG == 2) ? 2 : 1;   // two co-resident CTAs double the warps that hide latency
+    static constexpr int CTAS_PER_SM = smem_bytes <= 113 * 1024 ? 2 : 1;   // two co-resident CTAs double the warps that hide latency
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -168,7 +159,7 @@ __device__ __forceinline__ void issue_ss(bool leader, uint32_t d, uint32_t a_hi,
 // load in flight per iteration, i.e. ~27 serial L2 round trips (~12 us) in front of the critic chain's first tile.
 template <class C>
 __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
-    constexpr int H = C::H, K1P = C::K1P, NT = C::NTHREADS;
+    constexpr int H = C::H, K1P = C::K1P, NT = 288;
     constexpr int N1 = (H * K1P + NT - 1) / NT, N2 = (H * H + NT - 1) / NT, N3 = (H * 8 + NT - 1) / NT;
     static_assert(4 * H <= NT, "one b1 element per thread");
     const float* P = nd.params;
@@ -244,9 +235,9 @@ __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
 
 // ------------------------------------------------------------------------------------------------
 // The kernel: 8 compute warps + 1 MMA-issue warp.
-//   compute thread (cw, lane): TMEM quadrant q = cw & 3, sample s = 32 q + lane, column group hg = cw >> 2 (NG groups):
-//   it owns the 16-column chunks c of the H-wide matrices with c % NG == hg and the 8-column chunks of X
-//   with c % NG == hg, so the groups carry the same load in every round of the weight-gradient GEMMs.
+//   compute thread (cw, lane): TMEM quadrant q = cw & 3, sample s = 32 q + lane, column half hf = cw >> 2:
+//   it owns the 16-column chunks c of the H-wide matrices with (c & 1) == hf and the 8-column chunks of X
+//   with (c & 1) == hf, so both halves carry the same load in every round of the weight-gradient GEMMs.
 //   Hand-offs: compute -> issuer through "ready" mbarriers (256 arrivals), issuer -> compute through
 //   tcgen05.commit on "done" mbarriers; every barrier completes exactly one phase per tile.
 // ------------------------------------------------------------------------------------------------
@@ -255,9 +246,11 @@ __device__ long long g_tc_timeline[64];
 __device__ int g_tc_timeline_on = 0;
 #define TL_STAMP(slot) do { if (tl_on) g_tc_timeline[slot] = clock64(); } while (0)
 
+constexpr int NCOMP = 256;                    // compute threads
+constexpr int NTHREADS = NCOMP + 32;          // + the issue warp
 enum { R_X = 0, R_H1, R_DH2, R_W2B, R_W1A, R_W1B, D_F1, D_F2, D_B1, D_W2A, D_W2B, D_W1A, D_W1B, N_BARS };
 
-template <int NCOMP> __device__ __forceinline__ void compute_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(NCOMP) : "memory"); }
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // operands written by this thread (TMEM stores and/or generic-proxy shared stores) -> visible to the issuer's MMAs
 __device__ __forceinline__ void publish(uint64_t* bar) {
@@ -301,16 +294,14 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[NV], int lane, in
 }
 
 template <class C, class Head>
-__global__ void __launch_bounds__(C::NTHREADS, C::CTAS_PER_SM)
+__global__ void __launch_bounds__(NTHREADS, C::CTAS_PER_SM)
 tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict__ partials, int p_net) {
     extern __shared__ __align__(1024) uint8_t sm[];
     constexpr int H = C::H, K1P = C::K1P, OUT = Head::OUT;
     constexpr bool TRAIN = C::TRAIN;
-    constexpr int NG = C::NG, NCOMP = C::NCOMP, NTHREADS = C::NTHREADS, IWARP = NCOMP / 32;
-    constexpr int NOWN = H / (16 * NG);          // 16-column chunks of an H-wide matrix owned by a thread: chunk NG * ci + hg
+    constexpr int NOWN = H / 32;                 // 16-column chunks of an H-wide matrix owned by a thread
     constexpr int NCX = K1P / 8;                 // 8-column chunks of X
-    constexpr int NXO = (NCX + NG - 1) / NG;     // ... owned by a thread (at most): chunk NG * i + hg
-    auto compute_bar = [] { compute_bar_n<NCOMP>(); };
+    constexpr int NXO = (NCX + 1) / 2;           // ... owned by a thread (at most)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // `src.indep` (the critic chain of an epoch, launched as a programmatic dependent of the actor chain): this grid
     // reads nothing the grid in front of it writes, so whatever is launched behind it may be scheduled right away ...
@@ -333,7 +324,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         for (int i = 0; i < N_BARS; ++i) tc::mbar_init(&bars[i], i < D_F1 ? NCOMP : 1);
         tc::fence_mbar_init();
     }
-    if (warp == IWARP) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (warp == 8) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
     // the grid in front of this one (and, transitively, everything before it) has completed past this point
     if (!src.indep) pdl_wait_then_trigger();
     load_weights_tc<C>(sm, nd, src.G);
@@ -349,7 +340,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     const uint32_t tmem = *tmem_slot;
     const uint32_t sbase = tc::smem_u32(sm);
 
-    if (warp == IWARP) {
+    if (warp == 8) {
         // ================================ MMA issue warp ==================================================
         {
             const uint32_t As_h = sbase + C::oAs, As_l = As_h + C::A_S_BYTES, Bs_h = sbase + C::oBs, Bs_l = Bs_h + B_S_BYTES;
@@ -405,14 +396,14 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         __syncwarp();
     } else {
         // ================================ compute warps ====================================================
-        const int q = warp & 3, hg = warp >> 2;                         // TMEM quadrant, column group
+        const int q = warp & 3, hf = warp >> 2;
         const int s = q * 32 + lane;                                    // sample within the tile = TMEM lane
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         const float* fb1 = reinterpret_cast<const float*>(sm + C::oB1);
         const float* fb2 = reinterpret_cast<const float*>(sm + C::oB2);
         const float* fw3 = reinterpret_cast<const float*>(sm + C::oW3T);
         const float* fb3 = reinterpret_cast<const float*>(sm + C::oB3);
-        float* zx = reinterpret_cast<float*>(sm + C::oZx);              // [NG - 1][OUT][128] partial outputs of groups 1.. (then dz in slot 0)
+        float* zx = reinterpret_cast<float*>(sm + C::oZx);              // [2][OUT][128] partial outputs of the two halves
         float* dw3acc = reinterpret_cast<float*>(sm + C::oDW3) + q * 8 * H;                     // [8][H] of this quadrant
         float* db3acc = reinterpret_cast<float*>(sm + C::oDW3) + 4 * 8 * H + q * 8;
         float* didacc = reinterpret_cast<float*>(sm + C::oDId);
@@ -424,7 +415,8 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             uint32_t zero[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) zero[i] = 0u;
-            for (int c = C::cW2 + 8 * hg; c < C::cEnd; c += 8 * NG) tmem_st8(tl + c, zero);
+            if (hf == 0)
+                for (int c = C::cW2; c < C::cEnd; c += 8) tmem_st8(tl + c, zero);
             tc::tmem_wait_st();
         }
 
@@ -432,7 +424,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
 #pragma unroll
         for (int k = 0; k < Head::NSTAT; ++k) st[k] = 0.0f;
 
-        // X chunks owned by this thread: chunk c = NG i + hg, i < NXO (chunks >= NCX do not exist)
+        // X chunks owned by this thread: chunk c = 2 i + hf, i < NXO (chunks >= NCX do not exist)
         float xr[NXO * 8];
         auto load_x = [&](int u) {
             int bt, r, t, g;
@@ -441,14 +433,14 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             const int b = bt * M + s;
             // 32-bit row offsets from one 64-bit base and one bound per thread: ~5 instructions per load (the 64-bit
             // products and double predicates of the obvious form were 14, a fifth of the critic kernel's instructions)
-            const float* xp = src.x + (size_t)t * src.stride_t + (size_t)g * src.stride_g + b + (size_t)(8 * hg) * src.B;
+            const float* xp = src.x + (size_t)t * src.stride_t + (size_t)g * src.stride_g + b + (size_t)(8 * hf) * src.B;
             const uint32_t step = (uint32_t)src.B;
-            const int rmax = (b < src.nb) ? nd.in_rows - 8 * hg : 0;     // this thread reads rows 8 NG i + e < rmax of its group
+            const int rmax = (b < src.nb) ? nd.in_rows - 8 * hf : 0;     // this thread reads rows 16 i + e < rmax of its half
 #pragma unroll
             for (int i = 0; i < NXO; ++i) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int rr = 8 * NG * i + e;
+                    const int rr = 16 * i + e;
                     xr[i * 8 + e] = (rr < rmax) ? __ldg(xp + (uint32_t)rr * step) : 0.0f;
                 }
             }
@@ -462,7 +454,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         auto stage_x = [&](int u_next_next) {
 #pragma unroll
             for (int i = 0; i < NXO; ++i) {
-                const int c = NG * i + hg;
+                const int c = 2 * i + hf;
                 if (c < NCX) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
@@ -493,7 +485,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             TL_STAMP(0);
             TL_STAMP(1);
             // the head's per-sample inputs (half 0 evaluates the head): loaded now, used after F2
-            const typename Head::In hin = Head::load(ha, t, g, b, src.G, src.B, inb && hg == 0);
+            const typename Head::In hin = Head::load(ha, t, g, b, src.G, src.B, inb && hf == 0);
 
             // ---- E1: H1 = relu(D1 + b1[g]) -> split -> TMEM A ---------------------------------------------
             // (every asm statement is a compiler barrier for memory operations: shared-memory constants are read BEFORE the
@@ -504,7 +496,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 for (int ci = 0; ci < NOWN; ++ci) {
 #pragma unroll
                     for (int i4 = 0; i4 < 16; i4 += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(fb1 + g * H + 16 * (NG * ci + hg) + i4);
+                        const float4 bb = *reinterpret_cast<const float4*>(fb1 + g * H + 16 * (2 * ci + hf) + i4);
                         bv1[ci][i4] = bb.x; bv1[ci][i4 + 1] = bb.y; bv1[ci][i4 + 2] = bb.z; bv1[ci][i4 + 3] = bb.w;
                     }
                 }
@@ -516,7 +508,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             {
                 uint32_t v[NOWN][16];
 #pragma unroll
-                for (int ci = 0; ci < NOWN; ++ci) tc::tmem_ld16(tl + C::cD1 + 16 * (NG * ci + hg), v[ci]);
+                for (int ci = 0; ci < NOWN; ++ci) tc::tmem_ld16(tl + C::cD1 + 16 * (2 * ci + hf), v[ci]);
                 tc::tmem_wait_ld();
 #pragma unroll
                 for (int ci = 0; ci < NOWN; ++ci) {
@@ -530,7 +522,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 }
 #pragma unroll
                 for (int ci = 0; ci < NOWN; ++ci) {
-                    const int c0 = 16 * (NG * ci + hg);
+                    const int c0 = 16 * (2 * ci + hf);
                     tmem_st16(tl + C::cAh + c0, h1h[ci]);
                     tmem_st16(tl + C::cAl + c0, h1l[ci]);
                 }
@@ -539,18 +531,12 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             TL_STAMP(3);
             if (!TRAIN && has_next) stage_x(u + 2 * gridDim.x);          // F1 of this tile has completed: X columns are free
             if (TRAIN) {
-                // round-0 features of H1 (chunks 0 and 1), sample-major, while F2 runs (B image is free: the previous
+                // round-0 features of H1 (chunk hf), sample-major, while F2 runs (B image is free: the previous
                 // tile's last weight-gradient round has completed)
 #pragma unroll
-                for (int ci = 0; ci < NOWN; ++ci) {
-                    const int c = NG * ci + hg;                          // round c / 2, B rows 16 (c % 2) ..
-                    if (c < 2) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            *reinterpret_cast<uint32_t*>(Bs_h + smaj(16 * c + i, 0) + so) = h1h[ci][i];
-                            *reinterpret_cast<uint32_t*>(Bs_l + smaj(16 * c + i, 0) + so) = h1l[ci][i];
-                        }
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    *reinterpret_cast<uint32_t*>(Bs_h + smaj(16 * hf + i, 0) + so) = h1h[0][i];
+                    *reinterpret_cast<uint32_t*>(Bs_l + smaj(16 * hf + i, 0) + so) = h1l[0][i];
                 }
             }
 
@@ -561,7 +547,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             for (int ci = 0; ci < NOWN; ++ci) {
 #pragma unroll
                 for (int i4 = 0; i4 < 16; i4 += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(fb2 + 16 * (NG * ci + hg) + i4);
+                    const float4 bb = *reinterpret_cast<const float4*>(fb2 + 16 * (2 * ci + hf) + i4);
                     bv2[ci][i4] = bb.x; bv2[ci][i4 + 1] = bb.y; bv2[ci][i4 + 2] = bb.z; bv2[ci][i4 + 3] = bb.w;
                 }
             }
@@ -574,13 +560,13 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             {
                 uint32_t v[NOWN][16];
 #pragma unroll
-                for (int ci = 0; ci < NOWN; ++ci) tc::tmem_ld16(tl + C::cD2 + 16 * (NG * ci + hg), v[ci]);
+                for (int ci = 0; ci < NOWN; ++ci) tc::tmem_ld16(tl + C::cD2 + 16 * (2 * ci + hf), v[ci]);
                 tc::tmem_wait_ld();
 #pragma unroll
                 for (int ci = 0; ci < NOWN; ++ci) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int j = 16 * (NG * ci + hg) + i;
+                        const int j = 16 * (2 * ci + hf) + i;
                         const float hv = fmaxf(__uint_as_float(v[ci][i]) + bv2[ci][i], 0.0f);
                         h2[ci * 16 + i] = hv;
                         if (OUT > 1) {
@@ -597,20 +583,15 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                     }
                 }
             }
-            // groups 1.. hand their partial outputs to group 0, which evaluates the head and hands dz back (slot 0)
-            if (hg > 0) {
+            // half 1 hands its partial outputs to half 0, which evaluates the head and hands dz back
+            if (hf == 1) {
 #pragma unroll
-                for (int a = 0; a < OUT; ++a) zx[((hg - 1) * OUT + a) * M + s] = z[a];
+                for (int a = 0; a < OUT; ++a) zx[a * M + s] = z[a];
             }
             compute_bar();
-            if (hg == 0) {
+            if (hf == 0) {
 #pragma unroll
-                for (int a = 0; a < OUT; ++a) {
-                    float acc = z[a];
-#pragma unroll
-                    for (int gg = 0; gg < NG - 1; ++gg) acc += zx[(gg * OUT + a) * M + s];      // fixed order
-                    z[a] = acc + fb3[a];
-                }
+                for (int a = 0; a < OUT; ++a) z[a] = (z[a] + zx[a * M + s]) + fb3[a];
                 Head::compute(ha, hin, z, TRAIN, dz, st);
                 if (TRAIN) {
 #pragma unroll
@@ -619,7 +600,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             }
             if (TRAIN) {
                 compute_bar();
-                if (hg > 0) {
+                if (hf == 1) {
 #pragma unroll
                     for (int a = 0; a < OUT; ++a) dz[a] = zx[a * M + s];
                 }
@@ -633,7 +614,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 // W3 load behind it (the compiler cannot prove they do not alias) and serialise 16 LDS round trips per chunk.
 #pragma unroll
                 for (int ci = 0; ci < NOWN; ++ci) {
-                    const int c0 = 16 * (NG * ci + hg);
+                    const int c0 = 16 * (2 * ci + hf);
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -674,9 +655,9 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                     for (int i = 0; i < NOWN * 16; ++i) p[i] = dz[a] * h2[i];
                     int idx;
                     warp_reduce_scatter<NOWN * 16>(p, lane, idx);
-                    const int j = 16 * (NG * (idx >> 4) + hg) + (idx & 15);
+                    const int j = 16 * (2 * (idx >> 4) + hf) + (idx & 15);
                     if (NOWN * 16 >= 32 || (lane & 1) == 0) dw3acc[a * H + j] += p[0];
-                    if (hg == 0) {
+                    if (hf == 0) {
                         float d = dz[a];
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
@@ -690,10 +671,10 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 acquire(&bars[D_B1], par);
                 TL_STAMP(9);
                 float dh1[NOWN * 16];
-                uint32_t r1h[16], r1l[16];                               // round-1 features of H1 (NR2 == 2): this thread's chunk 2 or 3
+                uint32_t r1h[16], r1l[16];                               // round-1 features of H1 (NR2 == 2)
 #pragma unroll
                 for (int ci = 0; ci < NOWN; ++ci) {
-                    const int c0 = 16 * (NG * ci + hg);
+                    const int c0 = 16 * (2 * ci + hf);
                     uint32_t v[16], d1[16];
                     tc::tmem_ld16(tl + C::cD2 + c0, v);
                     tc::tmem_ld16(tl + C::cD1 + c0, d1);
@@ -702,7 +683,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                     for (int i = 0; i < 16; ++i) {
                         const float pre = __uint_as_float(d1[i]) + bv1[ci][i];
                         dh1[ci * 16 + i] = pre > 0.0f ? __uint_as_float(v[i]) : 0.0f;
-                        if (C::NR2 == 2 && NG * ci + hg >= 2) {
+                        if (C::NR2 == 2 && ci == 1) {
                             float h, l;
                             tc::split_tf32(fmaxf(pre, 0.0f), h, l);
                             r1h[i] = __float_as_uint(h); r1l[i] = __float_as_uint(l);
@@ -713,14 +694,10 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 acquire(&bars[D_W2A], par);     // dW2 round 0 complete: the B image is free
                 TL_STAMP(11);
                 if (C::NR2 == 2) {
-                    // this thread's round-1 chunk c (2 or 3; with four groups only groups 2 and 3 own one) -> B rows 16 (c - 2) ..
-                    const int c1 = NG == 2 ? 2 + hg : hg;
-                    if (c1 >= 2) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            *reinterpret_cast<uint32_t*>(Bs_h + smaj(16 * (c1 - 2) + i, 0) + so) = r1h[i];
-                            *reinterpret_cast<uint32_t*>(Bs_l + smaj(16 * (c1 - 2) + i, 0) + so) = r1l[i];
-                        }
+                    for (int i = 0; i < 16; ++i) {
+                        *reinterpret_cast<uint32_t*>(Bs_h + smaj(16 * hf + i, 0) + so) = r1h[i];
+                        *reinterpret_cast<uint32_t*>(Bs_l + smaj(16 * hf + i, 0) + so) = r1l[i];
                     }
                     publish(&bars[R_W2B]);
                     TL_STAMP(12);
@@ -732,7 +709,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 for (int ci = 0; ci < NOWN; ++ci) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int j = 16 * (NG * ci + hg) + i;
+                        const int j = 16 * (2 * ci + hf) + i;
                         float h, l;
                         tc::split_tf32(dh1[ci * 16 + i], h, l);
                         *reinterpret_cast<float*>(As_h + smaj(j, 0) + so) = h;
@@ -741,10 +718,10 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 }
 #pragma unroll
                 for (int rd = 0; rd < C::NR1; ++rd) {
-                    // this thread's X chunks of the round (4 chunks = 32 rows per round): 4 rd + NG h2i + hg -> B rows 8 (NG h2i + hg) ..
+                    // this thread's X chunks of the round: 4 rd + hf and 4 rd + 2 + hf -> B rows 8 hf.. and 16 + 8 hf..
 #pragma unroll
-                    for (int h2i = 0; h2i < 4 / NG; ++h2i) {
-                        const int c = 4 * rd + NG * h2i + hg;            // X chunk (may not exist: zeros)
+                    for (int h2i = 0; h2i < 2; ++h2i) {
+                        const int c = 4 * rd + 2 * h2i + hf;             // X chunk (may not exist: zeros)
                         uint32_t xh[8], xl[8];
                         if (c < NCX) {
                             tc::tmem_ld8(tl + C::cXh + 8 * c, xh);
@@ -756,7 +733,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int row = 8 * (NG * h2i + hg) + i;
+                            const int row = 16 * h2i + 8 * hf + i;
                             *reinterpret_cast<uint32_t*>(Bs_h + smaj(row, 0) + so) = xh[i];
                             *reinterpret_cast<uint32_t*>(Bs_l + smaj(row, 0) + so) = xl[i];
                         }
@@ -769,32 +746,32 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                     TL_STAMP(15 + 2 * rd);
                 }
                 // ---- per-tile sums (lanes 0-15 of the quadrant) -> running sums (lanes 16-31) ------------------
-                // the dW2 | db2 | dW1 | db1 accumulator columns [cW2, cEnd) in 8-column chunks; group hg folds chunks hg, hg + NG, ..
+                // half 0 folds the dW2 | db2 columns, half 1 the dW1 | db1 columns
                 {
-                    constexpr int NCH = (C::nW2 + C::nW1) / 8;           // 10 or 18 chunks
-                    constexpr int IDCH = (C::nW2 + 32 * C::NR1) / 8;     // the chunk that starts with db1 (the ones row of dW1's B)
-                    constexpr int FU = NG == 2 ? 5 : 3;                  // chunks in flight per thread
+                    const int cb = hf == 0 ? C::cW2 : C::cW1;
+                    const int cn = hf == 0 ? C::nW2 : C::nW1;
+                    constexpr int FU = 5;                                // 8-column chunks in flight (cn = 40 or 72)
 #pragma unroll 1
-                    for (int c = hg; c < NCH; c += NG * FU) {
+                    for (int c = 0; c < cn; c += 8 * FU) {
                         uint32_t v[FU][8];
 #pragma unroll
                         for (int k = 0; k < FU; ++k)
-                            if (c + NG * k < NCH) tc::tmem_ld8(tl + C::cW2 + 8 * (c + NG * k), v[k]);      // warp-uniform guard
+                            if (c + 8 * k < cn) tc::tmem_ld8(tl + cb + c + 8 * k, v[k]);      // warp-uniform guard
                         tc::tmem_wait_ld();
 #pragma unroll
                         for (int k = 0; k < FU; ++k) {
-                            if (c + NG * k < NCH) {
+                            if (c + 8 * k < cn) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     const float part = __shfl_sync(0xffffffffu, __uint_as_float(v[k][i]), lane & 15);
                                     if (lane >= 16) v[k][i] = __float_as_uint(__uint_as_float(v[k][i]) + part);
                                 }
                                 // folded one-hot id column of this agent group: gradient = bias-gradient column of dW1
-                                if (nd.fold_ids && c + NG * k == IDCH && lane < 16) {
+                                if (nd.fold_ids && hf == 1 && c + 8 * k == 32 * C::NR1 && lane < 16) {
                                     const int row = q * 16 + lane;
                                     if (row < H) didacc[g * H + row] += __uint_as_float(v[k][0]);
                                 }
-                                tmem_st8(tl + C::cW2 + 8 * (c + NG * k), v[k]);
+                                tmem_st8(tl + cb + c + 8 * k, v[k]);
                             }
                         }
                     }
@@ -821,14 +798,12 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 // running sums live in lanes 16-31 of each quadrant; every lane executes the (warp-aligned) loads
                 const int row = q * 16 + (lane - 16);               // gradient row j held by this lane
                 const bool valid = lane >= 16 && row < H;
-                constexpr int NCH = (C::nW2 + C::nW1) / 8;
+                if (hf == 0) {
 #pragma unroll 1
-                for (int ch = hg; ch < NCH; ch += NG) {             // same chunk ownership as the fold
-                    uint32_t v[8];
-                    tc::tmem_ld8(tl + C::cW2 + 8 * ch, v);
-                    tc::tmem_wait_ld();
-                    if (8 * ch < C::nW2) {
-                        const int c = 8 * ch;
+                    for (int c = 0; c < C::nW2; c += 8) {
+                        uint32_t v[8];
+                        tc::tmem_ld8(tl + C::cW2 + c, v);
+                        tc::tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             if (valid) {
@@ -836,8 +811,13 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                                 else if (c + i == 32 * C::NR2) gb2[row] = __uint_as_float(v[i]);
                             }
                         }
-                    } else {
-                        const int c = 8 * ch - C::nW2;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < C::nW1; c += 8) {
+                        uint32_t v[8];
+                        tc::tmem_ld8(tl + C::cW1 + c, v);
+                        tc::tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             if (valid) {
@@ -877,7 +857,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (warp == IWARP) tc::tmem_dealloc(tmem, C::TMEM_COLS);
+    if (warp == 8) tc::tmem_dealloc(tmem, C::TMEM_COLS);
     // ... but whoever follows must see BOTH this grid and the one in front of it complete: it completes only after that one
     if (src.indep) pdl_wait();
 }
@@ -894,7 +874,7 @@ static int tc_set_attr() {
 template <class C, class Head>
 static int tc_launch(const cmarl_ctx* ctx, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
                      int p_net, int grid, cudaStream_t st) {
-    return cmarl_check_cuda(cmarl_launch_pdl(src.indep || cmarl_chained(ctx), tc_chain_kernel<C, Head>, dim3(grid), dim3(C::NTHREADS),
+    return cmarl_check_cuda(cmarl_launch_pdl(src.indep || cmarl_chained(ctx), tc_chain_kernel<C, Head>, dim3(grid), dim3(NTHREADS),
                                              C::smem_bytes, st, nd, src, ha, partials, p_net),
                             "tc_chain_kernel launch");
 }
@@ -911,18 +891,7 @@ int cmarl_tc_setup() {
     if (!e) e = tc_set_attr<TCfg<Hh, Kk, false, 1>, ValueHead>();
     SET(32, 24) SET(32, 56) SET(64, 24) SET(64, 56)
 #undef SET
-    if (!e) e = tc_set_attr<TCfg<64, 56, true, 1, 4>, ValueHead>();
     return e;
-}
-
-// 64-wide critic on the 54-row state (the default MAPPO critic), training: CMARL_TC_GROUPS=4 selects four column groups
-// = 16 compute warps instead of 8.  Measured round 2 (B200, 4096 envs): 100.6 us per launch against 95.0 us -- the CUDA-core
-// stages shorten (E1 539 -> 319 cycles) but every weight-gradient MMA round takes twice as long (1.3 k -> 2.6 k cycles:
-// the operands of the SS MMAs and the compute warps' staging stores share the 128 B/clk shared-memory port, and 17 warps
-// leave 96 registers per thread: 248 B of spills), so the 8-warp form stays the default; kept for measurements.
-static bool tc_wide_groups() {
-    static const bool on = [] { const char* v = getenv("CMARL_TC_GROUPS"); return v && v[0] == '4'; }();
-    return on;
 }
 
 int cmarl_tc_tile() { return M; }
@@ -953,11 +922,7 @@ int cmarl_tc_dispatch(const cmarl_ctx* ctx, int H, const NetDesc& nd, const Tile
     if (H == 32 && kin == 24) return tc_launch<TCfg<32, 24, TRAIN, Head::OUT>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
     if (H == 32 && kin == 56) return tc_launch<TCfg<32, 56, TRAIN, Head::OUT>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
     if (H == 64 && kin == 24) return tc_launch<TCfg<64, 24, TRAIN, Head::OUT>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
-    if (H == 64 && kin == 56) {
-        if constexpr (TRAIN && Head::OUT == 1)
-            if (tc_wide_groups()) return tc_launch<TCfg<64, 56, true, 1, 4>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
-        return tc_launch<TCfg<64, 56, TRAIN, Head::OUT>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
-    }
+    if (H == 64 && kin == 56) return tc_launch<TCfg<64, 56, TRAIN, Head::OUT>, Head>(ctx, nd, src, ha, partials, p_net, grid, st);
     cmarl_set_error("tc dispatch: unsupported hidden=%d in_rows=%d", H, nd.in_rows);
     return -1;
 }
