@@ -342,6 +342,49 @@ def test_cli_main_loop_logs_like_the_reference(tmp_path, monkeypatch):
     assert [e[0] for e in evals] == [6, 12, 18] and all(e[1] == 3 for e in evals)
 
 
+@pytest.mark.parametrize("script,prefix,ippo,recurrent", [("mappo", "MAPPO", False, False), ("ippo", "IPPO", True, False),
+                                                         ("mappo_lstm", "MAPPO-lstm", False, True), ("ippo_lstm", "IPPO-lstm", True, True)])
+def test_single_env_scripts_run_the_shared_loop(tmp_path, monkeypatch, script, prefix, ippo, recurrent):
+    """``cleanmarl_b200/single/*.py`` (drop-ins for the single-env ``mappo.py`` / ``ippo.py`` / ``*_lstm.py``): their own
+    ``Args`` class, the reference's run-directory prefix (mappo.py:277-279), and the shared
+    training loop -- run for ten iterations on the CPU double."""
+    import importlib
+    from cleanmarl_b200 import mappo_multienvs as cli
+    from cleanmarl_b200.mappo import MAPPO
+    from fake_engine import OracleEngine
+    mod = importlib.import_module(f"cleanmarl_b200.single.{script}")
+    monkeypatch.chdir(tmp_path)
+    log, evals = [], []
+
+    class CpuTrainer(MAPPO):
+        def __init__(self, args, device_index=0, rank=0, world_size=1, ippo=False):
+            super().__init__(args, rank=rank, world_size=world_size, ippo=ippo,
+                             engine_factory=lambda shapes, dev: OracleEngine(shapes))
+            self._g = torch.Generator().manual_seed(5)
+
+        def iteration(self):
+            super().iteration(None, torch.empty(25, 3, 5, self.B).exponential_(1, generator=self._g))
+
+    class Recorder:
+        def __init__(self, logdir): log.append(("dir", logdir))
+        def add_text(self, tag, text): pass
+        def add_scalar(self, tag, value, step): log.append((tag, float(value), int(step)))
+        def close(self): pass
+
+    def fake_eval(trainer, n, seed):
+        evals.append(trainer.training_step)
+        return -30.0, 2.0, 25.0
+
+    src = (Path(mod.__file__).read_text())
+    assert f'run_prefix="{prefix}"' in src
+    tr = cli.main(["--batch_size", "2", "--total_timesteps", "500", "--epochs", "1", "--eval_steps", "10"], algo=prefix, ippo=ippo, args_cls=mod.Args,
+                  run_prefix=prefix, trainer_cls=CpuTrainer, evaluate_fn=fake_eval, SummaryWriter=Recorder)
+    assert tr.ippo == ippo and tr.recurrent == recurrent          # (the Args defaults are checked against the reference fixture above)
+    assert re.fullmatch(rf"runs/{re.escape(prefix)}-pz__simple_spread_v3__\d{{4}}-\d\d-\d\d_\d\d-\d\d-\d\d", log[0][1])
+    assert tr.step == 500 and tr.training_step == 10 and evals == [10]      # (training_step / epochs) % 10 == 0 at the 10th iteration
+    assert sum(1 for e in log if e[0] == "train/actor_loss") == 10 and sum(1 for e in log if e[0] == "eval/ep_reward") == 1
+
+
 def test_env_duck_type_on_the_cpu_double():
     """SpreadVecEnv (env/common_interface.py:5-23 with a leading env axis) on the engine double; the same body runs against
     the CUDA library in tests/test_gpu_vecenv.py."""
