@@ -232,15 +232,15 @@ __global__ void __launch_bounds__(RED_COLS * RED_GROUPS) reduce_partials_kernel(
     if (valid && !zero) {
         int c = c0;
         if (is_count) {
-            for (; c < c1; ++c) d += (double)src[(size_t)c * stride + col];   // can exceed 2^24: sum in double
+            for (; c < c1; ++c) d += (double)__ldcg(src + (size_t)c * stride + col);   // can exceed 2^24: sum in double
         } else {
             for (; c + 3 < c1; c += 4) {
-                a0 += src[(size_t)c * stride + col];
-                a1 += src[(size_t)(c + 1) * stride + col];
-                a2 += src[(size_t)(c + 2) * stride + col];
-                a3 += src[(size_t)(c + 3) * stride + col];
+                a0 += __ldcg(src + (size_t)c * stride + col);
+                a1 += __ldcg(src + (size_t)(c + 1) * stride + col);
+                a2 += __ldcg(src + (size_t)(c + 2) * stride + col);
+                a3 += __ldcg(src + (size_t)(c + 3) * stride + col);
             }
-            for (; c < c1; ++c) a0 += src[(size_t)c * stride + col];
+            for (; c < c1; ++c) a0 += __ldcg(src + (size_t)c * stride + col);
         }
     }
     part[grp][col_l] = (a0 + a1) + (a2 + a3);
@@ -296,13 +296,19 @@ static int dispatch(const cmarl_ctx* ctx, int H, const NetDesc& nd, const TileSr
     return -1;
 }
 
+// tiles per flush group of the tcgen05 chains (tc_chain.cu); CMARL_TC_FLUSH overrides for measurements
+static int tc_flush_tiles() {
+    static const int v = [] { const char* e = getenv("CMARL_TC_FLUSH"); const int n = e ? atoi(e) : 0; return n >= 1 && n <= 64 ? n : 4; }();
+    return v;
+}
+
 static void actor_desc(const cmarl_ctx* ctx, const float* params, const float* state, const float* obs,
                        NetDesc& nd, TileSrc& src) {
     const cmarl_config& c = ctx->cfg;
     nd.params = params;
     nd.in_dim = c.obs_dim;
     nd.out_dim = c.n_actions;
-    src.T = c.n_steps; src.G = c.n_agents; src.B = c.n_envs; src.nb = c.n_envs; src.indep = 0;
+    src.T = c.n_steps; src.G = c.n_agents; src.B = c.n_envs; src.nb = c.n_envs; src.indep = 0; src.flush = tc_flush_tiles();
     if (obs) {
         nd.in_rows = c.obs_dim; nd.fold_ids = 0;
         src.x = obs; src.stride_t = (size_t)c.n_agents * c.obs_dim * c.n_envs; src.stride_g = (size_t)c.obs_dim * c.n_envs;
@@ -322,7 +328,7 @@ static void critic_desc(const cmarl_ctx* ctx, const float* params, const float* 
     }
     nd.params = params;
     nd.in_rows = c.state_dim; nd.in_dim = c.state_dim; nd.fold_ids = 0; nd.out_dim = 1;
-    src.x = state; src.T = c.n_steps; src.G = 1; src.B = c.n_envs; src.nb = c.n_envs; src.indep = 0;
+    src.x = state; src.T = c.n_steps; src.G = 1; src.B = c.n_envs; src.nb = c.n_envs; src.indep = 0; src.flush = tc_flush_tiles();
     src.stride_t = (size_t)c.state_dim * c.n_envs; src.stride_g = 0;
 }
 

@@ -123,6 +123,7 @@ struct TileSrc {
     int nb;                // envs of this launch: [0, nb) relative to the (pre-offset) base pointers -- the whole buffer
                            // (nb == B) or one minibatch (contiguous env block, cmarl_ppo_epoch_grads_ex)
     int indep;             // tc_chain_kernel only: 1 = reads nothing the launch in front of it writes (see tc_chain.cu)
+    int flush;             // tc_chain_kernel only: tiles whose weight-gradient products accumulate in TMEM between two flushes
 };
 
 struct PolicyHeadArgs {
@@ -204,7 +205,7 @@ __device__ void issue_tile(float* xbuf, uint64_t* bar, const TileSrc& src, int i
         const int valid = src.nb - b0;
         for (int i = threadIdx.x; i < in_rows * C::M; i += C::NT) {
             const int r = i / C::M, s = i - r * C::M;
-            xbuf[r * C::LD + s] = (s < valid) ? __ldg(base + (size_t)r * src.B + s) : 0.0f;
+            xbuf[r * C::LD + s] = (s < valid) ? __ldcg(base + (size_t)r * src.B + s) : 0.0f;
         }
         if (threadIdx.x == 0) mbar_arrive(bar);   // keeps the phase bookkeeping uniform
     }

@@ -171,6 +171,13 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // wait covers the kernel itself -- so only launch latency and pre-wait prologues (shared-memory zeroing, barrier
 // init, TMEM allocation) overlap, never a read with the write it depends on.
 // ------------------------------------------------------------------------------------------
+// NON-COHERENT LOADS ARE NOT ALLOWED on anything a predecessor kernel writes (parameters, rollout buffers, partial rows,
+// gradients): a programmatic dependent becomes resident while its primary still runs, so its lifetime overlaps the writes,
+// and ld.global.nc (`__ldg`, or what the compiler infers from `const T* __restrict__`) may then return a line the SM cached
+// during an EARLIER launch -- griddepcontrol.wait orders coherent loads only.  Measured round 2: the actor chain of epoch 2,
+// launched as a dependent of the Adam step of epoch 1, read parameters of epoch 0 from the read-only cache (gradient
+// sums off by 1e-4 relative; profiles/tools/chain_diag2.py); the same mechanism was behind round 1's unexplained loss of
+// bit-identity.  Such data is read with `__ldcg` (L2, coherent); it is streamed once per kernel, so nothing is lost.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -32,9 +32,9 @@ __global__ void __launch_bounds__(256) td_lambda_kernel(const float* __restrict_
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const int tt = t - u;
-            vv[u] = __ldg(vp + (size_t)tt * strideT);
-            rr[u] = __ldg(reward + (size_t)tt * B + b);
-            mm[u] = mask ? __ldg(mask + (size_t)tt * B + b) : (uint8_t)1;
+            vv[u] = __ldcg(vp + (size_t)tt * strideT);
+            rr[u] = __ldcg(reward + (size_t)tt * B + b);
+            mm[u] = mask ? __ldcg(mask + (size_t)tt * B + b) : (uint8_t)1;
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -54,9 +54,9 @@ __global__ void __launch_bounds__(256) td_lambda_kernel(const float* __restrict_
         }
     }
     for (; t >= 0; --t) {
-        const float vt = __ldg(vp + (size_t)t * strideT);
-        const float rt = __ldg(reward + (size_t)t * B + b);
-        const bool live = mask ? (__ldg(mask + (size_t)t * B + b) != 0) : true;
+        const float vt = __ldcg(vp + (size_t)t * strideT);
+        const float rt = __ldcg(reward + (size_t)t * B + b);
+        const bool live = mask ? (__ldcg(mask + (size_t)t * B + b) != 0) : true;
         float R = 0.0f, A = 0.0f;
         if (live) {
             const float nv = next_live ? vnext : 0.0f;

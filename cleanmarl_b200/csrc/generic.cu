@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(GE * MAXN) gen_rollout_kernel(GenRolloutArgs a
     }
     const float* W = a.actor;
     if (a.w_in_smem) {
-        for (int i = tid; i < a.net.count; i += blockDim.x) wsm[i] = __ldg(a.actor + i);
+        for (int i = tid; i < a.net.count; i += blockDim.x) wsm[i] = __ldcg(a.actor + i);
         W = wsm;
     }
     __syncthreads();
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256) gen_gather_kernel(const float* __restrict
     if (s >= S) return;
     const int b = s % nb, r = s / nb, g = r % G, t = t0 + r / G;
     const float* base = x + (size_t)t * stride_t + (size_t)g * stride_g + b;
-    for (int k = 0; k < in_rows; ++k) out[(size_t)k * S + s] = __ldg(base + (size_t)k * ld);
+    for (int k = 0; k < in_rows; ++k) out[(size_t)k * S + s] = __ldcg(base + (size_t)k * ld);
     for (int k = 0; k < id_rows; ++k) out[(size_t)(in_rows + k) * S + s] = (k == g) ? 1.0f : 0.0f;
 }
 
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) gen_gemm_kernel(const float* __restrict__
         for (int i = tid; i < TK * TM; i += 256) {
             const int kk = i / TM, mm = i - kk * TM;
             const int m = m0 + mm, k = k0 + kk;
-            As[kk][mm] = (m < M && k < K) ? __ldg(Aw + (size_t)m * a_rs + (size_t)k * a_cs) : 0.0f;
+            As[kk][mm] = (m < M && k < K) ? __ldcg(Aw + (size_t)m * a_rs + (size_t)k * a_cs) : 0.0f;
         }
         for (int i = tid; i < TK * TN; i += 256) {
             const int kk = i / TN, nn = i - kk * TN;

@@ -99,12 +99,12 @@ __device__ void load_weights(float* sm, const ChunkArgs& a) {
     // every loop is straight-line code (CMARL_STRIDED): the ~30 global loads of a thread are in flight together
     CMARL_STRIDED(i, KIN * H, NT) {
         const int k = i / H, j = i - k * H;
-        sm[oW1T + i] = (k < a.in_rows) ? __ldg(P + L.w1 + j * O + k) : 0.0f;
+        sm[oW1T + i] = (k < a.in_rows) ? __ldcg(P + L.w1 + j * O + k) : 0.0f;
     }
     CMARL_STRIDED(i, 4 * H, NT) {
         const int g = i / H, j = i - g * H;
-        float v = __ldg(P + L.b1 + j);
-        if (a.fold_ids && g < a.N) v += __ldg(P + L.w1 + j * O + a.in_rows + g);
+        float v = __ldcg(P + L.b1 + j);
+        if (a.fold_ids && g < a.N) v += __ldcg(P + L.w1 + j * O + a.in_rows + g);
         sm[oB1 + i] = v;
     }
     CMARL_STRIDED(i, 2 * H * H, NT) {
@@ -112,30 +112,30 @@ __device__ void load_weights(float* sm, const ChunkArgs& a) {
         const float* W = (k < H) ? P + L.wih : P + L.whh;
         const int kk = (k < H) ? k : k - H;
         float4 w;
-        w.x = __ldg(W + (0 * H + j) * H + kk);
-        w.y = __ldg(W + (1 * H + j) * H + kk);
-        w.z = __ldg(W + (2 * H + j) * H + kk);
+        w.x = __ldcg(W + (0 * H + j) * H + kk);
+        w.y = __ldcg(W + (1 * H + j) * H + kk);
+        w.z = __ldcg(W + (2 * H + j) * H + kk);
         w.w = 0.0f;
         *reinterpret_cast<float4*>(sm + oWgT + (size_t)i * 4) = w;
     }
     CMARL_STRIDED(j, H, NT) {
         float4 b;
-        b.x = __ldg(P + L.bih + j) + __ldg(P + L.bhh + j);
-        b.y = __ldg(P + L.bih + H + j) + __ldg(P + L.bhh + H + j);
-        b.z = __ldg(P + L.bih + 2 * H + j);
-        b.w = __ldg(P + L.bhh + 2 * H + j);
+        b.x = __ldcg(P + L.bih + j) + __ldcg(P + L.bhh + j);
+        b.y = __ldcg(P + L.bih + H + j) + __ldcg(P + L.bhh + H + j);
+        b.z = __ldcg(P + L.bih + 2 * H + j);
+        b.w = __ldcg(P + L.bhh + 2 * H + j);
         *reinterpret_cast<float4*>(sm + oBg + j * 4) = b;
     }
     CMARL_STRIDED(i, G3 * H, NT) {
         const int row = i / H, k = i - row * H;
-        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + (k & 1)] = __ldg(P + L.wih + i);
-        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + 2 + (k & 1)] = __ldg(P + L.whh + i);
+        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + (k & 1)] = __ldcg(P + L.wih + i);
+        sm[oWih + (row * (H / 2) + (k >> 1)) * 4 + 2 + (k & 1)] = __ldcg(P + L.whh + i);
     }
     CMARL_STRIDED(i, H * 8, NT) {
         const int j = i / 8, c = i - j * 8;
-        sm[oW2T + i] = (c < NA) ? __ldg(P + L.w2 + c * H + j) : 0.0f;
+        sm[oW2T + i] = (c < NA) ? __ldcg(P + L.w2 + c * H + j) : 0.0f;
     }
-    if (threadIdx.x < 8) sm[oB2 + threadIdx.x] = (threadIdx.x < NA) ? __ldg(P + L.b2 + threadIdx.x) : 0.0f;
+    if (threadIdx.x < 8) sm[oB2 + threadIdx.x] = (threadIdx.x < NA) ? __ldcg(P + L.b2 + threadIdx.x) : 0.0f;
 }
 
 // input rows of (t, g, b0) -> xbuf; full aligned tiles by TMA bulk copies, ragged ones by guarded loads
@@ -155,7 +155,7 @@ __device__ void issue_x(float* xbuf, uint64_t* bar, const ChunkArgs& a, int t, i
         const int valid = a.B - b0;
         for (int i = threadIdx.x; i < a.in_rows * M; i += NT) {
             const int r = i / M, s = i - r * M;
-            xbuf[r * LD + s] = (s < valid) ? __ldg(base + (size_t)r * a.B + s) : 0.0f;
+            xbuf[r * LD + s] = (s < valid) ? __ldcg(base + (size_t)r * a.B + s) : 0.0f;
         }
         if (threadIdx.x == 0) mbar_arrive(bar);
     }
@@ -758,11 +758,11 @@ __global__ void __launch_bounds__(128) actor_act_gru_kernel(ActGruArgs a) {
     const int O = L.in;
     float x1[H], h[H];
 #pragma unroll
-    for (int j = 0; j < H; ++j) x1[j] = __ldg(P + L.b1 + j);
+    for (int j = 0; j < H; ++j) x1[j] = __ldcg(P + L.b1 + j);
     for (int k = 0; k < O; ++k) {
         const float xk = a.obs[((size_t)n * O + k) * a.B + b];
 #pragma unroll
-        for (int j = 0; j < H; ++j) x1[j] = fmaf(__ldg(P + L.w1 + j * O + k), xk, x1[j]);
+        for (int j = 0; j < H; ++j) x1[j] = fmaf(__ldcg(P + L.w1 + j * O + k), xk, x1[j]);
     }
 #pragma unroll
     for (int j = 0; j < H; ++j) {
@@ -771,22 +771,22 @@ __global__ void __launch_bounds__(128) actor_act_gru_kernel(ActGruArgs a) {
     }
     float z[NA];
 #pragma unroll
-    for (int c = 0; c < NA; ++c) z[c] = __ldg(P + L.b2 + c);
+    for (int c = 0; c < NA; ++c) z[c] = __ldcg(P + L.b2 + c);
     for (int j = 0; j < H; ++j) {
-        float ar = __ldg(P + L.bih + j) + __ldg(P + L.bhh + j);
-        float az = __ldg(P + L.bih + H + j) + __ldg(P + L.bhh + H + j);
-        float ai = __ldg(P + L.bih + 2 * H + j), ah = __ldg(P + L.bhh + 2 * H + j);
+        float ar = __ldcg(P + L.bih + j) + __ldcg(P + L.bhh + j);
+        float az = __ldcg(P + L.bih + H + j) + __ldcg(P + L.bhh + H + j);
+        float ai = __ldcg(P + L.bih + 2 * H + j), ah = __ldcg(P + L.bhh + 2 * H + j);
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-            ar = fmaf(__ldg(P + L.wih + (0 * H + j) * H + k), x1[k], ar);
-            az = fmaf(__ldg(P + L.wih + (1 * H + j) * H + k), x1[k], az);
-            ai = fmaf(__ldg(P + L.wih + (2 * H + j) * H + k), x1[k], ai);
+            ar = fmaf(__ldcg(P + L.wih + (0 * H + j) * H + k), x1[k], ar);
+            az = fmaf(__ldcg(P + L.wih + (1 * H + j) * H + k), x1[k], az);
+            ai = fmaf(__ldcg(P + L.wih + (2 * H + j) * H + k), x1[k], ai);
         }
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-            ar = fmaf(__ldg(P + L.whh + (0 * H + j) * H + k), h[k], ar);
-            az = fmaf(__ldg(P + L.whh + (1 * H + j) * H + k), h[k], az);
-            ah = fmaf(__ldg(P + L.whh + (2 * H + j) * H + k), h[k], ah);
+            ar = fmaf(__ldcg(P + L.whh + (0 * H + j) * H + k), h[k], ar);
+            az = fmaf(__ldcg(P + L.whh + (1 * H + j) * H + k), h[k], az);
+            ah = fmaf(__ldcg(P + L.whh + (2 * H + j) * H + k), h[k], ah);
         }
         const float r = sigmoidf_(ar), zz = sigmoidf_(az);
         const float nn = tanhf(ai + r * ah);
@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(128) actor_act_gru_kernel(ActGruArgs a) {
         a.h_out[((size_t)n * H + j) * a.B + b] = hn;
         const float hr = fmaxf(hn, 0.0f);
 #pragma unroll
-        for (int c = 0; c < NA; ++c) z[c] = fmaf(__ldg(P + L.w2 + c * H + j), hr, z[c]);
+        for (int c = 0; c < NA; ++c) z[c] = fmaf(__ldcg(P + L.w2 + c * H + j), hr, z[c]);
     }
     float q[NA];
 #pragma unroll

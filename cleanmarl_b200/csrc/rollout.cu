@@ -222,27 +222,27 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
         const float* __restrict__ P = a.actor;
         CMARL_STRIDED(i, H * W1LD, NTHR) {
             const int j = i / W1LD, k = i - j * W1LD;
-            sw[sW1 + i] = (k < CMARL_RAW_OBS - 4) ? __ldg(P + pW1 + j * O + k) : 0.0f;
+            sw[sW1 + i] = (k < CMARL_RAW_OBS - 4) ? __ldcg(P + pW1 + j * O + k) : 0.0f;
         }
         CMARL_STRIDED(i, NAG * H, NTHR) {
             const int g = i / H, j = i - g * H;
-            sw[sB1 + i] = __ldg(P + pB1 + j) + (FOLD ? __ldg(P + pW1 + j * O + CMARL_RAW_OBS + g) : 0.0f);   // one-hot id column of agent g
+            sw[sB1 + i] = __ldcg(P + pB1 + j) + (FOLD ? __ldcg(P + pW1 + j * O + CMARL_RAW_OBS + g) : 0.0f);   // one-hot id column of agent g
         }
         if (GRU) {
-            CMARL_STRIDED(i, 3 * H * H, NTHR) { sw[RL::sWih + i] = __ldg(P + RL::pWih + i); sw[RL::sWhh + i] = __ldg(P + RL::pWhh + i); }
+            CMARL_STRIDED(i, 3 * H * H, NTHR) { sw[RL::sWih + i] = __ldcg(P + RL::pWih + i); sw[RL::sWhh + i] = __ldcg(P + RL::pWhh + i); }
             CMARL_STRIDED(j, H, NTHR) {     // bir + bhr, biz + bhz, bin, bhn
-                sw[RL::sBg + 4 * j + 0] = __ldg(P + RL::pBih + j) + __ldg(P + RL::pBhh + j);
-                sw[RL::sBg + 4 * j + 1] = __ldg(P + RL::pBih + H + j) + __ldg(P + RL::pBhh + H + j);
-                sw[RL::sBg + 4 * j + 2] = __ldg(P + RL::pBih + 2 * H + j);
-                sw[RL::sBg + 4 * j + 3] = __ldg(P + RL::pBhh + 2 * H + j);
+                sw[RL::sBg + 4 * j + 0] = __ldcg(P + RL::pBih + j) + __ldcg(P + RL::pBhh + j);
+                sw[RL::sBg + 4 * j + 1] = __ldcg(P + RL::pBih + H + j) + __ldcg(P + RL::pBhh + H + j);
+                sw[RL::sBg + 4 * j + 2] = __ldcg(P + RL::pBih + 2 * H + j);
+                sw[RL::sBg + 4 * j + 3] = __ldcg(P + RL::pBhh + 2 * H + j);
             }
             for (int i = tid; i < 2 * NAG * H * REPB; i += NTHR) (&hs[0][0][0][0])[i] = 0.0f;   // h = None
         } else {
-            CMARL_STRIDED(i, H * H, NTHR) sw[sW2 + i] = __ldg(P + pW2 + i);
-            CMARL_STRIDED(i, H, NTHR) sw[sB2 + i] = __ldg(P + pB2 + i);
+            CMARL_STRIDED(i, H * H, NTHR) sw[sW2 + i] = __ldcg(P + pW2 + i);
+            CMARL_STRIDED(i, H, NTHR) sw[sB2 + i] = __ldcg(P + pB2 + i);
         }
-        CMARL_STRIDED(i, NACT * H, NTHR) sw[sW3 + i] = __ldg(P + pW3 + i);
-        if (tid < 8) sw[sB3 + tid] = tid < NACT ? __ldg(P + pB3 + tid) : 0.0f;
+        CMARL_STRIDED(i, NACT * H, NTHR) sw[sW3 + i] = __ldcg(P + pW3 + i);
+        if (tid < 8) sw[sB3 + tid] = tid < NACT ? __ldcg(P + pB3 + tid) : 0.0f;
     }
     __syncthreads();
     double ep_acc = 0.0;                                     // threads 0..REPB-1: episode return of env tid
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(double* __restrict__ env
     pdl_wait_then_trigger();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    if (episode_dev) episode = *episode_dev;
+    if (episode_dev) episode = __ldcg(reinterpret_cast<const unsigned long long*>(episode_dev));   // written by episode_advance_kernel: coherent load
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     // 12 uniforms in reset_world order: agent positions (x,y) x3, then landmark positions x3
     double u[12];

@@ -16,10 +16,11 @@
 //                                                           B1: D3 = dH2 W2           (D3 reuses D2's columns)
 //   E3: dH1 = D3 . relu'(H1)
 //   weight gradients: dW2 = dH2^T H1, dW1 = dH1^T X  contract over the SAMPLES, so both operands are
-//   needed sample-major ([feature][sample]) in shared memory: A = dH (64 feature rows), B = H1 / X in rounds
-//   of 32 feature rows (+ a constant "ones" row group whose product is the bias gradient), M = 64 MMAs
-//   into per-tile accumulators; the per-tile sums are added to running sums kept in the TMEM lanes the
-//   M = 64 accumulator layout leaves unused (lanes 16..31 of every quadrant).
+//   needed sample-major ([feature][sample]) in shared memory: A = the hi image of dH stacked on its lo image
+//   (2H feature rows: ONE M = 2H MMA forms the A_hi and the A_lo products together), B = H1 / X in rounds of
+//   32 feature rows (+ a "ones" row group: its products are the bias gradient and, row 1 + g, the gradient of the
+//   folded one-hot id column of agent group g), two passes per round (B_lo, then B_hi).  The accumulators stay in
+//   TMEM across `src.flush` tiles of a CTA and are then added into the CTA's partial row.
 #include "chain.cuh"
 #include "heads.cuh"
 #include "tc_ptx.cuh"
@@ -39,8 +40,8 @@ constexpr int B_S_BYTES = B_GROUPS * SBO_S;
 template <int H_, int K1P_, bool TRAIN_, int OUT_>
 struct TCfg {
     static constexpr int ZX_BYTES = OUT_ * 128 * 4;
-    // dH operand of the weight-gradient GEMMs: H feature rows are stored; an M = 64 MMA also reads rows H..63, which
-    // for H = 32 alias whatever follows (finite or not, they only reach accumulator rows that are never read)
+    // dH operand of the weight-gradient GEMMs: the hi image (H feature rows) directly followed by the lo image: together
+    // the 2H rows of ONE A operand (M = 2H = 64 or 128)
     static constexpr int A_S_BYTES = (H_ / 8) * SBO_S;        // per hi / lo image
     static constexpr int H = H_, K1P = K1P_;
     static constexpr bool TRAIN = TRAIN_;
@@ -48,7 +49,7 @@ struct TCfg {
     static constexpr int NR1 = (K1P + 31) / 32;           // rounds of the dW1 GEMM
     // TMEM columns
     static constexpr int cXh = 0, cXl = K1P, cAh = 2 * K1P, cAl = cAh + H, cD1 = cAl + H, cD2 = cD1 + H;
-    static constexpr int cW2 = cD2 + H;                   // per-tile dW2 | db2 (lanes 0-15 of each quadrant), running sums in lanes 16-31
+    static constexpr int cW2 = cD2 + H;                   // dW2 | db2 accumulators: rows 0..H-1 = A_hi products, H..2H-1 = A_lo products
     static constexpr int nW2 = 32 * NR2 + 8;
     static constexpr int cW1 = cW2 + nW2;
     static constexpr int nW1 = 32 * NR1 + 8;
@@ -67,13 +68,16 @@ struct TCfg {
     static constexpr int oW3T = oB2 + H * 4;              // f32 [H][8]
     static constexpr int oB3 = oW3T + H * 8 * 4;          // f32 [8]
     static constexpr int oDW3 = oB3 + 32;                 // f32 [4 warps][8][H] + [4][8]: dW3 / db3 partial sums per warp
-    static constexpr int oDId = oDW3 + (TRAIN ? (4 * 8 * H + 32) * 4 : 0);       // f32 [4][H] folded id-column gradients per agent group
-    static constexpr int oRed = oDId + (TRAIN ? 4 * H * 4 : 0);                 // f32 [64]
+    static constexpr int oRed = oDW3 + (TRAIN ? (4 * 8 * H + 32) * 4 : 0);      // f32 [64]
     static constexpr int oZx = oRed + 64;                                       // f32 [OUT][128]: partial outputs half 1 -> half 0, then dz half 0 -> half 1
     static constexpr int oAs = ((oZx + ZX_BYTES + 127) / 128) * 128;            // dH sample-major hi | lo
     static constexpr int oBs = oAs + (TRAIN ? 2 * A_S_BYTES : 0);               // H1 / X sample-major hi | lo
     static constexpr int smem_bytes = oBs + (TRAIN ? 2 * B_S_BYTES : 0);
     static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
+    // flush scratch (the A images between two tiles): [H][nW2 + 1] | [H][nW1 + 1] floats
+    static constexpr int pS2 = nW2 + 1, pS1 = nW1 + 1;
+    static_assert(!TRAIN || (H * (pS2 + pS1)) * 4 <= 2 * A_S_BYTES, "flush scratch fits the A images");
+
     static constexpr int CTAS_PER_SM = smem_bytes <= 113 * 1024 ? 2 : 1;   // two co-resident CTAs double the warps that hide latency
 };
 
@@ -135,17 +139,23 @@ __device__ __forceinline__ void issue_ts(bool leader, uint32_t d, uint32_t a_hi,
         }
     }
 }
-// D[64 x N] = A(smem sample-major [64][128]) * B(smem sample-major [N][128])^T, contraction over the 128 samples
-template <int N>
-__device__ __forceinline__ void issue_ss(bool leader, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
-    constexpr uint32_t idesc = tc::make_idesc_tf32(64, N, 0, 0);
+// D[MROWS x N] (+)= [A_hi ; A_lo](smem sample-major, MROWS = 2H rows) * B(smem sample-major [N][128])^T over the 128 samples
+// of the tile.  Pass 0 multiplies by B_lo (rows 0..H-1 collect A_hi B_lo, rows H.. the negligible A_lo B_lo), pass 1 by
+// B_hi (A_hi B_hi | A_lo B_hi): small products first within a tile, as in issue_ts; the row blocks are added when the
+// accumulators are flushed.  `keep`: the accumulators already hold earlier tiles of the flush group.
+// (Round 1 issued three M = 64 passes (A_lo B_hi, A_hi B_lo, A_hi B_hi): 48 MMAs per round instead of 32.  The SS MMAs
+// are bound by their shared-memory operand reads, not by the tensor pipe -- measured 10.5 k cycles per critic tile for
+// the four rounds in that form, 7.1 k in this one.)
+template <int MROWS, int N>
+__device__ __forceinline__ void issue_ss(bool leader, uint32_t d, uint32_t a, uint32_t b_hi, uint32_t b_lo, uint32_t keep) {
+    constexpr uint32_t idesc = tc::make_idesc_tf32(MROWS, N, 0, 0);
 #pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-        uint64_t da = tc::make_smem_desc(pass == 0 ? a_lo : a_hi, LBO_S, SBO_S, 0);
-        uint64_t db = tc::make_smem_desc(pass == 1 ? b_lo : b_hi, LBO_S, SBO_S, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+        uint64_t da = tc::make_smem_desc(a, LBO_S, SBO_S, 0);
+        uint64_t db = tc::make_smem_desc(pass == 0 ? b_lo : b_hi, LBO_S, SBO_S, 0);
 #pragma unroll 2
         for (int ks = 0; ks < M / 8; ++ks) {
-            if (leader) tc::mma_tf32(d, da, db, idesc, (uint32_t)(pass | ks));
+            if (leader) tc::mma_tf32(d, da, db, idesc, keep | (uint32_t)(pass | ks));
             da += (uint64_t)(KSTEP_S >> 4);
             db += (uint64_t)(KSTEP_S >> 4);
         }
@@ -175,25 +185,25 @@ __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
 #pragma unroll
     for (int r = 0; r < N1; ++r) {
         const int i = tid + r * NT, j = i / K1P, k = i - j * K1P;
-        w1[r] = (i < H * K1P && k < nd.in_rows) ? __ldg(W1 + j * in_dim + k) : 0.0f;
+        w1[r] = (i < H * K1P && k < nd.in_rows) ? __ldcg(W1 + j * in_dim + k) : 0.0f;
     }
 #pragma unroll
     for (int r = 0; r < N2; ++r) {
         const int i = tid + r * NT;
-        w2[r] = i < H * H ? __ldg(W2 + i) : 0.0f;
+        w2[r] = i < H * H ? __ldcg(W2 + i) : 0.0f;
     }
 #pragma unroll
     for (int r = 0; r < N3; ++r) {
         const int i = tid + r * NT, j = i / 8, a = i - j * 8;
-        w3[r] = (i < H * 8 && a < nd.out_dim) ? __ldg(W3 + a * H + j) : 0.0f;
+        w3[r] = (i < H * 8 && a < nd.out_dim) ? __ldcg(W3 + a * H + j) : 0.0f;
     }
     if (tid < 4 * H) {
         const int g = tid / H, j = tid - g * H;
-        vb1 = __ldg(b1 + j);
-        if (nd.fold_ids && g < n_groups) vid = __ldg(W1 + j * in_dim + nd.in_rows + g);
+        vb1 = __ldcg(b1 + j);
+        if (nd.fold_ids && g < n_groups) vid = __ldcg(W1 + j * in_dim + nd.in_rows + g);
     }
-    if (tid < H) vb2 = __ldg(b2 + tid);
-    if (tid < 8 && tid < nd.out_dim) vb3 = __ldg(b3 + tid);
+    if (tid < H) vb2 = __ldcg(b2 + tid);
+    if (tid < 8 && tid < nd.out_dim) vb3 = __ldcg(b3 + tid);
 
 #pragma unroll
     for (int r = 0; r < N1; ++r) {
@@ -303,6 +313,8 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     constexpr int NCX = K1P / 8;                 // 8-column chunks of X
     constexpr int NXO = (NCX + 1) / 2;           // ... owned by a thread (at most)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool ktl = g_tc_timeline_on == (OUT > 1 ? 2 : 1) && blockIdx.x == 0 && tid == 0;     // kernel-level stamps, slots 20..
+    if (ktl) g_tc_timeline[20] = clock64();
     // `src.indep` (the critic chain of an epoch, launched as a programmatic dependent of the actor chain): this grid
     // reads nothing the grid in front of it writes, so whatever is launched behind it may be scheduled right away ...
     if (src.indep) pdl_trigger();
@@ -318,7 +330,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         for (int i = tid * 16; i < 2 * C::A_S_BYTES + 2 * B_S_BYTES; i += NTHREADS * 16)
             *reinterpret_cast<uint4*>(sm + C::oAs + i) = make_uint4(0, 0, 0, 0);
         float* z0 = reinterpret_cast<float*>(sm + C::oDW3);
-        for (int i = tid; i < 4 * 8 * H + 32 + 4 * H; i += NTHREADS) z0[i] = 0.0f;
+        for (int i = tid; i < 4 * 8 * H + 32; i += NTHREADS) z0[i] = 0.0f;
     }
     if (tid == 0) {
         for (int i = 0; i < N_BARS; ++i) tc::mbar_init(&bars[i], i < D_F1 ? NCOMP : 1);
@@ -339,16 +351,20 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     tc::tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t sbase = tc::smem_u32(sm);
+    if (ktl) g_tc_timeline[21] = clock64();
 
     if (warp == 8) {
         // ================================ MMA issue warp ==================================================
         {
-            const uint32_t As_h = sbase + C::oAs, As_l = As_h + C::A_S_BYTES, Bs_h = sbase + C::oBs, Bs_l = Bs_h + B_S_BYTES;
+            const uint32_t As = sbase + C::oAs, Bs_h = sbase + C::oBs, Bs_l = Bs_h + B_S_BYTES;
+            constexpr int MR = 2 * H;                    // rows of the stacked dH operand
+            int gpos = 0;                                // position of the tile in its flush group
             uint32_t par = 0;
             int it = 0;
             const bool leader = tc::elect_one();
-            for (int u = blockIdx.x; u < units; u += gridDim.x, par ^= 1, ++it) {
+            for (int u = blockIdx.x; u < units; u += gridDim.x, par ^= 1, ++it, gpos = (gpos + 1 == src.flush) ? 0 : gpos + 1) {
                 const bool tl_on = g_tc_timeline_on == (OUT > 1 ? 2 : 1) && blockIdx.x == 0 && it == 1 && lane == 0;
+                const uint32_t keep = gpos != 0 ? 1u : 0u;
                 TL_STAMP(32);
                 acquire(&bars[R_X], par);
                 TL_STAMP(33);
@@ -366,27 +382,27 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                     issue_ts<H, H>(leader, tmem + C::cD2, tmem + C::cAh, tmem + C::cAl, sbase + C::oW2T, sbase + C::oW2T + C::szW2);
                     if (leader) tc::mma_commit(&bars[D_B1]);
                     TL_STAMP(38);
-                    if (C::NR2 == 1) issue_ss<40>(leader, tmem + C::cW2, As_h, As_l, Bs_h, Bs_l);
-                    else             issue_ss<32>(leader, tmem + C::cW2, As_h, As_l, Bs_h, Bs_l);
+                    if (C::NR2 == 1) issue_ss<MR, 40>(leader, tmem + C::cW2, As, Bs_h, Bs_l, keep);
+                    else             issue_ss<MR, 32>(leader, tmem + C::cW2, As, Bs_h, Bs_l, keep);
                     if (leader) tc::mma_commit(&bars[D_W2A]);
                     TL_STAMP(39);
                     if (C::NR2 == 2) {
                         acquire(&bars[R_W2B], par);
                         TL_STAMP(40);
-                        issue_ss<40>(leader, tmem + C::cW2 + 32, As_h, As_l, Bs_h, Bs_l);
+                        issue_ss<MR, 40>(leader, tmem + C::cW2 + 32, As, Bs_h, Bs_l, keep);
                         if (leader) tc::mma_commit(&bars[D_W2B]);
                         TL_STAMP(41);
                     }
                     acquire(&bars[R_W1A], par);
                     TL_STAMP(42);
-                    if (C::NR1 == 1) issue_ss<40>(leader, tmem + C::cW1, As_h, As_l, Bs_h, Bs_l);
-                    else             issue_ss<32>(leader, tmem + C::cW1, As_h, As_l, Bs_h, Bs_l);
+                    if (C::NR1 == 1) issue_ss<MR, 40>(leader, tmem + C::cW1, As, Bs_h, Bs_l, keep);
+                    else             issue_ss<MR, 32>(leader, tmem + C::cW1, As, Bs_h, Bs_l, keep);
                     if (leader) tc::mma_commit(&bars[D_W1A]);
                     TL_STAMP(43);
                     if (C::NR1 == 2) {
                         acquire(&bars[R_W1B], par);
                         TL_STAMP(44);
-                        issue_ss<40>(leader, tmem + C::cW1 + 32, As_h, As_l, Bs_h, Bs_l);
+                        issue_ss<MR, 40>(leader, tmem + C::cW1 + 32, As, Bs_h, Bs_l, keep);
                         if (leader) tc::mma_commit(&bars[D_W1B]);
                         TL_STAMP(45);
                     }
@@ -406,19 +422,16 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         float* zx = reinterpret_cast<float*>(sm + C::oZx);              // [2][OUT][128] partial outputs of the two halves
         float* dw3acc = reinterpret_cast<float*>(sm + C::oDW3) + q * 8 * H;                     // [8][H] of this quadrant
         float* db3acc = reinterpret_cast<float*>(sm + C::oDW3) + 4 * 8 * H + q * 8;
-        float* didacc = reinterpret_cast<float*>(sm + C::oDId);
         uint8_t* As_h = sm + C::oAs; uint8_t* As_l = As_h + C::A_S_BYTES;
         uint8_t* Bs_h = sm + C::oBs; uint8_t* Bs_l = Bs_h + B_S_BYTES;
         const int so = smaj(0, s);                                      // this sample's offset inside a feature row
 
-        if (TRAIN) {   // running gradient sums (lanes 16-31 of each quadrant) start at zero
-            uint32_t zero[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) zero[i] = 0u;
-            if (hf == 0)
-                for (int c = C::cW2; c < C::cEnd; c += 8) tmem_st8(tl + c, zero);
-            tc::tmem_wait_st();
-        }
+        // this thread's row of the weight-gradient accumulators (M = 2H): feature `feat` of the A_hi (quadrants 0, 1) or A_lo
+        // (quadrants 2, 3) products; an M = 64 accumulator keeps row r in lane (r / 16) * 32 + r % 16
+        const int feat = (q & 1) * (H / 2) + lane;
+        const bool lo_rows = q >= 2, row_ok = lane < H / 2;
+        float* part_out = TRAIN ? partials + (size_t)blockIdx.x * (p_net + CMARL_N_STATS) : nullptr;
+        bool flushed = false;                                        // the partial row holds earlier flushes
 
         float st[Head::NSTAT];
 #pragma unroll
@@ -441,7 +454,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int rr = 16 * i + e;
-                    xr[i * 8 + e] = (rr < rmax) ? __ldg(xp + (uint32_t)rr * step) : 0.0f;
+                    xr[i * 8 + e] = (rr < rmax) ? __ldcg(xp + (uint32_t)rr * step) : 0.0f;
                 }
             }
         };
@@ -473,14 +486,15 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
         if ((int)blockIdx.x < units) stage_x(blockIdx.x + gridDim.x);
 
         uint32_t par = 0;
-        int it = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, par ^= 1, ++it) {
+        int it = 0, gpos = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, par ^= 1, ++it, gpos = (gpos + 1 == src.flush) ? 0 : gpos + 1) {
             int bt, r, t, g;
             fast_divmod(u, tiles_b, inv_tb, r, bt);
             fast_divmod(r, src.G, inv_g, t, g);
             const int b = bt * M + s;
             const bool inb = b < src.nb;
             const bool tl_on = g_tc_timeline_on == (OUT > 1 ? 2 : 1) && blockIdx.x == 0 && it == 1 && tid == 0;
+            if (ktl && it < 8) g_tc_timeline[48 + it] = clock64();       // start of tile `it`
             const bool has_next = u + (int)gridDim.x < units;
             TL_STAMP(0);
             TL_STAMP(1);
@@ -537,6 +551,13 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 for (int i = 0; i < 16; ++i) {
                     *reinterpret_cast<uint32_t*>(Bs_h + smaj(16 * hf + i, 0) + so) = h1h[0][i];
                     *reinterpret_cast<uint32_t*>(Bs_l + smaj(16 * hf + i, 0) + so) = h1l[0][i];
+                }
+                // ones group, rows 1 + g': 1 for the samples of agent group g' (= this tile's g): the product with dH1 is the
+                // gradient of the id column folded into b1[g'].  (The previous tile's last round has completed: B is free.)
+                if (nd.fold_ids && hf == 1) {
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg)
+                        *reinterpret_cast<float*>(Bs_h + smaj(33 + gg, 0) + so) = (gg == g) ? 1.0f : 0.0f;
                 }
             }
 
@@ -745,96 +766,103 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                     acquire(&bars[rd == 0 ? D_W1A : D_W1B], par);
                     TL_STAMP(15 + 2 * rd);
                 }
-                // ---- per-tile sums (lanes 0-15 of the quadrant) -> running sums (lanes 16-31) ------------------
-                // half 0 folds the dW2 | db2 columns, half 1 the dW1 | db1 columns
-                {
-                    const int cb = hf == 0 ? C::cW2 : C::cW1;
-                    const int cn = hf == 0 ? C::nW2 : C::nW1;
-                    constexpr int FU = 5;                                // 8-column chunks in flight (cn = 40 or 72)
+                // ---- every src.flush tiles (and after the CTA's last one): accumulators -> the CTA's partial row ------------
+                if (gpos + 1 == src.flush || !has_next) {
+                    // the A images are free between two tiles: scratch [H][pS2] | [H][pS1]; the A_lo row block first, the A_hi
+                    // block added to it (fixed order), then one coalesced pass over the parameter vector
+                    if (ktl && !flushed) g_tc_timeline[24] = clock64();
+                    float* S2 = reinterpret_cast<float*>(sm + C::oAs);
+                    float* S1 = S2 + H * C::pS2;
+                    float* Sm = hf == 0 ? S2 : S1;
+                    const int cb = hf == 0 ? C::cW2 : C::cW1, ps = hf == 0 ? C::pS2 : C::pS1, cn = hf == 0 ? C::nW2 : C::nW1;
+                    constexpr int FCH = (C::nW2 > C::nW1 ? C::nW2 : C::nW1) / 8;   // 8-column chunks per block (5 or 9)
 #pragma unroll 1
-                    for (int c = 0; c < cn; c += 8 * FU) {
-                        uint32_t v[FU][8];
+                    for (int ph = 0; ph < 2; ++ph) {
+                        if (lo_rows == (ph == 0)) {                     // warp-uniform
+                            uint32_t v[FCH][8];
 #pragma unroll
-                        for (int k = 0; k < FU; ++k)
-                            if (c + 8 * k < cn) tc::tmem_ld8(tl + cb + c + 8 * k, v[k]);      // warp-uniform guard
-                        tc::tmem_wait_ld();
+                            for (int k = 0; k < FCH; ++k)
+                                if (8 * k < cn) tc::tmem_ld8(tl + cb + 8 * k, v[k]);          // warp-uniform guard
+                            tc::tmem_wait_ld();
+                            if (row_ok) {
+                                float* p = Sm + feat * ps;
 #pragma unroll
-                        for (int k = 0; k < FU; ++k) {
-                            if (c + 8 * k < cn) {
+                                for (int k = 0; k < FCH; ++k)
+                                    if (8 * k < cn) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float part = __shfl_sync(0xffffffffu, __uint_as_float(v[k][i]), lane & 15);
-                                    if (lane >= 16) v[k][i] = __float_as_uint(__uint_as_float(v[k][i]) + part);
-                                }
-                                // folded one-hot id column of this agent group: gradient = bias-gradient column of dW1
-                                if (nd.fold_ids && hf == 1 && c + 8 * k == 32 * C::NR1 && lane < 16) {
-                                    const int row = q * 16 + lane;
-                                    if (row < H) didacc[g * H + row] += __uint_as_float(v[k][0]);
-                                }
-                                tmem_st8(tl + cb + c + 8 * k, v[k]);
+                                        for (int i = 0; i < 8; ++i)
+                                            p[8 * k + i] = ph == 0 ? __uint_as_float(v[k][i]) : p[8 * k + i] + __uint_as_float(v[k][i]);
+                                    }
                             }
                         }
+                        compute_bar();
+                        if (ktl && !flushed) g_tc_timeline[25 + ph] = clock64();
                     }
-                    tc::tmem_wait_st();
+                    {
+                        // one coalesced pass over W1 | b1 | W2 | b2 of the partial row: straight-line, predicated code (every
+                        // scratch read and every load of the row's earlier value in flight before the first store)
+                        const int in_dim = nd.in_dim, in_rows = nd.in_rows;
+                        const int nW1e = H * in_dim;
+                        const float inv_in = 1.0f / (float)in_dim;
+                        const int ct = warp * 32 + lane;
+                        constexpr int N1 = (H * (K1P + 4) + 255) / 256, N2 = H * H / 256;
+                        float* oW1 = part_out;
+                        float* oB = part_out + nW1e;                     // b1 [H], then (after W2) b2 [H]
+                        float* oW2 = oB + H;
+                        float v1[N1], v2[N2], vb = 0.0f;
+#pragma unroll
+                        for (int r = 0; r < N1; ++r) {
+                            const int i = ct + 256 * r;
+                            int jj, k;
+                            fast_divmod(i < nW1e ? i : 0, in_dim, inv_in, jj, k);
+                            const int col = k < in_rows ? k : 32 * C::NR1 + 1 + (k - in_rows);     // k >= in_rows: folded id column
+                            v1[r] = S1[jj * C::pS1 + col];
+                        }
+#pragma unroll
+                        for (int r = 0; r < N2; ++r) {
+                            const int i = ct + 256 * r;
+                            v2[r] = S2[(i / H) * C::pS2 + (i % H)];
+                        }
+                        if (ct < H) vb = S1[ct * C::pS1 + 32 * C::NR1];
+                        else if (ct < 2 * H) vb = S2[(ct - H) * C::pS2 + 32 * C::NR2];
+                        float* ob = ct < H ? oB + ct : oW2 + H * H + (ct - H);
+                        if (flushed) {
+                            float o1[N1], o2[N2], ob0 = 0.0f;
+#pragma unroll
+                            for (int r = 0; r < N1; ++r) o1[r] = (ct + 256 * r < nW1e) ? oW1[ct + 256 * r] : 0.0f;
+#pragma unroll
+                            for (int r = 0; r < N2; ++r) o2[r] = oW2[ct + 256 * r];
+                            if (ct < 2 * H) ob0 = *ob;
+#pragma unroll
+                            for (int r = 0; r < N1; ++r) v1[r] += o1[r];
+#pragma unroll
+                            for (int r = 0; r < N2; ++r) v2[r] += o2[r];
+                            vb += ob0;
+                        }
+#pragma unroll
+                        for (int r = 0; r < N1; ++r)
+                            if (ct + 256 * r < nW1e) oW1[ct + 256 * r] = v1[r];
+#pragma unroll
+                        for (int r = 0; r < N2; ++r) oW2[ct + 256 * r] = v2[r];
+                        if (ct < 2 * H) *ob = vb;
+                    }
+                    if (ktl && !flushed) g_tc_timeline[27] = clock64();
+                    flushed = true;
                     TL_STAMP(18);
-                    // the next tile's dW MMAs (accumulate = 0) are issued only after every compute thread's next
-                    // R_DH2 arrival, i.e. after this fold: publish() there carries the fence
+                    compute_bar();      // scratch reads done before the next tile's dH2 goes to the A images
                 }
             }
         }
 
-        // ---- write this CTA's partial: gradients in torch parameter order, then the statistics ------------
+        if (ktl) g_tc_timeline[22] = clock64();
+        // ---- the rest of this CTA's partial row: output-layer gradients (shared-memory sums), then the statistics; the
+        //      hidden-layer gradients went there with the flushes (the last tile always flushes) ------------------------
         if (TRAIN) {
             compute_bar();
-            float* out = partials + (size_t)blockIdx.x * (p_net + CMARL_N_STATS);
-            const int in_dim = nd.in_dim;
-            float* gW1 = out;
-            float* gb1 = gW1 + H * in_dim;
-            float* gW2 = gb1 + H;
-            float* gb2 = gW2 + H * H;
-            float* gW3 = gb2 + H;
+            float* out = part_out;
+            float* gW3 = out + (H * nd.in_dim + H + H * H + H);
             float* gb3 = gW3 + nd.out_dim * H;
-            {
-                // running sums live in lanes 16-31 of each quadrant; every lane executes the (warp-aligned) loads
-                const int row = q * 16 + (lane - 16);               // gradient row j held by this lane
-                const bool valid = lane >= 16 && row < H;
-                if (hf == 0) {
-#pragma unroll 1
-                    for (int c = 0; c < C::nW2; c += 8) {
-                        uint32_t v[8];
-                        tc::tmem_ld8(tl + C::cW2 + c, v);
-                        tc::tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (valid) {
-                                if (c + i < H) gW2[row * H + c + i] = __uint_as_float(v[i]);
-                                else if (c + i == 32 * C::NR2) gb2[row] = __uint_as_float(v[i]);
-                            }
-                        }
-                    }
-                } else {
-#pragma unroll 1
-                    for (int c = 0; c < C::nW1; c += 8) {
-                        uint32_t v[8];
-                        tc::tmem_ld8(tl + C::cW1 + c, v);
-                        tc::tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (valid) {
-                                if (c + i < nd.in_rows) gW1[row * in_dim + c + i] = __uint_as_float(v[i]);
-                                else if (c + i == 32 * C::NR1) gb1[row] = __uint_as_float(v[i]);
-                            }
-                        }
-                    }
-                }
-            }
-            compute_bar();
             const int ct = warp * 32 + lane;                        // 0..255
-            if (nd.fold_ids)
-                for (int i = ct; i < src.G * H; i += NCOMP) {
-                    const int gg = i / H, j = i - gg * H;
-                    gW1[j * in_dim + nd.in_rows + gg] = didacc[i];
-                }
             const float* w3all = reinterpret_cast<const float*>(sm + C::oDW3);
             for (int i = ct; i < nd.out_dim * H; i += NCOMP)
                 gW3[i] = ((w3all[i] + w3all[8 * H + i]) + w3all[2 * 8 * H + i]) + w3all[3 * 8 * H + i];
@@ -855,6 +883,7 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
                 for (int k = Head::NSTAT; k < CMARL_N_STATS; ++k) out[p_net + k] = 0.0f;
         }
     }
+    if (ktl) g_tc_timeline[23] = clock64();
     tc::tcgen05_fence_before();
     __syncthreads();
     if (warp == 8) tc::tmem_dealloc(tmem, C::TMEM_COLS);

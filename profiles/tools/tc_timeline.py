@@ -11,7 +11,8 @@ assert tr.engine.tensor_cores
 for _ in range(2): tr.iteration()
 torch.cuda.synchronize()
 buf=(C.c_longlong*64)()
-names={0:"tile start",1:"X published",2:"F1 done seen",3:"H1 published",4:"H1s stored",5:"F2 done seen",6:"head done",7:"dW3 done",8:"dH2 published",9:"B1 done seen",10:"E3 done",11:"dW2a done seen",12:"H1s r1 published",13:"dW2b done seen",14:"dW1 r0 published",15:"dW1a done seen",16:"Xs r1 published",17:"dW1b done seen",18:"fold done",
+names={0:"tile start",1:"X published",2:"F1 done seen",3:"H1 published",4:"H1s stored",5:"F2 done seen",6:"head done",7:"dW3 done",8:"dH2 published",9:"B1 done seen",10:"E3 done",11:"dW2a done seen",12:"H1s r1 published",13:"dW2b done seen",14:"dW1 r0 published",15:"dW1a done seen",16:"Xs r1 published",17:"dW1b done seen",18:"flush done",
+20:"K: kernel entry",21:"K: setup done",24:"K: first flush start",25:"K: flush: lo rows in scratch",26:"K: flush: hi rows added",27:"K: flush: partial row written",22:"K: tile loop done",23:"K: partial written",48:"K: tile 0 start",49:"K: tile 1 start",50:"K: tile 2 start",51:"K: tile 3 start",52:"K: tile 4 start",53:"K: tile 5 start",54:"K: tile 6 start",55:"K: tile 7 start",
 32:"I: tile start",33:"I: X ready",34:"I: F1 issued",35:"I: H1 ready",36:"I: F2 issued",37:"I: dH2 ready",38:"I: B1 issued",39:"I: dW2a issued",40:"I: H1s r1 ready",41:"I: dW2b issued",42:"I: dW1a ready",43:"I: dW1a issued",44:"I: Xs r1 ready",45:"I: dW1b issued"}
 def run(fn,label,mode=1):
     lib.cmarl_debug_tc_timeline(mode,None)
