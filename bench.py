@@ -495,10 +495,16 @@ def run_b200(a):
                     "issued_frac_of_tf32_dense": (3 * ach / tf32_peak) if ach else None,
                     "hbm_gbs": kernels[dom].get("gbs"), "hbm_frac": kernels[dom].get("hbm_frac"),
                     "fp32_ffma_equiv_frac": kernels[dom].get("fp32_frac"),
+                    # the two chain kernels of an epoch take about the same time; the same figures for each of them
+                    "chains": {k: {"ms_per_launch": kernels[k]["ms_per_launch"], "tflops": kernels[k].get("tflops"),
+                                   "frac": kernels[k]["tflops"] / bf16_peak, "frac_of_tf32_dense": kernels[k]["tflops"] / tf32_peak,
+                                   "hbm_frac": kernels[k].get("hbm_frac")}
+                               for k in ("ppo_actor_chain", "ppo_critic_chain") if k in kernels and kernels[k].get("tflops")},
                     "note": "tiny contractions (K 24..64, N 32..64, M = 128 samples per tile): the kernel is bound by the "
                             "CUDA-core stages between its GEMMs and by MMA issue, not by tensor-pipe throughput (ncu "
-                            "summaries under profiles/); issued_frac_of_tf32_dense is what sm__pipe_tensor_cycles_active "
-                            "measures; hbm_frac is the same launch against the HBM roofline; the HBM-bound GAE kernel is "
+                            "summaries under profiles/); issued_frac_of_tf32_dense is the issued-MMA rate (3 tf32 MMAs per product in "
+                            "the activation GEMMs, 2 stacked ones in the weight-gradient GEMMs) that sm__pipe_tensor_cycles_active "
+                            "follows; hbm_frac is the same launch against the HBM roofline; the HBM-bound GAE kernel is "
                             "`gae_roofline`"}
     else:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom].get("gbs"), "peak": hbm_peak, "unit": "GB/s",
