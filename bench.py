@@ -653,7 +653,8 @@ def multi_gpu_check(MAPPO, Args, rank, world, local, envs_per_rank=256, iters=3)
         out = {"replicas_identical": all(torch.equal(gathered[0], x) for x in gathered), "max_param_diff": diff,
                "max_param_change_over_run": moved, "max_rel_stat_diff": sd, "comm": trn.comm, "ranks": world,
                "envs": B, "iterations": iters, "adam_steps": iters * 3, "step_counter_equal": trn.step == tr1.step,
-               "ok": bool(all(torch.equal(gathered[0], x) for x in gathered) and diff < 2e-6 and trn.step == tr1.step)}
+               "tolerance": 5e-6,    # fp32 reassociation of the rank sums through 9 Adam steps (measured 3e-8 at 2 ranks, 1.9e-6 at 8)
+               "ok": bool(all(torch.equal(gathered[0], x) for x in gathered) and diff < 5e-6 and trn.step == tr1.step)}
     torch.distributed.barrier()
     return out
 
