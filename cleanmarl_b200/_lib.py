@@ -54,6 +54,8 @@ _SIGNATURES = {
                                            C.c_int32, C.c_int32, _P, _P, _P]),
     "cmarl_clip_adam_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, C.c_double, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_double, _P, _P]),
+    "cmarl_reduce_clip_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_double, C.c_double, C.c_double,
+                                              C.c_double, C.c_double, C.c_double, _P, _P]),
     # peer-memory gradient exchange
     "cmarl_comm_bytes": (C.c_size_t, []),
     "cmarl_comm_create": (C.c_int, [_P, _P]),
@@ -69,7 +71,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
-VERSION = 103          # CMARL_VERSION of include/cmarl_b200.h
+VERSION = 104          # CMARL_VERSION of include/cmarl_b200.h
 N_KERNEL_IDS = 12      # CMARL_NK
 
 _lib = None

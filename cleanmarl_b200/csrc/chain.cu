@@ -4,6 +4,7 @@
 
 #include "chain.cuh"
 #include "heads.cuh"
+#include "reduce.cuh"
 
 namespace chain {
 
@@ -194,71 +195,14 @@ chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict_
     }
 }
 
-// Fixed-order sum of the per-CTA partials -> flat gradient vector + statistics (deterministic).
-// 32 output columns per CTA (a warp reads 128 contiguous bytes of one partial row); 16 thread groups each sum
-// 1/16 of the partial rows with 4 independent accumulators, then a fixed-order tree over the groups.  (512-thread CTAs:
-// the 303 CTAs of the default shapes are resident at once -- 4 per SM; with 1 024 threads 7 of them formed a second wave.)
-constexpr int RED_COLS = 32, RED_GROUPS = 16;
-__global__ void __launch_bounds__(RED_COLS * RED_GROUPS) reduce_partials_kernel(const float* __restrict__ pa, int grid_a, int Pa,
-                                                                                const float* __restrict__ pc, int grid_c, int Pc,
-                                                                                float n_groups, int count_from_c,
-                                                                                float* __restrict__ out) {
-    __shared__ float part[RED_GROUPS][RED_COLS + 1];
-    __shared__ double dpart[RED_GROUPS];
+// Fixed-order sum of the per-CTA partials -> flat gradient vector + statistics (deterministic): reduce.cuh.
+// (512-thread CTAs: the 303 CTAs of the default shapes are resident at once -- 4 per SM.)
+constexpr int RED_COLS = 32;
+__global__ void __launch_bounds__(RED_COLS * RED_GROUPS) reduce_partials_kernel(ReduceArgs r, float* __restrict__ out) {
     pdl_wait_then_trigger();
-    const int col_l = threadIdx.x % RED_COLS, grp = threadIdx.x / RED_COLS;
-    const int i = blockIdx.x * RED_COLS + col_l;
-    const int P = Pa + Pc;
-    const bool valid = i < P + CMARL_N_STATS;
-    const float* src = pa;
-    int n = 0, stride = 1, col = 0;
-    bool zero = false;
-    if (valid) {
-        if (i < Pa) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = i; }
-        else if (i < P) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = i - Pa; }
-        else {
-            const int k = i - P;   // out stats: 0 actor loss 1 critic loss 2 entropy 3 kl 4 clipfrac 5 n_valid(b,t)
-            if (k == 1) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = Pc + 0; }
-            else if (k == 5 && count_from_c) { src = pc; n = grid_c; stride = Pc + CMARL_N_STATS; col = Pc + 1; }   // ValueHead stat 1
-            else if (k <= 5) { src = pa; n = grid_a; stride = Pa + CMARL_N_STATS; col = Pa + (k == 0 ? 0 : k - 1); }
-            else zero = true;
-        }
-    }
-    const int per = (n + RED_GROUPS - 1) / RED_GROUPS;
-    const int c0 = grp * per, c1 = min(n, c0 + per);
-    const bool is_count = valid && (i == P + 5);
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    double d = 0.0;
-    if (valid && !zero) {
-        int c = c0;
-        if (is_count) {
-            for (; c < c1; ++c) d += (double)__ldcg(src + (size_t)c * stride + col);   // can exceed 2^24: sum in double
-        } else {
-            for (; c + 3 < c1; c += 4) {
-                a0 += __ldcg(src + (size_t)c * stride + col);
-                a1 += __ldcg(src + (size_t)(c + 1) * stride + col);
-                a2 += __ldcg(src + (size_t)(c + 2) * stride + col);
-                a3 += __ldcg(src + (size_t)(c + 3) * stride + col);
-            }
-            for (; c < c1; ++c) a0 += __ldcg(src + (size_t)c * stride + col);
-        }
-    }
-    part[grp][col_l] = (a0 + a1) + (a2 + a3);
-    if (is_count) dpart[grp] = d;
-    __syncthreads();
-    // fixed-order pairwise tree over the 32 groups
-    for (int w = RED_GROUPS / 2; w >= 1; w >>= 1) {
-        if (grp < w) {
-            part[grp][col_l] += part[grp + w][col_l];
-            if (is_count) dpart[grp] += dpart[grp + w];
-        }
-        __syncthreads();
-    }
-    if (grp == 0 && valid) {
-        if (zero) out[i] = 0.0f;
-        else if (is_count) out[i] = (float)(dpart[0] / (double)n_groups);
-        else out[i] = part[0][col_l];
-    }
+    bool have; int i;
+    const float v = reduce_column<RED_COLS>(r, blockIdx.x, &have, &i);
+    if (have) out[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -435,7 +379,8 @@ extern "C" int cmarl_ppo_epoch_grads_ex(cmarl_ctx* ctx, const float* params, con
                                         const uint8_t* avail, double clip, double ent_coef, double value_clip,
                                         int32_t env_begin, int32_t env_count, float* grads_out, void* workspace,
                                         void* stream) {
-    CMARL_ARG(ctx && params && actions && logp_old && adv && returns && grads_out && workspace, "null argument");
+    CMARL_ARG(ctx && params && actions && logp_old && adv && returns && workspace, "null argument");
+    CMARL_ARG(grads_out || !ctx->generic, "grads_out = NULL (partial rows for cmarl_reduce_clip_adam_step) needs the fused kernels");
     CMARL_ARG(!ctx->cfg.actor_recurrent, "recurrent actor: use cmarl_tbptt_chunk_grads + cmarl_critic_epoch_grads");
     CMARL_ARG(state || obs, "state or obs required");
     CMARL_ARG(ctx->cfg.critic_on_obs || state, "MAPPO critic needs state");
@@ -491,11 +436,17 @@ extern "C" int cmarl_ppo_epoch_grads_ex(cmarl_ctx* ctx, const float* params, con
     }
     if (e) return e;
 
+    if (!grads_out) {      // the caller reduces and steps in one launch: cmarl_reduce_clip_adam_step
+        ctx->pending_grid_a = grid_a; ctx->pending_grid_c = grid_c;
+        return 0;
+    }
     const int n_out = Pa + Pc + CMARL_N_STATS;
     {
         KernelTimer kt(ctx, K_PPO_REDUCE, st);
-        CMARL_CUDA(cmarl_launch(ctx, reduce_partials_kernel, dim3(ceil_div(n_out, RED_COLS)), dim3(RED_COLS * RED_GROUPS), 0, st,
-                                part_a, grid_a, Pa, part_c, grid_c, Pc, (float)c.n_agents, 0, grads_out));
+        ReduceArgs ra;
+        ra.pa = part_a; ra.grid_a = grid_a; ra.Pa = Pa; ra.pc = part_c; ra.grid_c = grid_c; ra.Pc = Pc;
+        ra.n_groups = (float)c.n_agents; ra.count_from_c = 0;
+        CMARL_CUDA(cmarl_launch(ctx, reduce_partials_kernel, dim3(ceil_div(n_out, RED_COLS)), dim3(RED_COLS * RED_GROUPS), 0, st, ra, grads_out));
     }
     return 0;
 }
@@ -507,8 +458,10 @@ int cmarl_reduce_one_net(cmarl_ctx* ctx, const float* pa, int grid_a, int Pa, co
     const int n_out = Pa + Pc + CMARL_N_STATS;
     {
         KernelTimer kt(ctx, K_PPO_REDUCE, st);
-        CMARL_CUDA(cmarl_launch(ctx, reduce_partials_kernel, dim3(ceil_div(n_out, RED_COLS)), dim3(RED_COLS * RED_GROUPS), 0, st,
-                                pa, grid_a, Pa, pc, grid_c, Pc, count_div, (int)(pa == nullptr), out));
+        ReduceArgs ra;
+        ra.pa = pa; ra.grid_a = grid_a; ra.Pa = Pa; ra.pc = pc; ra.grid_c = grid_c; ra.Pc = Pc;
+        ra.n_groups = count_div; ra.count_from_c = (int)(pa == nullptr);
+        CMARL_CUDA(cmarl_launch(ctx, reduce_partials_kernel, dim3(ceil_div(n_out, RED_COLS)), dim3(RED_COLS * RED_GROUPS), 0, st, ra, out));
     }
     return 0;
 }

@@ -116,6 +116,7 @@ struct cmarl_ctx {
     int sm_count;
     int ppo_grid_actor, ppo_grid_critic;
     int launches;
+    int pending_grid_a, pending_grid_c;   // partial rows left in the workspace by cmarl_ppo_epoch_grads_ex(grads_out = NULL)
     int timing_on;
     int use_tc;         // 1: tcgen05 (3xTF32) chain kernels, 0: fp32 FFMA chain kernels
     cmarl_comm comm;         // peer-memory gradient exchange (world <= 1: off)
@@ -127,9 +128,9 @@ struct cmarl_ctx {
     float* dev_floats;       // CMARL_DEV_FLOATS device floats owned by the context (generic Adam: per-tensor sums of squares)
     unsigned int* dev_words; // CMARL_DEV_WORDS zero-initialised device words owned by the context (tickets of the kernels' last-CTA protocols)
 };
-enum { CMARL_DW_ADAM_TICKET = 0, CMARL_DW_ADAM_BARRIER = 1 /* 2 words: count, generation */, CMARL_DEV_WORDS = 64 };
-enum { CMARL_DF_GEN_TSQ = 0 /* 64 floats: generic Adam, per-tensor sums of squares */, CMARL_DF_ADAM_TSQ = 64 /* 16 x 12 */,
-       CMARL_DEV_FLOATS = 320 };
+enum { CMARL_DW_ADAM_TICKET = 0, CMARL_DW_ADAM_BARRIER = 1 /* 4 words: count, generation of the Adam CTAs' barrier; count, generation of the fused kernel's */, CMARL_DEV_WORDS = 64 };
+enum { CMARL_DF_GEN_TSQ = 0 /* 64 floats: generic Adam, per-tensor sums of squares */, CMARL_DF_ADAM_TSQ = 64 /* 32 x 12 */,
+       CMARL_DEV_FLOATS = 512 };
 constexpr int CMARL_MAX_PARAMS = 16384;     // per context on the fused path (clip_adam_kernel: <= 16 co-resident CTAs x 1024 threads; = CMARL_COMM_SLOT_FLOATS)
 
 void cmarl_time_begin(cmarl_ctx* ctx, int id, cudaStream_t st);

@@ -2,6 +2,7 @@
 // Compiled with -fmad=false: these kernels reproduce the reference's fp32 operation order
 // (separate ATen ops => separately rounded mul/add), FMA only where ATen itself fuses (lerp).
 #include "common.cuh"
+#include "reduce.cuh"
 
 // ---------------------------------------------------------------------------------------- K5
 // One thread per (value head v, env b); sequential in t (the recurrence is order-sensitive in
@@ -210,7 +211,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
 // clip coefficients in every CTA -- and on every rank of a multi-GPU run.  (Round 1 let every CTA reduce ALL gradients
 // redundantly: ~3 600 instructions per warp, 12.8 us per launch; this form is one gradient per thread.)
 constexpr int ADAM_THREADS = 1024;
-constexpr int ADAM_MAX_CTAS = 16;        // = CMARL_MAX_PARAMS / ADAM_THREADS; all co-resident (grid barrier)
+constexpr int ADAM_MAX_CTAS = 32;        // = CMARL_MAX_PARAMS / 512 (the fused kernel's CTAs hold 512 parameters); all co-resident (grid barrier)
 constexpr int ADAM_MAX_TENSORS = 12;
 
 __device__ __forceinline__ int tensor_of(const AdamArgs& a, int i) {
@@ -220,15 +221,20 @@ __device__ __forceinline__ int tensor_of(const AdamArgs& a, int i) {
     return k;
 }
 
-template <bool XCHG>
-__global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) {
+// `cta` of `ncta` Adam CTAs (the whole grid of clip_adam_kernel; the first CTAs of reduce_clip_adam_kernel).  `pushed`: this
+// rank's sums are already on their way to the peers (posted by the reduction phase of the fused kernel).
+// NT threads per CTA (1 024 stand-alone, 512 in the fused kernel).  The sums of squares are formed per 512 parameters (16
+// warps in order) and combined pairwise, (h0 + h1) per 1 024 parameters and those in order, so that both forms give the
+// same bits.
+template <bool XCHG, int NT>
+__device__ __forceinline__ void adam_body(const AdamArgs& a, const int cta, const int ncta, const bool pushed) {
+    constexpr int ADAM_THREADS = NT;
     __shared__ float wsum[ADAM_THREADS / 32][ADAM_MAX_TENSORS];
     __shared__ float tnorm[ADAM_MAX_TENSORS];
     __shared__ double bc_sh[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.tensor_off[12];
-    const int mine = blockIdx.x * ADAM_THREADS + tid;          // the parameter this thread updates
-    pdl_wait_then_trigger();
+    const int mine = cta * ADAM_THREADS + tid;                 // the parameter this thread updates
     constexpr bool xchg = XCHG;       // peer-memory exchange compiled in only for multi-GPU launches
     int par = 0;
     unsigned int tag = 0;
@@ -246,20 +252,20 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
         tag = (unsigned int)(seq + 1ull);
         if (tid == 0) {                          // every CTA has read seq once its ticket is in: the last one advances it
             const unsigned t = atomicAdd(&me->ticket_pub, 1u);
-            if (t == gridDim.x - 1) { me->ticket_pub = 0; me->seq = seq + 1; }
+            if (t == (unsigned)ncta - 1) { me->ticket_pub = 0; me->seq = seq + 1; }
         }
-        if (mine < P) {
+        if (!pushed && mine < P) {
             const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(a.grads[mine]);
             for (int r = 0; r < a.world; ++r) st_relaxed_sys(&a.ch[r]->slots[par][a.rank][mine], w);
         }
-        if (blockIdx.x == 0 && tid < CMARL_N_STATS) {
+        if (!pushed && cta == 0 && tid < CMARL_N_STATS) {
             const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(a.grads[P + tid]);
             for (int r = 0; r < a.world; ++r) st_relaxed_sys(&a.ch[r]->slots[par][a.rank][P + tid], w);
         }
     }
     // gradient sum i over the ranks in rank order (every rank computes the identical value); local when world <= 1
     auto G = [&](int i) -> float {
-        if (!xchg) return a.grads[i];
+        if (!xchg) return __ldcg(a.grads + i);      // (fused kernel: written by other CTAs of this launch)
         const unsigned long long* row = &a.ch[a.rank]->slots[par][0][i];
         float v[CMARL_MAX_RANKS];
 #pragma unroll
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
             step = *reinterpret_cast<volatile int32_t*>(a.step_dev) + 1;
             __threadfence();
             const unsigned t = atomicAdd(a.ticket, 1u);
-            if (t == gridDim.x - 1) { *a.ticket = 0; *a.step_dev = step; }
+            if (t == (unsigned)ncta - 1) { *a.ticket = 0; *a.step_dev = step; }
         }
         // beta^step by repeated squaring (<= 2 log2(step) fp64 multiplies, within a few ulp of pow(): no float32-visible
         // difference in bc1, sqrt(bc2) or lr / bc1 for step <= 10^6)
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
     __syncwarp();
     // sums of squares of g / count per tensor over this CTA's elements
     {
-        const int i0 = blockIdx.x * ADAM_THREADS + warp * 32;   // this warp's 32 consecutive elements
+        const int i0 = cta * ADAM_THREADS + warp * 32;          // this warp's 32 consecutive elements
         if (i0 < P) {                                           // warp-uniform
             const float gs = g_mine / count;
             const float sq = gs * gs;                           // 0 beyond P (g = 0)
@@ -330,13 +336,24 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
         }
     }
     __syncthreads();
+    constexpr int HALVES = NT / 512;                 // 512-parameter halves per CTA
+    const int nhalf = HALVES * ncta;                 // partial sums over all CTAs: [half][tensor]
     if (tid < ADAM_MAX_TENSORS) {
-        float s = 0.0f;
-        for (int w = 0; w < ADAM_THREADS / 32; ++w) s += wsum[w][tid];
-        if (gridDim.x > 1) a.tsq_part[blockIdx.x * ADAM_MAX_TENSORS + tid] = s;
-        else tnorm[tid] = sqrtf(s);
+        float h[HALVES];
+#pragma unroll
+        for (int q = 0; q < HALVES; ++q) {
+            float s = 0.0f;
+            for (int w = 16 * q; w < 16 * q + 16; ++w) s += wsum[w][tid];
+            h[q] = s;
+        }
+        if (ncta > 1) {
+#pragma unroll
+            for (int q = 0; q < HALVES; ++q) a.tsq_part[(cta * HALVES + q) * ADAM_MAX_TENSORS + tid] = h[q];
+        } else {
+            tnorm[tid] = sqrtf(HALVES == 2 ? h[0] + h[HALVES - 1] : h[0]);       // one 1 024-parameter block (or less)
+        }
     }
-    if (gridDim.x > 1) {
+    if (ncta > 1) {
         // grid barrier (generation word + arrival count, both per context; the count is back at 0 when the launch ends, so
         // launches with different grid sizes can follow each other; launches of one context are serialised on its stream)
         __syncthreads();
@@ -344,7 +361,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
             volatile unsigned* gen = reinterpret_cast<volatile unsigned*>(a.barrier + 1);
             const unsigned g0 = *gen;
             __threadfence();
-            if (atomicAdd(a.barrier, 1u) == gridDim.x - 1) {
+            if (atomicAdd(a.barrier, 1u) == (unsigned)ncta - 1) {
                 *reinterpret_cast<volatile unsigned*>(a.barrier) = 0u;
                 __threadfence();
                 atomicAdd(a.barrier + 1, 1u);
@@ -358,7 +375,11 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
         __syncthreads();
         if (tid < ADAM_MAX_TENSORS) {
             float s = 0.0f;
-            for (unsigned c = 0; c < gridDim.x; ++c) s += *reinterpret_cast<volatile float*>(&a.tsq_part[c * ADAM_MAX_TENSORS + tid]);   // CTA order
+            for (int c = 0; c < nhalf; c += 2) {          // pairs of halves = 1 024-parameter blocks, in order
+                const float h0 = *reinterpret_cast<volatile float*>(&a.tsq_part[c * ADAM_MAX_TENSORS + tid]);
+                const float h1 = c + 1 < nhalf ? *reinterpret_cast<volatile float*>(&a.tsq_part[(c + 1) * ADAM_MAX_TENSORS + tid]) : 0.0f;
+                s += h0 + h1;
+            }
             tnorm[tid] = sqrtf(s);
         }
     }
@@ -400,7 +421,7 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
         a.m[mine] = m;
         a.v[mine] = v;
     }
-    if (blockIdx.x == 0 && tid == 0) {
+    if (cta == 0 && tid == 0) {
         if (a.stats_out && a.raw_stats) {
             for (int k = 0; k < 5; ++k) a.stats_out[k] = G(P + k);
             a.stats_out[5] = net_norm[0];
@@ -415,6 +436,62 @@ __global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) 
     }
 }
 
+template <bool XCHG>
+__global__ void __launch_bounds__(ADAM_THREADS, 1) clip_adam_kernel(AdamArgs a) {
+    pdl_wait_then_trigger();
+    adam_body<XCHG, ADAM_THREADS>(a, blockIdx.x, gridDim.x, false);
+}
+
+// The fixed-order reduction of the chain kernels' per-CTA partial rows (reduce.cuh; the same per-column order as
+// reduce_partials_kernel) and the Adam step in ONE launch: every CTA reduces 64 columns, posts them to the peers right away
+// (multi-GPU) and arrives at a barrier; the first `n_adam` CTAs wait for all arrivals and run the Adam body, the others
+// exit.  (Only the Adam CTAs ever spin, so the grid need not be co-resident as a whole.)  512-thread CTAs of 32 columns like
+// reduce_partials_kernel (four per SM: the 303 CTAs of the default shapes are one wave); a first version with 1 024-thread
+// CTAs of 64 columns (one per SM, 152 CTAs = two waves) was slower than the two separate launches (0.651 vs 0.638 ms).
+constexpr int FUSED_THREADS = 512;
+constexpr int FUSED_COLS = FUSED_THREADS / chain::RED_GROUPS;      // 32
+template <bool XCHG>
+__global__ void __launch_bounds__(FUSED_THREADS, 2) reduce_clip_adam_kernel(chain::ReduceArgs r, float* __restrict__ grads_out, AdamArgs a,
+                                                                           int n_adam) {
+    __shared__ unsigned long long seq_sh;
+    __shared__ unsigned gen_sh;
+    const int tid = threadIdx.x;
+    pdl_wait_then_trigger();
+    if (tid == 0) {
+        gen_sh = *reinterpret_cast<volatile unsigned*>(a.barrier + 3);
+        if (XCHG) seq_sh = *reinterpret_cast<volatile unsigned long long*>(&a.ch[a.rank]->seq);
+    }
+    bool have; int i;
+    const float v = chain::reduce_column<FUSED_COLS>(r, blockIdx.x, &have, &i);      // (contains block barriers)
+    if (have) {
+        grads_out[i] = v;
+        if (XCHG) {
+            const unsigned long long seq = seq_sh;
+            const int par = (int)(seq & 1ull);
+            const unsigned long long w = ((unsigned long long)(unsigned int)(seq + 1ull) << 32) | (unsigned long long)__float_as_uint(v);
+            for (int rk = 0; rk < a.world; ++rk) st_relaxed_sys(&a.ch[rk]->slots[par][a.rank][i], w);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(a.barrier + 2, 1u) == gridDim.x - 1) {
+            *reinterpret_cast<volatile unsigned*>(a.barrier + 2) = 0u;
+            __threadfence();
+            atomicAdd(a.barrier + 3, 1u);
+        } else if ((int)blockIdx.x < n_adam) {
+            volatile unsigned* gen = reinterpret_cast<volatile unsigned*>(a.barrier + 3);
+            unsigned spins = 0;
+            while (*gen == gen_sh)
+                if (++spins > (1u << 30)) __trap();
+        }
+        __threadfence();
+    }
+    if ((int)blockIdx.x >= n_adam) return;
+    __syncthreads();
+    adam_body<XCHG, FUSED_THREADS>(a, blockIdx.x, n_adam, true);
+}
+
 static void fill_comm(const cmarl_ctx* ctx, AdamArgs& a, int channel) {
     a.rank = ctx->comm.rank;
     a.world = ctx->comm.world;
@@ -426,17 +503,17 @@ int cmarl_gen_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, 
                              int32_t* step_dev, double lr_actor, double lr_critic, double beta1, double beta2, double eps,
                              double max_norm, float* stats_out, cudaStream_t st);
 
-extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, float* exp_avg,
-                                    float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor,
-                                    double lr_critic, double beta1, double beta2, double eps, double max_norm,
-                                    float* stats_out, void* stream) {
+static int clip_adam_impl(cmarl_ctx* ctx, const void* fused_workspace, float* params, const float* grads, float* grads_rw, float* exp_avg,
+                          float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor,
+                          double lr_critic, double beta1, double beta2, double eps, double max_norm,
+                          float* stats_out, void* stream) {
     CMARL_ARG(ctx && params && grads && exp_avg && exp_avg_sq, "null argument");
     CMARL_ARG(step_dev || step >= 1, "step must be >= 1");
     CMARL_ARG(!ctx->cfg.actor_recurrent, "recurrent actor: use cmarl_adam_step_net");
     if (ctx->generic)
         return cmarl_gen_clip_adam_step(ctx, params, grads, exp_avg, exp_avg_sq, step, step_dev, lr_actor, lr_critic, beta1, beta2, eps,
                                         max_norm, stats_out, as_stream(stream));
-    CMARL_ARG(ctx->actor.count + ctx->critic.count <= ADAM_THREADS * ADAM_MAX_CTAS, "too many parameters for clip_adam_kernel");
+    CMARL_ARG(ctx->actor.count + ctx->critic.count <= CMARL_MAX_PARAMS, "too many parameters for clip_adam_kernel");
     AdamArgs a;
     a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.stats_out = stats_out;
     a.step_dev = step_dev; a.step = step; a.ticket = ctx->dev_words + CMARL_DW_ADAM_TICKET;
@@ -455,13 +532,49 @@ extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* 
     a.extra_div = 1.0f; a.raw_stats = 0;
     a.wd[0] = ctx->weight_decay[0]; a.wd[1] = ctx->weight_decay[1];
     fill_comm(ctx, a, 0);
+    const dim3 grid(ceil_div(a.tensor_off[12], ADAM_THREADS)), block(ADAM_THREADS);
+    if (fused_workspace) {
+        const dim3 fblock(FUSED_THREADS);
+        const int n_adam = ceil_div(a.tensor_off[12], FUSED_THREADS);
+        // reduction of the partial rows cmarl_ppo_epoch_grads_ex(grads_out = NULL) left in the workspace + Adam, one launch
+        const int Pa = ctx->actor.count, Pc = ctx->critic.count;
+        chain::ReduceArgs r;
+        r.pa = reinterpret_cast<const float*>(fused_workspace); r.grid_a = ctx->pending_grid_a; r.Pa = Pa;
+        r.pc = r.pa + (size_t)2 * ctx->sm_count * (Pa + CMARL_N_STATS); r.grid_c = ctx->pending_grid_c; r.Pc = Pc;
+        r.n_groups = (float)ctx->cfg.n_agents; r.count_from_c = 0;
+        const dim3 fgrid(ceil_div(Pa + Pc + CMARL_N_STATS, FUSED_COLS));
+        KernelTimer kt(ctx, K_ADAM, as_stream(stream));
+        CMARL_CUDA(a.world > 1 ? cmarl_launch(ctx, reduce_clip_adam_kernel<true>, fgrid, fblock, 0, as_stream(stream), r, grads_rw, a, n_adam)
+                               : cmarl_launch(ctx, reduce_clip_adam_kernel<false>, fgrid, fblock, 0, as_stream(stream), r, grads_rw, a, n_adam));
+        return 0;
+    }
     {
         KernelTimer kt(ctx, K_ADAM, as_stream(stream));
-        const dim3 grid(ceil_div(a.tensor_off[12], ADAM_THREADS)), block(ADAM_THREADS);
         CMARL_CUDA(a.world > 1 ? cmarl_launch(ctx, clip_adam_kernel<true>, grid, block, 0, as_stream(stream), a)
                                : cmarl_launch(ctx, clip_adam_kernel<false>, grid, block, 0, as_stream(stream), a));
     }
     return 0;
+}
+
+extern "C" int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, float* exp_avg,
+                                    float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor,
+                                    double lr_critic, double beta1, double beta2, double eps, double max_norm,
+                                    float* stats_out, void* stream) {
+    return clip_adam_impl(ctx, nullptr, params, grads, nullptr, exp_avg, exp_avg_sq, step, step_dev, lr_actor, lr_critic, beta1, beta2,
+                          eps, max_norm, stats_out, stream);
+}
+
+extern "C" int cmarl_reduce_clip_adam_step(cmarl_ctx* ctx, const void* workspace, float* params, float* grads_out, float* exp_avg,
+                                           float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor,
+                                           double lr_critic, double beta1, double beta2, double eps, double max_norm,
+                                           float* stats_out, void* stream) {
+    CMARL_ARG(ctx && workspace && grads_out, "null argument");
+    CMARL_ARG(!ctx->generic, "layered shapes: use cmarl_ppo_epoch_grads + cmarl_clip_adam_step");
+    CMARL_ARG(ctx->pending_grid_a > 0 && ctx->pending_grid_c > 0, "call cmarl_ppo_epoch_grads_ex with grads_out = NULL first");
+    const int e = clip_adam_impl(ctx, workspace, params, grads_out, grads_out, exp_avg, exp_avg_sq, step, step_dev, lr_actor, lr_critic,
+                                 beta1, beta2, eps, max_norm, stats_out, stream);
+    ctx->pending_grid_a = ctx->pending_grid_c = 0;
+    return e;
 }
 
 // One network at a time (recurrent path: the actor is stepped once per truncated-BPTT chunk, the critic once
@@ -493,7 +606,7 @@ extern "C" int cmarl_adam_step_net(cmarl_ctx* ctx, int32_t net, float* params, c
     }
     for (int j = k + 1; j < 13; ++j) a.tensor_off[j] = a.tensor_off[k];
     a.n_tensors = k; a.n_actor_tensors = k;
-    CMARL_ARG(a.tensor_off[k] <= ADAM_THREADS * ADAM_MAX_CTAS, "too many parameters for clip_adam_kernel");
+    CMARL_ARG(a.tensor_off[k] <= CMARL_MAX_PARAMS, "too many parameters for clip_adam_kernel");
     a.lr[0] = lr; a.lr[1] = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
     a.extra_div = (float)extra_div; a.raw_stats = 1;
     a.wd[0] = a.wd[1] = ctx->weight_decay[net];

@@ -87,6 +87,11 @@ class Engine:
         self.n_params = self.n_actor + self.n_critic
         self.n_heads = self.lib.cmarl_value_heads(h)
         self.workspace = torch.empty(self.lib.cmarl_workspace_bytes(h) // 4, dtype=torch.float32, device=self.device)
+        # default shapes, MLP actor: the partial reduction and the Adam step can share one launch (reduce_clip_adam_step)
+        self.fused_update = (not shapes.actor_recurrent and shapes.n_agents == 3 and (shapes.n_landmarks or 3) == 3
+                             and shapes.actor_layers == 1 and shapes.critic_layers == 1
+                             and shapes.actor_hidden in (32, 64) and shapes.critic_hidden in (32, 64)
+                             and os.environ.get("CMARL_FUSED_UPDATE", "0") == "1")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -242,8 +247,9 @@ class Engine:
                         avail=None, clip=0.2, ent_coef=0.001, value_clip=-1.0, values_old=None, env_begin=0,
                         env_count=None):
         """``value_clip`` / ``values_old`` and the env block ``[env_begin, env_begin + env_count)`` are the two default-off
-        extensions of cmarl_ppo_epoch_grads_ex (not in the reference); without them this is cmarl_ppo_epoch_grads."""
-        if value_clip <= 0 and env_begin == 0 and env_count in (None, self.shapes.n_envs):
+        extensions of cmarl_ppo_epoch_grads_ex (not in the reference); without them this is cmarl_ppo_epoch_grads.
+        ``grads=None`` leaves the chain kernels' partial rows in the workspace for ``reduce_clip_adam_step``."""
+        if grads is not None and value_clip <= 0 and env_begin == 0 and env_count in (None, self.shapes.n_envs):
             _lib.check(self.lib.cmarl_ppo_epoch_grads(
                 self._h, self._f(params, "params"), self._f(state, "state"), self._f(obs, "obs"),
                 _ptr(actions, torch.int32, self.device, "actions"), self._f(logp_old, "logp_old"), self._f(adv, "adv"),
@@ -258,6 +264,17 @@ class Engine:
             _ptr(avail, torch.uint8, self.device, "avail"), float(clip), float(ent_coef), float(value_clip),
             int(env_begin), int(self.shapes.n_envs - env_begin if env_count is None else env_count),
             self._f(grads, "grads"), C.c_void_p(self.workspace.data_ptr()), self._stream()), "cmarl_ppo_epoch_grads_ex")
+
+    def reduce_clip_adam_step(self, params, grads, exp_avg, exp_avg_sq, *, step=1, step_dev=None, lr_actor=8e-4,
+                              lr_critic=8e-4, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=-1.0, stats_out=None):
+        """cmarl_reduce_clip_adam_step: the reduction of the partial rows left by ``ppo_epoch_grads(grads=None)`` and the
+        Adam step in one launch; ``grads`` receives the reduced sums."""
+        _lib.check(self.lib.cmarl_reduce_clip_adam_step(
+            self._h, C.c_void_p(self.workspace.data_ptr()), self._f(params, "params"), self._f(grads, "grads"),
+            self._f(exp_avg, "exp_avg"), self._f(exp_avg_sq, "exp_avg_sq"), int(step),
+            _ptr(step_dev, torch.int32, self.device, "step_dev"), float(lr_actor), float(lr_critic), float(beta1),
+            float(beta2), float(eps), float(max_norm), self._f(stats_out, "stats_out"), self._stream()),
+            "cmarl_reduce_clip_adam_step")
 
     def clip_adam_step(self, params, grads, exp_avg, exp_avg_sq, *, step=1, step_dev=None, lr_actor=8e-4,
                        lr_critic=8e-4, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=-1.0, stats_out=None):

@@ -441,14 +441,16 @@ class MAPPO:
                 if M > 1:                                        # minibatch = contiguous block of this GPU's envs
                     lo, hi = mb * self.B // M, (mb + 1) * self.B // M
                     ext.update(env_begin=lo, env_count=hi - lo)
-                eng.ppo_epoch_grads(self.net.flat, self.grads, state=buf["state"], actions=buf["actions"],
+                # one launch for the partial reduction + Adam unless an NCCL all-reduce has to sit between them
+                fused = getattr(eng, "fused_update", False) and (self.world == 1 or self.comm == "p2p")
+                eng.ppo_epoch_grads(self.net.flat, None if fused else self.grads, state=buf["state"], actions=buf["actions"],
                                     logp_old=buf["logp"], adv=buf["adv"], returns=buf["returns"], clip=a.ppo_clip,
                                     ent_coef=a.entropy_coef, **ext)
                 self._allreduce_grads(self.grads)
-                eng.clip_adam_step(self.net.flat, self.grads, self.exp_avg, self.exp_avg_sq, step_dev=self.adam_step,
-                                   lr_actor=a.learning_rate_actor, lr_critic=a.learning_rate_critic,
-                                   max_norm=a.clip_gradients,
-                                   stats_out=self.epoch_stats[ep] if M == 1 else self.mb_stats[ep, mb])
+                (eng.reduce_clip_adam_step if fused else eng.clip_adam_step)(
+                    self.net.flat, self.grads, self.exp_avg, self.exp_avg_sq, step_dev=self.adam_step,
+                    lr_actor=a.learning_rate_actor, lr_critic=a.learning_rate_critic, max_norm=a.clip_gradients,
+                    stats_out=self.epoch_stats[ep] if M == 1 else self.mb_stats[ep, mb])
                 self.training_step += 1
         if M > 1:                                                # logged per epoch: the mean over its optimizer steps
             torch.mean(self.mb_stats, dim=1, out=self.epoch_stats)

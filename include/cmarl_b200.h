@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CMARL_VERSION 103
+#define CMARL_VERSION 104
 #define CMARL_N_STATS 8          /* floats appended to the flat gradient vector, see cmarl_ppo_epoch_grads */
 #define CMARL_RAW_OBS 18
 
@@ -214,6 +214,15 @@ int cmarl_clip_adam_step(cmarl_ctx* ctx, float* params, const float* grads, floa
                          float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor,
                          double lr_critic, double beta1, double beta2, double eps, double max_norm,
                          float* stats_out, void* stream);
+/* The fixed-order reduction of cmarl_ppo_epoch_grads and this step in ONE launch: call cmarl_ppo_epoch_grads_ex with
+ * grads_out = NULL (the chain kernels' per-CTA partial rows then stay in `workspace`), then this entry with the same
+ * workspace; grads_out receives the reduced sums (the same values cmarl_ppo_epoch_grads would have written) and the step
+ * follows as in cmarl_clip_adam_step.  With a peer-memory exchange attached the sums go to the peers as they are formed.
+ * Fused kernels only (default shapes, MLP actor). */
+int cmarl_reduce_clip_adam_step(cmarl_ctx* ctx, const void* workspace, float* params, float* grads_out, float* exp_avg,
+                                float* exp_avg_sq, int32_t step, int32_t* step_dev, double lr_actor, double lr_critic,
+                                double beta1, double beta2, double eps, double max_norm, float* stats_out, void* stream);
+
 
 /* ======================================================================================================
  * Recurrent-actor path (BASELINE config 4): cleanmarl/mappo_lstm_multienvs.py ("LSTM" below).

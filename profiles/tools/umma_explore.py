@@ -295,6 +295,33 @@ def exp_E5x3(env):
     exp_E5(env, ((128, 56),))
 
 
+def exp_E10(env):
+    globals().update(env)
+    # ---- E10 (round 2): brute force over the descriptor fields of an MN-major B operand (no swizzle and the swizzled
+    #      layout types), B = W stored [k = 64][n = 64] with rows = k in the K-major core layout (what B1 of tc_chain would
+    #      read if it used the W2 image of F2 instead of a second, transposed image).  A stays K-major (known good).
+    W = rng.standard_normal((64, 64)).astype(np.float32)
+    img = np.zeros(96 * 1024, dtype=np.uint8)
+    put(img, 0, A, core_offsets(128, 64, lbo, sbo))
+    put(img, 40 * 1024, W, core_offsets(64, 64, lbo, sbo))
+    ref7 = (trunc_tf32(A).astype(np.float64) @ trunc_tf32(W).astype(np.float64)).astype(np.float32)
+    cand = (16, 32, 64, 128, 256, 512, 1024, 2048)
+    hits = 0
+    for layout in (0,):
+        for bl in cand:
+            for bs in cand:
+                for kst in cand:
+                    rc, st, out = run(img, 0, 40 * 1024, lbo, sbo, bl, bs, 0, layout, idesc(128, 64, 0, 1), 64 // 8, 2 * lbo, kst, 64)
+                    if rc or st:
+                        print(f"E10 layout {layout} lbo {bl} sbo {bs} kstep {kst}: rc {rc} status {st}", flush=True)
+                        continue
+                    err = np.abs(out - ref7).max() / np.abs(ref7).max()
+                    if err < 1e-3:
+                        hits += 1
+                        print(f"E10 MATCH layout {layout} b_lbo {bl} b_sbo {bs} b_kstep {kst}: rel_err {err:.3e}", flush=True)
+    print(f"E10 done: {hits} matching descriptor settings out of {len(cand) ** 3}", flush=True)
+
+
 EXPERIMENTS = ["E8", "E9", "E1", "E1b", "E2", "E3", "E4", "E5", "E6", "E7", "E5x1", "E5x2", "E5x3"]
 
 

@@ -35,7 +35,7 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, s), f"{s} declared in include/cmarl_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == syms, "cleanmarl_b200/_lib.py must bind exactly the header's entry points"
     _lib.load()
-    assert _lib.load().cmarl_version() == _lib.VERSION == 103
+    assert _lib.load().cmarl_version() == _lib.VERSION == 104
 
 
 def test_no_gpu_fails_loudly():
