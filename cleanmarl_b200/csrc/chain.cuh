@@ -136,6 +136,25 @@ struct PolicyHeadArgs {
     float clip, ent_coef, inv_groups;
 };
 
+// One truncated-BPTT chunk of the recurrent actor (gru.cu: fp32 FFMA kernel, tc_gru.cu: tcgen05 kernels)
+struct GruChunkArgs {
+    const float* params;      // recurrent actor, torch order
+    GruLayout L;
+    const float* x;           // state [T][S][B] (rows 18 g + k) or obs [T][N][O][B]
+    size_t stride_t, stride_g;
+    int in_rows;              // 18 (ids folded into the bias) or O
+    int fold_ids;
+    int T, N, B;
+    int t0, t1;
+    float* h_seq;             // [T+1][N][H][B]
+    float* stash;             // [T][N][5H][B] or null: x1, r, z, n, ghn of every step (pass 1 writes, pass 2 reads instead
+                              // of recomputing the gates: 640 B per sample-step through L2 / HBM for 27 % fewer instructions)
+    float* partials;          // [grid][P + 8]
+    PolicyHeadArgs head;
+    int passes;               // FFMA kernel: bit 0 = pass 1 (hidden states, stash), bit 1 = pass 2 (head + backward; alone it needs the stash)
+    int flush;                // tcgen05 backward kernel: steps whose weight-gradient products accumulate in TMEM between two flushes
+};
+
 struct ValueHeadArgs {
     const float* returns;      // [T][V][B]  (train)
     const uint8_t* mask;

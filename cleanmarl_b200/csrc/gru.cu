@@ -24,10 +24,13 @@
 // read them as LDS.128 and the weights as warp-broadcast LDS.64/128.  Input rows arrive by cp.async.bulk (TMA
 // engine) + mbarrier, double buffered across steps; h_seq[t] of the next backward step is prefetched into registers.
 #include <stdlib.h>
+#include <string.h>
 
 #include "chain.cuh"
 #include "heads.cuh"
 
+int cmarl_tc_gru_setup();
+int cmarl_tc_gru_launch(cmarl_ctx* ctx, const chain::GruChunkArgs& a, int which, int* grid_out, cudaStream_t st);
 int cmarl_reduce_one_net(cmarl_ctx* ctx, const float* pa, int grid_a, int Pa, const float* pc, int grid_c, int Pc,
                          float count_div, float* out, cudaStream_t st);
 
@@ -73,21 +76,7 @@ constexpr size_t SMEM_BYTES = (size_t)oEnd * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(oX % 4 == 0 && oHp % 4 == 0 && oG % 4 == 0 && oDW % 4 == 0 && oWgT % 4 == 0 && oWih % 4 == 0, "16-B alignment");
 
-struct ChunkArgs {
-    const float* params;      // recurrent actor, torch order
-    GruLayout L;
-    const float* x;           // state [T][S][B] (rows 18 g + k) or obs [T][N][O][B]
-    size_t stride_t, stride_g;
-    int in_rows;              // 18 (ids folded into the bias) or O
-    int fold_ids;
-    int T, N, B;
-    int t0, t1;
-    float* h_seq;             // [T+1][N][H][B]
-    float* stash;             // [T][N][5H][B] or null: x1, r, z, n, ghn of every step (pass 1 writes, pass 2 reads instead
-                              // of recomputing the gates: 640 B per sample-step through L2 / HBM for 27 % fewer instructions)
-    float* partials;          // [grid][P + 8]
-    PolicyHeadArgs head;
-};
+using ChunkArgs = chain::GruChunkArgs;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -350,7 +339,7 @@ __global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a)
         const int valid = min(M, a.B - b0);
         // step list of this tile: pass 1 t0..t1-1, pass 2 t1-1..t0.  Step i's input rows are issued one step ahead.
         auto t_of = [&](int i) { return i < nsteps ? a.t0 + i : a.t1 - 1 - (i - nsteps); };
-        issue_x(sm + oX + (it & 1) * KIN * LD, &bars[it & 1], a, t_of(0), g, b0);
+        issue_x(sm + oX + (it & 1) * KIN * LD, &bars[it & 1], a, t_of((a.passes & 1) ? 0 : nsteps), g, b0);
         // chunk-start hidden state: zeros at the start of an epoch (LSTM:558), else h_seq[t0]
         for (int i = tid; i < H * M; i += NT) {
             const int j = i / M, s = i - j * M;
@@ -361,9 +350,10 @@ __global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a)
         __syncthreads();
 
         // ------------------------------------------------------------------ pass 1: hidden states
-        for (int i = 0; i < nsteps; ++i, ++it) {
+        for (int i = 0; i < ((a.passes & 1) ? nsteps : 0); ++i, ++it) {
             const int t = a.t0 + i;
-            issue_x(sm + oX + ((it + 1) & 1) * KIN * LD, &bars[(it + 1) & 1], a, t_of(i + 1), g, b0);
+            if (i + 1 < nsteps || (a.passes & 2))
+                issue_x(sm + oX + ((it + 1) & 1) * KIN * LD, &bars[(it + 1) & 1], a, t_of(i + 1), g, b0);
             const float* X = sm + oX + (it & 1) * KIN * LD;
             GTL(0, true);
             mbar_wait(&bars[it & 1], (it >> 1) & 1);
@@ -397,7 +387,7 @@ __global__ void __launch_bounds__(NTMAX / NU, 1) tbptt_chunk_kernel(ChunkArgs a)
         // ------------------------------------------------------------------ pass 2: recompute + backward
         for (int i = tid; i < H * LD; i += NT) DH[i] = 0.0f;
         // Hp currently holds h_{t1}; the first backward step needs h_{t1-1}: reload below like every other step
-        for (int i = 0; i < nsteps; ++i, ++it) {
+        for (int i = 0; i < ((a.passes & 2) ? nsteps : 0); ++i, ++it) {
             const int t = a.t1 - 1 - i;
             GTL(4, true);
             if (i + 1 < nsteps)
@@ -846,6 +836,7 @@ int cmarl_gru_setup(cmarl_ctx* ctx) {
         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru::SMEM_BYTES), "cudaFuncSetAttribute(tbptt_chunk_kernel)");
     SETK(1, false) SETK(1, true) SETK(2, false) SETK(2, true)
 #undef SETK
+    if (!e) e = cmarl_tc_gru_setup();
     return e;
 }
 
@@ -876,25 +867,43 @@ extern "C" int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params
     a.head.actions = actions; a.head.logp_old = logp_old; a.head.adv = adv; a.head.mask = mask; a.head.avail = avail;
     a.head.V = ctx->n_heads; a.head.A = c.n_actions;
     a.head.clip = (float)clip; a.head.ent_coef = (float)ent_coef; a.head.inv_groups = 1.0f / (float)c.n_agents;
+    a.passes = 3; a.flush = 5;
+    // Which kernels: the tcgen05 pair of tc_gru.cu (tensor cores on and a gate stash given: it is how the two kernels meet),
+    // else the fp32 FFMA kernel below.  CMARL_TBPTT = ffma | tc | tcfwd | tcbwd mixes them (cross-checks, measurements).
+    // (read at every call: a host-side getenv is noise next to a launch, and tests switch modes within one process)
+    const int mode_env = [] {
+        const char* v = getenv("CMARL_TBPTT");
+        if (!v) return -1;
+        return !strcmp(v, "ffma") ? 0 : !strcmp(v, "tc") ? 3 : !strcmp(v, "tcfwd") ? 1 : !strcmp(v, "tcbwd") ? 2 : -1;
+    }();
+    const int flush_env = [] { const char* v = getenv("CMARL_TC_GRU_FLUSH"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 64 ? n : 0; }();
+    if (flush_env) a.flush = flush_env;
+    int tc_which = (ctx->use_tc && stash) ? 3 : 0;
+    if (mode_env >= 0 && stash) tc_which = mode_env;
     const int units = c.n_agents * ceil_div(c.n_envs, gru::M);
-    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    int grid = units < ctx->sm_count ? units : ctx->sm_count;
     {
         KernelTimer kt(ctx, K_TBPTT, st);
-        // units per thread: 2 -> 256 threads (8 warps / SM, the default), 1 -> 512 threads (16 warps / SM).  Measured at
-        // 8 192 envs: 0.475 vs 0.533 ms per chunk -- twice the warps leave the gate GEMM at the same 7 900 cycles per
-        // step and slow the dx1/dh stage down (11.7 k vs 7.4 k cycles): the stages are not latency-bound.
-        static const int nu = [] { const char* v = getenv("CMARL_TBPTT_NU"); return (v && v[0] == '1') ? 1 : 2; }();
-        cudaError_t ce;
-        if (nu == 2) {
-            const dim3 block(gru::NTMAX / 2);
-            ce = stash ? cmarl_launch(ctx, gru::tbptt_chunk_kernel<2, true>, dim3(grid), block, gru::SMEM_BYTES, st, a)
-                       : cmarl_launch(ctx, gru::tbptt_chunk_kernel<2, false>, dim3(grid), block, gru::SMEM_BYTES, st, a);
-        } else {
-            const dim3 block(gru::NTMAX);
-            ce = stash ? cmarl_launch(ctx, gru::tbptt_chunk_kernel<1, true>, dim3(grid), block, gru::SMEM_BYTES, st, a)
-                       : cmarl_launch(ctx, gru::tbptt_chunk_kernel<1, false>, dim3(grid), block, gru::SMEM_BYTES, st, a);
+        if (tc_which & 1) { const int e = cmarl_tc_gru_launch(ctx, a, 1, nullptr, st); if (e) return e; }
+        if (tc_which != 3) {
+            // units per thread: 2 -> 256 threads (8 warps / SM, the default), 1 -> 512 threads (16 warps / SM).  Measured at
+            // 8 192 envs: 0.475 vs 0.533 ms per chunk -- twice the warps leave the gate GEMM at the same 7 900 cycles per
+            // step and slow the dx1/dh stage down (11.7 k vs 7.4 k cycles): the stages are not latency-bound.
+            static const int nu = [] { const char* v = getenv("CMARL_TBPTT_NU"); return (v && v[0] == '1') ? 1 : 2; }();
+            a.passes = tc_which == 1 ? 2 : tc_which == 2 ? 1 : 3;
+            cudaError_t ce;
+            if (nu == 2) {
+                const dim3 block(gru::NTMAX / 2);
+                ce = stash ? cmarl_launch(ctx, gru::tbptt_chunk_kernel<2, true>, dim3(grid), block, gru::SMEM_BYTES, st, a)
+                           : cmarl_launch(ctx, gru::tbptt_chunk_kernel<2, false>, dim3(grid), block, gru::SMEM_BYTES, st, a);
+            } else {
+                const dim3 block(gru::NTMAX);
+                ce = stash ? cmarl_launch(ctx, gru::tbptt_chunk_kernel<1, true>, dim3(grid), block, gru::SMEM_BYTES, st, a)
+                           : cmarl_launch(ctx, gru::tbptt_chunk_kernel<1, false>, dim3(grid), block, gru::SMEM_BYTES, st, a);
+            }
+            CMARL_CUDA(ce);
         }
-        CMARL_CUDA(ce);
+        if (tc_which & 2) { const int e = cmarl_tc_gru_launch(ctx, a, 2, &grid, st); if (e) return e; }
     }
     return cmarl_reduce_one_net(ctx, a.partials, grid, ctx->gru.count, nullptr, 0, 0, (float)c.n_agents, grads_out, st);
 }
