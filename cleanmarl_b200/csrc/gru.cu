@@ -867,7 +867,7 @@ extern "C" int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params
     a.head.actions = actions; a.head.logp_old = logp_old; a.head.adv = adv; a.head.mask = mask; a.head.avail = avail;
     a.head.V = ctx->n_heads; a.head.A = c.n_actions;
     a.head.clip = (float)clip; a.head.ent_coef = (float)ent_coef; a.head.inv_groups = 1.0f / (float)c.n_agents;
-    a.passes = 3; a.flush = 5;
+    a.passes = 3; a.flush = 32;      // weight-gradient accumulators leave TMEM at the end of every tile (<= 25 steps)
     // Which kernels: the tcgen05 pair of tc_gru.cu (tensor cores on and a gate stash given: it is how the two kernels meet),
     // else the fp32 FFMA kernel below.  CMARL_TBPTT = ffma | tc | tcfwd | tcbwd mixes them (cross-checks, measurements).
     // (read at every call: a host-side getenv is noise next to a launch, and tests switch modes within one process)

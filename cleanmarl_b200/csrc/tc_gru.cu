@@ -99,6 +99,10 @@ __device__ __forceinline__ void issue_ss(bool leader, uint32_t d, uint32_t a, ui
     }
 }
 
+// Row r of a thread's column: one CTA-uniform 64-bit base + a 32-bit per-thread offset (an element index < 2^32), so that
+// a batch of row loads keeps ONE address register alive instead of a 64-bit pair per row.
+__device__ __forceinline__ float ld_row(const float* base_u, uint32_t off, bool ok) { return ok ? __ldcg(base_u + off) : 0.0f; }
+
 __device__ __forceinline__ void st_split(uint8_t* hi_img, uint8_t* lo_img, int off, float v) {
     float h, l;
     tc::split_tf32(v, h, l);
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 hp[i] = 0.0f;       // zeros at the start of an epoch (LSTM:558), else h_seq[t0]
-                if (a.t0 > 0 && inb) hp[i] = __ldcg(a.h_seq + (((size_t)a.t0 * a.N + g) * H + 16 * hf + i) * a.B + b);
+                if (a.t0 > 0 && inb) hp[i] = __ldcg(a.h_seq + (((size_t)a.t0 * a.N + g) * H + 16 * hf) * a.B + b + (uint32_t)i * (uint32_t)a.B);
             }
             {
                 uint32_t hi[16], lo[16];
@@ -282,8 +286,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
                 const int t = a.t0 + i;
                 const bool tl_on = g_tcgru_tl_on && blockIdx.x == 0 && u == (int)blockIdx.x && i == 1 && tid == 0;
                 BTL(16);
-                float* slab = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B + b;
-                float* hrow = a.h_seq + (((size_t)(t + 1) * a.N + g) * H) * a.B + b;
+                // one 64-bit base per step and 32-bit row offsets (the obvious 64-bit products are ~10 instructions per access)
+                const size_t rs = (size_t)a.B;
+                // running pointers into this thread's rows of the stash (x1, r, z, n, Whn h) and of h_seq[t + 1]
+                float* q0 = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B + (size_t)(16 * hf) * rs + b;
+                float* q1 = q0 + (size_t)H * rs;
+                float* q2 = q1 + (size_t)H * rs;
+                float* q3 = q2 + (size_t)H * rs;
+                float* q4 = q3 + (size_t)H * rs;
+                float* q5 = a.h_seq + (((size_t)(t + 1) * a.N + g) * H) * a.B + (size_t)(16 * hf) * rs + b;
                 // ---- x1 = relu(fc1 + b1[g]) -> stash, split -> A columns -----------------------------------
                 float bv1[16];
 #pragma unroll
@@ -300,7 +311,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         const float x1 = fmaxf(__uint_as_float(v[k]) + bv1[k], 0.0f);
-                        if (inb) slab[(size_t)(16 * hf + k) * a.B] = x1;
+                        if (inb) *q0 = x1;
+                        q0 += rs;
                         float h, l;
                         tc::split_tf32(x1, h, l);
                         hi[k] = __float_as_uint(h); lo[k] = __float_as_uint(l);
@@ -338,13 +350,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
                         const float n = tanh_sfu(fmaf(r, ah, ai));
                         const float hn = fmaf(hp[8 * k + e] - n, z, n);
                         hp[8 * k + e] = hn;
-                        if (inb) {
-                            slab[(size_t)(1 * H + j) * a.B] = r;
-                            slab[(size_t)(2 * H + j) * a.B] = z;
-                            slab[(size_t)(3 * H + j) * a.B] = n;
-                            slab[(size_t)(4 * H + j) * a.B] = ah;
-                            hrow[(size_t)j * a.B] = hn;
-                        }
+                        if (inb) { *q1 = r; *q2 = z; *q3 = n; *q4 = ah; *q5 = hn; }
+                        q1 += rs; q2 += rs; q3 += rs; q4 += rs; q5 += rs;
                     }
                 }
                 if (i + 1 < nsteps) {
@@ -400,6 +407,122 @@ constexpr int TMEM_COLS = 512;
 enum { R_1 = 0, R_2, R_3, D_1, D_2, D_3, N_BARS };
 }  // namespace bwd
 
+// Weight-gradient accumulators of one tile -> the CTA's partial row.  Scratch = the gradient vector up to W2 in parameter
+// order (the A image, free between two tiles): zero, the lo row blocks, the hi row blocks added to them (fixed order), one
+// coalesced pass.  Every TMEM chunk of a thread is requested before the first one is used (chunk-by-chunk round trips made
+// the flush 24 k cycles).  NOT inlined: inside the step loop its register demand made the compiler park the prefetched gate
+// operands on the stack as they arrived; as a call, live registers are saved around it only when a tile ends.
+__device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, int q, int hf, int lane, int ct, int g,
+                                       float* part_out, bool flushed, bool ktl) {
+    using namespace bwd;
+    const GruLayout& L = a.L;
+        if (ktl && !flushed) g_tcgru_tl[12] = clock64();
+        float* S = reinterpret_cast<float*>(sm + oAs);
+        const int nflush = L.w2;
+        for (int i = ct; i < nflush; i += NCOMP) S[i] = 0.0f;
+        compute_bar();
+        const int gsel = q & 1;                      // rows of this quadrant: gate r / n (0) or z / hn (1)
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+            if ((q >= 2) == (ph == 0)) {             // warp-uniform: lo row blocks first
+                uint32_t vz[5][8], vn[3][8], v1[2][8];
+                // this thread's chunks: (r | z) rows: 8-column chunks 2 kk + hf < 9; (n | hn) rows: the two chunks of the
+                // wanted 32 columns (x1 columns for n rows, h columns for hn rows) + the ones chunk (half 0); dx1 rows: 2 kk + hf
+#pragma unroll
+                for (int kk = 0; kk < 5; ++kk)
+                    if (2 * kk + hf < NB / 8) tc::tmem_ld8(tl + cWrz + 8 * (2 * kk + hf), vz[kk]);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) tc::tmem_ld8(tl + cWn + 8 * (4 * gsel + 2 * kk + hf), vn[kk]);
+                if (hf == 0) tc::tmem_ld8(tl + cWn + 64, vn[2]);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) tc::tmem_ld8(tl + cW1 + 8 * (2 * kk + hf), v1[kk]);
+                tc::tmem_wait_ld();
+                {
+                    const int R = gsel * H + lane;   // gate row in Wih / Whh / bih / bhh
+#pragma unroll
+                    for (int kk = 0; kk < 5; ++kk) {
+                        const int c8 = 2 * kk + hf;
+                        if (c8 < 8) {
+                            float* p = S + (c8 < 4 ? L.wih : L.whh) + R * H + 8 * (c8 & 3);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) p[e] = ph == 0 ? __uint_as_float(vz[kk][e]) : p[e] + __uint_as_float(vz[kk][e]);
+                        } else if (c8 == 8) {
+                            const float x = __uint_as_float(vz[kk][0]);
+                            S[L.bih + R] = ph == 0 ? x : S[L.bih + R] + x;
+                            S[L.bhh + R] = ph == 0 ? x : S[L.bhh + R] + x;
+                        }
+                    }
+                }
+                {
+                    const int R = 2 * H + lane;      // n rows -> Wih_n, bih_n; hn rows -> Whh_n, bhh_n
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        float* p = S + (gsel == 0 ? L.wih : L.whh) + R * H + 8 * (2 * kk + hf);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) p[e] = ph == 0 ? __uint_as_float(vn[kk][e]) : p[e] + __uint_as_float(vn[kk][e]);
+                    }
+                    if (hf == 0) {
+                        const int o = (gsel == 0 ? L.bih : L.bhh) + R;
+                        const float x = __uint_as_float(vn[2][0]);
+                        S[o] = ph == 0 ? x : S[o] + x;
+                    }
+                }
+                if (lane < 16) {                     // dx1 rows (M = 64 accumulator: row r sits in lane (r / 16) * 32 + r % 16)
+                    const int j = gsel * 16 + lane;
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int c8 = 2 * kk + hf;
+                        if (c8 < 3) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int k = 8 * c8 + e;
+                                if (k < a.in_rows) {
+                                    float* p = S + L.w1 + j * L.in + k;
+                                    *p = ph == 0 ? __uint_as_float(v1[kk][e]) : *p + __uint_as_float(v1[kk][e]);
+                                }
+                            }
+                        } else {
+                            const float x = __uint_as_float(v1[kk][0]);
+                            S[L.b1 + j] = ph == 0 ? x : S[L.b1 + j] + x;
+                            if (a.fold_ids) {
+                                float* p = S + L.w1 + j * L.in + a.in_rows + g;
+                                *p = ph == 0 ? x : *p + x;
+                            }
+                        }
+                    }
+                }
+            }
+            compute_bar();
+        }
+        {
+            constexpr int NF = 28;                   // >= ceil(7 040 / 256)
+            float v[NF];
+#pragma unroll
+            for (int r = 0; r < NF; ++r) {
+                const int i = ct + NCOMP * r;
+                v[r] = i < nflush ? S[i] : 0.0f;
+            }
+            if (flushed) {
+                float o[NF];
+#pragma unroll
+                for (int r = 0; r < NF; ++r) {
+                    const int i = ct + NCOMP * r;
+                    o[r] = i < nflush ? part_out[i] : 0.0f;
+                }
+#pragma unroll
+                for (int r = 0; r < NF; ++r) v[r] += o[r];
+            }
+#pragma unroll
+            for (int r = 0; r < NF; ++r) {
+                const int i = ct + NCOMP * r;
+                if (i < nflush) part_out[i] = v[r];
+            }
+        }
+        if (ktl && !flushed) g_tcgru_tl[13] = clock64();
+        compute_bar();          // scratch reads done before the next step's gate gradients go to the A image
+}
+
+// (9 warps: the SM sub-partition that hosts three of them caps the kernel at 168 registers per thread)
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
     using namespace bwd;
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -427,7 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
         // B of the dx1 | dh GEMM: output n < 32: dx1 unit n = sum_k da_i[k] Wih[k][n] (k < 96: r, z, n gate rows);
         //                         output 32 + n: dh unit n = sum_k da_h[k] Whh[k][n] (A columns 0..63 and 96..127: r, z, hn)
         CMARL_STRIDED(i, 2 * H * 4 * H, NTHREADS) {
-            const int n = i / (4 * H), k = i - n * (4 * H);
+            const int k = i / (2 * H), n = i - k * (2 * H);      // n fastest: consecutive threads read consecutive floats
             float w = 0.0f;
             if (n < H) { if (k < G3) w = __ldcg(P + L.wih + k * H + n); }
             else if (k < 2 * H) w = __ldcg(P + L.whh + k * H + (n - H));
@@ -449,7 +572,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
     tc::tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t sbase = tc::smem_u32(sm);
-    const int flush_every = a.flush < 1 ? 1 : a.flush;
     if (ktl) g_tcgru_tl[11] = clock64();
 
     if (warp == 8) {
@@ -457,10 +579,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
         const bool leader = tc::elect_one();
         const uint32_t As = sbase + oAs, Bs_h = sbase + oBs, Bs_l = Bs_h + B_BYTES;
         uint32_t par = 0;
-        int cnt = 0;                                     // steps accumulated since the last flush
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             for (int i = 0; i < nsteps; ++i, par ^= 1) {
-                const uint32_t keep = cnt != 0 ? 1u : 0u;
+                const uint32_t keep = i != 0 ? 1u : 0u;      // the accumulators leave TMEM at the end of every tile
                 acquire(&bars[R_1], par);
                 issue_ss<128, NB>(leader, tmem + cWrz, As, Bs_h, Bs_l, keep);
                 if (leader) tc::mma_commit(&bars[D_1]);
@@ -471,8 +592,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                 acquire(&bars[R_3], par);
                 issue_ss<64, H>(leader, tmem + cW1, As, Bs_h, Bs_l, keep);
                 if (leader) tc::mma_commit(&bars[D_3]);
-                ++cnt;
-                if (cnt == flush_every || i + 1 == nsteps) cnt = 0;
             }
         }
         __syncwarp();
@@ -491,41 +610,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
         uint8_t* Bs_h = sm + oBs; uint8_t* Bs_l = Bs_h + B_BYTES;
         const int so = smaj(0, s);
         float* part_out = a.partials + (size_t)blockIdx.x * (L.count + CMARL_N_STATS);
-        bool flushed = false;
 
         float st[PolicyHead::NSTAT];
 #pragma unroll
         for (int k = 0; k < PolicyHead::NSTAT; ++k) st[k] = 0.0f;
 
-        // what the forward pass left for step t: x1, r, z, n, Whn h + bhn (stash) and h_t (h_seq), this thread's 16 units.
-        // Two groups: (h_t, n, z) feed the recomputation of h_{t+1} at the top of the step and are requested at the end of
-        // the step before; (r, Whn h, x1) are first used by the gate gradients and are requested at the top of the step,
-        // under the head.  (All 96 values requested one step ahead did not fit the 168 registers of a 288-thread CTA: the
-        // compiler parked them on the stack as they arrived, one L2 round trip after the other -- 16.5 k cycles per step.)
-        float sx1[16], sr[16], sz[16], sn[16], sg[16], shp[16];
-        auto load_a = [&](int t, int g, int b) {
-            const bool inb = b < a.B;
-            const float* slab = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B + b;
-            const float* hrow = a.h_seq + (((size_t)t * a.N + g) * H) * a.B + b;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int j = 16 * hf + i;
-                sz[i] = inb ? __ldcg(slab + (size_t)(2 * H + j) * a.B) : 0.0f;
-                sn[i] = inb ? __ldcg(slab + (size_t)(3 * H + j) * a.B) : 0.0f;
-                shp[i] = (inb && t > 0) ? __ldcg(hrow + (size_t)j * a.B) : 0.0f;
-            }
-        };
-        auto load_b = [&](int t, int g, int b) {
-            const bool inb = b < a.B;
-            const float* slab = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B + b;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int j = 16 * hf + i;
-                sx1[i] = inb ? __ldcg(slab + (size_t)j * a.B) : 0.0f;
-                sr[i] = inb ? __ldcg(slab + (size_t)(H + j) * a.B) : 0.0f;
-                sg[i] = inb ? __ldcg(slab + (size_t)(4 * H + j) * a.B) : 0.0f;
-            }
-        };
+        // What the forward pass left for step t: x1, r, z, n, Whn h + bhn (stash) and h_t (h_seq), this thread's 16 units.
+        // 9 warps cap the kernel at 168 registers per thread, and a step's 96 operands do not survive a step in them: every
+        // attempt to request them ahead ended with the compiler parking them on the stack as they arrived (LDG; STL pairs: one
+        // L2 round trip per value, 10-16 k cycles per step).  So nothing is carried: the head of a step runs one step AHEAD on
+        // short-lived copies of (h_t, n, z) and prefetches the step's other lines into L2; the gate-gradient stage loads its
+        // operands itself, four units at a time, one group ahead of the arithmetic.  Addresses: one CTA-uniform 64-bit base +
+        // a running 32-bit offset (64-bit products per row are ~10 instructions and a register pair each).
         float xr[NXO * 8];
         auto load_x = [&](int t, int g, int b) {
             const float* xp = a.x + (size_t)t * a.stride_t + (size_t)g * a.stride_g + b + (size_t)(8 * hf) * a.B;
@@ -540,259 +636,229 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                 }
         };
 
-        // accumulators -> the CTA's partial row.  Scratch = the gradient vector up to W2 in parameter order (A image, free
-        // between two steps): zero, the lo row blocks, the hi row blocks added to them (fixed order), one coalesced pass.
-        auto flush = [&](int g) {
-            if (ktl && !flushed) g_tcgru_tl[12] = clock64();
-            float* S = reinterpret_cast<float*>(sm + oAs);
-            const int nflush = L.w2;
-            for (int i = ct; i < nflush; i += NCOMP) S[i] = 0.0f;
-            compute_bar();
-            const int gsel = q & 1;                      // rows of this quadrant: gate r / n (0) or z / hn (1)
-#pragma unroll 1
-            for (int ph = 0; ph < 2; ++ph) {
-                if ((q >= 2) == (ph == 0)) {             // warp-uniform: lo row blocks first
-                    // (r | z) rows: every column is wanted
-                    {
-                        const int R = gsel * H + lane;   // gate row in Wih / Whh / bih / bhh
-#pragma unroll 1
-                        for (int c8 = hf; c8 < NB / 8; c8 += 2) {
-                            uint32_t v[8];
-                            tc::tmem_ld8(tl + cWrz + 8 * c8, v);
-                            tc::tmem_wait_ld();
-                            if (c8 < 8) {
-                                float* p = S + (c8 < 4 ? L.wih : L.whh) + R * H + 8 * (c8 & 3);
+
+
+        // h_{t+1} (recomputed exactly as the forward pass formed it) -> relu', logits -> head -> dlogits (head_stage), then
+        // dW2 / db2 (dw2_stage) of one step.  Both run one step AHEAD, in the shadow of the tensor rounds of the step before
+        // (the head does not depend on the backward recurrence): head_stage under the (r, z) round and the dx1 | dh GEMM,
+        // dw2_stage under the (n, hn) round.
+        float dz[NA], dzn[NA], rhn[16];                  // dlogits of this step; dlogits and relu(h') of the next one
+        uint32_t hcmask = 0u, hcmask_n = 0u;             // relu'(h_{t+1}) of this step / the next one
+        float tz[16], tn[16], th[16];                    // (z, n, h_t) of the step whose head runs next: requested at the top of
+                                                         // the iteration, consumed behind the gate-gradient stage
+        auto head_load = [&](int t, int g, int b) {
+            const bool inb = b < a.B, hb = inb && t > 0;
+            const size_t rs = (size_t)a.B;
+            const float* slab = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B;        // CTA-uniform
+            const float* hrow = a.h_seq + (((size_t)t * a.N + g) * H) * a.B;
+            // running pointers: one 64-bit multiply-add per row (per-row 64-bit products were ~6 instructions and a register pair each)
+            const float* pz = slab + (size_t)(2 * H + 16 * hf) * rs + b;
+            const float* pn = pz + (size_t)H * rs;
+            const float* ph = hrow + (size_t)(16 * hf) * rs + b;
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) p[e] = ph == 0 ? __uint_as_float(v[e]) : p[e] + __uint_as_float(v[e]);
-                            } else {
-                                const float x = __uint_as_float(v[0]);
-                                S[L.bih + R] = ph == 0 ? x : S[L.bih + R] + x;
-                                S[L.bhh + R] = ph == 0 ? x : S[L.bhh + R] + x;
-                            }
-                        }
-                    }
-                    // (n | hn) rows: n rows x (x1 columns, ones) -> Wih_n, bih_n; hn rows x (h columns, ones) -> Whh_n, bhh_n
-                    {
-                        const int R = 2 * H + lane;
-#pragma unroll 1
-                        for (int c8 = hf; c8 < NB / 8; c8 += 2) {
-                            const bool want = c8 == 8 || (gsel == 0 ? c8 < 4 : c8 >= 4);
-                            if (!want) continue;         // warp-uniform
-                            uint32_t v[8];
-                            tc::tmem_ld8(tl + cWn + 8 * c8, v);
-                            tc::tmem_wait_ld();
-                            if (c8 < 8) {
-                                float* p = S + (gsel == 0 ? L.wih : L.whh) + R * H + 8 * (c8 & 3);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) p[e] = ph == 0 ? __uint_as_float(v[e]) : p[e] + __uint_as_float(v[e]);
-                            } else {
-                                const int o = (gsel == 0 ? L.bih : L.bhh) + R;
-                                const float x = __uint_as_float(v[0]);
-                                S[o] = ph == 0 ? x : S[o] + x;
-                            }
-                        }
-                    }
-                    // dx1 rows (M = 64 accumulator: row r sits in lane (r / 16) * 32 + r % 16): W1, b1 (+ folded id column)
-                    {
-                        const int j = gsel * 16 + lane;
-#pragma unroll 1
-                        for (int c8 = hf; c8 < H / 8; c8 += 2) {
-                            uint32_t v[8];
-                            tc::tmem_ld8(tl + cW1 + 8 * c8, v);
-                            tc::tmem_wait_ld();
-                            if (lane < 16) {
-                                if (c8 < 3) {
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) {
-                                        const int k = 8 * c8 + e;
-                                        if (k < a.in_rows) {
-                                            float* p = S + L.w1 + j * L.in + k;
-                                            *p = ph == 0 ? __uint_as_float(v[e]) : *p + __uint_as_float(v[e]);
-                                        }
-                                    }
-                                } else {
-                                    const float x = __uint_as_float(v[0]);
-                                    S[L.b1 + j] = ph == 0 ? x : S[L.b1 + j] + x;
-                                    if (a.fold_ids) {
-                                        float* p = S + L.w1 + j * L.in + a.in_rows + g;
-                                        *p = ph == 0 ? x : *p + x;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                compute_bar();
+            for (int k = 0; k < 16; ++k, pz += rs, pn += rs, ph += rs) {
+                tz[k] = inb ? __ldcg(pz) : 0.0f;
+                tn[k] = inb ? __ldcg(pn) : 0.0f;
+                th[k] = hb ? __ldcg(ph) : 0.0f;
             }
+            // L2 prefetch, one row per LANE (a warp's 32 samples of a row are one 128-B line): the 48 rows (x1, r, Whn h) of
+            // this step, wanted by its gate-gradient stage one iteration from now, and the 48 rows (z, n, h) of the step below
+            // it, whose head runs then.  Three instructions per warp instead of 96.
             {
-                constexpr int NF = 28;                   // >= ceil(7 040 / 256)
-                float v[NF];
+                const int bw = b - lane;                     // first sample of this warp
+                if (bw < a.B) {
 #pragma unroll
-                for (int r = 0; r < NF; ++r) {
-                    const int i = ct + NCOMP * r;
-                    v[r] = i < nflush ? S[i] : 0.0f;
-                }
-                if (flushed) {
-                    float o[NF];
-#pragma unroll
-                    for (int r = 0; r < NF; ++r) {
-                        const int i = ct + NCOMP * r;
-                        o[r] = i < nflush ? part_out[i] : 0.0f;
+                    for (int m = 0; m < 3; ++m) {
+                        const int r = lane + 32 * m, arr = r >> 4, k = r & 15;   // r < 48: this step, arr 0..2 -> x1, r, Whn h
+                        const float* pf;
+                        if (r < 48) pf = slab + (size_t)((arr == 2 ? 4 : arr) * H + 16 * hf + k) * rs + bw;
+                        else if (arr - 3 < 2) pf = slab - (size_t)a.N * (5 * H) * rs + (size_t)((arr - 3 + 2) * H + 16 * hf + k) * rs + bw;
+                        else pf = hrow - (size_t)a.N * H * rs + (size_t)(16 * hf + k) * rs + bw;
+                        if (r < 48 || (t > a.t0 && (arr - 3 < 2 || t > 1))) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
                     }
-#pragma unroll
-                    for (int r = 0; r < NF; ++r) v[r] += o[r];
-                }
-#pragma unroll
-                for (int r = 0; r < NF; ++r) {
-                    const int i = ct + NCOMP * r;
-                    if (i < nflush) part_out[i] = v[r];
                 }
             }
-            if (ktl && !flushed) g_tcgru_tl[13] = clock64();
-            flushed = true;
-            compute_bar();          // scratch reads done before the next step's gate gradients go to the A image
         };
-
-        uint32_t par = 0;
-        int cnt = 0;
-        bool first = true, flush_due = false;
-        int g_prev = 0;
-        {
-            const int u0 = blockIdx.x;
-            if (u0 < units) {
-                const int g0 = u0 / tiles_b;
-                load_a(a.t1 - 1, g0, (u0 - g0 * tiles_b) * M + s);
-            }
-        }
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int g = u / tiles_b, b = (u - g * tiles_b) * M + s;
+        auto head_stage = [&](int t, int g, int b) {
             const bool inb = b < a.B;
-            float carry[16];                             // dL/dh_{t+1} carried down the chunk (this thread's units)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) carry[i] = 0.0f;
-
-            for (int i = 0; i < nsteps; ++i, par ^= 1) {
-                const int t = a.t1 - 1 - i;
-                const bool tl_on = g_tcgru_tl_on && blockIdx.x == 0 && u == (int)blockIdx.x && i == 1 && tid == 0;
-                BTL(0);
-                const PolicyHead::In hin = PolicyHead::load(a.head, t, g, b, a.N, a.B, inb && hf == 0);
-                load_b(t, g, b);
-                // ---- the previous step's last round has completed: images free, accumulators readable --------
-                if (!first) {
-                    acquire(&bars[D_3], par ^ 1);
-                    if (flush_due) flush(g_prev);
-                }
-                first = false;
-                BTL(3);
-                // ---- h_{t+1} (recomputed exactly as the forward pass formed it), logits, head --------------------
-                float rh[16];
-                uint32_t hcmask = 0u;                   // relu'(h_{t+1})
-                float z[NA], dz[NA];
+            const PolicyHead::In hin = PolicyHead::load(a.head, t, g, b, a.N, a.B, inb && hf == 0);
+            float z[NA];
+            {
+                hcmask_n = 0u;
 #pragma unroll
                 for (int c = 0; c < NA; ++c) z[c] = 0.0f;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const int j = 16 * hf + k;
-                    const float hc = fmaf(shp[k] - sn[k], sz[k], sn[k]);
-                    rh[k] = fmaxf(hc, 0.0f);
-                    hcmask |= (hc > 0.0f ? 1u : 0u) << k;
+                    const float hc = fmaf(th[k] - tn[k], tz[k], tn[k]);
+                    rhn[k] = fmaxf(hc, 0.0f);
+                    hcmask_n |= (hc > 0.0f ? 1u : 0u) << k;
                     const float4 w = *reinterpret_cast<const float4*>(fw2 + j * 8);
                     const float w4 = fw2[j * 8 + 4];
-                    z[0] = fmaf(w.x, rh[k], z[0]); z[1] = fmaf(w.y, rh[k], z[1]); z[2] = fmaf(w.z, rh[k], z[2]);
-                    z[3] = fmaf(w.w, rh[k], z[3]); z[4] = fmaf(w4, rh[k], z[4]);
+                    z[0] = fmaf(w.x, rhn[k], z[0]); z[1] = fmaf(w.y, rhn[k], z[1]); z[2] = fmaf(w.z, rhn[k], z[2]);
+                    z[3] = fmaf(w.w, rhn[k], z[3]); z[4] = fmaf(w4, rhn[k], z[4]);
                 }
-                if (hf == 1) {
+            }
+            if (hf == 1) {
 #pragma unroll
-                    for (int c = 0; c < NA; ++c) zx[c * M + s] = z[c];
-                }
-                compute_bar();
-                // B image: x1 -> rows 0..31, h_t -> rows 32..63 (this thread's units).  Half 1 stages while half 0 evaluates the head.
-                uint32_t x1mask = 0u;
-                auto stage_b = [&]() {
+                for (int c = 0; c < NA; ++c) zx[c * M + s] = z[c];
+            }
+            compute_bar();
+            if (hf == 0) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const int j = 16 * hf + k;
-                        st_split(Bs_h, Bs_l, smaj(j, 0) + so, sx1[k]);
-                        st_split(Bs_h, Bs_l, smaj(H + j, 0) + so, shp[k]);
-                        x1mask |= (sx1[k] > 0.0f ? 1u : 0u) << k;
-                    }
-                };
+                for (int c = 0; c < NA; ++c) z[c] = (z[c] + zx[c * M + s]) + fb2[c];
+                PolicyHead::compute(a.head, hin, z, true, dzn, st);
+#pragma unroll
+                for (int c = 0; c < NA; ++c) zx[c * M + s] = dzn[c];
+            }
+            compute_bar();
+            if (hf == 1) {
+#pragma unroll
+                for (int c = 0; c < NA; ++c) dzn[c] = zx[c * M + s];
+            }
+            __syncwarp();
+        };
+        auto dw2_stage = [&]() {        // dW2[c][j] += sum_s dz[s][c] relu(h')[s][j], db2
+#pragma unroll
+            for (int c = 0; c < NA; ++c) {
+                float p[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) p[k] = dzn[c] * rhn[k];
+                int idx;
+                warp_reduce_scatter<16>(p, lane, idx);
+                if ((lane & 1) == 0) dw2acc[c * H + 16 * hf + idx] += p[0];
                 if (hf == 0) {
+                    float d = dzn[c];
 #pragma unroll
-                    for (int c = 0; c < NA; ++c) z[c] = (z[c] + zx[c * M + s]) + fb2[c];
-                    PolicyHead::compute(a.head, hin, z, true, dz, st);
-#pragma unroll
-                    for (int c = 0; c < NA; ++c) zx[c * M + s] = dz[c];
-                } else {
-                    stage_b();
+                    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                    if (lane == 0) db2acc[c] += d;
                 }
-                compute_bar();
-                if (hf == 1) {
+            }
+            compute_bar();          // (zx is free for the next head_stage)
+        };
+        // what a step starts from: the head's results of the stage that ran ahead, and the gate operands
+        auto adopt_next = [&]() {
 #pragma unroll
-                    for (int c = 0; c < NA; ++c) dz[c] = zx[c * M + s];
-                } else {
-                    stage_b();
+            for (int c = 0; c < NA; ++c) dz[c] = dzn[c];
+            hcmask = hcmask_n;
+        };
+
+        // ONE flat loop over the steps of all tiles of this CTA, so that every stage exists once in the code (the kernel is
+        // ~10 k instructions; three copies of the head stage made 'no instruction' a top stall reason).  Iteration k works on
+        // step k ("cur") and prepares step k + 1 ("nxt") in the shadow of cur's tensor rounds; k = -1 only prepares step 0.
+        const int ntiles = (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total = ntiles * nsteps;
+        uint32_t par = 0;
+        bool flushed = false;
+        float carry[16];                                 // dL/dh_{t+1} carried down the chunk (this thread's units)
+        int ci = 0, cu = blockIdx.x;                    // cur: step index within its tile, tile
+        int ni = 0, nu = blockIdx.x;                    // nxt
+#pragma unroll 1
+        for (int k = -1; k < total; ++k) {
+            const bool active = k >= 0, has_next = k + 1 < total;
+            const int g = cu / tiles_b, b = (cu - g * tiles_b) * M + s, t = a.t1 - 1 - ci;
+            const int gn = nu / tiles_b, bn = (nu - gn * tiles_b) * M + s, tn = a.t1 - 1 - ni;
+            const bool inb = b < a.B;
+            const bool tl_on = g_tcgru_tl_on && blockIdx.x == 0 && k == 1 && tid == 0;
+            BTL(0);
+            uint32_t x1mask = 0u;
+            if (active) {
+                // ---- the previous step's last round has completed: the images are free (a tile's first step: waited at its end)
+                if (ci > 0) acquire(&bars[D_3], par ^ 1);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) carry[i] = 0.0f;
                 }
-                __syncwarp();
                 BTL(1);
-                // ---- dW2[c][j] += sum_s dz[s][c] relu(h')[s][j], db2 -------------------------------------------
+                // ---- four units at a time, operands one group ahead of the arithmetic: x1, h_t -> B image rows 0..31 / 32..63;
+                //      gate gradients da -> TMEM A columns, their (r, z) pair -> A image --------------------------------------
+                {
+                    const size_t rs = (size_t)a.B;
+                    const bool hb = inb && t > 0;
+                    // running pointers into the stash rows x1, r, z, n, Whn h and the h_seq row of this thread's units
+                    const float* p0 = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B + (size_t)(16 * hf) * rs + b;
+                    const float* p1 = p0 + (size_t)H * rs;
+                    const float* p2 = p1 + (size_t)H * rs;
+                    const float* p3 = p2 + (size_t)H * rs;
+                    const float* p4 = p3 + (size_t)H * rs;
+                    const float* p5 = a.h_seq + (((size_t)t * a.N + g) * H) * a.B + (size_t)(16 * hf) * rs + b;
+                    float nx1[4], nhp[4], nr[4], nz[4], nn[4], ng[4];
+                    auto load4 = [&]() {
 #pragma unroll
-                for (int c = 0; c < NA; ++c) {
-                    float p[16];
+                        for (int e = 0; e < 4; ++e, p0 += rs, p1 += rs, p2 += rs, p3 += rs, p4 += rs, p5 += rs) {
+                            nx1[e] = inb ? __ldcg(p0) : 0.0f;
+                            nr[e] = inb ? __ldcg(p1) : 0.0f;
+                            nz[e] = inb ? __ldcg(p2) : 0.0f;
+                            nn[e] = inb ? __ldcg(p3) : 0.0f;
+                            ng[e] = inb ? __ldcg(p4) : 0.0f;
+                            nhp[e] = hb ? __ldcg(p5) : 0.0f;
+                        }
+                    };
+                    load4();
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) p[k] = dz[c] * rh[k];
-                    int idx;
-                    warp_reduce_scatter<16>(p, lane, idx);
-                    if ((lane & 1) == 0) dw2acc[c * H + 16 * hf + idx] += p[0];
-                    if (hf == 0) {
-                        float d = dz[c];
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        float sx1[4], shp[4], sr[4], sz[4], sn[4], sg[4];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                        if (lane == 0) db2acc[c] += d;
+                        for (int e = 0; e < 4; ++e) { sx1[e] = nx1[e]; shp[e] = nhp[e]; sr[e] = nr[e]; sz[e] = nz[e]; sn[e] = nn[e]; sg[e] = ng[e]; }
+                        if (k4 < 3) load4();
+                        const int j0 = 16 * hf + 4 * k4;
+                        float dan[4], daz[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int kk = 4 * k4 + e, j = j0 + e;
+                            st_split(Bs_h, Bs_l, smaj(H + j, 0) + so, shp[e]);
+                            st_split(Bs_h, Bs_l, smaj(j, 0) + so, sx1[e]);
+                            x1mask |= (sx1[e] > 0.0f ? 1u : 0u) << kk;
+                            const float4 w = *reinterpret_cast<const float4*>(fw2 + j * 8);
+                            const float w4 = fw2[j * 8 + 4];
+                            float up = w.x * dz[0];
+                            up = fmaf(w.y, dz[1], up); up = fmaf(w.z, dz[2], up); up = fmaf(w.w, dz[3], up); up = fmaf(w4, dz[4], up);
+                            const float dh = carry[kk] + (((hcmask >> kk) & 1u) ? up : 0.0f);
+                            const float dn = dh * (1.0f - sz[e]);
+                            const float dzg = dh * (shp[e] - sn[e]);
+                            carry[kk] = dh * sz[e];
+                            dan[e] = dn * (1.0f - sn[e] * sn[e]);
+                            daz[e] = dzg * (sz[e] * (1.0f - sz[e]));
+                        }
+                        const uint32_t c0 = tl + 16 * hf + 4 * k4;
+                        uint32_t vh[4], vl[4];
+                        auto split4 = [&](auto&& f) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float h, l;
+                                tc::split_tf32(f(e), h, l);
+                                vh[e] = __float_as_uint(h); vl[e] = __float_as_uint(l);
+                            }
+                        };
+                        split4([&](int e) { return dan[e] * sg[e] * (sr[e] * (1.0f - sr[e])); });      // da_r
+                        tmem_st4(c0 + cDAh, vh); tmem_st4(c0 + cDAl, vl);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            *reinterpret_cast<uint32_t*>(As + smaj(j0 + e, 0) + so) = vh[e];
+                            *reinterpret_cast<uint32_t*>(As + smaj(2 * H + j0 + e, 0) + so) = vl[e];
+                        }
+                        split4([&](int e) { return daz[e]; });                                          // da_z
+                        tmem_st4(c0 + cDAh + H, vh); tmem_st4(c0 + cDAl + H, vl);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            *reinterpret_cast<uint32_t*>(As + smaj(H + j0 + e, 0) + so) = vh[e];
+                            *reinterpret_cast<uint32_t*>(As + smaj(3 * H + j0 + e, 0) + so) = vl[e];
+                        }
+                        split4([&](int e) { return dan[e]; });                                          // da_n
+                        tmem_st4(c0 + cDAh + 2 * H, vh); tmem_st4(c0 + cDAl + 2 * H, vl);
+                        split4([&](int e) { return dan[e] * sr[e]; });                                  // da_hn
+                        tmem_st4(c0 + cDAh + 3 * H, vh); tmem_st4(c0 + cDAl + 3 * H, vl);
                     }
                 }
                 BTL(2);
-                // ---- gate gradients (8 units at a time): da -> TMEM A columns, (r, z) -> A image ----------------
-#pragma unroll
-                for (int k8 = 0; k8 < 2; ++k8) {
-                    uint32_t rh_[8], rl_[8], zh_[8], zl_[8], nh_[8], nl_[8], hh_[8], hl_[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int k = 8 * k8 + e, j = 16 * hf + k;
-                        const float4 w = *reinterpret_cast<const float4*>(fw2 + j * 8);
-                        const float w4 = fw2[j * 8 + 4];
-                        float up = w.x * dz[0];
-                        up = fmaf(w.y, dz[1], up); up = fmaf(w.z, dz[2], up); up = fmaf(w.w, dz[3], up); up = fmaf(w4, dz[4], up);
-                        const float dh = carry[k] + (((hcmask >> k) & 1u) ? up : 0.0f);
-                        const float dn = dh * (1.0f - sz[k]);
-                        const float dzg = dh * (shp[k] - sn[k]);
-                        carry[k] = dh * sz[k];
-                        const float dan = dn * (1.0f - sn[k] * sn[k]);
-                        const float o_n = dan;
-                        const float o_h = dan * sr[k];
-                        const float o_r = dan * sg[k] * (sr[k] * (1.0f - sr[k]));
-                        const float o_z = dzg * (sz[k] * (1.0f - sz[k]));
-                        float h, l;
-                        tc::split_tf32(o_r, h, l); rh_[e] = __float_as_uint(h); rl_[e] = __float_as_uint(l);
-                        tc::split_tf32(o_z, h, l); zh_[e] = __float_as_uint(h); zl_[e] = __float_as_uint(l);
-                        tc::split_tf32(o_n, h, l); nh_[e] = __float_as_uint(h); nl_[e] = __float_as_uint(l);
-                        tc::split_tf32(o_h, h, l); hh_[e] = __float_as_uint(h); hl_[e] = __float_as_uint(l);
-                    }
-                    const uint32_t c0 = tl + 16 * hf + 8 * k8;
-                    tmem_st8(c0 + cDAh, rh_); tmem_st8(c0 + cDAh + H, zh_); tmem_st8(c0 + cDAh + 2 * H, nh_); tmem_st8(c0 + cDAh + 3 * H, hh_);
-                    tmem_st8(c0 + cDAl, rl_); tmem_st8(c0 + cDAl + H, zl_); tmem_st8(c0 + cDAl + 2 * H, nl_); tmem_st8(c0 + cDAl + 3 * H, hl_);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int j = 16 * hf + 8 * k8 + e;
-                        *reinterpret_cast<uint32_t*>(As + smaj(j, 0) + so) = rh_[e];
-                        *reinterpret_cast<uint32_t*>(As + smaj(H + j, 0) + so) = zh_[e];
-                        *reinterpret_cast<uint32_t*>(As + smaj(2 * H + j, 0) + so) = rl_[e];
-                        *reinterpret_cast<uint32_t*>(As + smaj(3 * H + j, 0) + so) = zl_[e];
-                    }
-                }
                 publish(&bars[R_1]);            // issuer: (r, z) weight-gradient round, then the dx1 | dh GEMM
-                BTL(4);
-                load_x(t, g, b);                // this step's input rows (dW1 round); latency under the first round
+                BTL(3);
+                load_x(t, g, b);                // this step's input rows (dW1 round)
+            }
+            // ---- the next step's head, under the (r, z) round and the dx1 | dh GEMM ------------------------------------
+            if (has_next) { head_load(tn, gn, bn); head_stage(tn, gn, bn); }
+            BTL(4);
+            if (active) {
                 // ---- (n, hn) pair: back from the TMEM A columns into the A image once the first round is done ----
                 acquire(&bars[D_1], par);
                 BTL(5);
@@ -804,16 +870,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                     tc::tmem_ld16(tl + cDAl + 3 * H + 16 * hf, v3);
                     tc::tmem_wait_ld();
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const int j = 16 * hf + k;
-                        *reinterpret_cast<uint32_t*>(As + smaj(j, 0) + so) = v0[k];
-                        *reinterpret_cast<uint32_t*>(As + smaj(H + j, 0) + so) = v1[k];
-                        *reinterpret_cast<uint32_t*>(As + smaj(2 * H + j, 0) + so) = v2[k];
-                        *reinterpret_cast<uint32_t*>(As + smaj(3 * H + j, 0) + so) = v3[k];
+                    for (int i = 0; i < 16; ++i) {
+                        const int j = 16 * hf + i;
+                        *reinterpret_cast<uint32_t*>(As + smaj(j, 0) + so) = v0[i];
+                        *reinterpret_cast<uint32_t*>(As + smaj(H + j, 0) + so) = v1[i];
+                        *reinterpret_cast<uint32_t*>(As + smaj(2 * H + j, 0) + so) = v2[i];
+                        *reinterpret_cast<uint32_t*>(As + smaj(3 * H + j, 0) + so) = v3[i];
                     }
                 }
                 publish(&bars[R_2]);
                 BTL(6);
+            }
+            // ---- the next step's dW2, under the (n, hn) round ----------------------------------------------------------
+            if (has_next) dw2_stage();
+            if (active) {
                 // ---- dx1 = (da_i Wih) . relu'(x1), dh carry += da_h Whh; dW1 round: A image <- dx1, B image <- x | 1 ----
                 acquire(&bars[D_2], par);       // second round and the dx1 | dh GEMM complete
                 BTL(7);
@@ -823,10 +893,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                     tc::tmem_ld16(tl + cDB + H + 16 * hf, vh);
                     tc::tmem_wait_ld();
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const int j = 16 * hf + k;
-                        carry[k] += __uint_as_float(vh[k]);
-                        const float dx1 = ((x1mask >> k) & 1u) ? __uint_as_float(vx[k]) : 0.0f;
+                    for (int i = 0; i < 16; ++i) {
+                        const int j = 16 * hf + i;
+                        carry[i] += __uint_as_float(vh[i]);
+                        const float dx1 = ((x1mask >> i) & 1u) ? __uint_as_float(vx[i]) : 0.0f;
                         float h, l;
                         tc::split_tf32(dx1, h, l);
                         *reinterpret_cast<float*>(As + smaj(j, 0) + so) = h;
@@ -847,25 +917,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                 }
                 publish(&bars[R_3]);
                 BTL(8);
-                // ---- next step's inputs: in flight under the last round -------------------------------------
-                g_prev = g;
-                ++cnt;
-                flush_due = cnt == flush_every || i + 1 == nsteps;
-                if (flush_due) cnt = 0;
-                if (i + 1 < nsteps) load_a(t - 1, g, b);
-                else if (u + (int)gridDim.x < units) {
-                    const int un = u + gridDim.x, gn = un / tiles_b;
-                    load_a(a.t1 - 1, gn, (un - gn * tiles_b) * M + s);
+                // ---- end of a tile: its weight-gradient sums leave TMEM before the next tile's operands are requested ------
+                if (ci + 1 == nsteps) {
+                    acquire(&bars[D_3], par);
+                    bwd_flush(sm, a, tl, q, hf, lane, ct, g, part_out, flushed, ktl);
+                    flushed = true;
                 }
-                BTL(9);
+                par ^= 1;
             }
+            if (has_next) adopt_next();
+            BTL(9);
+            ci = ni; cu = nu;
+            if (++ni == nsteps) { ni = 0; nu += gridDim.x; }
         }
         if (ktl) g_tcgru_tl[14] = clock64();
-        // ---- the last step's accumulators, then the rest of the partial row: W2 / b2 and the statistics ------------
-        if (!first) {
-            acquire(&bars[D_3], par ^ 1);
-            flush(g_prev);
-        }
+        // ---- the rest of the partial row: W2 / b2 and the statistics ------------------------------------------------
         {
             const float* w2all = reinterpret_cast<const float*>(sm + oDW2);
             for (int i = ct; i < NA * H; i += NCOMP)

@@ -28,6 +28,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  : "memory");
 }
 
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+                 : "memory");
+}
+
 // byte offset of element (feature row r, sample s) in a sample-major image
 __device__ __forceinline__ int smaj(int r, int s) { return (r >> 3) * SBO_S + (r & 7) * 16 + (s >> 2) * LBO_S + (s & 3) * 4; }
 // byte offset of element (row n, k) in a K-major weight image with KTOT columns
