@@ -346,7 +346,10 @@ extern "C" size_t cmarl_workspace_bytes(const cmarl_ctx* ctx) {
     // (the recurrent chunk kernel, gru.cu, launches at most one CTA per SM: covered as well)
     const size_t a = (size_t)2 * ctx->sm_count * (ctx->actor.count + CMARL_N_STATS);
     const size_t c = (size_t)2 * ctx->sm_count * (ctx->critic.count + CMARL_N_STATS);
-    return (a + c) * sizeof(float);
+    // recurrent actor on the tensor cores (tc_gru.cu): the forward kernel's partial rows (dW2 | db2 | statistics, one per
+    // forward CTA, up to two per SM) live in the second half of the actor block; its dlogits [T][N][8][B] behind both blocks
+    const size_t dl = ctx->cfg.actor_recurrent ? (size_t)ctx->cfg.n_steps * ctx->cfg.n_agents * 8 * ctx->cfg.n_envs : 0;
+    return (a + c + dl) * sizeof(float);
 }
 
 extern "C" int cmarl_critic_values(cmarl_ctx* ctx, const float* critic_params, const float* state, const float* obs,

@@ -152,7 +152,12 @@ struct GruChunkArgs {
     float* partials;          // [grid][P + 8]
     PolicyHeadArgs head;
     int passes;               // FFMA kernel: bit 0 = pass 1 (hidden states, stash), bit 1 = pass 2 (head + backward; alone it needs the stash)
-    int flush;                // tcgen05 backward kernel: steps whose weight-gradient products accumulate in TMEM between two flushes
+    int flush;                // (unused: the tcgen05 backward kernel flushes its TMEM accumulators at the end of every tile)
+    // tcgen05 pair (tc_gru.cu): the forward kernel evaluates the head as well -- dlogits of every step go to `dlogits`
+    // [T][N][8][B], its dW2 / db2 / statistics to one row of 176 floats per forward CTA in `fwd_partials`
+    float* dlogits;
+    float* fwd_partials;
+    int grid_fwd;
 };
 
 struct ValueHeadArgs {

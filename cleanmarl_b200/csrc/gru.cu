@@ -879,7 +879,17 @@ extern "C" int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params
     const int flush_env = [] { const char* v = getenv("CMARL_TC_GRU_FLUSH"); const int n = v ? atoi(v) : 0; return n >= 1 && n <= 64 ? n : 0; }();
     if (flush_env) a.flush = flush_env;
     int tc_which = (ctx->use_tc && stash) ? 3 : 0;
-    if (mode_env >= 0 && stash) tc_which = mode_env;
+    if (mode_env >= 0 && stash) tc_which = mode_env == 2 ? 3 : mode_env;     // (the tcgen05 backward needs the tcgen05 forward's dlogits)
+    {
+        // workspace map of the tcgen05 pair (cmarl_workspace_bytes): [0, sm_count) actor rows: backward partials; second half
+        // of the actor block: forward partials; behind the actor and critic blocks: dlogits
+        const size_t arow = (size_t)ctx->actor.count + CMARL_N_STATS, crow = (size_t)ctx->critic.count + CMARL_N_STATS;
+        float* ws = reinterpret_cast<float*>(workspace);
+        a.fwd_partials = ws + (size_t)ctx->sm_count * arow;
+        a.dlogits = ws + (size_t)2 * ctx->sm_count * (arow + crow);
+        const int units_tc = c.n_agents * ceil_div(c.n_envs, 128);
+        a.grid_fwd = units_tc < 2 * ctx->sm_count ? units_tc : 2 * ctx->sm_count;
+    }
     const int units = c.n_agents * ceil_div(c.n_envs, gru::M);
     int grid = units < ctx->sm_count ? units : ctx->sm_count;
     {

@@ -128,7 +128,12 @@ constexpr int oWhh = oW1 + 2 * szW1;            // Whh hi | lo  [96][32]   rows 
 constexpr int oWih = oWhh + 2 * szWg;           // Wih hi | lo  [96][32]
 constexpr int oB1 = oWih + 2 * szWg;            // f32 [4][32]  b1 (+ folded id column) per agent
 constexpr int oBg = oB1 + 4 * H * 4;            // f32 [32][4]  bir + bhr, biz + bhz, bin, bhn
-constexpr int oX = oBg + H * 4 * 4;             // X hi | lo    [128][24]  K-major image (A of fc1)
+constexpr int oW2T = oBg + H * 4 * 4;           // f32 [32][8]  output layer, unit-major
+constexpr int oB2 = oW2T + H * 8 * 4;           // f32 [8]
+constexpr int oDW2 = oB2 + 32;                  // f32 [4 quadrants][8][32] + [4][8]: dW2 / db2 partial sums
+constexpr int oRed = oDW2 + (4 * 8 * H + 32) * 4;
+constexpr int oZx = oRed + 256;                 // f32 [5][128]: partial logits half 1 -> half 0, then dlogits half 0 -> half 1
+constexpr int oX = ((oZx + NA * M * 4 + 127) / 128) * 128;     // X hi | lo    [128][24]  K-major image (A of fc1)
 constexpr int szX = M * K1P * 4;                // 12 288
 constexpr int SMEM = oX + 2 * szX;
 static_assert(oX % 128 == 0 && SMEM <= 113 * 1024, "two CTAs per SM");
@@ -156,11 +161,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
         tc::fence_mbar_init();
     }
     if (warp == 8) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    for (int i = tid; i < 4 * 8 * H + 32; i += NTHREADS) reinterpret_cast<float*>(sm + oDW2)[i] = 0.0f;
     pdl_wait_then_trigger();
     // ---- weights -> K-major hi | lo images ---------------------------------------------------------
     {
         const float* P = a.params;
         const int O = L.in;
+        CMARL_STRIDED(i, H * 8, NTHREADS) {
+            const int j = i / 8, c = i - j * 8;
+            reinterpret_cast<float*>(sm + oW2T)[i] = (c < NA) ? __ldcg(P + L.w2 + c * H + j) : 0.0f;
+        }
+        if (tid < 8) reinterpret_cast<float*>(sm + oB2)[tid] = (tid < NA) ? __ldcg(P + L.b2 + tid) : 0.0f;
         CMARL_STRIDED(i, H * K1P, NTHREADS) {
             const int j = i / K1P, k = i - j * K1P;
             const float w = k < a.in_rows ? __ldcg(P + L.w1 + j * O + k) : 0.0f;
@@ -221,6 +232,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
         const float* fb1 = reinterpret_cast<const float*>(sm + oB1);
         const float4* fbg = reinterpret_cast<const float4*>(sm + oBg);
         const int xoff = (s >> 3) * (K1P / 4) * LBO_K + (s & 7) * 16;     // this sample's row in the K-major X image
+        const float* fw2 = reinterpret_cast<const float*>(sm + oW2T);
+        const float* fb2 = reinterpret_cast<const float*>(sm + oB2);
+        float* zx = reinterpret_cast<float*>(sm + oZx);
+        float* dw2acc = reinterpret_cast<float*>(sm + oDW2) + q * 8 * H;
+        float* db2acc = reinterpret_cast<float*>(sm + oDW2) + 4 * 8 * H + q * 8;
+        const int ct = warp * 32 + lane;
+        float st[PolicyHead::NSTAT];
+#pragma unroll
+        for (int k = 0; k < PolicyHead::NSTAT; ++k) st[k] = 0.0f;
 
         float xr[NXO * 8];
         auto load_x = [&](int t, int g, int b) {
@@ -367,7 +387,85 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
                     publish(&bars[R_H]);
                 }
                 BTL(21);
+                // ---- the head of this step (LSTM:574-593, 628-638), behind the hand-off of h_{t+1} so that the next step's
+                //      MMAs run under it: logits = W2 relu(h') + b2 -> loss terms, statistics, dlogits (-> global, for the
+                //      backward kernel), dW2 / db2 ------------------------------------------------------------------------
+                {
+                    const PolicyHead::In hin = PolicyHead::load(a.head, t, g, b, a.N, a.B, inb && hf == 0);
+                    float rh[16], z[NA], dz[NA];
+#pragma unroll
+                    for (int c = 0; c < NA; ++c) z[c] = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int j = 16 * hf + k;
+                        rh[k] = fmaxf(hp[k], 0.0f);
+                        const float4 w = *reinterpret_cast<const float4*>(fw2 + j * 8);
+                        const float w4 = fw2[j * 8 + 4];
+                        z[0] = fmaf(w.x, rh[k], z[0]); z[1] = fmaf(w.y, rh[k], z[1]); z[2] = fmaf(w.z, rh[k], z[2]);
+                        z[3] = fmaf(w.w, rh[k], z[3]); z[4] = fmaf(w4, rh[k], z[4]);
+                    }
+                    if (hf == 1) {
+#pragma unroll
+                        for (int c = 0; c < NA; ++c) zx[c * M + s] = z[c];
+                    }
+                    compute_bar();
+                    if (hf == 0) {
+#pragma unroll
+                        for (int c = 0; c < NA; ++c) z[c] = (z[c] + zx[c * M + s]) + fb2[c];
+                        PolicyHead::compute(a.head, hin, z, true, dz, st);
+                        float* dzp = a.dlogits + ((size_t)t * a.N + g) * 8 * a.B + b;
+#pragma unroll
+                        for (int c = 0; c < NA; ++c) {
+                            zx[c * M + s] = dz[c];
+                            if (inb) dzp[(size_t)c * a.B] = dz[c];
+                        }
+                    }
+                    compute_bar();
+                    if (hf == 1) {
+#pragma unroll
+                        for (int c = 0; c < NA; ++c) dz[c] = zx[c * M + s];
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < NA; ++c) {
+                        float p[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) p[k] = dz[c] * rh[k];
+                        int idx;
+                        warp_reduce_scatter<16>(p, lane, idx);
+                        if ((lane & 1) == 0) dw2acc[c * H + 16 * hf + idx] += p[0];
+                        if (hf == 0) {
+                            float d = dz[c];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                            if (lane == 0) db2acc[c] += d;
+                        }
+                    }
+                }
             }
+        }
+        // ---- this CTA's row of fwd_partials: dW2 (160) | db2 (5) | statistics (8) ------------------------------------
+        {
+            compute_bar();
+            float* out = a.fwd_partials + (size_t)blockIdx.x * (NA * H + NA + CMARL_N_STATS);
+            const float* w2all = reinterpret_cast<const float*>(sm + oDW2);
+            for (int i = ct; i < NA * H; i += NCOMP)
+                out[i] = ((w2all[i] + w2all[8 * H + i]) + w2all[2 * 8 * H + i]) + w2all[3 * 8 * H + i];
+            if (ct < NA) {
+                const float* b2all = w2all + 4 * 8 * H;
+                out[NA * H + ct] = ((b2all[ct] + b2all[8 + ct]) + b2all[16 + ct]) + b2all[24 + ct];
+            }
+            float* red = reinterpret_cast<float*>(sm + oRed);
+#pragma unroll
+            for (int k = 0; k < PolicyHead::NSTAT; ++k) {
+                const float v = warp_sum_f(st[k]);              // half-1 warps carry zeros
+                compute_bar();
+                if (lane == 0) red[warp] = v;
+                compute_bar();
+                if (ct == 0) out[NA * H + NA + k] = ((red[0] + red[1]) + red[2]) + red[3];
+            }
+            if (ct == 0)
+                for (int k = PolicyHead::NSTAT; k < CMARL_N_STATS; ++k) out[NA * H + NA + k] = 0.0f;
         }
     }
     tc::tcgen05_fence_before();
@@ -538,7 +636,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
 
     // ---- set-up that touches no global memory --------------------------------------------------------
     for (int i = tid * 16; i < A_BYTES + 2 * B_BYTES; i += NTHREADS * 16) *reinterpret_cast<uint4*>(sm + oAs + i) = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 4 * 8 * H + 32; i += NTHREADS) reinterpret_cast<float*>(sm + oDW2)[i] = 0.0f;
     if (tid == 0) {
         for (int i = 0; i < N_BARS; ++i) tc::mbar_init(&bars[i], i < D_1 ? NCOMP : 1);
         tc::fence_mbar_init();
@@ -602,18 +699,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
         const int ct = warp * 32 + lane;                 // 0..255
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         const float* fw2 = reinterpret_cast<const float*>(sm + oW2T);
-        const float* fb2 = reinterpret_cast<const float*>(sm + oB2);
-        float* zx = reinterpret_cast<float*>(sm + oZx);
-        float* dw2acc = reinterpret_cast<float*>(sm + oDW2) + q * 8 * H;
-        float* db2acc = reinterpret_cast<float*>(sm + oDW2) + 4 * 8 * H + q * 8;
         uint8_t* As = sm + oAs;
         uint8_t* Bs_h = sm + oBs; uint8_t* Bs_l = Bs_h + B_BYTES;
         const int so = smaj(0, s);
         float* part_out = a.partials + (size_t)blockIdx.x * (L.count + CMARL_N_STATS);
-
-        float st[PolicyHead::NSTAT];
-#pragma unroll
-        for (int k = 0; k < PolicyHead::NSTAT; ++k) st[k] = 0.0f;
 
         // What the forward pass left for step t: x1, r, z, n, Whn h + bhn (stash) and h_t (h_seq), this thread's 16 units.
         // 9 warps cap the kernel at 168 registers per thread, and a step's 96 operands do not survive a step in them: every
@@ -638,126 +727,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
 
 
 
-        // h_{t+1} (recomputed exactly as the forward pass formed it) -> relu', logits -> head -> dlogits (head_stage), then
-        // dW2 / db2 (dw2_stage) of one step.  Both run one step AHEAD, in the shadow of the tensor rounds of the step before
-        // (the head does not depend on the backward recurrence): head_stage under the (r, z) round and the dx1 | dh GEMM,
-        // dw2_stage under the (n, hn) round.
-        float dz[NA], dzn[NA], rhn[16];                  // dlogits of this step; dlogits and relu(h') of the next one
-        uint32_t hcmask = 0u, hcmask_n = 0u;             // relu'(h_{t+1}) of this step / the next one
-        float tz[16], tn[16], th[16];                    // (z, n, h_t) of the step whose head runs next: requested at the top of
-                                                         // the iteration, consumed behind the gate-gradient stage
-        auto head_load = [&](int t, int g, int b) {
-            const bool inb = b < a.B, hb = inb && t > 0;
-            const size_t rs = (size_t)a.B;
-            const float* slab = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B;        // CTA-uniform
-            const float* hrow = a.h_seq + (((size_t)t * a.N + g) * H) * a.B;
-            // running pointers: one 64-bit multiply-add per row (per-row 64-bit products were ~6 instructions and a register pair each)
-            const float* pz = slab + (size_t)(2 * H + 16 * hf) * rs + b;
-            const float* pn = pz + (size_t)H * rs;
-            const float* ph = hrow + (size_t)(16 * hf) * rs + b;
-#pragma unroll
-            for (int k = 0; k < 16; ++k, pz += rs, pn += rs, ph += rs) {
-                tz[k] = inb ? __ldcg(pz) : 0.0f;
-                tn[k] = inb ? __ldcg(pn) : 0.0f;
-                th[k] = hb ? __ldcg(ph) : 0.0f;
-            }
-            // L2 prefetch, one row per LANE (a warp's 32 samples of a row are one 128-B line): the 48 rows (x1, r, Whn h) of
-            // this step, wanted by its gate-gradient stage one iteration from now, and the 48 rows (z, n, h) of the step below
-            // it, whose head runs then.  Three instructions per warp instead of 96.
-            {
-                const int bw = b - lane;                     // first sample of this warp
-                if (bw < a.B) {
-#pragma unroll
-                    for (int m = 0; m < 3; ++m) {
-                        const int r = lane + 32 * m, arr = r >> 4, k = r & 15;   // r < 48: this step, arr 0..2 -> x1, r, Whn h
-                        const float* pf;
-                        if (r < 48) pf = slab + (size_t)((arr == 2 ? 4 : arr) * H + 16 * hf + k) * rs + bw;
-                        else if (arr - 3 < 2) pf = slab - (size_t)a.N * (5 * H) * rs + (size_t)((arr - 3 + 2) * H + 16 * hf + k) * rs + bw;
-                        else pf = hrow - (size_t)a.N * H * rs + (size_t)(16 * hf + k) * rs + bw;
-                        if (r < 48 || (t > a.t0 && (arr - 3 < 2 || t > 1))) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-                    }
-                }
-            }
-        };
-        auto head_stage = [&](int t, int g, int b) {
-            const bool inb = b < a.B;
-            const PolicyHead::In hin = PolicyHead::load(a.head, t, g, b, a.N, a.B, inb && hf == 0);
-            float z[NA];
-            {
-                hcmask_n = 0u;
-#pragma unroll
-                for (int c = 0; c < NA; ++c) z[c] = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int j = 16 * hf + k;
-                    const float hc = fmaf(th[k] - tn[k], tz[k], tn[k]);
-                    rhn[k] = fmaxf(hc, 0.0f);
-                    hcmask_n |= (hc > 0.0f ? 1u : 0u) << k;
-                    const float4 w = *reinterpret_cast<const float4*>(fw2 + j * 8);
-                    const float w4 = fw2[j * 8 + 4];
-                    z[0] = fmaf(w.x, rhn[k], z[0]); z[1] = fmaf(w.y, rhn[k], z[1]); z[2] = fmaf(w.z, rhn[k], z[2]);
-                    z[3] = fmaf(w.w, rhn[k], z[3]); z[4] = fmaf(w4, rhn[k], z[4]);
-                }
-            }
-            if (hf == 1) {
-#pragma unroll
-                for (int c = 0; c < NA; ++c) zx[c * M + s] = z[c];
-            }
-            compute_bar();
-            if (hf == 0) {
-#pragma unroll
-                for (int c = 0; c < NA; ++c) z[c] = (z[c] + zx[c * M + s]) + fb2[c];
-                PolicyHead::compute(a.head, hin, z, true, dzn, st);
-#pragma unroll
-                for (int c = 0; c < NA; ++c) zx[c * M + s] = dzn[c];
-            }
-            compute_bar();
-            if (hf == 1) {
-#pragma unroll
-                for (int c = 0; c < NA; ++c) dzn[c] = zx[c * M + s];
-            }
-            __syncwarp();
-        };
-        auto dw2_stage = [&]() {        // dW2[c][j] += sum_s dz[s][c] relu(h')[s][j], db2
-#pragma unroll
-            for (int c = 0; c < NA; ++c) {
-                float p[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) p[k] = dzn[c] * rhn[k];
-                int idx;
-                warp_reduce_scatter<16>(p, lane, idx);
-                if ((lane & 1) == 0) dw2acc[c * H + 16 * hf + idx] += p[0];
-                if (hf == 0) {
-                    float d = dzn[c];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                    if (lane == 0) db2acc[c] += d;
-                }
-            }
-            compute_bar();          // (zx is free for the next head_stage)
-        };
-        // what a step starts from: the head's results of the stage that ran ahead, and the gate operands
-        auto adopt_next = [&]() {
-#pragma unroll
-            for (int c = 0; c < NA; ++c) dz[c] = dzn[c];
-            hcmask = hcmask_n;
-        };
-
-        // ONE flat loop over the steps of all tiles of this CTA, so that every stage exists once in the code (the kernel is
-        // ~10 k instructions; three copies of the head stage made 'no instruction' a top stall reason).  Iteration k works on
-        // step k ("cur") and prepares step k + 1 ("nxt") in the shadow of cur's tensor rounds; k = -1 only prepares step 0.
+        // ONE flat loop over the steps of all tiles of this CTA (every stage exists once in the code).  The head of every step
+        // (logits, loss terms, dlogits, dW2) was evaluated by the forward kernel: this one reads 5 dlogits per sample.
         const int ntiles = (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total = ntiles * nsteps;
         uint32_t par = 0;
         bool flushed = false;
         float carry[16];                                 // dL/dh_{t+1} carried down the chunk (this thread's units)
         int ci = 0, cu = blockIdx.x;                    // cur: step index within its tile, tile
-        int ni = 0, nu = blockIdx.x;                    // nxt
 #pragma unroll 1
-        for (int k = -1; k < total; ++k) {
-            const bool active = k >= 0, has_next = k + 1 < total;
+        for (int k = 0; k < total; ++k) {
+            const bool active = true;
             const int g = cu / tiles_b, b = (cu - g * tiles_b) * M + s, t = a.t1 - 1 - ci;
-            const int gn = nu / tiles_b, bn = (nu - gn * tiles_b) * M + s, tn = a.t1 - 1 - ni;
             const bool inb = b < a.B;
             const bool tl_on = g_tcgru_tl_on && blockIdx.x == 0 && k == 1 && tid == 0;
             BTL(0);
@@ -782,6 +763,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                     const float* p3 = p2 + (size_t)H * rs;
                     const float* p4 = p3 + (size_t)H * rs;
                     const float* p5 = a.h_seq + (((size_t)t * a.N + g) * H) * a.B + (size_t)(16 * hf) * rs + b;
+                    float dz[NA];
+                    {
+                        const float* dzp = a.dlogits + ((size_t)t * a.N + g) * 8 * a.B + b;
+#pragma unroll
+                        for (int c = 0; c < NA; ++c, dzp += rs) dz[c] = inb ? __ldcg(dzp) : 0.0f;
+                    }
                     float nx1[4], nhp[4], nr[4], nz[4], nn[4], ng[4];
                     auto load4 = [&]() {
 #pragma unroll
@@ -813,7 +800,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                             const float w4 = fw2[j * 8 + 4];
                             float up = w.x * dz[0];
                             up = fmaf(w.y, dz[1], up); up = fmaf(w.z, dz[2], up); up = fmaf(w.w, dz[3], up); up = fmaf(w4, dz[4], up);
-                            const float dh = carry[kk] + (((hcmask >> kk) & 1u) ? up : 0.0f);
+                            const float hc = fmaf(shp[e] - sn[e], sz[e], sn[e]);      // h_{t+1}, exactly as the forward pass formed it
+                            const float dh = carry[kk] + (hc > 0.0f ? up : 0.0f);
                             const float dn = dh * (1.0f - sz[e]);
                             const float dzg = dh * (shp[e] - sn[e]);
                             carry[kk] = dh * sz[e];
@@ -855,8 +843,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                 BTL(3);
                 load_x(t, g, b);                // this step's input rows (dW1 round)
             }
-            // ---- the next step's head, under the (r, z) round and the dx1 | dh GEMM ------------------------------------
-            if (has_next) { head_load(tn, gn, bn); head_stage(tn, gn, bn); }
             BTL(4);
             if (active) {
                 // ---- (n, hn) pair: back from the TMEM A columns into the A image once the first round is done ----
@@ -881,8 +867,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                 publish(&bars[R_2]);
                 BTL(6);
             }
-            // ---- the next step's dW2, under the (n, hn) round ----------------------------------------------------------
-            if (has_next) dw2_stage();
             if (active) {
                 // ---- dx1 = (da_i Wih) . relu'(x1), dh carry += da_h Whh; dW1 round: A image <- dx1, B image <- x | 1 ----
                 acquire(&bars[D_2], par);       // second round and the dx1 | dh GEMM complete
@@ -925,32 +909,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                 }
                 par ^= 1;
             }
-            if (has_next) adopt_next();
             BTL(9);
-            ci = ni; cu = nu;
-            if (++ni == nsteps) { ni = 0; nu += gridDim.x; }
+            if (++ci == nsteps) { ci = 0; cu += gridDim.x; }
         }
         if (ktl) g_tcgru_tl[14] = clock64();
-        // ---- the rest of the partial row: W2 / b2 and the statistics ------------------------------------------------
+        // ---- the rest of the partial row: W2 / b2 / statistics = this CTA's share of the forward kernel's rows (fixed order) --
         {
-            const float* w2all = reinterpret_cast<const float*>(sm + oDW2);
-            for (int i = ct; i < NA * H; i += NCOMP)
-                part_out[L.w2 + i] = ((w2all[i] + w2all[8 * H + i]) + w2all[2 * 8 * H + i]) + w2all[3 * 8 * H + i];
-            if (ct < NA) {
-                const float* b2all = w2all + 4 * 8 * H;
-                part_out[L.b2 + ct] = ((b2all[ct] + b2all[8 + ct]) + b2all[16 + ct]) + b2all[24 + ct];
+            constexpr int NFW = NA * H + NA + CMARL_N_STATS;        // 173: contiguous behind bhh in the parameter order
+            for (int i = ct; i < NFW; i += NCOMP) {
+                float v = 0.0f;
+                for (int r = blockIdx.x; r < a.grid_fwd; r += gridDim.x) v += __ldcg(a.fwd_partials + (size_t)r * NFW + i);
+                part_out[L.w2 + i] = v;
             }
-            float* red = reinterpret_cast<float*>(sm + oRed);
-#pragma unroll
-            for (int k = 0; k < PolicyHead::NSTAT; ++k) {
-                const float v = warp_sum_f(st[k]);              // half-1 warps carry zeros
-                compute_bar();
-                if (lane == 0) red[warp] = v;
-                compute_bar();
-                if (ct == 0) part_out[L.count + k] = ((red[0] + red[1]) + red[2]) + red[3];
-            }
-            if (ct == 0)
-                for (int k = PolicyHead::NSTAT; k < CMARL_N_STATS; ++k) part_out[L.count + k] = 0.0f;
         }
     }
     if (ktl) g_tcgru_tl[15] = clock64();
@@ -975,7 +945,7 @@ int cmarl_tc_gru_launch(cmarl_ctx* ctx, const chain::GruChunkArgs& a, int which,
     const int units = a.N * ceil_div(a.B, tctile::M);
     if (units >= (1 << 24)) { cmarl_set_error("tc_gru: too many tiles"); return -1; }
     if (which & 1) {
-        const int grid = units < 2 * ctx->sm_count ? units : 2 * ctx->sm_count;
+        const int grid = a.grid_fwd;
         CMARL_CUDA(cmarl_launch(ctx, tcgru::tc_gru_fwd_kernel, dim3(grid), dim3(tctile::NTHREADS), tcgru::fwd::SMEM, st, a));
     }
     if (which & 2) {

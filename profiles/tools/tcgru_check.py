@@ -53,7 +53,7 @@ def run(mode, eng, flat, d, adv_d, chunks, use_mask=True, time_it=False):
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     tb = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-    modes = sys.argv[3:] or ["tcfwd", "tcbwd", "tc"]
+    modes = sys.argv[3:] or ["tcfwd", "tc"]
     gen = torch.Generator().manual_seed(B)
     actor, critic = ol.build_networks(B)
     batch = list(om.synthetic_batch(B, seed=B + 1))

@@ -45,8 +45,8 @@ def main():
     buf = (C.c_longlong * 32)()
     raw.cmarl_debug_tcgru_timeline(0, buf)
     v = list(buf)
-    names_b = ["step start", "D_3(prev)", "x1/h staged", "da staged, R_1", "next head", "D_1 (round rz done)", "n/hn staged, R_2",
-               "next dW2 + D_2 (dx1|dh, round n)", "dx1/X staged, R_3", "next gate operands requested"]
+    names_b = ["step start", "D_3(prev)", "operands, x1/h staged, da -> TMEM / A image", "R_1 published", "(x rows requested)", "D_1 (round rz done)",
+               "n/hn staged, R_2", "D_2 (dx1|dh, round n)", "dx1/X staged, R_3", "(tile end: flush)"]
     print(f"backward step (B {B}, tbptt {tb}), cycles:")
     for i in range(1, 10):
         print(f"  {names_b[i]:34s} +{v[i] - v[i - 1]:7d}   (t = {v[i] - v[0]})")
