@@ -9,7 +9,14 @@ namespace chain {
 // ------------------------------------------------------------------------------------------------
 // Heads: what happens to the network output z of one sample
 // ------------------------------------------------------------------------------------------------
-struct PolicyHead {
+// SFU = true (tc_gru.cu): exp / log / the softmax divisions on the special-function unit (ex2.approx, lg2.approx, rcp.approx:
+// <= 2 ulp each on the argument ranges that occur: logits - max in [-1e9, 0], a sum of exponentials in [1, 5], a log-ratio of a
+// few tenths) instead of the libm forms, which are ~3x the instructions of the whole head.
+template <bool SFU>
+struct PolicyHeadT {
+    static __device__ __forceinline__ float exp_(float x) { return SFU ? __expf(x) : expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return SFU ? __logf(x) : logf(x); }
+    static __device__ __forceinline__ float div_(float a, float b) { return SFU ? __fdividef(a, b) : a / b; }
     static constexpr int OUT = 5;
     static constexpr int NSTAT = 5;     // loss, entropy, kl, clip fraction, valid samples
     using Args = PolicyHeadArgs;
@@ -58,24 +65,24 @@ struct PolicyHead {
         for (int a = 1; a < OUT; ++a) mx = fmaxf(mx, z[a]);
         float se = 0.0f;
 #pragma unroll
-        for (int a = 0; a < OUT; ++a) se += expf(z[a] - mx);
-        const float lse = mx + logf(se);
+        for (int a = 0; a < OUT; ++a) se += exp_(z[a] - mx);
+        const float lse = mx + log_(se);
         float l[OUT], p[OUT];
         float mx2 = -INFINITY;
 #pragma unroll
         for (int a = 0; a < OUT; ++a) { l[a] = z[a] - lse; mx2 = fmaxf(mx2, l[a]); }
         float se2 = 0.0f;
 #pragma unroll
-        for (int a = 0; a < OUT; ++a) { p[a] = expf(l[a] - mx2); se2 += p[a]; }
+        for (int a = 0; a < OUT; ++a) { p[a] = exp_(l[a] - mx2); se2 += p[a]; }
         float ent = 0.0f;
 #pragma unroll
-        for (int a = 0; a < OUT; ++a) { p[a] = p[a] / se2; ent -= l[a] * p[a]; }
+        for (int a = 0; a < OUT; ++a) { p[a] = div_(p[a], se2); ent -= l[a] * p[a]; }
         const int act = in.act;
         float logp = l[0];
 #pragma unroll
         for (int a = 1; a < OUT; ++a) logp = (act == a) ? l[a] : logp;
         const float log_ratio = logp - in.logp_old;
-        const float ratio = expf(log_ratio);
+        const float ratio = exp_(log_ratio);
         const float A = in.adv;
         const float lo = 1.0f - h.clip, hi = 1.0f + h.clip;
         const float pg1 = A * ratio;
@@ -104,6 +111,7 @@ struct PolicyHead {
             if (in.unavail & (1u << a)) dz[a] = 0.0f;
     }
 };
+using PolicyHead = PolicyHeadT<false>;
 
 struct ValueHead {
     static constexpr int OUT = 1;

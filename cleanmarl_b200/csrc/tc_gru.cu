@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
         float* dw2acc = reinterpret_cast<float*>(sm + oDW2) + q * 8 * H;
         float* db2acc = reinterpret_cast<float*>(sm + oDW2) + 4 * 8 * H + q * 8;
         const int ct = warp * 32 + lane;
-        float st[PolicyHead::NSTAT];
+        float st[PolicyHeadT<true>::NSTAT];
 #pragma unroll
-        for (int k = 0; k < PolicyHead::NSTAT; ++k) st[k] = 0.0f;
+        for (int k = 0; k < PolicyHeadT<true>::NSTAT; ++k) st[k] = 0.0f;
 
         float xr[NXO * 8];
         auto load_x = [&](int t, int g, int b) {
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
                 //      MMAs run under it: logits = W2 relu(h') + b2 -> loss terms, statistics, dlogits (-> global, for the
                 //      backward kernel), dW2 / db2 ------------------------------------------------------------------------
                 {
-                    const PolicyHead::In hin = PolicyHead::load(a.head, t, g, b, a.N, a.B, inb && hf == 0);
+                    const PolicyHeadT<true>::In hin = PolicyHeadT<true>::load(a.head, t, g, b, a.N, a.B, inb && hf == 0);
                     float rh[16], z[NA], dz[NA];
 #pragma unroll
                     for (int c = 0; c < NA; ++c) z[c] = 0.0f;
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
                     if (hf == 0) {
 #pragma unroll
                         for (int c = 0; c < NA; ++c) z[c] = (z[c] + zx[c * M + s]) + fb2[c];
-                        PolicyHead::compute(a.head, hin, z, true, dz, st);
+                        PolicyHeadT<true>::compute(a.head, hin, z, true, dz, st);
                         float* dzp = a.dlogits + ((size_t)t * a.N + g) * 8 * a.B + b;
 #pragma unroll
                         for (int c = 0; c < NA; ++c) {
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
             }
             float* red = reinterpret_cast<float*>(sm + oRed);
 #pragma unroll
-            for (int k = 0; k < PolicyHead::NSTAT; ++k) {
+            for (int k = 0; k < PolicyHeadT<true>::NSTAT; ++k) {
                 const float v = warp_sum_f(st[k]);              // half-1 warps carry zeros
                 compute_bar();
                 if (lane == 0) red[warp] = v;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
                 if (ct == 0) out[NA * H + NA + k] = ((red[0] + red[1]) + red[2]) + red[3];
             }
             if (ct == 0)
-                for (int k = PolicyHead::NSTAT; k < CMARL_N_STATS; ++k) out[NA * H + NA + k] = 0.0f;
+                for (int k = PolicyHeadT<true>::NSTAT; k < CMARL_N_STATS; ++k) out[NA * H + NA + k] = 0.0f;
         }
     }
     tc::tcgen05_fence_before();
@@ -517,7 +517,11 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
         if (ktl && !flushed) g_tcgru_tl[12] = clock64();
         float* S = reinterpret_cast<float*>(sm + oAs);
         const int nflush = L.w2;
-        for (int i = ct; i < nflush; i += NCOMP) S[i] = 0.0f;
+        // scratch index of a Wih / Whh element: rows of 33 floats (a warp's lanes are 32 different rows of one column: 32
+        // floats apart they all hit one bank -- the flush was 31 k cycles); bih / bhh follow, shifted by the padding
+        constexpr int GP = H + 1, GSHIFT = 2 * G3 * (GP - H);
+        const int oG = L.wih;                            // Wih rows 0..95, Whh rows 96..191
+        for (int i = ct; i < nflush + GSHIFT; i += NCOMP) S[i] = 0.0f;
         compute_bar();
         const int gsel = q & 1;                      // rows of this quadrant: gate r / n (0) or z / hn (1)
 #pragma unroll 1
@@ -541,13 +545,13 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
                     for (int kk = 0; kk < 5; ++kk) {
                         const int c8 = 2 * kk + hf;
                         if (c8 < 8) {
-                            float* p = S + (c8 < 4 ? L.wih : L.whh) + R * H + 8 * (c8 & 3);
+                            float* p = S + oG + ((c8 < 4 ? 0 : G3) + R) * GP + 8 * (c8 & 3);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) p[e] = ph == 0 ? __uint_as_float(vz[kk][e]) : p[e] + __uint_as_float(vz[kk][e]);
                         } else if (c8 == 8) {
                             const float x = __uint_as_float(vz[kk][0]);
-                            S[L.bih + R] = ph == 0 ? x : S[L.bih + R] + x;
-                            S[L.bhh + R] = ph == 0 ? x : S[L.bhh + R] + x;
+                            S[L.bih + GSHIFT + R] = ph == 0 ? x : S[L.bih + GSHIFT + R] + x;
+                            S[L.bhh + GSHIFT + R] = ph == 0 ? x : S[L.bhh + GSHIFT + R] + x;
                         }
                     }
                 }
@@ -555,12 +559,12 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
                     const int R = 2 * H + lane;      // n rows -> Wih_n, bih_n; hn rows -> Whh_n, bhh_n
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
-                        float* p = S + (gsel == 0 ? L.wih : L.whh) + R * H + 8 * (2 * kk + hf);
+                        float* p = S + oG + ((gsel == 0 ? 0 : G3) + R) * GP + 8 * (2 * kk + hf);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) p[e] = ph == 0 ? __uint_as_float(vn[kk][e]) : p[e] + __uint_as_float(vn[kk][e]);
                     }
                     if (hf == 0) {
-                        const int o = (gsel == 0 ? L.bih : L.bhh) + R;
+                        const int o = (gsel == 0 ? L.bih : L.bhh) + GSHIFT + R;
                         const float x = __uint_as_float(vn[2][0]);
                         S[o] = ph == 0 ? x : S[o] + x;
                     }
@@ -598,7 +602,9 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
 #pragma unroll
             for (int r = 0; r < NF; ++r) {
                 const int i = ct + NCOMP * r;
-                v[r] = i < nflush ? S[i] : 0.0f;
+                const int g0 = i - oG;
+            const int si = i < oG ? i : (i < L.bih ? oG + (g0 >> 5) * GP + (g0 & 31) : i + GSHIFT);
+            v[r] = i < nflush ? S[si] : 0.0f;
             }
             if (flushed) {
                 float o[NF];
