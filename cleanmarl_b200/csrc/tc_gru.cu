@@ -521,8 +521,8 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
         // floats apart they all hit one bank -- the flush was 31 k cycles); bih / bhh follow, shifted by the padding
         constexpr int GP = H + 1, GSHIFT = 2 * G3 * (GP - H);
         const int oG = L.wih;                            // Wih rows 0..95, Whh rows 96..191
-        for (int i = ct; i < nflush + GSHIFT; i += NCOMP) S[i] = 0.0f;
-        compute_bar();
+        // (no zeroing pass: every scratch element the last pass reads is written by the lo phase, except the folded id columns
+        // of the OTHER agents, which that pass takes as zero)
         const int gsel = q & 1;                      // rows of this quadrant: gate r / n (0) or z / hn (1)
 #pragma unroll 1
         for (int ph = 0; ph < 2; ++ph) {
@@ -546,8 +546,11 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
                         const int c8 = 2 * kk + hf;
                         if (c8 < 8) {
                             float* p = S + oG + ((c8 < 4 ? 0 : G3) + R) * GP + 8 * (c8 & 3);
+                            float o8[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) p[e] = ph == 0 ? __uint_as_float(vz[kk][e]) : p[e] + __uint_as_float(vz[kk][e]);
+                            for (int e = 0; e < 8; ++e) o8[e] = ph == 0 ? 0.0f : p[e];     // every load before the first store
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) p[e] = o8[e] + __uint_as_float(vz[kk][e]);
                         } else if (c8 == 8) {
                             const float x = __uint_as_float(vz[kk][0]);
                             S[L.bih + GSHIFT + R] = ph == 0 ? x : S[L.bih + GSHIFT + R] + x;
@@ -560,8 +563,11 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
                         float* p = S + oG + ((gsel == 0 ? 0 : G3) + R) * GP + 8 * (2 * kk + hf);
+                        float o8[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) p[e] = ph == 0 ? __uint_as_float(vn[kk][e]) : p[e] + __uint_as_float(vn[kk][e]);
+                        for (int e = 0; e < 8; ++e) o8[e] = ph == 0 ? 0.0f : p[e];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) p[e] = o8[e] + __uint_as_float(vn[kk][e]);
                     }
                     if (hf == 0) {
                         const int o = (gsel == 0 ? L.bih : L.bhh) + GSHIFT + R;
@@ -604,7 +610,9 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
                 const int i = ct + NCOMP * r;
                 const int g0 = i - oG;
             const int si = i < oG ? i : (i < L.bih ? oG + (g0 >> 5) * GP + (g0 & 31) : i + GSHIFT);
-            v[r] = i < nflush ? S[si] : 0.0f;
+            bool other_id = false;                   // W1 column of another agent's folded one-hot id: no gradient from this tile
+            if (i < L.b1) { const int kcol = i % L.in; other_id = kcol >= a.in_rows && kcol != a.in_rows + g; }
+            v[r] = (i < nflush && !other_id) ? S[si] : 0.0f;
             }
             if (flushed) {
                 float o[NF];
