@@ -247,9 +247,14 @@ int cmarl_actor_act_recurrent(cmarl_ctx* ctx, const float* actor_params, const f
  * caller's all-reduce.  h_seq f32 [T+1][N][H][B] is caller-owned scratch that carries the hidden state from chunk
  * to chunk inside one epoch: t0 == 0 starts from zeros (LSTM:558, the kernel ignores slice 0); on return slices
  * t0+1..t1 hold the hidden states after each step (computed with the weights of THIS call, LSTM:620 detach).
- * stash: optional caller-owned scratch f32 [T][N][5H][B] (x1 and the gates r, z, n, W_hn h + b_hn of every step): with it
- * the backward pass reads the forward pass's gate activations back instead of recomputing them (faster, 640 B per
- * (agent, env, step) of extra traffic); NULL selects the recompute variant.  Both give the same results bit for bit. */
+ * stash: optional caller-owned scratch f32 [T][N][5H][B] (x1 and the gates r, z, n, W_hn h + b_hn of every step).
+ *   With a stash (and the tensor cores on, the default) the chunk runs as the two tcgen05 kernels of csrc/tc_gru.cu --
+ *   forward (hidden states, stash, head: dlogits into `workspace`) and backward through time -- which meet through h_seq,
+ *   the stash and the workspace (cmarl_workspace_bytes of a recurrent context covers the dlogits buffer f32 [T][N][8][B]).
+ *   Without one, or with cmarl_ctx_set_tensor_cores(ctx, 0), the fp32 FFMA kernel of csrc/gru.cu runs (one launch; NULL
+ *   selects its recompute variant, which gives the same results as its stash variant bit for bit).  The two
+ *   implementations agree to the tolerance both are held to against the reference (gradients <= 2e-5 of the chunk
+ *   gradient's max, hidden states <= 2e-6). */
 int cmarl_tbptt_chunk_grads(cmarl_ctx* ctx, const float* actor_params, const float* state, const float* obs,
                             const int32_t* actions, const float* logp_old, const float* adv, const uint8_t* mask,
                             const uint8_t* avail, double clip, double ent_coef, int32_t t0, int32_t t1,
