@@ -292,3 +292,56 @@ def test_trainer_recurrent_iteration_runs_and_matches_oracle(cm):
     assert abs(sc["critic_loss"] - np.mean(st["critic_loss"])) < 2e-5 * abs(np.mean(st["critic_loss"]))
     assert abs(sc["actor_gradients"] - np.mean(st["actor_grad_norm"])) < 1e-4 * np.mean(st["actor_grad_norm"])
     assert tr.step == B * 25 and tr.training_step == 3
+
+
+def test_tcgen05_chunk_kernels_at_baseline_size(cm):
+    """BASELINE configs[3] size (8 192 envs: 192 tiles of 128 envs over 296 forward / 148 backward CTAs, i.e. CTAs that
+    walk several tiles and add a second tile's sums into their partial row), one epoch of three chunks:
+    * forward: hidden states and gate stash of tc_gru_fwd_kernel within 2e-6 of the fp32 FFMA kernel's (csrc/gru.cu, itself
+      held to the oracle at the sizes the oracle finishes quickly);
+    * backward: tc_gru_bwd_kernel against the FFMA backward pass ON THE SAME forward results (CMARL_TBPTT=tcfwd), so both
+      see identical relu' masks: every chunk's gradient sums within 2e-5 of the chunk gradient's max (per tensor: 2e-5 of
+      the tensor's max), statistics within 1e-6 relative."""
+    import os
+    from cleanmarl_b200 import engine as E
+    from cleanmarl_b200.mappo import tbptt_chunks
+    B = 8192
+    gen = torch.Generator().manual_seed(5)
+    actor, critic = ol.build_networks(5)
+    batch = list(om.synthetic_batch(B, seed=6))
+    batch[7] = ragged_mask(B, 25, gen)
+    batch[2] = ol.synthetic_old_logp(actor, batch, seed=3)
+    adv = torch.randn(B, 25, 1, generator=gen).expand(B, 25, 3).contiguous()
+    eng = make_engine(cm, B)
+    dev = eng.device
+    d = E.to_device_layout(tuple(batch), dev)
+    adv_d = E.heads_to_device(adv, eng.n_heads, dev)
+    na = eng.n_actor
+    flat = torch.cat([actor.flat_params(), critic.flat_params()]).to(dev).contiguous()
+    chunks = tbptt_chunks(25, 10)
+    res = {}
+    for mode in ("ffma", "tcfwd", "tc"):
+        os.environ["CMARL_TBPTT"] = mode
+        try:
+            h_seq, stash, ga = eng.alloc_h_seq(), eng.alloc_gate_stash(), eng.empty(na + 8)
+            stash.zero_()
+            grads = []
+            for (t0, t1) in chunks:
+                eng.tbptt_chunk_grads(flat[:na], ga, h_seq, t0, t1, state=d["state"], actions=d["actions"],
+                                      logp_old=d["logp"], adv=adv_d, mask=d["mask"], clip=0.2, ent_coef=0.001, stash=stash)
+                grads.append(ga.clone())
+            torch.cuda.synchronize()
+            res[mode] = (h_seq.clone(), stash.clone(), grads)
+        finally:
+            os.environ.pop("CMARL_TBPTT", None)
+    assert (res["tcfwd"][0] - res["ffma"][0]).abs().max() < 2e-6
+    assert (res["tcfwd"][1] - res["ffma"][1]).abs().max() < 2e-6
+    assert torch.equal(res["tc"][0], res["tcfwd"][0]) and torch.equal(res["tc"][1], res["tcfwd"][1])
+    sizes = [32 * 21, 32, 3072, 3072, 96, 96, 160, 5]
+    for g_tc, g_ref in zip(res["tc"][2], res["tcfwd"][2]):
+        assert (g_tc[:na] - g_ref[:na]).abs().max() <= 2e-5 * g_ref[:na].abs().max()
+        o = 0
+        for n in sizes:
+            assert (g_tc[o:o + n] - g_ref[o:o + n]).abs().max() <= 2e-5 * g_ref[o:o + n].abs().max(), (o, n)
+            o += n
+        assert (g_tc[na:] - g_ref[na:]).abs().max() <= 1e-6 * g_ref[na:].abs().max()
