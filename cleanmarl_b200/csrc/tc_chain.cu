@@ -808,8 +808,14 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     if (src.indep) pdl_wait();
 }
 
-template <class C, class Head>
+// The tensor-core chains evaluate the policy head with exp / log / the softmax divisions on the special-function unit
+// (heads.cuh, PolicyHeadT<true>: <= 2 ulp each; the head runs on half of a CTA's compute warps while the others wait).
+template <class Hd> struct TcHead { using type = Hd; };
+template <> struct TcHead<PolicyHead> { using type = PolicyHeadT<true>; };
+
+template <class C, class Head0>
 static int tc_set_attr() {
+    using Head = typename TcHead<Head0>::type;
     return cmarl_check_cuda(cudaFuncSetAttribute(tc_chain_kernel<C, Head>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  C::smem_bytes),
                             "cudaFuncSetAttribute(tc_chain_kernel)");
@@ -817,9 +823,10 @@ static int tc_set_attr() {
 
 // `src.indep` launches (the critic chain of an epoch) are programmatic dependents of the kernel in front of them whatever
 // the context's launch-chaining switch says; everything else follows the switch (cmarl_launch).
-template <class C, class Head>
-static int tc_launch(const cmarl_ctx* ctx, const NetDesc& nd, const TileSrc& src, const typename Head::Args& ha, float* partials,
+template <class C, class Head0>
+static int tc_launch(const cmarl_ctx* ctx, const NetDesc& nd, const TileSrc& src, const typename Head0::Args& ha, float* partials,
                      int p_net, int grid, cudaStream_t st) {
+    using Head = typename TcHead<Head0>::type;
     return cmarl_check_cuda(cmarl_launch_pdl(src.indep || cmarl_chained(ctx), tc_chain_kernel<C, Head>, dim3(grid), dim3(NTHREADS),
                                              C::smem_bytes, st, nd, src, ha, partials, p_net),
                             "tc_chain_kernel launch");
