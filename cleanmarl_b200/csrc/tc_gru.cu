@@ -255,6 +255,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
                     xr[i * 8 + e] = (rr < rmax) ? __ldcg(xp + (uint32_t)rr * step) : 0.0f;
                 }
         };
+        // the input rows of a later step -> L2, one row per lane (a warp's 32 samples of a row are one 128-B line)
+        auto prefetch_x = [&](int t, int g, int b) {
+            const int bw = b - lane;
+            if (lane < a.in_rows && bw < a.B)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + (size_t)t * a.stride_t + (size_t)g * a.stride_g + (size_t)lane * a.B + bw));
+        };
         auto stage_x = [&]() {
 #pragma unroll
             for (int i = 0; i < NXO; ++i) {
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
                 publish(&bars[R_H]);
             }
             stage_x();
-            if (nsteps > 1) load_x(a.t0 + 1, g, b);
+            if (nsteps > 1) prefetch_x(a.t0 + 1, g, b);
 
             for (int i = 0; i < nsteps; ++i, par ^= 1) {
                 const int t = a.t0 + i;
@@ -344,8 +350,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) tc_gru_fwd_kernel(Args a) {
                 BTL(18);
                 // fc1 of this step has completed: the X image is free for the next step's rows
                 if (i + 1 < nsteps) {
+                    // (the rows are L2 hits, prefetched a step ago, requested only now: held in registers across a step -- or
+                    // just across the fc1 epilogue -- they were parked on the stack as they arrived; the wait falls under
+                    // the gate MMAs that the hand-off above released)
+                    load_x(t + 1, g, b);
                     stage_x();
-                    if (i + 2 < nsteps) load_x(t + 2, g, b);
+                    if (i + 2 < nsteps) prefetch_x(t + 2, g, b);
                 }
                 // ---- gates -> h_{t+1} -----------------------------------------------------------------------
                 BTL(19);
