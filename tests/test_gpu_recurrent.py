@@ -197,7 +197,7 @@ def test_tbptt_update_vs_reference_run(cm, golden, name):
     assert (out["params"][na:] - T(g["critic_final"])).abs().max() < 3e-6
 
 
-@pytest.mark.parametrize("B,use_obs,tbptt", [(200, False, 10), (77, True, 7), (1024, False, 25)])
+@pytest.mark.parametrize("B,use_obs,tbptt", [(200, False, 10), (77, True, 7), (1024, False, 25), (130, False, 12)])   # 12: the last chunk is ONE step
 def test_tbptt_chunk_gradients_vs_oracle(cm, B, use_obs, tbptt):
     """Per-chunk actor gradients (ragged masks, masked-out actions, ragged last tile, explicit obs / obs rebuilt from
     state) against autograd through the oracle's truncated-BPTT loop: each chunk's flat gradient within 2e-5 of its own
