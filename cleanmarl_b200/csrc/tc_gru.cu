@@ -767,6 +767,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
             const bool tl_on = g_tcgru_tl_on && blockIdx.x == 0 && k == 1 && tid == 0;
             BTL(0);
             uint32_t x1mask = 0u;
+            // L2 prefetch of the step BELOW this one (its lines were written by the forward kernel up to 10 steps x 0.8 KB x
+            // 24 k samples ago: more than L2 holds), one row per LANE (a warp's 32 samples of a row are one 128-B line): this
+            // warp's 80 stash rows + 16 h rows, the 5 dlogits rows and the input rows of its tile -- 4 instructions per warp
+            if (ci + 1 < nsteps) {
+                const int bw = b - lane;
+                if (bw < a.B) {
+                    const size_t rs = (size_t)a.B;
+                    const float* slab = a.stash + ((size_t)(t - 1) * a.N + g) * (5 * H) * rs + bw;
+                    const float* hrow = a.h_seq + (((size_t)(t - 1) * a.N + g) * H) * rs + bw;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) {
+                        const int r = lane + 32 * m, arr = r >> 4, k = r & 15;       // 96 rows: 5 stash arrays + h, 16 units each
+                        const float* pf = arr < 5 ? slab + (size_t)(arr * H + 16 * hf + k) * rs : hrow + (size_t)(16 * hf + k) * rs;
+                        if (arr < 5 || t > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                    }
+                    const float* pf2 = lane < 8 ? a.dlogits + (((size_t)(t - 1) * a.N + g) * 8 + lane) * rs + bw
+                                                : a.x + (size_t)(t - 1) * a.stride_t + (size_t)g * a.stride_g + (size_t)(lane - 8) * rs + bw;
+                    if (lane < NA || (lane >= 8 && lane - 8 < a.in_rows)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf2));
+                }
+            }
             if (active) {
                 // ---- the previous step's last round has completed: the images are free (a tile's first step: waited at its end)
                 if (ci > 0) acquire(&bars[D_3], par ^ 1);
