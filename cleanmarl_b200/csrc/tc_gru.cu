@@ -788,13 +788,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                 }
             }
             if (active) {
-                // ---- the previous step's last round has completed: the images are free (a tile's first step: waited at its end)
-                if (ci > 0) acquire(&bars[D_3], par ^ 1);
-                else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) carry[i] = 0.0f;
-                }
-                BTL(1);
                 // ---- four units at a time, operands one group ahead of the arithmetic: x1, h_t -> B image rows 0..31 / 32..63;
                 //      gate gradients da -> TMEM A columns, their (r, z) pair -> A image --------------------------------------
                 {
@@ -826,6 +819,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
                         }
                     };
                     load4();
+                    // (the first group and the dlogits are in flight across the wait for the images)
+                    if (ci > 0) acquire(&bars[D_3], par ^ 1);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) carry[i] = 0.0f;
+                    }
+                    BTL(1);
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         float sx1[4], shp[4], sr[4], sz[4], sn[4], sg[4];
