@@ -644,8 +644,8 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
         compute_bar();          // scratch reads done before the next step's gate gradients go to the A image
 }
 
-// (9 warps: the SM sub-partition that hosts three of them caps the kernel at 168 registers per thread)
-__global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
+constexpr int BWD_THREADS = NCOMP + 128;
+__global__ void __launch_bounds__(BWD_THREADS, 1) tc_gru_bwd_kernel(Args a) {
     using namespace bwd;
     extern __shared__ __align__(1024) uint8_t sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
     if (ktl) g_tcgru_tl[10] = clock64();
 
     // ---- set-up that touches no global memory --------------------------------------------------------
-    for (int i = tid * 16; i < A_BYTES + 2 * B_BYTES; i += NTHREADS * 16) *reinterpret_cast<uint4*>(sm + oAs + i) = make_uint4(0, 0, 0, 0);
+    for (int i = tid * 16; i < A_BYTES + 2 * B_BYTES; i += BWD_THREADS * 16) *reinterpret_cast<uint4*>(sm + oAs + i) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int i = 0; i < N_BARS; ++i) tc::mbar_init(&bars[i], i < D_1 ? NCOMP : 1);
         tc::fence_mbar_init();
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
         const float* P = a.params;
         // B of the dx1 | dh GEMM: output n < 32: dx1 unit n = sum_k da_i[k] Wih[k][n] (k < 96: r, z, n gate rows);
         //                         output 32 + n: dh unit n = sum_k da_h[k] Whh[k][n] (A columns 0..63 and 96..127: r, z, hn)
-        CMARL_STRIDED(i, 2 * H * 4 * H, NTHREADS) {
+        CMARL_STRIDED(i, 2 * H * 4 * H, BWD_THREADS) {
             const int k = i / (2 * H), n = i - k * (2 * H);      // n fastest: consecutive threads read consecutive floats
             float w = 0.0f;
             if (n < H) { if (k < G3) w = __ldcg(P + L.wih + k * H + n); }
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
             else if (k >= G3) w = __ldcg(P + L.whh + (k - H) * H + (n - H));
             st_split(sm + oWb, sm + oWb + szWb, kmaj(n, k, 4 * H), w);
         }
-        CMARL_STRIDED(i, H * 8, NTHREADS) {
+        CMARL_STRIDED(i, H * 8, BWD_THREADS) {
             const int j = i / 8, c = i - j * 8;
             reinterpret_cast<float*>(sm + oW2T)[i] = (c < NA) ? __ldcg(P + L.w2 + c * H + j) : 0.0f;
         }
@@ -695,7 +695,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
     const uint32_t sbase = tc::smem_u32(sm);
     if (ktl) g_tcgru_tl[11] = clock64();
 
-    if (warp == 8) {
+    if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 8) {
         // ================================ MMA issue warp ==================================================
         const bool leader = tc::elect_one();
         const uint32_t As = sbase + oAs, Bs_h = sbase + oBs, Bs_l = Bs_h + B_BYTES;
@@ -716,7 +718,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gru_bwd_kernel(Args a) {
             }
         }
         __syncwarp();
+        }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         // ================================ compute warps ====================================================
         const int q = warp & 3, hf = warp >> 2;
         const int s = q * 32 + lane;
@@ -994,7 +998,7 @@ int cmarl_tc_gru_launch(cmarl_ctx* ctx, const chain::GruChunkArgs& a, int which,
     }
     if (which & 2) {
         const int grid = units < ctx->sm_count ? units : ctx->sm_count;
-        CMARL_CUDA(cmarl_launch(ctx, tcgru::tc_gru_bwd_kernel, dim3(grid), dim3(tctile::NTHREADS), tcgru::bwd::SMEM, st, a));
+        CMARL_CUDA(cmarl_launch(ctx, tcgru::tc_gru_bwd_kernel, dim3(grid), dim3(tcgru::BWD_THREADS), tcgru::bwd::SMEM, st, a));
         if (grid_out) *grid_out = grid;
     }
     return 0;
