@@ -755,6 +755,40 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_gru_bwd_kernel(Args a) {
 
 
 
+        // A step's operands: x1, r, z, n, Whn h + bhn (stash), h_t (h_seq), this thread's 16 units, and its 5 dlogits.  With the
+        // compute groups at 232 registers they are requested a step AHEAD -- right after the hand-off of the (n, hn) round, in
+        // the shadow of that round and the dx1 | dh GEMM -- and sit in registers until the gate-gradient stage of their step.
+        float ox1[16], orr[16], oz[16], on[16], og[16], ohp[16], odz[NA];
+        auto load_ops = [&](int t, int g, int b, int half) {
+            const bool inb = b < a.B, hb = inb && t > 0;
+            const size_t rs = (size_t)a.B;
+            const float* p0 = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B + (size_t)(16 * hf) * rs + b;
+            if (half != 1) {
+                const float* p1 = p0 + (size_t)H * rs;
+                const float* p2 = p1 + (size_t)H * rs;
+                const float* dzp = a.dlogits + ((size_t)t * a.N + g) * 8 * a.B + b;
+#pragma unroll
+                for (int c = 0; c < NA; ++c, dzp += rs) odz[c] = inb ? __ldcg(dzp) : 0.0f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e, p0 += rs, p1 += rs, p2 += rs) {
+                    ox1[e] = inb ? __ldcg(p0) : 0.0f;
+                    orr[e] = inb ? __ldcg(p1) : 0.0f;
+                    oz[e] = inb ? __ldcg(p2) : 0.0f;
+                }
+            }
+            if (half != 0) {
+                const float* p3 = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B + (size_t)(3 * H + 16 * hf) * rs + b;
+                const float* p4 = p3 + (size_t)H * rs;
+                const float* p5 = a.h_seq + (((size_t)t * a.N + g) * H) * a.B + (size_t)(16 * hf) * rs + b;
+#pragma unroll
+                for (int e = 0; e < 16; ++e, p3 += rs, p4 += rs, p5 += rs) {
+                    on[e] = inb ? __ldcg(p3) : 0.0f;
+                    og[e] = inb ? __ldcg(p4) : 0.0f;
+                    ohp[e] = hb ? __ldcg(p5) : 0.0f;
+                }
+            }
+        };
+
         // ONE flat loop over the steps of all tiles of this CTA (every stage exists once in the code).  The head of every step
         // (logits, loss terms, dlogits, dW2) was evaluated by the forward kernel: this one reads 5 dlogits per sample.
         const int ntiles = (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -792,50 +826,27 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_gru_bwd_kernel(Args a) {
                 }
             }
             if (active) {
-                // ---- four units at a time, operands one group ahead of the arithmetic: x1, h_t -> B image rows 0..31 / 32..63;
-                //      gate gradients da -> TMEM A columns, their (r, z) pair -> A image --------------------------------------
+                // ---- x1, h_t -> B image rows 0..31 / 32..63; gate gradients da -> TMEM A columns, their (r, z) pair -> A image
+                //      (four units at a time; operands prefetched a step ago, a tile's first step requests them here) ----------
                 {
-                    const size_t rs = (size_t)a.B;
-                    const bool hb = inb && t > 0;
-                    // running pointers into the stash rows x1, r, z, n, Whn h and the h_seq row of this thread's units
-                    const float* p0 = a.stash + ((size_t)t * a.N + g) * (5 * H) * a.B + (size_t)(16 * hf) * rs + b;
-                    const float* p1 = p0 + (size_t)H * rs;
-                    const float* p2 = p1 + (size_t)H * rs;
-                    const float* p3 = p2 + (size_t)H * rs;
-                    const float* p4 = p3 + (size_t)H * rs;
-                    const float* p5 = a.h_seq + (((size_t)t * a.N + g) * H) * a.B + (size_t)(16 * hf) * rs + b;
-                    float dz[NA];
-                    {
-                        const float* dzp = a.dlogits + ((size_t)t * a.N + g) * 8 * a.B + b;
-#pragma unroll
-                        for (int c = 0; c < NA; ++c, dzp += rs) dz[c] = inb ? __ldcg(dzp) : 0.0f;
-                    }
-                    float nx1[4], nhp[4], nr[4], nz[4], nn[4], ng[4];
-                    auto load4 = [&]() {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e, p0 += rs, p1 += rs, p2 += rs, p3 += rs, p4 += rs, p5 += rs) {
-                            nx1[e] = inb ? __ldcg(p0) : 0.0f;
-                            nr[e] = inb ? __ldcg(p1) : 0.0f;
-                            nz[e] = inb ? __ldcg(p2) : 0.0f;
-                            nn[e] = inb ? __ldcg(p3) : 0.0f;
-                            ng[e] = inb ? __ldcg(p4) : 0.0f;
-                            nhp[e] = hb ? __ldcg(p5) : 0.0f;
-                        }
-                    };
-                    load4();
-                    // (the first group and the dlogits are in flight across the wait for the images)
+                    if (ci == 0) load_ops(t, g, b, 2);
                     if (ci > 0) acquire(&bars[D_3], par ^ 1);
                     else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) carry[i] = 0.0f;
                     }
                     BTL(1);
+                    float dz[NA];
+#pragma unroll
+                    for (int c = 0; c < NA; ++c) dz[c] = odz[c];
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         float sx1[4], shp[4], sr[4], sz[4], sn[4], sg[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) { sx1[e] = nx1[e]; shp[e] = nhp[e]; sr[e] = nr[e]; sz[e] = nz[e]; sn[e] = nn[e]; sg[e] = ng[e]; }
-                        if (k4 < 3) load4();
+                        for (int e = 0; e < 4; ++e) {
+                            sx1[e] = ox1[4 * k4 + e]; shp[e] = ohp[4 * k4 + e]; sr[e] = orr[4 * k4 + e];
+                            sz[e] = oz[4 * k4 + e]; sn[e] = on[4 * k4 + e]; sg[e] = og[4 * k4 + e];
+                        }
                         const int j0 = 16 * hf + 4 * k4;
                         float dan[4], daz[4];
 #pragma unroll
@@ -889,7 +900,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_gru_bwd_kernel(Args a) {
                 BTL(2);
                 publish(&bars[R_1]);            // issuer: (r, z) weight-gradient round, then the dx1 | dh GEMM
                 BTL(3);
-                load_x(t, g, b);                // this step's input rows (dW1 round)
             }
             BTL(4);
             if (active) {
@@ -914,11 +924,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_gru_bwd_kernel(Args a) {
                 }
                 publish(&bars[R_2]);
                 BTL(6);
+                if (ci + 1 < nsteps) load_ops(t - 1, g, b, 2);  // in flight under the (n, hn) round and the dx1 | dh GEMM (split over both
+                                                                // rounds' shadows it delayed the restaging: 13.5 k vs 13.0 k cycles per step)
+                load_x(t, g, b);                // this step's input rows (dW1 round): requested here, not at the first hand-off
+                                                // (held across the restaging they were spilled as they arrived)
             }
             if (active) {
                 // ---- dx1 = (da_i Wih) . relu'(x1), dh carry += da_h Whh; dW1 round: A image <- dx1, B image <- x | 1 ----
                 acquire(&bars[D_2], par);       // second round and the dx1 | dh GEMM complete
                 BTL(7);
+
                 {
                     uint32_t vx[16], vh[16];
                     tc::tmem_ld16(tl + cDB + 16 * hf, vx);
