@@ -1,12 +1,14 @@
 // Recurrent-actor path on the 5th-gen tensor cores (tcgen05 / TMEM): one truncated-BPTT chunk of
 // cleanmarl/mappo_lstm_multienvs.py:551-620 ("LSTM" below) as TWO kernels that meet in global memory (h_seq + gate stash,
-// the formats of gru.cu, so either half can be exchanged for the fp32 FFMA kernel of gru.cu -- CMARL_TBPTT=tcfwd / tcbwd):
+// the formats of gru.cu, so the backward half can be exchanged for the fp32 FFMA kernel of gru.cu -- CMARL_TBPTT=tcfwd):
 //
-//   tc_gru_fwd_kernel   t = t0 .. t1-1: x1 = relu(W1 x + b1), GRUCell, h_{t+1} -> h_seq, (x1, r, z, n, Whn h + bhn) -> stash
-//   tc_gru_bwd_kernel   t = t1-1 .. t0: head (loss terms, statistics, dlogits), gate gradients, dx1 / dh through the
-//                       recurrence, weight gradients accumulated in TMEM -> one partial row per CTA
+//   tc_gru_fwd_kernel   t = t0 .. t1-1: x1 = relu(W1 x + b1), GRUCell, h_{t+1} -> h_seq, (x1, r, z, n, Whn h + bhn) -> stash;
+//                       the head of every step (loss terms, statistics, dlogits -> workspace, dW2 / db2)
+//   tc_gru_bwd_kernel   t = t1-1 .. t0: gate gradients from the dlogits, dx1 / dh through the recurrence, weight gradients
+//                       accumulated in TMEM -> one partial row per CTA (+ the forward CTAs' dW2 / db2 / statistics rows)
 //
-// Both: one CTA = 8 compute warps + 1 MMA-issue warp, one tile = 128 consecutive envs of one agent = 128 TMEM lanes;
+// Both: one CTA = 8 compute warps + 1 MMA-issue warp (backward: + 3 idle warps that complete the issue warp's warpgroup, see
+// there), one tile = 128 consecutive envs of one agent = 128 TMEM lanes;
 // compute thread (q = warp & 3, hf = warp >> 2, lane) owns sample s = 32 q + lane and hidden units 16 hf .. 16 hf + 15.
 // Precision: kind::tf32 with the 3-term split of tc_chain.cu (x = hi + lo; lo*hi, hi*lo, hi*hi; fp32 accumulation).
 //
@@ -16,8 +18,8 @@
 // Backward (1 CTA / SM; 496 TMEM columns): the four gate gradients da = [da_r | da_z | da_n | da_hn] are the A operand of
 // ONE GEMM against [Wih | Whh] (dx1 | dh); the weight gradients contract over the samples and take sample-major
 // shared-memory images like tc_chain.cu's: A = two gates' hi images stacked on their lo images (M = 128), B = [x1 | h | 1],
-// two rounds (r, z) and (n, hn) per step plus one for dW1 = dx1^T [x | 1]; their accumulators stay in TMEM for `flush`
-// steps and are then added into the CTA's partial row.
+// two rounds (r, z) and (n, hn) per step plus one for dW1 = dx1^T [x | 1]; their accumulators stay in TMEM for the steps of a
+// tile and are then added into the CTA's partial row.
 #include <stdlib.h>
 
 #include "chain.cuh"
@@ -644,6 +646,15 @@ __device__ __noinline__ void bwd_flush(uint8_t* sm, const Args& a, uint32_t tl, 
         compute_bar();          // scratch reads done before the next step's gate gradients go to the A image
 }
 
+// THREE warpgroups: two of compute warps and one that holds the MMA-issue warp (its other three warps idle), so that the
+// groups can trade registers (setmaxnreg).  A 9-warp CTA is capped at 168 registers per thread (three warps share one
+// scheduler partition's 16 K registers), and at that cap every attempt to hold a step's 96 operands in registers ended with
+// the compiler parking them on the stack as they arrived (LDG; STL pairs: one L2 round trip per value, 10-16 k cycles per
+// step).  The issue group gives registers back (40), the compute groups take 232 -- ptxas budgets the two roles separately
+// only if each role's whole branch is dominated by its own setmaxnreg (an if / else that merges before the roles split again
+// left the compute code at 168 with 1.5 KB of spills).  Folding the issuing into compute warp 0 instead (8 warps, 254
+// registers) was slower: tcgen05.mma issue blocks while the pipe's queue is full, warp 0 arrived ~3 k cycles late at every
+// hand-off.
 constexpr int BWD_THREADS = NCOMP + 128;
 __global__ void __launch_bounds__(BWD_THREADS, 1) tc_gru_bwd_kernel(Args a) {
     using namespace bwd;
@@ -732,13 +743,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) tc_gru_bwd_kernel(Args a) {
         const int so = smaj(0, s);
         float* part_out = a.partials + (size_t)blockIdx.x * (L.count + CMARL_N_STATS);
 
-        // What the forward pass left for step t: x1, r, z, n, Whn h + bhn (stash) and h_t (h_seq), this thread's 16 units.
-        // 9 warps cap the kernel at 168 registers per thread, and a step's 96 operands do not survive a step in them: every
-        // attempt to request them ahead ended with the compiler parking them on the stack as they arrived (LDG; STL pairs: one
-        // L2 round trip per value, 10-16 k cycles per step).  So nothing is carried: the head of a step runs one step AHEAD on
-        // short-lived copies of (h_t, n, z) and prefetches the step's other lines into L2; the gate-gradient stage loads its
-        // operands itself, four units at a time, one group ahead of the arithmetic.  Addresses: one CTA-uniform 64-bit base +
-        // a running 32-bit offset (64-bit products per row are ~10 instructions and a register pair each).
+        // Loads: running pointers (one 64-bit add per row; 64-bit products per row were ~10 instructions and a register pair
+        // each); whatever is wanted a step later is first pulled into L2, one row per lane.
         float xr[NXO * 8];
         auto load_x = [&](int t, int g, int b) {
             const float* xp = a.x + (size_t)t * a.stride_t + (size_t)g * a.stride_g + b + (size_t)(8 * hf) * a.B;
