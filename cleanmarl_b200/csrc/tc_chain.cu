@@ -221,7 +221,7 @@ __device__ int g_tc_timeline_on = 0;
 enum { R_X = 0, R_H1, R_DH2, R_W2B, R_W1A, R_W1B, D_F1, D_F2, D_B1, D_W2A, D_W2B, D_W1A, D_W1B, N_BARS };
 
 template <class C, class Head>
-__global__ void __launch_bounds__(NTHREADS, C::CTAS_PER_SM)
+__global__ void __launch_bounds__(C::CTAS_PER_SM == 1 ? NTHREADS + 96 : NTHREADS, C::CTAS_PER_SM)
 tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restrict__ partials, int p_net) {
     extern __shared__ __align__(1024) uint8_t sm[];
     constexpr int H = C::H, K1P = C::K1P, OUT = Head::OUT;
@@ -270,7 +270,13 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     const uint32_t sbase = tc::smem_u32(sm);
     if (ktl) g_tc_timeline[21] = clock64();
 
-    if (warp == 8) {
+    // One CTA per SM (the 64-wide training chains): the CTA is launched as THREE warpgroups -- the issue warp's group is
+    // completed by three idle warps -- so that the groups can trade registers: a 9-warp CTA is capped at 168 per thread,
+    // the issue group gives back what it does not need, the compute groups take 232 (see tc_gru.cu).
+    // (ptxas budgets the two roles separately only if each role's whole branch is dominated by its own setmaxnreg)
+    if (warp >= 8) {
+        if (C::CTAS_PER_SM == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 8) {
         // ================================ MMA issue warp ==================================================
         {
             const uint32_t As = sbase + C::oAs, Bs_h = sbase + C::oBs, Bs_l = Bs_h + B_S_BYTES;
@@ -327,7 +333,9 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
             }
         }
         __syncwarp();
+        }
     } else {
+        if (C::CTAS_PER_SM == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         // ================================ compute warps ====================================================
         const int q = warp & 3, hf = warp >> 2;
         const int s = q * 32 + lane;                                    // sample within the tile = TMEM lane
@@ -827,7 +835,7 @@ template <class C, class Head0>
 static int tc_launch(const cmarl_ctx* ctx, const NetDesc& nd, const TileSrc& src, const typename Head0::Args& ha, float* partials,
                      int p_net, int grid, cudaStream_t st) {
     using Head = typename TcHead<Head0>::type;
-    return cmarl_check_cuda(cmarl_launch_pdl(src.indep || cmarl_chained(ctx), tc_chain_kernel<C, Head>, dim3(grid), dim3(NTHREADS),
+    return cmarl_check_cuda(cmarl_launch_pdl(src.indep || cmarl_chained(ctx), tc_chain_kernel<C, Head>, dim3(grid), dim3(C::CTAS_PER_SM == 1 ? NTHREADS + 96 : NTHREADS),
                                              C::smem_bytes, st, nd, src, ha, partials, p_net),
                             "tc_chain_kernel launch");
 }
