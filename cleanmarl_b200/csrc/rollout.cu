@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "spread.cuh"
 #include "sample.cuh"
+#include "tc_ptx.cuh"
+#include "tc_tile.cuh"
 
 namespace {
 
@@ -490,6 +492,354 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rollout with layer 2 of the actor on the tensor cores (H = 64 MLP actor: the benchmark shape).
+//   The 96 samples of a CTA's step (3 agents x 32 envs) are the rows of ONE M = 128 tile: layer 1 stays on the CUDA cores
+//   (K = 14: four warps per agent, 16 hidden units each, as in rollout_kernel) and writes relu(h1) split into tf32 hi / lo
+//   straight into the K-major A images in shared memory (row 32 n + e; one 16-byte chunk per four units: conflict-free
+//   STS.128); a dedicated issue warp multiplies by the hi / lo images of W2 (3xTF32: A_lo B_hi, A_hi B_lo, A_hi B_hi,
+//   24 tcgen05.mma of 128 x 64 x 8) into 64 TMEM columns.  The epilogue (b2, relu, output layer) is bound to the TMEM lane
+//   quadrants: warp w reads quadrant w % 4, so the rows of agent a are finished by the warps (n', qq = a) -- one of each
+//   agent's four -- in column groups of 24 / 24 / 16; the qq = 3 warps, which own no quadrant with rows in it, draw the
+//   race noise meanwhile.  Warp (0, a) samples agent a.
+//   The distance table of the team reward moves to the contact-force warps (off the critical path: they evaluate it for
+//   the state the previous step left, next to the pair forces, while the actor warps run the network).
+//   Measured on CTA 0 (cycles per step): FFMA layer 2 + output layer 3 480, here see profiles/rollout_timeline_r2.txt.
+// ------------------------------------------------------------------------------------------------
+namespace tcroll {
+constexpr int NCG = 3;                                   // column groups of the epilogue (one per warp reading a TMEM quadrant)
+constexpr int NTHR = RTHREADS + 32 * RPHYS + 32;         // 12 actor warps, 3 contact-force warps, the issue warp
+constexpr int NBAR = RTHREADS + 32 * RPHYS;              // the per-step block barriers leave the issue warp out
+constexpr int LBO = 128;                                 // next chunk of 4 k
+template <int H_>
+struct L {
+    static constexpr int H = H_;
+    static constexpr int NC0 = H == 64 ? 24 : 16;        // columns per epilogue group: 24 / 24 / 16 (H = 64), 16 / 16 / - (H = 32)
+    static constexpr int A_BYTES = 128 * H * 4;          // one A image (hi or lo): 128 rows x H k, K-major core matrices
+    static constexpr int B_BYTES = H * H * 4;            // one W2 image
+    static constexpr int SBO = (H / 4) * 128;            // next group of 8 rows
+    // shared memory (bytes)
+    static constexpr int oBar = 0;                       // full, done mbarriers + the TMEM base
+    static constexpr int oAh = 128, oAl = oAh + A_BYTES;
+    static constexpr int oBh = oAl + A_BYTES, oBl = oBh + B_BYTES;
+    static constexpr int oW1 = oBl + B_BYTES;            // f32 [H][16]
+    static constexpr int oB1 = oW1 + H * W1LD * 4;       // f32 [3][H] b1 (+ the agent's folded id column)
+    static constexpr int oB2 = oB1 + NAG * H * 4;        // f32 [H]
+    static constexpr int oW3 = oB2 + H * 4;              // f32 [H][8] (5 used)
+    static constexpr int oB3 = oW3 + H * 8 * 4;          // f32 [8]
+    static constexpr int oZp = oB3 + 32;                 // f32 [NAG][NCG][NACT][32] partial logits
+    static constexpr int oQs = oZp + NAG * NCG * NACT * REPB * 4;   // f32 [NAG][NACT][32] race noise
+    static constexpr int smem_bytes = oQs + NAG * NACT * REPB * 4;
+};
+template <int NT> __device__ __forceinline__ void bar_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+// b2, relu and the output layer on 8 accumulator columns starting at column j0
+__device__ __forceinline__ void head8(const uint32_t (&v)[8], int j0, const float* sB2f, const float* sW3f, float (&z)[NACT]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int j = j0 + i;
+        const float h2 = fmaxf(__uint_as_float(v[i]) + sB2f[j], 0.0f);
+        const float4 wv = *reinterpret_cast<const float4*>(sW3f + j * 8);
+        z[0] = fmaf(h2, wv.x, z[0]); z[1] = fmaf(h2, wv.y, z[1]); z[2] = fmaf(h2, wv.z, z[2]); z[3] = fmaf(h2, wv.w, z[3]);
+        z[4] = fmaf(h2, sW3f[j * 8 + 4], z[4]);
+    }
+}
+}  // namespace tcroll
+
+template <int H, int O>
+__global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a) {
+    using namespace tcroll;
+    using C = L<H>;
+    constexpr int A_BYTES = C::A_BYTES, SBO = C::SBO, NC0 = C::NC0;
+    constexpr int oBar = C::oBar, oAh = C::oAh, oAl = C::oAl, oBh = C::oBh, oBl = C::oBl, oW1 = C::oW1, oB1 = C::oB1, oB2 = C::oB2,
+                  oW3 = C::oW3, oB3 = C::oB3, oZp = C::oZp, oQs = C::oQs;
+    using RL = RolloutLayout<H, O, false>;
+    constexpr bool FOLD = O > CMARL_RAW_OBS;
+    constexpr int JL = H / NQ;
+    extern __shared__ __align__(128) uint8_t smb[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smb + oBar);            // [0] full (384 arrivals), [1] done (commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smb + oBar + 16);
+    const float* sW1f = reinterpret_cast<const float*>(smb + oW1);
+    const float* sB1f = reinterpret_cast<const float*>(smb + oB1);
+    const float* sB2f = reinterpret_cast<const float*>(smb + oB2);
+    const float* sW3f = reinterpret_cast<const float*>(smb + oW3);
+    const float* sB3f = reinterpret_cast<const float*>(smb + oB3);
+    float (*zp)[NCG][NACT][REPB] = reinterpret_cast<float (*)[NCG][NACT][REPB]>(smb + oZp);
+    float (*qs)[NACT][REPB] = reinterpret_cast<float (*)[NACT][REPB]>(smb + oQs);
+    __shared__ double es[18][REPB];
+    __shared__ int acts[NAG][REPB];
+    __shared__ double pf[3][REPB][2];
+    __shared__ double rd[REPB][12];
+    const int tid = threadIdx.x;
+    const int w = tid >> 5, e = tid & 31;
+    const int n = w >> 2, qq = w & 3;
+    const int b = blockIdx.x * REPB + e;
+    const bool live = b < a.B;
+    const int B = a.B;
+    const int j0 = qq * JL;
+
+    // ---- set-up: what touches no global memory first (runs under the tail of the launch in front) ----------------------
+    for (int i = tid * 16; i < 2 * A_BYTES; i += NTHR * 16) *reinterpret_cast<uint4*>(smb + oAh + i) = make_uint4(0, 0, 0, 0);   // rows 96..127 stay zero
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], RTHREADS);
+        tc::mbar_init(&bars[1], 1);
+        tc::fence_mbar_init();
+    }
+    if (w == 15) tc::tmem_alloc(tmem_slot, H);
+    pdl_wait_then_trigger();
+    CMARL_STRIDED(i, 18 * REPB, NTHR) {
+        const int r = i / REPB, c = i - r * REPB;
+        const int bb = blockIdx.x * REPB + c;
+        es[r][c] = (bb < B) ? a.env[(size_t)r * B + bb] : 0.0;
+    }
+    {
+        const float* __restrict__ P = a.actor;
+        float* fw = reinterpret_cast<float*>(smb);
+        CMARL_STRIDED(i, H * W1LD, NTHR) {
+            const int j = i / W1LD, k = i - j * W1LD;
+            fw[oW1 / 4 + i] = (k < CMARL_RAW_OBS - 4) ? __ldcg(P + RL::pW1 + j * O + k) : 0.0f;
+        }
+        CMARL_STRIDED(i, NAG * H, NTHR) {
+            const int g = i / H, j = i - g * H;
+            fw[oB1 / 4 + i] = __ldcg(P + RL::pB1 + j) + (FOLD ? __ldcg(P + RL::pW1 + j * O + CMARL_RAW_OBS + g) : 0.0f);
+        }
+        {   // W2 [out j][in k] -> B images (N = j, K = k), every load of a thread in flight before the first split
+            constexpr int NR = H * H / NTHR;
+            static_assert(NR * NTHR == H * H, "W2 elements per thread");
+            float wv[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) wv[r] = __ldcg(P + RL::pW2 + tid + r * NTHR);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int i = tid + r * NTHR, j = i / H, k = i - j * H;
+                float hi, lo;
+                tc::split_tf32(wv[r], hi, lo);
+                const int o = tctile::kmaj(j, k, H);
+                *reinterpret_cast<float*>(smb + oBh + o) = hi;
+                *reinterpret_cast<float*>(smb + oBl + o) = lo;
+            }
+        }
+        CMARL_STRIDED(i, H, NTHR) fw[oB2 / 4 + i] = __ldcg(P + RL::pB2 + i);
+        CMARL_STRIDED(i, H * 8, NTHR) {
+            const int j = i >> 3, k = i & 7;
+            fw[oW3 / 4 + i] = k < NACT ? __ldcg(P + RL::pW3 + k * H + j) : 0.0f;
+        }
+        if (tid < 8) fw[oB3 / 4 + tid] = tid < NACT ? __ldcg(P + RL::pB3 + tid) : 0.0f;
+    }
+    tc::fence_proxy_async_smem();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    double ep_acc = 0.0;
+    const uint64_t episode = a.episode_dev ? *a.episode_dev : a.episode;
+
+    if (w == 15) {
+        // ================================ MMA issue warp ==================================================
+        const uint32_t sbase = tc::smem_u32(smb);
+        constexpr uint32_t idesc = tc::make_idesc_tf32(128, H, 0, 0);
+        const bool leader = tc::elect_one();
+        for (int t = 0; t < a.T; ++t) {
+            tctile::acquire(&bars[0], (uint32_t)(t & 1));
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {           // small products first: A_lo B_hi, A_hi B_lo, A_hi B_hi
+                uint64_t da = tc::make_smem_desc(sbase + (pass == 0 ? oAl : oAh), LBO, SBO, 0);
+                uint64_t db = tc::make_smem_desc(sbase + (pass == 1 ? oBl : oBh), LBO, SBO, 0);
+#pragma unroll 2
+                for (int ks = 0; ks < H / 8; ++ks) {
+                    if (leader) tc::mma_tf32(tmem, da, db, idesc, (uint32_t)(pass | ks));
+                    da += (uint64_t)((2 * LBO) >> 4);
+                    db += (uint64_t)((2 * LBO) >> 4);
+                }
+            }
+            if (leader) tc::mma_commit(&bars[1]);
+            __syncwarp();
+        }
+    } else if (w >= NAG * NQ) {
+        // ================================ contact-force warps =============================================
+        // pair p = (0,1), (0,2), (1,2) of every env from the positions the previous step left, and (t > 0) that state's
+        // distance table for the team reward: tasks 0-8 agent a to landmark l (task = 3 l + a), 9-10 agents 1, 2 to agent 0
+        const int p = w - NAG * NQ;
+        const int ia = (p == 2) ? 1 : 0, ib = (p == 0) ? 1 : 2;
+        for (int t = 0; t <= a.T; ++t) {
+            if (t > 0) {
+#pragma unroll
+                for (int task = p; task < 11; task += 3) {
+                    int ea, eb;
+                    if (task < 9) { ea = 2 * (task % 3); eb = 12 + 2 * (task / 3); }
+                    else { ea = 2 * (task - 8); eb = 0; }
+                    rd[e][task] = spread::dist2d(es[ea][e], es[ea + 1][e], es[eb][e], es[eb + 1][e]);
+                }
+            }
+            if (t == a.T) break;
+            double gx, gy;
+            spread::pair_force(es[2 * ia][e], es[2 * ia + 1][e], es[2 * ib][e], es[2 * ib + 1][e], gx, gy);
+            pf[p][e][0] = gx; pf[p][e][1] = gy;
+            block_bar<NBAR>();
+            block_bar<NBAR>();
+        }
+    } else
+    for (int t = 0; t < a.T; ++t) {
+        // ---- observation before the action (MME:426-430), as in rollout_kernel ---------------------------------------
+        RTL(0, w == 0); RTL(8, w == 1);
+        const double opx = es[2 * n][e], opy = es[2 * n + 1][e], ovx = es[6 + 2 * n][e], ovy = es[6 + 2 * n + 1][e];
+        const int oj0 = (n == 0) ? 1 : 0, oj1 = (n == 2) ? 1 : 2;
+        float x[CMARL_RAW_OBS];
+        x[0] = (float)ovx; x[1] = (float)ovy; x[2] = (float)opx; x[3] = (float)opy;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            x[4 + 2 * l] = (float)(es[12 + 2 * l][e] - opx);
+            x[5 + 2 * l] = (float)(es[13 + 2 * l][e] - opy);
+        }
+        x[10] = (float)(es[2 * oj0][e] - opx); x[11] = (float)(es[2 * oj0 + 1][e] - opy);
+        x[12] = (float)(es[2 * oj1][e] - opx); x[13] = (float)(es[2 * oj1 + 1][e] - opy);
+        x[14] = 0.0f; x[15] = 0.0f; x[16] = 0.0f; x[17] = 0.0f;
+        // ---- layer 1 (this warp's JL units) -> relu -> tf32 hi / lo -> A images, row 32 n + e --------------------------
+        {
+            float acc[JL];
+#pragma unroll
+            for (int i = 0; i < JL; ++i) acc[i] = sB1f[n * H + j0 + i];
+#pragma unroll
+            for (int k4 = 0; k4 < W1LD; k4 += 4) {
+#pragma unroll
+                for (int i = 0; i < JL; ++i) {
+                    const float4 wv = *reinterpret_cast<const float4*>(sW1f + (j0 + i) * W1LD + k4);   // warp-uniform address
+                    acc[i] = fmaf(x[k4], wv.x, acc[i]); acc[i] = fmaf(x[k4 + 1], wv.y, acc[i]);
+                    acc[i] = fmaf(x[k4 + 2], wv.z, acc[i]); acc[i] = fmaf(x[k4 + 3], wv.w, acc[i]);
+                }
+            }
+            const int r = 32 * n + e;
+            uint8_t* row = smb + (r >> 3) * SBO + (r & 7) * 16 + (j0 >> 2) * LBO;
+#pragma unroll
+            for (int c = 0; c < JL / 4; ++c) {
+                float4 hi, lo;
+                tc::split_tf32(fmaxf(acc[4 * c], 0.0f), hi.x, lo.x);
+                tc::split_tf32(fmaxf(acc[4 * c + 1], 0.0f), hi.y, lo.y);
+                tc::split_tf32(fmaxf(acc[4 * c + 2], 0.0f), hi.z, lo.z);
+                tc::split_tf32(fmaxf(acc[4 * c + 3], 0.0f), hi.w, lo.w);
+                *reinterpret_cast<float4*>(row + oAh + c * LBO) = hi;
+                *reinterpret_cast<float4*>(row + oAl + c * LBO) = lo;
+            }
+        }
+        tctile::publish(&bars[0]);
+        RTL(2, w == 0);
+        // ---- under the MMAs: the buffer stores of the observation (row k by warp k % 4) and the race noise -------------
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < CMARL_RAW_OBS; ++k)
+                if ((k & 3) == qq) __stcs(a.state + ((size_t)t * 54 + n * CMARL_RAW_OBS + k) * B + b, x[k]);
+            if (a.obs) {
+                float* o = a.obs + ((size_t)t * NAG + n) * O * B + b;
+#pragma unroll
+                for (int k = 0; k < CMARL_RAW_OBS; ++k)
+                    if ((k & 3) == qq) __stcs(o + (size_t)k * B, x[k]);
+                if (FOLD && qq < NAG) __stcs(o + (size_t)(CMARL_RAW_OBS + qq) * B, qq == n ? 1.0f : 0.0f);
+            }
+        }
+        RTL(1, w == 0);
+        if (qq == 3) {   // warp (n, 3): the race noise of (t, agent n, env)
+            float q[NACT];
+            if (a.noise) {
+#pragma unroll
+                for (int k = 0; k < NACT; ++k)
+                    q[k] = live ? __ldcs(a.noise + (((size_t)t * NAG + n) * NACT + k) * B + b) : 1.0f;
+            } else {
+                philox_exp5(a.seed, episode, (uint32_t)t, (uint32_t)n, (uint32_t)b, q);
+            }
+#pragma unroll
+            for (int k = 0; k < NACT; ++k) qs[n][k][e] = q[k];
+            bar_named<128>(1 + n);
+        } else {
+            // ---- epilogue of agent qq's rows (TMEM quadrant qq), column group n: b2, relu, output layer -----------------
+            const int c0 = n * NC0;                          // warp-uniform
+            float z[NACT];
+#pragma unroll
+            for (int k = 0; k < NACT; ++k) z[k] = 0.0f;
+            tctile::acquire(&bars[1], (uint32_t)(t & 1));
+            RTL(3, w == 0);
+            const uint32_t ta = tmem + ((uint32_t)(32 * qq) << 16) + (uint32_t)c0;
+            uint32_t v0[8], v1[8], v2[8];
+            const bool g0 = c0 < H, g2 = NC0 == 24 && c0 + 16 < H;    // H = 64: the last group holds 16 columns; H = 32: none
+            if (g0) { tc::tmem_ld8(ta, v0); tc::tmem_ld8(ta + 8, v1); }
+            if (g2) tc::tmem_ld8(ta + 16, v2);
+            tc::tmem_wait_ld();
+            if (g0) { head8(v0, c0, sB2f, sW3f, z); head8(v1, c0 + 8, sB2f, sW3f, z); }
+            if (g2) head8(v2, c0 + 16, sB2f, sW3f, z);
+#pragma unroll
+            for (int k = 0; k < NACT; ++k) zp[qq][n][k][e] = z[k];
+            RTL(4, w == 0);
+            bar_named<128>(1 + qq);
+            RTL(5, w == 0);
+            if (n == 0) {
+                // ---- Categorical sample of agent qq: column-group sums in fixed order, then the exponential race ---------
+                float q[NACT];
+#pragma unroll
+                for (int k = 0; k < NACT; ++k) {
+                    z[k] = ((zp[qq][0][k][e] + zp[qq][1][k][e]) + zp[qq][2][k][e]) + sB3f[k];
+                    q[k] = qs[qq][k][e];
+                }
+                int action; float lp;
+                race_sample(z, q, action, lp);
+                acts[qq][e] = action;
+                if (live) {
+                    __stcs(a.actions + ((size_t)t * NAG + qq) * B + b, action);
+                    __stcs(a.logp + ((size_t)t * NAG + qq) * B + b, lp);
+                }
+            }
+        }
+        RTL(6, w == 0); RTL(9, w == 1);
+        block_bar<NBAR>();
+        RTL(10, w == 1);
+        // ---- physics (World.step) -----------------------------------------------------------------------------------
+        // (a) last step's team reward from the distance table the contact-force warps wrote before the barrier
+        if (t > 0 && tid < REPB) {
+            const double r = reward_from_table(rd[tid]);
+            ep_acc += r;
+            if (live) __stcs(a.reward + (size_t)(t - 1) * B + b, (float)r);
+        }
+        if (qq == 1) {
+            RTL(12, w == 1);
+            // (c) integration of agent n; forces added in the reference's pair order (0,1),(0,2),(1,2)
+            const int act = acts[n][e];
+            double ux = 0.0, uy = 0.0;
+            if (act == 1) ux = -1.0;
+            if (act == 2) ux = +1.0;
+            if (act == 3) uy = -1.0;
+            if (act == 4) uy = +1.0;
+            double fx = ux * spread::SENSITIVITY + 0.0;
+            double fy = uy * spread::SENSITIVITY + 0.0;
+            const int p1 = (n == 2) ? 1 : 0, p2 = (n == 0) ? 1 : 2;
+            const bool neg1 = (n != 0), neg2 = (n == 2);
+            const double g1x = pf[p1][e][0], g1y = pf[p1][e][1], g2x = pf[p2][e][0], g2y = pf[p2][e][1];
+            fx = (neg1 ? -g1x : g1x) + fx; fy = (neg1 ? -g1y : g1y) + fy;
+            fx = (neg2 ? -g2x : g2x) + fx; fy = (neg2 ? -g2y : g2y) + fy;
+            double px = opx, py = opy, vx = ovx, vy = ovy;
+            spread::integrate(px, py, vx, vy, fx, fy);
+            // every reader of the old state (the other warps' observations, the pair forces) is behind the barrier above
+            es[2 * n][e] = px; es[2 * n + 1][e] = py;
+            es[6 + 2 * n][e] = vx; es[6 + 2 * n + 1][e] = vy;
+            RTL(13, w == 1);
+        }
+        block_bar<NBAR>();
+        RTL(14, w == 1); RTL(7, w == 0);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (w == 15) tc::tmem_dealloc(tmem, H);
+    if (tid < REPB) {
+        const double r = reward_from_table(rd[tid]);
+        ep_acc += r;
+        if (live) {
+            __stcs(a.reward + (size_t)(a.T - 1) * B + b, (float)r);
+            if (a.ep_return) a.ep_return[b] = ep_acc;
+        }
+    }
+    for (int i = tid; i < 12 * REPB; i += NTHR) {
+        const int r = i / REPB, c = i - r * REPB;
+        const int bb = blockIdx.x * REPB + c;
+        if (bb < B) a.env[(size_t)r * B + bb] = es[r][c];
+    }
+}
+
 // ---- K2 alone ------------------------------------------------------------------------------
 struct ActArgs {
     const float* actor;
@@ -626,6 +976,10 @@ int cmarl_rollout_setup(cmarl_ctx* ctx) {
                                     (int)(RolloutLayout<32, 18, true>::floats * sizeof(float))));
     CMARL_CUDA(cudaFuncSetAttribute(actor_act_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)actor_smem_bytes<64>()));
+    CMARL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<64, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcroll::L<64>::smem_bytes));
+    CMARL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<64, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcroll::L<64>::smem_bytes));
+    CMARL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<32, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcroll::L<32>::smem_bytes));
+    CMARL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<32, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcroll::L<32>::smem_bytes));
     return 0;
 }
 
@@ -705,6 +1059,20 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
                                  NAG * NACT * REPB) * sizeof(float);
     const dim3 block(RolloutThreads<false>::N);
     KernelTimer kt(ctx, K_ROLLOUT, st);
+    {
+        // layer 2 on the tensor cores (default); CMARL_ROLLOUT=ffma selects the CUDA-core kernel (read at every call: tests
+        // compare the two within one process)
+        const char* v = getenv("CMARL_ROLLOUT");
+        if (!(v && v[0] == 'f')) {
+            const dim3 tb(tcroll::NTHR);
+            cudaError_t err;
+            if (H == 32) err = ids ? cmarl_launch(ctx, rollout_tc_kernel<32, 21>, dim3(grid), tb, (size_t)tcroll::L<32>::smem_bytes, st, a)
+                                   : cmarl_launch(ctx, rollout_tc_kernel<32, 18>, dim3(grid), tb, (size_t)tcroll::L<32>::smem_bytes, st, a);
+            else         err = ids ? cmarl_launch(ctx, rollout_tc_kernel<64, 21>, dim3(grid), tb, (size_t)tcroll::L<64>::smem_bytes, st, a)
+                                   : cmarl_launch(ctx, rollout_tc_kernel<64, 18>, dim3(grid), tb, (size_t)tcroll::L<64>::smem_bytes, st, a);
+            return cmarl_check_cuda(err, "rollout_tc_kernel");
+        }
+    }
     if (H == 32)
         return cmarl_check_cuda(ids ? cmarl_launch(ctx, rollout_kernel<32, 21, false>, dim3(grid), block, smem, st, a)
                                     : cmarl_launch(ctx, rollout_kernel<32, 18, false>, dim3(grid), block, smem, st, a), "rollout_kernel");

@@ -269,13 +269,16 @@ def test_actor_act_vs_reference_sample(cm, golden):
 
 
 # ----------------------------------------------------------------------------------------- K1+K2+K3
+@pytest.mark.parametrize("path", ["tc", "ffma"])
 @pytest.mark.parametrize("B", [96, 1000])
-def test_rollout_vs_oracle(cm, B):
-    """Device rollout vs the float64 oracle env + oracle actor, input driven (start positions and race
+def test_rollout_vs_oracle(cm, B, path, monkeypatch):
+    """Device rollout (layer 2 on the tensor cores: rollout_tc_kernel, the default; CUDA-core rollout_kernel) vs the
+    float64 oracle env + oracle actor, input driven (start positions and race
     noise supplied).  Physics: the oracle env replays the DEVICE actions open loop -> observations within
     1e-6 and team reward within 1e-6 of the oracle at every step.  Policy: the oracle actor on the device
     observations with the same noise reproduces the device actions (ties excepted) and log-probs."""
     from cleanmarl_b200 import engine as E
+    monkeypatch.setenv("CMARL_ROLLOUT", path)
     Tn = 25
     actor, critic = om.build_networks(1)
     eng = make_engine(cm, B)
