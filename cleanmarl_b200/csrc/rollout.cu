@@ -122,6 +122,7 @@ struct RolloutArgs {
     float* reward;          // [T][B]
     double* ep_return;      // [B] or null
     int T, B, O;
+    int dbg;                // timeline experiments (CMARL_ROLLOUT_DBG): 1 = constant race noise, 2 = no buffer stores of the observation
 };
 
 // Rollout kernel.  CTA = 32 envs = 12 warps; warp w = (agent n = w / 4, quarter qq = w % 4), lane = env.
@@ -148,7 +149,7 @@ template <bool GRU> struct RolloutThreads { static constexpr int N = RTHREADS + 
 constexpr int W1LD = 16;                 // layer-1 rows padded to 16 inputs (14 non-zero observation entries)
 
 // debug timeline of CTA 0, step 10 (clock64): slots 0-7 warp (0,0) [sampler], 8-15 warp (0,1) [physics]
-__device__ long long g_roll_tl[16];
+__device__ long long g_roll_tl[16 + 32];      // + 32: issue stamps of the MMAs (rollout_tc_kernel)
 #define RTL(slot, cond) do { if (blockIdx.x == 0 && t == 10 && e == 0 && (cond)) g_roll_tl[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ void agent_bar(int n) { asm volatile("bar.sync %0, 128;" ::"r"(1 + n) : "memory"); }
@@ -506,6 +507,22 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
 //   the state the previous step left, next to the pair forces, while the actor warps run the network).
 //   Measured on CTA 0 (cycles per step): FFMA layer 2 + output layer 3 480, here see profiles/rollout_timeline_r2.txt.
 // ------------------------------------------------------------------------------------------------
+// log of the Exp(1) race noise of (t, agent n, env b): supplied by the caller or drawn with Philox
+__device__ __forceinline__ void draw_log_noise(const RolloutArgs& a, uint64_t episode, int t, int n, int b, bool live, float (&lq)[NACT]) {
+    float q[NACT];
+    if (a.noise) {
+#pragma unroll
+        for (int k = 0; k < NACT; ++k) q[k] = live ? __ldcs(a.noise + (((size_t)t * NAG + n) * NACT + k) * a.B + b) : 1.0f;
+    } else if (a.dbg & 1) {
+#pragma unroll
+        for (int k = 0; k < NACT; ++k) q[k] = 1.0f + k;
+    } else {
+        philox_exp5(a.seed, episode, (uint32_t)t, (uint32_t)n, (uint32_t)b, q);
+    }
+#pragma unroll
+    for (int k = 0; k < NACT; ++k) lq[k] = logf(q[k]);
+}
+
 namespace tcroll {
 constexpr int NCG = 3;                                   // column groups of the epilogue (one per warp reading a TMEM quadrant)
 constexpr int NTHR = RTHREADS + 32 * RPHYS + 32;         // 12 actor warps, 3 contact-force warps, the issue warp
@@ -533,11 +550,13 @@ struct L {
 };
 template <int NT> __device__ __forceinline__ void bar_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
 // b2, relu and the output layer on 8 accumulator columns starting at column j0
-__device__ __forceinline__ void head8(const uint32_t (&v)[8], int j0, const float* sB2f, const float* sW3f, float (&z)[NACT]) {
+// (v: hi hi + lo hi products, u: hi lo products)
+__device__ __forceinline__ void head8(const uint32_t (&v)[8], const uint32_t (&u)[8], int j0, const float* sB2f, const float* sW3f,
+                                      float (&z)[NACT]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int j = j0 + i;
-        const float h2 = fmaxf(__uint_as_float(v[i]) + sB2f[j], 0.0f);
+        const float h2 = fmaxf((__uint_as_float(v[i]) + __uint_as_float(u[i])) + sB2f[j], 0.0f);
         const float4 wv = *reinterpret_cast<const float4*>(sW3f + j * 8);
         z[0] = fmaf(h2, wv.x, z[0]); z[1] = fmaf(h2, wv.y, z[1]); z[2] = fmaf(h2, wv.z, z[2]); z[3] = fmaf(h2, wv.w, z[3]);
         z[4] = fmaf(h2, sW3f[j * 8 + 4], z[4]);
@@ -564,7 +583,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
     const float* sW3f = reinterpret_cast<const float*>(smb + oW3);
     const float* sB3f = reinterpret_cast<const float*>(smb + oB3);
     float (*zp)[NCG][NACT][REPB] = reinterpret_cast<float (*)[NCG][NACT][REPB]>(smb + oZp);
-    float (*qs)[NACT][REPB] = reinterpret_cast<float (*)[NACT][REPB]>(smb + oQs);
+    float (*qs)[NACT][REPB] = reinterpret_cast<float (*)[NACT][REPB]>(smb + oQs);    // log race noise
     __shared__ double es[18][REPB];
     __shared__ int acts[NAG][REPB];
     __shared__ double pf[3][REPB][2];
@@ -584,8 +603,9 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
         tc::mbar_init(&bars[1], 1);
         tc::fence_mbar_init();
     }
-    if (w == 15) tc::tmem_alloc(tmem_slot, H);
+    if (w == 15) tc::tmem_alloc(tmem_slot, 2 * H);       // D = A_hi W2_hi^T + A_lo W2_hi^T | A_hi W2_lo^T
     pdl_wait_then_trigger();
+    const uint64_t episode = a.episode_dev ? *a.episode_dev : a.episode;
     CMARL_STRIDED(i, 18 * REPB, NTHR) {
         const int r = i / REPB, c = i - r * REPB;
         const int bb = blockIdx.x * REPB + c;
@@ -625,33 +645,45 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
         }
         if (tid < 8) fw[oB3 / 4 + tid] = tid < NACT ? __ldcg(P + RL::pB3 + tid) : 0.0f;
     }
+    if (w >= NAG * NQ && w < 15) {     // the race noise of step 0 (step t + 1 is drawn during step t by the warps (2, a))
+        float q[NACT];
+        draw_log_noise(a, episode, 0, w - NAG * NQ, b, live, q);
+#pragma unroll
+        for (int k = 0; k < NACT; ++k) qs[w - NAG * NQ][k][e] = q[k];
+    }
     tc::fence_proxy_async_smem();
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
-    double ep_acc = 0.0;
-    const uint64_t episode = a.episode_dev ? *a.episode_dev : a.episode;
+    double ep_acc = 0.0;                                     // warp 8: episode return of env e
 
     if (w == 15) {
         // ================================ MMA issue warp ==================================================
         const uint32_t sbase = tc::smem_u32(smb);
-        constexpr uint32_t idesc = tc::make_idesc_tf32(128, H, 0, 0);
+        // pass 0: A_hi x [W2_hi ; W2_lo] (the lo image directly follows the hi image: ONE N = 2H operand, A read once) ->
+        // columns 0..H-1 = hi hi, H..2H-1 = hi lo; pass 1: A_lo x W2_hi added to columns 0..H-1.  2 x H/8 MMAs instead of
+        // 3 x H/8: an MMA of this size costs ~50 cycles whatever its N (measured: issue stamps of the timeline tool)
+        constexpr uint32_t idesc2 = tc::make_idesc_tf32(128, 2 * H, 0, 0), idesc1 = tc::make_idesc_tf32(128, H, 0, 0);
         const bool leader = tc::elect_one();
         for (int t = 0; t < a.T; ++t) {
             tctile::acquire(&bars[0], (uint32_t)(t & 1));
+            RTL(11, true);
 #pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {           // small products first: A_lo B_hi, A_hi B_lo, A_hi B_hi
-                uint64_t da = tc::make_smem_desc(sbase + (pass == 0 ? oAl : oAh), LBO, SBO, 0);
-                uint64_t db = tc::make_smem_desc(sbase + (pass == 1 ? oBl : oBh), LBO, SBO, 0);
+            for (int pass = 0; pass < 2; ++pass) {
+                uint64_t da = tc::make_smem_desc(sbase + (pass == 0 ? oAh : oAl), LBO, SBO, 0);
+                uint64_t db = tc::make_smem_desc(sbase + oBh, LBO, SBO, 0);
+                const uint32_t idesc = pass == 0 ? idesc2 : idesc1;
 #pragma unroll 2
                 for (int ks = 0; ks < H / 8; ++ks) {
                     if (leader) tc::mma_tf32(tmem, da, db, idesc, (uint32_t)(pass | ks));
+                    if (blockIdx.x == 0 && t == 10 && e == 0) g_roll_tl[16 + pass * (H / 8) + ks] = clock64();
                     da += (uint64_t)((2 * LBO) >> 4);
                     db += (uint64_t)((2 * LBO) >> 4);
                 }
             }
             if (leader) tc::mma_commit(&bars[1]);
+            RTL(15, true);
             __syncwarp();
         }
     } else if (w >= NAG * NQ) {
@@ -674,8 +706,8 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             double gx, gy;
             spread::pair_force(es[2 * ia][e], es[2 * ia + 1][e], es[2 * ib][e], es[2 * ib + 1][e], gx, gy);
             pf[p][e][0] = gx; pf[p][e][1] = gy;
-            block_bar<NBAR>();
-            block_bar<NBAR>();
+            bar_named<NBAR>(5);
+            bar_named<NBAR>(6);
         }
     } else
     for (int t = 0; t < a.T; ++t) {
@@ -722,8 +754,8 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
         }
         tctile::publish(&bars[0]);
         RTL(2, w == 0);
-        // ---- under the MMAs: the buffer stores of the observation (row k by warp k % 4) and the race noise -------------
-        if (live) {
+        // ---- under the MMAs: the buffer stores of the observation (row k by warp k % 4) ------------------------------------
+        if (live && !(a.dbg & 2)) {
 #pragma unroll
             for (int k = 0; k < CMARL_RAW_OBS; ++k)
                 if ((k & 3) == qq) __stcs(a.state + ((size_t)t * 54 + n * CMARL_RAW_OBS + k) * B + b, x[k]);
@@ -736,69 +768,82 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             }
         }
         RTL(1, w == 0);
-        if (qq == 3) {   // warp (n, 3): the race noise of (t, agent n, env)
-            float q[NACT];
-            if (a.noise) {
-#pragma unroll
-                for (int k = 0; k < NACT; ++k)
-                    q[k] = live ? __ldcs(a.noise + (((size_t)t * NAG + n) * NACT + k) * B + b) : 1.0f;
-            } else {
-                philox_exp5(a.seed, episode, (uint32_t)t, (uint32_t)n, (uint32_t)b, q);
-            }
-#pragma unroll
-            for (int k = 0; k < NACT; ++k) qs[n][k][e] = q[k];
-            bar_named<128>(1 + n);
-        } else {
+        // the log race noise of agent qq for the NEXT step: warp (2, qq) -- for H = 32 it has no accumulator columns to
+        // finish, for H = 64 the draw runs while the MMAs do.  (Not the warps (n, 3): they share the issue warp's scheduler,
+        // and Philox + 10 logf under the MMAs starved it -- 1 450 instead of 680 cycles for 12 MMAs, timeline tool.)
+        const bool noisew = n == 2 && qq < 3 && t + 1 < a.T;
+        float lqn[NACT];
+        if (noisew) draw_log_noise(a, episode, t + 1, qq, b, live, lqn);
+        const bool logpw = n == 1 && qq < 3;                 // warp (1, a): log-probability of agent a's action, off the critical path
+        if (qq < 3) {
             // ---- epilogue of agent qq's rows (TMEM quadrant qq), column group n: b2, relu, output layer -----------------
             const int c0 = n * NC0;                          // warp-uniform
             float z[NACT];
 #pragma unroll
             for (int k = 0; k < NACT; ++k) z[k] = 0.0f;
-            tctile::acquire(&bars[1], (uint32_t)(t & 1));
-            RTL(3, w == 0);
-            const uint32_t ta = tmem + ((uint32_t)(32 * qq) << 16) + (uint32_t)c0;
-            uint32_t v0[8], v1[8], v2[8];
             const bool g0 = c0 < H, g2 = NC0 == 24 && c0 + 16 < H;    // H = 64: the last group holds 16 columns; H = 32: none
-            if (g0) { tc::tmem_ld8(ta, v0); tc::tmem_ld8(ta + 8, v1); }
-            if (g2) tc::tmem_ld8(ta + 16, v2);
-            tc::tmem_wait_ld();
-            if (g0) { head8(v0, c0, sB2f, sW3f, z); head8(v1, c0 + 8, sB2f, sW3f, z); }
-            if (g2) head8(v2, c0 + 16, sB2f, sW3f, z);
+            if (g0) {
+                tctile::acquire(&bars[1], (uint32_t)(t & 1));
+                RTL(3, w == 0);
+                const uint32_t ta = tmem + ((uint32_t)(32 * qq) << 16) + (uint32_t)c0;
+                uint32_t v0[8], v1[8], v2[8], u0[8], u1[8], u2[8];
+                tc::tmem_ld8(ta, v0); tc::tmem_ld8(ta + H, u0); tc::tmem_ld8(ta + 8, v1); tc::tmem_ld8(ta + H + 8, u1);
+                if (g2) { tc::tmem_ld8(ta + 16, v2); tc::tmem_ld8(ta + H + 16, u2); }
+                tc::tmem_wait_ld();
+                head8(v0, u0, c0, sB2f, sW3f, z); head8(v1, u1, c0 + 8, sB2f, sW3f, z);
+                if (g2) head8(v2, u2, c0 + 16, sB2f, sW3f, z);
+            }
 #pragma unroll
             for (int k = 0; k < NACT; ++k) zp[qq][n][k][e] = z[k];
             RTL(4, w == 0);
-            bar_named<128>(1 + qq);
+            bar_named<96>(1 + qq);
             RTL(5, w == 0);
-            if (n == 0) {
-                // ---- Categorical sample of agent qq: column-group sums in fixed order, then the exponential race ---------
-                float q[NACT];
+            if (n < 2) {
+                // ---- Categorical sample of agent qq: column-group sums in fixed order, then the race in the log domain.
+                //      Warp (0, qq) publishes the action -- the only thing the physics waits for --, warp (1, qq) evaluates
+                //      the same decision from the same operands and the log-probability, and writes both to the buffer ------
+                float lq[NACT];
 #pragma unroll
                 for (int k = 0; k < NACT; ++k) {
                     z[k] = ((zp[qq][0][k][e] + zp[qq][1][k][e]) + zp[qq][2][k][e]) + sB3f[k];
-                    q[k] = qs[qq][k][e];
+                    lq[k] = qs[qq][k][e];
                 }
-                int action; float lp;
-                race_sample(z, q, action, lp);
-                acts[qq][e] = action;
-                if (live) {
-                    __stcs(a.actions + ((size_t)t * NAG + qq) * B + b, action);
-                    __stcs(a.logp + ((size_t)t * NAG + qq) * B + b, lp);
+                int action; float zsel;
+                sample::race_action_log(z, lq, action, zsel);
+                if (n == 0) {
+                    acts[qq][e] = action;
+                    RTL(6, w == 0);
+                } else {
+                    // reads no env state and produces nothing the physics needs: arrives without waiting -- but only with the
+                    // noise consumed (the decision depends on every value read): warp (2, qq) replaces it behind this barrier
+                    asm volatile("bar.arrive 5, %0;" ::"n"(NBAR), "r"(action) : "memory");
+                    const float lp = sample::race_logp(z, zsel);
+                    if (live) {
+                        __stcs(a.actions + ((size_t)t * NAG + qq) * B + b, action);
+                        __stcs(a.logp + ((size_t)t * NAG + qq) * B + b, lp);
+                    }
                 }
             }
         }
-        RTL(6, w == 0); RTL(9, w == 1);
-        block_bar<NBAR>();
-        RTL(10, w == 1);
+        RTL(9, w == 1);
+        if (!logpw) bar_named<NBAR>(5);
+        RTL(10, w == 3);
+        if (noisew) {   // this step's samplers are done with theirs
+#pragma unroll
+            for (int k = 0; k < NACT; ++k) qs[qq][k][e] = lqn[k];
+        }
         // ---- physics (World.step) -----------------------------------------------------------------------------------
         // (a) last step's team reward from the distance table the contact-force warps wrote before the barrier
-        if (t > 0 && tid < REPB) {
-            const double r = reward_from_table(rd[tid]);
+        //     (warp 8: an epilogue warp that neither samples nor integrates)
+        if (t > 0 && w == 8) {
+            const double r = reward_from_table(rd[e]);
             ep_acc += r;
             if (live) __stcs(a.reward + (size_t)(t - 1) * B + b, (float)r);
         }
-        if (qq == 1) {
-            RTL(12, w == 1);
-            // (c) integration of agent n; forces added in the reference's pair order (0,1),(0,2),(1,2)
+        if (qq == 3) {
+            RTL(12, w == 3);
+            // (c) integration of agent n by warp (n, 3) -- it owns no TMEM quadrant with rows in it, so it is free when the
+            //     action arrives; forces added in the reference's pair order (0,1),(0,2),(1,2)
             const int act = acts[n][e];
             double ux = 0.0, uy = 0.0;
             if (act == 1) ux = -1.0;
@@ -817,16 +862,16 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             // every reader of the old state (the other warps' observations, the pair forces) is behind the barrier above
             es[2 * n][e] = px; es[2 * n + 1][e] = py;
             es[6 + 2 * n][e] = vx; es[6 + 2 * n + 1][e] = vy;
-            RTL(13, w == 1);
+            RTL(13, w == 3);
         }
-        block_bar<NBAR>();
-        RTL(14, w == 1); RTL(7, w == 0);
+        bar_named<NBAR>(6);
+        RTL(14, w == 3); RTL(7, w == 0);
     }
     tc::tcgen05_fence_before();
     __syncthreads();
-    if (w == 15) tc::tmem_dealloc(tmem, H);
-    if (tid < REPB) {
-        const double r = reward_from_table(rd[tid]);
+    if (w == 15) tc::tmem_dealloc(tmem, 2 * H);
+    if (w == 8) {
+        const double r = reward_from_table(rd[e]);
         ep_acc += r;
         if (live) {
             __stcs(a.reward + (size_t)(a.T - 1) * B + b, (float)r);
@@ -952,6 +997,9 @@ size_t actor_smem_bytes() { return (size_t)ActorSmem<H>::oEnd * sizeof(float); }
 extern "C" int cmarl_debug_rollout_timeline(long long* out_host16) {
     return (int)cudaMemcpyFromSymbol(out_host16, g_roll_tl, sizeof(long long) * 16);
 }
+extern "C" int cmarl_debug_rollout_timeline_mma(long long* out_host32) {
+    return (int)cudaMemcpyFromSymbol(out_host32, g_roll_tl, sizeof(long long) * 32, sizeof(long long) * 16);
+}
 
 // generic.cu: the layered kernels behind the same entries when cmarl_ctx.generic is set
 int cmarl_gen_env_reset(cmarl_ctx* ctx, double* env, uint64_t seed, uint64_t episode, cudaStream_t st);
@@ -1043,6 +1091,7 @@ extern "C" int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* 
     a.episode_dev = ctx->episode_dev;
     a.state = state; a.obs = obs; a.actions = actions; a.logp = logp; a.reward = reward; a.ep_return = ep_return;
     a.T = ctx->cfg.n_steps; a.B = ctx->cfg.n_envs; a.O = ctx->cfg.obs_dim;
+    { const char* v = getenv("CMARL_ROLLOUT_DBG"); a.dbg = v ? atoi(v) : 0; }
     const int grid = ceil_div(a.B, REPB);
     cudaStream_t st = as_stream(stream);
     const bool ids = a.O > CMARL_RAW_OBS;

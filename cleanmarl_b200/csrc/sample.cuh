@@ -35,6 +35,31 @@ __device__ __forceinline__ void race_sample(const float (&z)[NACT], const float 
     }
 }
 
+// The same draw for a kernel whose critical path is the ACTION (rollout_tc_kernel): argmax_a p_a / q_a = argmax_a (z_a - log q_a)
+// -- the softmax normalisations of race_sample are a common positive factor and log is monotone; log q_a comes with the
+// noise, off the critical path, so the decision is five subtractions and a compare chain (the two forms can differ only
+// for races closer than a few ulp).  log_prob(action) = z_a - logsumexp(z) with the sum accumulated in race_sample's
+// order: bit-identical to race_sample's logp for the same action.
+__device__ __forceinline__ void race_action_log(const float (&z)[NACT], const float (&lq)[NACT], int& action, float& zsel) {
+    float best = -INFINITY;
+    action = 0;
+    zsel = z[0];
+#pragma unroll
+    for (int a = 0; a < NACT; ++a) {
+        const float r = z[a] - lq[a];
+        if (r > best) { best = r; action = a; zsel = z[a]; }
+    }
+}
+__device__ __forceinline__ float race_logp(const float (&z)[NACT], float zsel) {
+    float mx = z[0];
+#pragma unroll
+    for (int a = 1; a < NACT; ++a) mx = fmaxf(mx, z[a]);
+    float se = 0.0f;
+#pragma unroll
+    for (int a = 0; a < NACT; ++a) se += expf(z[a] - mx);
+    return zsel - (mx + logf(se));
+}
+
 __device__ __forceinline__ void philox_exp5(uint64_t seed, uint64_t episode, uint32_t t, uint32_t n, uint32_t b,
                                             float (&q)[NACT]) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);

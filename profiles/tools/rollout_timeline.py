@@ -12,9 +12,18 @@ v = list(buf)
 # rollout_tc_kernel (default): 2 = L1 + A images published, 1 = buffer stores issued, 3 = layer-2 MMAs complete, 4 = epilogue done;
 # CMARL_ROLLOUT=ffma: the CUDA-core kernel's stages
 names = {0: "S: step start", 1: "S: obs stores done", 2: "S: L1 done", 3: "S: after agent bar 1 / MMAs done", 4: "S: L2+L3 done", 5: "S: after agent bar 2",
-         6: "S: sampling done", 7: "S: step end", 8: "P: step start", 9: "P: before B1", 10: "P: after B1", 11: "P: pair force done",
-         12: "P: after physics bar", 13: "P: integrate done", 14: "P: after B3", 15: "P: dist done"}
+         6: "S: sampling done", 7: "S: step end", 8: "P: step start", 9: "P: before B1", 10: "P: after B1", 11: "P: pair force done / I: operands complete",
+         12: "P: after physics bar", 13: "P: integrate done", 14: "P: after B3", 15: "P: dist done / I: MMAs issued"}
 ev = sorted((v[k], k) for k in names if v[k] > 0)
 t0 = ev[0][0]; prev = t0
 for t, k in ev:
     print(f"{t - t0:8d} (+{t - prev:6d})  {names[k]}"); prev = t
+
+try:
+    buf2 = (C.c_longlong * 32)()
+    lib.cmarl_debug_rollout_timeline_mma(buf2)
+    m = [x for x in buf2 if x > 0]
+    if m:
+        print("MMA issue stamps (cycles after the first):", [x - m[0] for x in m], "first at", m[0] - t0)
+except AttributeError:
+    pass

@@ -12,7 +12,10 @@ out = torch.zeros(2, dtype=torch.int64, device="cuda")
 print("M N A nacc lbo  cycles/MMA(total) cycles/MMA(issue)")
 for (m, n, a_tmem, lbo, sbo, kstep) in ((128, 64, 1, 128, 2048, 256), (128, 32, 1, 128, 2048, 256), (128, 64, 0, 128, 2048, 256),
                                          (64, 32, 0, 144, 4608, 288), (64, 40, 0, 144, 4608, 288), (64, 32, 0, 128, 4096, 256),
-                                         (64, 64, 0, 144, 4608, 288), (128, 128, 1, 128, 2048, 256)):
+                                         (64, 64, 0, 144, 4608, 288), (128, 128, 1, 128, 2048, 256),
+                                         # rollout_tc_kernel's layer 2 (SS, K-major A and B images): H = 32, H = 64, padded variants
+                                         (128, 32, 0, 128, 1024, 256), (128, 64, 0, 128, 2048, 256), (128, 32, 0, 144, 4608, 288),
+                                         (128, 32, 0, 144, 1152, 288), (128, 32, 0, 128, 1040, 256), (128, 32, 0, 128, 1152, 256)):
     for nacc in (1, 2, 4):
         if nacc * n > 384:
             continue
