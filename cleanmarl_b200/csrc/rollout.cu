@@ -149,8 +149,10 @@ template <bool GRU> struct RolloutThreads { static constexpr int N = RTHREADS + 
 constexpr int W1LD = 16;                 // layer-1 rows padded to 16 inputs (14 non-zero observation entries)
 
 // debug timeline of CTA 0, step 10 (clock64): slots 0-7 warp (0,0) [sampler], 8-15 warp (0,1) [physics]
-__device__ long long g_roll_tl[16 + 32];      // + 32: issue stamps of the MMAs (rollout_tc_kernel)
-#define RTL(slot, cond) do { if (blockIdx.x == 0 && t == 10 && e == 0 && (cond)) g_roll_tl[slot] = clock64(); } while (0)
+__device__ long long g_roll_tl[16 + 32 + 32];      // + 32: issue stamps of the MMAs, + 32: arrival of every warp at the two block barriers (rollout_tc_kernel)
+// (a volatile asm with a memory clobber: the plain clock64() was hoisted across bar.sync by the compiler)
+__device__ __forceinline__ long long clock_here() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) :: "memory"); return c; }
+#define RTL(slot, cond) do { if (blockIdx.x == 0 && t == 10 && e == 0 && (cond)) g_roll_tl[slot] = clock_here(); } while (0)
 
 __device__ __forceinline__ void agent_bar(int n) { asm volatile("bar.sync %0, 128;" ::"r"(1 + n) : "memory"); }
 // the per-step block barriers: the actor warps and the contact-force warps arrive from DIFFERENT instructions (warp
@@ -507,20 +509,19 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
 //   the state the previous step left, next to the pair forces, while the actor warps run the network).
 //   Measured on CTA 0 (cycles per step): FFMA layer 2 + output layer 3 480, here see profiles/rollout_timeline_r2.txt.
 // ------------------------------------------------------------------------------------------------
-// log of the Exp(1) race noise of (t, agent n, env b): supplied by the caller or drawn with Philox
-__device__ __forceinline__ void draw_log_noise(const RolloutArgs& a, uint64_t episode, int t, int n, int b, bool live, float (&lq)[NACT]) {
-    float q[NACT];
+// log of the Exp(1) race noise of (t, agent n, env b), supplied by the caller or drawn with Philox: values 0..3 (first Philox
+// block) and value 4 (second block)
+__device__ __forceinline__ void log_noise_block0(const RolloutArgs& a, uint64_t episode, int t, int n, int b, bool live, float (&lq)[4]) {
     if (a.noise) {
 #pragma unroll
-        for (int k = 0; k < NACT; ++k) q[k] = live ? __ldcs(a.noise + (((size_t)t * NAG + n) * NACT + k) * a.B + b) : 1.0f;
-    } else if (a.dbg & 1) {
-#pragma unroll
-        for (int k = 0; k < NACT; ++k) q[k] = 1.0f + k;
+        for (int k = 0; k < 4; ++k) lq[k] = live ? __logf(__ldcs(a.noise + (((size_t)t * NAG + n) * NACT + k) * a.B + b)) : 0.0f;
     } else {
-        philox_exp5(a.seed, episode, (uint32_t)t, (uint32_t)n, (uint32_t)b, q);
+        sample::philox_logexp_block0(a.seed, episode, (uint32_t)t, (uint32_t)n, (uint32_t)b, lq);
     }
-#pragma unroll
-    for (int k = 0; k < NACT; ++k) lq[k] = logf(q[k]);
+}
+__device__ __forceinline__ float log_noise_block1(const RolloutArgs& a, uint64_t episode, int t, int n, int b, bool live) {
+    if (a.noise) return live ? __logf(__ldcs(a.noise + (((size_t)t * NAG + n) * NACT + 4) * a.B + b)) : 0.0f;
+    return sample::philox_logexp_block1(a.seed, episode, (uint32_t)t, (uint32_t)n, (uint32_t)b);
 }
 
 namespace tcroll {
@@ -531,7 +532,7 @@ constexpr int LBO = 128;                                 // next chunk of 4 k
 template <int H_>
 struct L {
     static constexpr int H = H_;
-    static constexpr int NC0 = H == 64 ? 24 : 16;        // columns per epilogue group: 24 / 24 / 16 (H = 64), 16 / 16 / - (H = 32)
+    static constexpr int NC0 = H == 64 ? 24 : 12;        // columns per epilogue group: 24 / 24 / 16 (H = 64), 12 / 12 / 8 (H = 32)
     static constexpr int A_BYTES = 128 * H * 4;          // one A image (hi or lo): 128 rows x H k, K-major core matrices
     static constexpr int B_BYTES = H * H * 4;            // one W2 image
     static constexpr int SBO = (H / 4) * 128;            // next group of 8 rows
@@ -545,16 +546,17 @@ struct L {
     static constexpr int oW3 = oB2 + H * 4;              // f32 [H][8] (5 used)
     static constexpr int oB3 = oW3 + H * 8 * 4;          // f32 [8]
     static constexpr int oZp = oB3 + 32;                 // f32 [NAG][NCG][NACT][32] partial logits
-    static constexpr int oQs = oZp + NAG * NCG * NACT * REPB * 4;   // f32 [NAG][NACT][32] race noise
-    static constexpr int smem_bytes = oQs + NAG * NACT * REPB * 4;
+    static constexpr int oQs = oZp + NAG * NCG * NACT * REPB * 4;   // f32 [2][NAG][NACT][32] log race noise, by step parity
+    static constexpr int smem_bytes = oQs + 2 * NAG * NACT * REPB * 4;
 };
 template <int NT> __device__ __forceinline__ void bar_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
-// b2, relu and the output layer on 8 accumulator columns starting at column j0
+// b2, relu and the output layer on NC accumulator columns starting at column j0
 // (v: hi hi + lo hi products, u: hi lo products)
-__device__ __forceinline__ void head8(const uint32_t (&v)[8], const uint32_t (&u)[8], int j0, const float* sB2f, const float* sW3f,
+template <int NC>
+__device__ __forceinline__ void headn(const uint32_t (&v)[NC], const uint32_t (&u)[NC], int j0, const float* sB2f, const float* sW3f,
                                       float (&z)[NACT]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NC; ++i) {
         const int j = j0 + i;
         const float h2 = fmaxf((__uint_as_float(v[i]) + __uint_as_float(u[i])) + sB2f[j], 0.0f);
         const float4 wv = *reinterpret_cast<const float4*>(sW3f + j * 8);
@@ -583,14 +585,18 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
     const float* sW3f = reinterpret_cast<const float*>(smb + oW3);
     const float* sB3f = reinterpret_cast<const float*>(smb + oB3);
     float (*zp)[NCG][NACT][REPB] = reinterpret_cast<float (*)[NCG][NACT][REPB]>(smb + oZp);
-    float (*qs)[NACT][REPB] = reinterpret_cast<float (*)[NACT][REPB]>(smb + oQs);    // log race noise
+    float (*qs)[NAG][NACT][REPB] = reinterpret_cast<float (*)[NAG][NACT][REPB]>(smb + oQs);    // [step parity] log race noise
     __shared__ double es[18][REPB];
     __shared__ int acts[NAG][REPB];
     __shared__ double pf[3][REPB][2];
     __shared__ double rd[REPB][12];
     const int tid = threadIdx.x;
     const int w = tid >> 5, e = tid & 31;
-    const int n = w >> 2, qq = w & 3;
+    // roles: warps 3, 7, 11 are the contact-force warps (pair p = w / 4), warps 12-14 the actor warps (n = w - 12, qq = 3):
+    // the float64 physics then shares its scheduler (warp id % 4 == 3) only with the issue warp, and the four schedulers
+    // carry about the same number of instructions per step
+    const bool physw = w < NAG * NQ && (w & 3) == 3;
+    const int n = w < NAG * NQ ? w >> 2 : w - NAG * NQ, qq = w < NAG * NQ ? w & 3 : 3;
     const int b = blockIdx.x * REPB + e;
     const bool live = b < a.B;
     const int B = a.B;
@@ -645,18 +651,19 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
         }
         if (tid < 8) fw[oB3 / 4 + tid] = tid < NACT ? __ldcg(P + RL::pB3 + tid) : 0.0f;
     }
-    if (w >= NAG * NQ && w < 15) {     // the race noise of step 0 (step t + 1 is drawn during step t by the warps (2, a))
-        float q[NACT];
-        draw_log_noise(a, episode, 0, w - NAG * NQ, b, live, q);
+    if (physw) {     // the race noise of step 0 (step t + 1 is drawn during step t, below)
+        float q[4];
+        log_noise_block0(a, episode, 0, w >> 2, b, live, q);
 #pragma unroll
-        for (int k = 0; k < NACT; ++k) qs[w - NAG * NQ][k][e] = q[k];
+        for (int k = 0; k < 4; ++k) qs[0][w >> 2][k][e] = q[k];
+        qs[0][w >> 2][4][e] = log_noise_block1(a, episode, 0, w >> 2, b, live);
     }
     tc::fence_proxy_async_smem();
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
-    double ep_acc = 0.0;                                     // warp 8: episode return of env e
+    double ep_acc = 0.0;                                     // warp 3: episode return of env e
 
     if (w == 15) {
         // ================================ MMA issue warp ==================================================
@@ -677,7 +684,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
 #pragma unroll 2
                 for (int ks = 0; ks < H / 8; ++ks) {
                     if (leader) tc::mma_tf32(tmem, da, db, idesc, (uint32_t)(pass | ks));
-                    if (blockIdx.x == 0 && t == 10 && e == 0) g_roll_tl[16 + pass * (H / 8) + ks] = clock64();
+                    if (blockIdx.x == 0 && t == 10 && e == 0) g_roll_tl[16 + pass * (H / 8) + ks] = clock_here();
                     da += (uint64_t)((2 * LBO) >> 4);
                     db += (uint64_t)((2 * LBO) >> 4);
                 }
@@ -686,11 +693,11 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             RTL(15, true);
             __syncwarp();
         }
-    } else if (w >= NAG * NQ) {
+    } else if (physw) {
         // ================================ contact-force warps =============================================
         // pair p = (0,1), (0,2), (1,2) of every env from the positions the previous step left, and (t > 0) that state's
         // distance table for the team reward: tasks 0-8 agent a to landmark l (task = 3 l + a), 9-10 agents 1, 2 to agent 0
-        const int p = w - NAG * NQ;
+        const int p = w >> 2;
         const int ia = (p == 2) ? 1 : 0, ib = (p == 0) ? 1 : 2;
         for (int t = 0; t <= a.T; ++t) {
             if (t > 0) {
@@ -706,7 +713,18 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             double gx, gy;
             spread::pair_force(es[2 * ia][e], es[2 * ia + 1][e], es[2 * ib][e], es[2 * ib + 1][e], gx, gy);
             pf[p][e][0] = gx; pf[p][e][1] = gy;
+            // the second Philox block of agent p's race noise for the NEXT step (see the actor warps)
+            if (t + 1 < a.T) qs[(t + 1) & 1][p][4][e] = log_noise_block1(a, episode, t + 1, p, b, live);
+            RTL(48 + w, true);
             bar_named<NBAR>(5);
+            // last step's team reward from the distance table (complete: every contact-force warp is behind the barrier);
+            // this scheduler is idle while the actor warps integrate
+            if (t > 0 && w == 3) {
+                const double r = reward_from_table(rd[e]);
+                ep_acc += r;
+                if (live) __stcs(a.reward + (size_t)(t - 1) * B + b, (float)r);
+            }
+            RTL(64 + w, true);
             bar_named<NBAR>(6);
         }
     } else
@@ -768,12 +786,17 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             }
         }
         RTL(1, w == 0);
-        // the log race noise of agent qq for the NEXT step: warp (2, qq) -- for H = 32 it has no accumulator columns to
-        // finish, for H = 64 the draw runs while the MMAs do.  (Not the warps (n, 3): they share the issue warp's scheduler,
-        // and Philox + 10 logf under the MMAs starved it -- 1 450 instead of 680 cycles for 12 MMAs, timeline tool.)
-        const bool noisew = n == 2 && qq < 3 && t + 1 < a.T;
-        float lqn[NACT];
-        if (noisew) draw_log_noise(a, episode, t + 1, qq, b, live, lqn);
+        // the log race noise of the NEXT step goes to the other half of the double-buffered table: warp (2, a) draws the first
+        // Philox block of agent a (four values) while the MMAs run -- at H = 32 its share of the epilogue is the shortest --,
+        // the contact-force warp a the second block behind its physics.  (Measured alternatives, timeline tool: on the
+        // warps (n, 3) under the MMAs the draws starved the issue warp on the same scheduler -- 1 450 instead of 680 cycles
+        // for 12 MMAs --; all of it on the contact-force warps or on warp (2, a) made that warp the last at the barrier.)
+        if (n == 2 && qq < 3 && t + 1 < a.T) {
+            float lqn[4];
+            log_noise_block0(a, episode, t + 1, qq, b, live, lqn);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) qs[(t + 1) & 1][qq][k][e] = lqn[k];
+        }
         const bool logpw = n == 1 && qq < 3;                 // warp (1, a): log-probability of agent a's action, off the critical path
         if (qq < 3) {
             // ---- epilogue of agent qq's rows (TMEM quadrant qq), column group n: b2, relu, output layer -----------------
@@ -781,17 +804,24 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             float z[NACT];
 #pragma unroll
             for (int k = 0; k < NACT; ++k) z[k] = 0.0f;
-            const bool g0 = c0 < H, g2 = NC0 == 24 && c0 + 16 < H;    // H = 64: the last group holds 16 columns; H = 32: none
-            if (g0) {
-                tctile::acquire(&bars[1], (uint32_t)(t & 1));
-                RTL(3, w == 0);
-                const uint32_t ta = tmem + ((uint32_t)(32 * qq) << 16) + (uint32_t)c0;
-                uint32_t v0[8], v1[8], v2[8], u0[8], u1[8], u2[8];
-                tc::tmem_ld8(ta, v0); tc::tmem_ld8(ta + H, u0); tc::tmem_ld8(ta + 8, v1); tc::tmem_ld8(ta + H + 8, u1);
-                if (g2) { tc::tmem_ld8(ta + 16, v2); tc::tmem_ld8(ta + H + 16, u2); }
+            tctile::acquire(&bars[1], (uint32_t)(t & 1));
+            RTL(3, w == 0);
+            const uint32_t ta = tmem + ((uint32_t)(32 * qq) << 16) + (uint32_t)c0;
+            uint32_t v0[8], u0[8];
+            tc::tmem_ld8(ta, v0); tc::tmem_ld8(ta + H, u0);
+            if constexpr (H == 64) {       // 24 / 24 / 16 columns
+                uint32_t v1[8], u1[8], v2[8], u2[8];
+                tc::tmem_ld8(ta + 8, v1); tc::tmem_ld8(ta + H + 8, u1);
+                if (n < 2) { tc::tmem_ld8(ta + 16, v2); tc::tmem_ld8(ta + H + 16, u2); }
                 tc::tmem_wait_ld();
-                head8(v0, u0, c0, sB2f, sW3f, z); head8(v1, u1, c0 + 8, sB2f, sW3f, z);
-                if (g2) head8(v2, u2, c0 + 16, sB2f, sW3f, z);
+                headn<8>(v0, u0, c0, sB2f, sW3f, z); headn<8>(v1, u1, c0 + 8, sB2f, sW3f, z);
+                if (n < 2) headn<8>(v2, u2, c0 + 16, sB2f, sW3f, z);
+            } else {                       // 12 / 12 / 8 columns
+                uint32_t v1[4], u1[4];
+                if (n < 2) { tc::tmem_ld4(ta + 8, v1); tc::tmem_ld4(ta + H + 8, u1); }
+                tc::tmem_wait_ld();
+                headn<8>(v0, u0, c0, sB2f, sW3f, z);
+                if (n < 2) headn<4>(v1, u1, c0 + 8, sB2f, sW3f, z);
             }
 #pragma unroll
             for (int k = 0; k < NACT; ++k) zp[qq][n][k][e] = z[k];
@@ -806,7 +836,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
 #pragma unroll
                 for (int k = 0; k < NACT; ++k) {
                     z[k] = ((zp[qq][0][k][e] + zp[qq][1][k][e]) + zp[qq][2][k][e]) + sB3f[k];
-                    lq[k] = qs[qq][k][e];
+                    lq[k] = qs[t & 1][qq][k][e];
                 }
                 int action; float zsel;
                 sample::race_action_log(z, lq, action, zsel);
@@ -817,7 +847,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
                     // reads no env state and produces nothing the physics needs: arrives without waiting -- but only with the
                     // noise consumed (the decision depends on every value read): warp (2, qq) replaces it behind this barrier
                     asm volatile("bar.arrive 5, %0;" ::"n"(NBAR), "r"(action) : "memory");
-                    const float lp = sample::race_logp(z, zsel);
+                    const float lp = sample::race_logp_fast(z, zsel);
                     if (live) {
                         __stcs(a.actions + ((size_t)t * NAG + qq) * B + b, action);
                         __stcs(a.logp + ((size_t)t * NAG + qq) * B + b, lp);
@@ -826,22 +856,12 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             }
         }
         RTL(9, w == 1);
+        RTL(48 + w, true);
         if (!logpw) bar_named<NBAR>(5);
-        RTL(10, w == 3);
-        if (noisew) {   // this step's samplers are done with theirs
-#pragma unroll
-            for (int k = 0; k < NACT; ++k) qs[qq][k][e] = lqn[k];
-        }
+        RTL(10, w == 12);
         // ---- physics (World.step) -----------------------------------------------------------------------------------
-        // (a) last step's team reward from the distance table the contact-force warps wrote before the barrier
-        //     (warp 8: an epilogue warp that neither samples nor integrates)
-        if (t > 0 && w == 8) {
-            const double r = reward_from_table(rd[e]);
-            ep_acc += r;
-            if (live) __stcs(a.reward + (size_t)(t - 1) * B + b, (float)r);
-        }
         if (qq == 3) {
-            RTL(12, w == 3);
+            RTL(12, w == 12);
             // (c) integration of agent n by warp (n, 3) -- it owns no TMEM quadrant with rows in it, so it is free when the
             //     action arrives; forces added in the reference's pair order (0,1),(0,2),(1,2)
             const int act = acts[n][e];
@@ -862,15 +882,16 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             // every reader of the old state (the other warps' observations, the pair forces) is behind the barrier above
             es[2 * n][e] = px; es[2 * n + 1][e] = py;
             es[6 + 2 * n][e] = vx; es[6 + 2 * n + 1][e] = vy;
-            RTL(13, w == 3);
+            RTL(13, w == 12);
         }
+        RTL(64 + w, true);
         bar_named<NBAR>(6);
-        RTL(14, w == 3); RTL(7, w == 0);
+        RTL(14, w == 12); RTL(7, w == 0);
     }
     tc::tcgen05_fence_before();
     __syncthreads();
     if (w == 15) tc::tmem_dealloc(tmem, 2 * H);
-    if (w == 8) {
+    if (w == 3) {
         const double r = reward_from_table(rd[e]);
         ep_acc += r;
         if (live) {
@@ -998,7 +1019,7 @@ extern "C" int cmarl_debug_rollout_timeline(long long* out_host16) {
     return (int)cudaMemcpyFromSymbol(out_host16, g_roll_tl, sizeof(long long) * 16);
 }
 extern "C" int cmarl_debug_rollout_timeline_mma(long long* out_host32) {
-    return (int)cudaMemcpyFromSymbol(out_host32, g_roll_tl, sizeof(long long) * 32, sizeof(long long) * 16);
+    return (int)cudaMemcpyFromSymbol(out_host32, g_roll_tl, sizeof(long long) * 64, sizeof(long long) * 16);
 }
 
 // generic.cu: the layered kernels behind the same entries when cmarl_ctx.generic is set

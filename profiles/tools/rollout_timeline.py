@@ -20,10 +20,12 @@ for t, k in ev:
     print(f"{t - t0:8d} (+{t - prev:6d})  {names[k]}"); prev = t
 
 try:
-    buf2 = (C.c_longlong * 32)()
+    buf2 = (C.c_longlong * 64)()
     lib.cmarl_debug_rollout_timeline_mma(buf2)
-    m = [x for x in buf2 if x > 0]
+    m = [x for x in buf2[:32] if x > 0]
     if m:
         print("MMA issue stamps (cycles after the first):", [x - m[0] for x in m], "first at", m[0] - t0)
+        print("arrival at the barrier behind the sampling, warps 0-14:", [x - t0 for x in buf2[32:47]])
+        print("arrival at the barrier behind the integration, warps 0-14:", [x - t0 for x in buf2[48:63]])
 except AttributeError:
     pass
