@@ -527,7 +527,7 @@ __device__ __forceinline__ float log_noise_block1(const RolloutArgs& a, uint64_t
 namespace tcroll {
 constexpr int NCG = 3;                                   // column groups of the epilogue (one per warp reading a TMEM quadrant)
 constexpr int NTHR = RTHREADS + 32 * RPHYS + 32;         // 12 actor warps, 3 contact-force warps, the issue warp
-constexpr int NBAR = RTHREADS + 32 * RPHYS;              // the per-step block barriers leave the issue warp out
+constexpr int NBAR = RTHREADS + 32 * RPHYS;              // the per-step block barriers leave the issue warp out (it meets the others through mbarriers only)
 constexpr int LBO = 128;                                 // next chunk of 4 k
 template <int H_>
 struct L {
@@ -665,6 +665,11 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
     const uint32_t tmem = *tmem_slot;
     double ep_acc = 0.0;                                     // warp 3: episode return of env e
 
+    // The issue warp runs its own loop (it meets the others through the two mbarriers only); the contact-force and the actor
+    // warps share ONE step loop, so that they meet the step's two block barriers at the same instructions
+    // (compute-sanitizer's synccheck reports warps arriving at a barrier from different instructions as divergent; with the
+    // issue warp inside that loop too, the compiler no longer kept the MMA descriptors in uniform registers: 116 instead of
+    // 50 cycles per MMA).
     if (w == 15) {
         // ================================ MMA issue warp ==================================================
         const uint32_t sbase = tc::smem_u32(smb);
@@ -693,13 +698,18 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             RTL(15, true);
             __syncwarp();
         }
-    } else if (physw) {
-        // ================================ contact-force warps =============================================
-        // pair p = (0,1), (0,2), (1,2) of every env from the positions the previous step left, and (t > 0) that state's
-        // distance table for the team reward: tasks 0-8 agent a to landmark l (task = 3 l + a), 9-10 agents 1, 2 to agent 0
-        const int p = w >> 2;
-        const int ia = (p == 2) ? 1 : 0, ib = (p == 0) ? 1 : 2;
-        for (int t = 0; t <= a.T; ++t) {
+    } else {
+    const int p = w >> 2;                                    // contact-force warp: pair p = (0,1), (0,2), (1,2) of every env
+    const int ia = (p == 2) ? 1 : 0, ib = (p == 0) ? 1 : 2;
+    const bool logpw = w < NAG * NQ && n == 1 && qq < 3;     // warp (1, a): log-probability of agent a's action, off the critical path
+    for (int t = 0; t < a.T; ++t) {
+        double opx = 0.0, opy = 0.0, ovx = 0.0, ovy = 0.0;   // actor warps: this agent's state before the step
+        float zl[NACT] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, zsel = 0.0f;   // warps (0, a), (1, a): the logits of this lane's sample
+        int action = 0;
+        if (physw) {
+            // ================================ contact-force warps =============================================
+            // pair p of every env from the positions the previous step left, and (t > 0) that state's distance table for
+            // the team reward: tasks 0-8 agent a to landmark l (task = 3 l + a), 9-10 agents 1, 2 to agent 0
             if (t > 0) {
 #pragma unroll
                 for (int task = p; task < 11; task += 3) {
@@ -709,14 +719,133 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
                     rd[e][task] = spread::dist2d(es[ea][e], es[ea + 1][e], es[eb][e], es[eb + 1][e]);
                 }
             }
-            if (t == a.T) break;
             double gx, gy;
             spread::pair_force(es[2 * ia][e], es[2 * ia + 1][e], es[2 * ib][e], es[2 * ib + 1][e], gx, gy);
             pf[p][e][0] = gx; pf[p][e][1] = gy;
             // the second Philox block of agent p's race noise for the NEXT step (see the actor warps)
             if (t + 1 < a.T) qs[(t + 1) & 1][p][4][e] = log_noise_block1(a, episode, t + 1, p, b, live);
-            RTL(48 + w, true);
-            bar_named<NBAR>(5);
+        } else {
+            // ================================ actor warps =====================================================
+            // ---- observation before the action (MME:426-430), as in rollout_kernel ---------------------------------------
+            RTL(0, w == 0); RTL(8, w == 1);
+            opx = es[2 * n][e]; opy = es[2 * n + 1][e]; ovx = es[6 + 2 * n][e]; ovy = es[6 + 2 * n + 1][e];
+            const int oj0 = (n == 0) ? 1 : 0, oj1 = (n == 2) ? 1 : 2;
+            float x[CMARL_RAW_OBS];
+            x[0] = (float)ovx; x[1] = (float)ovy; x[2] = (float)opx; x[3] = (float)opy;
+    #pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                x[4 + 2 * l] = (float)(es[12 + 2 * l][e] - opx);
+                x[5 + 2 * l] = (float)(es[13 + 2 * l][e] - opy);
+            }
+            x[10] = (float)(es[2 * oj0][e] - opx); x[11] = (float)(es[2 * oj0 + 1][e] - opy);
+            x[12] = (float)(es[2 * oj1][e] - opx); x[13] = (float)(es[2 * oj1 + 1][e] - opy);
+            x[14] = 0.0f; x[15] = 0.0f; x[16] = 0.0f; x[17] = 0.0f;
+            // ---- layer 1 (this warp's JL units) -> relu -> tf32 hi / lo -> A images, row 32 n + e --------------------------
+            {
+                float acc[JL];
+    #pragma unroll
+                for (int i = 0; i < JL; ++i) acc[i] = sB1f[n * H + j0 + i];
+    #pragma unroll
+                for (int k4 = 0; k4 < W1LD; k4 += 4) {
+    #pragma unroll
+                    for (int i = 0; i < JL; ++i) {
+                        const float4 wv = *reinterpret_cast<const float4*>(sW1f + (j0 + i) * W1LD + k4);   // warp-uniform address
+                        acc[i] = fmaf(x[k4], wv.x, acc[i]); acc[i] = fmaf(x[k4 + 1], wv.y, acc[i]);
+                        acc[i] = fmaf(x[k4 + 2], wv.z, acc[i]); acc[i] = fmaf(x[k4 + 3], wv.w, acc[i]);
+                    }
+                }
+                const int r = 32 * n + e;
+                uint8_t* row = smb + (r >> 3) * SBO + (r & 7) * 16 + (j0 >> 2) * LBO;
+    #pragma unroll
+                for (int c = 0; c < JL / 4; ++c) {
+                    float4 hi, lo;
+                    tc::split_tf32(fmaxf(acc[4 * c], 0.0f), hi.x, lo.x);
+                    tc::split_tf32(fmaxf(acc[4 * c + 1], 0.0f), hi.y, lo.y);
+                    tc::split_tf32(fmaxf(acc[4 * c + 2], 0.0f), hi.z, lo.z);
+                    tc::split_tf32(fmaxf(acc[4 * c + 3], 0.0f), hi.w, lo.w);
+                    *reinterpret_cast<float4*>(row + oAh + c * LBO) = hi;
+                    *reinterpret_cast<float4*>(row + oAl + c * LBO) = lo;
+                }
+            }
+            tctile::publish(&bars[0]);
+            RTL(2, w == 0);
+            // ---- under the MMAs: the buffer stores of the observation (row k by warp k % 4) ------------------------------------
+            if (live && !(a.dbg & 2)) {
+    #pragma unroll
+                for (int k = 0; k < CMARL_RAW_OBS; ++k)
+                    if ((k & 3) == qq) __stcs(a.state + ((size_t)t * 54 + n * CMARL_RAW_OBS + k) * B + b, x[k]);
+                if (a.obs) {
+                    float* o = a.obs + ((size_t)t * NAG + n) * O * B + b;
+    #pragma unroll
+                    for (int k = 0; k < CMARL_RAW_OBS; ++k)
+                        if ((k & 3) == qq) __stcs(o + (size_t)k * B, x[k]);
+                    if (FOLD && qq < NAG) __stcs(o + (size_t)(CMARL_RAW_OBS + qq) * B, qq == n ? 1.0f : 0.0f);
+                }
+            }
+            RTL(1, w == 0);
+            // the log race noise of the NEXT step goes to the other half of the double-buffered table: warp (2, a) draws the first
+            // Philox block of agent a (four values) while the MMAs run -- at H = 32 its share of the epilogue is the shortest --,
+            // the contact-force warp a the second block behind its physics.  (Measured alternatives, timeline tool: on the
+            // warps (n, 3) under the MMAs the draws starved the issue warp on the same scheduler -- 1 450 instead of 680 cycles
+            // for 12 MMAs --; all of it on the contact-force warps or on warp (2, a) made that warp the last at the barrier.)
+            if (n == 2 && qq < 3 && t + 1 < a.T) {
+                float lqn[4];
+                log_noise_block0(a, episode, t + 1, qq, b, live, lqn);
+    #pragma unroll
+                for (int k = 0; k < 4; ++k) qs[(t + 1) & 1][qq][k][e] = lqn[k];
+            }
+            if (qq < 3) {
+                // ---- epilogue of agent qq's rows (TMEM quadrant qq), column group n: b2, relu, output layer -----------------
+                const int c0 = n * NC0;                          // warp-uniform
+                float z[NACT];
+    #pragma unroll
+                for (int k = 0; k < NACT; ++k) z[k] = 0.0f;
+                tctile::acquire(&bars[1], (uint32_t)(t & 1));
+                RTL(3, w == 0);
+                const uint32_t ta = tmem + ((uint32_t)(32 * qq) << 16) + (uint32_t)c0;
+                uint32_t v0[8], u0[8];
+                tc::tmem_ld8(ta, v0); tc::tmem_ld8(ta + H, u0);
+                if constexpr (H == 64) {       // 24 / 24 / 16 columns
+                    uint32_t v1[8], u1[8], v2[8], u2[8];
+                    tc::tmem_ld8(ta + 8, v1); tc::tmem_ld8(ta + H + 8, u1);
+                    if (n < 2) { tc::tmem_ld8(ta + 16, v2); tc::tmem_ld8(ta + H + 16, u2); }
+                    tc::tmem_wait_ld();
+                    headn<8>(v0, u0, c0, sB2f, sW3f, z); headn<8>(v1, u1, c0 + 8, sB2f, sW3f, z);
+                    if (n < 2) headn<8>(v2, u2, c0 + 16, sB2f, sW3f, z);
+                } else {                       // 12 / 12 / 8 columns
+                    uint32_t v1[4], u1[4];
+                    if (n < 2) { tc::tmem_ld4(ta + 8, v1); tc::tmem_ld4(ta + H + 8, u1); }
+                    tc::tmem_wait_ld();
+                    headn<8>(v0, u0, c0, sB2f, sW3f, z);
+                    if (n < 2) headn<4>(v1, u1, c0 + 8, sB2f, sW3f, z);
+                }
+    #pragma unroll
+                for (int k = 0; k < NACT; ++k) zp[qq][n][k][e] = z[k];
+                RTL(4, w == 0);
+                bar_named<96>(1 + qq);
+                RTL(5, w == 0);
+                if (n < 2) {
+                    // ---- Categorical sample of agent qq: column-group sums in fixed order, then the race in the log domain.
+                    //      Warp (0, qq) publishes the action -- the only thing the physics waits for --; warp (1, qq) evaluates
+                    //      the same decision from the same operands and, behind the barrier, while the physics runs, the
+                    //      log-probability, and writes both to the buffer ---------------------------------------------------------
+                    float lq[NACT];
+    #pragma unroll
+                    for (int k = 0; k < NACT; ++k) {
+                        zl[k] = ((zp[qq][0][k][e] + zp[qq][1][k][e]) + zp[qq][2][k][e]) + sB3f[k];
+                        lq[k] = qs[t & 1][qq][k][e];
+                    }
+                    sample::race_action_log(zl, lq, action, zsel);
+                    if (n == 0) acts[qq][e] = action;
+                    RTL(6, w == 0);
+                }
+            }
+        }
+        RTL(9, w == 1);
+        RTL(48 + w, true);
+        bar_named<NBAR>(5);
+        RTL(10, w == 12);
+        if (physw) {
             // last step's team reward from the distance table (complete: every contact-force warp is behind the barrier);
             // this scheduler is idle while the actor warps integrate
             if (t > 0 && w == 3) {
@@ -724,169 +853,53 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
                 ep_acc += r;
                 if (live) __stcs(a.reward + (size_t)(t - 1) * B + b, (float)r);
             }
-            RTL(64 + w, true);
-            bar_named<NBAR>(6);
-        }
-    } else
-    for (int t = 0; t < a.T; ++t) {
-        // ---- observation before the action (MME:426-430), as in rollout_kernel ---------------------------------------
-        RTL(0, w == 0); RTL(8, w == 1);
-        const double opx = es[2 * n][e], opy = es[2 * n + 1][e], ovx = es[6 + 2 * n][e], ovy = es[6 + 2 * n + 1][e];
-        const int oj0 = (n == 0) ? 1 : 0, oj1 = (n == 2) ? 1 : 2;
-        float x[CMARL_RAW_OBS];
-        x[0] = (float)ovx; x[1] = (float)ovy; x[2] = (float)opx; x[3] = (float)opy;
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            x[4 + 2 * l] = (float)(es[12 + 2 * l][e] - opx);
-            x[5 + 2 * l] = (float)(es[13 + 2 * l][e] - opy);
-        }
-        x[10] = (float)(es[2 * oj0][e] - opx); x[11] = (float)(es[2 * oj0 + 1][e] - opy);
-        x[12] = (float)(es[2 * oj1][e] - opx); x[13] = (float)(es[2 * oj1 + 1][e] - opy);
-        x[14] = 0.0f; x[15] = 0.0f; x[16] = 0.0f; x[17] = 0.0f;
-        // ---- layer 1 (this warp's JL units) -> relu -> tf32 hi / lo -> A images, row 32 n + e --------------------------
-        {
-            float acc[JL];
-#pragma unroll
-            for (int i = 0; i < JL; ++i) acc[i] = sB1f[n * H + j0 + i];
-#pragma unroll
-            for (int k4 = 0; k4 < W1LD; k4 += 4) {
-#pragma unroll
-                for (int i = 0; i < JL; ++i) {
-                    const float4 wv = *reinterpret_cast<const float4*>(sW1f + (j0 + i) * W1LD + k4);   // warp-uniform address
-                    acc[i] = fmaf(x[k4], wv.x, acc[i]); acc[i] = fmaf(x[k4 + 1], wv.y, acc[i]);
-                    acc[i] = fmaf(x[k4 + 2], wv.z, acc[i]); acc[i] = fmaf(x[k4 + 3], wv.w, acc[i]);
+        } else {
+            if (logpw) {
+                const float lp = sample::race_logp_fast(zl, zsel);
+                if (live) {
+                    __stcs(a.actions + ((size_t)t * NAG + qq) * B + b, action);
+                    __stcs(a.logp + ((size_t)t * NAG + qq) * B + b, lp);
                 }
             }
-            const int r = 32 * n + e;
-            uint8_t* row = smb + (r >> 3) * SBO + (r & 7) * 16 + (j0 >> 2) * LBO;
-#pragma unroll
-            for (int c = 0; c < JL / 4; ++c) {
-                float4 hi, lo;
-                tc::split_tf32(fmaxf(acc[4 * c], 0.0f), hi.x, lo.x);
-                tc::split_tf32(fmaxf(acc[4 * c + 1], 0.0f), hi.y, lo.y);
-                tc::split_tf32(fmaxf(acc[4 * c + 2], 0.0f), hi.z, lo.z);
-                tc::split_tf32(fmaxf(acc[4 * c + 3], 0.0f), hi.w, lo.w);
-                *reinterpret_cast<float4*>(row + oAh + c * LBO) = hi;
-                *reinterpret_cast<float4*>(row + oAl + c * LBO) = lo;
+            // ---- physics (World.step) -----------------------------------------------------------------------------------
+            if (qq == 3) {
+                RTL(12, w == 12);
+                // (c) integration of agent n by warp (n, 3) -- it owns no TMEM quadrant with rows in it, so it is free when the
+                //     action arrives; forces added in the reference's pair order (0,1),(0,2),(1,2)
+                const int act = acts[n][e];
+                double ux = 0.0, uy = 0.0;
+                if (act == 1) ux = -1.0;
+                if (act == 2) ux = +1.0;
+                if (act == 3) uy = -1.0;
+                if (act == 4) uy = +1.0;
+                double fx = ux * spread::SENSITIVITY + 0.0;
+                double fy = uy * spread::SENSITIVITY + 0.0;
+                const int p1 = (n == 2) ? 1 : 0, p2 = (n == 0) ? 1 : 2;
+                const bool neg1 = (n != 0), neg2 = (n == 2);
+                const double g1x = pf[p1][e][0], g1y = pf[p1][e][1], g2x = pf[p2][e][0], g2y = pf[p2][e][1];
+                fx = (neg1 ? -g1x : g1x) + fx; fy = (neg1 ? -g1y : g1y) + fy;
+                fx = (neg2 ? -g2x : g2x) + fx; fy = (neg2 ? -g2y : g2y) + fy;
+                double px = opx, py = opy, vx = ovx, vy = ovy;
+                spread::integrate(px, py, vx, vy, fx, fy);
+                // every reader of the old state (the other warps' observations, the pair forces) is behind the barrier above
+                es[2 * n][e] = px; es[2 * n + 1][e] = py;
+                es[6 + 2 * n][e] = vx; es[6 + 2 * n + 1][e] = vy;
+                RTL(13, w == 12);
             }
-        }
-        tctile::publish(&bars[0]);
-        RTL(2, w == 0);
-        // ---- under the MMAs: the buffer stores of the observation (row k by warp k % 4) ------------------------------------
-        if (live && !(a.dbg & 2)) {
-#pragma unroll
-            for (int k = 0; k < CMARL_RAW_OBS; ++k)
-                if ((k & 3) == qq) __stcs(a.state + ((size_t)t * 54 + n * CMARL_RAW_OBS + k) * B + b, x[k]);
-            if (a.obs) {
-                float* o = a.obs + ((size_t)t * NAG + n) * O * B + b;
-#pragma unroll
-                for (int k = 0; k < CMARL_RAW_OBS; ++k)
-                    if ((k & 3) == qq) __stcs(o + (size_t)k * B, x[k]);
-                if (FOLD && qq < NAG) __stcs(o + (size_t)(CMARL_RAW_OBS + qq) * B, qq == n ? 1.0f : 0.0f);
-            }
-        }
-        RTL(1, w == 0);
-        // the log race noise of the NEXT step goes to the other half of the double-buffered table: warp (2, a) draws the first
-        // Philox block of agent a (four values) while the MMAs run -- at H = 32 its share of the epilogue is the shortest --,
-        // the contact-force warp a the second block behind its physics.  (Measured alternatives, timeline tool: on the
-        // warps (n, 3) under the MMAs the draws starved the issue warp on the same scheduler -- 1 450 instead of 680 cycles
-        // for 12 MMAs --; all of it on the contact-force warps or on warp (2, a) made that warp the last at the barrier.)
-        if (n == 2 && qq < 3 && t + 1 < a.T) {
-            float lqn[4];
-            log_noise_block0(a, episode, t + 1, qq, b, live, lqn);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) qs[(t + 1) & 1][qq][k][e] = lqn[k];
-        }
-        const bool logpw = n == 1 && qq < 3;                 // warp (1, a): log-probability of agent a's action, off the critical path
-        if (qq < 3) {
-            // ---- epilogue of agent qq's rows (TMEM quadrant qq), column group n: b2, relu, output layer -----------------
-            const int c0 = n * NC0;                          // warp-uniform
-            float z[NACT];
-#pragma unroll
-            for (int k = 0; k < NACT; ++k) z[k] = 0.0f;
-            tctile::acquire(&bars[1], (uint32_t)(t & 1));
-            RTL(3, w == 0);
-            const uint32_t ta = tmem + ((uint32_t)(32 * qq) << 16) + (uint32_t)c0;
-            uint32_t v0[8], u0[8];
-            tc::tmem_ld8(ta, v0); tc::tmem_ld8(ta + H, u0);
-            if constexpr (H == 64) {       // 24 / 24 / 16 columns
-                uint32_t v1[8], u1[8], v2[8], u2[8];
-                tc::tmem_ld8(ta + 8, v1); tc::tmem_ld8(ta + H + 8, u1);
-                if (n < 2) { tc::tmem_ld8(ta + 16, v2); tc::tmem_ld8(ta + H + 16, u2); }
-                tc::tmem_wait_ld();
-                headn<8>(v0, u0, c0, sB2f, sW3f, z); headn<8>(v1, u1, c0 + 8, sB2f, sW3f, z);
-                if (n < 2) headn<8>(v2, u2, c0 + 16, sB2f, sW3f, z);
-            } else {                       // 12 / 12 / 8 columns
-                uint32_t v1[4], u1[4];
-                if (n < 2) { tc::tmem_ld4(ta + 8, v1); tc::tmem_ld4(ta + H + 8, u1); }
-                tc::tmem_wait_ld();
-                headn<8>(v0, u0, c0, sB2f, sW3f, z);
-                if (n < 2) headn<4>(v1, u1, c0 + 8, sB2f, sW3f, z);
-            }
-#pragma unroll
-            for (int k = 0; k < NACT; ++k) zp[qq][n][k][e] = z[k];
-            RTL(4, w == 0);
-            bar_named<96>(1 + qq);
-            RTL(5, w == 0);
-            if (n < 2) {
-                // ---- Categorical sample of agent qq: column-group sums in fixed order, then the race in the log domain.
-                //      Warp (0, qq) publishes the action -- the only thing the physics waits for --, warp (1, qq) evaluates
-                //      the same decision from the same operands and the log-probability, and writes both to the buffer ------
-                float lq[NACT];
-#pragma unroll
-                for (int k = 0; k < NACT; ++k) {
-                    z[k] = ((zp[qq][0][k][e] + zp[qq][1][k][e]) + zp[qq][2][k][e]) + sB3f[k];
-                    lq[k] = qs[t & 1][qq][k][e];
-                }
-                int action; float zsel;
-                sample::race_action_log(z, lq, action, zsel);
-                if (n == 0) {
-                    acts[qq][e] = action;
-                    RTL(6, w == 0);
-                } else {
-                    // reads no env state and produces nothing the physics needs: arrives without waiting -- but only with the
-                    // noise consumed (the decision depends on every value read): warp (2, qq) replaces it behind this barrier
-                    asm volatile("bar.arrive 5, %0;" ::"n"(NBAR), "r"(action) : "memory");
-                    const float lp = sample::race_logp_fast(z, zsel);
-                    if (live) {
-                        __stcs(a.actions + ((size_t)t * NAG + qq) * B + b, action);
-                        __stcs(a.logp + ((size_t)t * NAG + qq) * B + b, lp);
-                    }
-                }
-            }
-        }
-        RTL(9, w == 1);
-        RTL(48 + w, true);
-        if (!logpw) bar_named<NBAR>(5);
-        RTL(10, w == 12);
-        // ---- physics (World.step) -----------------------------------------------------------------------------------
-        if (qq == 3) {
-            RTL(12, w == 12);
-            // (c) integration of agent n by warp (n, 3) -- it owns no TMEM quadrant with rows in it, so it is free when the
-            //     action arrives; forces added in the reference's pair order (0,1),(0,2),(1,2)
-            const int act = acts[n][e];
-            double ux = 0.0, uy = 0.0;
-            if (act == 1) ux = -1.0;
-            if (act == 2) ux = +1.0;
-            if (act == 3) uy = -1.0;
-            if (act == 4) uy = +1.0;
-            double fx = ux * spread::SENSITIVITY + 0.0;
-            double fy = uy * spread::SENSITIVITY + 0.0;
-            const int p1 = (n == 2) ? 1 : 0, p2 = (n == 0) ? 1 : 2;
-            const bool neg1 = (n != 0), neg2 = (n == 2);
-            const double g1x = pf[p1][e][0], g1y = pf[p1][e][1], g2x = pf[p2][e][0], g2y = pf[p2][e][1];
-            fx = (neg1 ? -g1x : g1x) + fx; fy = (neg1 ? -g1y : g1y) + fy;
-            fx = (neg2 ? -g2x : g2x) + fx; fy = (neg2 ? -g2y : g2y) + fy;
-            double px = opx, py = opy, vx = ovx, vy = ovy;
-            spread::integrate(px, py, vx, vy, fx, fy);
-            // every reader of the old state (the other warps' observations, the pair forces) is behind the barrier above
-            es[2 * n][e] = px; es[2 * n + 1][e] = py;
-            es[6 + 2 * n][e] = vx; es[6 + 2 * n + 1][e] = vy;
-            RTL(13, w == 12);
         }
         RTL(64 + w, true);
         bar_named<NBAR>(6);
         RTL(14, w == 12); RTL(7, w == 0);
+    }
+    }
+    if (physw) {   // the distance table of the final state
+#pragma unroll
+        for (int task = w >> 2; task < 11; task += 3) {
+            int ea, eb;
+            if (task < 9) { ea = 2 * (task % 3); eb = 12 + 2 * (task / 3); }
+            else { ea = 2 * (task - 8); eb = 0; }
+            rd[e][task] = spread::dist2d(es[ea][e], es[ea + 1][e], es[eb][e], es[eb + 1][e]);
+        }
     }
     tc::tcgen05_fence_before();
     __syncthreads();
