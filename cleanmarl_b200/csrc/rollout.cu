@@ -149,7 +149,9 @@ template <bool GRU> struct RolloutThreads { static constexpr int N = RTHREADS + 
 constexpr int W1LD = 16;                 // layer-1 rows padded to 16 inputs (14 non-zero observation entries)
 
 // debug timeline of CTA 0, step 10 (clock64): slots 0-7 warp (0,0) [sampler], 8-15 warp (0,1) [physics]
-__device__ long long g_roll_tl[16 + 32 + 32];      // + 32: issue stamps of the MMAs, + 32: arrival of every warp at the two block barriers (rollout_tc_kernel)
+__device__ long long g_roll_tl[16 + 32 + 32 + 8];   // + 8: kernel-level stamps of CTA 0 (entry, predecessor complete, set-up done, steps done, exit)
+#define KTL(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_roll_tl[80 + slot] = clock_here(); } while (0)
+__device__ long long g_roll_tl_unused_;      // + 32: issue stamps of the MMAs, + 32: arrival of every warp at the two block barriers (rollout_tc_kernel)
 // (a volatile asm with a memory clobber: the plain clock64() was hoisted across bar.sync by the compiler)
 __device__ __forceinline__ long long clock_here() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) :: "memory"); return c; }
 #define RTL(slot, cond) do { if (blockIdx.x == 0 && t == 10 && e == 0 && (cond)) g_roll_tl[slot] = clock_here(); } while (0)
@@ -540,7 +542,7 @@ struct L {
     static constexpr int oBar = 0;                       // full, done mbarriers + the TMEM base
     static constexpr int oAh = 128, oAl = oAh + A_BYTES;
     static constexpr int oBh = oAl + A_BYTES, oBl = oBh + B_BYTES;
-    static constexpr int oW1 = oBl + B_BYTES;            // f32 [H][16]
+    static constexpr int oW1 = oBl + B_BYTES;            // f32 [16][H]: input-major, so that one LDS.128 holds four units' weights of one input
     static constexpr int oB1 = oW1 + H * W1LD * 4;       // f32 [3][H] b1 (+ the agent's folded id column)
     static constexpr int oB2 = oB1 + NAG * H * 4;        // f32 [H]
     static constexpr int oW3 = oB2 + H * 4;              // f32 [H][8] (5 used)
@@ -550,19 +552,34 @@ struct L {
     static constexpr int smem_bytes = oQs + 2 * NAG * NACT * REPB * 4;
 };
 template <int NT> __device__ __forceinline__ void bar_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+// two IEEE fp32 FMAs in one instruction (FFMA2): the kernel is bound by instruction issue, not by the FMA pipe; each half
+// rounds like fmaf, so results are bit-identical to the scalar form
+__device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
 // b2, relu and the output layer on NC accumulator columns starting at column j0
 // (v: hi hi + lo hi products, u: hi lo products)
 template <int NC>
 __device__ __forceinline__ void headn(const uint32_t (&v)[NC], const uint32_t (&u)[NC], int j0, const float* sB2f, const float* sW3f,
                                       float (&z)[NACT]) {
+    float2 z01 = make_float2(z[0], z[1]), z23 = make_float2(z[2], z[3]);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
         const int j = j0 + i;
         const float h2 = fmaxf((__uint_as_float(v[i]) + __uint_as_float(u[i])) + sB2f[j], 0.0f);
         const float4 wv = *reinterpret_cast<const float4*>(sW3f + j * 8);
-        z[0] = fmaf(h2, wv.x, z[0]); z[1] = fmaf(h2, wv.y, z[1]); z[2] = fmaf(h2, wv.z, z[2]); z[3] = fmaf(h2, wv.w, z[3]);
+        z01 = ffma2(h2, make_float2(wv.x, wv.y), z01);
+        z23 = ffma2(h2, make_float2(wv.z, wv.w), z23);
         z[4] = fmaf(h2, sW3f[j * 8 + 4], z[4]);
     }
+    z[0] = z01.x; z[1] = z01.y; z[2] = z23.x; z[3] = z23.y;
 }
 }  // namespace tcroll
 
@@ -602,6 +619,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
     const int B = a.B;
     const int j0 = qq * JL;
 
+    KTL(0);
     // ---- set-up: what touches no global memory first (runs under the tail of the launch in front) ----------------------
     for (int i = tid * 16; i < 2 * A_BYTES; i += NTHR * 16) *reinterpret_cast<uint4*>(smb + oAh + i) = make_uint4(0, 0, 0, 0);   // rows 96..127 stay zero
     if (tid == 0) {
@@ -610,7 +628,9 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
         tc::fence_mbar_init();
     }
     if (w == 15) tc::tmem_alloc(tmem_slot, 2 * H);       // D = A_hi W2_hi^T + A_lo W2_hi^T | A_hi W2_lo^T
+    KTL(1);
     pdl_wait_then_trigger();
+    KTL(2);
     const uint64_t episode = a.episode_dev ? *a.episode_dev : a.episode;
     CMARL_STRIDED(i, 18 * REPB, NTHR) {
         const int r = i / REPB, c = i - r * REPB;
@@ -621,7 +641,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
         const float* __restrict__ P = a.actor;
         float* fw = reinterpret_cast<float*>(smb);
         CMARL_STRIDED(i, H * W1LD, NTHR) {
-            const int j = i / W1LD, k = i - j * W1LD;
+            const int k = i / H, j = i - k * H;
             fw[oW1 / 4 + i] = (k < CMARL_RAW_OBS - 4) ? __ldcg(P + RL::pW1 + j * O + k) : 0.0f;
         }
         CMARL_STRIDED(i, NAG * H, NTHR) {
@@ -662,6 +682,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
+    KTL(3);
     const uint32_t tmem = *tmem_slot;
     double ep_acc = 0.0;                                     // warp 3: episode return of env e
 
@@ -732,7 +753,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             const int oj0 = (n == 0) ? 1 : 0, oj1 = (n == 2) ? 1 : 2;
             float x[CMARL_RAW_OBS];
             x[0] = (float)ovx; x[1] = (float)ovy; x[2] = (float)opx; x[3] = (float)opy;
-    #pragma unroll
+#pragma unroll
             for (int l = 0; l < 3; ++l) {
                 x[4 + 2 * l] = (float)(es[12 + 2 * l][e] - opx);
                 x[5 + 2 * l] = (float)(es[13 + 2 * l][e] - opy);
@@ -742,21 +763,25 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             x[14] = 0.0f; x[15] = 0.0f; x[16] = 0.0f; x[17] = 0.0f;
             // ---- layer 1 (this warp's JL units) -> relu -> tf32 hi / lo -> A images, row 32 n + e --------------------------
             {
-                float acc[JL];
-    #pragma unroll
-                for (int i = 0; i < JL; ++i) acc[i] = sB1f[n * H + j0 + i];
-    #pragma unroll
-                for (int k4 = 0; k4 < W1LD; k4 += 4) {
-    #pragma unroll
-                    for (int i = 0; i < JL; ++i) {
-                        const float4 wv = *reinterpret_cast<const float4*>(sW1f + (j0 + i) * W1LD + k4);   // warp-uniform address
-                        acc[i] = fmaf(x[k4], wv.x, acc[i]); acc[i] = fmaf(x[k4 + 1], wv.y, acc[i]);
-                        acc[i] = fmaf(x[k4 + 2], wv.z, acc[i]); acc[i] = fmaf(x[k4 + 3], wv.w, acc[i]);
+                // pairs of units advance together (FFMA2); per unit the inputs are added in ascending order, as before
+                float2 acc2[JL / 2];
+#pragma unroll
+                for (int i = 0; i < JL / 2; ++i) acc2[i] = *reinterpret_cast<const float2*>(sB1f + n * H + j0 + 2 * i);
+#pragma unroll
+                for (int k = 0; k < CMARL_RAW_OBS - 4; ++k) {                       // x[14..17] == 0
+#pragma unroll
+                    for (int c = 0; c < JL / 4; ++c) {
+                        const float4 wv = *reinterpret_cast<const float4*>(sW1f + k * H + j0 + 4 * c);   // warp-uniform address
+                        acc2[2 * c] = ffma2(x[k], make_float2(wv.x, wv.y), acc2[2 * c]);
+                        acc2[2 * c + 1] = ffma2(x[k], make_float2(wv.z, wv.w), acc2[2 * c + 1]);
                     }
                 }
+                float acc[JL];
+#pragma unroll
+                for (int i = 0; i < JL / 2; ++i) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
                 const int r = 32 * n + e;
                 uint8_t* row = smb + (r >> 3) * SBO + (r & 7) * 16 + (j0 >> 2) * LBO;
-    #pragma unroll
+#pragma unroll
                 for (int c = 0; c < JL / 4; ++c) {
                     float4 hi, lo;
                     tc::split_tf32(fmaxf(acc[4 * c], 0.0f), hi.x, lo.x);
@@ -771,12 +796,12 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             RTL(2, w == 0);
             // ---- under the MMAs: the buffer stores of the observation (row k by warp k % 4) ------------------------------------
             if (live && !(a.dbg & 2)) {
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < CMARL_RAW_OBS; ++k)
                     if ((k & 3) == qq) __stcs(a.state + ((size_t)t * 54 + n * CMARL_RAW_OBS + k) * B + b, x[k]);
                 if (a.obs) {
                     float* o = a.obs + ((size_t)t * NAG + n) * O * B + b;
-    #pragma unroll
+#pragma unroll
                     for (int k = 0; k < CMARL_RAW_OBS; ++k)
                         if ((k & 3) == qq) __stcs(o + (size_t)k * B, x[k]);
                     if (FOLD && qq < NAG) __stcs(o + (size_t)(CMARL_RAW_OBS + qq) * B, qq == n ? 1.0f : 0.0f);
@@ -791,14 +816,14 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             if (n == 2 && qq < 3 && t + 1 < a.T) {
                 float lqn[4];
                 log_noise_block0(a, episode, t + 1, qq, b, live, lqn);
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < 4; ++k) qs[(t + 1) & 1][qq][k][e] = lqn[k];
             }
             if (qq < 3) {
                 // ---- epilogue of agent qq's rows (TMEM quadrant qq), column group n: b2, relu, output layer -----------------
                 const int c0 = n * NC0;                          // warp-uniform
                 float z[NACT];
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < NACT; ++k) z[k] = 0.0f;
                 tctile::acquire(&bars[1], (uint32_t)(t & 1));
                 RTL(3, w == 0);
@@ -819,7 +844,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
                     headn<8>(v0, u0, c0, sB2f, sW3f, z);
                     if (n < 2) headn<4>(v1, u1, c0 + 8, sB2f, sW3f, z);
                 }
-    #pragma unroll
+#pragma unroll
                 for (int k = 0; k < NACT; ++k) zp[qq][n][k][e] = z[k];
                 RTL(4, w == 0);
                 bar_named<96>(1 + qq);
@@ -830,7 +855,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
                     //      the same decision from the same operands and, behind the barrier, while the physics runs, the
                     //      log-probability, and writes both to the buffer ---------------------------------------------------------
                     float lq[NACT];
-    #pragma unroll
+#pragma unroll
                     for (int k = 0; k < NACT; ++k) {
                         zl[k] = ((zp[qq][0][k][e] + zp[qq][1][k][e]) + zp[qq][2][k][e]) + sB3f[k];
                         lq[k] = qs[t & 1][qq][k][e];
@@ -901,6 +926,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
             rd[e][task] = spread::dist2d(es[ea][e], es[ea + 1][e], es[eb][e], es[eb + 1][e]);
         }
     }
+    KTL(4);
     tc::tcgen05_fence_before();
     __syncthreads();
     if (w == 15) tc::tmem_dealloc(tmem, 2 * H);
@@ -917,6 +943,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
         const int bb = blockIdx.x * REPB + c;
         if (bb < B) a.env[(size_t)r * B + bb] = es[r][c];
     }
+    KTL(5);
 }
 
 // ---- K2 alone ------------------------------------------------------------------------------
@@ -1032,7 +1059,7 @@ extern "C" int cmarl_debug_rollout_timeline(long long* out_host16) {
     return (int)cudaMemcpyFromSymbol(out_host16, g_roll_tl, sizeof(long long) * 16);
 }
 extern "C" int cmarl_debug_rollout_timeline_mma(long long* out_host32) {
-    return (int)cudaMemcpyFromSymbol(out_host32, g_roll_tl, sizeof(long long) * 64, sizeof(long long) * 16);
+    return (int)cudaMemcpyFromSymbol(out_host32, g_roll_tl, sizeof(long long) * 72, sizeof(long long) * 16);
 }
 
 // generic.cu: the layered kernels behind the same entries when cmarl_ctx.generic is set

@@ -144,7 +144,10 @@ int cmarl_env_step(cmarl_ctx* ctx, double* env, const int32_t* actions, float* s
  *   state, actions, logp, reward   outputs in the device layout above
  *   obs     optional output [T][N][O][B] (NULL to skip; K7 rebuilds it from state)
  *   ep_return f64 [B]   sum over t of the team reward (MME:433), optional
- * `env` holds the start state on entry and the final state on exit. */
+ * `env` holds the start state on entry and the final state on exit.
+ * MLP actor (hidden 32 / 64): rollout_tc_kernel, layer 2 on tcgen05 (3xTF32) and the exponential race decided in the log
+ * domain (argmax_a z_a - log q_a == argmax_a softmax(z)_a / q_a up to races closer than a few ulp); the environment
+ * variable CMARL_ROLLOUT=ffma selects the CUDA-core kernel with the reference's form of the race (read at every call). */
 int cmarl_rollout(cmarl_ctx* ctx, const float* actor_params, double* env, const float* noise,
                   uint64_t seed, uint64_t episode,
                   float* state, float* obs, int32_t* actions, float* logp, float* reward,

@@ -20,12 +20,15 @@ for t, k in ev:
     print(f"{t - t0:8d} (+{t - prev:6d})  {names[k]}"); prev = t
 
 try:
-    buf2 = (C.c_longlong * 64)()
+    buf2 = (C.c_longlong * 72)()
     lib.cmarl_debug_rollout_timeline_mma(buf2)
     m = [x for x in buf2[:32] if x > 0]
     if m:
         print("MMA issue stamps (cycles after the first):", [x - m[0] for x in m], "first at", m[0] - t0)
         print("arrival at the barrier behind the sampling, warps 0-14:", [x - t0 for x in buf2[32:47]])
         print("arrival at the barrier behind the integration, warps 0-14:", [x - t0 for x in buf2[48:63]])
+        k = list(buf2[64:70])
+        print("kernel level (cycles after entry): before the dependency wait %d, predecessor complete %d, set-up done %d, 25 steps done %d, exit %d"
+              % tuple(x - k[0] for x in k[1:]))
 except AttributeError:
     pass

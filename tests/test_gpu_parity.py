@@ -269,9 +269,10 @@ def test_actor_act_vs_reference_sample(cm, golden):
 
 
 # ----------------------------------------------------------------------------------------- K1+K2+K3
+@pytest.mark.parametrize("hid", [32, 64])
 @pytest.mark.parametrize("path", ["tc", "ffma"])
 @pytest.mark.parametrize("B", [96, 1000])
-def test_rollout_vs_oracle(cm, B, path, monkeypatch):
+def test_rollout_vs_oracle(cm, B, path, hid, monkeypatch):
     """Device rollout (layer 2 on the tensor cores: rollout_tc_kernel, the default; CUDA-core rollout_kernel) vs the
     float64 oracle env + oracle actor, input driven (start positions and race
     noise supplied).  Physics: the oracle env replays the DEVICE actions open loop -> observations within
@@ -280,8 +281,8 @@ def test_rollout_vs_oracle(cm, B, path, monkeypatch):
     from cleanmarl_b200 import engine as E
     monkeypatch.setenv("CMARL_ROLLOUT", path)
     Tn = 25
-    actor, critic = om.build_networks(1)
-    eng = make_engine(cm, B)
+    actor, critic = om.build_networks(1, actor_hidden=hid)
+    eng = make_engine(cm, B, actor_hidden=hid)
     dev = eng.device
     rng = np.random.default_rng(B)
     pos0 = rng.uniform(-1, 1, (B, 3, 2))
