@@ -129,10 +129,14 @@ __device__ __forceinline__ void issue_ss(bool leader, uint32_t d, uint32_t a, ui
 // ------------------------------------------------------------------------------------------------
 // Every global load of a thread is issued before the first value is used: as a plain strided loop the compiler keeps one
 // load in flight per iteration, i.e. ~27 serial L2 round trips (~12 us) in front of the critic chain's first tile.
+// A warp fills one core matrix (8 rows x 4 k = 128 contiguous bytes) per round: lane = (row l & 7, k l >> 3), so the hi / lo
+// stores are conflict-free (consecutive k per lane, the first mapping, put 8 lanes on every bank: the 31 k scalar stores of
+// the critic's images were most of its 10.5 k-cycle set-up) and a load instruction still covers whole 16-byte pieces of 8 rows.
 template <class C>
 __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
-    constexpr int H = C::H, K1P = C::K1P, NT = 288;
-    constexpr int N1 = (H * K1P + NT - 1) / NT, N2 = (H * H + NT - 1) / NT, N3 = (H * 8 + NT - 1) / NT;
+    constexpr int H = C::H, K1P = C::K1P, NT = 288, NW = NT / 32;
+    constexpr int M1 = (H / 8) * (K1P / 4), M2 = (H / 8) * (H / 4);          // core matrices of the W1 / W2 images
+    constexpr int N1 = (M1 + NW - 1) / NW, N2 = (M2 + NW - 1) / NW, N3 = (H * 8 + NT - 1) / NT;
     static_assert(4 * H <= NT, "one b1 element per thread");
     const float* P = nd.params;
     const int in_dim = nd.in_dim;
@@ -143,16 +147,20 @@ __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
     const float* W3 = b2 + H;
     const float* b3 = W3 + nd.out_dim * H;
     const int tid = threadIdx.x;
+    if (tid >= NT) return;                       // the idle warps of the three-warpgroup launch
+    const int wi = tid >> 5, jl = tid & 7, kk = (tid & 31) >> 3;
+    const int eo = jl * 16 + kk * 4;             // byte offset of this lane's element inside a core matrix
     float w1[N1], w2[N2], w3[N3], vb1 = 0.0f, vid = 0.0f, vb2 = 0.0f, vb3 = 0.0f;
 #pragma unroll
     for (int r = 0; r < N1; ++r) {
-        const int i = tid + r * NT, j = i / K1P, k = i - j * K1P;
-        w1[r] = (i < H * K1P && k < nd.in_rows) ? __ldcg(W1 + j * in_dim + k) : 0.0f;
+        const int m = wi + r * NW, jg = m / (K1P / 4), kc = m - jg * (K1P / 4);
+        const int j = 8 * jg + jl, k = 4 * kc + kk;
+        w1[r] = (m < M1 && k < nd.in_rows) ? __ldcg(W1 + j * in_dim + k) : 0.0f;
     }
 #pragma unroll
     for (int r = 0; r < N2; ++r) {
-        const int i = tid + r * NT;
-        w2[r] = i < H * H ? __ldcg(W2 + i) : 0.0f;
+        const int m = wi + r * NW, jg = m / (H / 4), kc = m - jg * (H / 4);
+        w2[r] = m < M2 ? __ldcg(W2 + (8 * jg + jl) * H + 4 * kc + kk) : 0.0f;
     }
 #pragma unroll
     for (int r = 0; r < N3; ++r) {
@@ -169,26 +177,27 @@ __device__ void load_weights_tc(uint8_t* sm, const NetDesc& nd, int n_groups) {
 
 #pragma unroll
     for (int r = 0; r < N1; ++r) {
-        const int i = tid + r * NT, j = i / K1P, k = i - j * K1P;
-        if (i < H * K1P) {
+        const int m = wi + r * NW;
+        if (m < M1) {
             float hi, lo;
             tc::split_tf32(w1[r], hi, lo);
-            const int o = kmaj(j, k, K1P);
+            const int o = m * 128 + eo;                      // == kmaj(j, k, K1P)
             *reinterpret_cast<float*>(sm + C::oW1 + o) = hi;
             *reinterpret_cast<float*>(sm + C::oW1 + C::szW1 + o) = lo;
         }
     }
 #pragma unroll
     for (int r = 0; r < N2; ++r) {
-        const int i = tid + r * NT, j = i / H, k = i - j * H;
-        if (i < H * H) {
+        const int m = wi + r * NW;
+        if (m < M2) {
             float hi, lo;
             tc::split_tf32(w2[r], hi, lo);
-            const int o = kmaj(j, k, H);                     // B of F2: N = j, K = k
+            const int o = m * 128 + eo;                      // B of F2: N = j, K = k: kmaj(j, k, H)
             *reinterpret_cast<float*>(sm + C::oW2 + o) = hi;
             *reinterpret_cast<float*>(sm + C::oW2 + C::szW2 + o) = lo;
             if (C::TRAIN) {
-                const int ot = kmaj(k, j, H);                // B of B1: N = k, K = j
+                const int jg = m / (H / 4), kc = m - jg * (H / 4);
+                const int ot = kmaj(4 * kc + kk, 8 * jg + jl, H);   // B of B1: N = k, K = j
                 *reinterpret_cast<float*>(sm + C::oW2T + ot) = hi;
                 *reinterpret_cast<float*>(sm + C::oW2T + C::szW2 + ot) = lo;
             }
