@@ -149,7 +149,7 @@ template <bool GRU> struct RolloutThreads { static constexpr int N = RTHREADS + 
 constexpr int W1LD = 16;                 // layer-1 rows padded to 16 inputs (14 non-zero observation entries)
 
 // debug timeline of CTA 0, step 10 (clock64): slots 0-7 warp (0,0) [sampler], 8-15 warp (0,1) [physics]
-__device__ long long g_roll_tl[16 + 32 + 32 + 8];   // + 8: kernel-level stamps of CTA 0 (entry, predecessor complete, set-up done, steps done, exit)
+__device__ long long g_roll_tl[16 + 32 + 32 + 8 + 32];   // + 8: kernel-level stamps of CTA 0 (entry, predecessor complete, set-up done, steps done, exit)
 #define KTL(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_roll_tl[80 + slot] = clock_here(); } while (0)
 __device__ long long g_roll_tl_unused_;      // + 32: issue stamps of the MMAs, + 32: arrival of every warp at the two block barriers (rollout_tc_kernel)
 // (a volatile asm with a memory clobber: the plain clock64() was hoisted across bar.sync by the compiler)
@@ -915,6 +915,7 @@ __global__ void __launch_bounds__(tcroll::NTHR) rollout_tc_kernel(RolloutArgs a)
         RTL(64 + w, true);
         bar_named<NBAR>(6);
         RTL(14, w == 12); RTL(7, w == 0);
+        if (blockIdx.x == 0 && tid == 0 && t < 32) g_roll_tl[88 + t] = clock_here();     // end of every step, warp 0
     }
     }
     if (physw) {   // the distance table of the final state
@@ -1059,7 +1060,7 @@ extern "C" int cmarl_debug_rollout_timeline(long long* out_host16) {
     return (int)cudaMemcpyFromSymbol(out_host16, g_roll_tl, sizeof(long long) * 16);
 }
 extern "C" int cmarl_debug_rollout_timeline_mma(long long* out_host32) {
-    return (int)cudaMemcpyFromSymbol(out_host32, g_roll_tl, sizeof(long long) * 72, sizeof(long long) * 16);
+    return (int)cudaMemcpyFromSymbol(out_host32, g_roll_tl, sizeof(long long) * 104, sizeof(long long) * 16);
 }
 
 // generic.cu: the layered kernels behind the same entries when cmarl_ctx.generic is set

@@ -20,7 +20,7 @@ for t, k in ev:
     print(f"{t - t0:8d} (+{t - prev:6d})  {names[k]}"); prev = t
 
 try:
-    buf2 = (C.c_longlong * 72)()
+    buf2 = (C.c_longlong * 104)()
     lib.cmarl_debug_rollout_timeline_mma(buf2)
     m = [x for x in buf2[:32] if x > 0]
     if m:
@@ -30,5 +30,7 @@ try:
         k = list(buf2[64:70])
         print("kernel level (cycles after entry): before the dependency wait %d, predecessor complete %d, set-up done %d, 25 steps done %d, exit %d"
               % tuple(x - k[0] for x in k[1:]))
+        st = [k[3]] + [x for x in buf2[72:104] if x > 0]
+        print("cycles of every step (warp 0):", [b - a for a, b in zip(st, st[1:])])
 except AttributeError:
     pass
