@@ -75,7 +75,10 @@ struct TCfg {
     static constexpr int pS2 = nW2 + 1, pS1 = nW1 + 1;
     static_assert(!TRAIN || (H * (pS2 + pS1)) * 4 <= 2 * A_S_BYTES, "flush scratch fits the A images");
 
-    static constexpr int CTAS_PER_SM = smem_bytes <= 113 * 1024 ? 2 : 1;   // two co-resident CTAs double the warps that hide latency
+    // two co-resident CTAs double the warps that hide latency -- if BOTH fit: a CTA that needs more than half of the SM's 512
+    // TMEM columns makes its neighbour wait in tcgen05.alloc until it has exited (the 64-wide critic forward, 368 -> 512
+    // columns, ran as two consecutive waves of 148 CTAs, each paying the 12 k-cycle set-up for three tiles: 31 us)
+    static constexpr int CTAS_PER_SM = (smem_bytes <= 113 * 1024 && TMEM_COLS <= 256) ? 2 : 1;
 };
 
 // ------------------------------------------------------------------------------------------------

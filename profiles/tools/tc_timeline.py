@@ -32,3 +32,7 @@ def critic_train():
 run(critic_train,"ppo_epoch_grads (timeline = last kernel writing: critic train H=64 K=56)")
 
 run(critic_train,"actor train H=32 K=24 (policy head)",2)
+
+def critic_forward():
+    eng.critic_values(tr.net.critic, b["values"], state=b["state"])
+run(critic_forward,"critic forward (cmarl_critic_values: TCfg<64,56,0,1>, 296 CTAs; stamps of tile 1 of CTA 0)")
