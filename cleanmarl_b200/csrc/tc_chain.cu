@@ -268,6 +268,33 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     if (warp == 8) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
     // the grid in front of this one (and, transitively, everything before it) has completed past this point
     if (!src.indep) pdl_wait_then_trigger();
+    // compute thread (warp < 8): TMEM quadrant q, column half hf, sample s of the tile
+    const int q = warp & 3, hf = warp >> 2;
+    const int s = q * 32 + lane;                                        // sample within the tile = TMEM lane
+    // X chunks owned by this thread: chunk c = 2 i + hf, i < NXO (chunks >= NCX do not exist)
+    float xr[NXO * 8];
+    auto load_x = [&](int u) {
+        int bt, r, t, g;
+        fast_divmod(u, tiles_b, inv_tb, r, bt);
+        fast_divmod(r, src.G, inv_g, t, g);
+        const int b = bt * M + s;
+        // 32-bit row offsets from one 64-bit base and one bound per thread: ~5 instructions per load (the 64-bit
+        // products and double predicates of the obvious form were 14, a fifth of the critic kernel's instructions)
+        const float* xp = src.x + (size_t)t * src.stride_t + (size_t)g * src.stride_g + b + (size_t)(8 * hf) * src.B;
+        const uint32_t step = (uint32_t)src.B;
+        const int rmax = (b < src.nb) ? nd.in_rows - 8 * hf : 0;     // this thread reads rows 16 i + e < rmax of its half
+#pragma unroll
+        for (int i = 0; i < NXO; ++i) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int rr = 16 * i + e;
+                xr[i * 8 + e] = (rr < rmax) ? __ldcg(xp + (uint32_t)rr * step) : 0.0f;
+            }
+        }
+    };
+    // the first tile's rows are requested BEFORE the weights: their DRAM latency (5-6 k cycles between set-up and the first
+    // tile's start, profiles/tc_timeline_r2.txt) then runs under the set-up instead of behind it
+    if (warp < 8 && (int)blockIdx.x < units) load_x(blockIdx.x);
     load_weights_tc<C>(sm, nd, src.G);
     __syncthreads();
     if (TRAIN && tid < M) {
@@ -349,8 +376,6 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
     } else {
         if (C::CTAS_PER_SM == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         // ================================ compute warps ====================================================
-        const int q = warp & 3, hf = warp >> 2;
-        const int s = q * 32 + lane;                                    // sample within the tile = TMEM lane
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         const float* fb1 = reinterpret_cast<const float*>(sm + C::oB1);
         const float* fb2 = reinterpret_cast<const float*>(sm + C::oB2);
@@ -374,28 +399,6 @@ tc_chain_kernel(NetDesc nd, TileSrc src, typename Head::Args ha, float* __restri
 #pragma unroll
         for (int k = 0; k < Head::NSTAT; ++k) st[k] = 0.0f;
 
-        // X chunks owned by this thread: chunk c = 2 i + hf, i < NXO (chunks >= NCX do not exist)
-        float xr[NXO * 8];
-        auto load_x = [&](int u) {
-            int bt, r, t, g;
-            fast_divmod(u, tiles_b, inv_tb, r, bt);
-            fast_divmod(r, src.G, inv_g, t, g);
-            const int b = bt * M + s;
-            // 32-bit row offsets from one 64-bit base and one bound per thread: ~5 instructions per load (the 64-bit
-            // products and double predicates of the obvious form were 14, a fifth of the critic kernel's instructions)
-            const float* xp = src.x + (size_t)t * src.stride_t + (size_t)g * src.stride_g + b + (size_t)(8 * hf) * src.B;
-            const uint32_t step = (uint32_t)src.B;
-            const int rmax = (b < src.nb) ? nd.in_rows - 8 * hf : 0;     // this thread reads rows 16 i + e < rmax of its half
-#pragma unroll
-            for (int i = 0; i < NXO; ++i) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int rr = 16 * i + e;
-                    xr[i * 8 + e] = (rr < rmax) ? __ldcg(xp + (uint32_t)rr * step) : 0.0f;
-                }
-            }
-        };
-        if ((int)blockIdx.x < units) load_x(blockIdx.x);
 
         // X stage: the prefetched rows (xr) -> split -> TMEM X columns, hand-off to the issuer (F1), then prefetch the
         // rows of the tile after.  It runs one tile AHEAD of the rest of the chain: as soon as the current tile no longer
