@@ -42,6 +42,30 @@ def test_g3_categorical_sample_is_exponential_race(golden):
     assert not ((~g["avail"]) & (np.eye(5, dtype=bool)[g["actions"]])).any()
 
 
+def test_log_domain_race_is_the_same_decision(golden):
+    """rollout_tc_kernel decides the exponential race as argmax_a (z_a - log q_a) instead of the reference's
+    argmax_a softmax(z)_a / q_a (MME:172-176 -> torch.multinomial): the same decision on the reference's own G3 draws
+    (the unmodified Actor.act under the reference's seed) and on 10^6 random races, up to races closer than a few ulp;
+    log_prob = z_a - logsumexp(z) equals Categorical.log_prob to fp32 round-off."""
+    g = golden("g3_sample")
+    logits, q = T(g["logits"]), T(g["q"])
+    a_log = torch.argmax(logits - torch.log(q), dim=-1)
+    assert np.array_equal(a_log.numpy(), g["actions"])
+    gen = torch.Generator().manual_seed(5)
+    z = torch.randn(1_000_000, 5, generator=gen) * 2.0
+    qq = om.draw_race_noise((1_000_000, 5), generator=gen)
+    a_ref, lp_ref = om.race_sample(z, qq)
+    a_new = torch.argmax(z - torch.log(qq), dim=-1)
+    agree = a_new == a_ref
+    assert agree.float().mean() > 0.99999
+    # the disagreements are races decided in the last bits: the runner-up is within 1e-5 relative of the winner
+    r = torch.softmax(z[~agree], -1) / qq[~agree]
+    top2 = r.topk(2, dim=-1).values
+    assert ((top2[:, 0] - top2[:, 1]) <= 1e-5 * top2[:, 0]).all()
+    lp_new = z.gather(-1, a_new[:, None])[:, 0] - torch.logsumexp(z, -1)
+    assert (lp_new[agree] - lp_ref[agree]).abs().max() < 2e-6
+
+
 def _episodes(g, tag, n):
     eps = []
     for i in range(n):
