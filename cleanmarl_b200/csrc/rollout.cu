@@ -122,7 +122,7 @@ struct RolloutArgs {
     float* reward;          // [T][B]
     double* ep_return;      // [B] or null
     int T, B, O;
-    int dbg;                // timeline experiments (CMARL_ROLLOUT_DBG): 1 = constant race noise, 2 = no buffer stores of the observation
+    int dbg;                // timeline experiments (CMARL_ROLLOUT_DBG, rollout_tc_kernel): 2 = no buffer stores of the observation
 };
 
 // Rollout kernel.  CTA = 32 envs = 12 warps; warp w = (agent n = w / 4, quarter qq = w % 4), lane = env.
@@ -498,18 +498,22 @@ __global__ void __launch_bounds__(RolloutThreads<GRU>::N) rollout_kernel(Rollout
 }
 
 // ------------------------------------------------------------------------------------------------
-// Rollout with layer 2 of the actor on the tensor cores (H = 64 MLP actor: the benchmark shape).
+// Rollout with layer 2 of the actor on the tensor cores (MLP actor, H = 32 -- the reference's default -- or 64).
 //   The 96 samples of a CTA's step (3 agents x 32 envs) are the rows of ONE M = 128 tile: layer 1 stays on the CUDA cores
-//   (K = 14: four warps per agent, 16 hidden units each, as in rollout_kernel) and writes relu(h1) split into tf32 hi / lo
-//   straight into the K-major A images in shared memory (row 32 n + e; one 16-byte chunk per four units: conflict-free
-//   STS.128); a dedicated issue warp multiplies by the hi / lo images of W2 (3xTF32: A_lo B_hi, A_hi B_lo, A_hi B_hi,
-//   24 tcgen05.mma of 128 x 64 x 8) into 64 TMEM columns.  The epilogue (b2, relu, output layer) is bound to the TMEM lane
-//   quadrants: warp w reads quadrant w % 4, so the rows of agent a are finished by the warps (n', qq = a) -- one of each
-//   agent's four -- in column groups of 24 / 24 / 16; the qq = 3 warps, which own no quadrant with rows in it, draw the
-//   race noise meanwhile.  Warp (0, a) samples agent a.
-//   The distance table of the team reward moves to the contact-force warps (off the critical path: they evaluate it for
-//   the state the previous step left, next to the pair forces, while the actor warps run the network).
-//   Measured on CTA 0 (cycles per step): FFMA layer 2 + output layer 3 480, here see profiles/rollout_timeline_r2.txt.
+//   (K = 14: four warps per agent, H / 4 hidden units each, FFMA2) and writes relu(h1), split into tf32 hi / lo, straight
+//   into the K-major A images in shared memory (row 32 n + e; one 16-byte chunk per four units: conflict-free STS.128); a
+//   dedicated issue warp multiplies by the hi / lo images of W2 -- pass 0: A_hi x [W2_hi ; W2_lo] (one N = 2H operand),
+//   pass 1: A_lo x W2_hi on the first H columns: 2 H / 8 tcgen05.mma of 128 x (2H | H) x 8 -- into 2H TMEM columns.
+//   The epilogue (b2, relu, output layer) is bound to the TMEM lane quadrants: warp w reads quadrant w % 4, so the rows of
+//   agent a are finished by the warps (n', qq = a) -- one of each agent's four -- in column groups of 12 / 12 / 8 (H = 64:
+//   24 / 24 / 16).  Warp (0, a) decides agent a's race in the log domain (argmax_a z_a - log q_a) and publishes the action;
+//   warp (1, a) repeats the decision and, behind the block barrier, evaluates the log-probability; warp (2, a) draws the
+//   first Philox block of the next step's noise under the MMAs; the warps (n, 3) = warps 12-14, which own no TMEM quadrant
+//   with rows in it, integrate agent n.  Warps 3, 7, 11 are the contact-force warps: pair forces, the distance table of the
+//   team reward for the state the previous step left, the second Philox block, and (warp 3) the reward itself -- on the
+//   issue warp's scheduler, off the critical path of a step.  Two 480-thread block barriers per step (behind the sampling,
+//   behind the integration), met by these 15 warps at the same two instructions; the issue warp meets them through the two
+//   mbarriers only.  DESIGN.md 3 has the measurements that shaped this; profiles/rollout_timeline_r2.txt the timelines.
 // ------------------------------------------------------------------------------------------------
 // log of the Exp(1) race noise of (t, agent n, env b), supplied by the caller or drawn with Philox: values 0..3 (first Philox
 // block) and value 4 (second block)
